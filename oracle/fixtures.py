@@ -1,0 +1,188 @@
+"""Seeded weights / inputs shared by the golden generator and the tests.  TEST INFRASTRUCTURE ONLY.
+
+``init_state_dict`` restates the reference ``NoiseModel.__init__`` bodies (registration order
+matters: it fixes both the ``state_dict`` key order and the order in which the default
+initialisers consume the global RNG), so that ``torch.manual_seed(0)`` followed by
+``init_state_dict(name)`` yields bit-identical weights to ``reference.NoiseModel()`` under the
+same seed -- which ``tests/test_oracle_vs_reference.py`` checks.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+WEIGHT_SEED = 0
+DATA_SEED = 1234
+BN_SEED = 4321
+
+
+def _cbr(cin, cout):
+    return [nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU()]
+
+
+def _unet_modules(in_ch, c0, c1, c2, c3, cb, time_dim, cond: str) -> nn.Module:
+    """diffusion.py:16-107 / conditional_diffusion.py:19-110 / conditional_diffusion_laion.py:235-302."""
+    m = nn.Module()
+    if cond == "sinusoidal+text":
+        m.time_mlp = nn.Sequential(nn.Linear(time_dim, time_dim), nn.SiLU(), nn.Linear(time_dim, time_dim))
+    else:
+        m.time_embedding = nn.Sequential(nn.Linear(1, time_dim), nn.SiLU(), nn.Linear(time_dim, time_dim))
+    if cond == "linear+class":
+        m.class_embedding = nn.Embedding(10, time_dim)
+    m.initial_conv = nn.Conv2d(in_ch, c0, 3, padding=1)
+    m.enc1 = nn.Sequential(*_cbr(c0, c1), *_cbr(c1, c1))
+    m.enc2 = nn.Sequential(*_cbr(c1, c2), *_cbr(c2, c2))
+    m.enc3 = nn.Sequential(*_cbr(c2, c3), *_cbr(c3, c3))
+    m.bottleneck = nn.Sequential(*_cbr(c3, cb))
+    m.dec3 = nn.Sequential(*_cbr(cb + c3, c2 if cond != "sinusoidal+text" else c3),
+                           *_cbr(c2 if cond != "sinusoidal+text" else c3,
+                                 c2 if cond != "sinusoidal+text" else c3))
+    if cond != "sinusoidal+text":
+        m.dec2 = nn.Sequential(*_cbr(c2 + c2, c1), *_cbr(c1, c1))
+        m.dec1 = nn.Sequential(*_cbr(c1 + c1, c0), *_cbr(c0, c0))
+        m.final_conv = nn.Conv2d(c0, in_ch, 3, padding=1)
+    else:
+        m.dec2 = nn.Sequential(*_cbr(c3 + c2, c2), *_cbr(c2, c2))
+        m.dec1 = nn.Sequential(*_cbr(c2 + c1, c1), *_cbr(c1, c1))
+        m.final_conv = nn.Conv2d(c1, in_ch, 3, padding=1)
+    m.time_proj1 = nn.Conv2d(time_dim, c1, 1)
+    m.time_proj2 = nn.Conv2d(time_dim, c2, 1)
+    m.time_proj3 = nn.Conv2d(time_dim, c3, 1)
+    return m
+
+
+class _Block(nn.Module):
+    """diffusion_transformer.py:16-29 (parameter containers only)."""
+
+    def __init__(self, dim, heads, ff, dropout):
+        super().__init__()
+        self.attention = nn.MultiheadAttention(dim, heads, dropout=dropout)
+        self.norm1 = nn.LayerNorm(dim)
+        self.ff = nn.Sequential(nn.Linear(dim, ff), nn.GELU(), nn.Linear(ff, dim), nn.Dropout(dropout))
+        self.norm2 = nn.LayerNorm(dim)
+        self.dropout = nn.Dropout(dropout)
+
+
+def _dit_modules(time_dim=256, num_classes=10, latent_dim=20, heads=4, layers=4, dropout=0.0):
+    """diffusion_transformer.py:48-79."""
+    m = nn.Module()
+    m.time_embedding = nn.Sequential(nn.Linear(1, time_dim), nn.SiLU(), nn.Linear(time_dim, time_dim))
+    m.class_embedding = nn.Embedding(num_classes, time_dim)
+    m.input_proj = nn.Linear(latent_dim, time_dim)
+    m.pos_encoding = nn.Parameter(torch.randn(1, 1, time_dim))
+    m.transformer_blocks = nn.ModuleList([_Block(time_dim, heads, time_dim * 4, dropout)
+                                          for _ in range(layers)])
+    m.final_layer = nn.Sequential(nn.LayerNorm(time_dim), nn.Linear(time_dim, latent_dim))
+    return m
+
+
+def make_modules(modname: str) -> nn.Module:
+    if modname == "diffusion":
+        return _unet_modules(1, 64, 128, 256, 512, 512, 256, "linear")
+    if modname == "conditional_diffusion":
+        return _unet_modules(1, 64, 128, 256, 512, 512, 256, "linear+class")
+    if modname == "conditional_diffusion_laion":
+        return _unet_modules(4, 32, 64, 128, 256, 256, 768, "sinusoidal+text")
+    if modname == "diffusion_transformer":
+        return _dit_modules()
+    raise KeyError(modname)
+
+
+def perturb_bn(model: nn.Module, seed: int = BN_SEED) -> nn.Module:
+    """Make BatchNorm non-trivial (default init is gamma=1, beta=0, mean=0, var=1)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in model.modules():
+            if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                n = mod.num_features
+                mod.weight.copy_(0.5 + torch.rand(n, generator=g))
+                mod.bias.copy_(0.1 * torch.randn(n, generator=g))
+                mod.running_mean.copy_(0.1 * torch.randn(n, generator=g))
+                mod.running_var.copy_(0.5 + torch.rand(n, generator=g))
+    return model
+
+
+def init_state_dict(modname: str, seed: int = WEIGHT_SEED, perturb: bool = True) -> Dict[str, torch.Tensor]:
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        m = make_modules(modname)
+    finally:
+        torch.set_rng_state(state)
+    if perturb:
+        perturb_bn(m)
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def build_reference_model(ref_module, modname: str, seed: int = WEIGHT_SEED):
+    """Reference NoiseModel() under the weight seed (drawn AFTER import: vae.py:33 reseeds)."""
+    state = torch.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        if modname == "diffusion_transformer":
+            model = ref_module.NoiseModel(dropout=0.0)
+        else:
+            model = ref_module.NoiseModel()
+    finally:
+        torch.set_rng_state(state)
+    return model
+
+
+def make_inputs(modname: str, B: int, seed: int = DATA_SEED) -> Dict[str, torch.Tensor]:
+    """Synthetic inputs of SURVEY.md section 8(d)."""
+    g = torch.Generator().manual_seed(seed)
+    out: Dict[str, torch.Tensor] = {}
+    if modname in ("diffusion", "conditional_diffusion"):
+        out["x0"] = torch.rand(B, 1, 28, 28, generator=g) * 2 - 1
+    elif modname == "conditional_diffusion_laion":
+        out["x0"] = 0.18215 * torch.randn(B, 4, 32, 32, generator=g)
+    else:
+        out["x0"] = torch.randn(B, 20, generator=g)
+    out["t"] = torch.randint(0, 1000, (B,), generator=g)
+    out["noise"] = torch.randn(out["x0"].shape, generator=g)
+    if modname in ("conditional_diffusion", "diffusion_transformer"):
+        out["cond"] = torch.randint(0, 10, (B,), generator=g)
+    elif modname == "conditional_diffusion_laion":
+        out["cond"] = torch.randn(B, 768, generator=g)
+    return out
+
+
+def checksum(x: torch.Tensor) -> torch.Tensor:
+    """(sum, L2 norm, a fixed pseudo-random projection) in fp64 -- cheap to store, hard to fake."""
+    xd = x.detach().double().flatten()
+    n = xd.numel()
+    idx = torch.arange(n, dtype=torch.float64)
+    proj = torch.cos(idx * 0.61803398875 + 0.25)
+    return torch.stack([xd.sum(), xd.norm(), (xd * proj).sum()])
+
+
+@contextlib.contextmanager
+def injected_randn(ref_module, tensors: List[torch.Tensor]):
+    """Make the reference module's ``torch.randn`` / ``torch.randn_like`` return the given
+    tensors in order (SURVEY.md section 8b RNG contract: q_sample draws once, diffusion.py:178;
+    sample() draws x_T then one z per step t>0, diffusion.py:257,268)."""
+    queue = list(tensors)
+    real = ref_module.torch
+
+    class Proxy:
+        def __getattr__(self, name):
+            return getattr(real, name)
+
+        @staticmethod
+        def randn(*a, **k):
+            return queue.pop(0).clone()
+
+        @staticmethod
+        def randn_like(x, **k):
+            t = queue.pop(0)
+            assert t.shape == x.shape, (t.shape, x.shape)
+            return t.clone()
+
+    ref_module.torch = Proxy()
+    try:
+        yield
+    finally:
+        ref_module.torch = real

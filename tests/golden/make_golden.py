@@ -1,0 +1,148 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures are committed; this script is committed beside them so they can be regenerated.
+Weights are the reference's own default init under ``torch.manual_seed(0)`` (drawn after the
+module import), with BatchNorm affine/running statistics perturbed by ``perturb_bn`` so that
+eval-mode BatchNorm is not the identity.  Inputs come from ``torch.Generator().manual_seed(1234)``.
+Only small tensors are stored (outputs, checksums); weights are re-created from the seed.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import reference_shim as shim          # noqa: E402
+from oracle.fixtures import (build_reference_model, make_inputs, perturb_bn, checksum,   # noqa: E402
+                             injected_randn)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def unet_case(modname: str, B: int = 4, n_samp: int = 2):
+    ref = shim.load(modname)
+    model = build_reference_model(ref, modname)
+    perturb_bn(model)
+    fp = ref.ForwardProcess()
+    inp = make_inputs(modname, B)
+    cond = inp.get("cond")
+    args = (lambda x, t: (x, t) if cond is None else (x, t, cond))
+    g = {"schedule": {"betas": fp.betas.clone(), "alphas": fp.alphas.clone(),
+                      "alphas_cumprod": fp.alphas_cumprod.clone()}}
+
+    # q_sample with the reference's own arithmetic, noise injected through torch.randn_like
+    with injected_randn(ref, [inp["noise"]]):
+        x_t, noise = fp.q_sample(torch.device("cpu"), inp["x0"], inp["t"])
+    assert torch.equal(noise, inp["noise"])
+    g["x_t"] = x_t.clone()
+
+    # eval-mode eps
+    model.eval()
+    with torch.no_grad():
+        g["eps_eval"] = model(*args(x_t, inp["t"])).clone()
+
+    # train step: loss, grads, BN buffers, one Adam step (diffusion.py:220-236)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    pred = model(*args(x_t, inp["t"]))
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    opt.zero_grad()
+    loss.backward()
+    g["eps_train"] = pred.detach().clone()
+    g["loss"] = loss.detach().clone()
+    g["grad_checksums"] = {k: checksum(p.grad) for k, p in model.named_parameters()}
+    # a few full gradients for tight checks (small ones)
+    g["grads_small"] = {k: p.grad.clone() for k, p in model.named_parameters()
+                        if p.numel() <= 1024}
+    opt.step()
+    g["param_checksums_after_step"] = {k: checksum(v) for k, v in model.state_dict().items()}
+
+    # reverse loop, n_samp samples, full T, injected x_T and z (diffusion.py:254-276)
+    gen = torch.Generator().manual_seed(77)
+    shape = (n_samp,) + tuple(inp["x0"].shape[1:])
+    x_T = torch.randn(shape, generator=gen)
+    T = fp.num_timesteps
+    zs = [torch.randn(shape, generator=gen) for _ in range(T - 1)]     # used at t = T-1 .. 1
+    kept = {}
+    scond = None if cond is None else cond[:n_samp]
+
+    model2 = build_reference_model(ref, modname)
+    perturb_bn(model2)
+    orig_forward = model2.forward
+
+    def spy(x, t, *rest):
+        out = orig_forward(x, t, *rest)
+        tt = int(t[0])
+        if tt % 100 == 0 or tt == T - 1:
+            kept[tt] = (x.clone(), out.clone())
+        return out
+    model2.forward = spy
+    with injected_randn(ref, [x_T] + zs):
+        if modname == "diffusion":
+            x0 = ref.sample(model2, fp, torch.device("cpu"), n_samples=n_samp)
+        elif modname == "conditional_diffusion":
+            x0 = ref.sample(model2, fp, torch.device("cpu"), n_samples=n_samp, y=scond)
+    g["sample"] = {"x_0": x0.clone(), "kept": kept, "seed": 77, "n": n_samp}
+    torch.save(g, os.path.join(OUT, f"{modname}.pt"))
+    print(modname, "loss", float(loss), "eps_eval norm", float(g["eps_eval"].norm()),
+          "x0 norm", float(x0.norm()))
+
+
+def laion_case(B: int = 2):
+    modname = "conditional_diffusion_laion"
+    ref = shim.load(modname)
+    model = build_reference_model(ref, modname)
+    perturb_bn(model)
+    fp = ref.ForwardProcess()
+    inp = make_inputs(modname, B)
+    g = {}
+    with injected_randn(ref, [inp["noise"]]):
+        x_t, noise = fp.q_sample(torch.device("cpu"), inp["x0"], inp["t"])
+    g["x_t"] = x_t.clone()
+    model.eval()
+    with torch.no_grad():
+        g["eps_eval"] = model(x_t, inp["t"], inp["cond"]).clone()
+    model.train()
+    pred = model(x_t, inp["t"], inp["cond"])
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    loss.backward()
+    g["eps_train"] = pred.detach().clone()
+    g["loss"] = loss.detach().clone()
+    g["grad_checksums"] = {k: checksum(p.grad) for k, p in model.named_parameters()}
+    g["sin_emb"] = ref.get_timestep_embedding(inp["t"], 768).clone()
+    torch.save(g, os.path.join(OUT, f"{modname}.pt"))
+    print(modname, "loss", float(loss))
+
+
+def dit_case(B: int = 8):
+    modname = "diffusion_transformer"
+    ref = shim.load(modname)
+    model = build_reference_model(ref, modname)
+    fp = ref.ForwardProcess()
+    inp = make_inputs(modname, B)
+    g = {}
+    with injected_randn(ref, [inp["noise"]]):
+        x_t, noise = fp.q_sample(torch.device("cpu"), inp["x0"], inp["t"])
+    g["x_t"] = x_t.clone()
+    model.eval()
+    with torch.no_grad():
+        g["eps_eval"] = model(x_t, inp["t"], inp["cond"]).clone()
+    model.train()      # dropout=0.0 model: train == eval numerically
+    pred = model(x_t, inp["t"], inp["cond"])
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    loss.backward()
+    g["loss"] = loss.detach().clone()
+    g["grad_checksums"] = {k: checksum(p.grad) for k, p in model.named_parameters()}
+    torch.save(g, os.path.join(OUT, f"{modname}.pt"))
+    print(modname, "loss", float(loss))
+
+
+if __name__ == "__main__":
+    assert shim.available(), "reference not mounted"
+    torch.set_num_threads(os.cpu_count() or 1)
+    unet_case("diffusion")
+    unet_case("conditional_diffusion")
+    laion_case()
+    dit_case()
