@@ -1,0 +1,117 @@
+"""ctypes binding of libtinydiff.so (the C ABI declared in include/tinydiff.h).
+
+There is no CPU fallback: if the shared library is missing, or the device is not an sm_100-class
+GPU, every compute call raises.  PyTorch is used only for device memory, streams and
+torch.distributed; all arithmetic on the hot path happens inside libtinydiff.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtinydiff.so")
+
+TD_F32, TD_BF16 = 0, 1
+CONV_SIMT, CONV_TC, CONV_DIRECT = 0, 1, 2
+
+_P = C.c_void_p
+
+
+class EmbedArgs(C.Structure):
+    _fields_ = [("batch", C.c_int), ("dim", C.c_int), ("in_mode", C.c_int), ("proj_out", C.c_int),
+                ("t", _P), ("t_dev", _P), ("w0", _P), ("b0", _P), ("w2", _P), ("b2", _P),
+                ("y", _P), ("class_table", _P), ("text", _P), ("proj_w", _P), ("proj_b", _P),
+                ("emb_out", _P), ("h_out", _P), ("proj_out_ptr", _P)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
+                ("cin", C.c_int), ("cout", C.c_int), ("x_dtype", C.c_int), ("y_dtype", C.c_int),
+                ("x", _P), ("ldx", C.c_int), ("x_coff", C.c_int),
+                ("y", _P), ("ldy", C.c_int), ("y_coff", C.c_int),
+                ("w", _P), ("scale", _P), ("shift", _P), ("relu", C.c_int),
+                ("stats", _P), ("x_nchw", C.c_int), ("y_nchw", C.c_int)]
+
+
+_SIGS = {
+    "td_version": (C.c_int, []),
+    "td_last_error_string": (C.c_char_p, []),
+    "td_device_check": (C.c_int, [C.c_int]),
+    "td_qsample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "td_mse_num_partials": (C.c_int64, [C.c_int64]),
+    "td_mse_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_float, _P]),
+    "td_psample_step": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, _P]),
+    "td_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, _P]),
+    "td_counter_add": (C.c_int, [_P, C.c_int32, _P]),
+    "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, C.c_float,
+                                C.c_float, C.c_float, _P, _P, _P]),
+    "td_embed_head_fwd": (C.c_int, [C.POINTER(EmbedArgs), _P]),
+    "td_conv3x3_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), C.c_int]),
+    "td_conv3x3_run": (C.c_int, [_P, _P]),
+    "td_conv3x3_plan_destroy": (None, [_P]),
+    "td_conv3x3_flops": (C.c_double, [_P]),
+    "td_maxpool2_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_upcat_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int, _P]),
+    "td_resize_bilinear_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_cast_f32_to_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "td_pack_conv_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libtinydiff.so (no CUDA call is made by loading)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"libtinydiff.so not found at {LIB_PATH}; build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (or `make -C tiny-diffusion_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().td_last_error_string().decode("utf-8", "replace")
+        raise RuntimeError(f"libtinydiff {what} failed (status {status}): {msg}")
+
+
+def require_device(device) -> torch.device:
+    """Raise unless `device` is a CUDA device libtinydiff can run on (no CPU fallback)."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"tinydiff runs on sm_100a GPUs only (got device '{device}'); there is no CPU path")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    check(load().td_device_check(idx), "td_device_check")
+    return torch.device("cuda", idx)
+
+
+def ptr(t) -> int:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return TD_F32
+    if dt == torch.bfloat16:
+        return TD_BF16
+    raise ValueError(f"unsupported dtype {dt}")

@@ -1,0 +1,59 @@
+// Library-level entry points: version, error reporting, architecture gate.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace td {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int require_sm100() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached_status = TD_ERR_ARCH;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("no CUDA device: %s (libtinydiff has no CPU fallback)", cudaGetErrorString(e));
+        return TD_ERR_ARCH;
+    }
+    if (dev == cached_dev) {
+        if (cached_status != TD_OK) set_error("device %d is not sm_100-class (libtinydiff is sm_100a only)", dev);
+        return cached_status;
+    }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cached_dev = dev;
+    cached_status = (major == 10) ? TD_OK : TD_ERR_ARCH;
+    if (cached_status != TD_OK)
+        set_error("device %d is sm_%d%d; libtinydiff is built for sm_100a only and has no fallback", dev, major, minor);
+    return cached_status;
+}
+
+}  // namespace td
+
+extern "C" int td_version(void) { return 100; }
+extern "C" const char* td_last_error_string(void) { return td::g_err; }
+
+extern "C" int td_device_check(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) {
+        td::set_error("device %d not available (%s)", device, e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+        return TD_ERR_ARCH;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+        td::set_error("device %d has compute capability major %d; need 10 (B200)", device, major);
+        return TD_ERR_ARCH;
+    }
+    return TD_OK;
+}

@@ -1,0 +1,345 @@
+// fp32-accumulate CUDA-core convolutions:
+//   * conv3x3_simt_kernel  : generic implicit GEMM, fp32 FFMA.  This is the fp32 parity path
+//                            (north_star: eps within 1e-4 of the reference in fp32) and covers any
+//                            channel count.
+//   * conv3x3_first_kernel : tiny-Cin direct conv (network input, 1 or 4 channels) - bandwidth bound.
+//   * conv3x3_last_kernel  : tiny-Cout direct conv (network output) - bandwidth bound.
+// The tensor-core engine lives in conv_tc.cu.
+#include "conv_plan.h"
+
+namespace td {
+
+// generic element loads with optional NCHW addressing (network boundary tensors only)
+template <typename T>
+__device__ inline float load_in(const T* __restrict__ x, const td_conv3x3_desc& d, int b, int h, int w, int c) {
+    if (d.x_nchw) return to_f32(x[(((int64_t)b * d.cin + c) * d.height + h) * d.width + w]);
+    return to_f32(x[(((int64_t)b * d.height + h) * d.width + w) * d.ldx + d.x_coff + c]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic implicit GEMM: M = B*H*W pixels, N = Cout, K = 9*Cin (k = tap*Cin + c).
+// 64x64 tile, BK = 16, 256 threads, 4x4 register tile per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int SM_BM = 64, SM_BN = 64, SM_BK = 16, SM_THREADS = 256;
+
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(SM_THREADS)
+conv3x3_simt_kernel(const td_conv3x3_desc d) {
+    __shared__ float As[SM_BK][SM_BM + 4];
+    __shared__ float Bs[SM_BK][SM_BN + 4];
+    const Tin* __restrict__ x = reinterpret_cast<const Tin*>(d.x);
+    const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);
+    const int64_t M = (int64_t)d.batch * d.height * d.width;
+    const int K = 9 * d.cin;
+    const int64_t m0 = (int64_t)blockIdx.x * SM_BM;
+    const int n0 = blockIdx.y * SM_BN;
+    const int tid = threadIdx.x;
+
+    // loader mapping: row = tid / 4, 4 consecutive k per thread
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    const int64_t pm = m0 + lrow;
+    int pb = 0, ph = 0, pw = 0;
+    const bool pvalid = pm < M;
+    if (pvalid) {
+        pw = (int)(pm % d.width);
+        int64_t r = pm / d.width;
+        ph = (int)(r % d.height);
+        pb = (int)(r / d.height);
+    }
+    const int wn = n0 + lrow;   // weight row (cout) this thread loads
+    const bool wvalid = wn < d.cout;
+
+    const int ty = tid >> 4, tx = tid & 15;   // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += SM_BK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + lk + q;
+            float av = 0.f, bv = 0.f;
+            if (k < K) {
+                const int tap = k / d.cin, c = k - tap * d.cin;
+                const int hh = ph + tap / 3 - 1, ww = pw + tap % 3 - 1;
+                if (pvalid && hh >= 0 && hh < d.height && ww >= 0 && ww < d.width) av = load_in<Tin>(x, d, pb, hh, ww, c);
+                if (wvalid) bv = wt[(int64_t)wn * K + k];
+            }
+            As[lk + q][lrow] = av;
+            Bs[lk + q][lrow] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < SM_BK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    Tout* __restrict__ y = reinterpret_cast<Tout*>(d.y);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const int w_ = (int)(m % d.width);
+        const int64_t r = m / d.width;
+        const int h_ = (int)(r % d.height);
+        const int b_ = (int)(r / d.height);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= d.cout) continue;
+            float v = acc[i][j];
+            if (d.scale) v *= d.scale[n];
+            if (d.shift) v += d.shift[n];
+            if (d.relu) v = fmaxf(v, 0.f);
+            if (d.y_nchw) y[(((int64_t)b_ * d.cout + n) * d.height + h_) * d.width + w_] = from_f32<Tout>(v);
+            else y[m * d.ldy + d.y_coff + n] = from_f32<Tout>(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny-Cin direct conv: one thread produces 8 consecutive output channels of one pixel.
+// Weights (cout*9*cin fp32, OHWI) are staged in shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(256)
+conv3x3_first_kernel(const td_conv3x3_desc d) {
+    extern __shared__ float wsm[];          // [cout][9*cin]
+    const int K = 9 * d.cin;
+    for (int i = threadIdx.x; i < d.cout * K; i += blockDim.x) wsm[i] = reinterpret_cast<const float*>(d.w)[i];
+    __syncthreads();
+    const Tin* __restrict__ x = reinterpret_cast<const Tin*>(d.x);
+    Tout* __restrict__ y = reinterpret_cast<Tout*>(d.y);
+    const int groups = d.cout / 8;
+    const int64_t total = (int64_t)d.batch * d.height * d.width * groups;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const int64_t m = i / groups;
+        const int w_ = (int)(m % d.width);
+        const int64_t r = m / d.width;
+        const int h_ = (int)(r % d.height);
+        const int b_ = (int)(r / d.height);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h_ + tap / 3 - 1, ww = w_ + tap % 3 - 1;
+            if (hh < 0 || hh >= d.height || ww < 0 || ww >= d.width) continue;
+            for (int c = 0; c < d.cin; ++c) {
+                const float xv = load_in<Tin>(x, d, b_, hh, ww, c);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wsm[(g * 8 + j) * K + tap * d.cin + c], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = g * 8 + j;
+            float v = acc[j];
+            if (d.scale) v *= d.scale[n];
+            if (d.shift) v += d.shift[n];
+            if (d.relu) v = fmaxf(v, 0.f);
+            acc[j] = v;
+        }
+        Tout* dst = y + m * d.ldy + d.y_coff + g * 8;
+        if constexpr (sizeof(Tout) == 2) {
+            Vec<__nv_bfloat16>::pack(acc).store(reinterpret_cast<__nv_bfloat16*>(dst));
+        } else {
+            Vec<float>::pack(acc).store(reinterpret_cast<float*>(dst));
+            Vec<float>::pack(acc + 4).store(reinterpret_cast<float*>(dst) + 4);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny-Cout direct conv: L = cin / V lanes cooperate on one pixel (each lane owns one 16-byte
+// channel vector per tap, so a pixel row is one coalesced read), shuffle-reduce, lane 0 stores.
+// ---------------------------------------------------------------------------------------------
+template <typename Tin, int COUT>
+__global__ void __launch_bounds__(256)
+conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
+    extern __shared__ float wsm[];          // [COUT][9*cin]
+    constexpr int V = Vec<Tin>::N;
+    const int K = 9 * d.cin;
+    for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) wsm[i] = reinterpret_cast<const float*>(d.w)[i];
+    __syncthreads();
+    const Tin* __restrict__ x = reinterpret_cast<const Tin*>(d.x);
+    float* __restrict__ y = reinterpret_cast<float*>(d.y);
+    const int L = lanes_per_pixel;
+    const int64_t M = (int64_t)d.batch * d.height * d.width;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    // iterate so that whole warps stay converged for the shuffles
+    const int64_t iters = ceil_div(M * L, gthreads);
+    for (int64_t it = 0; it < iters; ++it) {
+        const int64_t i = it * gthreads + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const int64_t m = i / L;
+        const int lane = (int)(i % L);
+        const bool valid = m < M;
+        float acc[COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+        if (valid) {
+            const int w_ = (int)(m % d.width);
+            const int64_t r = m / d.width;
+            const int h_ = (int)(r % d.height);
+            const int b_ = (int)(r / d.height);
+            for (int tap = 0; tap < 9; ++tap) {
+                const int hh = h_ + tap / 3 - 1, ww = w_ + tap % 3 - 1;
+                if (hh < 0 || hh >= d.height || ww < 0 || ww >= d.width) continue;
+                const Tin* px = x + (((int64_t)b_ * d.height + hh) * d.width + ww) * d.ldx + d.x_coff;
+                for (int cv = lane; cv * V < d.cin; cv += L) {
+                    float f[V];
+                    Vec<Tin>::load(px + cv * V).unpack(f);
+#pragma unroll
+                    for (int j = 0; j < COUT; ++j) {
+                        const float* wr = wsm + j * K + tap * d.cin + cv * V;
+#pragma unroll
+                        for (int k = 0; k < V; ++k) acc[j] = fmaf(f[k], wr[k], acc[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < COUT; ++j)
+            for (int o = L >> 1; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        if (valid && lane == 0) {
+            const int w_ = (int)(m % d.width);
+            const int64_t r = m / d.width;
+            const int h_ = (int)(r % d.height);
+            const int b_ = (int)(r / d.height);
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) {
+                float v = acc[j];
+                if (d.scale) v *= d.scale[j];
+                if (d.shift) v += d.shift[j];
+                if (d.relu) v = fmaxf(v, 0.f);
+                if (d.y_nchw) y[(((int64_t)b_ * COUT + j) * d.height + h_) * d.width + w_] = v;
+                else y[m * d.ldy + d.y_coff + j] = v;
+            }
+        }
+    }
+}
+
+static int run_simt(const td_conv_plan* p, cudaStream_t s) {
+    const td_conv3x3_desc& d = p->d;
+    const int64_t M = (int64_t)d.batch * d.height * d.width;
+    dim3 grid((unsigned)ceil_div(M, SM_BM), (unsigned)ceil_div(d.cout, SM_BN));
+    if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) conv3x3_simt_kernel<float, float><<<grid, SM_THREADS, 0, s>>>(d);
+    else if (d.x_dtype == TD_BF16 && d.y_dtype == TD_BF16) conv3x3_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, SM_THREADS, 0, s>>>(d);
+    else if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) conv3x3_simt_kernel<float, __nv_bfloat16><<<grid, SM_THREADS, 0, s>>>(d);
+    else conv3x3_simt_kernel<__nv_bfloat16, float><<<grid, SM_THREADS, 0, s>>>(d);
+    return launch_status("conv3x3_simt");
+}
+
+static int run_direct(const td_conv_plan* p, cudaStream_t s) {
+    const td_conv3x3_desc& d = p->d;
+    const int64_t M = (int64_t)d.batch * d.height * d.width;
+    if (d.cin <= 8) {
+        const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
+        const int64_t items = M * (d.cout / 8);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 256), kNumSMs * 8));
+        if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) conv3x3_first_kernel<float, __nv_bfloat16><<<grid, 256, smem, s>>>(d);
+        else if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) conv3x3_first_kernel<float, float><<<grid, 256, smem, s>>>(d);
+        else { set_error("direct first conv: unsupported dtype combination"); return TD_ERR_UNSUPPORTED; }
+        return launch_status("conv3x3_first");
+    }
+    // tiny cout
+    const int V = d.x_dtype == TD_BF16 ? 8 : 4;
+    int L = d.cin / V;
+    if (L > 32) L = 32;
+    const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M * L, 256), kNumSMs * 8));
+#define TD_LAST(T, CO) conv3x3_last_kernel<T, CO><<<grid, 256, smem, s>>>(d, L)
+    if (d.x_dtype == TD_BF16) {
+        if (d.cout == 1) TD_LAST(__nv_bfloat16, 1);
+        else if (d.cout == 4) TD_LAST(__nv_bfloat16, 4);
+        else { set_error("direct last conv: cout must be 1 or 4"); return TD_ERR_UNSUPPORTED; }
+    } else {
+        if (d.cout == 1) TD_LAST(float, 1);
+        else if (d.cout == 4) TD_LAST(float, 4);
+        else { set_error("direct last conv: cout must be 1 or 4"); return TD_ERR_UNSUPPORTED; }
+    }
+#undef TD_LAST
+    return launch_status("conv3x3_last");
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc* desc, int engine) {
+    TD_CHECK_ARG(plan && desc, "td_conv3x3_plan_create: null pointer");
+    const td_conv3x3_desc& d = *desc;
+    TD_CHECK_ARG(d.batch > 0 && d.height > 0 && d.width > 0 && d.cin > 0 && d.cout > 0, "conv plan: bad sizes");
+    TD_CHECK_ARG(d.x && d.y && d.w, "conv plan: null tensor pointer");
+    TD_CHECK_ARG((d.x_dtype == TD_F32 || d.x_dtype == TD_BF16) && (d.y_dtype == TD_F32 || d.y_dtype == TD_BF16),
+                 "conv plan: bad dtype");
+    TD_CHECK_ARG(d.x_nchw || (d.ldx >= d.x_coff + d.cin), "conv plan: ldx too small");
+    TD_CHECK_ARG(d.y_nchw || (d.ldy >= d.y_coff + d.cout), "conv plan: ldy too small");
+    td_conv_plan* p = new td_conv_plan();
+    memset(p, 0, sizeof(*p));
+    p->d = d;
+    p->engine = engine;
+    int st = TD_OK;
+    if (engine == TD_CONV_TC) {
+        st = tc_plan_init(p);
+    } else if (engine == TD_CONV_DIRECT) {
+        const bool first = d.cin <= 8 && d.cout % 8 == 0 && d.x_dtype == TD_F32 && !d.y_nchw;
+        const int V = d.x_dtype == TD_BF16 ? 8 : 4;
+        const int L = d.cin / V;
+        const bool last = d.cin > 8 && (d.cout == 1 || d.cout == 4) && d.y_dtype == TD_F32 && !d.x_nchw &&
+                          d.cin % V == 0 && (L & (L - 1)) == 0 && d.ldx % V == 0 && d.x_coff % V == 0;
+        if (!first && !last) {
+            set_error("conv plan: shape not supported by the direct engine (cin=%d cout=%d)", d.cin, d.cout);
+            st = TD_ERR_UNSUPPORTED;
+        }
+        if (first && (d.ldy % 8 != 0 || d.y_coff % 8 != 0)) {
+            set_error("conv plan: direct first conv needs ldy, y_coff multiples of 8");
+            st = TD_ERR_UNSUPPORTED;
+        }
+        if ((size_t)d.cout * 9 * d.cin * sizeof(float) > 48 * 1024) {
+            set_error("conv plan: direct engine weights exceed 48 KB shared memory");
+            st = TD_ERR_UNSUPPORTED;
+        }
+    } else if (engine == TD_CONV_SIMT) {
+        if (d.stats) { set_error("conv plan: SIMT engine does not emit statistics"); st = TD_ERR_UNSUPPORTED; }
+    } else {
+        set_error("conv plan: unknown engine %d", engine);
+        st = TD_ERR_ARG;
+    }
+    if (st != TD_OK) {
+        delete p;
+        return st;
+    }
+    *plan = p;
+    return TD_OK;
+}
+
+extern "C" int td_conv3x3_run(const td_conv_plan* plan, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(plan, "td_conv3x3_run: null plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (plan->engine) {
+        case TD_CONV_TC: return tc_plan_run(plan, s);
+        case TD_CONV_DIRECT: return run_direct(plan, s);
+        default: return run_simt(plan, s);
+    }
+}
+
+extern "C" void td_conv3x3_plan_destroy(td_conv_plan* plan) { delete plan; }
+
+extern "C" double td_conv3x3_flops(const td_conv_plan* plan) {
+    if (!plan) return 0.0;
+    const td_conv3x3_desc& d = plan->d;
+    return 2.0 * d.batch * d.height * d.width * (double)d.cout * 9.0 * d.cin;
+}

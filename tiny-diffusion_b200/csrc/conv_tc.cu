@@ -1,0 +1,296 @@
+// 3x3 convolution as an implicit GEMM on the 5th-generation tensor cores (sm_100a).
+//
+//   D[pixel, cout] = sum_{tap, c} X[pixel + tap_offset, c] * W[cout, tap, c]
+//
+//   * M tile  = 128 TMEM lanes = one spatial box (bw x bh x bn output pixels, <= 128) of the NHWC
+//               activation tensor; N tile = BLOCK_N output channels; K loop = 9 taps x Cin/64.
+//   * A operand: one 4-D TMA box load per (tap, 64-channel chunk) at coordinates shifted by the
+//               tap offset; the zero padding of the convolution is TMA's out-of-bounds zero fill.
+//               The box lands as 128-byte rows with SWIZZLE_128B = the canonical K-major UMMA layout.
+//   * B operand: 2-D TMA box (64 k x BLOCK_N couts) of the OHWI bf16 weight matrix, same layout.
+//   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BLOCK_N, K=16) issued by one elected thread,
+//               fp32 accumulator in TMEM; smem slots recycled through tcgen05.commit -> mbarrier.
+//   * Epilogue: 4 warps read their TMEM lane quadrant with tcgen05.ld, apply the folded
+//               BatchNorm/bias affine (+ReLU) in fp32 and store NHWC bf16/fp32 rows.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (warp 2 also owns TMEM alloc).
+#include <mutex>
+
+#include "conv_plan.h"
+#include "sm100.cuh"
+
+namespace td {
+
+using namespace sm100;
+
+struct TcParams {
+    int B, H, W, cin, x_coff;
+    int cout, ldy, y_coff, y_dtype;
+    void* y;
+    const float* scale;
+    const float* shift;
+    int relu;
+    int bw, bh, bn, tiles_w, tiles_h;
+    int stages;
+    uint32_t a_bytes;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_STAGE = 128 * 128;   // 128 rows x 128 bytes (64 bf16)
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int B_STAGE = BLOCK_N * 128;
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);     // SWIZZLE_128B needs 1024-byte alignment
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * TC_A_STAGE;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * B_STAGE);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* tmem_full_bar = empty_bar + p.stages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int mt = blockIdx.x;
+    const int tw = mt % p.tiles_w;
+    const int th = (mt / p.tiles_w) % p.tiles_h;
+    const int tn = mt / (p.tiles_w * p.tiles_h);
+    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+    const int nt = blockIdx.y;
+    const int kchunks = p.cin >> 6;
+    const int iters = 9 * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<BLOCK_N>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[s], p.a_bytes + (uint32_t)B_STAGE);
+                const int tap = it / kchunks, cc = it - tap * kchunks;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                tma_load_4d(smem_a + (size_t)s * TC_A_STAGE, &tmap_x, &full_bar[s], p.x_coff + cc * 64, w0 + dx, h0 + dy, n0);
+                tma_load_2d(smem_b + (size_t)s * B_STAGE, &tmap_w, &full_bar[s], tap * p.cin + cc * 64, nt * BLOCK_N);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem_a + (size_t)s * TC_A_STAGE);
+                const uint32_t b_addr = smem_u32(smem_b + (size_t)s * B_STAGE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {       // 4 x (K = 16 bf16 = 32 bytes) per 128-byte swizzle row
+                    const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                    const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs retire
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ---- epilogue: TMEM -> registers -> global ------------------------------------------------
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int rows_valid = p.bw * p.bh * p.bn;
+        const int rw = row % p.bw;
+        const int rh = (row / p.bw) % p.bh;
+        const int rn = row / (p.bw * p.bh);
+        const int w_ = w0 + rw, h_ = h0 + rh, n_ = n0 + rn;
+        const bool valid = row < rows_valid && w_ < p.W && h_ < p.H && n_ < p.B;
+        const int64_t pix = ((int64_t)n_ * p.H + h_) * p.W + w_;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+            const int cbase = nt * BLOCK_N + c0;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float f = __uint_as_float(r[j]);
+                if (p.scale) f *= __ldg(p.scale + cbase + j);
+                if (p.shift) f += __ldg(p.shift + cbase + j);
+                if (p.relu) f = fmaxf(f, 0.f);
+                v[j] = f;
+            }
+            if (valid) {
+                if (p.y_dtype == TD_BF16) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) Vec<__nv_bfloat16>::pack(v + j).store(dst + j);
+                } else {
+                    float* dst = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) Vec<float>::pack(v + j).store(dst + j);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<BLOCK_N>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    });
+    return fn;
+}
+
+static int pick_block_n(int cout) {
+    if (const char* e = getenv("TD_TC_BLOCK_N")) {
+        int v = atoi(e);
+        if ((v == 64 || v == 128 || v == 256) && cout % v == 0) return v;
+    }
+    if (cout % 256 == 0) return 256;
+    if (cout % 128 == 0) return 128;
+    return 64;
+}
+
+int tc_plan_init(td_conv_plan* p) {
+    const td_conv3x3_desc& d = p->d;
+    if (d.x_dtype != TD_BF16) { set_error("tc conv: input must be bf16"); return TD_ERR_UNSUPPORTED; }
+    if (d.cin % 64 != 0 || d.cout % 64 != 0) {
+        set_error("tc conv: cin (%d) and cout (%d) must be multiples of 64", d.cin, d.cout);
+        return TD_ERR_UNSUPPORTED;
+    }
+    if (d.ldx % 8 != 0 || d.x_coff % 8 != 0 || d.ldy % 8 != 0 || d.y_coff % 8 != 0) {
+        set_error("tc conv: channel strides/offsets must be multiples of 8");
+        return TD_ERR_UNSUPPORTED;
+    }
+    if (d.x_nchw || d.y_nchw || d.stats) { set_error("tc conv: NCHW / stats not supported"); return TD_ERR_UNSUPPORTED; }
+    if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15) || ((uintptr_t)d.y & 15)) {
+        set_error("tc conv: tensors must be 16-byte aligned");
+        return TD_ERR_ARG;
+    }
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TD_ERR_DRIVER; }
+
+    // spatial box: maximise useful rows per 128-row MMA tile
+    const int bw = d.width <= 32 ? d.width : 32;
+    const int tiles_w = (int)ceil_div(d.width, bw);
+    double best = -1.0;
+    int bbh = 1, bbn = 1;
+    for (int bh = 1; bh <= d.height && bw * bh <= 128; ++bh) {
+        int bn = 128 / (bw * bh);
+        if (bn > d.batch) bn = d.batch;
+        if (bn > 256) bn = 256;
+        if (bn < 1) continue;
+        const double tiles = (double)tiles_w * ceil_div(d.height, bh) * ceil_div(d.batch, bn);
+        const double eff = (double)d.batch * d.height * d.width / (tiles * 128.0);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && bh > bbh)) { best = eff; bbh = bh; bbn = bn; }
+    }
+    p->bw = bw; p->bh = bbh; p->bn = bbn;
+    p->tiles_w = tiles_w;
+    p->tiles_h = (int)ceil_div(d.height, bbh);
+    p->tiles_n = (int)ceil_div(d.batch, bbn);
+    p->block_n = pick_block_n(d.cout);
+    p->n_tiles = d.cout / p->block_n;
+    const int stage_bytes = TC_A_STAGE + p->block_n * 128;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (const char* e = getenv("TD_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
+    p->stages = stages;
+    p->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+
+    {   // activations: (C, W, H, N)
+        cuuint64_t gdim[4] = {(cuuint64_t)d.ldx, (cuuint64_t)d.width, (cuuint64_t)d.height, (cuuint64_t)d.batch};
+        cuuint64_t gstr[3] = {(cuuint64_t)d.ldx * 2, (cuuint64_t)d.width * d.ldx * 2,
+                              (cuuint64_t)d.height * d.width * d.ldx * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)p->bw, (cuuint32_t)p->bh, (cuuint32_t)p->bn};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p->tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return TD_ERR_DRIVER; }
+    }
+    {   // weights: (K = 9*Cin, Cout)
+        cuuint64_t gdim[2] = {(cuuint64_t)9 * d.cin, (cuuint64_t)d.cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)9 * d.cin * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)p->block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&p->tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return TD_ERR_DRIVER; }
+    }
+    return TD_OK;
+}
+
+template <int BLOCK_N>
+static int launch_tc(const td_conv_plan* p, const TcParams& prm, cudaStream_t s) {
+    static int configured_smem = 0;
+    if (p->smem_bytes > configured_smem) {
+        TD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        configured_smem = p->smem_bytes;
+    }
+    dim3 grid((unsigned)(p->tiles_w * p->tiles_h * p->tiles_n), (unsigned)p->n_tiles);
+    conv3x3_tc_kernel<BLOCK_N><<<grid, TC_THREADS, p->smem_bytes, s>>>(p->tmap_x, p->tmap_w, prm);
+    return launch_status("conv3x3_tc");
+}
+
+int tc_plan_run(const td_conv_plan* p, cudaStream_t s) {
+    const td_conv3x3_desc& d = p->d;
+    TcParams prm;
+    prm.B = d.batch; prm.H = d.height; prm.W = d.width; prm.cin = d.cin; prm.x_coff = d.x_coff;
+    prm.cout = d.cout; prm.ldy = d.ldy; prm.y_coff = d.y_coff; prm.y_dtype = d.y_dtype;
+    prm.y = d.y; prm.scale = d.scale; prm.shift = d.shift; prm.relu = d.relu;
+    prm.bw = p->bw; prm.bh = p->bh; prm.bn = p->bn; prm.tiles_w = p->tiles_w; prm.tiles_h = p->tiles_h;
+    prm.stages = p->stages;
+    prm.a_bytes = (uint32_t)(64 * p->bw * p->bh * p->bn * 2);
+    switch (p->block_n) {
+        case 64: return launch_tc<64>(p, prm, s);
+        case 128: return launch_tc<128>(p, prm, s);
+        case 256: return launch_tc<256>(p, prm, s);
+    }
+    set_error("tc conv: bad block_n %d", p->block_n);
+    return TD_ERR_ARG;
+}
+
+}  // namespace td

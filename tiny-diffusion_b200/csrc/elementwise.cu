@@ -1,0 +1,331 @@
+// Elementwise DDPM kernels: q_sample, MSE loss + gradient, p_sample step, fused Adam.
+// All are HBM-bound streaming kernels: 128-bit accesses, grid sized from the element count,
+// no shared-memory staging (no reuse to exploit).
+#include "common.cuh"
+
+namespace td {
+
+constexpr int kEwThreads = 256;
+
+// x_t = sqrt(abar[t]) * x0 + sqrt(1 - abar[t]) * noise          (diffusion.py:180-190)
+// __fmul_rn/__fadd_rn keep the reference's separate roundings (no FMA contraction) so the
+// result is bit-identical to the PyTorch expression.
+__global__ void __launch_bounds__(kEwThreads)
+qsample_kernel(const float* __restrict__ x0, float* __restrict__ noise, const int64_t* __restrict__ t,
+               const float* __restrict__ abar, float* __restrict__ x_t, int64_t per_sample4,
+               int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+    const int64_t b = blockIdx.y;
+    int tt = (int)t[b];
+    tt = min(max(tt, 0), num_timesteps - 1);
+    const float ab = abar[tt];
+    const float ca = sqrtf(ab);
+    const float cb = sqrtf(__fsub_rn(1.0f, ab));
+    const int64_t base = b * per_sample4;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_sample4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float4 x = reinterpret_cast<const float4*>(x0)[base + i];
+        float4 n;
+        if (seed_ptr) {
+            Philox rng(seed_ptr[0]);
+            float z[4];
+            rng.normal4((uint64_t)(base + i), seed_ptr[1], z);
+            n = make_float4(z[0], z[1], z[2], z[3]);
+            reinterpret_cast<float4*>(noise)[base + i] = n;
+        } else {
+            n = reinterpret_cast<const float4*>(noise)[base + i];
+        }
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn(ca, x.x), __fmul_rn(cb, n.x));
+        o.y = __fadd_rn(__fmul_rn(ca, x.y), __fmul_rn(cb, n.y));
+        o.z = __fadd_rn(__fmul_rn(ca, x.z), __fmul_rn(cb, n.z));
+        o.w = __fadd_rn(__fmul_rn(ca, x.w), __fmul_rn(cb, n.w));
+        reinterpret_cast<float4*>(x_t)[base + i] = o;
+    }
+}
+
+// scalar tail-safe variant (per_sample not a multiple of 4, e.g. the 20-d latents)
+__global__ void __launch_bounds__(kEwThreads)
+qsample_scalar_kernel(const float* __restrict__ x0, float* __restrict__ noise, const int64_t* __restrict__ t,
+                      const float* __restrict__ abar, float* __restrict__ x_t, int64_t batch,
+                      int64_t per_sample, int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+    const int64_t total = batch * per_sample;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / per_sample;
+        int tt = (int)t[b];
+        tt = min(max(tt, 0), num_timesteps - 1);
+        const float ab = abar[tt];
+        float n;
+        if (seed_ptr) {
+            Philox rng(seed_ptr[0]);
+            float z[4];
+            rng.normal4((uint64_t)(i >> 2), seed_ptr[1], z);
+            n = z[i & 3];
+            noise[i] = n;
+        } else {
+            n = noise[i];
+        }
+        x_t[i] = __fadd_rn(__fmul_rn(sqrtf(ab), x0[i]), __fmul_rn(sqrtf(__fsub_rn(1.0f, ab)), n));
+    }
+}
+
+// loss = mean((pred-target)^2), grad = 2*(pred-target)/n          (diffusion.py:231)
+__global__ void __launch_bounds__(kEwThreads)
+mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ grad,
+                float* __restrict__ loss_out, float* __restrict__ partials, unsigned int* __restrict__ counter,
+                int64_t n, float inv_n) {
+    float acc = 0.f;
+    const float g2 = 2.0f * inv_n;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = reinterpret_cast<const float4*>(pred)[i];
+        float4 q = reinterpret_cast<const float4*>(target)[i];
+        float4 d = make_float4(p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w);
+        acc += d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w;
+        if (grad) reinterpret_cast<float4*>(grad)[i] = make_float4(g2 * d.x, g2 * d.y, g2 * d.z, g2 * d.w);
+    }
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float d = pred[i] - target[i];
+            acc += d * d;
+            if (grad) grad[i] = g2 * d;
+        }
+    }
+    __shared__ float warp_part[kEwThreads / 32];
+    __shared__ bool is_last;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < kEwThreads / 32; ++i) s += warp_part[i];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        unsigned int done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        // fixed-order final reduction by one warp (deterministic for a given grid)
+        if (threadIdx.x < 32) {
+            double s = 0.0;
+            for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) s += (double)__ldcg(&partials[i]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) {
+                loss_out[0] = (float)(s * (double)inv_n);
+                *counter = 0u;
+            }
+        }
+    }
+}
+
+// x <- c1*(x - c2*eps) + c3*z        (diffusion.py:272-274), separate roundings as in PyTorch.
+__global__ void __launch_bounds__(kEwThreads)
+psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z_base,
+               int64_t z_step_stride, const float* __restrict__ coef, const int32_t* __restrict__ t_dev, int64_t n,
+               const uint64_t* __restrict__ seed_ptr) {
+    const int t = t_dev[0];
+    const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
+    const float4 c = reinterpret_cast<const float4*>(coef)[t];
+    const float c1 = c.x, c2 = c.y, c3 = c.z;
+    const bool use_noise = (t > 0);
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float4 xv = reinterpret_cast<const float4*>(x)[i];
+        float4 ev = reinterpret_cast<const float4*>(eps)[i];
+        float zz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (use_noise) {
+            if (z) {
+                float4 zv = reinterpret_cast<const float4*>(z)[i];
+                zz[0] = zv.x; zz[1] = zv.y; zz[2] = zv.z; zz[3] = zv.w;
+            } else if (seed_ptr) {
+                Philox rng(seed_ptr[0]);
+                rng.normal4((uint64_t)i, seed_ptr[1] + (uint64_t)t, zz);
+            }
+        }
+        float4 o;
+        o.x = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.x, __fmul_rn(c2, ev.x))), __fmul_rn(c3, zz[0]));
+        o.y = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.y, __fmul_rn(c2, ev.y))), __fmul_rn(c3, zz[1]));
+        o.z = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.z, __fmul_rn(c2, ev.z))), __fmul_rn(c3, zz[2]));
+        o.w = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.w, __fmul_rn(c2, ev.w))), __fmul_rn(c3, zz[3]));
+        reinterpret_cast<float4*>(x)[i] = o;
+    }
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float zz = 0.f;
+            if (use_noise) {
+                if (z) zz = z[i];
+                else if (seed_ptr) {
+                    Philox rng(seed_ptr[0]);
+                    float q[4];
+                    rng.normal4((uint64_t)(i >> 2), seed_ptr[1] + (uint64_t)t, q);
+                    zz = q[i & 3];
+                }
+            }
+            x[i] = __fadd_rn(__fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, eps[i]))), __fmul_rn(c3, zz));
+        }
+    }
+}
+
+__global__ void counter_add_kernel(int32_t* c, int32_t delta) { c[0] += delta; }
+
+// Fused multi-tensor Adam (torch.optim.Adam defaults; diffusion.py:211,236).
+__global__ void __launch_bounds__(kEwThreads)
+adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__ g, float* const* __restrict__ m,
+                  float* const* __restrict__ v, const int64_t* __restrict__ numel,
+                  const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_offset,
+                  int64_t chunk_elems, const int32_t* __restrict__ step_dev, float lr, float beta1, float beta2,
+                  float eps, const float* __restrict__ grad_scale_dev, void* const* __restrict__ bf16_shadow) {
+    const int tid = chunk_tensor[blockIdx.x];
+    const int64_t off = chunk_offset[blockIdx.x];
+    const int64_t n = min(chunk_elems, numel[tid] - off);
+    float* __restrict__ pp = p[tid] + off;
+    const float* __restrict__ gp = g[tid] + off;
+    float* __restrict__ mp = m[tid] + off;
+    float* __restrict__ vp = v[tid] + off;
+    __nv_bfloat16* sh = bf16_shadow ? reinterpret_cast<__nv_bfloat16*>(bf16_shadow[tid]) : nullptr;
+    if (sh) sh += off;
+    const float step = (float)step_dev[0];
+    const float bc1 = 1.0f - powf(beta1, step);
+    const float bc2 = 1.0f - powf(beta2, step);
+    const float step_size = lr / bc1;
+    const float inv_bc2_sqrt = 1.0f / sqrtf(bc2);
+    const float gs = grad_scale_dev ? grad_scale_dev[0] : 1.0f;
+    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+
+    auto upd = [&](float& pv, float gv, float& mv, float& vv) {
+        gv *= gs;
+        mv = mv + omb1 * (gv - mv);                  // exp_avg.lerp_(grad, 1-beta1)
+        vv = vv * beta2 + omb2 * gv * gv;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
+        const float denom = sqrtf(vv) * inv_bc2_sqrt + eps;
+        pv = pv - step_size * (mv / denom);
+    };
+    // all four arrays share alignment only if the tensor base pointers are 16B aligned and
+    // off % 4 == 0 (chunk_elems is a multiple of 4); torch allocations are 512B aligned.
+    const bool vec_ok = ((((uintptr_t)pp | (uintptr_t)gp | (uintptr_t)mp | (uintptr_t)vp) & 15) == 0);
+    const int64_t n4 = vec_ok ? (n >> 2) : 0;
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 pv = reinterpret_cast<float4*>(pp)[i];
+        float4 gv = reinterpret_cast<const float4*>(gp)[i];
+        float4 mv = reinterpret_cast<float4*>(mp)[i];
+        float4 vv = reinterpret_cast<float4*>(vp)[i];
+        upd(pv.x, gv.x, mv.x, vv.x);
+        upd(pv.y, gv.y, mv.y, vv.y);
+        upd(pv.z, gv.z, mv.z, vv.z);
+        upd(pv.w, gv.w, mv.w, vv.w);
+        reinterpret_cast<float4*>(pp)[i] = pv;
+        reinterpret_cast<float4*>(mp)[i] = mv;
+        reinterpret_cast<float4*>(vp)[i] = vv;
+        if (sh) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(pv.x, pv.y), b = __floats2bfloat162_rn(pv.z, pv.w);
+            if ((((uintptr_t)sh) & 7) == 0) {
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&a);
+                u.y = *reinterpret_cast<uint32_t*>(&b);
+                reinterpret_cast<uint2*>(sh)[i] = u;
+            } else {
+                sh[4 * i] = a.x; sh[4 * i + 1] = a.y; sh[4 * i + 2] = b.x; sh[4 * i + 3] = b.y;
+            }
+        }
+    }
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+        float pv = pp[i], mv = mp[i], vv = vp[i];
+        upd(pv, gp[i], mv, vv);
+        pp[i] = pv; mp[i] = mv; vp[i] = vv;
+        if (sh) sh[i] = __float2bfloat16_rn(pv);
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+static inline int ew_grid(int64_t work_items) {
+    int64_t blocks = ceil_div(work_items, kEwThreads);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_qsample(const float* x0, float* noise, const int64_t* t, const float* alphas_cumprod,
+                          float* x_t, int64_t batch, int64_t per_sample, int num_timesteps,
+                          const uint64_t* seed_ptr, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x0 && noise && t && alphas_cumprod && x_t, "td_qsample: null pointer");
+    TD_CHECK_ARG(batch >= 0 && per_sample >= 0 && num_timesteps > 0, "td_qsample: bad sizes");
+    if (batch == 0 || per_sample == 0) return TD_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (per_sample % 4 == 0 && batch <= 65535) {
+        int64_t ps4 = per_sample / 4;
+        int gx = (int)std::min<int64_t>(ceil_div(ps4, kEwThreads), std::max<int64_t>(1, (kNumSMs * 16) / batch));
+        dim3 grid(gx, (unsigned)batch);
+        qsample_kernel<<<grid, kEwThreads, 0, s>>>(x0, noise, t, alphas_cumprod, x_t, ps4, num_timesteps, seed_ptr);
+    } else {
+        qsample_scalar_kernel<<<ew_grid(batch * per_sample), kEwThreads, 0, s>>>(
+            x0, noise, t, alphas_cumprod, x_t, batch, per_sample, num_timesteps, seed_ptr);
+    }
+    return launch_status("qsample");
+}
+
+extern "C" int64_t td_mse_num_partials(int64_t n) { return ew_grid(std::max<int64_t>(n / 4, 1)); }
+
+extern "C" int td_mse_grad(const float* pred, const float* target, float* grad, float* loss_out, float* partials,
+                           unsigned int* counter, int64_t n, float inv_n, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(pred && target && loss_out && partials && counter, "td_mse_grad: null pointer");
+    TD_CHECK_ARG(n > 0, "td_mse_grad: n must be positive");
+    mse_grad_kernel<<<(int)td_mse_num_partials(n), kEwThreads, 0, (cudaStream_t)stream>>>(
+        pred, target, grad, loss_out, partials, counter, n, inv_n);
+    return launch_status("mse_grad");
+}
+
+extern "C" int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef,
+                               const int32_t* t_dev, int64_t n, const uint64_t* seed_ptr, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step: null pointer");
+    TD_CHECK_ARG(n > 0, "td_psample_step: n must be positive");
+    psample_kernel<<<ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream>>>(
+        x, eps, z, z_step_stride, coef, t_dev, n, seed_ptr);
+    return launch_status("psample_step");
+}
+
+extern "C" int td_counter_add(int32_t* t_dev, int32_t delta, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(t_dev, "td_counter_add: null pointer");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, delta);
+    return launch_status("counter_add");
+}
+
+extern "C" int td_adam_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
+                             const int64_t* numel, const int32_t* chunk_tensor, const int64_t* chunk_offset,
+                             int64_t num_chunks, int64_t chunk_elems, const int32_t* step_dev, float lr,
+                             float beta1, float beta2, float eps, const float* grad_scale_dev,
+                             void* const* bf16_shadow, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(p && g && m && v && numel && chunk_tensor && chunk_offset && step_dev, "td_adam_multi: null pointer");
+    TD_CHECK_ARG(chunk_elems > 0 && chunk_elems % 4 == 0, "td_adam_multi: chunk_elems must be a positive multiple of 4");
+    if (num_chunks == 0) return TD_OK;
+    adam_multi_kernel<<<(unsigned)num_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(
+        p, g, m, v, numel, chunk_tensor, chunk_offset, chunk_elems, step_dev, lr, beta1, beta2, eps,
+        grad_scale_dev, bf16_shadow);
+    return launch_status("adam_multi");
+}
+
+extern "C" int td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(src && dst && n >= 0, "td_cast_f32_to_bf16: bad args");
+    if (n == 0) return TD_OK;
+    cast_bf16_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+    return launch_status("cast_bf16");
+}

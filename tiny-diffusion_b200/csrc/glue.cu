@@ -1,0 +1,378 @@
+// NHWC glue kernels around the convolutions (all HBM/L2-bound, 16-byte vector accesses):
+// max-pool, decoder-input assembly (bilinear up-sample + skip/embedding add + resize + concat),
+// bilinear resize, the conditioning head and weight packing.
+#include "common.cuh"
+
+namespace td {
+
+constexpr int kThreads = 256;
+
+struct Bil { int i0, i1; float l0, l1; };
+// align_corners=True source index, same fp32 op order as ATen's area_pixel_compute_* helpers.
+__device__ inline Bil bil(int dst, int in, int out) {
+    Bil b;
+    const float scale = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    const float src = scale * (float)dst;
+    b.i0 = min((int)floorf(src), in - 1);
+    b.l1 = fminf(fmaxf(src - (float)b.i0, 0.f), 1.f);
+    b.l0 = 1.f - b.l1;
+    b.i1 = b.i0 + ((b.i0 < in - 1) ? 1 : 0);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(2, ceil_mode)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+    constexpr int V = Vec<T>::N;
+    const int cv = C / V;
+    const int64_t total = (int64_t)B * Ho * Wo * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv);
+        int64_t p = i / cv;
+        int wo = (int)(p % Wo); p /= Wo;
+        int ho = (int)(p % Ho);
+        int b = (int)(p / Ho);
+        float m[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) m[k] = -INFINITY;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            int h = 2 * ho + dy;
+            if (h >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                int w = 2 * wo + dx;
+                if (w >= W) continue;
+                float f[V];
+                Vec<T>::load(x + (((int64_t)b * H + h) * W + w) * C + c * V).unpack(f);
+#pragma unroll
+                for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], f[k]);
+            }
+        }
+        Vec<T>::pack(m).store(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + c * V);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out = [ up2x(low) | resize(skip + temb) ]
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ inline void bilerp_nhwc(const T* __restrict__ src, int b, int Hs, int Ws, int C, int c0, const Bil& bh,
+                                   const Bil& bw, float* out) {
+    constexpr int V = Vec<T>::N;
+    float f00[V], f01[V], f10[V], f11[V];
+    const T* base = src + (int64_t)b * Hs * Ws * C + c0;
+    Vec<T>::load(base + ((int64_t)bh.i0 * Ws + bw.i0) * C).unpack(f00);
+    Vec<T>::load(base + ((int64_t)bh.i0 * Ws + bw.i1) * C).unpack(f01);
+    Vec<T>::load(base + ((int64_t)bh.i1 * Ws + bw.i0) * C).unpack(f10);
+    Vec<T>::load(base + ((int64_t)bh.i1 * Ws + bw.i1) * C).unpack(f11);
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        out[k] = bh.l0 * (bw.l0 * f00[k] + bw.l1 * f01[k]) + bh.l1 * (bw.l0 * f10[k] + bw.l1 * f11[k]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
+             int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
+    constexpr int V = Vec<T>::N;
+    const int Ct = Cu + Cs;
+    const int cv = Ct / V;
+    const int Hl = Ho / 2, Wl = Wo / 2;
+    const int64_t total = (int64_t)B * Ho * Wo * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * V;
+        int64_t p = i / cv;
+        int wo = (int)(p % Wo); p /= Wo;
+        int ho = (int)(p % Ho);
+        int b = (int)(p / Ho);
+        float r[V];
+        if (c < Cu) {
+            bilerp_nhwc<T>(low, b, Hl, Wl, Cu, c, bil(ho, Hl, Ho), bil(wo, Wl, Wo), r);
+        } else {
+            const int cs = c - Cu;
+            if (Hs == Ho && Ws == Wo) {
+                Vec<T>::load(skip + (((int64_t)b * Hs + ho) * Ws + wo) * Cs + cs).unpack(r);
+            } else {
+                bilerp_nhwc<T>(skip, b, Hs, Ws, Cs, cs, bil(ho, Hs, Ho), bil(wo, Ws, Wo), r);
+            }
+            // the embedding is constant over space and the bilinear weights sum to one, so
+            // resize(skip + t) == resize(skip) + t
+            const float* te = temb + (int64_t)b * ld_temb + temb_off + cs;
+#pragma unroll
+            for (int k = 0; k < V; ++k) r[k] += te[k];
+        }
+        Vec<T>::pack(r).store(out + (((int64_t)b * Ho + ho) * Wo + wo) * Ct + c);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+    constexpr int V = Vec<T>::N;
+    const int cv = C / V;
+    const int64_t total = (int64_t)B * Ho * Wo * cv;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cv) * V;
+        int64_t p = i / cv;
+        int wo = (int)(p % Wo); p /= Wo;
+        int ho = (int)(p % Ho);
+        int b = (int)(p / Ho);
+        float r[V];
+        bilerp_nhwc<T>(x, b, Hi, Wi, C, c, bil(ho, Hi, Ho), bil(wo, Wi, Wo), r);
+        Vec<T>::pack(r).store(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conditioning head.  One CTA handles kS samples so each weight row is read once per kS samples;
+// one warp per output row, lanes stride the reduction dimension (coalesced), shuffle reduce.
+// ---------------------------------------------------------------------------------------------
+constexpr int kS = 4;
+constexpr int kEmbThreads = 512;
+
+__device__ inline float silu(float x) { return x / (1.0f + expf(-x)); }
+
+__global__ void __launch_bounds__(kEmbThreads)
+embed_head_kernel(td_embed_args a) {
+    extern __shared__ float sm[];
+    const int D = a.dim;
+    float* in0 = sm;               // [kS][D]   sinusoidal input (in_mode 2) else [kS] scalars
+    float* h = sm + kS * D;        // [kS][D]
+    float* e = sm + 2 * kS * D;    // [kS][D]
+    const int b0 = blockIdx.x * kS;
+    const int ns = min(kS, a.batch - b0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+
+    float tval[kS];
+#pragma unroll
+    for (int s = 0; s < kS; ++s) {
+        float tv = 0.f;
+        if (s < ns) tv = a.t ? (float)a.t[b0 + s] : (float)a.t_dev[0];
+        if (a.in_mode == 1) tv = tv / 1000.0f;
+        tval[s] = tv;
+    }
+    if (a.in_mode == 2) {
+        const int half = D / 2;
+        const float lg = logf(10000.0f);
+        for (int i = threadIdx.x; i < kS * D; i += blockDim.x) {
+            int s = i / D, j = i % D;
+            int jj = (j < half) ? j : j - half;
+            float v = 0.f;
+            if (jj < half && j < 2 * half) {
+                float fr = expf(-lg * (float)jj / (float)(half - 1));
+                float arg = tval[s] * fr;
+                v = (j < half) ? sinf(arg) : cosf(arg);
+            }
+            in0[i] = v;
+        }
+        __syncthreads();
+        for (int j = warp; j < D; j += nw) {
+            float acc[kS] = {0.f, 0.f, 0.f, 0.f};
+            const float* wr = a.w0 + (int64_t)j * D;
+            for (int i = lane; i < D; i += 32) {
+                float w = wr[i];
+#pragma unroll
+                for (int s = 0; s < kS; ++s) acc[s] += w * in0[s * D + i];
+            }
+#pragma unroll
+            for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
+            if (lane == 0) {
+#pragma unroll
+                for (int s = 0; s < kS; ++s) {
+                    float pre = acc[s] + a.b0[j];
+                    if (a.h_out && s < ns) a.h_out[(int64_t)(b0 + s) * D + j] = pre;
+                    h[s * D + j] = silu(pre);
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < kS * D; i += blockDim.x) {
+            int s = i / D, j = i % D;
+            float pre = a.w0[j] * tval[s] + a.b0[j];      // Linear(1, D)
+            if (a.h_out && s < ns) a.h_out[(int64_t)(b0 + s) * D + j] = pre;
+            h[i] = silu(pre);
+        }
+    }
+    __syncthreads();
+    for (int j = warp; j < D; j += nw) {
+        float acc[kS] = {0.f, 0.f, 0.f, 0.f};
+        const float* wr = a.w2 + (int64_t)j * D;
+        for (int i = lane; i < D; i += 32) {
+            float w = wr[i];
+#pragma unroll
+            for (int s = 0; s < kS; ++s) acc[s] += w * h[s * D + i];
+        }
+#pragma unroll
+        for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kS; ++s) {
+                float v = acc[s] + a.b2[j];
+                if (s < ns) {
+                    if (a.y && a.class_table) v += a.class_table[(int64_t)a.y[b0 + s] * D + j];
+                    if (a.text) v += a.text[(int64_t)(b0 + s) * D + j];
+                    if (a.emb_out) a.emb_out[(int64_t)(b0 + s) * D + j] = v;
+                }
+                e[s * D + j] = v;
+            }
+        }
+    }
+    __syncthreads();
+    for (int j = warp; j < a.proj_out; j += nw) {
+        float acc[kS] = {0.f, 0.f, 0.f, 0.f};
+        const float* wr = a.proj_w + (int64_t)j * D;
+        for (int i = lane; i < D; i += 32) {
+            float w = wr[i];
+#pragma unroll
+            for (int s = 0; s < kS; ++s) acc[s] += w * e[s * D + i];
+        }
+#pragma unroll
+        for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
+        if (lane == 0) {
+            const float pb = a.proj_b[j];
+#pragma unroll
+            for (int s = 0; s < kS; ++s)
+                if (s < ns) a.proj_out_ptr[(int64_t)(b0 + s) * a.proj_out + j] = acc[s] + pb;
+        }
+    }
+}
+
+// OIHW fp32 -> OHWI (fp32 or bf16)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+pack_weight_kernel(const float* __restrict__ oihw, T* __restrict__ ohwi, int cout, int cin) {
+    const int64_t total = (int64_t)cout * 9 * cin;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % cin);
+        int64_t r = i / cin;
+        int tap = (int)(r % 9);
+        int o = (int)(r / 9);
+        ohwi[i] = from_f32<T>(oihw[((int64_t)o * cin + c) * 9 + tap]);
+    }
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ conv_bias, float eps, float* __restrict__ scale,
+                               float* __restrict__ shift, int c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = beta[i] + ((conv_bias ? conv_bias[i] : 0.f) - mean[i]) * s;
+}
+
+static inline int grid_for(int64_t items) {
+    int64_t blocks = ceil_div(items, kThreads);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_maxpool2_fwd(const void* x, void* y, int dtype, int batch, int h, int w, int c, int ceil_mode,
+                               void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && y && batch > 0 && h > 0 && w > 0 && c > 0, "td_maxpool2_fwd: bad args");
+    const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == TD_BF16) {
+        TD_CHECK_ARG(c % 8 == 0, "td_maxpool2_fwd: channels must be a multiple of 8 for bf16");
+        maxpool2_kernel<__nv_bfloat16><<<grid_for((int64_t)batch * ho * wo * c / 8), kThreads, 0, s>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, h, w, c, ho, wo);
+    } else if (dtype == TD_F32) {
+        TD_CHECK_ARG(c % 4 == 0, "td_maxpool2_fwd: channels must be a multiple of 4 for fp32");
+        maxpool2_kernel<float><<<grid_for((int64_t)batch * ho * wo * c / 4), kThreads, 0, s>>>(
+            (const float*)x, (float*)y, batch, h, w, c, ho, wo);
+    } else {
+        TD_CHECK_ARG(false, "td_maxpool2_fwd: unknown dtype %d", dtype);
+    }
+    return launch_status("maxpool2");
+}
+
+extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb, int ld_temb, int temb_off,
+                            void* out, int dtype, int batch, int ho, int wo, int cu, int hs, int ws, int cs,
+                            void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(low && skip && temb && out, "td_upcat_fwd: null pointer");
+    TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0, "td_upcat_fwd: bad output size");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t elems = (int64_t)batch * ho * wo * (cu + cs);
+    if (dtype == TD_BF16) {
+        TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
+        upcat_kernel<__nv_bfloat16><<<grid_for(elems / 8), kThreads, 0, s>>>(
+            (const __nv_bfloat16*)low, (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out,
+            batch, ho, wo, cu, hs, ws, cs);
+    } else if (dtype == TD_F32) {
+        TD_CHECK_ARG(cu % 4 == 0 && cs % 4 == 0, "td_upcat_fwd: channel counts must be multiples of 4");
+        upcat_kernel<float><<<grid_for(elems / 4), kThreads, 0, s>>>(
+            (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs);
+    } else {
+        TD_CHECK_ARG(false, "td_upcat_fwd: unknown dtype %d", dtype);
+    }
+    return launch_status("upcat");
+}
+
+extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int batch, int hi, int wi, int ho, int wo,
+                                      int c, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && y && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_fwd: bad args");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t elems = (int64_t)batch * ho * wo * c;
+    if (dtype == TD_BF16) {
+        TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");
+        resize_kernel<__nv_bfloat16><<<grid_for(elems / 8), kThreads, 0, s>>>(
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c);
+    } else if (dtype == TD_F32) {
+        TD_CHECK_ARG(c % 4 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 4 for fp32");
+        resize_kernel<float><<<grid_for(elems / 4), kThreads, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
+    } else {
+        TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
+    }
+    return launch_status("resize_bilinear");
+}
+
+extern "C" int td_embed_head_fwd(const td_embed_args* a, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(a, "td_embed_head_fwd: null args");
+    TD_CHECK_ARG(a->batch > 0 && a->dim > 0 && a->dim <= 1024, "td_embed_head_fwd: bad batch/dim");
+    TD_CHECK_ARG(a->t || a->t_dev, "td_embed_head_fwd: need t or t_dev");
+    TD_CHECK_ARG(a->w0 && a->b0 && a->w2 && a->b2, "td_embed_head_fwd: null weights");
+    TD_CHECK_ARG(a->proj_out == 0 || (a->proj_w && a->proj_b && a->proj_out_ptr), "td_embed_head_fwd: null projection");
+    TD_CHECK_ARG(a->in_mode >= 0 && a->in_mode <= 2, "td_embed_head_fwd: bad in_mode");
+    const size_t smem = (size_t)3 * kS * a->dim * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        TD_CUDA(cudaFuncSetAttribute(embed_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    embed_head_kernel<<<(a->batch + kS - 1) / kS, kEmbThreads, smem, (cudaStream_t)stream>>>(*a);
+    return launch_status("embed_head");
+}
+
+extern "C" int td_pack_conv_weight(const float* oihw, void* ohwi, int out_dtype, int cout, int cin, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(oihw && ohwi && cout > 0 && cin > 0, "td_pack_conv_weight: bad args");
+    const int64_t n = (int64_t)cout * cin * 9;
+    if (out_dtype == TD_BF16)
+        pack_weight_kernel<__nv_bfloat16><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(oihw, (__nv_bfloat16*)ohwi, cout, cin);
+    else if (out_dtype == TD_F32)
+        pack_weight_kernel<float><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(oihw, (float*)ohwi, cout, cin);
+    else
+        TD_CHECK_ARG(false, "td_pack_conv_weight: unknown dtype %d", out_dtype);
+    return launch_status("pack_conv_weight");
+}
+
+extern "C" int td_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                          const float* conv_bias, float eps, float* scale, float* shift, int c, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(gamma && beta && mean && var && scale && shift && c > 0, "td_bn_fold: bad args");
+    bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, eps, scale, shift, c);
+    return launch_status("bn_fold");
+}

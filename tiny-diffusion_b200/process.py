@@ -1,0 +1,123 @@
+"""ForwardProcess (diffusion.py:165-190) and the ancestral reverse loop (diffusion.py:254-276)
+on top of libtinydiff.
+
+``ForwardProcess`` keeps the reference's attribute contract -- ``num_timesteps`` and the fp32 CPU
+tensors ``betas`` / ``alphas`` / ``alphas_cumprod`` built by the same op sequence -- and adds
+private device-side tables so that q_sample is one kernel and a p_sample step is one kernel whose
+timestep comes from a device counter (the loop is CUDA-graph capturable).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+
+
+class ForwardProcess:
+    def __init__(self, num_timesteps: int = 1000, beta_start: float = 1e-4, beta_end: float = 0.02):
+        # diffusion.py:172-175 -- identical op sequence (fp32, CPU)
+        self.num_timesteps = num_timesteps
+        self.betas = torch.linspace(beta_start, beta_end, num_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self._dev: Dict[torch.device, Dict[str, torch.Tensor]] = {}
+
+    # device-side tables -------------------------------------------------------------------
+    def _tables(self, device: torch.device) -> Dict[str, torch.Tensor]:
+        tab = self._dev.get(device)
+        if tab is None:
+            # coefficients of diffusion.py:272-274 in the reference's own fp32 op order:
+            # (1 - alpha), not beta; sigma_t = sqrt(beta_t)
+            c1 = 1 / torch.sqrt(self.alphas)
+            c2 = (1 - self.alphas) / torch.sqrt(1 - self.alphas_cumprod)
+            c3 = torch.sqrt(self.betas)
+            coef = torch.stack([c1, c2, c3, torch.zeros_like(c1)], dim=1).contiguous()
+            tab = {"abar": self.alphas_cumprod.to(device).contiguous(), "coef": coef.to(device)}
+            self._dev[device] = tab
+        return tab
+
+    def q_sample(self, device, x_0: torch.Tensor, t: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """diffusion.py:177-190.  Returns ``(x_t, noise)``.  ``noise`` may be injected; by default it is
+        drawn with ``torch.randn_like`` exactly where the reference draws it (:178) so that the
+        global RNG stream is consumed identically."""
+        device = L.require_device(device)
+        x_0 = x_0.to(device=device, dtype=torch.float32).contiguous()
+        t = t.to(device=device, dtype=torch.int64).contiguous()
+        if noise is None:
+            noise = torch.randn_like(x_0)
+        noise = noise.to(device=device, dtype=torch.float32).contiguous()
+        if x_0.shape[0] != t.shape[0]:
+            raise ValueError("t must have one entry per sample")
+        x_t = torch.empty_like(x_0)
+        B = x_0.shape[0]
+        per = x_0.numel() // max(B, 1)
+        tab = self._tables(device)
+        L.check(L.load().td_qsample(x_0.data_ptr(), noise.data_ptr(), t.data_ptr(), tab["abar"].data_ptr(),
+                                    x_t.data_ptr(), B, per, self.num_timesteps, None, L.stream_ptr()), "td_qsample")
+        return x_t, noise
+
+
+class ReverseLoop:
+    """x_{t-1} = c1*(x_t - c2*eps) + c3*z for t = T-1 .. 0, one fused kernel per step, the step
+    index held on the device.  ``eps_launch`` enqueues the denoiser for the current ``x``/``t``."""
+
+    def __init__(self, process: ForwardProcess, x: torch.Tensor, eps: torch.Tensor, t_dev: torch.Tensor,
+                 eps_launch, use_graph: bool = True):
+        self.p, self.x, self.eps, self.t_dev, self.eps_launch = process, x, eps, t_dev, eps_launch
+        self.use_graph = use_graph
+        self.lib = L.load()
+        self.tab = process._tables(x.device)
+        self.seed = torch.zeros(2, device=x.device, dtype=torch.int64)
+        self.graph = None
+        self._z_ref = None
+
+    def _step(self, z_ptr, z_stride, seed_ptr):
+        st = L.stream_ptr()
+        self.eps_launch()
+        L.check(self.lib.td_psample_step(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
+                                         self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
+                                         seed_ptr, st), "td_psample_step")
+        L.check(self.lib.td_counter_add(self.t_dev.data_ptr(), -1, st), "td_counter_add")
+
+    def run(self, z: Optional[torch.Tensor] = None, seed: int = 0, steps: Optional[int] = None) -> None:
+        """Run ``steps`` (default all T) reverse steps in place on ``self.x``.
+        z: optional injected noise table [T, *x.shape] (row t used at step t; row 0 unused)."""
+        T = self.p.num_timesteps
+        steps = T if steps is None else steps
+        n = self.x.numel()
+        if z is not None:
+            assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.shape[0] == T
+            assert z.numel() == T * n
+            z_ptr, z_stride, seed_ptr = z.data_ptr(), n, None
+        else:
+            self.seed[0] = seed
+            self.seed[1] = 0
+            z_ptr, z_stride, seed_ptr = None, 0, self.seed.data_ptr()
+        if not self.use_graph:
+            self.t_dev.fill_(T - 1)
+            for _ in range(steps):
+                self._step(z_ptr, z_stride, seed_ptr)
+            return
+        key = (z_ptr, z_stride, seed_ptr)
+        if self.graph is None or self._key != key:
+            # one eager step first (lazy module loading and cudaFuncSetAttribute are not capturable),
+            # on a copy-restored x, then capture ONE step; the graph is replayed `steps` times.
+            x_saved = self.x.clone()
+            self.t_dev.fill_(T - 1)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._step(z_ptr, z_stride, seed_ptr)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step(z_ptr, z_stride, seed_ptr)
+            self.x.copy_(x_saved)
+            self.graph, self._key, self._z_ref = g, key, z
+        self.t_dev.fill_(T - 1)
+        for _ in range(steps):
+            self.graph.replay()
