@@ -101,7 +101,7 @@ typedef struct {
     int proj_out;            /* rows of proj_w (sum of the three time_proj Cout); 0 = none */
     const int64_t* t;        /* [batch] or NULL */
     const int32_t* t_dev;    /* used for every sample when t == NULL (sampler step counter) */
-    const float* w0;         /* [D, Din] */
+    const float* w0;         /* [D, Din]   Din = 1 (modes 0, 1) or D (mode 2) */
     const float* b0;         /* [D] */
     const float* w2;         /* [D, D] */
     const float* b2;         /* [D] */
@@ -110,11 +110,23 @@ typedef struct {
     const float* text;       /* [batch, D] additive embedding or NULL */
     const float* proj_w;     /* [proj_out, D] */
     const float* proj_b;     /* [proj_out] */
-    float* emb_out;          /* [batch, D]  (combined embedding; needed by backward) or NULL */
-    float* h_out;            /* [batch, D]  pre-SiLU hidden (needed by backward) or NULL */
+    float* saved;            /* td_embed_head_saved_floats() floats, consecutive row-major blocks:      */
+                             /* feat [B, Din] | h_pre [B, D] | h = silu(h_pre) [B, D] | emb [B, D]      */
     float* proj_out_ptr;     /* [batch, proj_out] */
 } td_embed_args;
+/* gradients of the head's parameters given d_proj = dL/d(proj_out_ptr); `a` must be the forward's
+ * argument block (same `saved`).  scratch: 2*batch*dim floats. */
+typedef struct {
+    const float* d_proj;     /* [batch, proj_out] */
+    float* scratch;
+    float* d_w0; float* d_b0; float* d_w2; float* d_b2;
+    float* d_class_table;    /* [num_classes, D] or NULL */
+    int num_classes;
+    float* d_proj_w; float* d_proj_b;
+} td_embed_grads;
+int64_t td_embed_head_saved_floats(int batch, int dim, int in_mode);
 int td_embed_head_fwd(const td_embed_args* a, void* stream);
+int td_embed_head_bwd(const td_embed_args* a, const td_embed_grads* g, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3x3 / stride 1 / pad 1 convolutions, NHWC.  Replaces nn.Conv2d(.,.,3,padding=1) (+ the
@@ -182,6 +194,122 @@ int td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* OIHW fp32 (PyTorch conv weight) -> OHWI fp32 or bf16 */
 int td_pack_conv_weight(const float* oihw, void* ohwi, int out_dtype, int cout, int cin,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training: data / weight gradients of the 3x3 convolutions (autograd of diffusion.py:28-98).
+ * The data gradient is td_conv3x3_run on the flipped-transposed weights
+ * (td_pack_conv_weight_dgrad); the weight gradient is the plan below.
+ * ---------------------------------------------------------------------------------------- */
+/* OIHW fp32 -> [cin][3][3][cout] (fp32 / bf16), taps flipped: dX = conv3x3(dY, Wd) */
+int td_pack_conv_weight_dgrad(const float* oihw, void* out, int out_dtype, int cout, int cin, void* stream);
+
+typedef struct {
+    int batch, height, width;
+    int cin, cout;
+    int x_dtype, dy_dtype;
+    const void* x;           /* conv input  [batch, height, width, ldx] channels [x_coff, x_coff+cin)   */
+    int ldx, x_coff, x_nchw; /* x_nchw: fp32 NCHW network input (SIMT engine only)                      */
+    const void* dy;          /* grad of conv output [batch, height, width, lddy] at dy_coff             */
+    int lddy, dy_coff, dy_nchw;
+    float* dw;               /* OIHW fp32 [cout][cin][3][3]: PyTorch's .grad layout (overwritten)       */
+    float* workspace;        /* td_conv3x3_wgrad_workspace() floats of split-K partials                 */
+} td_wgrad_desc;
+typedef struct td_wgrad_plan td_wgrad_plan;
+int64_t td_conv3x3_wgrad_workspace(const td_wgrad_desc* desc, int engine);
+int td_conv3x3_wgrad_plan_create(td_wgrad_plan** plan, const td_wgrad_desc* desc, int engine); /* TD_CONV_SIMT | TD_CONV_TC */
+int td_conv3x3_wgrad_run(const td_wgrad_plan* plan, void* stream);
+void td_conv3x3_wgrad_plan_destroy(td_wgrad_plan* plan);
+
+/* ------------------------------------------------------------------------------------------
+ * Training: BatchNorm2d (+ReLU) in train mode and its backward, nn.BatchNorm2d/nn.ReLU at
+ * diffusion.py:34-35.  NHWC, `pixels` = batch*height*width rows.  Reductions write one row of
+ * [2][channels] partial sums per CTA (td_chan_reduce_rows rows) and are finalised in fixed order.
+ * ---------------------------------------------------------------------------------------- */
+int td_chan_reduce_rows(int dtype, int64_t pixels, int channels);
+/* partials[r] = { sum x, sum x^2 } of the raw conv output x (conv bias NOT included) */
+int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, int64_t pixels, int channels, float* partials,
+                void* stream);
+/* batch mean / biased variance -> scale = gamma*invstd, shift = beta - mean*scale; running stats
+ * momentum update with the unbiased variance and mean + conv_bias; num_batches_tracked += 1 */
+int td_bn_finalize(const float* partials, int nrows, int channels, int64_t count, const float* gamma,
+                   const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
+                   float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
+                   float* save_invstd, void* stream);
+/* a[p, a_coff + c] = relu?(y[p, c] * scale[c] + shift[c]) */
+int td_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
+                     int a_coff, int64_t pixels, int channels, int relu, void* stream);
+/* partials[r] = { sum g, sum g*y },  g = da * [y*scale+shift > 0] */
+int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int dtype, const float* scale,
+                          const float* shift, int64_t pixels, int channels, float* partials, void* stream);
+/* dgamma, dbeta and the per-channel coefficients coef[3][channels] of the apply pass */
+int td_bn_bwd_finalize(const float* partials, int nrows, int channels, int64_t count, const float* scale,
+                       const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* coef,
+                       void* stream);
+/* dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) */
+int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const void* y, int dtype, const float* scale,
+                         const float* shift, const float* coef, void* dy, int64_t pixels, int channels, void* stream);
+
+/* backward of td_maxpool2_fwd (first maximum in scan order takes the gradient, like ATen) */
+int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int batch, int h, int w, int c, int ceil_mode,
+                    int accumulate, void* stream);
+/* backward of td_resize_bilinear_fwd: dx[b,hi,wi,:] from dy [b,ho,wo,ld_dy] at channel dy_coff (gather form) */
+int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff, void* dx, int dtype, int batch, int hi, int wi,
+                           int ho, int wo, int c, void* stream);
+/* backward of td_upcat_fwd: dlow [b,ho/2,wo/2,cu], dskip [b,hs,ws,cs] (overwritten) and
+ * dtemb[b, temb_off + c] = sum_{h,w} dout[b,h,w,cu+c] */
+int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dtemb, int ld_temb, int temb_off, int dtype,
+                 int batch, int ho, int wo, int cu, int hs, int ws, int cs, void* stream);
+/* out[c] = sum_r partials[r][which][c] */
+int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream);
+/* out[c] = sum_{b,hw} x[b,c,hw]  (final_conv bias gradient) */
+int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 dense layers: nn.Linear / nn.LayerNorm / nn.BatchNorm1d / nn.GELU / nn.SiLU of the
+ * conditioning head (diffusion.py:21-25), the latent MLP denoiser (latent_diffusion.py:24-105) and
+ * the DiT blocks (diffusion_transformer.py:16-109).
+ * ---------------------------------------------------------------------------------------- */
+#define TD_ACT_NONE 0
+#define TD_ACT_RELU 1
+#define TD_ACT_SILU 2
+#define TD_ACT_GELU 3      /* exact (erf) GELU, nn.GELU() default */
+/* C[i,j] = epilogue( alpha * sum_k A(i,k) * B(k,j) ),  A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]
+ * epilogue(v): v += bias[j]; pre_out[i,j] = v; v = act(v); v += residual[i,j]; v += gather_table[gather_idx[i], j];
+ *              if (accumulate) v += C[i,j]
+ * nn.Linear forward y = x W^T + b: A = x (a_rs=K, a_cs=1), B = W [N,K] (b_rs=1, b_cs=K). */
+typedef struct {
+    int M, N, K;
+    const float* A; int64_t a_rs, a_cs;
+    const float* B; int64_t b_rs, b_cs;
+    float* C; int64_t ldc;
+    float alpha;
+    const float* bias;
+    int act;
+    float* pre_out; int64_t ld_pre;
+    const float* residual; int64_t ldr;
+    const int64_t* gather_idx; const float* gather_table; int64_t ld_table;
+    int accumulate;
+    float* splitk_ws;        /* NULL, or td_gemm_f32_workspace(M,N,K) floats: deterministic split-K */
+} td_gemm_args;
+int64_t td_gemm_f32_workspace(int M, int N, int K);
+int td_gemm_f32(const td_gemm_args* a, void* stream);
+int td_colsum_f32(const float* x, int64_t ldx, float* out, int M, int N, int accumulate, void* stream);
+int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream);
+/* table_grad[c,:] = sum_{i: idx[i]==c} g[i,:]   (nn.Embedding backward, conditional_diffusion.py:31) */
+int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx, float* table_grad, int M, int D, int num_rows,
+                     int accumulate, void* stream);
+/* out[b, :] = t (mode 0), t/1000 (mode 1) [width 1] or the sinusoidal embedding [width dim] (mode 2) */
+int td_time_features(const int64_t* t, const int32_t* t_dev, float* out, int batch, int dim, int mode, void* stream);
+int td_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M,
+                     int D, float eps, void* stream);
+int td_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                     float* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+int td_bn1d_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float* running_mean,
+                float* running_var, float* save_mean, float* save_rstd, float* y, int64_t ldy, int M, int N, float eps,
+                float momentum, int training, int relu, void* stream);
+int td_bn1d_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* y_out, int64_t ldy,
+                const float* gamma, const float* save_mean, const float* save_rstd, float* dx, int64_t lddx,
+                float* dgamma, float* dbeta, int M, int N, int relu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,310 @@
+"""Training-path parity on a real B200: every backward / train-mode kernel against ATen autograd
+(fp32, CPU), then the whole train step (loss, eps, every parameter gradient, BatchNorm buffers,
+one Adam update) against the CPU oracle and the reference-generated golden fixtures.
+
+Tolerances: fp32 engine -- loss 1e-5, eps 1e-4, gradients 1e-3 rel-L2 per tensor;
+bf16 tcgen05 engine -- loss 1e-2, eps 1e-2, gradients 3e-2 (5e-2 for the tiny conditioning tensors)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ddpm_oracle as O                       # noqa: E402  (checker only)
+from oracle.fixtures import checksum, init_state_dict, make_inputs   # noqa: E402
+
+SPECS = {"diffusion": O.UNET_MNIST, "conditional_diffusion": O.UNET_COND, "conditional_diffusion_laion": O.UNET_LAION}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from tinydiff import _lib as L
+    return L.require_device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# kernels
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,H,Cc", [(3, 7, 64), (2, 28, 128), (5, 4, 512), (2, 16, 32)])
+def test_bn_train_fwd_bwd(dev, dtype, tol, B, H, Cc):
+    from tinydiff import ops
+    if dtype == torch.bfloat16 and Cc % 64:
+        pytest.skip("bf16 path is used with multiples of 64 channels")
+    g = torch.Generator().manual_seed(B * 100 + H)
+    y = (torch.randn(B, Cc, H, H, generator=g) * 1.7 + 0.3).to(dtype).float()
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g) * 0.1
+    bias = torch.randn(Cc, generator=g) * 0.2
+    rm, rv = torch.randn(Cc, generator=g) * 0.1, torch.rand(Cc, generator=g) + 0.5
+    da = torch.randn(B, Cc, H, H, generator=g).to(dtype).float()
+    # reference: BN(train) on conv output y + bias, then ReLU
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    a_ref = F.relu(F.batch_norm(yr + bias.view(1, -1, 1, 1), rm_ref, rv_ref, gr, br, True, 0.1, 1e-5))
+    a_ref.backward(da)
+    rm_d, rv_d = rm.to(dev), rv.to(dev)
+    nbt = torch.zeros(1, dtype=torch.int64, device=dev)
+    yd = nhwc(y).to(dev).to(dtype)
+    a, scale, shift, mean, invstd = ops.bn_train_fwd(yd, gamma.to(dev), beta.to(dev), bias.to(dev), rm_d, rv_d, nbt)
+    assert rel(nchw(a.float()), a_ref) < tol
+    assert rel(rm_d, rm_ref) < 1e-5 and rel(rv_d, rv_ref) < 1e-5 and int(nbt) == 1
+    dy, dgamma, dbeta = ops.bn_train_bwd(nhwc(da).to(dev).to(dtype), yd, scale, shift, mean, invstd)
+    assert rel(nchw(dy.float()), yr.grad) < max(tol, 2e-5) * 3
+    assert rel(dgamma, gr.grad) < max(tol, 1e-5) * 2 and rel(dbeta, br.grad) < max(tol, 1e-5) * 2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("H,ceil", [(28, True), (7, True), (7, False), (14, True), (8, False)])
+def test_maxpool_bwd_with_ties(dev, dtype, H, ceil):
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(H)
+    x = F.relu(torch.randn(3, 16, H, H, generator=g)).to(dtype).float()       # many exact-zero ties
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, ceil_mode=ceil)
+    dy = torch.randn(yr.shape, generator=g).to(dtype).float()
+    yr.backward(dy)
+    dx = ops.maxpool2_bwd(nhwc(x).to(dev).to(dtype), nhwc(dy).to(dev).to(dtype), ceil)
+    assert torch.equal(nchw(dx.float()).cpu(), xr.grad)
+    # accumulate form
+    base = torch.randn(x.shape, generator=g).to(dtype).float()
+    dx2 = nhwc(base).to(dev).to(dtype)
+    ops.maxpool2_bwd(nhwc(x).to(dev).to(dtype), nhwc(dy).to(dev).to(dtype), ceil, dx=dx2)
+    assert rel(nchw(dx2.float()), base + xr.grad) < (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("hi,ho", [(32, 28), (28, 32), (7, 8), (14, 16), (4, 8), (16, 16)])
+def test_resize_bwd(dev, dtype, tol, hi, ho):
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(hi * 100 + ho)
+    x = torch.randn(2, 16, hi, hi, generator=g, requires_grad=True)
+    y = F.interpolate(x, size=(ho, ho), mode="bilinear", align_corners=True)
+    dy = torch.randn(y.shape, generator=g).to(dtype).float()
+    y.backward(dy)
+    dx = ops.resize_bilinear_bwd(nhwc(dy).to(dev).to(dtype), hi, hi)
+    assert rel(nchw(dx.float()), x.grad) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("hl,hs,cu,cs", [(4, 7, 64, 64), (8, 14, 32, 64), (16, 28, 128, 128), (8, 16, 64, 32)])
+def test_upcat_bwd(dev, dtype, tol, hl, hs, cu, cs):
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(hl)
+    B, ho = 3, 2 * hl
+    low = torch.randn(B, cu, hl, hl, generator=g, requires_grad=True)
+    skip = torch.randn(B, cs, hs, hs, generator=g, requires_grad=True)
+    temb = torch.randn(B, cs + 5, generator=g, requires_grad=True)
+    up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=True)
+    sk = skip + temb[:, 5:].view(B, cs, 1, 1)
+    if hs != ho:
+        sk = F.interpolate(sk, size=(ho, ho), mode="bilinear", align_corners=True)
+    out = torch.cat([up, sk], dim=1)
+    dout = torch.randn(out.shape, generator=g).to(dtype).float()
+    out.backward(dout)
+    dlow, dskip, dtemb = ops.upcat_bwd(nhwc(dout).to(dev).to(dtype), cu, hs, hs, cs + 5, 5)
+    assert rel(nchw(dlow.float()), low.grad) < tol
+    assert rel(nchw(dskip.float()), skip.grad) < tol
+    assert rel(dtemb[:, 5:], temb.grad[:, 5:]) < tol
+    assert float(dtemb[:, :5].abs().max()) == 0.0
+
+
+def _conv_case(B, H, cin, cout, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cin, H, H, generator=g).to(torch.bfloat16).float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).to(torch.bfloat16).float()
+    dy = torch.randn(B, cout, H, H, generator=g).to(torch.bfloat16).float()
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    F.conv2d(xr, wr, padding=1).backward(dy)
+    return x, w, dy, xr.grad, wr.grad
+
+
+@pytest.mark.parametrize("B,H,cin,cout", [(2, 7, 8, 12), (3, 28, 64, 1), (3, 28, 1, 64), (2, 9, 20, 36), (5, 4, 64, 64)])
+def test_conv_wgrad_dgrad_simt_fp32(dev, B, H, cin, cout):
+    from tinydiff import _lib as L, ops
+    x, w, dy, dx_ref, dw_ref = _conv_case(B, H, cin, cout)
+    dw = ops.conv3x3_wgrad(nhwc(x).to(dev), nhwc(dy).to(dev), L.CONV_SIMT)
+    assert rel(dw, dw_ref) < 1e-5
+    wd = ops.pack_conv_weight_dgrad(w.to(dev), torch.float32)
+    dx = ops.conv3x3(nhwc(dy).to(dev), wd, engine=L.CONV_SIMT)
+    assert rel(nchw(dx), dx_ref) < 1e-5
+    # NCHW boundary tensors (network input / output)
+    dw2 = ops.conv3x3_wgrad(x.to(dev), nhwc(dy).to(dev), L.CONV_SIMT, x_nchw=True)
+    assert rel(dw2, dw_ref) < 1e-5
+    dw3 = ops.conv3x3_wgrad(nhwc(x).to(dev), dy.to(dev), L.CONV_SIMT, dy_nchw=True)
+    assert rel(dw3, dw_ref) < 1e-5
+
+
+TC_SHAPES = [(2, 8, 64, 64), (3, 28, 64, 128), (3, 28, 128, 128), (5, 14, 128, 256), (4, 7, 256, 512),
+             (16, 7, 512, 512), (9, 4, 512, 512), (3, 8, 1024, 256), (3, 16, 512, 128), (2, 32, 256, 64),
+             (2, 32, 64, 64), (1, 28, 128, 64), (37, 7, 256, 256)]
+
+
+@pytest.mark.parametrize("B,H,cin,cout", TC_SHAPES)
+def test_conv_wgrad_tc_bf16(dev, B, H, cin, cout):
+    from tinydiff import _lib as L, ops
+    x, w, dy, dx_ref, dw_ref = _conv_case(B, H, cin, cout)
+    dw = ops.conv3x3_wgrad(nhwc(x).to(dev).to(torch.bfloat16), nhwc(dy).to(dev).to(torch.bfloat16), L.CONV_TC)
+    assert rel(dw, dw_ref) < 2e-3         # bf16-exact inputs, fp32 accumulate: only summation order differs
+
+
+@pytest.mark.parametrize("B,H,cin,cout", TC_SHAPES[:8])
+def test_conv_dgrad_tc_bf16(dev, B, H, cin, cout):
+    from tinydiff import _lib as L, ops
+    x, w, dy, dx_ref, dw_ref = _conv_case(B, H, cin, cout)
+    wd = ops.pack_conv_weight_dgrad(w.to(dev), torch.bfloat16)
+    dx = ops.conv3x3(nhwc(dy).to(dev).to(torch.bfloat16), wd, engine=L.CONV_TC, out_dtype=torch.float32)
+    assert rel(nchw(dx), dx_ref) < 2e-3
+
+
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 256), (37, 20, 1), (130, 70, 33), (256, 256, 4096)])
+def test_gemm_f32(dev, ta, tb, M, N, K):
+    from tinydiff import _lib as L, ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    Bm = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    want = F.gelu((A.t() if ta else A).double() @ (Bm.t() if tb else Bm).double() + bias.double()) + res.double()
+    for splitk in (False, True):
+        got = ops.gemm(A.to(dev), Bm.to(dev), bias.to(dev), L.ACT_GELU, res.to(dev), ta, tb, splitk=splitk)
+        assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_embed_head_bwd(dev, mode):
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(3)
+    B, D, P = 9, 64, 96
+    din = D if mode == 2 else 1
+    t = torch.randint(0, 1000, (B,), generator=g)
+    ps = {"w0": torch.randn(D, din, generator=g) * (0.01 if mode == 0 else 0.1), "b0": torch.randn(D, generator=g) * 0.1,
+          "w2": torch.randn(D, D, generator=g) * 0.1, "b2": torch.randn(D, generator=g) * 0.1,
+          "proj_w": torch.randn(P, D, generator=g) * 0.1, "proj_b": torch.randn(P, generator=g) * 0.1,
+          "class_table": torch.randn(10, D, generator=g)}
+    y = torch.randint(0, 10, (B,), generator=g)
+    d_proj = torch.randn(B, P, generator=g)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in ps.items()}
+    feat = O.timestep_embedding_sinusoidal(t, D) if mode == 2 else t.float().view(B, 1)
+    h = F.silu(feat @ leaf["w0"].t() + leaf["b0"])
+    emb = h @ leaf["w2"].t() + leaf["b2"] + leaf["class_table"][y]
+    proj = emb @ leaf["proj_w"].t() + leaf["proj_b"]
+    proj.backward(d_proj)
+    d = {k: v.to(dev) for k, v in ps.items()}
+    out, emb_got, grads = ops.embed_head(t.to(dev), d["w0"], d["b0"], d["w2"], d["b2"], d["proj_w"], d["proj_b"], mode,
+                                         y=y.to(dev), class_table=d["class_table"], grads_for=d_proj.to(dev))
+    assert rel(out, proj) < 1e-5 and rel(emb_got, emb) < 1e-5
+    for k, gq in grads.items():
+        assert rel(gq, leaf[k].grad) < 2e-5, k
+
+
+# ------------------------------------------------------------------------------------------
+# whole train step
+# ------------------------------------------------------------------------------------------
+def build(name, dev, precision):
+    import importlib
+    mod = importlib.import_module(f"tinydiff.{name}")
+    torch.manual_seed(0)
+    model = mod.NoiseModel()
+    model.load_state_dict(init_state_dict(name), strict=True)
+    model.precision = precision
+    return mod, model.to(dev).train()
+
+
+GRAD_TOL = {"fp32": 1e-3, "bf16": 3e-2}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["diffusion", "conditional_diffusion", "conditional_diffusion_laion"])
+def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
+    """The reference's five train-step statements (diffusion.py:220-236) with the drop-in classes."""
+    g = golden(name)
+    mod, model = build(name, dev, precision)
+    B = g["x_t"].shape[0]
+    sd = init_state_dict(name)
+    inp = make_inputs(name, B)
+    fp = mod.ForwardProcess()
+    loss_ref, grads_ref, stats_ref, pred_ref = O.unet_loss_and_grads(SPECS[name], sd, inp["x0"], inp["t"], inp["noise"],
+                                                                    fp.alphas_cumprod, inp.get("cond"))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x_t, noise = fp.q_sample(dev, inp["x0"], inp["t"].to(dev), noise=inp["noise"])
+    args = [x_t, inp["t"].to(dev)] + ([inp["cond"].to(dev)] if "cond" in inp else [])
+    pred = model(*args)
+    loss = F.mse_loss(pred, noise)
+    opt.zero_grad()
+    loss.backward()
+    etol = 1e-4 if precision == "fp32" else 1e-2
+    assert rel(pred.detach(), pred_ref) < etol
+    if "eps_train" in g:
+        assert rel(pred.detach(), g["eps_train"]) < etol
+    assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < (1e-5 if precision == "fp32" else 1e-2)
+    worst = {}
+    for k, p in model.named_parameters():
+        ref = grads_ref[k]
+        if float(ref.norm()) < 1e-6:          # conv bias in front of a train-mode BN: mathematically zero
+            assert float(p.grad.abs().max()) < 1e-5, k
+            continue
+        worst[k] = rel(p.grad, ref)
+    tol = GRAD_TOL[precision]
+    bad = {k: v for k, v in worst.items() if v > tol}
+    assert not bad, f"gradient mismatch: {bad}"
+    # BatchNorm running statistics after one train-mode forward
+    for k, v in stats_ref.items():
+        got = dict(model.named_buffers())[k]
+        if k.endswith("num_batches_tracked"):
+            assert int(got) == int(v), k
+        else:
+            assert rel(got, v) < (1e-5 if precision == "fp32" else 2e-3), k
+    opt.step()
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_train_step_vs_oracle_adam(dev, precision, use_graph):
+    """TrainStep (fused, no autograd): two steps, parameters against the oracle's Adam updates."""
+    from tinydiff.train import TrainStep
+    name = "conditional_diffusion"
+    mod, model = build(name, dev, precision)
+    B = 6
+    sd = {k: v.clone() for k, v in init_state_dict(name).items()}
+    fp = mod.ForwardProcess()
+    ts = TrainStep(model, fp, B, dev, lr=1e-3, use_graph=use_graph)
+    m = {k: torch.zeros_like(v) for k, v in sd.items() if O.is_param(k)}
+    v_ = {k: torch.zeros_like(v) for k, v in sd.items() if O.is_param(k)}
+    for step in (1, 2):
+        inp = make_inputs(name, B, seed=500 + step)
+        loss_ref, grads_ref, stats_ref, _ = O.unet_loss_and_grads(O.UNET_COND, sd, inp["x0"], inp["t"], inp["noise"],
+                                                                fp.alphas_cumprod, inp["cond"])
+        loss = ts(inp["x0"], inp["cond"], t=inp["t"], noise=inp["noise"])
+        assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < (1e-5 if precision == "fp32" else 2e-2)
+        for k in m:
+            g_ = grads_ref[k]
+            if float(g_.norm()) < 1e-6:
+                g_ = torch.zeros_like(g_)       # see DESIGN.md: zero-gradient conv biases
+            sd[k], m[k], v_[k] = O.adam_step(sd[k], g_, m[k], v_[k], step)
+        sd.update(stats_ref)
+    got = model.state_dict()
+    # Adam's first steps move every weight by ~lr regardless of gradient scale, so compare the
+    # *update* direction loosely and the parameters tightly
+    init = init_state_dict(name)
+    for k in m:
+        if float(grads_ref[k].norm()) < 1e-6:
+            continue
+        upd_ref, upd = sd[k] - init[k], got[k].cpu() - init[k]
+        assert rel(upd, upd_ref) < (2e-2 if precision == "fp32" else 0.35), k
+        assert rel(got[k], sd[k]) < 5e-3, k

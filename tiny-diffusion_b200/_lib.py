@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtinydiff.so")
 
 TD_F32, TD_BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 CONV_SIMT, CONV_TC, CONV_DIRECT = 0, 1, 2
 
 _P = C.c_void_p
@@ -24,7 +25,30 @@ class EmbedArgs(C.Structure):
     _fields_ = [("batch", C.c_int), ("dim", C.c_int), ("in_mode", C.c_int), ("proj_out", C.c_int),
                 ("t", _P), ("t_dev", _P), ("w0", _P), ("b0", _P), ("w2", _P), ("b2", _P),
                 ("y", _P), ("class_table", _P), ("text", _P), ("proj_w", _P), ("proj_b", _P),
-                ("emb_out", _P), ("h_out", _P), ("proj_out_ptr", _P)]
+                ("saved", _P), ("proj_out_ptr", _P)]
+
+
+class EmbedGrads(C.Structure):
+    _fields_ = [("d_proj", _P), ("scratch", _P), ("d_w0", _P), ("d_b0", _P), ("d_w2", _P), ("d_b2", _P),
+                ("d_class_table", _P), ("num_classes", C.c_int), ("d_proj_w", _P), ("d_proj_b", _P)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("batch", C.c_int), ("height", C.c_int), ("width", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
+                ("x_dtype", C.c_int), ("dy_dtype", C.c_int),
+                ("x", _P), ("ldx", C.c_int), ("x_coff", C.c_int), ("x_nchw", C.c_int),
+                ("dy", _P), ("lddy", C.c_int), ("dy_coff", C.c_int), ("dy_nchw", C.c_int),
+                ("dw", _P), ("workspace", _P)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+                ("A", _P), ("a_rs", C.c_int64), ("a_cs", C.c_int64),
+                ("B", _P), ("b_rs", C.c_int64), ("b_cs", C.c_int64),
+                ("C", _P), ("ldc", C.c_int64), ("alpha", C.c_float), ("bias", _P), ("act", C.c_int),
+                ("pre_out", _P), ("ld_pre", C.c_int64), ("residual", _P), ("ldr", C.c_int64),
+                ("gather_idx", _P), ("gather_table", _P), ("ld_table", C.c_int64),
+                ("accumulate", C.c_int), ("splitk_ws", _P)]
 
 
 class ConvDesc(C.Structure):
@@ -48,7 +72,9 @@ _SIGS = {
     "td_counter_add": (C.c_int, [_P, C.c_int32, _P]),
     "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, C.c_float,
                                 C.c_float, C.c_float, _P, _P, _P]),
+    "td_embed_head_saved_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "td_embed_head_fwd": (C.c_int, [C.POINTER(EmbedArgs), _P]),
+    "td_embed_head_bwd": (C.c_int, [C.POINTER(EmbedArgs), C.POINTER(EmbedGrads), _P]),
     "td_conv3x3_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), C.c_int]),
     "td_conv3x3_run": (C.c_int, [_P, _P]),
     "td_conv3x3_plan_destroy": (None, [_P]),
@@ -59,6 +85,38 @@ _SIGS = {
     "td_resize_bilinear_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_cast_f32_to_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
     "td_pack_conv_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "td_pack_conv_weight_dgrad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "td_conv3x3_wgrad_workspace": (C.c_int64, [C.POINTER(WgradDesc), C.c_int]),
+    "td_conv3x3_wgrad_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(WgradDesc), C.c_int]),
+    "td_conv3x3_wgrad_run": (C.c_int, [_P, _P]),
+    "td_conv3x3_wgrad_plan_destroy": (None, [_P]),
+    "td_chan_reduce_rows": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
+    "td_bn_stats": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P,
+                                 _P, _P, _P, _P]),
+    "td_bn_relu_apply": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
+    "td_bn_relu_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_bwd_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "td_bn_relu_bwd_apply": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_resize_bilinear_bwd": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, _P]),
+    "td_upcat_bwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_int, C.c_int, _P]),
+    "td_partial_sum": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "td_nchw_chansum": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "td_gemm_f32_workspace": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "td_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "td_colsum_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "td_act_bwd_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    "td_embedding_bwd": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_time_features": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "td_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
+    "td_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "td_bn1d_fwd": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_float,
+                              C.c_float, C.c_int, C.c_int, _P]),
+    "td_bn1d_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int,
+                              C.c_int, C.c_int, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -19,7 +19,20 @@ struct td_conv_plan {
     int split_k;
 };
 
+struct td_wgrad_plan {
+    td_wgrad_desc d;
+    int engine;
+    int splits;
+    // --- tcgen05 engine state (conv_wgrad_tc.cu) ---
+    CUtensorMap tmap_m, tmap_n;
+    int bw, bh, bn, rows, tiles_w, tiles_h, tiles_n;
+    int x_on_m, block_n, m_tiles, n_tiles, m_boxes, n_boxes, stages, boxes_per_split, smem_bytes;
+};
+
 namespace td {
+int wgrad_tc_splits(const td_wgrad_desc& d);                      // conv_wgrad_tc.cu
+int wgrad_tc_plan_init(td_wgrad_plan* p);                         // conv_wgrad_tc.cu
+int wgrad_tc_plan_run(const td_wgrad_plan* p, cudaStream_t s);    // conv_wgrad_tc.cu
 int tc_plan_init(td_conv_plan* p);                       // conv_tc.cu
 int tc_plan_run(const td_conv_plan* p, cudaStream_t s);   // conv_tc.cu
 }

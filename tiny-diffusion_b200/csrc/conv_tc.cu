@@ -170,7 +170,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn get_encode_fn() {
+EncodeTiledFn tc_get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -209,7 +209,7 @@ int tc_plan_init(td_conv_plan* p) {
         set_error("tc conv: tensors must be 16-byte aligned");
         return TD_ERR_ARG;
     }
-    EncodeTiledFn encode = get_encode_fn();
+    EncodeTiledFn encode = tc_get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TD_ERR_DRIVER; }
 
     // spatial box: maximise useful rows per 128-row MMA tile

@@ -1,0 +1,206 @@
+// Weight gradient of the 3x3 convolutions (backward of diffusion.py:28-98):
+//   dW[o, c, ky, kx] = sum_{b,h,w} dY[b,h,w,o] * X[b, h+ky-1, w+kx-1, c]
+// as an implicit GEMM with M = Cout, N = 9*Cin, K = B*H*W pixels, split along K across CTAs.
+// Partials go to a workspace [splits][Cout][9*Cin]; a second kernel sums them in fixed order
+// (deterministic) and writes PyTorch's OIHW layout.
+//   TD_CONV_SIMT : fp32 FFMA, any shape / dtype / NCHW boundary tensors (parity path, first/last conv)
+//   TD_CONV_TC   : tcgen05, conv_wgrad_tc.cu
+#include "conv_plan.h"
+
+namespace td {
+
+constexpr int WG_BM = 64, WG_BN = 64, WG_BK = 16, WG_THREADS = 256;
+
+template <typename Tx, typename Tdy>
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_simt_kernel(const td_wgrad_desc d, int pixels_per_split) {
+    __shared__ float As[WG_BK][WG_BM + 4];   // dY  [k = pixel][i = cout]
+    __shared__ float Bs[WG_BK][WG_BN + 4];   // X   [k = pixel][j = tap*cin + c]
+    const Tx* __restrict__ x = reinterpret_cast<const Tx*>(d.x);
+    const Tdy* __restrict__ dy = reinterpret_cast<const Tdy*>(d.dy);
+    const int N = 9 * d.cin;
+    const int64_t P = (int64_t)d.batch * d.height * d.width;
+    const int n0 = blockIdx.x * WG_BN, m0 = blockIdx.y * WG_BM;
+    const int64_t pbeg = (int64_t)blockIdx.z * pixels_per_split;
+    const int64_t pend = min(P, pbeg + pixels_per_split);
+    const int tid = threadIdx.x;
+    const int li = tid & 63, lk = tid >> 6;          // loader: column li, pixel rows lk, lk+4, lk+8, lk+12
+    const int ty = tid >> 4, tx = tid & 15;
+
+    // the B column this thread loads is fixed: tap / channel decomposition once
+    const int jn = n0 + li;
+    const bool jvalid = jn < N;
+    const int tap = jvalid ? jn / d.cin : 0, cc = jvalid ? jn - tap * d.cin : 0;
+    const int ddy = tap / 3 - 1, ddx = tap % 3 - 1;
+    const int io = m0 + li;
+    const bool ivalid = io < d.cout;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int64_t p0 = pbeg; p0 < pend; p0 += WG_BK) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int k = lk + l * 4;
+            const int64_t p = p0 + k;
+            float av = 0.f, bv = 0.f;
+            if (p < pend) {
+                const int w_ = (int)(p % d.width);
+                const int64_t r = p / d.width;
+                const int h_ = (int)(r % d.height);
+                const int b_ = (int)(r / d.height);
+                if (ivalid) {
+                    av = d.dy_nchw ? to_f32(dy[(((int64_t)b_ * d.cout + io) * d.height + h_) * d.width + w_])
+                                   : to_f32(dy[p * d.lddy + d.dy_coff + io]);
+                }
+                const int hh = h_ + ddy, ww = w_ + ddx;
+                if (jvalid && hh >= 0 && hh < d.height && ww >= 0 && ww < d.width) {
+                    bv = d.x_nchw ? to_f32(x[(((int64_t)b_ * d.cin + cc) * d.height + hh) * d.width + ww])
+                                  : to_f32(x[(((int64_t)b_ * d.height + hh) * d.width + ww) * d.ldx + d.x_coff + cc]);
+                }
+            }
+            As[k][li] = av;
+            Bs[k][li] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < WG_BK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* ws = d.workspace + (int64_t)blockIdx.z * d.cout * N;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = m0 + ty * 4 + i;
+        if (o >= d.cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) ws[(int64_t)o * N + n] = acc[i][j];
+        }
+    }
+}
+
+// dw[o][c][tap] = sum_s ws[s][o][tap*cin + c]     (OHWI partials -> OIHW gradient)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
+    const int64_t total = (int64_t)cout * cin * 9;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        // iterate in OHWI order (coalesced reads); scattered 4-byte writes are absorbed by L2
+        const int c = (int)(e % cin);
+        const int64_t r = e / cin;
+        const int tap = (int)(r % 9);
+        const int o = (int)(r / 9);
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * total + e];
+        dw[((int64_t)o * cin + c) * 9 + tap] = s;
+    }
+}
+
+// OIHW fp32 -> [Cin][3][3][Cout] with the taps flipped: the weight operand of the data gradient,
+// dX = conv3x3(dY, Wd),  Wd[i][ky][kx][o] = W[o][i][2-ky][2-kx]
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weight_dgrad_kernel(const float* __restrict__ oihw, T* __restrict__ out, int cout, int cin) {
+    const int64_t total = (int64_t)cout * 9 * cin;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int o = (int)(e % cout);
+        const int64_t r = e / cout;
+        const int tap = (int)(r % 9);
+        const int i = (int)(r / 9);
+        out[e] = from_f32<T>(oihw[((int64_t)o * cin + i) * 9 + (8 - tap)]);
+    }
+}
+
+static int simt_splits(const td_wgrad_desc& d) {
+    const int64_t P = (int64_t)d.batch * d.height * d.width;
+    const int64_t base = ceil_div(9 * d.cin, WG_BN) * ceil_div(d.cout, WG_BM);
+    int64_t s = ceil_div(2 * kNumSMs, base);
+    s = std::min<int64_t>(s, std::max<int64_t>(1, P / 256));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(s, 512));
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int64_t td_conv3x3_wgrad_workspace(const td_wgrad_desc* d, int engine) {
+    if (!d) return 0;
+    const int64_t per = (int64_t)d->cout * 9 * d->cin;
+    if (engine == TD_CONV_TC) return (int64_t)wgrad_tc_splits(*d) * per;
+    return (int64_t)simt_splits(*d) * per;
+}
+
+extern "C" int td_conv3x3_wgrad_plan_create(td_wgrad_plan** plan, const td_wgrad_desc* desc, int engine) {
+    TD_CHECK_ARG(plan && desc, "wgrad plan: null pointer");
+    const td_wgrad_desc& d = *desc;
+    TD_CHECK_ARG(d.batch > 0 && d.height > 0 && d.width > 0 && d.cin > 0 && d.cout > 0, "wgrad plan: bad sizes");
+    TD_CHECK_ARG(d.x && d.dy && d.dw && d.workspace, "wgrad plan: null tensor pointer");
+    td_wgrad_plan* p = new td_wgrad_plan();
+    memset(p, 0, sizeof(*p));
+    p->d = d;
+    p->engine = engine;
+    int st = TD_OK;
+    if (engine == TD_CONV_TC) {
+        st = wgrad_tc_plan_init(p);
+    } else if (engine == TD_CONV_SIMT) {
+        p->splits = simt_splits(d);
+    } else {
+        set_error("wgrad plan: unknown engine %d", engine);
+        st = TD_ERR_ARG;
+    }
+    if (st != TD_OK) { delete p; return st; }
+    *plan = p;
+    return TD_OK;
+}
+
+extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(p, "td_conv3x3_wgrad_run: null plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    const td_wgrad_desc& d = p->d;
+    if (p->engine == TD_CONV_TC) {
+        int st = wgrad_tc_plan_run(p, s);
+        if (st != TD_OK) return st;
+    } else {
+        const int64_t P = (int64_t)d.batch * d.height * d.width;
+        const int per = (int)(ceil_div(ceil_div(P, p->splits), WG_BK) * WG_BK);
+        dim3 grid((unsigned)ceil_div(9 * d.cin, WG_BN), (unsigned)ceil_div(d.cout, WG_BM), (unsigned)p->splits);
+        if (d.x_dtype == TD_F32 && d.dy_dtype == TD_F32) wgrad_simt_kernel<float, float><<<grid, WG_THREADS, 0, s>>>(d, per);
+        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_BF16) wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, WG_THREADS, 0, s>>>(d, per);
+        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_F32) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, WG_THREADS, 0, s>>>(d, per);
+        else wgrad_simt_kernel<float, __nv_bfloat16><<<grid, WG_THREADS, 0, s>>>(d, per);
+        int st = launch_status("wgrad_simt");
+        if (st != TD_OK) return st;
+    }
+    const int64_t total = (int64_t)d.cout * d.cin * 9;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8));
+    wgrad_reduce_kernel<<<grid, 256, 0, s>>>(d.workspace, p->splits, d.cout, d.cin, d.dw);
+    return launch_status("wgrad_reduce");
+}
+
+extern "C" void td_conv3x3_wgrad_plan_destroy(td_wgrad_plan* p) { delete p; }
+
+extern "C" int td_pack_conv_weight_dgrad(const float* oihw, void* out, int out_dtype, int cout, int cin, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(oihw && out && cout > 0 && cin > 0, "td_pack_conv_weight_dgrad: bad args");
+    const int64_t n = (int64_t)cout * cin * 9;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), kNumSMs * 16));
+    if (out_dtype == TD_BF16)
+        pack_weight_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(oihw, (__nv_bfloat16*)out, cout, cin);
+    else if (out_dtype == TD_F32)
+        pack_weight_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(oihw, (float*)out, cout, cin);
+    else
+        TD_CHECK_ARG(false, "td_pack_conv_weight_dgrad: unknown dtype %d", out_dtype);
+    return launch_status("pack_conv_weight_dgrad");
+}

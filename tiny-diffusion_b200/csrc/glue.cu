@@ -127,120 +127,6 @@ resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi,
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Conditioning head.  One CTA handles kS samples so each weight row is read once per kS samples;
-// one warp per output row, lanes stride the reduction dimension (coalesced), shuffle reduce.
-// ---------------------------------------------------------------------------------------------
-constexpr int kS = 4;
-constexpr int kEmbThreads = 512;
-
-__device__ inline float silu(float x) { return x / (1.0f + expf(-x)); }
-
-__global__ void __launch_bounds__(kEmbThreads)
-embed_head_kernel(td_embed_args a) {
-    extern __shared__ float sm[];
-    const int D = a.dim;
-    float* in0 = sm;               // [kS][D]   sinusoidal input (in_mode 2) else [kS] scalars
-    float* h = sm + kS * D;        // [kS][D]
-    float* e = sm + 2 * kS * D;    // [kS][D]
-    const int b0 = blockIdx.x * kS;
-    const int ns = min(kS, a.batch - b0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-
-    float tval[kS];
-#pragma unroll
-    for (int s = 0; s < kS; ++s) {
-        float tv = 0.f;
-        if (s < ns) tv = a.t ? (float)a.t[b0 + s] : (float)a.t_dev[0];
-        if (a.in_mode == 1) tv = tv / 1000.0f;
-        tval[s] = tv;
-    }
-    if (a.in_mode == 2) {
-        const int half = D / 2;
-        const float lg = logf(10000.0f);
-        for (int i = threadIdx.x; i < kS * D; i += blockDim.x) {
-            int s = i / D, j = i % D;
-            int jj = (j < half) ? j : j - half;
-            float v = 0.f;
-            if (jj < half && j < 2 * half) {
-                float fr = expf(-lg * (float)jj / (float)(half - 1));
-                float arg = tval[s] * fr;
-                v = (j < half) ? sinf(arg) : cosf(arg);
-            }
-            in0[i] = v;
-        }
-        __syncthreads();
-        for (int j = warp; j < D; j += nw) {
-            float acc[kS] = {0.f, 0.f, 0.f, 0.f};
-            const float* wr = a.w0 + (int64_t)j * D;
-            for (int i = lane; i < D; i += 32) {
-                float w = wr[i];
-#pragma unroll
-                for (int s = 0; s < kS; ++s) acc[s] += w * in0[s * D + i];
-            }
-#pragma unroll
-            for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
-            if (lane == 0) {
-#pragma unroll
-                for (int s = 0; s < kS; ++s) {
-                    float pre = acc[s] + a.b0[j];
-                    if (a.h_out && s < ns) a.h_out[(int64_t)(b0 + s) * D + j] = pre;
-                    h[s * D + j] = silu(pre);
-                }
-            }
-        }
-    } else {
-        for (int i = threadIdx.x; i < kS * D; i += blockDim.x) {
-            int s = i / D, j = i % D;
-            float pre = a.w0[j] * tval[s] + a.b0[j];      // Linear(1, D)
-            if (a.h_out && s < ns) a.h_out[(int64_t)(b0 + s) * D + j] = pre;
-            h[i] = silu(pre);
-        }
-    }
-    __syncthreads();
-    for (int j = warp; j < D; j += nw) {
-        float acc[kS] = {0.f, 0.f, 0.f, 0.f};
-        const float* wr = a.w2 + (int64_t)j * D;
-        for (int i = lane; i < D; i += 32) {
-            float w = wr[i];
-#pragma unroll
-            for (int s = 0; s < kS; ++s) acc[s] += w * h[s * D + i];
-        }
-#pragma unroll
-        for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < kS; ++s) {
-                float v = acc[s] + a.b2[j];
-                if (s < ns) {
-                    if (a.y && a.class_table) v += a.class_table[(int64_t)a.y[b0 + s] * D + j];
-                    if (a.text) v += a.text[(int64_t)(b0 + s) * D + j];
-                    if (a.emb_out) a.emb_out[(int64_t)(b0 + s) * D + j] = v;
-                }
-                e[s * D + j] = v;
-            }
-        }
-    }
-    __syncthreads();
-    for (int j = warp; j < a.proj_out; j += nw) {
-        float acc[kS] = {0.f, 0.f, 0.f, 0.f};
-        const float* wr = a.proj_w + (int64_t)j * D;
-        for (int i = lane; i < D; i += 32) {
-            float w = wr[i];
-#pragma unroll
-            for (int s = 0; s < kS; ++s) acc[s] += w * e[s * D + i];
-        }
-#pragma unroll
-        for (int s = 0; s < kS; ++s) acc[s] = warp_sum(acc[s]);
-        if (lane == 0) {
-            const float pb = a.proj_b[j];
-#pragma unroll
-            for (int s = 0; s < kS; ++s)
-                if (s < ns) a.proj_out_ptr[(int64_t)(b0 + s) * a.proj_out + j] = acc[s] + pb;
-        }
-    }
-}
-
 // OIHW fp32 -> OHWI (fp32 or bf16)
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -336,24 +222,6 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
         TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
     }
     return launch_status("resize_bilinear");
-}
-
-extern "C" int td_embed_head_fwd(const td_embed_args* a, void* stream) {
-    TD_REQUIRE_ARCH();
-    TD_CHECK_ARG(a, "td_embed_head_fwd: null args");
-    TD_CHECK_ARG(a->batch > 0 && a->dim > 0 && a->dim <= 1024, "td_embed_head_fwd: bad batch/dim");
-    TD_CHECK_ARG(a->t || a->t_dev, "td_embed_head_fwd: need t or t_dev");
-    TD_CHECK_ARG(a->w0 && a->b0 && a->w2 && a->b2, "td_embed_head_fwd: null weights");
-    TD_CHECK_ARG(a->proj_out == 0 || (a->proj_w && a->proj_b && a->proj_out_ptr), "td_embed_head_fwd: null projection");
-    TD_CHECK_ARG(a->in_mode >= 0 && a->in_mode <= 2, "td_embed_head_fwd: bad in_mode");
-    const size_t smem = (size_t)3 * kS * a->dim * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        TD_CUDA(cudaFuncSetAttribute(embed_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
-    embed_head_kernel<<<(a->batch + kS - 1) / kS, kEmbThreads, smem, (cudaStream_t)stream>>>(*a);
-    return launch_status("embed_head");
 }
 
 extern "C" int td_pack_conv_weight(const float* oihw, void* ohwi, int out_dtype, int cout, int cin, void* stream) {

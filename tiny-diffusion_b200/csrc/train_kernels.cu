@@ -1,0 +1,551 @@
+// Train-mode kernels of the conv UNet (all HBM-bound, NHWC, 16-byte vector accesses):
+//   BatchNorm2d batch statistics / finalize / apply+ReLU and its two-pass backward
+//   (diffusion.py:34-35 in train mode), MaxPool2d backward, the transposes of the bilinear
+//   resizes (decoder concat assembly, final 32->28 resize) and per-channel sums (bias gradients).
+// Reductions are deterministic: every CTA writes its partial to its own row, a finalize kernel
+// sums the rows in fixed order (in double).
+#include "common.cuh"
+
+namespace td {
+
+constexpr int kT = 256;
+
+struct Bil { int i0, i1; float l0, l1; };
+// identical to the forward helper in glue.cu (align_corners=True)
+__device__ inline Bil bil_t(int dst, int in, int out) {
+    Bil b;
+    const float scale = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    const float src = scale * (float)dst;
+    b.i0 = min((int)floorf(src), in - 1);
+    b.l1 = fminf(fmaxf(src - (float)b.i0, 0.f), 1.f);
+    b.l0 = 1.f - b.l1;
+    b.i1 = b.i0 + ((b.i0 < in - 1) ? 1 : 0);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel partial sums over pixels.
+//   MODE 0: s1 = sum x,           s2 = sum x^2            (BatchNorm batch statistics)
+//   MODE 1: s1 = sum g,           s2 = sum g * y          (BatchNorm backward), g = da * [y*scale+shift > 0]
+// thread layout: lanesC = C / V channel-vector lanes, rows = kT / lanesC pixel rows per CTA pass.
+// partials: [gridDim.x][2][C]
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kT)
+chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const T* __restrict__ y, int64_t P, int C,
+                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ partials) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ float red[];               // [rows][2*C]
+    const int lanesC = C / V;
+    const int rows = kT / lanesC;
+    const int lane = threadIdx.x % lanesC, row = threadIdx.x / lanesC;
+    const int c0 = lane * V;
+    float s1[V], s2[V], sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = 1.f; sh[k] = 0.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+    }
+    if (row < rows) {
+        for (int64_t p = (int64_t)blockIdx.x * rows + row; p < P; p += (int64_t)gridDim.x * rows) {
+            float f[V];
+            if (MODE == 0) {
+                Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
+#pragma unroll
+                for (int k = 0; k < V; ++k) { s1[k] += f[k]; s2[k] = fmaf(f[k], f[k], s2[k]); }
+            } else {
+                float yy[V];
+                Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
+                Vec<T>::load(y + p * C + c0).unpack(yy);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float g = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? f[k] : 0.f;
+                    s1[k] += g;
+                    s2[k] = fmaf(g, yy[k], s2[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            red[(size_t)row * 2 * C + c0 + k] = s1[k];
+            red[(size_t)row * 2 * C + C + c0 + k] = s2[k];
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * C; j += kT) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += red[(size_t)r * 2 * C + j];
+        partials[(size_t)blockIdx.x * 2 * C + j] = t;
+    }
+}
+
+// BatchNorm2d train-mode finalize (diffusion.py:34): batch mean / biased variance -> the affine
+// used by the apply pass; running statistics updated like torch (momentum, unbiased variance,
+// conv bias folded into the mean only).
+__global__ void __launch_bounds__(128)
+bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double count, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
+                   float* __restrict__ save_invstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt) nbt[0] += 1;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < nrows; ++r) {
+        s1 += (double)partials[(size_t)r * 2 * C + c];
+        s2 += (double)partials[(size_t)r * 2 * C + C + c];
+    }
+    const double mean = s1 / count;
+    double var = s2 / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = invstd;
+    if (running_mean) {
+        const float mb = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mb;
+    }
+    if (running_var) {
+        const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// a = relu(y * scale + shift)
+template <typename T>
+__global__ void __launch_bounds__(kT)
+bn_relu_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                     T* __restrict__ a, int64_t lda, int a_coff, int64_t P, int C, int relu) {
+    constexpr int V = Vec<T>::N;
+    const int lanesC = C / V;
+    const int64_t total = P * lanesC;
+    const int64_t stride = (int64_t)gridDim.x * kT;       // multiple of lanesC -> channel group is loop invariant
+    int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+    const int c0 = (int)(i % lanesC) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+    for (; i < total; i += stride) {
+        const int64_t p = i / lanesC;
+        float f[V];
+        Vec<T>::load(y + p * C + c0).unpack(f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            f[k] = fmaf(f[k], sc[k], sh[k]);
+            if (relu) f[k] = fmaxf(f[k], 0.f);
+        }
+        Vec<T>::pack(f).store(a + p * lda + a_coff + c0);
+    }
+}
+
+// BatchNorm backward coefficients: dy = cA*g + cB*y + cC (see bn_relu_bwd_apply_kernel)
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double count,
+                       const float* __restrict__ scale, const float* __restrict__ save_mean,
+                       const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < nrows; ++r) {
+        s1 += (double)partials[(size_t)r * 2 * C + c];
+        s2 += (double)partials[(size_t)r * 2 * C + C + c];
+    }
+    const double mean = save_mean[c], invstd = save_invstd[c], sc = scale[c];
+    const double dg = (s2 - mean * s1) * invstd;       // sum g * xhat
+    dgamma[c] = (float)dg;
+    dbeta[c] = (float)s1;
+    const double cB = -sc * invstd * dg / count;
+    coef[c] = (float)sc;
+    coef[C + c] = (float)cB;
+    coef[2 * C + c] = (float)(-sc * s1 / count - cB * mean);
+}
+
+// dy = scale*(g - mean(g) - xhat*mean(g*xhat)) = cA*g + cB*y + cC,  g = da * [y*scale+shift > 0]
+template <typename T>
+__global__ void __launch_bounds__(kT)
+bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const T* __restrict__ y,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ coef, T* __restrict__ dy, int64_t P, int C) {
+    constexpr int V = Vec<T>::N;
+    const int lanesC = C / V;
+    const int64_t total = P * lanesC;
+    const int64_t stride = (int64_t)gridDim.x * kT;
+    int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+    const int c0 = (int)(i % lanesC) * V;
+    float sc[V], sh[V], cA[V], cB[V], cC[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k];
+        cA[k] = coef[c0 + k]; cB[k] = coef[C + c0 + k]; cC[k] = coef[2 * C + c0 + k];
+    }
+    for (; i < total; i += stride) {
+        const int64_t p = i / lanesC;
+        float g[V], yy[V];
+        Vec<T>::load(da + p * ldda + da_coff + c0).unpack(g);
+        Vec<T>::load(y + p * C + c0).unpack(yy);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float gm = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            g[k] = fmaf(cA[k], gm, fmaf(cB[k], yy[k], cC[k]));
+        }
+        Vec<T>::pack(g).store(dy + p * C + c0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool2d(2, ceil_mode) backward, gather form: an input pixel receives the window's gradient
+// iff it is the first maximum in (h, w) scan order (ATen's tie rule).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kT)
+maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
+                    int Ho, int Wo, int accumulate) {
+    constexpr int V = Vec<T>::N;
+    const int cv = C / V;
+    const int64_t total = (int64_t)B * H * W * cv;
+    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+        const int c = (int)(i % cv) * V;
+        int64_t p = i / cv;
+        const int w = (int)(p % W); p /= W;
+        const int h = (int)(p % H);
+        const int b = (int)(p / H);
+        const int ho = h >> 1, wo = w >> 1;
+        float out[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) out[k] = 0.f;
+        if (ho < Ho && wo < Wo) {
+            float best[V];
+            int arg[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) { best[k] = -INFINITY; arg[k] = -1; }
+#pragma unroll
+            for (int dyy = 0; dyy < 2; ++dyy) {
+                const int hh = 2 * ho + dyy;
+                if (hh >= H) continue;
+#pragma unroll
+                for (int dxx = 0; dxx < 2; ++dxx) {
+                    const int ww = 2 * wo + dxx;
+                    if (ww >= W) continue;
+                    float f[V];
+                    Vec<T>::load(x + (((int64_t)b * H + hh) * W + ww) * C + c).unpack(f);
+#pragma unroll
+                    for (int k = 0; k < V; ++k)
+                        if (f[k] > best[k] || arg[k] < 0) { best[k] = f[k]; arg[k] = dyy * 2 + dxx; }
+                }
+            }
+            const int me = (h & 1) * 2 + (w & 1);
+            float g[V];
+            Vec<T>::load(dy + (((int64_t)b * Ho + ho) * Wo + wo) * C + c).unpack(g);
+#pragma unroll
+            for (int k = 0; k < V; ++k) out[k] = (arg[k] == me) ? g[k] : 0.f;
+        }
+        T* dst = dx + (((int64_t)b * H + h) * W + w) * C + c;
+        if (accumulate) {
+            float prev[V];
+            Vec<T>::load(dst).unpack(prev);
+#pragma unroll
+            for (int k = 0; k < V; ++k) out[k] += prev[k];
+        }
+        Vec<T>::pack(out).store(dst);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Transposed bilinear resize (gather form, deterministic): dx[b,hi,wi,:] = sum over the output
+// pixels that read (hi,wi) of weight * dy.  dy: [B,Ho,Wo,ld] at channel offset coff.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ inline void resize_bwd_pixel(const T* __restrict__ dy, int64_t ld, int coff, int b, int Hi, int Wi, int Ho,
+                                        int Wo, int hi, int wi, int c, float* acc) {
+    constexpr int V = Vec<T>::N;
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    if (Hi == Ho && Wi == Wo) {
+        Vec<T>::load(dy + (((int64_t)b * Ho + hi) * Wo + wi) * ld + coff + c).unpack(acc);
+        return;
+    }
+    // candidate output range (conservative), exact membership re-tested with the forward helper
+    const float sh = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    const float sw = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    int oh_lo = 0, oh_hi = Ho - 1, ow_lo = 0, ow_hi = Wo - 1;
+    if (sh > 0.f) { oh_lo = max(0, (int)floorf((hi - 1) / sh) - 1); oh_hi = min(Ho - 1, (int)ceilf((hi + 1) / sh) + 1); }
+    if (sw > 0.f) { ow_lo = max(0, (int)floorf((wi - 1) / sw) - 1); ow_hi = min(Wo - 1, (int)ceilf((wi + 1) / sw) + 1); }
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        const Bil bh = bil_t(oh, Hi, Ho);
+        const float wh = (bh.i0 == hi ? bh.l0 : 0.f) + (bh.i1 == hi ? bh.l1 : 0.f);
+        if (wh == 0.f) continue;
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            const Bil bw = bil_t(ow, Wi, Wo);
+            const float ww = (bw.i0 == wi ? bw.l0 : 0.f) + (bw.i1 == wi ? bw.l1 : 0.f);
+            if (ww == 0.f) continue;
+            float g[V];
+            Vec<T>::load(dy + (((int64_t)b * Ho + oh) * Wo + ow) * ld + coff + c).unpack(g);
+            const float wgt = wh * ww;
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT)
+resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
+                  int Wo, int C) {
+    constexpr int V = Vec<T>::N;
+    const int cv = C / V;
+    const int64_t total = (int64_t)B * Hi * Wi * cv;
+    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+        const int c = (int)(i % cv) * V;
+        int64_t p = i / cv;
+        const int wi = (int)(p % Wi); p /= Wi;
+        const int hi = (int)(p % Hi);
+        const int b = (int)(p / Hi);
+        float acc[V];
+        resize_bwd_pixel<T>(dy, ld, coff, b, Hi, Wi, Ho, Wo, hi, wi, c, acc);
+        Vec<T>::pack(acc).store(dx + (((int64_t)b * Hi + hi) * Wi + wi) * C + c);
+    }
+}
+
+// d_temb[b, off + c] = sum over the Ho*Wo output pixels of d_out[b, :, :, Cu + c]   (one CTA per sample)
+template <typename T>
+__global__ void __launch_bounds__(kT)
+temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restrict__ dtemb, int ld_temb, int temb_off,
+                int HW, int Cs) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ float red[];               // [rows][Cs]
+    const int lanesC = Cs / V;
+    const int rows = kT / lanesC;
+    const int lane = threadIdx.x % lanesC, row = threadIdx.x / lanesC;
+    const int b = blockIdx.x;
+    float s[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = 0.f;
+    if (row < rows) {
+        for (int p = row; p < HW; p += rows) {
+            float f[V];
+            Vec<T>::load(dout + ((int64_t)b * HW + p) * ld + coff + lane * V).unpack(f);
+#pragma unroll
+            for (int k = 0; k < V; ++k) s[k] += f[k];
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) red[(size_t)row * Cs + lane * V + k] = s[k];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < Cs; j += kT) {
+        float t = 0.f;
+        for (int r = 0; r < rows; ++r) t += red[(size_t)r * Cs + j];
+        dtemb[(int64_t)b * ld_temb + temb_off + j] = t;
+    }
+}
+
+// out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials)
+__global__ void __launch_bounds__(128)
+partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int which, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += (double)partials[(size_t)r * 2 * C + which * C + c];
+    out[c] = (float)s;
+}
+
+// per-channel sum of an NCHW fp32 tensor (final_conv bias gradient): grid (C), fixed-order tree
+__global__ void __launch_bounds__(kT)
+nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ out) {
+    __shared__ double red[kT];
+    const int c = blockIdx.x;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < (int64_t)B * HW; i += kT) {
+        const int b = (int)(i / HW), p = (int)(i % HW);
+        s += (double)x[((int64_t)b * C + c) * HW + p];
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = kT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = (float)red[0];
+}
+
+static inline int reduce_grid(int64_t P, int rows) {
+    const int64_t want = ceil_div(P, (int64_t)rows * 8);     // >= 8 pixel rows per thread
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * 4));
+}
+static inline int stream_grid(int64_t items, int lanesC) {
+    // grid * kT must stay a multiple of lanesC (kT is, for every power-of-two lanesC <= kT)
+    (void)lanesC;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, kT), (int64_t)kNumSMs * 16));
+}
+static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace td
+
+using namespace td;
+
+#define TD_DISPATCH_T(dtype, ...)                                       \
+    if ((dtype) == TD_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }   \
+    else if ((dtype) == TD_F32) { using T = float; __VA_ARGS__; }       \
+    else { TD_CHECK_ARG(false, "unknown dtype %d", (int)(dtype)); }
+
+static int check_lanes(const char* what, int dtype, int C) {
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    TD_CHECK_ARG(C % V == 0 && pow2(C / V) && C / V <= kT, "%s: channel count %d unsupported", what, C);
+    return TD_OK;
+}
+
+extern "C" int td_chan_reduce_rows(int dtype, int64_t pixels, int channels) {
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    const int lanesC = std::max(1, channels / V);
+    return reduce_grid(pixels, std::max(1, kT / lanesC));
+}
+
+extern "C" int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, int64_t pixels, int channels,
+                           float* partials, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && partials && pixels > 0, "td_bn_stats: bad args");
+    if (int st = check_lanes("td_bn_stats", dtype, channels)) return st;
+    const int grid = td_chan_reduce_rows(dtype, pixels, channels);
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
+    TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 0><<<grid, kT, smem, (cudaStream_t)stream>>>(
+                             (const T*)x, ldx, x_coff, nullptr, pixels, channels, nullptr, nullptr, partials)));
+    return launch_status("bn_stats");
+}
+
+extern "C" int td_bn_finalize(const float* partials, int nrows, int channels, int64_t count, const float* gamma,
+                              const float* beta, const float* conv_bias, float eps, float momentum,
+                              float* running_mean, float* running_var, int64_t* num_batches_tracked, float* scale,
+                              float* shift, float* save_mean, float* save_invstd, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && gamma && beta && scale && shift && save_mean &&
+                     save_invstd, "td_bn_finalize: bad args");
+    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        partials, nrows, channels, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
+        num_batches_tracked, scale, shift, save_mean, save_invstd);
+    return launch_status("bn_finalize");
+}
+
+extern "C" int td_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
+                                int a_coff, int64_t pixels, int channels, int relu, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(y && scale && shift && a && pixels > 0, "td_bn_relu_apply: bad args");
+    if (int st = check_lanes("td_bn_relu_apply", dtype, channels)) return st;
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    const int lanesC = channels / V;
+    const int grid = stream_grid(pixels * lanesC, lanesC);
+    TD_DISPATCH_T(dtype, (bn_relu_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+                             (const T*)y, scale, shift, (T*)a, lda, a_coff, pixels, channels, relu)));
+    return launch_status("bn_relu_apply");
+}
+
+extern "C" int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int dtype,
+                                     const float* scale, const float* shift, int64_t pixels, int channels,
+                                     float* partials, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(da && y && scale && shift && partials && pixels > 0, "td_bn_relu_bwd_reduce: bad args");
+    if (int st = check_lanes("td_bn_relu_bwd_reduce", dtype, channels)) return st;
+    const int grid = td_chan_reduce_rows(dtype, pixels, channels);
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
+    TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 1><<<grid, kT, smem, (cudaStream_t)stream>>>(
+                             (const T*)da, ldda, da_coff, (const T*)y, pixels, channels, scale, shift, partials)));
+    return launch_status("bn_relu_bwd_reduce");
+}
+
+extern "C" int td_bn_bwd_finalize(const float* partials, int nrows, int channels, int64_t count, const float* scale,
+                                  const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                                  float* coef, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && scale && save_mean && save_invstd && dgamma &&
+                     dbeta && coef, "td_bn_bwd_finalize: bad args");
+    bn_bwd_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        partials, nrows, channels, (double)count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
+    return launch_status("bn_bwd_finalize");
+}
+
+extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const void* y, int dtype,
+                                    const float* scale, const float* shift, const float* coef, void* dy,
+                                    int64_t pixels, int channels, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(da && y && scale && shift && coef && dy && pixels > 0, "td_bn_relu_bwd_apply: bad args");
+    if (int st = check_lanes("td_bn_relu_bwd_apply", dtype, channels)) return st;
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    const int lanesC = channels / V;
+    const int grid = stream_grid(pixels * lanesC, lanesC);
+    TD_DISPATCH_T(dtype, (bn_relu_bwd_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+                             (const T*)da, ldda, da_coff, (const T*)y, scale, shift, coef, (T*)dy, pixels, channels)));
+    return launch_status("bn_relu_bwd_apply");
+}
+
+extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int batch, int h, int w, int c,
+                               int ceil_mode, int accumulate, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && dy && dx && batch > 0 && h > 0 && w > 0 && c > 0, "td_maxpool2_bwd: bad args");
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    TD_CHECK_ARG(c % V == 0, "td_maxpool2_bwd: channels must be a multiple of %d", V);
+    const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
+    const int grid = stream_grid((int64_t)batch * h * w * c / V, 1);
+    TD_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+                             (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
+    return launch_status("maxpool2_bwd");
+}
+
+extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff, void* dx, int dtype, int batch,
+                                      int hi, int wi, int ho, int wo, int c, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(dy && dx && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_bwd: bad args");
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    TD_CHECK_ARG(c % V == 0 && ld_dy % V == 0 && dy_coff % V == 0, "td_resize_bilinear_bwd: channels must be a multiple of %d", V);
+    const int grid = stream_grid((int64_t)batch * hi * wi * c / V, 1);
+    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+                             (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c)));
+    return launch_status("resize_bilinear_bwd");
+}
+
+extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dtemb, int ld_temb, int temb_off,
+                            int dtype, int batch, int ho, int wo, int cu, int hs, int ws, int cs, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(dout && dlow && dskip && dtemb, "td_upcat_bwd: null pointer");
+    TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0, "td_upcat_bwd: bad output size");
+    const int V = dtype == TD_BF16 ? 8 : 4;
+    TD_CHECK_ARG(cu % V == 0 && cs % V == 0, "td_upcat_bwd: channel counts must be multiples of %d", V);
+    if (int st = check_lanes("td_upcat_bwd", dtype, cs)) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ld = cu + cs;
+    {
+        const int grid = stream_grid((int64_t)batch * (ho / 2) * (wo / 2) * cu / V, 1);
+        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, s>>>((const T*)dout, ld, 0, (T*)dlow, batch, ho / 2,
+                                                                        wo / 2, ho, wo, cu)));
+    }
+    {
+        const int grid = stream_grid((int64_t)batch * hs * ws * cs / V, 1);
+        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, s>>>((const T*)dout, ld, cu, (T*)dskip, batch, hs, ws,
+                                                                        ho, wo, cs)));
+    }
+    {
+        const size_t smem = (size_t)(kT / (cs / V)) * cs * sizeof(float);
+        TD_DISPATCH_T(dtype, (temb_bwd_kernel<T><<<batch, kT, smem, s>>>((const T*)dout, ld, cu, dtemb, ld_temb, temb_off,
+                                                                         ho * wo, cs)));
+    }
+    return launch_status("upcat_bwd");
+}
+
+extern "C" int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(partials && out && nrows > 0 && channels > 0 && (which == 0 || which == 1), "td_partial_sum: bad args");
+    partial_sum_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
+    return launch_status("partial_sum");
+}
+
+extern "C" int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && out && batch > 0 && channels > 0 && hw > 0, "td_nchw_chansum: bad args");
+    nchw_chansum_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(x, batch, channels, hw, out);
+    return launch_status("nchw_chansum");
+}

@@ -88,11 +88,9 @@ class ConvUNetBase(nn.Module):
         p = next(self.parameters())
         if p.device != device:
             raise RuntimeError(f"NoiseModel parameters are on {p.device}, input on {device}")
-        if self.training and torch.is_grad_enabled():
-            from .train import unet_train_forward       # train-mode BatchNorm + autograd
-            return unet_train_forward(self, x, t, cond)
         if self.training:
-            raise RuntimeError("train-mode forward without autograd is not implemented; call .eval()")
+            from .train import unet_train_forward       # batch-statistics BatchNorm (+ autograd)
+            return unet_train_forward(self, x, t, cond)
         eng = self.engine(x.shape[0], device)
         return eng.forward(x.to(torch.float32).contiguous(), t, cond)
 

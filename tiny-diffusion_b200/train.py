@@ -1,0 +1,685 @@
+"""Training path of the conv-UNet denoisers: train-mode forward (batch-statistics BatchNorm),
+the full backward, and the fused train step (diffusion.py:220-236).
+
+``UNetTrainEngine`` is the train-mode sibling of ``unet.UNetEngine``: a fixed launch sequence of
+libtinydiff kernels over preallocated NHWC buffers, for one (batch, precision) pair.  Two ways in:
+
+* ``unet_train_forward`` -- what ``NoiseModel.forward`` calls in train mode: a
+  ``torch.autograd.Function`` whose backward runs the backward plan, so the reference's own five
+  statements (``q_sample; model(x_t, t); F.mse_loss; loss.backward(); optimizer.step()``) work
+  unchanged and ``.grad`` of every parameter is populated.
+* ``TrainStep`` -- the same work without autograd: q_sample -> forward -> MSE(+grad) -> backward ->
+  (gradient all-reduce) -> fused Adam, captured in one CUDA graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .unet import UNetConfig, _CONVS, _ConvPlan, _pool
+
+BN_EPS_DEFAULT = 1e-5
+
+
+class _WgradPlan:
+    def __init__(self, desc: L.WgradDesc, engine: int):
+        self.lib = L.load()
+        self.handle = C.c_void_p()
+        self.desc = desc
+        L.check(self.lib.td_conv3x3_wgrad_plan_create(C.byref(self.handle), C.byref(desc), engine),
+                "td_conv3x3_wgrad_plan_create")
+
+    def run(self, stream: int) -> None:
+        L.check(self.lib.td_conv3x3_wgrad_run(self.handle, stream), "td_conv3x3_wgrad_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.td_conv3x3_wgrad_plan_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+class UNetTrainEngine:
+    """Train-mode forward + backward plan.  ``precision``: "bf16" (tcgen05 convolutions, bf16 NHWC
+    activations and activation gradients, fp32 statistics / parameter gradients) or "fp32"
+    (FFMA convolutions; the tight-tolerance parity path)."""
+
+    def __init__(self, cfg: UNetConfig, module: torch.nn.Module, batch: int, device: torch.device,
+                 precision: str = "bf16"):
+        assert precision in ("bf16", "fp32")
+        self.cfg, self.module, self.B, self.device, self.precision = cfg, module, batch, device, precision
+        self.lib = L.load()
+        self.act = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.adt = L.dtype_code(self.act)
+        c0, c1, c2, c3 = cfg.enc
+        d3, d2, d1 = cfg.dec
+        s0 = cfg.image
+        s1 = _pool(s0, cfg.ceil_pool)
+        s2 = _pool(s1, cfg.ceil_pool)
+        s3 = _pool(s2, cfg.ceil_pool)
+        u3, u2, u1 = 2 * s3, 4 * s3, 8 * s3
+        self.S = dict(s0=s0, s1=s1, s2=s2, s3=s3, u3=u3, u2=u2, u1=u1)
+        B = batch
+        dev = device
+
+        def buf(h, c, dtype=None):
+            return torch.zeros(B, h, h, c, device=dev, dtype=dtype or self.act)
+
+        # (block name) -> input buffer, cin, spatial size, output buffer name
+        self.layers: List[Tuple[str, str, int, int, str, int]] = [
+            # name, input buffer, cin, size, output buffer, cout
+            ("enc1.0", "x0", c0, s0, "enc1a", c1), ("enc1.3", "enc1a", c1, s0, "e1", c1),
+            ("enc2.0", "p1", c1, s1, "enc2a", c2), ("enc2.3", "enc2a", c2, s1, "e2", c2),
+            ("enc3.0", "p2", c2, s2, "enc3a", c3), ("enc3.3", "enc3a", c3, s2, "e3", c3),
+            ("bottleneck.0", "p3", c3, s3, "b", cfg.bott),
+            ("dec3.0", "cat3", cfg.bott + c3, u3, "dec3a", d3), ("dec3.3", "dec3a", d3, u3, "d3", d3),
+            ("dec2.0", "cat2", d3 + c2, u2, "dec2a", d2), ("dec2.3", "dec2a", d2, u2, "d2", d2),
+            ("dec1.0", "cat1", d2 + c1, u1, "dec1a", d1), ("dec1.3", "dec1a", d1, u1, "d1", d1),
+        ]
+        shapes = {
+            "x0": (s0, c0), "enc1a": (s0, c1), "e1": (s0, c1), "p1": (s1, c1),
+            "enc2a": (s1, c2), "e2": (s1, c2), "p2": (s2, c2),
+            "enc3a": (s2, c3), "e3": (s2, c3), "p3": (s3, c3), "b": (s3, cfg.bott),
+            "cat3": (u3, cfg.bott + c3), "dec3a": (u3, d3), "d3": (u3, d3),
+            "cat2": (u2, d3 + c2), "dec2a": (u2, d2), "d2": (u2, d2),
+            "cat1": (u1, d2 + c1), "dec1a": (u1, d1), "d1": (u1, d1),
+        }
+        self.last = "d1"
+        if cfg.final_resize:
+            shapes["d1r"] = (s0, d1)
+            self.last = "d1r"
+        self.bufs = {k: buf(h, c) for k, (h, c) in shapes.items()}          # activations
+        self.grads = {k: buf(h, c) for k, (h, c) in shapes.items()}         # dL/d(activation)
+        self.yraw = {name: buf(size, cout) for name, _, _, size, _, cout in self.layers}    # pre-BN conv outputs
+        max_y = max(B * size * size * cout for _, _, _, size, _, cout in self.layers)
+        self.dy = torch.zeros(max_y, device=dev, dtype=self.act)             # dL/d(conv output), one layer at a time
+        self.x_in = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
+        self.eps = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
+        self.d_eps = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
+        self.temb = torch.zeros(B, c1 + c2 + c3, device=dev, dtype=torch.float32)
+        self.d_temb = torch.zeros(B, c1 + c2 + c3, device=dev, dtype=torch.float32)
+        self.emb_saved = torch.zeros(int(self.lib.td_embed_head_saved_floats(B, cfg.time_dim, cfg.emb_mode)),
+                                     device=dev, dtype=torch.float32)
+        self.emb_scratch = torch.zeros(2 * B * cfg.time_dim, device=dev, dtype=torch.float32)
+        self.t_in = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.y_in = torch.zeros(B, device=dev, dtype=torch.int64) if cfg.cond == "class" else None
+        self.text_in = (torch.zeros(B, cfg.time_dim, device=dev, dtype=torch.float32) if cfg.cond == "text" else None)
+
+        # per-BN-layer state
+        self.bn: Dict[str, Dict[str, torch.Tensor]] = {}
+        max_part = 1
+        for name, _, _, size, _, cout in self.layers:
+            rows = int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout))
+            max_part = max(max_part, rows * 2 * cout)
+            self.bn[name] = {k: torch.zeros(cout, device=dev) for k in ("scale", "shift", "mean", "invstd")}
+            self.bn[name]["coef"] = torch.zeros(3, cout, device=dev)
+            self.bn[name]["rows"] = rows
+        rows0 = int(self.lib.td_chan_reduce_rows(self.adt, B * s0 * s0, c0))
+        max_part = max(max_part, rows0 * 2 * c0)
+        self.rows_x0 = rows0
+        self.partials = torch.zeros(max_part, device=dev)
+
+        # parameter gradients (PyTorch layouts), keyed like state_dict
+        self.pgrad: Dict[str, torch.Tensor] = {k: torch.zeros_like(p, device=dev) for k, p in module.named_parameters()}
+        self.proj_w = torch.zeros(c1 + c2 + c3, cfg.time_dim, device=dev)
+        self.proj_b = torch.zeros(c1 + c2 + c3, device=dev)
+        self.d_proj_w = torch.zeros_like(self.proj_w)
+        self.d_proj_b = torch.zeros_like(self.proj_b)
+
+        self._alloc_packed()
+        self._build()
+        self._weights_version = None
+
+    # ------------------------------------------------------------------ parameters
+    def _conv_modules(self):
+        m = self.module
+        out = [("initial_conv", m.initial_conv, None)]
+        for blk, idx in _CONVS:
+            seq = getattr(m, blk)
+            out.append((f"{blk}.{idx}", seq[idx], seq[idx + 1]))
+        out.append(("final_conv", m.final_conv, None))
+        return out
+
+    def _tc(self, cin: int, cout: int) -> bool:
+        return self.precision == "bf16" and cin % 64 == 0 and cout % 64 == 0
+
+    def _alloc_packed(self):
+        self.w_fwd: Dict[str, torch.Tensor] = {}
+        self.w_bwd: Dict[str, torch.Tensor] = {}
+        self.conv_of: Dict[str, Tuple[torch.nn.Module, Optional[torch.nn.Module]]] = {}
+        for name, conv, bn in self._conv_modules():
+            cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+            self.conv_of[name] = (conv, bn)
+            direct = name in ("initial_conv", "final_conv")
+            wdt_f = torch.bfloat16 if (not direct and self._tc(cin, cout)) else torch.float32
+            wdt_b = torch.bfloat16 if (not direct and self._tc(cout, cin)) else torch.float32
+            self.w_fwd[name] = torch.zeros(cout, 3, 3, cin, device=self.device, dtype=wdt_f)
+            if name != "initial_conv":
+                self.w_bwd[name] = torch.zeros(cin, 3, 3, cout, device=self.device, dtype=wdt_b)
+
+    def weights_version(self):
+        return tuple(p._version for p in self.module.parameters())
+
+    def refresh_weights(self, force: bool = False) -> None:
+        ver = self.weights_version()
+        if not force and ver == self._weights_version:
+            return
+        st = L.stream_ptr()
+        lib = self.lib
+        for name, (conv, bn) in self.conv_of.items():
+            w = conv.weight.detach()
+            assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+            pk = self.w_fwd[name]
+            L.check(lib.td_pack_conv_weight(w.data_ptr(), pk.data_ptr(), L.dtype_code(pk.dtype), w.shape[0], w.shape[1],
+                                            st), "td_pack_conv_weight")
+            if name in self.w_bwd:
+                pb = self.w_bwd[name]
+                L.check(lib.td_pack_conv_weight_dgrad(w.data_ptr(), pb.data_ptr(), L.dtype_code(pb.dtype), w.shape[0],
+                                                      w.shape[1], st), "td_pack_conv_weight_dgrad")
+        m = self.module
+        c1, c2, c3 = self.cfg.enc[1:]
+        D = self.cfg.time_dim
+        off = 0
+        for proj, c in ((m.time_proj1, c1), (m.time_proj2, c2), (m.time_proj3, c3)):
+            self.proj_w[off:off + c].copy_(proj.weight.detach().view(c, D))
+            self.proj_b[off:off + c].copy_(proj.bias.detach())
+            off += c
+        self._weights_version = ver
+
+    # ------------------------------------------------------------------ plan construction
+    def _conv_desc(self, x, cin, y, cout, w, x_coff=0, shift=None, x_nchw=False, y_nchw=False, size=None):
+        d = L.ConvDesc()
+        H = size if size is not None else (x.shape[2] if x_nchw else x.shape[1])
+        d.batch, d.height, d.width, d.cin, d.cout = self.B, H, H, cin, cout
+        d.x_dtype, d.y_dtype = L.dtype_code(x.dtype), L.dtype_code(y.dtype)
+        d.x, d.ldx, d.x_coff = x.data_ptr(), (cin if x_nchw else x.shape[3]), x_coff
+        d.y, d.ldy, d.y_coff = y.data_ptr(), (cout if y_nchw else y.shape[3]), 0
+        d.w, d.scale, d.shift, d.relu, d.stats = w.data_ptr(), None, L.ptr(shift), 0, None
+        d.x_nchw, d.y_nchw = int(x_nchw), int(y_nchw)
+        return d
+
+    def _wgrad(self, name, x, cin, dy, cout, size, engine, x_nchw=False, dy_nchw=False):
+        d = L.WgradDesc()
+        d.batch, d.height, d.width, d.cin, d.cout = self.B, size, size, cin, cout
+        d.x_dtype, d.dy_dtype = L.dtype_code(x.dtype), L.dtype_code(dy.dtype)
+        d.x, d.ldx, d.x_coff, d.x_nchw = x.data_ptr(), (cin if x_nchw else x.shape[3]), 0, int(x_nchw)
+        d.dy, d.lddy, d.dy_coff, d.dy_nchw = dy.data_ptr(), cout, 0, int(dy_nchw)
+        d.dw = self.pgrad[self._wkey(name)].data_ptr()
+        need = int(self.lib.td_conv3x3_wgrad_workspace(C.byref(d), engine))
+        self._wg_specs.append((name, d, engine, need))
+
+    @staticmethod
+    def _wkey(name: str) -> str:
+        return f"{name}.weight"
+
+    def _build(self):
+        cfg, bf, gr, lib, B, S = self.cfg, self.bufs, self.grads, self.lib, self.B, self.S
+        c0, c1, c2, c3 = cfg.enc
+        d3, d2, d1 = cfg.dec
+        adt = self.adt
+        self.conv_plans: Dict[str, _ConvPlan] = {}
+        self._wg_specs: List = []
+        fwd: List[Tuple[str, Callable[[int], None]]] = []
+        bwd: List[Tuple[str, Callable[[int], None]]] = []
+        m = self.module
+        part = self.partials.data_ptr()
+
+        def conv_plan(key, desc, engine):
+            p = _ConvPlan(desc, engine)
+            self.conv_plans[key] = p
+            return p
+
+        # ---- forward ---------------------------------------------------------------------------
+        fwd.append(("embed", self._run_embed))
+        ic = m.initial_conv
+        p = conv_plan("initial_conv", self._conv_desc(self.x_in, cfg.in_ch, bf["x0"], c0, self.w_fwd["initial_conv"],
+                                                      shift=ic.bias, x_nchw=True), L.CONV_DIRECT)
+        fwd.append(("initial_conv", p.run))
+
+        def add_block(name, xin, cin, size, out, cout):
+            conv, bn = self.conv_of[name]
+            x, y, a = bf[xin], self.yraw[name], bf[out]
+            eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
+            p = conv_plan(name, self._conv_desc(x, cin, y, cout, self.w_fwd[name]), eng)
+            fwd.append((name, p.run))
+            st_ = self.bn[name]
+            rows, P = st_["rows"], B * size * size
+            yp, ap = y.data_ptr(), a.data_ptr()
+            g_, b_, cb = bn.weight.data_ptr(), bn.bias.data_ptr(), conv.bias.data_ptr()
+            rm, rv, nbt = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()
+            eps_, mom = float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1)
+            sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
+
+            def bn_fwd(st):
+                L.check(lib.td_bn_stats(yp, adt, cout, 0, P, cout, part, st), "td_bn_stats")
+                L.check(lib.td_bn_finalize(part, rows, cout, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, st),
+                        "td_bn_finalize")
+                L.check(lib.td_bn_relu_apply(yp, sc, sh, ap, adt, cout, 0, P, cout, 1, st), "td_bn_relu_apply")
+            fwd.append((f"bn:{name}", bn_fwd))
+
+        def add_pool(src, dst, h, c):
+            sp, dp = bf[src].data_ptr(), bf[dst].data_ptr()
+            ceil = int(cfg.ceil_pool)
+            fwd.append((f"pool:{src}", lambda st: L.check(lib.td_maxpool2_fwd(sp, dp, adt, B, h, h, c, ceil, st),
+                                                          "td_maxpool2_fwd")))
+
+        def add_upcat(low, skip, dst, ho, cu, hs, cs, toff):
+            lp, sp, dp, tp = bf[low].data_ptr(), bf[skip].data_ptr(), bf[dst].data_ptr(), self.temb.data_ptr()
+            ld = self.temb.shape[1]
+            fwd.append((f"upcat:{dst}", lambda st: L.check(
+                lib.td_upcat_fwd(lp, sp, tp, ld, toff, dp, adt, B, ho, ho, cu, hs, hs, cs, st), "td_upcat_fwd")))
+
+        Ls = {l[0]: l for l in self.layers}
+        for nm in ("enc1.0", "enc1.3"):
+            add_block(*Ls[nm])
+        add_pool("e1", "p1", S["s0"], c1)
+        for nm in ("enc2.0", "enc2.3"):
+            add_block(*Ls[nm])
+        add_pool("e2", "p2", S["s1"], c2)
+        for nm in ("enc3.0", "enc3.3"):
+            add_block(*Ls[nm])
+        add_pool("e3", "p3", S["s2"], c3)
+        add_block(*Ls["bottleneck.0"])
+        add_upcat("b", "e3", "cat3", S["u3"], cfg.bott, S["s2"], c3, c1 + c2)
+        for nm in ("dec3.0", "dec3.3"):
+            add_block(*Ls[nm])
+        add_upcat("d3", "e2", "cat2", S["u2"], d3, S["s1"], c2, c1)
+        for nm in ("dec2.0", "dec2.3"):
+            add_block(*Ls[nm])
+        add_upcat("d2", "e1", "cat1", S["u1"], d2, S["s0"], c1, 0)
+        for nm in ("dec1.0", "dec1.3"):
+            add_block(*Ls[nm])
+        if cfg.final_resize:
+            sp, dp = bf["d1"].data_ptr(), bf["d1r"].data_ptr()
+            u1, s0 = S["u1"], S["s0"]
+            fwd.append(("resize:d1r", lambda st: L.check(
+                lib.td_resize_bilinear_fwd(sp, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_fwd")))
+        fc = m.final_conv
+        p = conv_plan("final_conv", self._conv_desc(bf[self.last], d1, self.eps, cfg.in_ch, self.w_fwd["final_conv"],
+                                                    shift=fc.bias, y_nchw=True), L.CONV_DIRECT)
+        fwd.append(("final_conv", p.run))
+
+        # ---- backward --------------------------------------------------------------------------
+        s0 = S["s0"]
+        # final_conv: bias / weight gradients and the data gradient (a tiny-Cin direct conv of d_eps)
+        dep, fcb = self.d_eps.data_ptr(), self.pgrad["final_conv.bias"].data_ptr()
+        bwd.append(("final_conv:dbias", lambda st: L.check(
+            lib.td_nchw_chansum(dep, B, cfg.in_ch, s0 * s0, fcb, st), "td_nchw_chansum")))
+        self._wgrad("final_conv", bf[self.last], d1, self.d_eps, cfg.in_ch, s0, L.CONV_SIMT, dy_nchw=True)
+        bwd.append(("final_conv:wgrad", None))
+        p = conv_plan("final_conv:dgrad", self._conv_desc(self.d_eps, cfg.in_ch, gr[self.last], d1,
+                                                          self.w_bwd["final_conv"], x_nchw=True), L.CONV_DIRECT)
+        bwd.append(("final_conv:dgrad", p.run))
+        if cfg.final_resize:
+            gp, dp = gr["d1r"].data_ptr(), gr["d1"].data_ptr()
+            u1 = S["u1"]
+            bwd.append(("resize:d1r:bwd", lambda st: L.check(
+                lib.td_resize_bilinear_bwd(gp, d1, 0, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_bwd")))
+
+        def add_block_bwd(name, xin, cin, size, out, cout, need_dx=True):
+            conv, bn = self.conv_of[name]
+            st_ = self.bn[name]
+            rows, P = st_["rows"], B * size * size
+            y, da = self.yraw[name], gr[out]
+            dyv = self.dy[:P * cout].view(B, size, size, cout)
+            yp, dap, dyp = y.data_ptr(), da.data_ptr(), dyv.data_ptr()
+            sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
+            coef = st_["coef"].data_ptr()
+            blk, idx = name.split(".")
+            dg = self.pgrad[f"{blk}.{int(idx) + 1}.weight"].data_ptr()
+            db = self.pgrad[f"{blk}.{int(idx) + 1}.bias"].data_ptr()
+
+            def bn_bwd(st):
+                L.check(lib.td_bn_relu_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, P, cout, part, st),
+                        "td_bn_relu_bwd_reduce")
+                L.check(lib.td_bn_bwd_finalize(part, rows, cout, P, sc, mu, iv, dg, db, coef, st), "td_bn_bwd_finalize")
+                L.check(lib.td_bn_relu_bwd_apply(dap, cout, 0, yp, adt, sc, sh, coef, dyp, P, cout, st),
+                        "td_bn_relu_bwd_apply")
+            bwd.append((f"bn:{name}:bwd", bn_bwd))
+            eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
+            self._wgrad(name, bf[xin], cin, dyv, cout, size, eng)
+            bwd.append((f"{name}:wgrad", None))
+            if need_dx:
+                engd = L.CONV_TC if self._tc(cout, cin) else L.CONV_SIMT
+                p = conv_plan(f"{name}:dgrad", self._conv_desc(dyv, cout, gr[xin], cin, self.w_bwd[name], size=size), engd)
+                bwd.append((f"{name}:dgrad", p.run))
+
+        def add_upcat_bwd(low, skip, dst, ho, cu, hs, cs, toff):
+            gp, lp, sp, tp = gr[dst].data_ptr(), gr[low].data_ptr(), gr[skip].data_ptr(), self.d_temb.data_ptr()
+            ld = self.d_temb.shape[1]
+            bwd.append((f"upcat:{dst}:bwd", lambda st: L.check(
+                lib.td_upcat_bwd(gp, lp, sp, tp, ld, toff, adt, B, ho, ho, cu, hs, hs, cs, st), "td_upcat_bwd")))
+
+        def add_pool_bwd(src, dst, h, c):
+            xp, gyp, gxp = bf[src].data_ptr(), gr[dst].data_ptr(), gr[src].data_ptr()
+            ceil = int(cfg.ceil_pool)
+            bwd.append((f"pool:{src}:bwd", lambda st: L.check(
+                lib.td_maxpool2_bwd(xp, gyp, gxp, adt, B, h, h, c, ceil, 1, st), "td_maxpool2_bwd")))
+
+        for nm in ("dec1.3", "dec1.0"):
+            add_block_bwd(*Ls[nm])
+        add_upcat_bwd("d2", "e1", "cat1", S["u1"], d2, S["s0"], c1, 0)
+        for nm in ("dec2.3", "dec2.0"):
+            add_block_bwd(*Ls[nm])
+        add_upcat_bwd("d3", "e2", "cat2", S["u2"], d3, S["s1"], c2, c1)
+        for nm in ("dec3.3", "dec3.0"):
+            add_block_bwd(*Ls[nm])
+        add_upcat_bwd("b", "e3", "cat3", S["u3"], cfg.bott, S["s2"], c3, c1 + c2)
+        add_block_bwd(*Ls["bottleneck.0"])
+        add_pool_bwd("e3", "p3", S["s2"], c3)
+        for nm in ("enc3.3", "enc3.0"):
+            add_block_bwd(*Ls[nm])
+        add_pool_bwd("e2", "p2", S["s1"], c2)
+        for nm in ("enc2.3", "enc2.0"):
+            add_block_bwd(*Ls[nm])
+        add_pool_bwd("e1", "p1", S["s0"], c1)
+        for nm in ("enc1.3", "enc1.0"):
+            add_block_bwd(*Ls[nm])
+        # initial_conv: bias gradient = per-channel sum of d(x0); weight gradient; no data gradient
+        gx0, icb, rows0 = gr["x0"].data_ptr(), self.pgrad["initial_conv.bias"].data_ptr(), self.rows_x0
+        P0 = B * s0 * s0
+
+        def ic_bias(st):
+            L.check(lib.td_bn_stats(gx0, adt, c0, 0, P0, c0, part, st), "td_bn_stats")
+            L.check(lib.td_partial_sum(part, rows0, c0, 0, icb, st), "td_partial_sum")
+        bwd.append(("initial_conv:dbias", ic_bias))
+        self._wgrad("initial_conv", self.x_in, cfg.in_ch, gr["x0"], c0, s0, L.CONV_SIMT, x_nchw=True)
+        bwd.append(("initial_conv:wgrad", None))
+        bwd.append(("embed:bwd", self._run_embed_bwd))
+
+        # weight-gradient plans share one workspace
+        ws_floats = max(need for _, _, _, need in self._wg_specs)
+        self.wg_ws = torch.zeros(max(ws_floats, 1), device=self.device)
+        self.wg_plans: Dict[str, _WgradPlan] = {}
+        for name, d, engine, _ in self._wg_specs:
+            d.workspace = self.wg_ws.data_ptr()
+            self.wg_plans[name] = _WgradPlan(d, engine)
+        bwd = [(n, (self.wg_plans[n.split(":")[0]].run if fn is None else fn)) for n, fn in bwd]
+        self.fwd_ops, self.bwd_ops = fwd, bwd
+
+    # ------------------------------------------------------------------ conditioning head
+    def _embed_args(self) -> "L.EmbedArgs":
+        m, cfg = self.module, self.cfg
+        a = L.EmbedArgs()
+        a.batch, a.dim, a.in_mode, a.proj_out = self.B, cfg.time_dim, cfg.emb_mode, self.temb.shape[1]
+        a.t, a.t_dev = self.t_in.data_ptr(), None
+        mlp = m.time_mlp if cfg.cond == "text" else m.time_embedding
+        a.w0, a.b0 = mlp[0].weight.data_ptr(), mlp[0].bias.data_ptr()
+        a.w2, a.b2 = mlp[2].weight.data_ptr(), mlp[2].bias.data_ptr()
+        a.y = self.y_in.data_ptr() if cfg.cond == "class" else None
+        a.class_table = m.class_embedding.weight.data_ptr() if cfg.cond == "class" else None
+        a.text = self.text_in.data_ptr() if cfg.cond == "text" else None
+        a.proj_w, a.proj_b = self.proj_w.data_ptr(), self.proj_b.data_ptr()
+        a.saved = self.emb_saved.data_ptr()
+        a.proj_out_ptr = self.temb.data_ptr()
+        return a
+
+    def _run_embed(self, st: int) -> None:
+        L.check(self.lib.td_embed_head_fwd(C.byref(self._embed_args()), st), "td_embed_head_fwd")
+
+    def _run_embed_bwd(self, st: int) -> None:
+        cfg = self.cfg
+        pre = "time_mlp" if cfg.cond == "text" else "time_embedding"
+        g = L.EmbedGrads()
+        g.d_proj, g.scratch = self.d_temb.data_ptr(), self.emb_scratch.data_ptr()
+        g.d_w0, g.d_b0 = self.pgrad[f"{pre}.0.weight"].data_ptr(), self.pgrad[f"{pre}.0.bias"].data_ptr()
+        g.d_w2, g.d_b2 = self.pgrad[f"{pre}.2.weight"].data_ptr(), self.pgrad[f"{pre}.2.bias"].data_ptr()
+        if cfg.cond == "class":
+            g.d_class_table = self.pgrad["class_embedding.weight"].data_ptr()
+            g.num_classes = self.module.class_embedding.weight.shape[0]
+        g.d_proj_w, g.d_proj_b = self.d_proj_w.data_ptr(), self.d_proj_b.data_ptr()
+        L.check(self.lib.td_embed_head_bwd(C.byref(self._embed_args()), C.byref(g), st), "td_embed_head_bwd")
+        # scatter the fused projection gradient back to the three 1x1-conv parameters
+        c1, c2, c3 = cfg.enc[1:]
+        D, off = cfg.time_dim, 0
+        for i, c in enumerate((c1, c2, c3), start=1):
+            self.pgrad[f"time_proj{i}.weight"].view(c, D).copy_(self.d_proj_w[off:off + c])
+            self.pgrad[f"time_proj{i}.bias"].copy_(self.d_proj_b[off:off + c])
+            off += c
+
+    # ------------------------------------------------------------------ execution
+    def launch_forward(self) -> None:
+        st = L.stream_ptr()
+        for _, fn in self.fwd_ops:
+            fn(st)
+
+    def launch_backward(self) -> None:
+        """Reads d_eps; fills ``pgrad`` (every parameter).  Conv biases that feed a BatchNorm have a
+        mathematically zero gradient in train mode and are left at zero."""
+        st = L.stream_ptr()
+        for _, fn in self.bwd_ops:
+            fn(st)
+
+    def load_inputs(self, x, t, cond) -> None:
+        assert x.shape == self.x_in.shape, (x.shape, self.x_in.shape)
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        if self.cfg.cond == "class":
+            self.y_in.copy_(cond)
+        elif self.cfg.cond == "text":
+            self.text_in.copy_(cond)
+
+    def num_launches(self) -> Tuple[int, int]:
+        return len(self.fwd_ops), len(self.bwd_ops)
+
+    def conv_flops(self) -> float:
+        """Algorithmic FLOPs of one forward + backward (forward conv, data gradient, weight gradient)."""
+        f = sum(p.flops for p in self.conv_plans.values())
+        wg = sum(2.0 * d.batch * d.height * d.width * d.cout * 9.0 * d.cin for _, d, _, _ in self._wg_specs)
+        return f + wg
+
+
+class _UNetTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine: UNetTrainEngine, x, t, cond, *params):
+        engine.refresh_weights()
+        engine.load_inputs(x, t, cond)
+        engine.launch_forward()
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        return engine.eps.clone()
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        eng: UNetTrainEngine = ctx.engine
+        eng.d_eps.copy_(d_eps)
+        eng.launch_backward()
+        grads = tuple(eng.pgrad[k].clone() for k, _ in eng.module.named_parameters())
+        return (None, None, None, None) + grads
+
+
+def train_engine(model, batch: int, device: torch.device) -> UNetTrainEngine:
+    key = ("train", batch, str(device), model.precision)
+    eng = model._engines.get(key)
+    if eng is None:
+        cfg = model.config
+        if cfg.time_dim != model.time_dim:
+            cfg = UNetConfig(**{**cfg.__dict__, "time_dim": model.time_dim})
+        eng = UNetTrainEngine(cfg, model, batch, device, model.precision)
+        model._engines[key] = eng
+    return eng
+
+
+def unet_train_forward(model, x, t, cond):
+    """Train-mode ``NoiseModel.forward`` with autograd (diffusion.py:228 followed by :235)."""
+    device = x.device
+    eng = train_engine(model, x.shape[0], device)
+    params = tuple(p for _, p in model.named_parameters())
+    return _UNetTrainFunction.apply(eng, x.to(torch.float32).contiguous(), t, cond, *params)
+
+
+class TrainStep:
+    """Fused train step: ``t ~ randint; x_t, noise = q_sample(x_0, t); eps = model(x_t, t[, y]);
+    loss = mse(eps, noise); backward; Adam`` (diffusion.py:220-236) as one CUDA-graph replay.
+
+    ``world_size > 1``: data parallel -- gradients are all-reduced (sum) through ``torch.distributed``
+    (NCCL) in buckets, and the Adam pass scales them by 1/world_size.
+    """
+
+    def __init__(self, model, process, batch: int, device, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_graph: bool = True, process_group=None, bucket_mb: float = 8.0):
+        self.device = L.require_device(device)
+        self.model, self.process, self.B = model, process, batch
+        self.lib = L.load()
+        self.eng = train_engine(model, batch, self.device)
+        self.lr, self.betas, self.adam_eps = lr, betas, eps
+        self.use_graph = use_graph
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        dev = self.device
+        e = self.eng
+        self.x0 = torch.zeros_like(e.x_in)
+        self.noise = torch.zeros_like(e.x_in)
+        self.loss = torch.zeros(1, device=dev)
+        n = e.eps.numel()
+        self.partials = torch.zeros(int(self.lib.td_mse_num_partials(n)), device=dev)
+        self.counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.grad_scale = torch.full((1,), 1.0 / self.world, device=dev)
+        self.tab = process._tables(dev)
+        # flat gradient buffer: pgrad tensors become views of it, so one all-reduce per bucket
+        self.names = [k for k, _ in model.named_parameters()]
+        self.params = [p for _, p in model.named_parameters()]
+        sizes = [p.numel() for p in self.params]
+        self.flat_grad = torch.zeros(sum((s + 3) // 4 * 4 for s in sizes), device=dev)
+        off = 0
+        self.offsets = []
+        for k, p, s in zip(self.names, self.params, sizes):
+            view = self.flat_grad[off:off + s].view_as(p)
+            e.pgrad[k] = view
+            self.offsets.append(off)
+            off += (s + 3) // 4 * 4
+        e._build()          # rebuild the plans against the flat gradient views
+        self.m = torch.zeros_like(self.flat_grad)
+        self.v = torch.zeros_like(self.flat_grad)
+        self._adam_tables()
+        # buckets in reverse registration order ~ reverse execution order of the backward
+        self.buckets: List[Tuple[int, int]] = []
+        lim = int(bucket_mb * 1024 * 1024 / 4)
+        end = self.flat_grad.numel()
+        cur = end
+        for o in reversed(self.offsets):
+            if cur - o >= lim:
+                self.buckets.append((o, cur))
+                cur = o
+        if cur > 0:
+            self.buckets.append((0, cur))
+        self.graph = None
+
+    def _adam_tables(self):
+        dev = self.device
+        CH = 65536
+        ptrs_p, ptrs_g, ptrs_m, ptrs_v, numel, ct, co = [], [], [], [], [], [], []
+        for i, (p, off) in enumerate(zip(self.params, self.offsets)):
+            n = p.numel()
+            ptrs_p.append(p.data_ptr())
+            ptrs_g.append(self.flat_grad.data_ptr() + 4 * off)
+            ptrs_m.append(self.m.data_ptr() + 4 * off)
+            ptrs_v.append(self.v.data_ptr() + 4 * off)
+            numel.append(n)
+            for c in range(0, n, CH):
+                ct.append(i)
+                co.append(c)
+        t64 = lambda v: torch.tensor(v, dtype=torch.int64, device=dev)
+        self._tp, self._tg, self._tm, self._tv = t64(ptrs_p), t64(ptrs_g), t64(ptrs_m), t64(ptrs_v)
+        self._numel = t64(numel)
+        self._ct = torch.tensor(ct, dtype=torch.int32, device=dev)
+        self._co = t64(co)
+        self._chunks, self._chunk_elems = len(ct), CH
+
+    # -- pieces ------------------------------------------------------------------------------
+    def _compute(self):
+        """q_sample -> forward -> mse + dL/deps -> backward (everything up to the gradients)."""
+        e, lib, st = self.eng, self.lib, L.stream_ptr()
+        per = e.x_in.numel() // self.B
+        L.check(lib.td_qsample(self.x0.data_ptr(), self.noise.data_ptr(), e.t_in.data_ptr(), self.tab["abar"].data_ptr(),
+                               e.x_in.data_ptr(), self.B, per, self.process.num_timesteps, None, st), "td_qsample")
+        e.launch_forward()
+        n = e.eps.numel()
+        L.check(lib.td_mse_grad(e.eps.data_ptr(), self.noise.data_ptr(), e.d_eps.data_ptr(), self.loss.data_ptr(),
+                                self.partials.data_ptr(), self.counter.data_ptr(), n, 1.0 / n, st), "td_mse_grad")
+        e.launch_backward()
+
+    def _allreduce(self):
+        if self.world == 1:
+            return
+        for lo, hi in self.buckets:
+            torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg)
+
+    def _update(self):
+        lib, st = self.lib, L.stream_ptr()
+        L.check(lib.td_counter_add(self.step_dev.data_ptr(), 1, st), "td_counter_add")
+        L.check(lib.td_adam_multi(self._tp.data_ptr(), self._tg.data_ptr(), self._tm.data_ptr(), self._tv.data_ptr(),
+                                  self._numel.data_ptr(), self._ct.data_ptr(), self._co.data_ptr(), self._chunks,
+                                  self._chunk_elems, self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1],
+                                  self.adam_eps, self.grad_scale.data_ptr(), None, st), "td_adam_multi")
+        self.eng.refresh_weights(force=True)
+
+    def _body(self):
+        self._compute()
+        self._allreduce()
+        self._update()
+
+    # -- public ------------------------------------------------------------------------------
+    def load(self, x_0, y=None, t=None, noise=None):
+        """Stage one batch: x_0 (any device), optional labels / text, and optionally injected t / noise."""
+        e = self.eng
+        self.x0.copy_(x_0, non_blocking=True)
+        if e.cfg.cond == "class":
+            e.y_in.copy_(y, non_blocking=True)
+        elif e.cfg.cond == "text":
+            e.text_in.copy_(y, non_blocking=True)
+        if t is None:
+            e.t_in.copy_(torch.randint(0, self.process.num_timesteps, (self.B,), device=self.device))   # diffusion.py:220
+        else:
+            e.t_in.copy_(t, non_blocking=True)
+        if noise is None:
+            self.noise.normal_()                                                                        # diffusion.py:178
+        else:
+            self.noise.copy_(noise, non_blocking=True)
+
+    def run(self) -> torch.Tensor:
+        """One optimisation step on the staged batch; returns the (device) loss tensor."""
+        self.model.train()
+        if not self.use_graph or self.world > 1:
+            self.eng.refresh_weights()
+            self._body()
+            return self.loss
+        if self.graph is None:
+            self.eng.refresh_weights(force=True)
+            # warm-up outside capture on a side stream (lazy module load / cudaFuncSetAttribute), restoring
+            # every piece of state the step mutates
+            saved = [p.detach().clone() for p in self.params]
+            bufs = [b.detach().clone() for b in self.model.buffers()]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            with torch.no_grad():
+                for p, s in zip(self.params, saved):
+                    p.copy_(s)
+                for b, s in zip(self.model.buffers(), bufs):
+                    b.copy_(s)
+            self.m.zero_()
+            self.v.zero_()
+            self.step_dev.zero_()
+            self.eng.refresh_weights(force=True)
+            self.graph = g
+        self.graph.replay()
+        return self.loss
+
+    def __call__(self, x_0, y=None, t=None, noise=None) -> torch.Tensor:
+        self.load(x_0, y, t, noise)
+        return self.run()

@@ -117,6 +117,8 @@ class UNetEngine:
         self.x_in = torch.zeros(B, cfg.in_ch, s0, s0, device=device, dtype=torch.float32)
         self.eps = torch.zeros(B, cfg.in_ch, s0, s0, device=device, dtype=torch.float32)
         self.temb = torch.zeros(B, c1 + c2 + c3, device=device, dtype=torch.float32)
+        self.emb_saved = torch.zeros(int(self.lib.td_embed_head_saved_floats(B, cfg.time_dim, cfg.emb_mode)),
+                                     device=device, dtype=torch.float32)
         self.t_in = torch.zeros(B, device=device, dtype=torch.int64)
         self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)       # sampler step counter
         self.y_in = torch.zeros(B, device=device, dtype=torch.int64) if cfg.cond == "class" else None
@@ -275,7 +277,7 @@ class UNetEngine:
         self.ops = ops
         self.use_t_dev = False
 
-    def _run_embed(self, st: int) -> None:
+    def _embed_args(self) -> "L.EmbedArgs":
         m, cfg = self.module, self.cfg
         a = L.EmbedArgs()
         a.batch, a.dim, a.in_mode, a.proj_out = self.B, cfg.time_dim, cfg.emb_mode, self.temb.shape[1]
@@ -288,9 +290,12 @@ class UNetEngine:
         a.class_table = m.class_embedding.weight.data_ptr() if cfg.cond == "class" else None
         a.text = self.text_in.data_ptr() if cfg.cond == "text" else None
         a.proj_w, a.proj_b = self.proj_w.data_ptr(), self.proj_b.data_ptr()
-        a.emb_out, a.h_out = None, None
+        a.saved = self.emb_saved.data_ptr()
         a.proj_out_ptr = self.temb.data_ptr()
-        L.check(self.lib.td_embed_head_fwd(C.byref(a), st), "td_embed_head_fwd")
+        return a
+
+    def _run_embed(self, st: int) -> None:
+        L.check(self.lib.td_embed_head_fwd(C.byref(self._embed_args()), st), "td_embed_head_fwd")
 
     # ------------------------------------------------------------------ execution
     def launch(self) -> None:
