@@ -226,27 +226,31 @@ void td_conv3x3_wgrad_plan_destroy(td_wgrad_plan* plan);
  * [2][channels] partial sums per CTA (td_chan_reduce_rows rows) and are finalised in fixed order.
  * ---------------------------------------------------------------------------------------- */
 int td_chan_reduce_rows(int dtype, int64_t pixels, int channels);
-/* partials[r] = { sum x, sum x^2 } of the raw conv output x (conv bias NOT included) */
+/* partials[r] = { sum (x-K), sum (x-K)^2 } of x (the raw fp32 conv output, conv bias NOT included, for
+ * BatchNorm; any NHWC tensor for per-channel sums), followed by the row K[channels]: K = x[pixel 0]
+ * when `shifted` (guards E[x^2]-mean^2 against cancellation), else 0.
+ * partials holds td_chan_reduce_rows()*2*channels + channels floats. */
 int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, int64_t pixels, int channels, float* partials,
-                void* stream);
+                int shifted, void* stream);
 /* batch mean / biased variance -> scale = gamma*invstd, shift = beta - mean*scale; running stats
  * momentum update with the unbiased variance and mean + conv_bias; num_batches_tracked += 1 */
 int td_bn_finalize(const float* partials, int nrows, int channels, int64_t count, const float* gamma,
                    const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                    float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
                    float* save_invstd, void* stream);
-/* a[p, a_coff + c] = relu?(y[p, c] * scale[c] + shift[c]) */
-int td_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
+/* a[p, a_coff + c] = relu?(y[p, c] * scale[c] + shift[c]);  y: fp32 [pixels, channels]; a: `dtype` */
+int td_bn_relu_apply(const float* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
                      int a_coff, int64_t pixels, int channels, int relu, void* stream);
-/* partials[r] = { sum g, sum g*y },  g = da * [y*scale+shift > 0] */
-int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int dtype, const float* scale,
-                          const float* shift, int64_t pixels, int channels, float* partials, void* stream);
+/* partials[r] = { sum g, sum g*(y-mean) },  g = da * [y*scale+shift > 0]   (da: `dtype`, y: fp32) */
+int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
+                          const float* shift, const float* save_mean, int64_t pixels, int channels, float* partials,
+                          void* stream);
 /* dgamma, dbeta and the per-channel coefficients coef[3][channels] of the apply pass */
 int td_bn_bwd_finalize(const float* partials, int nrows, int channels, int64_t count, const float* scale,
                        const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* coef,
                        void* stream);
 /* dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) */
-int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const void* y, int dtype, const float* scale,
+int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
                          const float* shift, const float* coef, void* dy, int64_t pixels, int channels, void* stream);
 
 /* backward of td_maxpool2_fwd (first maximum in scan order takes the gradient, like ATen) */

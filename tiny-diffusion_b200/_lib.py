@@ -91,11 +91,11 @@ _SIGS = {
     "td_conv3x3_wgrad_run": (C.c_int, [_P, _P]),
     "td_conv3x3_wgrad_plan_destroy": (None, [_P]),
     "td_chan_reduce_rows": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
-    "td_bn_stats": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_stats": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, C.c_int, _P]),
     "td_bn_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P,
                                  _P, _P, _P, _P]),
     "td_bn_relu_apply": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
-    "td_bn_relu_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_relu_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "td_bn_bwd_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "td_bn_relu_bwd_apply": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

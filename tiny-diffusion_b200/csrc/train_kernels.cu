@@ -24,45 +24,56 @@ __device__ inline Bil bil_t(int dst, int in, int out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-channel partial sums over pixels.
-//   MODE 0: s1 = sum x,           s2 = sum x^2            (BatchNorm batch statistics)
-//   MODE 1: s1 = sum g,           s2 = sum g * y          (BatchNorm backward), g = da * [y*scale+shift > 0]
+// per-channel partial sums over pixels (T = activation type; the raw conv output y is always fp32,
+// see DESIGN.md: a bf16 y loses the signal under the large per-sample time-embedding offsets).
+//   MODE 0: s1 = sum (x-K), s2 = sum (x-K)^2, K[c] = x[pixel 0, c] or 0   (shifted-data statistics)
+//   MODE 1: s1 = sum g,     s2 = sum g*(y-mean),  g = da * [y*scale+shift > 0]   (BatchNorm backward)
 // thread layout: lanesC = C / V channel-vector lanes, rows = kT / lanesC pixel rows per CTA pass.
-// partials: [gridDim.x][2][C]
+// partials: [gridDim.x][2][C] followed by K[C]
 // ---------------------------------------------------------------------------------------------
+template <int V> __device__ inline void load_f32(const float* p, float* f) {
+#pragma unroll
+    for (int k = 0; k < V; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + k);
+        f[k] = v.x; f[k + 1] = v.y; f[k + 2] = v.z; f[k + 3] = v.w;
+    }
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kT)
-chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const T* __restrict__ y, int64_t P, int C,
-                   const float* __restrict__ scale, const float* __restrict__ shift, float* __restrict__ partials) {
+chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const float* __restrict__ y, int64_t P, int C,
+                   const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                   int shifted, float* __restrict__ partials) {
     constexpr int V = Vec<T>::N;
     extern __shared__ float red[];               // [rows][2*C]
     const int lanesC = C / V;
     const int rows = kT / lanesC;
     const int lane = threadIdx.x % lanesC, row = threadIdx.x / lanesC;
     const int c0 = lane * V;
-    float s1[V], s2[V], sc[V], sh[V];
+    float s1[V], s2[V], sc[V], sh[V], mu[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = 1.f; sh[k] = 0.f; }
+    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = 1.f; sh[k] = 0.f; mu[k] = 0.f; }
     if (MODE == 1) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
+        for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k]; }
+    } else if (shifted) {
+        Vec<T>::load(a + a_coff + c0).unpack(mu);            // K = the first pixel of every channel
     }
     if (row < rows) {
         for (int64_t p = (int64_t)blockIdx.x * rows + row; p < P; p += (int64_t)gridDim.x * rows) {
             float f[V];
+            Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
             if (MODE == 0) {
-                Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
 #pragma unroll
-                for (int k = 0; k < V; ++k) { s1[k] += f[k]; s2[k] = fmaf(f[k], f[k], s2[k]); }
+                for (int k = 0; k < V; ++k) { const float d = f[k] - mu[k]; s1[k] += d; s2[k] = fmaf(d, d, s2[k]); }
             } else {
                 float yy[V];
-                Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
-                Vec<T>::load(y + p * C + c0).unpack(yy);
+                load_f32<V>(y + p * C + c0, yy);
 #pragma unroll
                 for (int k = 0; k < V; ++k) {
                     const float g = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? f[k] : 0.f;
                     s1[k] += g;
-                    s2[k] = fmaf(g, yy[k], s2[k]);
+                    s2[k] = fmaf(g, yy[k] - mu[k], s2[k]);
                 }
             }
         }
@@ -77,6 +88,10 @@ chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const T* __
         float t = 0.f;
         for (int r = 0; r < rows; ++r) t += red[(size_t)r * 2 * C + j];
         partials[(size_t)blockIdx.x * 2 * C + j] = t;
+    }
+    if (MODE == 0 && blockIdx.x == 0 && row == 0) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) partials[(size_t)gridDim.x * 2 * C + c0 + k] = mu[k];
     }
 }
 
@@ -97,8 +112,9 @@ bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double 
         s1 += (double)partials[(size_t)r * 2 * C + c];
         s2 += (double)partials[(size_t)r * 2 * C + C + c];
     }
-    const double mean = s1 / count;
-    double var = s2 / count - mean * mean;
+    const double dm = s1 / count;                         // mean of (x - K)
+    const double mean = (double)partials[(size_t)nrows * 2 * C + c] + dm;
+    double var = s2 / count - dm * dm;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
     const float sc = gamma[c] * invstd;
@@ -119,7 +135,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double 
 // a = relu(y * scale + shift)
 template <typename T>
 __global__ void __launch_bounds__(kT)
-bn_relu_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+bn_relu_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                      T* __restrict__ a, int64_t lda, int a_coff, int64_t P, int C, int relu) {
     constexpr int V = Vec<T>::N;
     const int lanesC = C / V;
@@ -133,7 +149,7 @@ bn_relu_apply_kernel(const T* __restrict__ y, const float* __restrict__ scale, c
     for (; i < total; i += stride) {
         const int64_t p = i / lanesC;
         float f[V];
-        Vec<T>::load(y + p * C + c0).unpack(f);
+        load_f32<V>(y + p * C + c0, f);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             f[k] = fmaf(f[k], sc[k], sh[k]);
@@ -157,7 +173,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, dou
         s2 += (double)partials[(size_t)r * 2 * C + C + c];
     }
     const double mean = save_mean[c], invstd = save_invstd[c], sc = scale[c];
-    const double dg = (s2 - mean * s1) * invstd;       // sum g * xhat
+    const double dg = s2 * invstd;                     // sum g * xhat   (s2 = sum g * (y - mean))
     dgamma[c] = (float)dg;
     dbeta[c] = (float)s1;
     const double cB = -sc * invstd * dg / count;
@@ -169,7 +185,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, dou
 // dy = scale*(g - mean(g) - xhat*mean(g*xhat)) = cA*g + cB*y + cC,  g = da * [y*scale+shift > 0]
 template <typename T>
 __global__ void __launch_bounds__(kT)
-bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const T* __restrict__ y,
+bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ coef, T* __restrict__ dy, int64_t P, int C) {
     constexpr int V = Vec<T>::N;
@@ -188,7 +204,7 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
         const int64_t p = i / lanesC;
         float g[V], yy[V];
         Vec<T>::load(da + p * ldda + da_coff + c0).unpack(g);
-        Vec<T>::load(y + p * C + c0).unpack(yy);
+        load_f32<V>(y + p * C + c0, yy);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const float gm = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
@@ -406,7 +422,7 @@ extern "C" int td_chan_reduce_rows(int dtype, int64_t pixels, int channels) {
 }
 
 extern "C" int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, int64_t pixels, int channels,
-                           float* partials, void* stream) {
+                           float* partials, int shifted, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && partials && pixels > 0, "td_bn_stats: bad args");
     if (int st = check_lanes("td_bn_stats", dtype, channels)) return st;
@@ -414,7 +430,8 @@ extern "C" int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, in
     const int V = dtype == TD_BF16 ? 8 : 4;
     const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
     TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 0><<<grid, kT, smem, (cudaStream_t)stream>>>(
-                             (const T*)x, ldx, x_coff, nullptr, pixels, channels, nullptr, nullptr, partials)));
+                             (const T*)x, ldx, x_coff, nullptr, pixels, channels, nullptr, nullptr, nullptr, shifted,
+                             partials)));
     return launch_status("bn_stats");
 }
 
@@ -431,7 +448,7 @@ extern "C" int td_bn_finalize(const float* partials, int nrows, int channels, in
     return launch_status("bn_finalize");
 }
 
-extern "C" int td_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
+extern "C" int td_bn_relu_apply(const float* y, const float* scale, const float* shift, void* a, int dtype, int64_t lda,
                                 int a_coff, int64_t pixels, int channels, int relu, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(y && scale && shift && a && pixels > 0, "td_bn_relu_apply: bad args");
@@ -440,21 +457,21 @@ extern "C" int td_bn_relu_apply(const void* y, const float* scale, const float* 
     const int lanesC = channels / V;
     const int grid = stream_grid(pixels * lanesC, lanesC);
     TD_DISPATCH_T(dtype, (bn_relu_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
-                             (const T*)y, scale, shift, (T*)a, lda, a_coff, pixels, channels, relu)));
+                             y, scale, shift, (T*)a, lda, a_coff, pixels, channels, relu)));
     return launch_status("bn_relu_apply");
 }
 
-extern "C" int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int dtype,
-                                     const float* scale, const float* shift, int64_t pixels, int channels,
-                                     float* partials, void* stream) {
+extern "C" int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype,
+                                     const float* scale, const float* shift, const float* save_mean, int64_t pixels,
+                                     int channels, float* partials, void* stream) {
     TD_REQUIRE_ARCH();
-    TD_CHECK_ARG(da && y && scale && shift && partials && pixels > 0, "td_bn_relu_bwd_reduce: bad args");
+    TD_CHECK_ARG(da && y && scale && shift && save_mean && partials && pixels > 0, "td_bn_relu_bwd_reduce: bad args");
     if (int st = check_lanes("td_bn_relu_bwd_reduce", dtype, channels)) return st;
     const int grid = td_chan_reduce_rows(dtype, pixels, channels);
     const int V = dtype == TD_BF16 ? 8 : 4;
     const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
     TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 1><<<grid, kT, smem, (cudaStream_t)stream>>>(
-                             (const T*)da, ldda, da_coff, (const T*)y, pixels, channels, scale, shift, partials)));
+                             (const T*)da, ldda, da_coff, y, pixels, channels, scale, shift, save_mean, 0, partials)));
     return launch_status("bn_relu_bwd_reduce");
 }
 
@@ -469,7 +486,7 @@ extern "C" int td_bn_bwd_finalize(const float* partials, int nrows, int channels
     return launch_status("bn_bwd_finalize");
 }
 
-extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const void* y, int dtype,
+extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const float* y, int dtype,
                                     const float* scale, const float* shift, const float* coef, void* dy,
                                     int64_t pixels, int channels, void* stream) {
     TD_REQUIRE_ARCH();
@@ -479,7 +496,7 @@ extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, c
     const int lanesC = channels / V;
     const int grid = stream_grid(pixels * lanesC, lanesC);
     TD_DISPATCH_T(dtype, (bn_relu_bwd_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
-                             (const T*)da, ldda, da_coff, (const T*)y, scale, shift, coef, (T*)dy, pixels, channels)));
+                             (const T*)da, ldda, da_coff, y, scale, shift, coef, (T*)dy, pixels, channels)));
     return launch_status("bn_relu_bwd_apply");
 }
 

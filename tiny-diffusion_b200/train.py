@@ -95,7 +95,9 @@ class UNetTrainEngine:
             self.last = "d1r"
         self.bufs = {k: buf(h, c) for k, (h, c) in shapes.items()}          # activations
         self.grads = {k: buf(h, c) for k, (h, c) in shapes.items()}         # dL/d(activation)
-        self.yraw = {name: buf(size, cout) for name, _, _, size, _, cout in self.layers}    # pre-BN conv outputs
+        # pre-BN conv outputs stay fp32: under the large per-sample time-embedding offsets a bf16 y loses
+        # the spatial signal before the normalisation (and flips ReLU masks in the backward)
+        self.yraw = {name: buf(size, cout, torch.float32) for name, _, _, size, _, cout in self.layers}
         max_y = max(B * size * size * cout for _, _, _, size, _, cout in self.layers)
         self.dy = torch.zeros(max_y, device=dev, dtype=self.act)             # dL/d(conv output), one layer at a time
         self.x_in = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
@@ -114,13 +116,15 @@ class UNetTrainEngine:
         self.bn: Dict[str, Dict[str, torch.Tensor]] = {}
         max_part = 1
         for name, _, _, size, _, cout in self.layers:
-            rows = int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout))
-            max_part = max(max_part, rows * 2 * cout)
+            rows = int(self.lib.td_chan_reduce_rows(L.TD_F32, B * size * size, cout))
+            rows_b = int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout))
+            max_part = max(max_part, (max(rows, rows_b) * 2 + 1) * cout)
             self.bn[name] = {k: torch.zeros(cout, device=dev) for k in ("scale", "shift", "mean", "invstd")}
             self.bn[name]["coef"] = torch.zeros(3, cout, device=dev)
             self.bn[name]["rows"] = rows
+            self.bn[name]["rows_bwd"] = rows_b
         rows0 = int(self.lib.td_chan_reduce_rows(self.adt, B * s0 * s0, c0))
-        max_part = max(max_part, rows0 * 2 * c0)
+        max_part = max(max_part, (rows0 * 2 + 1) * c0)
         self.rows_x0 = rows0
         self.partials = torch.zeros(max_part, device=dev)
 
@@ -256,7 +260,7 @@ class UNetTrainEngine:
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
 
             def bn_fwd(st):
-                L.check(lib.td_bn_stats(yp, adt, cout, 0, P, cout, part, st), "td_bn_stats")
+                L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
                 L.check(lib.td_bn_finalize(part, rows, cout, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, st),
                         "td_bn_finalize")
                 L.check(lib.td_bn_relu_apply(yp, sc, sh, ap, adt, cout, 0, P, cout, 1, st), "td_bn_relu_apply")
@@ -295,10 +299,9 @@ class UNetTrainEngine:
         for nm in ("dec1.0", "dec1.3"):
             add_block(*Ls[nm])
         if cfg.final_resize:
-            sp, dp = bf["d1"].data_ptr(), bf["d1r"].data_ptr()
-            u1, s0 = S["u1"], S["s0"]
-            fwd.append(("resize:d1r", lambda st: L.check(
-                lib.td_resize_bilinear_fwd(sp, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_fwd")))
+            fwd.append(("resize:d1r", lambda st, sp=bf["d1"].data_ptr(), dp=bf["d1r"].data_ptr(), u1=S["u1"], s0=S["s0"]:
+                        L.check(lib.td_resize_bilinear_fwd(sp, dp, adt, B, u1, u1, s0, s0, d1, st),
+                                "td_resize_bilinear_fwd")))
         fc = m.final_conv
         p = conv_plan("final_conv", self._conv_desc(bf[self.last], d1, self.eps, cfg.in_ch, self.w_fwd["final_conv"],
                                                     shift=fc.bias, y_nchw=True), L.CONV_DIRECT)
@@ -307,24 +310,22 @@ class UNetTrainEngine:
         # ---- backward --------------------------------------------------------------------------
         s0 = S["s0"]
         # final_conv: bias / weight gradients and the data gradient (a tiny-Cin direct conv of d_eps)
-        dep, fcb = self.d_eps.data_ptr(), self.pgrad["final_conv.bias"].data_ptr()
-        bwd.append(("final_conv:dbias", lambda st: L.check(
-            lib.td_nchw_chansum(dep, B, cfg.in_ch, s0 * s0, fcb, st), "td_nchw_chansum")))
+        bwd.append(("final_conv:dbias", lambda st, dep=self.d_eps.data_ptr(), fcb=self.pgrad["final_conv.bias"].data_ptr():
+                    L.check(lib.td_nchw_chansum(dep, B, cfg.in_ch, s0 * s0, fcb, st), "td_nchw_chansum")))
         self._wgrad("final_conv", bf[self.last], d1, self.d_eps, cfg.in_ch, s0, L.CONV_SIMT, dy_nchw=True)
         bwd.append(("final_conv:wgrad", None))
         p = conv_plan("final_conv:dgrad", self._conv_desc(self.d_eps, cfg.in_ch, gr[self.last], d1,
                                                           self.w_bwd["final_conv"], x_nchw=True), L.CONV_DIRECT)
         bwd.append(("final_conv:dgrad", p.run))
         if cfg.final_resize:
-            gp, dp = gr["d1r"].data_ptr(), gr["d1"].data_ptr()
-            u1 = S["u1"]
-            bwd.append(("resize:d1r:bwd", lambda st: L.check(
-                lib.td_resize_bilinear_bwd(gp, d1, 0, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_bwd")))
+            bwd.append(("resize:d1r:bwd", lambda st, gp=gr["d1r"].data_ptr(), dp=gr["d1"].data_ptr(), u1=S["u1"]:
+                        L.check(lib.td_resize_bilinear_bwd(gp, d1, 0, dp, adt, B, u1, u1, s0, s0, d1, st),
+                                "td_resize_bilinear_bwd")))
 
         def add_block_bwd(name, xin, cin, size, out, cout, need_dx=True):
             conv, bn = self.conv_of[name]
             st_ = self.bn[name]
-            rows, P = st_["rows"], B * size * size
+            rows, P = st_["rows_bwd"], B * size * size
             y, da = self.yraw[name], gr[out]
             dyv = self.dy[:P * cout].view(B, size, size, cout)
             yp, dap, dyp = y.data_ptr(), da.data_ptr(), dyv.data_ptr()
@@ -335,7 +336,7 @@ class UNetTrainEngine:
             db = self.pgrad[f"{blk}.{int(idx) + 1}.bias"].data_ptr()
 
             def bn_bwd(st):
-                L.check(lib.td_bn_relu_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, P, cout, part, st),
+                L.check(lib.td_bn_relu_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, mu, P, cout, part, st),
                         "td_bn_relu_bwd_reduce")
                 L.check(lib.td_bn_bwd_finalize(part, rows, cout, P, sc, mu, iv, dg, db, coef, st), "td_bn_bwd_finalize")
                 L.check(lib.td_bn_relu_bwd_apply(dap, cout, 0, yp, adt, sc, sh, coef, dyp, P, cout, st),
@@ -385,7 +386,7 @@ class UNetTrainEngine:
         P0 = B * s0 * s0
 
         def ic_bias(st):
-            L.check(lib.td_bn_stats(gx0, adt, c0, 0, P0, c0, part, st), "td_bn_stats")
+            L.check(lib.td_bn_stats(gx0, adt, c0, 0, P0, c0, part, 0, st), "td_bn_stats")
             L.check(lib.td_partial_sum(part, rows0, c0, 0, icb, st), "td_partial_sum")
         bwd.append(("initial_conv:dbias", ic_bias))
         self._wgrad("initial_conv", self.x_in, cfg.in_ch, gr["x0"], c0, s0, L.CONV_SIMT, x_nchw=True)
