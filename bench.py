@@ -126,6 +126,28 @@ def cpu_reference_samples_per_sec(reverse_steps: int, batch: int = PER_GPU_BATCH
     return batch / (per_step * T_STEPS), cores, dt
 
 
+def cpu_reference_train_imgs_per_sec(steps: int, batch: int = PER_GPU_BATCH):
+    """Time `steps` iterations of the reference train-step body (conditional_diffusion.py:254-263:
+    q_sample, train-mode forward, MSE, backward, Adam) at batch `batch` on all host cores."""
+    from oracle import ddpm_oracle as O
+    from oracle.fixtures import init_state_dict, make_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = init_state_dict(MODEL)
+    inp = make_inputs(MODEL, batch)
+    _, _, ac = O.make_schedule(T_STEPS)
+    m = {k: torch.zeros_like(v) for k, v in sd.items() if O.is_param(k)}
+    v = {k: torch.zeros_like(x) for k, x in sd.items() if O.is_param(k)}
+    t0 = time.perf_counter()
+    for step in range(1, steps + 1):
+        _, grads, stats, _ = O.unet_loss_and_grads(O.UNET_COND, sd, inp["x0"], inp["t"], inp["noise"], ac, inp["cond"])
+        for k in m:
+            sd[k], m[k], v[k] = O.adam_step(sd[k], grads[k], m[k], v[k], step)
+        sd.update(stats)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, cores, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -230,12 +252,71 @@ def run_gpu(args):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
+    # ---- training step (second half of the BASELINE metric: train imgs/sec) -----------------------
+    from tinydiff.train import TrainStep
+    torch.manual_seed(0)
+    tmodel = NoiseModel().to(dev).train()
+    tmodel.precision = args.precision
+    tfp = ForwardProcess(T_STEPS)
+    ts = TrainStep(tmodel, tfp, B, dev, lr=1e-3, use_graph=(world == 1))
+    x0_host = (torch.rand(B, 1, 28, 28, generator=gen) * 2 - 1).pin_memory()
+    x0_dev = x0_host.to(dev)
+    TS = args.train_steps
+
+    def train_dev_step():                      # inputs resident in HBM; t and noise drawn on the device
+        for _ in range(TS):
+            ts(x0_dev, y_dev)
+
+    def train_e2e_step():                      # host batch in, loss value out, every step
+        for _ in range(TS):
+            loss = ts(x0_host, y_host)
+            loss_host.copy_(loss)
+            torch.cuda.current_stream().synchronize()
+
+    loss_host = torch.zeros(1).pin_memory()
+    for _ in range(args.warmup):
+        train_dev_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        train_dev_step()
+    g1.record()
+    barrier()
+    train_ms = g0.elapsed_time(g1)
+    train_e2e_step()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for _ in range(args.steps):
+        train_e2e_step()
+    h1.record()
+    barrier()
+    train_e2e_ms = h0.elapsed_time(h1)
+    final_loss = float(loss_host)
+    assert final_loss == final_loss and final_loss < 1e6, f"training diverged: loss {final_loss}"
     clk = clocks.stop() if clocks else None
 
-    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([dev_ms, e2e_ms, train_ms, train_e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, train_ms, train_e2e_ms = (float(v) for v in t)
+    n_train = args.steps * TS
+    fwd_l, bwd_l = ts.eng.num_launches()
+    train = {
+        "metric": "ddpm_train_imgs_per_sec", "unit": "img/s",
+        "value": world * B * n_train / (train_ms / 1e3), "ms_per_step": train_ms / n_train, "train_steps": n_train,
+        "config": {"workload": f"{MODEL} UNet train step (randint t, q_sample, train-mode forward, MSE, backward, Adam), "
+                               f"batch {B}/GPU, data parallel x{world}"
+                               + (", bucketed NCCL gradient all-reduce overlapped with backward" if world > 1 else
+                                  ", whole step replayed as one CUDA graph")},
+        "e2e": {"value": world * B * n_train / (train_e2e_ms / 1e3), "unit": "img/s",
+                "h2d_bytes_per_step": int(x0_host.numel() * 4 + y_host.numel() * 8), "d2h_bytes_per_step": 4,
+                "ms_per_step": train_e2e_ms / n_train},
+        "gpu_launches_per_step": fwd_l + bwd_l + 5, "final_loss": final_loss,
+        "model_flops_per_step": ts.eng.conv_flops(),
+        "achieved_model_tflops": ts.eng.conv_flops() * n_train / (train_ms / 1e3) / 1e12,
+    }
     value = world * B * args.steps / (dev_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
 
@@ -262,12 +343,17 @@ def run_gpu(args):
             "roofline": roof,
             "model_flops_per_sample": eng.conv_flops() / B * T_STEPS,
             "achieved_model_tflops": value * eng.conv_flops() / B * T_STEPS / 1e12 / world,
+            "train": train,
         }
+        train["roofline_frac_of_sustained_bf16"] = train["achieved_model_tflops"] / peaks["bf16_sustained"]
         if world == 1 and not args.no_cpu_baseline:
             v, cores, dt = cpu_reference_samples_per_sec(args.cpu_reverse_steps)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{args.cpu_reverse_steps} of the {T_STEPS} reverse steps at batch {B} "
                                               f"({dt:.1f} s of CPU work), extrapolated to 1000"}
+            tv, cores, tdt = cpu_reference_train_imgs_per_sec(args.cpu_train_steps)
+            train["cpu_baseline"] = {"value": tv, "unit": "img/s", "cores": cores, "kind": "port",
+                                     "sample": f"{args.cpu_train_steps} train steps at batch {B} ({tdt:.1f} s of CPU work)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -328,6 +414,8 @@ def main():
     ap.add_argument("--cpu-reverse-steps", type=int, default=12)
     ap.add_argument("--ref-reverse-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=20, help="train steps per bench step")
+    ap.add_argument("--cpu-train-steps", type=int, default=3)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

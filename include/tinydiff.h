@@ -265,8 +265,8 @@ int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dtemb, int ld
                  int batch, int ho, int wo, int cu, int hs, int ws, int cs, void* stream);
 /* out[c] = sum_r partials[r][which][c] */
 int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream);
-/* out[c] = sum_{b,hw} x[b,c,hw]  (final_conv bias gradient) */
-int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, void* stream);
+/* out[c] = sum_{b,hw} x[b,c,hw]  (final_conv bias gradient); workspace: 128*channels floats */
+int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, float* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * fp32 dense layers: nn.Linear / nn.LayerNorm / nn.BatchNorm1d / nn.GELU / nn.SiLU of the

@@ -91,6 +91,87 @@ wgrad_simt_kernel(const td_wgrad_desc d, int pixels_per_split) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Network-boundary layers: one side of the product has 1..4 channels (NCHW fp32: the network input
+// of initial_conv, or d(eps) of final_conv), the other is a wide NHWC tensor.  Pure bandwidth: the
+// wide tensor is read once with 16-byte vectors, the narrow one comes from L1/L2 as scalars.
+//   final_conv  (narrow = dY, channel s = o):  dW[s][tap][c] = sum_p X[p, c]  * dY[p - off(tap), s]
+//   initial_conv(narrow = X,  channel s = i):  dW[c][tap][s] = sum_p dY[p, c] * X[p + off(tap), s]
+// grid = (CTAs over pixels, narrow channels); CTA partial -> ws[blockIdx.x][cout][9][cin].
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_narrow_kernel(const T* __restrict__ wide, int ldw, int w_coff, int cw, const float* __restrict__ narrow, int cn,
+                    int B, int H, int W, int narrow_is_dy, int cin, int cout, float* __restrict__ ws) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ float red[];                  // [rows][cw]
+    const int lanesC = cw / V;
+    const int rows = 256 / lanesC;
+    const int lane = threadIdx.x % lanesC, row = threadIdx.x / lanesC;
+    const int c0 = lane * V;
+    const int s = blockIdx.y;
+    const int sgn = narrow_is_dy ? -1 : 1;
+    const int64_t P = (int64_t)B * H * W;
+    float acc[9][V];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[t][k] = 0.f;
+    if (row < rows) {
+        for (int64_t p = (int64_t)blockIdx.x * rows + row; p < P; p += (int64_t)gridDim.x * rows) {
+            const int w_ = (int)(p % W);
+            const int64_t r = p / W;
+            const int h_ = (int)(r % H);
+            const int b_ = (int)(r / H);
+            float f[V];
+            Vec<T>::load(wide + p * ldw + w_coff + c0).unpack(f);
+            const float* nb = narrow + ((int64_t)b_ * cn + s) * H * W;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int hh = h_ + sgn * (t / 3 - 1), ww = w_ + sgn * (t % 3 - 1);
+                if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+                const float nv = __ldg(nb + hh * W + ww);
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[t][k] = fmaf(f[k], nv, acc[t][k]);
+            }
+        }
+    }
+    // cross-row reduction, one tap at a time through a [rows][cw] staging buffer (fixed order)
+    float* out = ws + (int64_t)blockIdx.x * cout * 9 * cin;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        if (row < rows) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) red[(size_t)row * cw + c0 + k] = acc[t][k];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < cw; c += 256) {
+            float tsum = 0.f;
+            for (int r = 0; r < rows; ++r) tsum += red[(size_t)r * cw + c];
+            if (narrow_is_dy) out[((int64_t)s * 9 + t) * cin + c] = tsum;          // o = s, cin = cw
+            else out[((int64_t)c * 9 + t) * cin + s] = tsum;                       // o = c, cin = cn
+        }
+        __syncthreads();
+    }
+}
+
+static bool narrow_ok(const td_wgrad_desc& d, int* grid_x) {
+    const bool fin = d.dy_nchw && d.dy_dtype == TD_F32 && d.cout <= 4 && !d.x_nchw;       // final_conv
+    const bool ini = d.x_nchw && d.x_dtype == TD_F32 && d.cin <= 4 && !d.dy_nchw;         // initial_conv
+    if (!fin && !ini) return false;
+    const int cw = fin ? d.cin : d.cout;
+    const int wdt = fin ? d.x_dtype : d.dy_dtype;
+    const int V = wdt == TD_BF16 ? 8 : 4;
+    if (cw % V != 0) return false;
+    const int lanesC = cw / V;
+    if (lanesC > 256 || (lanesC & (lanesC - 1)) != 0) return false;
+    const int rows = 256 / lanesC;
+    if ((size_t)rows * cw * sizeof(float) > 48 * 1024) return false;
+    const int64_t P = (int64_t)d.batch * d.height * d.width;
+    *grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(P, (int64_t)rows * 4), 2 * kNumSMs));
+    return true;
+}
+
 // dw[o][c][tap] = sum_s ws[s][o][tap*cin + c]     (OHWI partials -> OIHW gradient)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
@@ -123,6 +204,8 @@ pack_weight_dgrad_kernel(const float* __restrict__ oihw, T* __restrict__ out, in
 }
 
 static int simt_splits(const td_wgrad_desc& d) {
+    int gx = 0;
+    if (narrow_ok(d, &gx)) return gx;
     const int64_t P = (int64_t)d.batch * d.height * d.width;
     const int64_t base = ceil_div(9 * d.cin, WG_BN) * ceil_div(d.cout, WG_BM);
     int64_t s = ceil_div(2 * kNumSMs, base);
@@ -171,6 +254,25 @@ extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
     const td_wgrad_desc& d = p->d;
     if (p->engine == TD_CONV_TC) {
         int st = wgrad_tc_plan_run(p, s);
+        if (st != TD_OK) return st;
+    } else if (int gx = 0; narrow_ok(d, &gx)) {
+        const bool fin = d.dy_nchw != 0;
+        const int cw = fin ? d.cin : d.cout, cn = fin ? d.cout : d.cin;
+        const int wdt = fin ? d.x_dtype : d.dy_dtype;
+        const int V = wdt == TD_BF16 ? 8 : 4;
+        const size_t smem = (size_t)(256 / (cw / V)) * cw * sizeof(float);
+        const void* wide = fin ? d.x : d.dy;
+        const float* narrow = (const float*)(fin ? d.dy : d.x);
+        const int ldw = fin ? d.ldx : d.lddy, wcoff = fin ? d.x_coff : d.dy_coff;
+        dim3 grid((unsigned)gx, (unsigned)cn);
+        if (wdt == TD_BF16)
+            wgrad_narrow_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)wide, ldw, wcoff, cw, narrow, cn,
+                                                                        d.batch, d.height, d.width, fin ? 1 : 0, d.cin, d.cout,
+                                                                        d.workspace);
+        else
+            wgrad_narrow_kernel<float><<<grid, 256, smem, s>>>((const float*)wide, ldw, wcoff, cw, narrow, cn, d.batch,
+                                                               d.height, d.width, fin ? 1 : 0, d.cin, d.cout, d.workspace);
+        int st = launch_status("wgrad_narrow");
         if (st != TD_OK) return st;
     } else {
         const int64_t P = (int64_t)d.batch * d.height * d.width;

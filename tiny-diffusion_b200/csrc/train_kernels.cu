@@ -370,15 +370,18 @@ partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int whi
     out[c] = (float)s;
 }
 
-// per-channel sum of an NCHW fp32 tensor (final_conv bias gradient): grid (C), fixed-order tree
+// per-channel sum of an NCHW fp32 tensor (final_conv bias gradient): grid (chunks, C) partial sums,
+// then a fixed-order finalize
+constexpr int kChanSumChunks = 128;
 __global__ void __launch_bounds__(kT)
-nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ out) {
-    __shared__ double red[kT];
-    const int c = blockIdx.x;
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < (int64_t)B * HW; i += kT) {
+nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ ws) {
+    __shared__ float red[kT];
+    const int c = blockIdx.y;
+    const int64_t total = (int64_t)B * HW;
+    float s = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
         const int b = (int)(i / HW), p = (int)(i % HW);
-        s += (double)x[((int64_t)b * C + c) * HW + p];
+        s += x[((int64_t)b * C + c) * HW + p];
     }
     red[threadIdx.x] = s;
     __syncthreads();
@@ -386,7 +389,14 @@ nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[c] = (float)red[0];
+    if (threadIdx.x == 0) ws[(size_t)c * gridDim.x + blockIdx.x] = red[0];
+}
+__global__ void nchw_chansum_finalize_kernel(const float* __restrict__ ws, int chunks, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int i = 0; i < chunks; ++i) s += (double)ws[(size_t)c * chunks + i];
+    out[c] = (float)s;
 }
 
 static inline int reduce_grid(int64_t P, int rows) {
@@ -560,9 +570,12 @@ extern "C" int td_partial_sum(const float* partials, int nrows, int channels, in
     return launch_status("partial_sum");
 }
 
-extern "C" int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, void* stream) {
+extern "C" int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out, float* workspace,
+                               void* stream) {
     TD_REQUIRE_ARCH();
-    TD_CHECK_ARG(x && out && batch > 0 && channels > 0 && hw > 0, "td_nchw_chansum: bad args");
-    nchw_chansum_kernel<<<channels, kT, 0, (cudaStream_t)stream>>>(x, batch, channels, hw, out);
+    TD_CHECK_ARG(x && out && workspace && batch > 0 && channels > 0 && hw > 0, "td_nchw_chansum: bad args");
+    cudaStream_t s = (cudaStream_t)stream;
+    nchw_chansum_kernel<<<dim3(kChanSumChunks, channels), kT, 0, s>>>(x, batch, channels, hw, workspace);
+    nchw_chansum_finalize_kernel<<<(channels + 63) / 64, 64, 0, s>>>(workspace, kChanSumChunks, channels, out);
     return launch_status("nchw_chansum");
 }

@@ -19,6 +19,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
+from .dp import allreduce_mean_, grad_ready_index, plan_buckets   # noqa: F401
 from .unet import UNetConfig, _CONVS, _ConvPlan, _pool
 
 BN_EPS_DEFAULT = 1e-5
@@ -124,7 +125,7 @@ class UNetTrainEngine:
             self.bn[name]["rows"] = rows
             self.bn[name]["rows_bwd"] = rows_b
         rows0 = int(self.lib.td_chan_reduce_rows(self.adt, B * s0 * s0, c0))
-        max_part = max(max_part, (rows0 * 2 + 1) * c0)
+        max_part = max(max_part, (rows0 * 2 + 1) * c0, 128 * cfg.in_ch)
         self.rows_x0 = rows0
         self.partials = torch.zeros(max_part, device=dev)
 
@@ -311,7 +312,7 @@ class UNetTrainEngine:
         s0 = S["s0"]
         # final_conv: bias / weight gradients and the data gradient (a tiny-Cin direct conv of d_eps)
         bwd.append(("final_conv:dbias", lambda st, dep=self.d_eps.data_ptr(), fcb=self.pgrad["final_conv.bias"].data_ptr():
-                    L.check(lib.td_nchw_chansum(dep, B, cfg.in_ch, s0 * s0, fcb, st), "td_nchw_chansum")))
+                    L.check(lib.td_nchw_chansum(dep, B, cfg.in_ch, s0 * s0, fcb, part, st), "td_nchw_chansum")))
         self._wgrad("final_conv", bf[self.last], d1, self.d_eps, cfg.in_ch, s0, L.CONV_SIMT, dy_nchw=True)
         bwd.append(("final_conv:wgrad", None))
         p = conv_plan("final_conv:dgrad", self._conv_desc(self.d_eps, cfg.in_ch, gr[self.last], d1,
@@ -561,17 +562,13 @@ class TrainStep:
         self.m = torch.zeros_like(self.flat_grad)
         self.v = torch.zeros_like(self.flat_grad)
         self._adam_tables()
-        # buckets in reverse registration order ~ reverse execution order of the backward
-        self.buckets: List[Tuple[int, int]] = []
-        lim = int(bucket_mb * 1024 * 1024 / 4)
-        end = self.flat_grad.numel()
-        cur = end
-        for o in reversed(self.offsets):
-            if cur - o >= lim:
-                self.buckets.append((o, cur))
-                cur = o
-        if cur > 0:
-            self.buckets.append((0, cur))
+        # gradient buckets: contiguous ranges of the flat buffer, each all-reduced as soon as the backward
+        # entry that finalises its last gradient has been enqueued (overlaps the rest of the backward)
+        ready = grad_ready_index(self.names, [n for n, _ in e.bwd_ops])
+        self.buckets = plan_buckets(self.offsets, sizes, ready, int(bucket_mb * 1024 * 1024 / 4))
+        self._ready_at: Dict[int, List[Tuple[int, int]]] = {}
+        for lo, hi, r in self.buckets:
+            self._ready_at.setdefault(max(r, 0), []).append((lo, hi))
         self.graph = None
 
     def _adam_tables(self):
@@ -606,13 +603,23 @@ class TrainStep:
         n = e.eps.numel()
         L.check(lib.td_mse_grad(e.eps.data_ptr(), self.noise.data_ptr(), e.d_eps.data_ptr(), self.loss.data_ptr(),
                                 self.partials.data_ptr(), self.counter.data_ptr(), n, 1.0 / n, st), "td_mse_grad")
-        e.launch_backward()
+        if self.world == 1:
+            e.launch_backward()
+            return
+        # data parallel: NCCL all-reduce of each bucket is enqueued (async, on NCCL's stream) right after the
+        # backward entry that completes it, so the exchange overlaps the remaining backward kernels
+        self._works = []
+        for i, (_, fn) in enumerate(e.bwd_ops):
+            fn(st)
+            for lo, hi in self._ready_at.get(i, ()):
+                self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
 
     def _allreduce(self):
         if self.world == 1:
             return
-        for lo, hi in self.buckets:
-            torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg)
+        for w in self._works:
+            w.wait()
+        self._works = []
 
     def _update(self):
         lib, st = self.lib, L.stream_ptr()
