@@ -173,7 +173,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -354,7 +354,7 @@ def run_gpu(args):
             tv, cores, tdt = cpu_reference_train_imgs_per_sec(args.cpu_train_steps)
             train["cpu_baseline"] = {"value": tv, "unit": "img/s", "cores": cores, "kind": "port",
                                      "sample": f"{args.cpu_train_steps} train steps at batch {B} ({tdt:.1f} s of CPU work)"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -404,6 +404,37 @@ def conv_roofline(eng, peaks, iters=3):
             "per_kernel_us": {n: round(acc[n] * 1e3, 2) for n in names}}
 
 
+class _StdoutGuard:
+    """Keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1,
+    so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text: str):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+
+
+_GUARD = None
+
+
+def emit_line(line: dict):
+    text = json.dumps(line)
+    if _GUARD is not None:
+        _GUARD.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -417,10 +448,14 @@ def main():
     ap.add_argument("--train-steps", type=int, default=20, help="train steps per bench step")
     ap.add_argument("--cpu-train-steps", type=int, default=3)
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    global _GUARD
+    with _StdoutGuard() as g:
+        _GUARD = g
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_gpu(args)
+        _GUARD = None
 
 
 if __name__ == "__main__":

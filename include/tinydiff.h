@@ -277,6 +277,7 @@ int td_nchw_chansum(const float* x, int batch, int channels, int hw, float* out,
 #define TD_ACT_RELU 1
 #define TD_ACT_SILU 2
 #define TD_ACT_GELU 3      /* exact (erf) GELU, nn.GELU() default */
+#define TD_ACT_SIGMOID 4
 /* C[i,j] = epilogue( alpha * sum_k A(i,k) * B(k,j) ),  A(i,k) = A[i*a_rs + k*a_cs], B(k,j) = B[k*b_rs + j*b_cs]
  * epilogue(v): v += bias[j]; pre_out[i,j] = v; v = act(v); v += residual[i,j]; v += gather_table[gather_idx[i], j];
  *              if (accumulate) v += C[i,j]
@@ -299,6 +300,14 @@ int64_t td_gemm_f32_workspace(int M, int N, int K);
 int td_gemm_f32(const td_gemm_args* a, void* stream);
 int td_colsum_f32(const float* x, int64_t ldx, float* out, int M, int N, int accumulate, void* stream);
 int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream);
+/* dst[i,j] (+)= src[i,j] on strided fp32 matrices (residual-branch gradients) */
+int td_add2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int accumulate,
+                 void* stream);
+/* nn.Dropout / attention-weight dropout at L=1 (diffusion_transformer.py:19,27,29): out = x*keep/(1-p), one
+ * Bernoulli draw per `group` consecutive columns; Philox keyed by seed_ptr[0], subsequence seed_ptr[1].
+ * Applying the same call to a gradient is the backward. */
+int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int cols, int group, float p,
+                   const uint64_t* seed_ptr, void* stream);
 /* table_grad[c,:] = sum_{i: idx[i]==c} g[i,:]   (nn.Embedding backward, conditional_diffusion.py:31) */
 int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx, float* table_grad, int M, int D, int num_rows,
                      int accumulate, void* stream);

@@ -79,6 +79,41 @@ def _dit_modules(time_dim=256, num_classes=10, latent_dim=20, heads=4, layers=4,
     return m
 
 
+def _lbr(cin, cout):
+    return [nn.Linear(cin, cout), nn.BatchNorm1d(cout), nn.ReLU()]
+
+
+def _mlp_modules(time_dim=256, num_classes=10, latent_dim=20) -> nn.Module:
+    """latent_diffusion.py:17-105 (registration order = RNG consumption order)."""
+    m = nn.Module()
+    m.time_embedding = nn.Sequential(nn.Linear(1, time_dim), nn.SiLU(), nn.Linear(time_dim, time_dim))
+    m.class_embedding = nn.Embedding(num_classes, time_dim)
+    m.initial_fc = nn.Linear(latent_dim, 512)
+    m.enc1 = nn.Sequential(*_lbr(512, 512), *_lbr(512, 256))
+    m.enc2 = nn.Sequential(*_lbr(256, 256), *_lbr(256, 128))
+    m.enc3 = nn.Sequential(*_lbr(128, 128), *_lbr(128, 64))
+    m.bottleneck = nn.Sequential(*_lbr(64, 64))
+    m.dec3 = nn.Sequential(*_lbr(128, 128), *_lbr(128, 128))
+    m.dec2 = nn.Sequential(*_lbr(256, 256), *_lbr(256, 256))
+    m.dec1 = nn.Sequential(*_lbr(512, 512), *_lbr(512, 512))
+    m.final_fc = nn.Linear(512, latent_dim)
+    m.time_proj1 = nn.Linear(time_dim, 64)
+    m.time_proj2 = nn.Linear(time_dim, 128)
+    m.time_proj3 = nn.Linear(time_dim, 256)
+    return m
+
+
+def _vae_modules(input_dim=784, hidden_dim=400, latent_dim=20) -> nn.Module:
+    """vae.py:42-49."""
+    m = nn.Module()
+    m.fc1 = nn.Linear(input_dim, hidden_dim)
+    m.fc21 = nn.Linear(hidden_dim, latent_dim)
+    m.fc22 = nn.Linear(hidden_dim, latent_dim)
+    m.fc3 = nn.Linear(latent_dim, hidden_dim)
+    m.fc4 = nn.Linear(hidden_dim, input_dim)
+    return m
+
+
 def make_modules(modname: str) -> nn.Module:
     if modname == "diffusion":
         return _unet_modules(1, 64, 128, 256, 512, 512, 256, "linear")
@@ -88,6 +123,10 @@ def make_modules(modname: str) -> nn.Module:
         return _unet_modules(4, 32, 64, 128, 256, 256, 768, "sinusoidal+text")
     if modname == "diffusion_transformer":
         return _dit_modules()
+    if modname == "latent_diffusion":
+        return _mlp_modules()
+    if modname == "vae":
+        return _vae_modules()
     raise KeyError(modname)
 
 
@@ -143,7 +182,7 @@ def make_inputs(modname: str, B: int, seed: int = DATA_SEED) -> Dict[str, torch.
         out["x0"] = torch.randn(B, 20, generator=g)
     out["t"] = torch.randint(0, 1000, (B,), generator=g)
     out["noise"] = torch.randn(out["x0"].shape, generator=g)
-    if modname in ("conditional_diffusion", "diffusion_transformer"):
+    if modname in ("conditional_diffusion", "diffusion_transformer", "latent_diffusion"):
         out["cond"] = torch.randint(0, 10, (B,), generator=g)
     elif modname == "conditional_diffusion_laion":
         out["cond"] = torch.randn(B, 768, generator=g)

@@ -15,7 +15,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import reference_shim as shim          # noqa: E402
-from oracle.fixtures import (build_reference_model, make_inputs, perturb_bn, checksum,   # noqa: E402
+from oracle.fixtures import (init_state_dict, build_reference_model, make_inputs, perturb_bn, checksum,   # noqa: E402
                              injected_randn)
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -139,6 +139,44 @@ def dit_case(B: int = 8):
     print(modname, "loss", float(loss))
 
 
+def mlp_case(B: int = 8):
+    modname = "latent_diffusion"
+    ref = shim.load(modname)
+    model = build_reference_model(ref, modname)
+    perturb_bn(model)
+    fp = ref.ForwardProcess()
+    inp = make_inputs(modname, B)
+    g = {}
+    with injected_randn(ref, [inp["noise"]]):
+        x_t, noise = fp.q_sample(torch.device("cpu"), inp["x0"], inp["t"])
+    g["x_t"] = x_t.clone()
+    model.eval()
+    with torch.no_grad():
+        g["eps_eval"] = model(x_t, inp["t"], inp["cond"]).clone()
+    model.train()
+    pred = model(x_t, inp["t"], inp["cond"])
+    loss = torch.nn.functional.mse_loss(pred, noise)
+    loss.backward()
+    g["eps_train"] = pred.detach().clone()
+    g["loss"] = loss.detach().clone()
+    g["grad_checksums"] = {k: checksum(p.grad) for k, p in model.named_parameters()}
+    g["buffers_after"] = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "tracked" in k}
+    # VAE edges (vae.py:51-62) with seeded weights
+    vae_mod = shim.load("vae")
+    state = torch.get_rng_state()
+    torch.manual_seed(0)
+    vae = vae_mod.VAE(vae_mod.VAEConfig())
+    torch.set_rng_state(state)
+    xs = torch.rand(4, 784, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        mu, logvar = vae.encode(xs)
+        g["vae"] = {"x": xs, "mu": mu.clone(), "logvar": logvar.clone(), "dec": vae.decode(mu).clone()}
+    fix = init_state_dict("vae", perturb=False)          # the fixture init reproduces VAE() under seed 0
+    assert all(torch.equal(fix[k], v) for k, v in vae.state_dict().items())
+    torch.save(g, os.path.join(OUT, f"{modname}.pt"))
+    print(modname, "loss", float(loss))
+
+
 if __name__ == "__main__":
     assert shim.available(), "reference not mounted"
     torch.set_num_threads(os.cpu_count() or 1)
@@ -146,3 +184,4 @@ if __name__ == "__main__":
     unet_case("conditional_diffusion")
     laion_case()
     dit_case()
+    mlp_case()

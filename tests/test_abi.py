@@ -90,10 +90,11 @@ def test_state_dict_layout_matches_fixture_modules():
     """state_dict keys / shapes / dtypes identical to the reference layout."""
     from oracle.fixtures import init_state_dict
     import importlib
-    for name in ("diffusion", "conditional_diffusion", "conditional_diffusion_laion"):
+    for name in ("diffusion", "conditional_diffusion", "conditional_diffusion_laion", "latent_diffusion",
+                 "diffusion_transformer"):
         mod = importlib.import_module(f"tinydiff.{name}")
         model = mod.NoiseModel()
-        ref = init_state_dict(name)
+        ref = init_state_dict(name, perturb=(name != "diffusion_transformer"))
         mine = model.state_dict()
         assert list(mine.keys()) == list(ref.keys()), name
         for k in ref:

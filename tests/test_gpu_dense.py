@@ -1,0 +1,271 @@
+"""Parity of the two latent denoisers on a real B200: the MLP "U-Net" (latent_diffusion.py:16-128)
+and the length-1 "DiT" (diffusion_transformer.py:16-109), plus the VAE edges (vae.py:51-62).
+All fp32: eps / loss / gradients within 1e-4 of the CPU oracle (5e-4 for the BatchNorm1d MLP whose
+tiny-batch statistics amplify rounding)."""
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ddpm_oracle as O                        # noqa: E402  (checker only)
+from oracle.fixtures import init_state_dict, make_inputs   # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    from tinydiff import _lib as L
+    return L.require_device("cuda:0")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build(name, dev, train=False, **kw):
+    mod = importlib.import_module(f"tinydiff.{name}")
+    model = mod.NoiseModel(**kw)
+    sd = init_state_dict(name, perturb=(name == "latent_diffusion"))
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev)
+    return mod, (model.train() if train else model.eval()), sd
+
+
+FWD = {"latent_diffusion": lambda leaf, x, t, c, ns, tr=False: O.mlp_forward(leaf, x, t, c, training=tr, new_stats=ns),
+       "diffusion_transformer": lambda leaf, x, t, c, ns, tr=False: O.dit_forward(leaf, x, t, c)}
+KW = {"latent_diffusion": {}, "diffusion_transformer": {"dropout": 0.0}}
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_eval_forward_vs_golden(dev, golden, name):
+    g = golden(name)
+    mod, model, sd = build(name, dev, **KW[name])
+    inp = make_inputs(name, g["x_t"].shape[0])
+    with torch.no_grad():
+        eps = model(g["x_t"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+    assert eps.shape == g["eps_eval"].shape
+    assert rel(eps, g["eps_eval"]) < 1e-5
+    # ragged batch against the oracle
+    inp = make_inputs(name, 37, seed=5)
+    with torch.no_grad():
+        got = model(inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+        want = FWD[name](sd, inp["x0"], inp["t"], inp["cond"], None)
+    assert rel(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_train_step_autograd_vs_oracle(dev, golden, name):
+    """q_sample -> model -> mse_loss -> backward -> Adam with the drop-in classes
+    (latent_diffusion.py:207-223 / diffusion_transformer.py:189-202)."""
+    g = golden(name)
+    mod, model, sd = build(name, dev, train=True, **KW[name])
+    B = g["x_t"].shape[0]
+    inp = make_inputs(name, B)
+    fp = mod.ForwardProcess()
+    fwd = lambda leaf, x, t, c, ns: FWD[name](leaf, x, t, c, ns, True)
+    loss_ref, grads_ref, stats_ref, pred_ref = O.dense_loss_and_grads(fwd, sd, inp["x0"], inp["t"], inp["noise"],
+                                                                     fp.alphas_cumprod, inp["cond"])
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    x_t, noise = fp.q_sample(dev, inp["x0"], inp["t"].to(dev), noise=inp["noise"])
+    assert torch.equal(x_t.cpu(), g["x_t"])
+    pred = model(x_t, inp["t"].to(dev), inp["cond"].to(dev))
+    loss = F.mse_loss(pred, noise)
+    opt.zero_grad()
+    loss.backward()
+    tol = 5e-4 if name == "latent_diffusion" else 1e-4
+    assert rel(pred, pred_ref) < tol
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    bad = {}
+    for k, p in model.named_parameters():
+        ref = grads_ref[k]
+        if float(ref.norm()) < 1e-7:
+            # Linear biases in front of a train-mode BatchNorm1d (MLP); everything else must be exactly zero
+            assert float(p.grad.abs().max()) < 1e-6, k
+            continue
+        if k.endswith("in_proj_weight") or k.endswith("in_proj_bias"):
+            D = 256
+            assert float(p.grad[:2 * D].abs().max()) == 0.0, k        # dead Q / K projections
+        e = rel(p.grad, ref)
+        if e > 2e-3:
+            bad[k] = e
+    assert not bad, bad
+    for k, v in stats_ref.items():
+        got = dict(model.named_buffers())[k]
+        assert rel(got.float(), v.float()) < 1e-5, k
+    opt.step()
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_sampler_vs_oracle(dev, name):
+    """Reverse loop with injected x_T / z (short schedule) against the oracle's sample_loop."""
+    mod, model, sd = build(name, dev, **KW[name])
+    T, n = 50, 5
+    fp = mod.ForwardProcess(num_timesteps=T)
+    betas, alphas, ac = O.make_schedule(T)
+    g = torch.Generator().manual_seed(3)
+    x_T = torch.randn(n, 20, generator=g)
+    z = torch.randn(T, n, 20, generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    zs = [None] + [z[t] for t in range(1, T)]
+    want, _ = O.sample_loop(lambda x, t: FWD[name](sd, x, torch.full((n,), t), y, None), x_T, zs, betas, alphas, ac)
+    for use_graph in (False, True):
+        from tinydiff.dense import dense_sample
+        got = dense_sample(None, model, fp, dev, n, y.to(dev), x_T=x_T, z=z.to(dev), use_graph=use_graph)
+        assert rel(got, want) < 1e-4, use_graph
+    with pytest.raises(ValueError):
+        mod.sample(None, model, fp, dev, n_samples=n, y=None)
+    with pytest.raises(ValueError):
+        mod.sample(None, model, fp, dev, n_samples=n + 1, y=y.to(dev))
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_train_step(dev, name, use_graph):
+    from tinydiff.train import TrainStep
+    mod, model, sd0 = build(name, dev, train=True, **KW[name])
+    B = 16
+    fp = mod.ForwardProcess()
+    ts = TrainStep(model, fp, B, dev, lr=3e-4, use_graph=use_graph)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    m = {k: torch.zeros_like(v) for k, v in sd.items() if O.is_param(k)}
+    v_ = {k: torch.zeros_like(v) for k, v in sd.items() if O.is_param(k)}
+    fwd = lambda leaf, x, t, c, ns: FWD[name](leaf, x, t, c, ns, True)
+    for step in (1, 2):
+        inp = make_inputs(name, B, seed=700 + step)
+        loss_ref, grads, stats, _ = O.dense_loss_and_grads(fwd, sd, inp["x0"], inp["t"], inp["noise"], fp.alphas_cumprod,
+                                                          inp["cond"])
+        loss = ts(inp["x0"], inp["cond"], t=inp["t"], noise=inp["noise"])
+        assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < 2e-4
+        for k in m:
+            g_ = grads[k]
+            if float(g_.norm()) < 1e-7:
+                g_ = torch.zeros_like(g_)
+            sd[k], m[k], v_[k] = O.adam_step(sd[k], g_, m[k], v_[k], step, lr=3e-4)
+        sd.update(stats)
+    got = model.state_dict()
+    for k in m:
+        upd_ref = sd[k] - sd0[k]
+        if float(upd_ref.norm()) == 0:
+            continue
+        assert rel(got[k].cpu() - sd0[k], upd_ref) < 5e-2, k
+        assert rel(got[k], sd[k]) < 1e-4, k
+
+
+def test_dit_dropout_train_mode(dev):
+    """dropout = 0.05 (the reference default) in train mode: masks are Bernoulli(0.95)/0.95, shared per
+    (sample, head) on the attention branch; eval mode is unaffected; gradients stay finite and the
+    dead Q/K rows stay exactly zero."""
+    import ctypes as C
+    from tinydiff import _lib as L
+    lib = L.load()
+    rows, cols, group, p = 512, 256, 64, 0.05
+    x = torch.ones(rows, cols, device=dev)
+    out = torch.empty_like(x)
+    seed = torch.tensor([1234, 7], dtype=torch.int64, device=dev)
+    L.check(lib.td_dropout_f32(x.data_ptr(), cols, out.data_ptr(), cols, rows, cols, group, p, seed.data_ptr(),
+                               L.stream_ptr()))
+    vals = out.unique()
+    assert set(round(float(v), 5) for v in vals) <= {0.0, round(1 / 0.95, 5)}
+    assert torch.equal(out.view(rows, cols // group, group).amax(-1), out.view(rows, cols // group, group).amin(-1))
+    keep = float((out > 0).float().mean())
+    assert abs(keep - 0.95) < 0.02
+    out2 = torch.empty_like(x)
+    L.check(lib.td_dropout_f32(x.data_ptr(), cols, out2.data_ptr(), cols, rows, cols, group, p, seed.data_ptr(),
+                               L.stream_ptr()))
+    assert torch.equal(out, out2)
+    mod, model, sd = build("diffusion_transformer", dev, train=True, dropout=0.05)
+    inp = make_inputs("diffusion_transformer", 64)
+    args = (inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+    torch.manual_seed(1)
+    a = model(*args)
+    b = model(*args)
+    assert rel(a, b) > 1e-3                                   # different masks per call
+    loss = F.mse_loss(a, inp["noise"].to(dev))
+    loss.backward()
+    assert all(torch.isfinite(q.grad).all() for q in model.parameters())
+    assert float(model.transformer_blocks[0].attention.in_proj_weight.grad[:512].abs().max()) == 0.0
+    want = O.dit_forward(sd, inp["x0"], inp["t"], inp["cond"])
+    assert 1e-3 < rel(a, want) < 0.5                          # a perturbation of the dropout-free output
+    with torch.no_grad():
+        assert rel(model.eval()(*args), want) < 1e-5
+
+
+def test_vae_edges(dev, golden):
+    from tinydiff.vae import VAE
+    g = golden("latent_diffusion")["vae"]
+    vae = VAE()
+    vae.load_state_dict(init_state_dict("vae", perturb=False), strict=True)
+    vae = vae.to(dev).eval()
+    mu, logvar = vae.encode(g["x"].to(dev))
+    assert rel(mu, g["mu"]) < 1e-5 and rel(logvar, g["logvar"]) < 1e-5
+    assert rel(vae.decode(mu), g["dec"]) < 1e-5
+    eps = torch.randn_like(mu)
+    assert rel(vae.reparameterize(mu, logvar, eps), O.vae_reparameterize(mu.cpu(), logvar.cpu(), eps.cpu())) < 1e-6
+    # the sampler tail: decode(z).view(-1, 1, 28, 28)   (latent_diffusion.py:346)
+    from tinydiff.latent_diffusion import ForwardProcess, NoiseModel, sample
+    model = NoiseModel()
+    model.load_state_dict(init_state_dict("latent_diffusion"))
+    model = model.to(dev)
+    x = sample(vae, model, ForwardProcess(num_timesteps=5), dev, n_samples=3, y=torch.tensor([1, 2, 3], device=dev), seed=1)
+    assert x.shape == (3, 1, 28, 28) and float(x.min()) >= 0 and float(x.max()) <= 1
+
+
+@pytest.mark.parametrize("M,D", [(8, 256), (37, 20), (128, 1024)])
+def test_layernorm_kernels(dev, M, D):
+    import ctypes as C
+    from tinydiff import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, D, generator=g) * 3 + 1
+    gamma, beta = torch.rand(D, generator=g) + 0.5, torch.randn(D, generator=g)
+    dy = torch.randn(M, D, generator=g)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br)
+    yr.backward(dy)
+    xd, gd, bd, dyd = x.to(dev), gamma.to(dev), beta.to(dev), dy.to(dev)
+    y, mean, rstd = torch.empty_like(xd), torch.empty(M, device=dev), torch.empty(M, device=dev)
+    st = L.stream_ptr()
+    L.check(lib.td_layernorm_fwd(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                 rstd.data_ptr(), M, D, 1e-5, st))
+    assert rel(y, yr) < 1e-5
+    dx, dg, db = torch.empty_like(xd), torch.empty(D, device=dev), torch.empty(D, device=dev)
+    L.check(lib.td_layernorm_bwd(dyd.data_ptr(), xd.data_ptr(), gd.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                 dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, st))
+    assert rel(dx, xr.grad) < 1e-5 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,relu", [(8, 64, True), (128, 512, True), (37, 100, False)])
+def test_bn1d_kernels(dev, M, N, relu):
+    from tinydiff import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(M, N, generator=g) * 2 + 5
+    gamma, beta = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g) * 0.1
+    rm, rv = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.5
+    dy = torch.randn(M, N, generator=g)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    yr = F.batch_norm(xr, rm_r, rv_r, gr, br, True, 0.1, 1e-5)
+    yr = F.relu(yr) if relu else yr
+    yr.backward(dy)
+    d = lambda t: t.to(dev)
+    xd, gd, bd, rmd, rvd, dyd = d(x), d(gamma), d(beta), d(rm), d(rv), d(dy)
+    y, sm, sr = torch.empty_like(xd), torch.empty(N, device=dev), torch.empty(N, device=dev)
+    st = L.stream_ptr()
+    L.check(lib.td_bn1d_fwd(xd.data_ptr(), N, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(), sm.data_ptr(),
+                            sr.data_ptr(), y.data_ptr(), N, M, N, 1e-5, 0.1, 1, int(relu), st))
+    assert rel(y, yr) < 1e-5 and rel(rmd, rm_r) < 1e-6 and rel(rvd, rv_r) < 1e-5
+    dx, dg, db = torch.empty_like(xd), torch.empty(N, device=dev), torch.empty(N, device=dev)
+    L.check(lib.td_bn1d_bwd(dyd.data_ptr(), N, xd.data_ptr(), N, y.data_ptr(), N, gd.data_ptr(), sm.data_ptr(),
+                            sr.data_ptr(), dx.data_ptr(), N, dg.data_ptr(), db.data_ptr(), M, N, int(relu), st))
+    assert rel(dx, xr.grad) < 2e-5 and rel(dg, gr.grad) < 2e-5 and rel(db, br.grad) < 1e-5
+    # eval mode uses the running statistics
+    ye = torch.empty_like(xd)
+    L.check(lib.td_bn1d_fwd(xd.data_ptr(), N, gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(), None, None,
+                            ye.data_ptr(), N, M, N, 1e-5, 0.1, 0, int(relu), st))
+    want = F.batch_norm(x, rm_r, rv_r, gamma, beta, False, 0.1, 1e-5)
+    assert rel(ye, F.relu(want) if relu else want) < 1e-5

@@ -111,3 +111,46 @@ def test_dit(golden):
     with torch.no_grad():
         eps = O.dit_forward(sd, x_t, inp["t"], inp["cond"])
     assert rel(eps, g["eps_eval"]) < 1e-5
+
+
+def test_latent_mlp_and_vae(golden):
+    """latent_diffusion.NoiseModel (latent_diffusion.py:16-128) and the VAE edges (vae.py:51-62)."""
+    g = golden("latent_diffusion")
+    sd = init_state_dict("latent_diffusion")
+    B = g["x_t"].shape[0]
+    inp = make_inputs("latent_diffusion", B)
+    _, _, ac = O.make_schedule()
+    x_t = O.q_sample(ac, inp["x0"], inp["t"], inp["noise"])
+    assert torch.equal(x_t, g["x_t"])
+    with torch.no_grad():
+        assert rel(O.mlp_forward(sd, x_t, inp["t"], inp["cond"]), g["eps_eval"]) < 1e-6
+    fwd = lambda leaf, x, t, c, ns: O.mlp_forward(leaf, x, t, c, training=True, new_stats=ns)
+    loss, grads, stats, pred = O.dense_loss_and_grads(fwd, sd, inp["x0"], inp["t"], inp["noise"], ac, inp["cond"])
+    assert rel(pred, g["eps_train"]) < 1e-6
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-6)
+    for k, cs in g["grad_checksums"].items():
+        if float(cs[1]) < 1e-6:
+            assert float(checksum(grads[k])[1]) < 1e-5, k
+        else:
+            assert float(checksum(grads[k])[1]) == pytest.approx(float(cs[1]), rel=1e-4), k
+    for k, v in g["buffers_after"].items():
+        assert rel(stats[k].float(), v.float()) < 1e-6, k
+    vsd = init_state_dict("vae", perturb=False)
+    mu, logvar = O.vae_encode(vsd, g["vae"]["x"])
+    assert rel(mu, g["vae"]["mu"]) < 1e-6 and rel(logvar, g["vae"]["logvar"]) < 1e-6
+    assert rel(O.vae_decode(vsd, mu), g["vae"]["dec"]) < 1e-6
+
+
+def test_dit_grads(golden):
+    g = golden("diffusion_transformer")
+    sd = init_state_dict("diffusion_transformer", perturb=False)
+    inp = make_inputs("diffusion_transformer", g["x_t"].shape[0])
+    _, _, ac = O.make_schedule()
+    fwd = lambda leaf, x, t, c, ns: O.dit_forward(leaf, x, t, c)
+    loss, grads, _, _ = O.dense_loss_and_grads(fwd, sd, inp["x0"], inp["t"], inp["noise"], ac, inp["cond"])
+    assert float(loss) == pytest.approx(float(g["loss"]), rel=1e-5)
+    for k, cs in g["grad_checksums"].items():
+        if float(cs[1]) < 1e-9:           # Q/K projections are dead at L == 1 (SURVEY D4)
+            assert float(checksum(grads[k])[1]) < 1e-9, k
+        else:
+            assert float(checksum(grads[k])[1]) == pytest.approx(float(cs[1]), rel=2e-4), k

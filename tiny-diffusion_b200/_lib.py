@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtinydiff.so")
 
 TD_F32, TD_BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_SILU, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 CONV_SIMT, CONV_TC, CONV_DIRECT = 0, 1, 2
 
 _P = C.c_void_p
@@ -109,6 +109,8 @@ _SIGS = {
     "td_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _P]),
     "td_colsum_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_act_bwd_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    "td_add2d_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
+    "td_dropout_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "td_embedding_bwd": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_time_features": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),

@@ -14,6 +14,7 @@ __device__ inline float act_apply(float v, int act) {
         case TD_ACT_RELU: return fmaxf(v, 0.f);
         case TD_ACT_SILU: return v / (1.0f + expf(-v));
         case TD_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+        case TD_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
         default: return v;
     }
 }
@@ -29,6 +30,10 @@ __device__ inline float act_grad(float v, int act) {
             const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
             const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
             return cdf + v * pdf;
+        }
+        case TD_ACT_SIGMOID: {
+            const float sg = 1.0f / (1.0f + expf(-v));
+            return sg * (1.0f - sg);
         }
         default: return 1.f;
     }
@@ -407,6 +412,43 @@ bn1d_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restr
     }
 }
 
+// dst[i, j] (+)= src[i, j]  (strided fp32 matrices: residual-branch gradients, column-slice copies)
+__global__ void __launch_bounds__(256)
+add2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols,
+             int accumulate) {
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / cols), j = (int)(e % cols);
+        const float v = src[(int64_t)i * lds + j];
+        float* d = dst + (int64_t)i * ldd + j;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+// nn.Dropout / the attention-weight dropout of nn.MultiheadAttention at sequence length 1
+// (diffusion_transformer.py:19,27,29): out = x * keep / (1 - p), one Bernoulli(1-p) draw per `group`
+// consecutive columns of a row (group 1: elementwise; group = head_dim: per (sample, head)).
+// keep = Philox4x32-10(seed; counter = draw index, subsequence = seed_ptr[1]); the same call with the
+// same seed applied to a gradient is the backward.
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int rows, int cols,
+               int group, float p, const uint64_t* __restrict__ seed_ptr) {
+    const Philox rng(seed_ptr[0]);
+    const uint64_t sub = seed_ptr[1];
+    const int gcols = cols / group;
+    const float scale = 1.0f / (1.0f - p);
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(e / cols), j = (int)(e % cols);
+        const uint64_t draw = (uint64_t)i * gcols + j / group;
+        uint32_t r[4];
+        rng.gen(draw >> 2, sub, r);
+        const float u = ((float)r[draw & 3] + 0.5f) * 2.3283064365386963e-10f;
+        const float keep = (u >= p) ? scale : 0.f;
+        out[(int64_t)i * ldo + j] = x[(int64_t)i * ldx + j] * keep;
+    }
+}
+
 static inline int grid1d(int64_t items) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 256), (int64_t)kNumSMs * 8));
 }
@@ -427,7 +469,7 @@ extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(a && a->A && a->B && a->C, "td_gemm_f32: null pointer");
     TD_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "td_gemm_f32: bad shape %d %d %d", a->M, a->N, a->K);
-    TD_CHECK_ARG(a->act >= 0 && a->act <= TD_ACT_GELU, "td_gemm_f32: bad activation %d", a->act);
+    TD_CHECK_ARG(a->act >= 0 && a->act <= TD_ACT_SIGMOID, "td_gemm_f32: bad activation %d", a->act);
     cudaStream_t s = (cudaStream_t)stream;
     int nz = 1;
     const int64_t ws = td_gemm_f32_workspace(a->M, a->N, a->K);
@@ -452,6 +494,24 @@ extern "C" int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int6
     TD_CHECK_ARG(dy && pre && dx && n > 0, "td_act_bwd_f32: bad args");
     act_bwd_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(dy, pre, dx, n, act);
     return launch_status("act_bwd");
+}
+
+extern "C" int td_add2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int accumulate,
+                            void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(src && dst && rows > 0 && cols > 0, "td_add2d_f32: bad args");
+    add2d_kernel<<<grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols, accumulate);
+    return launch_status("add2d");
+}
+
+extern "C" int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int cols, int group,
+                              float p, const uint64_t* seed_ptr, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && out && seed_ptr && rows > 0 && cols > 0 && group > 0 && cols % group == 0, "td_dropout_f32: bad args");
+    TD_CHECK_ARG(p >= 0.f && p < 1.f, "td_dropout_f32: p must be in [0, 1)");
+    dropout_kernel<<<grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, rows, cols, group, p,
+                                                                                 seed_ptr);
+    return launch_status("dropout");
 }
 
 extern "C" int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx, float* table_grad, int M, int D,

@@ -1,0 +1,428 @@
+"""Dense (fully connected) denoisers on libtinydiff: the latent MLP "U-Net"
+(latent_diffusion.py:16-128) and the length-1-sequence "DiT" (diffusion_transformer.py:16-109).
+
+``DenseEngine`` is a small static tape: the model's forward is declared once as a list of
+libtinydiff launches over preallocated fp32 [batch, features] buffers (column slices of a buffer
+stand in for ``torch.cat``), and the backward plan is derived from it in reverse order -- every
+gradient lands either by overwrite (first producer in execution order) or through the GEMM
+epilogue's accumulate flag (later producers).  It exposes the same surface as
+``train.UNetTrainEngine`` so ``TrainStep``, the autograd wrapper and ``ReverseLoop`` work unchanged.
+
+Arithmetic: fp32 FFMA GEMMs (`td_gemm_f32`), LayerNorm / BatchNorm1d / activation / dropout kernels.
+These models are 2.8 / 5.4 MFLOP per sample -- latency-bound at the reference batch sizes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+Mat = Tuple[str, int, int]            # (buffer name, first column, end column)
+
+
+class DenseEngine:
+    def __init__(self, module: torch.nn.Module, batch: int, device: torch.device, training: bool, in_dim: int,
+                 emb_mode: int):
+        self.module, self.B, self.device, self.training = module, batch, device, training
+        self.lib = L.load()
+        self.emb_mode = emb_mode
+        self.widths: Dict[str, int] = {}
+        self.bufs: Dict[str, torch.Tensor] = {}
+        self.gbufs: Dict[str, torch.Tensor] = {}
+        self._ops: List[dict] = []
+        self.pgrad: Dict[str, torch.Tensor] = {k: torch.zeros_like(p, device=device) for k, p in module.named_parameters()}
+        self._pname = {id(p): k for k, p in module.named_parameters()}
+        self.x_in = self.new("x_in", in_dim)
+        self.eps = self.new("eps", in_dim)
+        self.d_eps = self.gbufs["eps"]
+        self.t_in = torch.zeros(batch, device=device, dtype=torch.int64)
+        self.t_dev = torch.zeros(1, device=device, dtype=torch.int32)
+        self.y_in = torch.zeros(batch, device=device, dtype=torch.int64)
+        self.zero_idx = torch.zeros(batch, device=device, dtype=torch.int64)
+        self.use_t_dev = False
+        self.seed = torch.zeros(2, device=device, dtype=torch.int64)       # dropout: (seed, unused)
+        self._drop_slots: List[torch.Tensor] = []
+        self.flops = 0.0
+        self.cfg = type("Cfg", (), {"cond": "class"})()
+        self.fwd_ops: List[Tuple[str, Callable[[int], None]]] = []
+        self.bwd_ops: List[Tuple[str, Callable[[int], None]]] = []
+
+    # ------------------------------------------------------------------ buffers
+    def new(self, name: str, width: int) -> torch.Tensor:
+        self.widths[name] = width
+        self.bufs[name] = torch.zeros(self.B, width, device=self.device)
+        self.gbufs[name] = torch.zeros(self.B, width, device=self.device)
+        return self.bufs[name]
+
+    def full(self, name: str) -> Mat:
+        return (name, 0, self.widths[name])
+
+    def val(self, m: Mat) -> torch.Tensor:
+        return self.bufs[m[0]][:, m[1]:m[2]]
+
+    def grad(self, m: Mat) -> torch.Tensor:
+        return self.gbufs[m[0]][:, m[1]:m[2]]
+
+    # ------------------------------------------------------------------ op declarations
+    def time_features(self, out: Mat):
+        self._ops.append({"kind": "time", "out": out})
+
+    def linear(self, name: str, x: Mat, weight, bias, out: Mat, act: int = L.ACT_NONE, pre: Optional[Mat] = None,
+               residual: Optional[Mat] = None, gather=None, rows: Optional[Tuple[int, int]] = None,
+               x_needs_grad: bool = True):
+        """out = act(x W[rows]^T + b[rows]) + residual + table[idx].  ``gather`` = (index tensor, Parameter)."""
+        self._ops.append({"kind": "linear", "name": name, "x": x, "w": weight, "b": bias, "out": out, "act": act,
+                          "pre": pre, "res": residual, "gather": gather, "rows": rows, "xg": x_needs_grad})
+
+    def bn1d(self, name: str, x: Mat, bn: torch.nn.BatchNorm1d, out: Mat, relu: bool = True):
+        self._ops.append({"kind": "bn", "name": name, "x": x, "bn": bn, "out": out, "relu": relu})
+
+    def layernorm(self, name: str, x: Mat, ln: torch.nn.LayerNorm, out: Mat):
+        self._ops.append({"kind": "ln", "name": name, "x": x, "ln": ln, "out": out})
+
+    def dropout(self, name: str, x: Mat, out: Mat, p: float, group: int = 1):
+        if self.training and p > 0.0:
+            slot = torch.zeros(2, device=self.device, dtype=torch.int64)
+            slot[1] = len(self._drop_slots) + 1
+            self._drop_slots.append(slot)
+            self._ops.append({"kind": "drop", "name": name, "x": x, "out": out, "p": float(p), "group": group,
+                              "slot": slot})
+        else:
+            self._ops.append({"kind": "copy", "name": name, "x": x, "out": out, "acc": 0})
+
+    def add_into(self, name: str, x: Mat, out: Mat, accumulate: bool):
+        """out (+)= x   (two of these build a residual sum when dropout sits between GEMM and add)."""
+        self._ops.append({"kind": "copy", "name": name, "x": x, "out": out, "acc": int(accumulate)})
+
+    # ------------------------------------------------------------------ plan construction
+    def _gemm(self, M, N, K, A, a_rs, a_cs, Bm, b_rs, b_cs, Cm, ldc, bias=None, act=0, pre=None, ld_pre=0, res=None,
+              ldr=0, gidx=None, gtab=None, ldt=0, accumulate=0):
+        g = L.GemmArgs()
+        g.M, g.N, g.K, g.alpha = M, N, K, 1.0
+        g.A, g.a_rs, g.a_cs = A, a_rs, a_cs
+        g.B, g.b_rs, g.b_cs = Bm, b_rs, b_cs
+        g.C, g.ldc, g.bias, g.act = Cm, ldc, bias, act
+        g.pre_out, g.ld_pre, g.residual, g.ldr = pre, ld_pre, res, ldr
+        g.gather_idx, g.gather_table, g.ld_table = gidx, gtab, ldt
+        g.accumulate, g.splitk_ws = accumulate, None
+        self.flops += 2.0 * M * N * K
+        lib = self.lib
+        return lambda st, g=g: L.check(lib.td_gemm_f32(C.byref(g), st), "td_gemm_f32")
+
+    def build(self):
+        """Materialise the forward launches and derive the backward plan (reverse order)."""
+        B, lib = self.B, self.lib
+        fwd: List[Tuple[str, Callable]] = []
+        self.flops = 0.0
+        self._saved: Dict[str, Dict[str, torch.Tensor]] = {}
+        for op in self._ops:
+            k = op["kind"]
+            if k == "time":
+                out = self.val(op["out"])
+                assert out.stride(0) == out.shape[1]
+                mode, D = self.emb_mode, out.shape[1]
+
+                def f(st, out=out, mode=mode, D=D):
+                    t = None if self.use_t_dev else self.t_in.data_ptr()
+                    L.check(lib.td_time_features(t, self.t_dev.data_ptr(), out.data_ptr(), B, D, mode, st),
+                            "td_time_features")
+                fwd.append(("time_features", f))
+            elif k == "linear":
+                x, out = self.val(op["x"]), self.val(op["out"])
+                w, b = op["w"], op["b"]
+                r0, r1 = op["rows"] if op["rows"] else (0, w.shape[0])
+                K, N = w.shape[1], r1 - r0
+                assert x.shape[1] == K and out.shape[1] == N, (op["name"], x.shape, w.shape, out.shape)
+                wp = w.data_ptr() + 4 * r0 * K
+                bp = (b.data_ptr() + 4 * r0) if b is not None else None
+                pre = self.val(op["pre"]) if op["pre"] else None
+                res = self.val(op["res"]) if op["res"] else None
+                gi, gt = (op["gather"][0], op["gather"][1]) if op["gather"] else (None, None)
+                fwd.append((op["name"], self._gemm(
+                    B, N, K, x.data_ptr(), x.stride(0), 1, wp, 1, K, out.data_ptr(), out.stride(0), bp, op["act"],
+                    L.ptr(pre), pre.stride(0) if pre is not None else 0, L.ptr(res),
+                    res.stride(0) if res is not None else 0, L.ptr(gi), L.ptr(gt), gt.shape[-1] if gt is not None else 0)))
+            elif k == "bn":
+                x, out, bn = self.val(op["x"]), self.val(op["out"]), op["bn"]
+                N = x.shape[1]
+                sv = {"mean": torch.zeros(N, device=self.device), "rstd": torch.zeros(N, device=self.device)}
+                self._saved[op["name"]] = sv
+                tr = int(self.training)
+                mom = float(bn.momentum if bn.momentum is not None else 0.1)
+
+                def f(st, x=x, out=out, bn=bn, sv=sv, N=N, tr=tr, mom=mom, relu=int(op["relu"])):
+                    L.check(lib.td_bn1d_fwd(x.data_ptr(), x.stride(0), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                            bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                            sv["mean"].data_ptr(), sv["rstd"].data_ptr(), out.data_ptr(), out.stride(0),
+                                            B, N, float(bn.eps), mom, tr, relu, st), "td_bn1d_fwd")
+                    if tr:
+                        bn.num_batches_tracked.add_(1)
+                fwd.append((op["name"], f))
+            elif k == "ln":
+                x, out, ln = self.val(op["x"]), self.val(op["out"]), op["ln"]
+                D = x.shape[1]
+                assert x.stride(0) == D and out.stride(0) == D
+                sv = {"mean": torch.zeros(B, device=self.device), "rstd": torch.zeros(B, device=self.device)}
+                self._saved[op["name"]] = sv
+                fwd.append((op["name"], lambda st, x=x, out=out, ln=ln, sv=sv, D=D: L.check(
+                    lib.td_layernorm_fwd(x.data_ptr(), ln.weight.data_ptr(), ln.bias.data_ptr(), out.data_ptr(),
+                                         sv["mean"].data_ptr(), sv["rstd"].data_ptr(), B, D, float(ln.eps), st),
+                    "td_layernorm_fwd")))
+            elif k == "drop":
+                x, out, slot = self.val(op["x"]), self.val(op["out"]), op["slot"]
+                fwd.append((op["name"], lambda st, x=x, out=out, slot=slot, p=op["p"], gsz=op["group"]: L.check(
+                    lib.td_dropout_f32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), B, x.shape[1], gsz, p,
+                                       slot.data_ptr(), st), "td_dropout_f32")))
+            elif k == "copy":
+                x, out = self.val(op["x"]), self.val(op["out"])
+                if x.data_ptr() != out.data_ptr():
+                    fwd.append((op["name"], lambda st, x=x, out=out, acc=op["acc"]: L.check(
+                        lib.td_add2d_f32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), B, x.shape[1], acc, st),
+                        "td_add2d_f32")))
+        self.fwd_ops = fwd
+        self.fwd_flops = self.flops
+        self.bwd_ops = self._build_backward() if self.training else []
+
+    def _build_backward(self):
+        B, lib = self.B, self.lib
+        bwd: List[Tuple[str, Callable]] = []
+        written: Dict[str, List[Tuple[int, int]]] = {}
+
+        def acc_flag(m: Mat) -> int:
+            """0 = first gradient to reach these columns (overwrite), 1 = accumulate."""
+            spans = written.setdefault(m[0], [])
+            for a, b in spans:
+                if a <= m[1] and m[2] <= b:                 # already covered by an earlier (wider or equal) write
+                    return 1
+                assert b <= m[1] or a >= m[2], f"partially overlapping gradient slices on {m[0]}"
+            spans.append((m[1], m[2]))
+            return 0
+
+        scratch_w = max(self.widths.values())
+        self._scratch = torch.zeros(self.B, scratch_w, device=self.device)
+        written["eps"] = [(0, self.widths["eps"])]               # seeded by the loss
+        for op in reversed(self._ops):
+            k = op["kind"]
+            if k == "time":
+                continue
+            if k == "linear":
+                x, out, w, b = self.val(op["x"]), self.val(op["out"]), op["w"], op["b"]
+                g_out = self.grad(op["out"])
+                r0, r1 = op["rows"] if op["rows"] else (0, w.shape[0])
+                K, N = w.shape[1], r1 - r0
+                name = op["name"]
+                steps: List[Callable] = []
+                if op["res"] is not None:                       # d residual (+)= d out (post-activation gradient)
+                    gr = self.grad(op["res"])
+                    af = acc_flag(op["res"])
+                    steps.append(lambda st, s=g_out, d=gr, af=af: L.check(
+                        lib.td_add2d_f32(s.data_ptr(), s.stride(0), d.data_ptr(), d.stride(0), B, s.shape[1], af, st),
+                        "td_add2d_f32"))
+                if op["gather"] is not None:
+                    idx, tab = op["gather"]
+                    tg = self.pgrad[self._pname[id(tab)]]
+                    steps.append(lambda st, s=g_out, idx=idx, tg=tg: L.check(
+                        lib.td_embedding_bwd(s.data_ptr(), s.stride(0), idx.data_ptr(), tg.data_ptr(), B, tg.shape[-1],
+                                             tg.numel() // tg.shape[-1], 0, st), "td_embedding_bwd"))
+                g_pre = g_out
+                if op["act"] != L.ACT_NONE:
+                    pre = self.val(op["pre"])
+                    assert g_out.stride(0) == N and pre.stride(0) == N, "activated outputs must be whole buffers"
+                    g_pre = self._scratch.view(-1)[:B * N].view(B, N)
+                    steps.append(lambda st, s=g_out, pre=pre, d=g_pre, act=op["act"]: L.check(
+                        lib.td_act_bwd_f32(s.data_ptr(), pre.data_ptr(), d.data_ptr(), B * N, act, st), "td_act_bwd_f32"))
+                wg = self.pgrad[self._pname[id(w)]]
+                wgp = wg.data_ptr() + 4 * r0 * K
+                steps.append(self._gemm(N, K, B, g_pre.data_ptr(), 1, g_pre.stride(0), x.data_ptr(), x.stride(0), 1,
+                                        wgp, K))                                       # dW = g^T x
+                if b is not None:
+                    bg = self.pgrad[self._pname[id(b)]]
+                    bgp = bg.data_ptr() + 4 * r0
+                    steps.append(lambda st, s=g_pre, bgp=bgp: L.check(
+                        lib.td_colsum_f32(s.data_ptr(), s.stride(0), bgp, B, N, 0, st), "td_colsum_f32"))
+                if op["xg"]:
+                    gx = self.grad(op["x"])
+                    af = acc_flag(op["x"])
+                    wp = w.data_ptr() + 4 * r0 * K
+                    steps.append(self._gemm(B, K, N, g_pre.data_ptr(), g_pre.stride(0), 1, wp, K, 1, gx.data_ptr(),
+                                            gx.stride(0), accumulate=af))             # dx (+)= g W
+                bwd.append((f"{name}:bwd", lambda st, steps=steps: [s(st) for s in steps] and None))
+            elif k == "bn":
+                x, out, bn = self.val(op["x"]), self.val(op["out"]), op["bn"]
+                g_out, gx = self.grad(op["out"]), self.grad(op["x"])
+                assert acc_flag(op["x"]) == 0, "BatchNorm1d input gradient must be the first writer"
+                sv = self._saved[op["name"]]
+                dg = self.pgrad[self._pname[id(bn.weight)]]
+                db = self.pgrad[self._pname[id(bn.bias)]]
+                N = x.shape[1]
+                bwd.append((f"{op['name']}:bwd", lambda st, x=x, out=out, bn=bn, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db,
+                            N=N, relu=int(op["relu"]): L.check(
+                    lib.td_bn1d_bwd(g_out.data_ptr(), g_out.stride(0), x.data_ptr(), x.stride(0), out.data_ptr(),
+                                    out.stride(0), bn.weight.data_ptr(), sv["mean"].data_ptr(), sv["rstd"].data_ptr(),
+                                    gx.data_ptr(), gx.stride(0), dg.data_ptr(), db.data_ptr(), B, N, relu, st),
+                    "td_bn1d_bwd")))
+            elif k == "ln":
+                x, ln = self.val(op["x"]), op["ln"]
+                g_out, gx = self.grad(op["out"]), self.grad(op["x"])
+                assert acc_flag(op["x"]) == 0, "LayerNorm input gradient must be the first writer"
+                sv = self._saved[op["name"]]
+                dg = self.pgrad[self._pname[id(ln.weight)]]
+                db = self.pgrad[self._pname[id(ln.bias)]]
+                D = x.shape[1]
+                assert g_out.stride(0) == D and gx.stride(0) == D
+                bwd.append((f"{op['name']}:bwd", lambda st, x=x, ln=ln, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db, D=D: L.check(
+                    lib.td_layernorm_bwd(g_out.data_ptr(), x.data_ptr(), ln.weight.data_ptr(), sv["mean"].data_ptr(),
+                                         sv["rstd"].data_ptr(), gx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, D, st),
+                    "td_layernorm_bwd")))
+            elif k == "drop":
+                g_out, gx, slot = self.grad(op["out"]), self.grad(op["x"]), op["slot"]
+                assert acc_flag(op["x"]) == 0
+                bwd.append((f"{op['name']}:bwd", lambda st, g_out=g_out, gx=gx, slot=slot, p=op["p"], gsz=op["group"]: L.check(
+                    lib.td_dropout_f32(g_out.data_ptr(), g_out.stride(0), gx.data_ptr(), gx.stride(0), B, g_out.shape[1],
+                                       gsz, p, slot.data_ptr(), st), "td_dropout_f32")))
+            elif k == "copy":
+                g_out, gx = self.grad(op["out"]), self.grad(op["x"])
+                if g_out.data_ptr() != gx.data_ptr():
+                    af = acc_flag(op["x"])
+                    bwd.append((f"{op['name']}:bwd", lambda st, s=g_out, d=gx, af=af: L.check(
+                        lib.td_add2d_f32(s.data_ptr(), s.stride(0), d.data_ptr(), d.stride(0), B, s.shape[1], af, st),
+                        "td_add2d_f32")))
+        return bwd
+
+    # ------------------------------------------------------------------ UNetTrainEngine-compatible surface
+    def _build(self):
+        self.build()
+
+    def refresh_weights(self, force: bool = False) -> None:      # parameters are read in place
+        return
+
+    def reseed(self, seed: int) -> None:
+        """New dropout masks: every dropout site gets (seed, site id) as its Philox key / subsequence."""
+        for s in self._drop_slots:
+            s[0] = seed
+
+    def load_inputs(self, x, t, cond) -> None:
+        self.x_in.copy_(x)
+        self.t_in.copy_(t)
+        self.y_in.copy_(cond)
+
+    def launch_forward(self) -> None:
+        st = L.stream_ptr()
+        for _, fn in self.fwd_ops:
+            fn(st)
+
+    launch = launch_forward
+
+    def launch_backward(self) -> None:
+        st = L.stream_ptr()
+        for _, fn in self.bwd_ops:
+            fn(st)
+
+    def num_launches(self):
+        return len(self.fwd_ops), len(self.bwd_ops)
+
+    def conv_flops(self) -> float:
+        return self.flops
+
+
+class _DenseTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, engine: DenseEngine, x, t, y, *params):
+        engine.load_inputs(x, t, y)
+        engine.reseed(int(torch.randint(0, 2 ** 62, (1,)).item()) if engine._drop_slots else 0)
+        engine.launch_forward()
+        ctx.engine = engine
+        return engine.eps.clone()
+
+    @staticmethod
+    def backward(ctx, d_eps):
+        eng: DenseEngine = ctx.engine
+        eng.d_eps.copy_(d_eps)
+        eng.launch_backward()
+        return (None, None, None, None) + tuple(eng.pgrad[k].clone() for k, _ in eng.module.named_parameters())
+
+
+class DenseNoiseModel(torch.nn.Module):
+    """Shared dispatch of the two latent denoisers; subclasses declare parameters and ``_declare``."""
+    in_dim = 20
+    emb_mode = 0
+
+    def _init_engines(self):
+        self._engines: Dict[Tuple, DenseEngine] = {}
+        self.precision = "fp32"
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_engines"] = {}
+        return st
+
+    def _apply(self, fn, *a, **k):
+        self._engines = {}
+        return super()._apply(fn, *a, **k)
+
+    def _declare(self, e: DenseEngine) -> None:
+        raise NotImplementedError
+
+    def engine(self, batch: int, device: torch.device, training: Optional[bool] = None) -> DenseEngine:
+        training = self.training if training is None else training
+        key = ("dense", batch, str(device), bool(training))
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = DenseEngine(self, batch, device, training, self.in_dim, self.emb_mode)
+            self._declare(eng)
+            eng.build()
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x, t, y):
+        device = L.require_device(x.device)
+        p = next(self.parameters())
+        if p.device != device:
+            raise RuntimeError(f"NoiseModel parameters are on {p.device}, input on {device}")
+        eng = self.engine(x.shape[0], device)
+        x = x.to(torch.float32).contiguous()
+        if self.training:
+            params = tuple(q for _, q in self.named_parameters())
+            return _DenseTrainFunction.apply(eng, x, t, y.to(device), *params)
+        eng.load_inputs(x, t, y.to(device))
+        eng.use_t_dev = False
+        eng.launch_forward()
+        return eng.eps.clone()
+
+
+def dense_sample(vae, noise_model: DenseNoiseModel, diffusion, device, n_samples, y, x_T=None, z=None, seed=None,
+                 use_graph=True, decode=True):
+    """latent_diffusion.py:308-347 / diffusion_transformer.py:291-330."""
+    from .process import ReverseLoop
+    if y is None:
+        raise ValueError("Class labels 'y' must be provided for conditional generation.")
+    if y.shape[0] != n_samples:
+        raise ValueError("y must have shape (n_samples,)")
+    device = L.require_device(device)
+    if vae is not None:
+        vae.eval()
+    noise_model.eval()
+    latent = vae.config.latent_dim if vae is not None else noise_model.in_dim
+    if x_T is None:
+        x_T = torch.randn(n_samples, latent)                       # CPU generator, then H2D (:326)
+    eng = noise_model.engine(n_samples, device, training=False)
+    eng.x_in.copy_(x_T.to(torch.float32))
+    eng.y_in.copy_(y)
+    eng.use_t_dev = True
+    loop = getattr(eng, "_reverse_loop", None)
+    if loop is None or loop.p is not diffusion or loop.use_graph != use_graph:
+        loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch_forward, use_graph=use_graph)
+        eng._reverse_loop = loop
+    if z is not None:
+        z = z.to(device=device, dtype=torch.float32).contiguous()
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    loop.run(z=z, seed=seed)
+    zf = eng.x_in.clone()
+    eng.use_t_dev = False
+    if vae is None or not decode:
+        return zf
+    return vae.decode(zf).view(-1, 1, 28, 28)                       # :346

@@ -495,7 +495,9 @@ class _UNetTrainFunction(torch.autograd.Function):
         return (None, None, None, None) + grads
 
 
-def train_engine(model, batch: int, device: torch.device) -> UNetTrainEngine:
+def train_engine(model, batch: int, device: torch.device):
+    if hasattr(model, "_declare"):                       # dense denoisers (latent MLP, DiT): dense.DenseEngine
+        return model.engine(batch, device, training=True)
     key = ("train", batch, str(device), model.precision)
     eng = model._engines.get(key)
     if eng is None:
@@ -652,6 +654,8 @@ class TrainStep:
             self.noise.normal_()                                                                        # diffusion.py:178
         else:
             self.noise.copy_(noise, non_blocking=True)
+        if getattr(e, "_drop_slots", None):              # fresh dropout masks (outside the captured graph)
+            e.reseed(int(torch.randint(0, 2 ** 62, (1,)).item()))
 
     def run(self) -> torch.Tensor:
         """One optimisation step on the staged batch; returns the (device) loss tensor."""
