@@ -232,8 +232,8 @@ class DenseEngine:
                     pre = self.val(op["pre"])
                     assert g_out.stride(0) == N and pre.stride(0) == N, "activated outputs must be whole buffers"
                     g_pre = self._scratch.view(-1)[:B * N].view(B, N)
-                    steps.append(lambda st, s=g_out, pre=pre, d=g_pre, act=op["act"]: L.check(
-                        lib.td_act_bwd_f32(s.data_ptr(), pre.data_ptr(), d.data_ptr(), B * N, act, st), "td_act_bwd_f32"))
+                    steps.append(lambda st, s=g_out, pre=pre, d=g_pre, act=op["act"], n=B * N: L.check(
+                        lib.td_act_bwd_f32(s.data_ptr(), pre.data_ptr(), d.data_ptr(), n, act, st), "td_act_bwd_f32"))
                 wg = self.pgrad[self._pname[id(w)]]
                 wgp = wg.data_ptr() + 4 * r0 * K
                 steps.append(self._gemm(N, K, B, g_pre.data_ptr(), 1, g_pre.stride(0), x.data_ptr(), x.stride(0), 1,
@@ -241,8 +241,8 @@ class DenseEngine:
                 if b is not None:
                     bg = self.pgrad[self._pname[id(b)]]
                     bgp = bg.data_ptr() + 4 * r0
-                    steps.append(lambda st, s=g_pre, bgp=bgp: L.check(
-                        lib.td_colsum_f32(s.data_ptr(), s.stride(0), bgp, B, N, 0, st), "td_colsum_f32"))
+                    steps.append(lambda st, s=g_pre, bgp=bgp, n=N: L.check(
+                        lib.td_colsum_f32(s.data_ptr(), s.stride(0), bgp, B, n, 0, st), "td_colsum_f32"))
                 if op["xg"]:
                     gx = self.grad(op["x"])
                     af = acc_flag(op["x"])
