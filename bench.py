@@ -218,10 +218,14 @@ def run_gpu(args):
         eng.x_in.copy_(xT_dev)
         eng.y_in.copy_(y_dev)
         eng.use_t_dev = True
+        eng.prepare_sampler_embed()
         loop.run(z=None, seed=7)
 
     from tinydiff.process import ReverseLoop
     xT_dev, y_dev = xT_host.to(dev), y_host.to(dev)
+    eng.y_in.copy_(y_dev)
+    eng.use_t_dev = True
+    eng.prepare_sampler_embed()
     loop = ReverseLoop(fp, eng.x_in, eng.eps, eng.t_dev, eng.launch, use_graph=True)
     eng._reverse_loop = loop
     for _ in range(args.warmup):
@@ -337,8 +341,8 @@ def run_gpu(args):
                        "cuda_graph": "one reverse step captured, replayed 1000x per bench step"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xT_host.numel() * 4 + y_host.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(args.steps * T_STEPS * launches_per_reverse_step),
-            "launches_per_reverse_step": launches_per_reverse_step,
+            "gpu_launches": int(args.steps * T_STEPS * (launches_per_reverse_step + 4)),
+            "launches_per_reverse_step": launches_per_reverse_step + 4,
             "clocks": clk,
             "roofline": roof,
             "model_flops_per_sample": eng.conv_flops() / B * T_STEPS,

@@ -123,11 +123,11 @@ conv3x3_first_kernel(const td_conv3x3_desc d) {
     Tout* __restrict__ y = reinterpret_cast<Tout*>(d.y);
     const int groups = d.cout / 8;
     const int64_t total = (int64_t)d.batch * d.height * d.width * groups;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
         const int g = (int)(i % groups);
-        const int64_t m = i / groups;
+        const uint32_t m = i / groups;
         const int w_ = (int)(m % d.width);
-        const int64_t r = m / d.width;
+        const uint32_t r = m / d.width;
         const int h_ = (int)(r % d.height);
         const int b_ = (int)(r / d.height);
         float acc[8];
@@ -151,7 +151,7 @@ conv3x3_first_kernel(const td_conv3x3_desc d) {
             if (d.relu) v = fmaxf(v, 0.f);
             acc[j] = v;
         }
-        Tout* dst = y + m * d.ldy + d.y_coff + g * 8;
+        Tout* dst = y + (int64_t)m * d.ldy + d.y_coff + g * 8;
         if constexpr (sizeof(Tout) == 2) {
             Vec<__nv_bfloat16>::pack(acc).store(reinterpret_cast<__nv_bfloat16*>(dst));
         } else {
@@ -181,16 +181,16 @@ conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
     // iterate so that whole warps stay converged for the shuffles
     const int64_t iters = ceil_div(M * L, gthreads);
     for (int64_t it = 0; it < iters; ++it) {
-        const int64_t i = it * gthreads + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const int64_t m = i / L;
-        const int lane = (int)(i % L);
+        const uint32_t i = (uint32_t)(it * gthreads) + blockIdx.x * blockDim.x + threadIdx.x;
+        const uint32_t m = i / (uint32_t)L;
+        const int lane = (int)(i % (uint32_t)L);
         const bool valid = m < M;
         float acc[COUT];
 #pragma unroll
         for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
         if (valid) {
             const int w_ = (int)(m % d.width);
-            const int64_t r = m / d.width;
+            const uint32_t r = m / d.width;
             const int h_ = (int)(r % d.height);
             const int b_ = (int)(r / d.height);
             for (int tap = 0; tap < 9; ++tap) {
@@ -214,7 +214,7 @@ conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
             for (int o = L >> 1; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
         if (valid && lane == 0) {
             const int w_ = (int)(m % d.width);
-            const int64_t r = m / d.width;
+            const uint32_t r = m / d.width;
             const int h_ = (int)(r % d.height);
             const int b_ = (int)(r / d.height);
 #pragma unroll
@@ -224,8 +224,98 @@ conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
                 if (d.shift) v += d.shift[j];
                 if (d.relu) v = fmaxf(v, 0.f);
                 if (d.y_nchw) y[(((int64_t)b_ * COUT + j) * d.height + h_) * d.width + w_] = v;
-                else y[m * d.ldy + d.y_coff + j] = v;
+                else y[(int64_t)m * d.ldy + d.y_coff + j] = v;
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast paths of the two network-boundary layers of the MNIST UNets (the generic kernels above were
+// instruction-bound: a shared-memory weight load per FMA and 64-bit index math per element).
+// One CTA per image row (b, h); weights live in registers; no integer division per element.
+// ---------------------------------------------------------------------------------------------
+// initial_conv with Cin == 1: threadIdx.x = group of 8 output channels, threadIdx.y = pixel of the row
+template <typename Tout>
+__global__ void __launch_bounds__(256)
+conv3x3_first1_kernel(const td_conv3x3_desc d) {
+    const int g = threadIdx.x;
+    const int b = blockIdx.x / d.height, h = blockIdx.x - b * d.height;
+    const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [cout][9]
+    float w[8][9], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) w[j][t] = __ldg(wt + (g * 8 + j) * 9 + t);
+        sc[j] = d.scale ? d.scale[g * 8 + j] : 1.f;
+        sh[j] = d.shift ? d.shift[g * 8 + j] : 0.f;
+    }
+    // NCHW with one channel == NHWC with one channel
+    const float* xb = reinterpret_cast<const float*>(d.x) + (int64_t)b * d.height * d.width;
+    Tout* yrow = reinterpret_cast<Tout*>(d.y) + ((int64_t)b * d.height + h) * d.width * d.ldy + d.y_coff + g * 8;
+    for (int x0 = threadIdx.y; x0 < d.width; x0 += blockDim.y) {
+        float xv[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = h + t / 3 - 1, ww = x0 + t % 3 - 1;
+            xv[t] = (hh >= 0 && hh < d.height && ww >= 0 && ww < d.width) ? __ldg(xb + hh * d.width + ww) : 0.f;
+        }
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) a = fmaf(xv[t], w[j][t], a);
+            a = fmaf(a, sc[j], sh[j]);
+            acc[j] = d.relu ? fmaxf(a, 0.f) : a;
+        }
+        Tout* dst = yrow + (int64_t)x0 * d.ldy;
+        if constexpr (sizeof(Tout) == 2) {
+            Vec<__nv_bfloat16>::pack(acc).store(reinterpret_cast<__nv_bfloat16*>(dst));
+        } else {
+            Vec<float>::pack(acc).store(reinterpret_cast<float*>(dst));
+            Vec<float>::pack(acc + 4).store(reinterpret_cast<float*>(dst) + 4);
+        }
+    }
+}
+
+// final_conv with Cout == 1: threadIdx.x = lane owning V input channels (L lanes per pixel, L a power of
+// two <= 32), threadIdx.y = pixel; shuffle-reduce over the L lanes.
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+conv3x3_last1_kernel(const td_conv3x3_desc d) {
+    constexpr int V = Vec<Tin>::N;
+    const int L = blockDim.x, lane = threadIdx.x;
+    const int b = blockIdx.x / d.height, h = blockIdx.x - b * d.height;
+    const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [1][9][cin]
+    float w[9][V];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < V; ++k) w[t][k] = __ldg(wt + t * d.cin + lane * V + k);
+    const float sc = d.scale ? d.scale[0] : 1.f, sh = d.shift ? d.shift[0] : 0.f;
+    const Tin* xb = reinterpret_cast<const Tin*>(d.x) + (int64_t)b * d.height * d.width * d.ldx + d.x_coff + lane * V;
+    float* yrow = reinterpret_cast<float*>(d.y) + ((int64_t)b * d.height + h) * d.width * (d.y_nchw ? 1 : d.ldy) +
+                  (d.y_nchw ? 0 : d.y_coff);
+    for (int w0 = 0; w0 < d.width; w0 += blockDim.y) {
+        const int x0 = w0 + threadIdx.y;
+        float acc = 0.f;
+        if (x0 < d.width) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int hh = h + t / 3 - 1, ww = x0 + t % 3 - 1;
+                if (hh < 0 || hh >= d.height || ww < 0 || ww >= d.width) continue;
+                float f[V];
+                Vec<Tin>::load(xb + ((int64_t)hh * d.width + ww) * d.ldx).unpack(f);
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc = fmaf(f[k], w[t][k], acc);
+            }
+        }
+        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (x0 < d.width && lane == 0) {
+            float v = fmaf(acc, sc, sh);
+            if (d.relu) v = fmaxf(v, 0.f);
+            yrow[(int64_t)x0 * (d.y_nchw ? 1 : d.ldy)] = v;
         }
     }
 }
@@ -244,6 +334,13 @@ static int run_simt(const td_conv_plan* p, cudaStream_t s) {
 static int run_direct(const td_conv_plan* p, cudaStream_t s) {
     const td_conv3x3_desc& d = p->d;
     const int64_t M = (int64_t)d.batch * d.height * d.width;
+    if (d.cin == 1 && d.x_dtype == TD_F32 && d.cout / 8 <= 256 && d.width * (int64_t)d.height < (1 << 30)) {
+        const int groups = d.cout / 8;
+        dim3 block((unsigned)groups, (unsigned)std::max(1, 256 / groups));
+        if (d.y_dtype == TD_BF16) conv3x3_first1_kernel<__nv_bfloat16><<<d.batch * d.height, block, 0, s>>>(d);
+        else conv3x3_first1_kernel<float><<<d.batch * d.height, block, 0, s>>>(d);
+        return launch_status("conv3x3_first1");
+    }
     if (d.cin <= 8) {
         const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
         const int64_t items = M * (d.cout / 8);
@@ -255,6 +352,13 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
     }
     // tiny cout
     const int V = d.x_dtype == TD_BF16 ? 8 : 4;
+    if (d.cout == 1 && d.cin / V <= 32) {
+        const int Ln = d.cin / V;            // power of two (checked at plan creation)
+        dim3 block((unsigned)Ln, (unsigned)(256 / Ln));
+        if (d.x_dtype == TD_BF16) conv3x3_last1_kernel<__nv_bfloat16><<<d.batch * d.height, block, 0, s>>>(d);
+        else conv3x3_last1_kernel<float><<<d.batch * d.height, block, 0, s>>>(d);
+        return launch_status("conv3x3_last1");
+    }
     int L = d.cin / V;
     if (L > 32) L = 32;
     const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);

@@ -235,6 +235,14 @@ int tc_plan_init(td_conv_plan* p) {
     const int stage_bytes = TC_A_STAGE + p->block_n * 128;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
+    // Enough tiles for two waves of CTAs: keep two CTAs resident per SM (<= ~100 KB of stages each, TMEM
+    // 2 x BLOCK_N <= 512 columns) so that one CTA's epilogue overlaps the other's main loop.  Measured on
+    // B200 (tools/tc_sweep.py): 28x28 128->128 70 -> 45 us, 16x16 512->128 60 -> 37 us.
+    const int64_t ctas = (int64_t)p->tiles_w * p->tiles_h * p->tiles_n * p->n_tiles;
+    if (ctas > kNumSMs) {
+        int s2 = (100 * 1024) / stage_bytes;
+        if (s2 >= 2) stages = s2 > 4 ? 4 : s2;
+    }
     if (const char* e = getenv("TD_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
     p->stages = stages;
     p->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;

@@ -168,24 +168,39 @@ static bool narrow_ok(const td_wgrad_desc& d, int* grid_x) {
     const int rows = 256 / lanesC;
     if ((size_t)rows * cw * sizeof(float) > 48 * 1024) return false;
     const int64_t P = (int64_t)d.batch * d.height * d.width;
-    *grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(P, (int64_t)rows * 4), 2 * kNumSMs));
+    *grid_x = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(P, (int64_t)rows * 4), kNumSMs));
     return true;
 }
 
 // dw[o][c][tap] = sum_s ws[s][o][tap*cin + c]     (OHWI partials -> OIHW gradient)
-__global__ void __launch_bounds__(256)
+// grid (cin chunks of 32, cout), 288 threads = 9 taps x 32 channels: coalesced reads of the tap rows,
+// fixed-order sum over the splits, transposed through shared memory so that the [c][tap] run is
+// written contiguously.
+constexpr int WR_C = 32;
+__global__ void __launch_bounds__(9 * WR_C)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
-    const int64_t total = (int64_t)cout * cin * 9;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        // iterate in OHWI order (coalesced reads); scattered 4-byte writes are absorbed by L2
-        const int c = (int)(e % cin);
-        const int64_t r = e / cin;
-        const int tap = (int)(r % 9);
-        const int o = (int)(r / 9);
-        float s = 0.f;
-        for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * total + e];
-        dw[((int64_t)o * cin + c) * 9 + tap] = s;
+    __shared__ float tile[9][WR_C + 1];
+    const int o = blockIdx.y;
+    const int c0 = blockIdx.x * WR_C;
+    const int nc = min(WR_C, cin - c0);
+    const int64_t per = (int64_t)cout * 9 * cin;
+    const int t = threadIdx.x / WR_C, c = threadIdx.x % WR_C;
+    if (c < nc) {
+        const float* src = ws + ((int64_t)o * 9 + t) * cin + c0 + c;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int z = 0;
+        for (; z + 4 <= splits; z += 4) {
+            a0 += src[(int64_t)z * per];
+            a1 += src[(int64_t)(z + 1) * per];
+            a2 += src[(int64_t)(z + 2) * per];
+            a3 += src[(int64_t)(z + 3) * per];
+        }
+        for (; z < splits; ++z) a0 += src[(int64_t)z * per];
+        tile[t][c] = (a0 + a1) + (a2 + a3);
     }
+    __syncthreads();
+    float* dst = dw + ((int64_t)o * cin + c0) * 9;
+    for (int e = threadIdx.x; e < nc * 9; e += 9 * WR_C) dst[e] = tile[e % 9][e / 9];
 }
 
 // OIHW fp32 -> [Cin][3][3][Cout] with the taps flipped: the weight operand of the data gradient,
@@ -285,9 +300,8 @@ extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
         int st = launch_status("wgrad_simt");
         if (st != TD_OK) return st;
     }
-    const int64_t total = (int64_t)d.cout * d.cin * 9;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), kNumSMs * 8));
-    wgrad_reduce_kernel<<<grid, 256, 0, s>>>(d.workspace, p->splits, d.cout, d.cin, d.dw);
+    dim3 rgrid((unsigned)ceil_div(d.cin, WR_C), (unsigned)d.cout);
+    wgrad_reduce_kernel<<<rgrid, 9 * WR_C, 0, s>>>(d.workspace, p->splits, d.cout, d.cin, d.dw);
     return launch_status("wgrad_reduce");
 }
 

@@ -222,10 +222,16 @@ static bool wg_geometry(const td_wgrad_desc& d, WgGeom& g) {
     g.n_tiles = cn / bn_ch;
     const int stage = (g.m_boxes + g.n_boxes) * box_bytes;
     g.stages = std::max(2, std::min(8, (200 * 1024) / stage));
+    // 64-channel N tiles: two stages (96 KB) keep two CTAs per SM resident (tools/wg_sweep.py: 28x28 64->128
+    // 48 -> 33 us, 32x32 256->64 110 -> 89 us)
+    if (g.block_n == 64 && 2 * stage <= 100 * 1024) g.stages = 2;
+    if (const char* e = getenv("TD_WG_STAGES")) { int v = atoi(e); if (v >= 2 && v <= g.stages) g.stages = v; }
     g.smem_bytes = g.stages * stage + (2 * g.stages + 1) * 8 + 16 + 1024;
     const int total_boxes = g.tiles_w * g.tiles_h * g.tiles_n;
     const int base = g.m_tiles * g.n_tiles * 9;
-    int splits = (int)ceil_div(2 * kNumSMs, base);
+    int target = 2 * kNumSMs;
+    if (const char* e = getenv("TD_WG_TARGET_CTAS")) { int v = atoi(e); if (v > 0) target = v; }
+    int splits = (int)ceil_div(target, base);
     splits = std::max(1, std::min(splits, std::max(1, total_boxes / 4)));
     g.boxes_per_split = (int)ceil_div(total_boxes, splits);
     g.splits = (int)ceil_div(total_boxes, g.boxes_per_split);

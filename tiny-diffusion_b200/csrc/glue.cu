@@ -20,39 +20,49 @@ __device__ inline Bil bil(int dst, int in, int out) {
     return b;
 }
 
+// Thread layout shared by the NHWC glue kernels: one CTA per output row (b, h); threadIdx.x walks the
+// 16-byte channel vectors of a pixel, threadIdx.y the pixels of the row -- no integer division on the
+// per-element path (these kernels were instruction-bound on 64-bit div/mod and bilinear setup).
+static inline dim3 row_block(int cv) {
+    const int bx = cv < 256 ? cv : 256;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    return dim3((unsigned)bx, (unsigned)by, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // MaxPool2d(2, ceil_mode)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
-    const int64_t total = (int64_t)B * Ho * Wo * cv;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv);
-        int64_t p = i / cv;
-        int wo = (int)(p % Wo); p /= Wo;
-        int ho = (int)(p % Ho);
-        int b = (int)(p / Ho);
-        float m[V];
+    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+    const T* xb = x + (int64_t)b * H * W * C;
+    T* yrow = y + ((int64_t)b * Ho + ho) * Wo * C;
+    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
+        const int c = cvi * V;
+        for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+            float m[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) m[k] = -INFINITY;
+            for (int k = 0; k < V; ++k) m[k] = -INFINITY;
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            int h = 2 * ho + dy;
-            if (h >= H) continue;
+            for (int dy = 0; dy < 2; ++dy) {
+                const int h = 2 * ho + dy;
+                if (h >= H) continue;
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                int w = 2 * wo + dx;
-                if (w >= W) continue;
-                float f[V];
-                Vec<T>::load(x + (((int64_t)b * H + h) * W + w) * C + c * V).unpack(f);
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int w = 2 * wo + dx;
+                    if (w >= W) continue;
+                    float f[V];
+                    Vec<T>::load(xb + ((int64_t)h * W + w) * C + c).unpack(f);
 #pragma unroll
-                for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], f[k]);
+                    for (int k = 0; k < V; ++k) m[k] = fmaxf(m[k], f[k]);
+                }
             }
+            Vec<T>::pack(m).store(yrow + (int64_t)wo * C + c);
         }
-        Vec<T>::pack(m).store(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + c * V);
     }
 }
 
@@ -60,70 +70,80 @@ maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W,
 // out = [ up2x(low) | resize(skip + temb) ]
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ inline void bilerp_nhwc(const T* __restrict__ src, int b, int Hs, int Ws, int C, int c0, const Bil& bh,
-                                   const Bil& bw, float* out) {
+__device__ inline void bilerp_row(const T* __restrict__ r0, const T* __restrict__ r1, int C, const Bil& bh, const Bil& bw,
+                                  float* out) {
     constexpr int V = Vec<T>::N;
     float f00[V], f01[V], f10[V], f11[V];
-    const T* base = src + (int64_t)b * Hs * Ws * C + c0;
-    Vec<T>::load(base + ((int64_t)bh.i0 * Ws + bw.i0) * C).unpack(f00);
-    Vec<T>::load(base + ((int64_t)bh.i0 * Ws + bw.i1) * C).unpack(f01);
-    Vec<T>::load(base + ((int64_t)bh.i1 * Ws + bw.i0) * C).unpack(f10);
-    Vec<T>::load(base + ((int64_t)bh.i1 * Ws + bw.i1) * C).unpack(f11);
+    Vec<T>::load(r0 + (int64_t)bw.i0 * C).unpack(f00);
+    Vec<T>::load(r0 + (int64_t)bw.i1 * C).unpack(f01);
+    Vec<T>::load(r1 + (int64_t)bw.i0 * C).unpack(f10);
+    Vec<T>::load(r1 + (int64_t)bw.i1 * C).unpack(f11);
 #pragma unroll
     for (int k = 0; k < V; ++k)
         out[k] = bh.l0 * (bw.l0 * f00[k] + bw.l1 * f01[k]) + bh.l1 * (bw.l0 * f10[k] + bw.l1 * f11[k]);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
              int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
     constexpr int V = Vec<T>::N;
     const int Ct = Cu + Cs;
     const int cv = Ct / V;
     const int Hl = Ho / 2, Wl = Wo / 2;
-    const int64_t total = (int64_t)B * Ho * Wo * cv;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * V;
-        int64_t p = i / cv;
-        int wo = (int)(p % Wo); p /= Wo;
-        int ho = (int)(p % Ho);
-        int b = (int)(p / Ho);
-        float r[V];
+    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+    T* orow = out + ((int64_t)b * Ho + ho) * Wo * Ct;
+    const bool same = (Hs == Ho && Ws == Wo);
+    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
+        const int c = cvi * V;
         if (c < Cu) {
-            bilerp_nhwc<T>(low, b, Hl, Wl, Cu, c, bil(ho, Hl, Ho), bil(wo, Wl, Wo), r);
+            const Bil bh = bil(ho, Hl, Ho);
+            const T* r0 = low + (((int64_t)b * Hl + bh.i0) * Wl) * Cu + c;
+            const T* r1 = low + (((int64_t)b * Hl + bh.i1) * Wl) * Cu + c;
+            for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+                float r[V];
+                bilerp_row<T>(r0, r1, Cu, bh, bil(wo, Wl, Wo), r);
+                Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
+            }
         } else {
             const int cs = c - Cu;
-            if (Hs == Ho && Ws == Wo) {
-                Vec<T>::load(skip + (((int64_t)b * Hs + ho) * Ws + wo) * Cs + cs).unpack(r);
-            } else {
-                bilerp_nhwc<T>(skip, b, Hs, Ws, Cs, cs, bil(ho, Hs, Ho), bil(wo, Ws, Wo), r);
-            }
             // the embedding is constant over space and the bilinear weights sum to one, so
             // resize(skip + t) == resize(skip) + t
-            const float* te = temb + (int64_t)b * ld_temb + temb_off + cs;
+            float te[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) r[k] += te[k];
+            for (int k = 0; k < V; ++k) te[k] = temb[(int64_t)b * ld_temb + temb_off + cs + k];
+            const Bil bh = bil(ho, Hs, Ho);
+            const T* r0 = skip + (((int64_t)b * Hs + (same ? ho : bh.i0)) * Ws) * Cs + cs;
+            const T* r1 = skip + (((int64_t)b * Hs + (same ? ho : bh.i1)) * Ws) * Cs + cs;
+            for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+                float r[V];
+                if (same) Vec<T>::load(r0 + (int64_t)wo * Cs).unpack(r);
+                else bilerp_row<T>(r0, r1, Cs, bh, bil(wo, Ws, Wo), r);
+#pragma unroll
+                for (int k = 0; k < V; ++k) r[k] += te[k];
+                Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
+            }
         }
-        Vec<T>::pack(r).store(out + (((int64_t)b * Ho + ho) * Wo + wo) * Ct + c);
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
-    const int64_t total = (int64_t)B * Ho * Wo * cv;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int c = (int)(i % cv) * V;
-        int64_t p = i / cv;
-        int wo = (int)(p % Wo); p /= Wo;
-        int ho = (int)(p % Ho);
-        int b = (int)(p / Ho);
-        float r[V];
-        bilerp_nhwc<T>(x, b, Hi, Wi, C, c, bil(ho, Hi, Ho), bil(wo, Wi, Wo), r);
-        Vec<T>::pack(r).store(y + (((int64_t)b * Ho + ho) * Wo + wo) * C + c);
+    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+    const Bil bh = bil(ho, Hi, Ho);
+    T* yrow = y + ((int64_t)b * Ho + ho) * Wo * C;
+    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
+        const int c = cvi * V;
+        const T* r0 = x + (((int64_t)b * Hi + bh.i0) * Wi) * C + c;
+        const T* r1 = x + (((int64_t)b * Hi + bh.i1) * Wi) * C + c;
+        for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+            float r[V];
+            bilerp_row<T>(r0, r1, C, bh, bil(wo, Wi, Wo), r);
+            Vec<T>::pack(r).store(yrow + (int64_t)wo * C + c);
+        }
     }
 }
 
@@ -132,9 +152,9 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pack_weight_kernel(const float* __restrict__ oihw, T* __restrict__ ohwi, int cout, int cin) {
     const int64_t total = (int64_t)cout * 9 * cin;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
         int c = (int)(i % cin);
-        int64_t r = i / cin;
+        uint32_t r = i / cin;
         int tap = (int)(r % 9);
         int o = (int)(r / 9);
         ohwi[i] = from_f32<T>(oihw[((int64_t)o * cin + c) * 9 + tap]);
@@ -170,11 +190,11 @@ extern "C" int td_maxpool2_fwd(const void* x, void* y, int dtype, int batch, int
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_maxpool2_fwd: channels must be a multiple of 8 for bf16");
-        maxpool2_kernel<__nv_bfloat16><<<grid_for((int64_t)batch * ho * wo * c / 8), kThreads, 0, s>>>(
+        maxpool2_kernel<__nv_bfloat16><<<batch * ho, row_block(c / 8), 0, s>>>(
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, h, w, c, ho, wo);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_maxpool2_fwd: channels must be a multiple of 4 for fp32");
-        maxpool2_kernel<float><<<grid_for((int64_t)batch * ho * wo * c / 4), kThreads, 0, s>>>(
+        maxpool2_kernel<float><<<batch * ho, row_block(c / 4), 0, s>>>(
             (const float*)x, (float*)y, batch, h, w, c, ho, wo);
     } else {
         TD_CHECK_ARG(false, "td_maxpool2_fwd: unknown dtype %d", dtype);
@@ -189,15 +209,14 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
     TD_CHECK_ARG(low && skip && temb && out, "td_upcat_fwd: null pointer");
     TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0, "td_upcat_fwd: bad output size");
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t elems = (int64_t)batch * ho * wo * (cu + cs);
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
-        upcat_kernel<__nv_bfloat16><<<grid_for(elems / 8), kThreads, 0, s>>>(
+        upcat_kernel<__nv_bfloat16><<<batch * ho, row_block((cu + cs) / 8), 0, s>>>(
             (const __nv_bfloat16*)low, (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out,
             batch, ho, wo, cu, hs, ws, cs);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(cu % 4 == 0 && cs % 4 == 0, "td_upcat_fwd: channel counts must be multiples of 4");
-        upcat_kernel<float><<<grid_for(elems / 4), kThreads, 0, s>>>(
+        upcat_kernel<float><<<batch * ho, row_block((cu + cs) / 4), 0, s>>>(
             (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs);
     } else {
         TD_CHECK_ARG(false, "td_upcat_fwd: unknown dtype %d", dtype);
@@ -210,14 +229,13 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && y && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_fwd: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t elems = (int64_t)batch * ho * wo * c;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");
-        resize_kernel<__nv_bfloat16><<<grid_for(elems / 8), kThreads, 0, s>>>(
+        resize_kernel<__nv_bfloat16><<<batch * ho, row_block(c / 8), 0, s>>>(
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 4 for fp32");
-        resize_kernel<float><<<grid_for(elems / 4), kThreads, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
+        resize_kernel<float><<<batch * ho, row_block(c / 4), 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
     } else {
         TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
     }

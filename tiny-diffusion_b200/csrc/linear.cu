@@ -147,6 +147,86 @@ gemm_f32_kernel(const td_gemm_args g) {
     }
 }
 
+// epilogue shared by the GEMM variants
+__device__ inline void gemm_store(const td_gemm_args& g, int gi, int gj, float acc) {
+    float v = acc * g.alpha;
+    if (g.bias) v += __ldg(g.bias + gj);
+    if (g.pre_out) g.pre_out[(int64_t)gi * g.ld_pre + gj] = v;
+    v = act_apply(v, g.act);
+    if (g.residual) v += g.residual[(int64_t)gi * g.ldr + gj];
+    if (g.gather_idx && g.gather_table) v += g.gather_table[g.gather_idx[gi] * g.ld_table + gj];
+    float* c = g.C + (int64_t)gi * g.ldc + gj;
+    if (g.accumulate) v += *c;
+    *c = v;
+}
+
+// Small-output variant: 32x32 tiles, BK = 32, 2x2 outputs per thread.  Used when the 64x64 grid would
+// leave most SMs idle (the conditioning head and the latent denoisers: M = batch = 128, N, K <= 1024):
+// 4x the CTAs and half the k-steps of the big-tile kernel.
+constexpr int S_BM = 32, S_BN = 32, S_BK = 32;
+__global__ void __launch_bounds__(256)
+gemm_f32_small_kernel(const td_gemm_args g) {
+    __shared__ float As[S_BK][S_BM + 1];
+    __shared__ float Bs[S_BK][S_BN + 1];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * S_BM, n0 = blockIdx.x * S_BN;
+    const int ty = tid >> 4, tx = tid & 15;
+    const bool a_kc = (g.a_cs == 1), b_kc = (g.b_rs == 1);
+    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = 0; k0 < g.K; k0 += S_BK) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int e = tid + l * 256;
+            int i, k;
+            if (a_kc) { k = e & 31; i = e >> 5; } else { i = e & 31; k = e >> 5; }
+            int gi = m0 + i, gk = k0 + k;
+            As[k][i] = (gi < g.M && gk < g.K) ? __ldg(g.A + (int64_t)gi * g.a_rs + (int64_t)gk * g.a_cs) : 0.f;
+            int j;
+            if (b_kc) { k = e & 31; j = e >> 5; } else { j = e & 31; k = e >> 5; }
+            const int gj = n0 + j;
+            gk = k0 + k;
+            Bs[k][j] = (gj < g.N && gk < g.K) ? __ldg(g.B + (int64_t)gk * g.b_rs + (int64_t)gj * g.b_cs) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < S_BK; ++k) {
+            const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+            const float b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+            acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+            acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int gi = m0 + ty * 2 + i, gj = n0 + tx * 2 + j;
+            if (gi < g.M && gj < g.N) gemm_store(g, gi, gj, acc[i][j]);
+        }
+}
+
+// Row-vector variant (M <= 4, both operands K-contiguous): one warp per output column, lanes stride K.
+// The sampler's per-step conditioning head is this shape (every sample shares t).
+__global__ void __launch_bounds__(256)
+gemv_f32_kernel(const td_gemm_args g) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= g.N) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* w = g.B + (int64_t)j * g.b_cs;
+    for (int k = lane; k < g.K; k += 32) {
+        const float wv = __ldg(w + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < g.M) acc[i] = fmaf(__ldg(g.A + (int64_t)i * g.a_rs + k), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);
+    if (lane == 0)
+        for (int i = 0; i < g.M; ++i) gemm_store(g, i, j, acc[i]);
+}
+
 // second pass of the deterministic split-K: fixed-order sum over slices + the same epilogue
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const td_gemm_args g, int nz) {
@@ -474,6 +554,15 @@ extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
     int nz = 1;
     const int64_t ws = td_gemm_f32_workspace(a->M, a->N, a->K);
     if (ws > 0 && a->splitk_ws) nz = (int)(ws / ((int64_t)a->M * a->N));
+    if (nz == 1 && a->M <= 4 && a->a_cs == 1 && a->b_rs == 1) {
+        gemv_f32_kernel<<<(unsigned)ceil_div(a->N, 8), 256, 0, s>>>(*a);
+        return launch_status("gemv_f32");
+    }
+    if (nz == 1 && ceil_div(a->N, G_BN) * ceil_div(a->M, G_BM) < kNumSMs) {
+        dim3 sgrid((unsigned)ceil_div(a->N, S_BN), (unsigned)ceil_div(a->M, S_BM));
+        gemm_f32_small_kernel<<<sgrid, 256, 0, s>>>(*a);
+        return launch_status("gemm_f32_small");
+    }
     dim3 grid((unsigned)ceil_div(a->N, G_BN), (unsigned)ceil_div(a->M, G_BM), (unsigned)nz);
     gemm_f32_kernel<<<grid, G_THREADS, 0, s>>>(*a);
     int st = launch_status("gemm_f32");

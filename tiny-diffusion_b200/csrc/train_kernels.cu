@@ -98,20 +98,35 @@ chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const float
 // BatchNorm2d train-mode finalize (diffusion.py:34): batch mean / biased variance -> the affine
 // used by the apply pass; running statistics updated like torch (momentum, unbiased variance,
 // conv bias folded into the mean only).
+// one warp per channel: lanes stride the partial rows, shuffle-reduce in double (fixed order)
+__device__ inline void warp_sum_partials(const float* __restrict__ partials, int nrows, int C, int c, double& s1,
+                                         double& s2) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (int r = lane; r < nrows; r += 32) {
+        a += (double)partials[(size_t)r * 2 * C + c];
+        b += (double)partials[(size_t)r * 2 * C + C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    s1 = a; s2 = b;
+}
+
 __global__ void __launch_bounds__(128)
 bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_invstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt) nbt[0] += 1;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < nrows; ++r) {
-        s1 += (double)partials[(size_t)r * 2 * C + c];
-        s2 += (double)partials[(size_t)r * 2 * C + C + c];
-    }
+    double s1, s2;
+    warp_sum_partials(partials, nrows, C, c, s1, s2);
+    if ((threadIdx.x & 31) != 0) return;
     const double dm = s1 / count;                         // mean of (x - K)
     const double mean = (double)partials[(size_t)nrows * 2 * C + c] + dm;
     double var = s2 / count - dm * dm;
@@ -140,14 +155,15 @@ bn_relu_apply_kernel(const float* __restrict__ y, const float* __restrict__ scal
     constexpr int V = Vec<T>::N;
     const int lanesC = C / V;
     const int64_t total = P * lanesC;
-    const int64_t stride = (int64_t)gridDim.x * kT;       // multiple of lanesC -> channel group is loop invariant
-    int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+    const uint32_t stride = gridDim.x * kT;               // multiple of lanesC -> channel group is loop invariant
+    uint32_t i = blockIdx.x * kT + threadIdx.x;
     const int c0 = (int)(i % lanesC) * V;
     float sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
-    for (; i < total; i += stride) {
-        const int64_t p = i / lanesC;
+    const int lsh = __ffs(lanesC) - 1;                    // lanesC is a power of two (checked on the host)
+    for (; i < (uint32_t)total; i += stride) {
+        const int64_t p = i >> lsh;
         float f[V];
         load_f32<V>(y + p * C + c0, f);
 #pragma unroll
@@ -165,13 +181,11 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, dou
                        const float* __restrict__ scale, const float* __restrict__ save_mean,
                        const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < nrows; ++r) {
-        s1 += (double)partials[(size_t)r * 2 * C + c];
-        s2 += (double)partials[(size_t)r * 2 * C + C + c];
-    }
+    double s1, s2;
+    warp_sum_partials(partials, nrows, C, c, s1, s2);
+    if ((threadIdx.x & 31) != 0) return;
     const double mean = save_mean[c], invstd = save_invstd[c], sc = scale[c];
     const double dg = s2 * invstd;                     // sum g * xhat   (s2 = sum g * (y - mean))
     dgamma[c] = (float)dg;
@@ -191,8 +205,8 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
     constexpr int V = Vec<T>::N;
     const int lanesC = C / V;
     const int64_t total = P * lanesC;
-    const int64_t stride = (int64_t)gridDim.x * kT;
-    int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+    const uint32_t stride = gridDim.x * kT;
+    uint32_t i = blockIdx.x * kT + threadIdx.x;
     const int c0 = (int)(i % lanesC) * V;
     float sc[V], sh[V], cA[V], cB[V], cC[V];
 #pragma unroll
@@ -200,8 +214,9 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
         sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k];
         cA[k] = coef[c0 + k]; cB[k] = coef[C + c0 + k]; cC[k] = coef[2 * C + c0 + k];
     }
-    for (; i < total; i += stride) {
-        const int64_t p = i / lanesC;
+    const int lsh = __ffs(lanesC) - 1;                    // lanesC is a power of two (checked on the host)
+    for (; i < (uint32_t)total; i += stride) {
+        const int64_t p = i >> lsh;
         float g[V], yy[V];
         Vec<T>::load(da + p * ldda + da_coff + c0).unpack(g);
         load_f32<V>(y + p * C + c0, yy);
@@ -222,53 +237,54 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
                     int Ho, int Wo, int accumulate) {
+    // one CTA per input row (b, h); threadIdx.x = channel vector, threadIdx.y = pixel of the row
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
-    const int64_t total = (int64_t)B * H * W * cv;
-    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-        const int c = (int)(i % cv) * V;
-        int64_t p = i / cv;
-        const int w = (int)(p % W); p /= W;
-        const int h = (int)(p % H);
-        const int b = (int)(p / H);
-        const int ho = h >> 1, wo = w >> 1;
-        float out[V];
+    const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+    const int ho = h >> 1;
+    const T* xb = x + (int64_t)b * H * W * C;
+    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
+        const int c = cvi * V;
+        for (int w = threadIdx.y; w < W; w += blockDim.y) {
+            const int wo = w >> 1;
+            float out[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) out[k] = 0.f;
-        if (ho < Ho && wo < Wo) {
-            float best[V];
-            int arg[V];
+            for (int k = 0; k < V; ++k) out[k] = 0.f;
+            if (ho < Ho && wo < Wo) {
+                float best[V];
+                int arg[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) { best[k] = -INFINITY; arg[k] = -1; }
+                for (int k = 0; k < V; ++k) { best[k] = -INFINITY; arg[k] = -1; }
 #pragma unroll
-            for (int dyy = 0; dyy < 2; ++dyy) {
-                const int hh = 2 * ho + dyy;
-                if (hh >= H) continue;
+                for (int dyy = 0; dyy < 2; ++dyy) {
+                    const int hh = 2 * ho + dyy;
+                    if (hh >= H) continue;
 #pragma unroll
-                for (int dxx = 0; dxx < 2; ++dxx) {
-                    const int ww = 2 * wo + dxx;
-                    if (ww >= W) continue;
-                    float f[V];
-                    Vec<T>::load(x + (((int64_t)b * H + hh) * W + ww) * C + c).unpack(f);
+                    for (int dxx = 0; dxx < 2; ++dxx) {
+                        const int ww = 2 * wo + dxx;
+                        if (ww >= W) continue;
+                        float f[V];
+                        Vec<T>::load(xb + ((int64_t)hh * W + ww) * C + c).unpack(f);
 #pragma unroll
-                    for (int k = 0; k < V; ++k)
-                        if (f[k] > best[k] || arg[k] < 0) { best[k] = f[k]; arg[k] = dyy * 2 + dxx; }
+                        for (int k = 0; k < V; ++k)
+                            if (f[k] > best[k] || arg[k] < 0) { best[k] = f[k]; arg[k] = dyy * 2 + dxx; }
+                    }
                 }
+                const int me = (h & 1) * 2 + (w & 1);
+                float g[V];
+                Vec<T>::load(dy + (((int64_t)b * Ho + ho) * Wo + wo) * C + c).unpack(g);
+#pragma unroll
+                for (int k = 0; k < V; ++k) out[k] = (arg[k] == me) ? g[k] : 0.f;
             }
-            const int me = (h & 1) * 2 + (w & 1);
-            float g[V];
-            Vec<T>::load(dy + (((int64_t)b * Ho + ho) * Wo + wo) * C + c).unpack(g);
+            T* dst = dx + (((int64_t)b * H + h) * W + w) * C + c;
+            if (accumulate) {
+                float prev[V];
+                Vec<T>::load(dst).unpack(prev);
 #pragma unroll
-            for (int k = 0; k < V; ++k) out[k] = (arg[k] == me) ? g[k] : 0.f;
+                for (int k = 0; k < V; ++k) out[k] += prev[k];
+            }
+            Vec<T>::pack(out).store(dst);
         }
-        T* dst = dx + (((int64_t)b * H + h) * W + w) * C + c;
-        if (accumulate) {
-            float prev[V];
-            Vec<T>::load(dst).unpack(prev);
-#pragma unroll
-            for (int k = 0; k < V; ++k) out[k] += prev[k];
-        }
-        Vec<T>::pack(out).store(dst);
     }
 }
 
@@ -276,55 +292,69 @@ maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __rest
 // Transposed bilinear resize (gather form, deterministic): dx[b,hi,wi,:] = sum over the output
 // pixels that read (hi,wi) of weight * dy.  dy: [B,Ho,Wo,ld] at channel offset coff.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ inline void resize_bwd_pixel(const T* __restrict__ dy, int64_t ld, int coff, int b, int Hi, int Wi, int Ho,
-                                        int Wo, int hi, int wi, int c, float* acc) {
-    constexpr int V = Vec<T>::N;
-#pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    if (Hi == Ho && Wi == Wo) {
-        Vec<T>::load(dy + (((int64_t)b * Ho + hi) * Wo + wi) * ld + coff + c).unpack(acc);
-        return;
-    }
-    // candidate output range (conservative), exact membership re-tested with the forward helper
-    const float sh = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
-    const float sw = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
-    int oh_lo = 0, oh_hi = Ho - 1, ow_lo = 0, ow_hi = Wo - 1;
-    if (sh > 0.f) { oh_lo = max(0, (int)floorf((hi - 1) / sh) - 1); oh_hi = min(Ho - 1, (int)ceilf((hi + 1) / sh) + 1); }
-    if (sw > 0.f) { ow_lo = max(0, (int)floorf((wi - 1) / sw) - 1); ow_hi = min(Wo - 1, (int)ceilf((wi + 1) / sw) + 1); }
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-        const Bil bh = bil_t(oh, Hi, Ho);
-        const float wh = (bh.i0 == hi ? bh.l0 : 0.f) + (bh.i1 == hi ? bh.l1 : 0.f);
-        if (wh == 0.f) continue;
-        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
-            const Bil bw = bil_t(ow, Wi, Wo);
-            const float ww = (bw.i0 == wi ? bw.l0 : 0.f) + (bw.i1 == wi ? bw.l1 : 0.f);
-            if (ww == 0.f) continue;
-            float g[V];
-            Vec<T>::load(dy + (((int64_t)b * Ho + oh) * Wo + ow) * ld + coff + c).unpack(g);
-            const float wgt = wh * ww;
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+// weights with which input index `i` enters the outputs o_lo .. o_lo+n-1 of one dimension (n <= 8)
+struct BilT { int o_lo, n; float w[8]; };
+__device__ inline BilT bil_transpose(int i, int in, int out) {
+    BilT t;
+    t.n = 0; t.o_lo = 0;
+    const float sc = (out > 1) ? (float)(in - 1) / (float)(out - 1) : 0.f;
+    int lo = 0, hi = out - 1;
+    if (sc > 0.f) { lo = max(0, (int)floorf((i - 1) / sc) - 1); hi = min(out - 1, (int)ceilf((i + 1) / sc) + 1); }
+    bool started = false;
+    for (int o = lo; o <= hi && t.n < 8; ++o) {
+        const Bil b = bil_t(o, in, out);
+        const float wgt = (b.i0 == i ? b.l0 : 0.f) + (b.i1 == i ? b.l1 : 0.f);
+        if (!started) {
+            if (wgt == 0.f) continue;
+            started = true;
+            t.o_lo = o;
         }
+        t.w[t.n++] = wgt;            // zeros inside the run are kept (harmless), trailing zeros trimmed below
     }
+    while (t.n > 0 && t.w[t.n - 1] == 0.f) --t.n;
+    return t;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kT)
 resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
                   int Wo, int C) {
+    // one CTA per input row (b, hi); the row's transposed weights are computed once per thread
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
-    const int64_t total = (int64_t)B * Hi * Wi * cv;
-    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-        const int c = (int)(i % cv) * V;
-        int64_t p = i / cv;
-        const int wi = (int)(p % Wi); p /= Wi;
-        const int hi = (int)(p % Hi);
-        const int b = (int)(p / Hi);
-        float acc[V];
-        resize_bwd_pixel<T>(dy, ld, coff, b, Hi, Wi, Ho, Wo, hi, wi, c, acc);
-        Vec<T>::pack(acc).store(dx + (((int64_t)b * Hi + hi) * Wi + wi) * C + c);
+    const int b = blockIdx.x / Hi, hi = blockIdx.x - b * Hi;
+    const bool same = (Hi == Ho && Wi == Wo);
+    BilT th;
+    th.n = 0; th.o_lo = 0;
+    if (!same) th = bil_transpose(hi, Hi, Ho);
+    T* xrow = dx + ((int64_t)b * Hi + hi) * Wi * C;
+    for (int wi = threadIdx.y; wi < Wi; wi += blockDim.y) {
+        BilT tw;
+        tw.n = 0; tw.o_lo = 0;
+        if (!same) tw = bil_transpose(wi, Wi, Wo);
+        for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
+            const int c = cvi * V;
+            float acc[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+            if (same) {
+                Vec<T>::load(dy + (((int64_t)b * Ho + hi) * Wo + wi) * ld + coff + c).unpack(acc);
+            } else {
+                for (int a = 0; a < th.n; ++a) {
+                    if (th.w[a] == 0.f) continue;
+                    const T* rowp = dy + (((int64_t)b * Ho + th.o_lo + a) * Wo + tw.o_lo) * ld + coff + c;
+                    for (int q = 0; q < tw.n; ++q) {
+                        const float wgt = th.w[a] * tw.w[q];
+                        if (wgt == 0.f) continue;
+                        float g[V];
+                        Vec<T>::load(rowp + (int64_t)q * ld).unpack(g);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+                    }
+                }
+            }
+            Vec<T>::pack(acc).store(xrow + (int64_t)wi * C + c);
+        }
     }
 }
 
@@ -360,14 +390,14 @@ temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restr
     }
 }
 
-// out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials)
+// out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials), one warp per channel
 __global__ void __launch_bounds__(128)
 partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int which, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0;
-    for (int r = 0; r < nrows; ++r) s += (double)partials[(size_t)r * 2 * C + which * C + c];
-    out[c] = (float)s;
+    double s1, s2;
+    warp_sum_partials(partials, nrows, C, c, s1, s2);
+    if ((threadIdx.x & 31) == 0) out[c] = (float)(which ? s2 : s1);
 }
 
 // per-channel sum of an NCHW fp32 tensor (final_conv bias gradient): grid (chunks, C) partial sums,
@@ -379,7 +409,7 @@ nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __
     const int c = blockIdx.y;
     const int64_t total = (int64_t)B * HW;
     float s = 0.f;
-    for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < (uint32_t)total; i += gridDim.x * kT) {
         const int b = (int)(i / HW), p = (int)(i % HW);
         s += x[((int64_t)b * C + c) * HW + p];
     }
@@ -409,6 +439,12 @@ static inline int stream_grid(int64_t items, int lanesC) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, kT), (int64_t)kNumSMs * 16));
 }
 static inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static inline dim3 row_block(int cv) {
+    const int bx = cv < kT ? cv : kT;
+    int by = kT / bx;
+    if (by < 1) by = 1;
+    return dim3((unsigned)bx, (unsigned)by, 1);
+}
 
 }  // namespace td
 
@@ -452,7 +488,7 @@ extern "C" int td_bn_finalize(const float* partials, int nrows, int channels, in
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && gamma && beta && scale && shift && save_mean &&
                      save_invstd, "td_bn_finalize: bad args");
-    bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    bn_finalize_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         partials, nrows, channels, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
         num_batches_tracked, scale, shift, save_mean, save_invstd);
     return launch_status("bn_finalize");
@@ -491,7 +527,7 @@ extern "C" int td_bn_bwd_finalize(const float* partials, int nrows, int channels
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && scale && save_mean && save_invstd && dgamma &&
                      dbeta && coef, "td_bn_bwd_finalize: bad args");
-    bn_bwd_finalize_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+    bn_bwd_finalize_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
         partials, nrows, channels, (double)count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
     return launch_status("bn_bwd_finalize");
 }
@@ -517,8 +553,7 @@ extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtyp
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0, "td_maxpool2_bwd: channels must be a multiple of %d", V);
     const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
-    const int grid = stream_grid((int64_t)batch * h * w * c / V, 1);
-    TD_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<batch * h, row_block(c / V), 0, (cudaStream_t)stream>>>(
                              (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
     return launch_status("maxpool2_bwd");
 }
@@ -529,8 +564,7 @@ extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff
     TD_CHECK_ARG(dy && dx && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_bwd: bad args");
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0 && ld_dy % V == 0 && dy_coff % V == 0, "td_resize_bilinear_bwd: channels must be a multiple of %d", V);
-    const int grid = stream_grid((int64_t)batch * hi * wi * c / V, 1);
-    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * hi, row_block(c / V), 0, (cudaStream_t)stream>>>(
                              (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c)));
     return launch_status("resize_bilinear_bwd");
 }
@@ -545,16 +579,10 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
     if (int st = check_lanes("td_upcat_bwd", dtype, cs)) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ld = cu + cs;
-    {
-        const int grid = stream_grid((int64_t)batch * (ho / 2) * (wo / 2) * cu / V, 1);
-        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, s>>>((const T*)dout, ld, 0, (T*)dlow, batch, ho / 2,
-                                                                        wo / 2, ho, wo, cu)));
-    }
-    {
-        const int grid = stream_grid((int64_t)batch * hs * ws * cs / V, 1);
-        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grid, kT, 0, s>>>((const T*)dout, ld, cu, (T*)dskip, batch, hs, ws,
-                                                                        ho, wo, cs)));
-    }
+    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * (ho / 2), row_block(cu / V), 0, s>>>(
+                             (const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu)));
+    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * hs, row_block(cs / V), 0, s>>>(
+                             (const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs)));
     {
         const size_t smem = (size_t)(kT / (cs / V)) * cs * sizeof(float);
         TD_DISPATCH_T(dtype, (temb_bwd_kernel<T><<<batch, kT, smem, s>>>((const T*)dout, ld, cu, dtemb, ld_temb, temb_off,
@@ -566,7 +594,7 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
 extern "C" int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && out && nrows > 0 && channels > 0 && (which == 0 || which == 1), "td_partial_sum: bad args");
-    partial_sum_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
+    partial_sum_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
     return launch_status("partial_sum");
 }
 

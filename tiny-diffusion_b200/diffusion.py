@@ -123,6 +123,7 @@ def _sample_impl(noise_model: ConvUNetBase, diffusion: ForwardProcess, device, s
     elif eng.cfg.cond == "text":
         eng.text_in.copy_(cond)
     eng.use_t_dev = True
+    eng.prepare_sampler_embed()
     loop = getattr(eng, "_reverse_loop", None)
     if loop is None or loop.p is not diffusion or loop.use_graph != use_graph:
         loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch, use_graph=use_graph)

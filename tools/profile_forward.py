@@ -21,6 +21,7 @@ eng.refresh_weights()
 eng.x_in.copy_(torch.randn(B, 1, 28, 28))
 eng.y_in.copy_(torch.randint(0, 10, (B,)))
 eng.use_t_dev = True
+eng.prepare_sampler_embed()
 loop = ReverseLoop(fp, eng.x_in, eng.eps, eng.t_dev, eng.launch, use_graph=False)
 torch.cuda.synchronize()
 loop.run(seed=3, steps=iters)
