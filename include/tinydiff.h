@@ -147,6 +147,8 @@ typedef struct {
     float* stats;            /* NULL, or [2*cout]: += per-channel sum / sum-of-squares of   */
                              /* (acc*scale+shift) -- train-mode BatchNorm batch statistics  */
     int x_nchw, y_nchw;      /* direct kernels only: tensor is NCHW fp32 (network input/output) */
+    float* splitk_ws;        /* NULL, or td_conv3x3_splitk_workspace() floats: lets the tcgen05 engine   */
+                             /* split the K loop across CTAs when the layer has too few tiles            */
 } td_conv3x3_desc;
 
 /* Engines.  Weight layout expected by each (w is [cout][3][3][cin] "OHWI" in every case):
@@ -158,6 +160,8 @@ typedef struct {
 #define TD_CONV_DIRECT 2
 
 typedef struct td_conv_plan td_conv_plan;
+/* floats of split-K workspace the tcgen05 engine may use for this layer (0: no split) */
+int64_t td_conv3x3_splitk_workspace(const td_conv3x3_desc* desc);
 int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc* desc, int engine);
 int td_conv3x3_run(const td_conv_plan* plan, void* stream);
 void td_conv3x3_plan_destroy(td_conv_plan* plan);

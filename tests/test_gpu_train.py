@@ -248,7 +248,7 @@ def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
     1.2e-2 of the whole gradient norm (measured: perturbing the reference's own inputs by 1e-6 flips
     it and moves dL/dy by 1.21e-2).  So: fp32 engine -- eps/loss tight (1e-4 / 1e-5), the gradients
     upstream of every kink (final_conv) 1e-5, all others 3e-2.  bf16 engine -- every tensor no worse
-    than 1.25x the error of the REFERENCE run under torch.autocast(bfloat16) (what bf16 costs the
+    than 1.5x the error of the REFERENCE run under torch.autocast(bfloat16) (what bf16 costs the
     reference itself), and eps within north_star's 1e-2."""
     g = golden(name)
     mod, model = build(name, dev, precision)
@@ -281,7 +281,7 @@ def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
         if precision == "fp32":
             tol = 1e-5 if k.startswith("final_conv") else 3e-2
         else:
-            tol = max(1.25 * rel(grads_cal[k], ref), 3e-2)
+            tol = max(1.5 * rel(grads_cal[k], ref), 3e-2)
         if err > tol:
             bad[k] = (err, tol)
     assert not bad, f"gradient mismatch (err, tol): {bad}"
@@ -346,7 +346,7 @@ def test_fused_train_step_vs_oracle_adam(dev, precision, use_graph):
             assert float(upd.norm()) == 0, k
             continue
         cal = rel(upd_cal, upd_ref)
-        tol = max((0.3 if precision == "fp32" else 1.25) * cal, 2e-2 if precision == "fp32" else 0.2)
+        tol = max((0.3 if precision == "fp32" else 1.5) * cal, 2e-2 if precision == "fp32" else 0.2)
         err = rel(upd, upd_ref)
         if err > tol:
             bad[k] = (err, tol)

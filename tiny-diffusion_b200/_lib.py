@@ -57,7 +57,7 @@ class ConvDesc(C.Structure):
                 ("x", _P), ("ldx", C.c_int), ("x_coff", C.c_int),
                 ("y", _P), ("ldy", C.c_int), ("y_coff", C.c_int),
                 ("w", _P), ("scale", _P), ("shift", _P), ("relu", C.c_int),
-                ("stats", _P), ("x_nchw", C.c_int), ("y_nchw", C.c_int)]
+                ("stats", _P), ("x_nchw", C.c_int), ("y_nchw", C.c_int), ("splitk_ws", _P)]
 
 
 _SIGS = {
@@ -75,6 +75,7 @@ _SIGS = {
     "td_embed_head_saved_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "td_embed_head_fwd": (C.c_int, [C.POINTER(EmbedArgs), _P]),
     "td_embed_head_bwd": (C.c_int, [C.POINTER(EmbedArgs), C.POINTER(EmbedGrads), _P]),
+    "td_conv3x3_splitk_workspace": (C.c_int64, [C.POINTER(ConvDesc)]),
     "td_conv3x3_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), C.c_int]),
     "td_conv3x3_run": (C.c_int, [_P, _P]),
     "td_conv3x3_plan_destroy": (None, [_P]),

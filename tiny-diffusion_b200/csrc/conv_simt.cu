@@ -235,12 +235,14 @@ conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
 // instruction-bound: a shared-memory weight load per FMA and 64-bit index math per element).
 // One CTA per image row (b, h); weights live in registers; no integer division per element.
 // ---------------------------------------------------------------------------------------------
-// initial_conv with Cin == 1: threadIdx.x = group of 8 output channels, threadIdx.y = pixel of the row
+// initial_conv with Cin == 1: threadIdx.x = group of 8 output channels, threadIdx.y = chunk of FP pixels of
+// a row; each thread keeps its 8x9 weights in registers and produces FP consecutive pixels per pass
+// (3 x (FP+2) input loads shared by the FP pixels).
+constexpr int FP = 4;
 template <typename Tout>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv3x3_first1_kernel(const td_conv3x3_desc d) {
     const int g = threadIdx.x;
-    const int b = blockIdx.x / d.height, h = blockIdx.x - b * d.height;
     const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [cout][9]
     float w[8][9], sc[8], sh[8];
 #pragma unroll
@@ -250,43 +252,56 @@ conv3x3_first1_kernel(const td_conv3x3_desc d) {
         sc[j] = d.scale ? d.scale[g * 8 + j] : 1.f;
         sh[j] = d.shift ? d.shift[g * 8 + j] : 0.f;
     }
+    const int chunks = (d.width + FP - 1) / FP;
+    const int items = d.batch * d.height * chunks;           // (row, chunk) work items
     // NCHW with one channel == NHWC with one channel
-    const float* xb = reinterpret_cast<const float*>(d.x) + (int64_t)b * d.height * d.width;
-    Tout* yrow = reinterpret_cast<Tout*>(d.y) + ((int64_t)b * d.height + h) * d.width * d.ldy + d.y_coff + g * 8;
-    for (int x0 = threadIdx.y; x0 < d.width; x0 += blockDim.y) {
-        float xv[9];
+    for (int it = blockIdx.x * blockDim.y + threadIdx.y; it < items; it += gridDim.x * blockDim.y) {
+        const int row = it / chunks, x0 = (it - row * chunks) * FP;
+        const int b = row / d.height, h = row - b * d.height;
+        const float* xb = reinterpret_cast<const float*>(d.x) + (int64_t)b * d.height * d.width;
+        float xv[3][FP + 2];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int hh = h + t / 3 - 1, ww = x0 + t % 3 - 1;
-            xv[t] = (hh >= 0 && hh < d.height && ww >= 0 && ww < d.width) ? __ldg(xb + hh * d.width + ww) : 0.f;
+        for (int r = 0; r < 3; ++r) {
+            const int hh = h + r - 1;
+#pragma unroll
+            for (int q = 0; q < FP + 2; ++q) {
+                const int ww = x0 + q - 1;
+                xv[r][q] = (hh >= 0 && hh < d.height && ww >= 0 && ww < d.width) ? __ldg(xb + hh * d.width + ww) : 0.f;
+            }
         }
-        float acc[8];
+        Tout* yrow = reinterpret_cast<Tout*>(d.y) + ((int64_t)b * d.height + h) * d.width * d.ldy + d.y_coff + g * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float a = 0.f;
+        for (int q = 0; q < FP; ++q) {
+            if (x0 + q >= d.width) break;
+            float acc[8];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) a = fmaf(xv[t], w[j][t], a);
-            a = fmaf(a, sc[j], sh[j]);
-            acc[j] = d.relu ? fmaxf(a, 0.f) : a;
-        }
-        Tout* dst = yrow + (int64_t)x0 * d.ldy;
-        if constexpr (sizeof(Tout) == 2) {
-            Vec<__nv_bfloat16>::pack(acc).store(reinterpret_cast<__nv_bfloat16*>(dst));
-        } else {
-            Vec<float>::pack(acc).store(reinterpret_cast<float*>(dst));
-            Vec<float>::pack(acc + 4).store(reinterpret_cast<float*>(dst) + 4);
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) a = fmaf(xv[t / 3][q + t % 3], w[j][t], a);
+                a = fmaf(a, sc[j], sh[j]);
+                acc[j] = d.relu ? fmaxf(a, 0.f) : a;
+            }
+            Tout* dst = yrow + (int64_t)(x0 + q) * d.ldy;
+            if constexpr (sizeof(Tout) == 2) {
+                Vec<__nv_bfloat16>::pack(acc).store(reinterpret_cast<__nv_bfloat16*>(dst));
+            } else {
+                Vec<float>::pack(acc).store(reinterpret_cast<float*>(dst));
+                Vec<float>::pack(acc + 4).store(reinterpret_cast<float*>(dst) + 4);
+            }
         }
     }
 }
 
 // final_conv with Cout == 1: threadIdx.x = lane owning V input channels (L lanes per pixel, L a power of
-// two <= 32), threadIdx.y = pixel; shuffle-reduce over the L lanes.
+// two <= 32), threadIdx.y = pixel slot; every thread handles LP pixels per pass (independent load chains),
+// shuffle-reduce over the L lanes.
+constexpr int LP = 2;
 template <typename Tin>
 __global__ void __launch_bounds__(256)
 conv3x3_last1_kernel(const td_conv3x3_desc d) {
     constexpr int V = Vec<Tin>::N;
     const int L = blockDim.x, lane = threadIdx.x;
-    const int b = blockIdx.x / d.height, h = blockIdx.x - b * d.height;
     const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [1][9][cin]
     float w[9][V];
 #pragma unroll
@@ -294,28 +309,42 @@ conv3x3_last1_kernel(const td_conv3x3_desc d) {
 #pragma unroll
         for (int k = 0; k < V; ++k) w[t][k] = __ldg(wt + t * d.cin + lane * V + k);
     const float sc = d.scale ? d.scale[0] : 1.f, sh = d.shift ? d.shift[0] : 0.f;
-    const Tin* xb = reinterpret_cast<const Tin*>(d.x) + (int64_t)b * d.height * d.width * d.ldx + d.x_coff + lane * V;
-    float* yrow = reinterpret_cast<float*>(d.y) + ((int64_t)b * d.height + h) * d.width * (d.y_nchw ? 1 : d.ldy) +
-                  (d.y_nchw ? 0 : d.y_coff);
-    for (int w0 = 0; w0 < d.width; w0 += blockDim.y) {
-        const int x0 = w0 + threadIdx.y;
-        float acc = 0.f;
-        if (x0 < d.width) {
+    const int HW = d.height * d.width;
+    const int total = d.batch * HW;
+    const int per_pass = gridDim.x * blockDim.y * LP;
+    const Tin* xall = reinterpret_cast<const Tin*>(d.x) + d.x_coff + lane * V;
+    float* yall = reinterpret_cast<float*>(d.y);
+    for (int base = 0; base < total; base += per_pass) {           // uniform trip count: shuffles stay converged
+        float acc[LP];
+        int pix[LP];
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int hh = h + t / 3 - 1, ww = x0 + t % 3 - 1;
-                if (hh < 0 || hh >= d.height || ww < 0 || ww >= d.width) continue;
-                float f[V];
-                Vec<Tin>::load(xb + ((int64_t)hh * d.width + ww) * d.ldx).unpack(f);
+        for (int u = 0; u < LP; ++u) {
+            pix[u] = base + (blockIdx.x * blockDim.y + threadIdx.y) * LP + u;
+            acc[u] = 0.f;
+            if (pix[u] < total) {
+                const int b = pix[u] / HW, rem = pix[u] - b * HW;
+                const int h = rem / d.width, x0 = rem - h * d.width;
+                const Tin* xb = xall + (int64_t)b * HW * d.ldx;
 #pragma unroll
-                for (int k = 0; k < V; ++k) acc = fmaf(f[k], w[t][k], acc);
+                for (int t = 0; t < 9; ++t) {
+                    const int hh = h + t / 3 - 1, ww = x0 + t % 3 - 1;
+                    if (hh < 0 || hh >= d.height || ww < 0 || ww >= d.width) continue;
+                    float f[V];
+                    Vec<Tin>::load(xb + ((int64_t)hh * d.width + ww) * d.ldx).unpack(f);
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[u] = fmaf(f[k], w[t][k], acc[u]);
+                }
             }
         }
-        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (x0 < d.width && lane == 0) {
-            float v = fmaf(acc, sc, sh);
-            if (d.relu) v = fmaxf(v, 0.f);
-            yrow[(int64_t)x0 * (d.y_nchw ? 1 : d.ldy)] = v;
+#pragma unroll
+        for (int u = 0; u < LP; ++u) {
+            for (int o = L >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+            if (pix[u] < total && lane == 0) {
+                float v = fmaf(acc[u], sc, sh);
+                if (d.relu) v = fmaxf(v, 0.f);
+                // NCHW with one channel: flat pixel index; NHWC: pixel * ldy + coff
+                yall[d.y_nchw ? (int64_t)pix[u] : (int64_t)pix[u] * d.ldy + d.y_coff] = v;
+            }
         }
     }
 }
@@ -337,8 +366,10 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
     if (d.cin == 1 && d.x_dtype == TD_F32 && d.cout / 8 <= 256 && d.width * (int64_t)d.height < (1 << 30)) {
         const int groups = d.cout / 8;
         dim3 block((unsigned)groups, (unsigned)std::max(1, 256 / groups));
-        if (d.y_dtype == TD_BF16) conv3x3_first1_kernel<__nv_bfloat16><<<d.batch * d.height, block, 0, s>>>(d);
-        else conv3x3_first1_kernel<float><<<d.batch * d.height, block, 0, s>>>(d);
+        const int items = d.batch * d.height * ((d.width + FP - 1) / FP);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, block.y), kNumSMs * 4));
+        if (d.y_dtype == TD_BF16) conv3x3_first1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+        else conv3x3_first1_kernel<float><<<grid, block, 0, s>>>(d);
         return launch_status("conv3x3_first1");
     }
     if (d.cin <= 8) {
@@ -355,8 +386,10 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
     if (d.cout == 1 && d.cin / V <= 32) {
         const int Ln = d.cin / V;            // power of two (checked at plan creation)
         dim3 block((unsigned)Ln, (unsigned)(256 / Ln));
-        if (d.x_dtype == TD_BF16) conv3x3_last1_kernel<__nv_bfloat16><<<d.batch * d.height, block, 0, s>>>(d);
-        else conv3x3_last1_kernel<float><<<d.batch * d.height, block, 0, s>>>(d);
+        const int64_t total = (int64_t)d.batch * d.height * d.width;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, (int64_t)block.y * LP), kNumSMs * 8));
+        if (d.x_dtype == TD_BF16) conv3x3_last1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+        else conv3x3_last1_kernel<float><<<grid, block, 0, s>>>(d);
         return launch_status("conv3x3_last1");
     }
     int L = d.cin / V;
@@ -427,6 +460,15 @@ extern "C" int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc
     }
     *plan = p;
     return TD_OK;
+}
+
+extern "C" int64_t td_conv3x3_splitk_workspace(const td_conv3x3_desc* d) {
+    if (!d || d->cin % 64 != 0 || d->cout % 64 != 0) return 0;
+    const int64_t pixels = (int64_t)d->batch * d->height * d->width;
+    const int64_t min_ctas = ceil_div(pixels, 128) * ceil_div(d->cout, 256);
+    if (2 * min_ctas > kNumSMs) return 0;                               // enough tiles: never split
+    const int64_t splits = std::min<int64_t>(8, kNumSMs / min_ctas);
+    return splits * pixels * d->cout;
 }
 
 extern "C" int td_conv3x3_run(const td_conv_plan* plan, void* stream) {

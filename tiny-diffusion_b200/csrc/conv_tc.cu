@@ -32,6 +32,8 @@ struct TcParams {
     int bw, bh, bn, tiles_w, tiles_h;
     int stages;
     uint32_t a_bytes;
+    int split_iters;          // K-loop iterations (tap x 64-channel chunk) per split; == 9*cin/64 without split-K
+    float* ws;                // split-K partials [gridDim.z][B*H*W][cout] fp32 (NULL without split-K)
 };
 
 constexpr int TC_THREADS = 192;
@@ -51,6 +53,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* tmem_full_bar = empty_bar + p.stages;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    // [BLOCK_N] epilogue affine, staged once per CTA (16-byte aligned for float4 reads)
+    float* s_scale = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);
+    float* s_shift = s_scale + BLOCK_N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -61,7 +66,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
     const int nt = blockIdx.y;
     const int kchunks = p.cin >> 6;
-    const int iters = 9 * kchunks;
+    const int it_begin = blockIdx.z * p.split_iters;
+    const int iters = min(9 * kchunks - it_begin, p.split_iters);     // this CTA's share of the K loop
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_x);
@@ -76,6 +82,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<BLOCK_N>(tmem_ptr);
+    if (warp >= 2) {
+        for (int c = threadIdx.x - 64; c < BLOCK_N; c += TC_THREADS - 64) {
+            s_scale[c] = p.scale ? __ldg(p.scale + nt * BLOCK_N + c) : 1.f;
+            s_shift[c] = p.shift ? __ldg(p.shift + nt * BLOCK_N + c) : 0.f;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -88,7 +100,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], p.a_bytes + (uint32_t)B_STAGE);
-                const int tap = it / kchunks, cc = it - tap * kchunks;
+                const int git = it_begin + it;
+                const int tap = git / kchunks, cc = git - tap * kchunks;
                 const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                 tma_load_4d(smem_a + (size_t)s * TC_A_STAGE, &tmap_x, &full_bar[s], p.x_coff + cc * 64, w0 + dx, h0 + dy, n0);
                 tma_load_2d(smem_b + (size_t)s * B_STAGE, &tmap_w, &full_bar[s], tap * p.cin + cc * 64, nt * BLOCK_N);
@@ -133,14 +146,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
             const int cbase = nt * BLOCK_N + c0;
+            if (p.ws) {          // split-K: raw fp32 partial, the affine / activation run in the reduce kernel
+                if (valid) {
+                    float* dst = p.ws + ((int64_t)blockIdx.z * ((int64_t)p.B * p.H * p.W) + pix) * p.cout + cbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+                continue;
+            }
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float f = __uint_as_float(r[j]);
-                if (p.scale) f *= __ldg(p.scale + cbase + j);
-                if (p.shift) f += __ldg(p.shift + cbase + j);
-                if (p.relu) f = fmaxf(f, 0.f);
-                v[j] = f;
+            for (int j = 0; j < 32; j += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(s_scale + c0 + j);
+                const float4 sh = *reinterpret_cast<const float4*>(s_shift + c0 + j);
+                v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
+                v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             if (valid) {
                 if (p.y_dtype == TD_BF16) {
@@ -160,6 +188,41 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<BLOCK_N>(tmem_base);
+    }
+}
+
+// split-K second pass: y = act(scale * sum_s ws[s] + shift), fixed summation order
+template <typename Tout>
+__global__ void __launch_bounds__(256)
+conv_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t pixels, int cout, const float* __restrict__ scale,
+                          const float* __restrict__ shift, int relu, Tout* __restrict__ y, int ldy, int y_coff) {
+    const int cq = cout >> 2;
+    const int64_t total = pixels * cq;
+    const int64_t slice = pixels * cout;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pix = e / cq;
+        const int c = (int)(e - pix * cq) * 4;
+        float4 a = *reinterpret_cast<const float4*>(ws + pix * cout + c);
+        for (int z = 1; z < splits; ++z) {
+            const float4 b = *reinterpret_cast<const float4*>(ws + z * slice + pix * cout + c);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = fmaf(v[k], scale ? scale[c + k] : 1.f, shift ? shift[c + k] : 0.f);
+            if (relu) v[k] = fmaxf(v[k], 0.f);
+        }
+        Tout* dst = y + pix * ldy + y_coff + c;
+        if constexpr (sizeof(Tout) == 2) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&lo);
+            u.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dst) = u;
+        } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
 }
 
@@ -243,9 +306,21 @@ int tc_plan_init(td_conv_plan* p) {
         int s2 = (100 * 1024) / stage_bytes;
         if (s2 >= 2) stages = s2 > 4 ? 4 : s2;
     }
+    // Too few tiles to fill the 148 SMs (4x4 / 7x7 / 8x8 feature maps at batch 128): split the K loop
+    // (taps x channel chunks) across CTAs.  Each split writes an fp32 partial tile; a second kernel sums
+    // them in fixed order and applies the epilogue.  Operand traffic per CTA is unchanged.
+    p->split_k = 1;
+    const int iters = 9 * (d.cin / 64);
+    if (d.splitk_ws && 2 * ctas <= kNumSMs && iters >= 64) {     // short K loops lose more to the second pass
+        int sk = (int)(kNumSMs / ctas);
+        if (sk > 8) sk = 8;
+        while (sk > 1 && iters / sk < 8) --sk;
+        if (const char* e = getenv("TD_TC_SPLIT_K")) { int v = atoi(e); if (v >= 1 && v <= sk) sk = v; }
+        p->split_k = sk;
+    }
     if (const char* e = getenv("TD_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
     p->stages = stages;
-    p->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    p->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * p->block_n * 4 + 1024;
 
     {   // activations: (C, W, H, N)
         cuuint64_t gdim[4] = {(cuuint64_t)d.ldx, (cuuint64_t)d.width, (cuuint64_t)d.height, (cuuint64_t)d.batch};
@@ -278,9 +353,20 @@ static int launch_tc(const td_conv_plan* p, const TcParams& prm, cudaStream_t s)
         TD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         configured_smem = p->smem_bytes;
     }
-    dim3 grid((unsigned)(p->tiles_w * p->tiles_h * p->tiles_n), (unsigned)p->n_tiles);
+    dim3 grid((unsigned)(p->tiles_w * p->tiles_h * p->tiles_n), (unsigned)p->n_tiles, (unsigned)p->split_k);
     conv3x3_tc_kernel<BLOCK_N><<<grid, TC_THREADS, p->smem_bytes, s>>>(p->tmap_x, p->tmap_w, prm);
-    return launch_status("conv3x3_tc");
+    int st = launch_status("conv3x3_tc");
+    if (st != TD_OK || p->split_k == 1) return st;
+    const td_conv3x3_desc& d = p->d;
+    const int64_t pixels = (int64_t)d.batch * d.height * d.width;
+    const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels * (d.cout / 4), 256), kNumSMs * 8));
+    if (d.y_dtype == TD_BF16)
+        conv_splitk_reduce_kernel<__nv_bfloat16><<<rgrid, 256, 0, s>>>(d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
+                                                                       d.relu, (__nv_bfloat16*)d.y, d.ldy, d.y_coff);
+    else
+        conv_splitk_reduce_kernel<float><<<rgrid, 256, 0, s>>>(d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
+                                                               d.relu, (float*)d.y, d.ldy, d.y_coff);
+    return launch_status("conv_splitk_reduce");
 }
 
 int tc_plan_run(const td_conv_plan* p, cudaStream_t s) {
@@ -292,6 +378,9 @@ int tc_plan_run(const td_conv_plan* p, cudaStream_t s) {
     prm.bw = p->bw; prm.bh = p->bh; prm.bn = p->bn; prm.tiles_w = p->tiles_w; prm.tiles_h = p->tiles_h;
     prm.stages = p->stages;
     prm.a_bytes = (uint32_t)(64 * p->bw * p->bh * p->bn * 2);
+    const int iters = 9 * (d.cin / 64);
+    prm.split_iters = (int)ceil_div(iters, p->split_k);
+    prm.ws = p->split_k > 1 ? d.splitk_ws : nullptr;
     switch (p->block_n) {
         case 64: return launch_tc<64>(p, prm, s);
         case 128: return launch_tc<128>(p, prm, s);

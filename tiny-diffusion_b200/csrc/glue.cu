@@ -69,18 +69,25 @@ maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W,
 // ---------------------------------------------------------------------------------------------
 // out = [ up2x(low) | resize(skip + temb) ]
 // ---------------------------------------------------------------------------------------------
+// 4 taps with precombined weights: out = w00*f00 + w01*f01 + w10*f10 + w11*f11
 template <typename T>
-__device__ inline void bilerp_row(const T* __restrict__ r0, const T* __restrict__ r1, int C, const Bil& bh, const Bil& bw,
-                                  float* out) {
+__device__ inline void bilerp4(const T* __restrict__ r0, const T* __restrict__ r1, int C, int i0, int i1, float w00,
+                               float w01, float w10, float w11, float* out) {
     constexpr int V = Vec<T>::N;
     float f00[V], f01[V], f10[V], f11[V];
-    Vec<T>::load(r0 + (int64_t)bw.i0 * C).unpack(f00);
-    Vec<T>::load(r0 + (int64_t)bw.i1 * C).unpack(f01);
-    Vec<T>::load(r1 + (int64_t)bw.i0 * C).unpack(f10);
-    Vec<T>::load(r1 + (int64_t)bw.i1 * C).unpack(f11);
+    Vec<T>::load(r0 + (int64_t)i0 * C).unpack(f00);
+    Vec<T>::load(r0 + (int64_t)i1 * C).unpack(f01);
+    Vec<T>::load(r1 + (int64_t)i0 * C).unpack(f10);
+    Vec<T>::load(r1 + (int64_t)i1 * C).unpack(f11);
 #pragma unroll
-    for (int k = 0; k < V; ++k)
-        out[k] = bh.l0 * (bw.l0 * f00[k] + bw.l1 * f01[k]) + bh.l1 * (bw.l0 * f10[k] + bw.l1 * f11[k]);
+    for (int k = 0; k < V; ++k) out[k] = fmaf(w00, f00[k], fmaf(w01, f01[k], fmaf(w10, f10[k], w11 * f11[k])));
+}
+
+constexpr int kMaxRowW = 64;      // widest output row the column tables are sized for
+
+// column interpolation table of one output row, built once per CTA
+__device__ inline void build_col_table(Bil* tab, int in, int out) {
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < out; i += blockDim.x * blockDim.y) tab[i] = bil(i, in, out);
 }
 
 template <typename T>
@@ -88,21 +95,27 @@ __global__ void __launch_bounds__(256)
 upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
              int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
     constexpr int V = Vec<T>::N;
+    __shared__ Bil col_low[kMaxRowW], col_skip[kMaxRowW];
     const int Ct = Cu + Cs;
     const int cv = Ct / V;
     const int Hl = Ho / 2, Wl = Wo / 2;
     const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
     T* orow = out + ((int64_t)b * Ho + ho) * Wo * Ct;
     const bool same = (Hs == Ho && Ws == Wo);
+    build_col_table(col_low, Wl, Wo);
+    if (!same) build_col_table(col_skip, Ws, Wo);
+    __syncthreads();
     for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
         const int c = cvi * V;
         if (c < Cu) {
             const Bil bh = bil(ho, Hl, Ho);
             const T* r0 = low + (((int64_t)b * Hl + bh.i0) * Wl) * Cu + c;
             const T* r1 = low + (((int64_t)b * Hl + bh.i1) * Wl) * Cu + c;
+#pragma unroll 2
             for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+                const Bil bw = col_low[wo];
                 float r[V];
-                bilerp_row<T>(r0, r1, Cu, bh, bil(wo, Wl, Wo), r);
+                bilerp4<T>(r0, r1, Cu, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
                 Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
             }
         } else {
@@ -115,10 +128,15 @@ upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float*
             const Bil bh = bil(ho, Hs, Ho);
             const T* r0 = skip + (((int64_t)b * Hs + (same ? ho : bh.i0)) * Ws) * Cs + cs;
             const T* r1 = skip + (((int64_t)b * Hs + (same ? ho : bh.i1)) * Ws) * Cs + cs;
+#pragma unroll 2
             for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
                 float r[V];
-                if (same) Vec<T>::load(r0 + (int64_t)wo * Cs).unpack(r);
-                else bilerp_row<T>(r0, r1, Cs, bh, bil(wo, Ws, Wo), r);
+                if (same) {
+                    Vec<T>::load(r0 + (int64_t)wo * Cs).unpack(r);
+                } else {
+                    const Bil bw = col_skip[wo];
+                    bilerp4<T>(r0, r1, Cs, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
+                }
 #pragma unroll
                 for (int k = 0; k < V; ++k) r[k] += te[k];
                 Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
@@ -131,17 +149,22 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
     constexpr int V = Vec<T>::N;
+    __shared__ Bil col[kMaxRowW];
     const int cv = C / V;
     const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
     const Bil bh = bil(ho, Hi, Ho);
     T* yrow = y + ((int64_t)b * Ho + ho) * Wo * C;
+    build_col_table(col, Wi, Wo);
+    __syncthreads();
     for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
         const int c = cvi * V;
         const T* r0 = x + (((int64_t)b * Hi + bh.i0) * Wi) * C + c;
         const T* r1 = x + (((int64_t)b * Hi + bh.i1) * Wi) * C + c;
+#pragma unroll 2
         for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
+            const Bil bw = col[wo];
             float r[V];
-            bilerp_row<T>(r0, r1, C, bh, bil(wo, Wi, Wo), r);
+            bilerp4<T>(r0, r1, C, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
             Vec<T>::pack(r).store(yrow + (int64_t)wo * C + c);
         }
     }
@@ -207,7 +230,7 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
                             void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(low && skip && temb && out, "td_upcat_fwd: null pointer");
-    TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0, "td_upcat_fwd: bad output size");
+    TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0 && wo <= kMaxRowW, "td_upcat_fwd: bad output size");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
@@ -227,7 +250,7 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
 extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int batch, int hi, int wi, int ho, int wo,
                                       int c, void* stream) {
     TD_REQUIRE_ARCH();
-    TD_CHECK_ARG(x && y && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_fwd: bad args");
+    TD_CHECK_ARG(x && y && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && wo <= kMaxRowW && c > 0, "td_resize_bilinear_fwd: bad args");
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");

@@ -127,6 +127,12 @@ def conv3x3(x, w_ohwi, scale=None, shift=None, relu=False, engine=L.CONV_SIMT, o
     d.y, d.ldy, d.y_coff = out.data_ptr(), (cout if y_nchw else out.shape[3]), y_coff
     d.w, d.scale, d.shift = w_ohwi.data_ptr(), L.ptr(scale), L.ptr(shift)
     d.relu, d.stats, d.x_nchw, d.y_nchw = int(relu), None, int(x_nchw), int(y_nchw)
+    ws = None
+    if engine == L.CONV_TC:
+        need = int(lib.td_conv3x3_splitk_workspace(C.byref(d)))
+        if need > 0:
+            ws = torch.empty(need, device=x.device)
+            d.splitk_ws = ws.data_ptr()
     h = C.c_void_p()
     L.check(lib.td_conv3x3_plan_create(C.byref(h), C.byref(d), engine), "td_conv3x3_plan_create")
     try:

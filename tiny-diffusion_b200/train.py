@@ -20,7 +20,7 @@ import torch
 
 from . import _lib as L
 from .dp import allreduce_mean_, grad_ready_index, plan_buckets   # noqa: F401
-from .unet import UNetConfig, _CONVS, _ConvPlan, _pool
+from .unet import UNetConfig, _CONVS, _ConvPlan, _pool, alloc_splitk_ws
 
 BN_EPS_DEFAULT = 1e-5
 
@@ -137,6 +137,9 @@ class UNetTrainEngine:
         self.d_proj_b = torch.zeros_like(self.proj_b)
 
         self._alloc_packed()
+        # forward convs (cout, size) and data-gradient convs (their "cout" is the layer's cin)
+        self.splitk_ws = alloc_splitk_ws(self.lib, batch, [(cout, size) for _, _, _, size, _, cout in self.layers] +
+                                         [(cin, size) for _, _, cin, size, _, _ in self.layers], device)
         self._build()
         self._weights_version = None
 
@@ -206,6 +209,7 @@ class UNetTrainEngine:
         d.y, d.ldy, d.y_coff = y.data_ptr(), (cout if y_nchw else y.shape[3]), 0
         d.w, d.scale, d.shift, d.relu, d.stats = w.data_ptr(), None, L.ptr(shift), 0, None
         d.x_nchw, d.y_nchw = int(x_nchw), int(y_nchw)
+        d.splitk_ws = L.ptr(self.splitk_ws)
         return d
 
     def _wgrad(self, name, x, cin, dy, cout, size, engine, x_nchw=False, dy_nchw=False):

@@ -49,6 +49,16 @@ def _pool(n: int, ceil: bool) -> int:
     return (n + 1) // 2 if ceil else n // 2
 
 
+def alloc_splitk_ws(lib, batch: int, layers, device) -> Optional[torch.Tensor]:
+    """One split-K workspace shared by every tcgen05 conv of a plan (layers: (cout, size) pairs)."""
+    need = 0
+    for cout, size in layers:
+        d = L.ConvDesc()
+        d.batch, d.height, d.width, d.cin, d.cout = batch, size, size, 64, cout
+        need = max(need, int(lib.td_conv3x3_splitk_workspace(C.byref(d))))
+    return torch.zeros(need, device=device) if need > 0 else None
+
+
 class _ConvPlan:
     """Owns one td_conv_plan handle."""
 
@@ -132,6 +142,8 @@ class UNetEngine:
         self.proj_w = torch.zeros(c1 + c2 + c3, cfg.time_dim, device=device, dtype=torch.float32)
         self.proj_b = torch.zeros(c1 + c2 + c3, device=device, dtype=torch.float32)
         self._alloc_packed()
+        self.splitk_ws = alloc_splitk_ws(self.lib, batch, [(c, s) for c, s in (
+            (c1, s0), (c2, s1), (c3, s2), (cfg.bott, s3), (d3, u3), (d2, u2), (d1, u1))], device)
         self._build_plans()
         self._weights_version = None
 
@@ -215,6 +227,7 @@ class UNetEngine:
         d.relu = 1 if relu else 0
         d.stats = None
         d.x_nchw, d.y_nchw = int(x_nchw), int(y_nchw)
+        d.splitk_ws = L.ptr(self.splitk_ws)
         plan = _ConvPlan(d, self.engines[name])
         self.plans[name] = plan
         return plan
