@@ -43,14 +43,17 @@ def launches(path):
     kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
     mu = hdr.index("Metric Unit")
     agg = collections.OrderedDict()
+    mn = hdr.index("Metric Name")
     for r in rows[1:]:
+        if r[mn] != "gpu__time_duration.sum":
+            continue
         name = r[kn].split("(")[0].replace("void ", "")[:90]
         ns = float(r[mv].replace(",", "")) * {"ns": 1.0, "us": 1e3, "ms": 1e6}.get(r[mu], 1.0)
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += ns
     tot = sum(v[1] for v in agg.values())
-    print(f"# {path}: {len(rows) - 1} launches, {tot / 1e3:.1f} us total (ncu per-launch times: cold cache, serialised)")
+    print(f"# {path}: {sum(v[0] for v in agg.values())} launches, {tot / 1e3:.1f} us total (ncu per-launch times: cold cache, serialised)")
     print(f"{'count':>6} {'total_us':>10} {'avg_us':>8} {'share':>7}  kernel")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{v[0]:6d} {v[1] / 1e3:10.1f} {v[1] / v[0] / 1e3:8.2f} {100 * v[1] / tot:6.1f}%  {k}")
