@@ -144,8 +144,9 @@ typedef struct {
     const float* scale;      /* [cout] or NULL (=1)  : y = relu?(acc*scale + shift)           */
     const float* shift;      /* [cout] or NULL (=0)                                         */
     int relu;
-    float* stats;            /* NULL, or [2*cout]: += per-channel sum / sum-of-squares of   */
-                             /* (acc*scale+shift) -- train-mode BatchNorm batch statistics  */
+    float* stats;            /* NULL, or train-mode BatchNorm partial sums emitted by the tcgen05 epilogue:  */
+                             /* [td_conv3x3_stats_rows(plan)][2][cout] { sum, sum of squares } of the fp32   */
+                             /* outputs, followed by one zero row [cout] -- the layout td_bn_finalize reads  */
     int x_nchw, y_nchw;      /* direct kernels only: tensor is NCHW fp32 (network input/output) */
     float* splitk_ws;        /* NULL, or td_conv3x3_splitk_workspace() floats: lets the tcgen05 engine   */
                              /* split the K loop across CTAs when the layer has too few tiles            */
@@ -164,6 +165,8 @@ typedef struct td_conv_plan td_conv_plan;
 int64_t td_conv3x3_splitk_workspace(const td_conv3x3_desc* desc);
 int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc* desc, int engine);
 int td_conv3x3_run(const td_conv_plan* plan, void* stream);
+/* number of partial rows the plan writes to desc.stats per run (0: statistics are not fused, use td_bn_stats) */
+int td_conv3x3_stats_rows(const td_conv_plan* plan);
 void td_conv3x3_plan_destroy(td_conv_plan* plan);
 /* algorithmic FLOPs (2*MAC) of one run of the plan */
 double td_conv3x3_flops(const td_conv_plan* plan);

@@ -176,6 +176,22 @@ def test_conv_dgrad_tc_bf16(dev, B, H, cin, cout):
     assert rel(nchw(dx), dx_ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,cin,cout", [(3, 28, 64, 128), (5, 14, 128, 256), (37, 7, 256, 256), (2, 32, 64, 64), (4, 16, 128, 128)])
+def test_conv_tc_fused_bn_statistics(dev, B, H, cin, cout):
+    """Train-mode BatchNorm partial sums from the tcgen05 epilogue == per-channel sums of the fp32 conv output."""
+    from tinydiff import _lib as L, ops
+    x, w, dy, _, _ = _conv_case(B, H, cin, cout)
+    wp = ops.pack_conv_weight(w.to(dev), torch.bfloat16)
+    y, part, krow = ops.conv3x3(nhwc(x).to(dev).to(torch.bfloat16), wp, engine=L.CONV_TC, out_dtype=torch.float32,
+                                want_stats=True)
+    assert part.shape[0] > 0 and torch.isfinite(part).all() and float(krow.abs().max()) == 0.0
+    yd = y.double().view(-1, cout)
+    assert rel(part[:, 0].double().sum(0), yd.sum(0)) < 1e-5
+    assert rel(part[:, 1].double().sum(0), (yd * yd).sum(0)) < 1e-5
+    want = F.conv2d(x, w, padding=1)
+    assert rel(nchw(y), want) < 2e-3
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 256), (37, 20, 1), (130, 70, 33), (256, 256, 4096)])
 def test_gemm_f32(dev, ta, tb, M, N, K):

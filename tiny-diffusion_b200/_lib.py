@@ -78,6 +78,7 @@ _SIGS = {
     "td_conv3x3_splitk_workspace": (C.c_int64, [C.POINTER(ConvDesc)]),
     "td_conv3x3_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), C.c_int]),
     "td_conv3x3_run": (C.c_int, [_P, _P]),
+    "td_conv3x3_stats_rows": (C.c_int, [_P]),
     "td_conv3x3_plan_destroy": (None, [_P]),
     "td_conv3x3_flops": (C.c_double, [_P]),
     "td_maxpool2_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

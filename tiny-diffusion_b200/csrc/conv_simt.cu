@@ -462,6 +462,11 @@ extern "C" int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc
     return TD_OK;
 }
 
+extern "C" int td_conv3x3_stats_rows(const td_conv_plan* plan) {
+    if (!plan || !plan->d.stats || plan->engine != TD_CONV_TC) return 0;
+    return plan->tiles_w * plan->tiles_h * plan->tiles_n;
+}
+
 extern "C" int64_t td_conv3x3_splitk_workspace(const td_conv3x3_desc* d) {
     if (!d || d->cin % 64 != 0 || d->cout % 64 != 0) return 0;
     const int64_t pixels = (int64_t)d->batch * d->height * d->width;

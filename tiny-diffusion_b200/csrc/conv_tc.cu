@@ -32,11 +32,28 @@ struct TcParams {
     int bw, bh, bn, tiles_w, tiles_h;
     int stages;
     uint32_t a_bytes;
+    float* stats;             // train-mode BatchNorm partials [m tiles][2][cout] (+ zero K row), or NULL
     int split_iters;          // K-loop iterations (tap x 64-channel chunk) per split; == 9*cin/64 without split-K
     float* ws;                // split-K partials [gridDim.z][B*H*W][cout] fp32 (NULL without split-K)
 };
 
 constexpr int TC_THREADS = 192;
+
+// v[j] of lane r = element (row r, column j) of a 32x32 tile; returns on lane L the sum over the 32 rows
+// of column L (31 shuffles: each step exchanges half of the live columns with the partner lane).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float send = up ? v[i] : v[i + s];
+            const float keep = up ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
 constexpr int TC_A_STAGE = 128 * 128;   // 128 rows x 128 bytes (64 bf16)
 
 template <int BLOCK_N>
@@ -181,6 +198,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                     for (int j = 0; j < 32; j += 4) Vec<float>::pack(v + j).store(dst + j);
                 }
             }
+            if (p.stats) {
+                // per-channel sum / sum of squares over this warp's 32 rows, from the fp32 accumulators;
+                // the pipeline stages are idle by now, so their shared memory stages the 4 warps' partials
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = valid ? v[j] : 0.f;
+                    sq[j] = v[j] * v[j];
+                }
+                const float cs = warp_column_sums(v, lane);
+                const float cq = warp_column_sums(sq, lane);
+                float* st = reinterpret_cast<float*>(smem_a);
+                st[(q * 2 + 0) * BLOCK_N + c0 + lane] = cs;
+                st[(q * 2 + 1) * BLOCK_N + c0 + lane] = cq;
+            }
+        }
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+            const float* st = reinterpret_cast<const float*>(smem_a);
+            const int tid = threadIdx.x - 64;
+            float* row = p.stats + (int64_t)blockIdx.x * 2 * p.cout + nt * BLOCK_N;
+            for (int c = tid; c < 2 * BLOCK_N; c += 128) {
+                const int which = c / BLOCK_N, cc = c - which * BLOCK_N;
+                const float t = (st[(0 * 2 + which) * BLOCK_N + cc] + st[(1 * 2 + which) * BLOCK_N + cc]) +
+                                (st[(2 * 2 + which) * BLOCK_N + cc] + st[(3 * 2 + which) * BLOCK_N + cc]);
+                row[which * p.cout + cc] = t;
+            }
+            if (blockIdx.x == 0)           // the finalize kernel reads a "shift" row K after the partial rows: zero here
+                for (int c = tid; c < BLOCK_N; c += 128) p.stats[(int64_t)gridDim.x * 2 * p.cout + nt * BLOCK_N + c] = 0.f;
         }
         tc_fence_before();
     }
@@ -267,7 +313,7 @@ int tc_plan_init(td_conv_plan* p) {
         set_error("tc conv: channel strides/offsets must be multiples of 8");
         return TD_ERR_UNSUPPORTED;
     }
-    if (d.x_nchw || d.y_nchw || d.stats) { set_error("tc conv: NCHW / stats not supported"); return TD_ERR_UNSUPPORTED; }
+    if (d.x_nchw || d.y_nchw) { set_error("tc conv: NCHW tensors not supported"); return TD_ERR_UNSUPPORTED; }
     if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15) || ((uintptr_t)d.y & 15)) {
         set_error("tc conv: tensors must be 16-byte aligned");
         return TD_ERR_ARG;
@@ -311,7 +357,7 @@ int tc_plan_init(td_conv_plan* p) {
     // them in fixed order and applies the epilogue.  Operand traffic per CTA is unchanged.
     p->split_k = 1;
     const int iters = 9 * (d.cin / 64);
-    if (d.splitk_ws && 2 * ctas <= kNumSMs && iters >= 64) {     // short K loops lose more to the second pass
+    if (d.splitk_ws && !d.stats && 2 * ctas <= kNumSMs && iters >= 64) {     // short K loops lose more to the second pass
         int sk = (int)(kNumSMs / ctas);
         if (sk > 8) sk = 8;
         while (sk > 1 && iters / sk < 8) --sk;
@@ -381,6 +427,7 @@ int tc_plan_run(const td_conv_plan* p, cudaStream_t s) {
     const int iters = 9 * (d.cin / 64);
     prm.split_iters = (int)ceil_div(iters, p->split_k);
     prm.ws = p->split_k > 1 ? d.splitk_ws : nullptr;
+    prm.stats = d.stats;
     switch (p->block_n) {
         case 64: return launch_tc<64>(p, prm, s);
         case 128: return launch_tc<128>(p, prm, s);

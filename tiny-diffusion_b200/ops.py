@@ -107,7 +107,7 @@ def pack_conv_weight(w_oihw, dtype=torch.float32):
 
 
 def conv3x3(x, w_ohwi, scale=None, shift=None, relu=False, engine=L.CONV_SIMT, out_dtype=None, x_nchw=False,
-            y_nchw=False, out=None, y_coff=0, x_coff=0, cin=None):
+            y_nchw=False, out=None, y_coff=0, x_coff=0, cin=None, want_stats=False):
     """x: NHWC (or NCHW fp32 when x_nchw).  Returns NHWC (or NCHW) output."""
     _dev(x)
     lib = L.load()
@@ -133,12 +133,19 @@ def conv3x3(x, w_ohwi, scale=None, shift=None, relu=False, engine=L.CONV_SIMT, o
         if need > 0:
             ws = torch.empty(need, device=x.device)
             d.splitk_ws = ws.data_ptr()
+    part = None
+    if want_stats:
+        part = torch.full(((B * H * W // 32 + 2) * 2 * cout + cout,), float("nan"), device=x.device)
+        d.stats = part.data_ptr()
     h = C.c_void_p()
     L.check(lib.td_conv3x3_plan_create(C.byref(h), C.byref(d), engine), "td_conv3x3_plan_create")
     try:
         L.check(lib.td_conv3x3_run(h, L.stream_ptr()), "td_conv3x3_run")
+        rows = int(lib.td_conv3x3_stats_rows(h)) if want_stats else 0
     finally:
         lib.td_conv3x3_plan_destroy(h)
+    if want_stats:
+        return out, part[:rows * 2 * cout].view(rows, 2, cout), part[rows * 2 * cout:rows * 2 * cout + cout]
     return out
 
 

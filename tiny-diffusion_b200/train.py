@@ -119,7 +119,8 @@ class UNetTrainEngine:
         for name, _, _, size, _, cout in self.layers:
             rows = int(self.lib.td_chan_reduce_rows(L.TD_F32, B * size * size, cout))
             rows_b = int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout))
-            max_part = max(max_part, (max(rows, rows_b) * 2 + 1) * cout)
+            rows_fused = B * size * size // 32 + 2          # upper bound on the conv epilogue's partial rows (tiles)
+            max_part = max(max_part, (max(rows, rows_b, rows_fused) * 2 + 1) * cout)
             self.bn[name] = {k: torch.zeros(cout, device=dev) for k in ("scale", "shift", "mean", "invstd")}
             self.bn[name]["coef"] = torch.zeros(3, cout, device=dev)
             self.bn[name]["rows"] = rows
@@ -254,10 +255,15 @@ class UNetTrainEngine:
             conv, bn = self.conv_of[name]
             x, y, a = bf[xin], self.yraw[name], bf[out]
             eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
-            p = conv_plan(name, self._conv_desc(x, cin, y, cout, self.w_fwd[name]), eng)
+            cd = self._conv_desc(x, cin, y, cout, self.w_fwd[name])
+            if eng == L.CONV_TC:
+                cd.stats = part                         # batch statistics from the fp32 accumulators (epilogue)
+            p = conv_plan(name, cd, eng)
             fwd.append((name, p.run))
             st_ = self.bn[name]
             rows, P = st_["rows"], B * size * size
+            fused_rows = int(lib.td_conv3x3_stats_rows(p.handle))
+            assert (fused_rows * 2 + 1) * cout <= self.partials.numel()
             yp, ap = y.data_ptr(), a.data_ptr()
             g_, b_, cb = bn.weight.data_ptr(), bn.bias.data_ptr(), conv.bias.data_ptr()
             rm, rv, nbt = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr()
@@ -265,8 +271,11 @@ class UNetTrainEngine:
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
 
             def bn_fwd(st):
-                L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
-                L.check(lib.td_bn_finalize(part, rows, cout, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, st),
+                nrows = fused_rows
+                if fused_rows == 0:
+                    nrows = rows
+                    L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
+                L.check(lib.td_bn_finalize(part, nrows, cout, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, st),
                         "td_bn_finalize")
                 L.check(lib.td_bn_relu_apply(yp, sc, sh, ap, adt, cout, 0, P, cout, 1, st), "td_bn_relu_apply")
             fwd.append((f"bn:{name}", bn_fwd))
