@@ -199,6 +199,39 @@ def test_conv_tc_bf16(dev, B, H, cin, cout):
     assert rel(got32, want) < 2e-5
 
 
+# The halo kernel (conv_halo.cu): both shared-memory layouts forced on every map size they accept, the
+# per-tap kernel forced on the same shapes, and batches large enough that each persistent CTA walks
+# several (n-tile, subtile) units with paired and unpaired subtiles.
+@pytest.mark.parametrize("mode", ["1", "3", "off"])
+@pytest.mark.parametrize("B,H,cin,cout", [(5, 28, 64, 128), (3, 14, 128, 256), (7, 7, 256, 128), (2, 16, 128, 128),
+                                          (3, 32, 64, 64), (2, 8, 64, 64), (9, 4, 64, 128), (66, 28, 64, 128),
+                                          (150, 16, 64, 64), (33, 20, 64, 64)])
+def test_conv_halo_layouts(dev, monkeypatch, mode, B, H, cin, cout):
+    if mode == "off":
+        monkeypatch.setenv("TD_TC_HALO", "0")
+    else:
+        monkeypatch.setenv("TD_TC_HALO_MODE", mode)
+    got32, want = _conv_case(dev, B, H, cin, cout, 1, torch.bfloat16, torch.float32, seed=B + H)
+    assert rel(got32, want) < 2e-5
+    assert float((got32 - want).abs().max()) < 1e-3           # no stray element (halo / dead-column handling)
+
+
+def test_conv_halo_channel_slices(dev):
+    """Input read from / output written into a channel slice of a wider NHWC buffer (the decoder concat)."""
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(5)
+    B, H, cin, cout = 4, 28, 64, 128
+    xw = torch.randn(B, H, H, 192, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+    out = torch.full((B, H, H, 256), 7.0, device=dev, dtype=torch.float32)
+    ops.conv3x3(xw.to(dev).to(torch.bfloat16), ops.pack_conv_weight(w.to(dev), torch.bfloat16), None, None, False, 1,
+                torch.float32, out=out, y_coff=128, x_coff=64, cin=cin)
+    xr = xw[..., 64:128].to(torch.bfloat16).double().permute(0, 3, 1, 2)
+    want = F.conv2d(xr, w.to(torch.bfloat16).double(), padding=1)
+    assert rel(nchw(out[..., 128:]), want) < 2e-5
+    assert float((out[..., :128] - 7.0).abs().max()) == 0.0
+
+
 def test_conv_direct_first_last(dev):
     from tinydiff import ops
     g = torch.Generator().manual_seed(9)

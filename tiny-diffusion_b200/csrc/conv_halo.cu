@@ -1,0 +1,426 @@
+// 3x3 convolution on the tcgen05 tensor cores, halo variant: the activation tile is loaded ONCE per
+// 64-channel chunk together with its one-pixel halo, and the nine taps of the stencil read it through
+// shifted shared-memory descriptors.
+//
+// Why: the per-tap kernel (conv_tc.cu) moves 9 activation boxes + 9 weight boxes per chunk through the
+// L2 -> SM path and is bound by it (measured ~45 B/clk/SM against 128 B/clk needed at full MMA rate).
+// Here an M subtile is 128 consecutive positions of the *padded* image held in shared memory
+//      position(h, w) = (h - h0 + 1) * PW + (w - w_box0),        PW = pixels per row of the box,
+// so the A operand of tap (dy, dx) is the same box read from row offset dy*PW + dx: a K-major SWIZZLE_128B
+// UMMA descriptor may start at any 128-byte row of a TMA-written tile (the swizzle is a function of the
+// absolute shared-memory address; tools/probe_umma_rowoff.cu checks this on the device).  Two layouts:
+//   G = 1 ("flat")  box columns -1 .. PW-2 with PW >= W + 1: the zero column that TMA fills right of the
+//                   image doubles as the left halo of the next row; positions with w >= W are computed
+//                   and dropped.  One box per chunk serves all 9 taps.
+//   G = 3 ("dx")    W % 8 == 0, PW = W, no dead positions: one box per horizontal shift dx (columns
+//                   dx .. dx+W-1, zero filled by TMA), each serving the three dy taps.
+// Two subtiles (each with its own box) share every weight stage, accumulators are double buffered in
+// TMEM, and the kernel is persistent: each CTA walks a contiguous range of (n-tile, subtile) units so
+// that the epilogue of one pair overlaps the main loop of the next.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.
+#include <algorithm>
+
+#include "conv_plan.h"
+#include "sm100.cuh"
+
+namespace td {
+
+using namespace sm100;
+
+struct HaloParams {
+    int B, H, W, cin, x_coff;
+    int cout, ldy, y_coff, y_dtype;
+    void* y;
+    const float* scale;
+    const float* shift;
+    int relu;
+    float* stats;            // train-mode BatchNorm partials [n_sub][2][cout] (+ zero row), or NULL
+    int G;                   // 1 or 3 (see above)
+    int PW, bh, BN, RH;
+    int tiles_h, n_sub, units;
+    int NA, NB;
+    uint32_t a_box_bytes, a_slot_bytes;
+};
+
+constexpr int HALO_THREADS = 192;
+constexpr int HALO_S = 2;     // subtiles sharing one weight stage
+
+struct UnitWalk {             // the same walk is replayed by the producer, the MMA issuer and the epilogue
+    int u, u_hi, n_sub;
+    __device__ bool next(int& nt, int& s0, int& cnt) {
+        if (u >= u_hi) return false;
+        nt = u / n_sub;
+        s0 = u - nt * n_sub;
+        cnt = min(HALO_S, min(u_hi - u, n_sub - s0));
+        u += cnt;
+        return true;
+    }
+};
+
+template <int N_TILE>
+__global__ void __launch_bounds__(HALO_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const HaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int B_STAGE = N_TILE * 128;
+    constexpr int ACC_COLS = HALO_S * N_TILE;              // TMEM columns of one accumulator buffer
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem_a + (size_t)p.NA * p.a_slot_bytes;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.NB * B_STAGE);
+    uint64_t* a_empty = a_full + p.NA;
+    uint64_t* b_full = a_empty + p.NA;
+    uint64_t* b_empty = b_full + p.NB;
+    uint64_t* acc_full = b_empty + p.NB;                   // [2]
+    uint64_t* acc_empty = acc_full + 2;                    // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2][2][N_TILE]
+    float* s_stats = s_affine + 4 * N_TILE;                // [4 warps][2][N_TILE]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int u_lo = (int)((int64_t)blockIdx.x * p.units / gridDim.x);
+    const int u_hi = (int)((int64_t)(blockIdx.x + 1) * p.units / gridDim.x);
+    const int kchunks = p.cin >> 6;
+    const int tpg = 9 / p.G;                               // taps per box group
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_x);
+        prefetch_tmap(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<2 * ACC_COLS>(tmem_ptr);
+    // The 1 KB tail of every A slot is never written by TMA: zero it once.  In the flat layout the position one
+    // past the box is the right-hand zero pad of the last row.
+    for (int s = 0; s < p.NA; ++s) {
+        uint32_t* tail = reinterpret_cast<uint32_t*>(smem_a + (size_t)(s + 1) * p.a_slot_bytes - 1024);
+        for (int i = threadIdx.x; i < 256; i += HALO_THREADS) tail[i] = 0u;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            UnitWalk wk{u_lo, u_hi, p.n_sub};
+            int nt, s0, cnt;
+            uint32_t a_it = 0, b_it = 0;
+            while (wk.next(nt, s0, cnt)) {
+                for (int cc = 0; cc < kchunks; ++cc) {
+                    for (int g = 0; g < p.G; ++g) {
+                        for (int j = 0; j < cnt; ++j) {
+                            const int sub = s0 + j;
+                            const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
+                            const uint32_t slot = a_it % (uint32_t)p.NA, ph = (a_it / (uint32_t)p.NA) & 1u;
+                            mbar_wait(&a_empty[slot], ph ^ 1u);
+                            mbar_arrive_expect_tx(&a_full[slot], p.a_box_bytes);
+                            tma_load_4d(smem_a + (size_t)slot * p.a_slot_bytes, &tmap_x, &a_full[slot], p.x_coff + cc * 64,
+                                        p.G == 3 ? g - 1 : -1, th * p.bh - 1, tn * p.BN);
+                            ++a_it;
+                        }
+                        for (int ti = 0; ti < tpg; ++ti) {
+                            const int tap = p.G == 3 ? ti * 3 + g : ti;
+                            const uint32_t bs = b_it % (uint32_t)p.NB, ph = (b_it / (uint32_t)p.NB) & 1u;
+                            mbar_wait(&b_empty[bs], ph ^ 1u);
+                            mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_STAGE);
+                            tma_load_2d(smem_b + (size_t)bs * B_STAGE, &tmap_w, &b_full[bs], tap * p.cin + cc * 64, nt * N_TILE);
+                            ++b_it;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 0, 0);
+            UnitWalk wk{u_lo, u_hi, p.n_sub};
+            int nt, s0, cnt;
+            uint32_t a_it = 0, b_it = 0, gi = 0;
+            while (wk.next(nt, s0, cnt)) {
+                const uint32_t ab = gi & 1u;
+                mbar_wait(&acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                bool first = true;
+                for (int cc = 0; cc < kchunks; ++cc) {
+                    for (int g = 0; g < p.G; ++g) {
+                        uint32_t a_addr[HALO_S];
+                        for (int j = 0; j < cnt; ++j) {
+                            const uint32_t it = a_it + j, slot = it % (uint32_t)p.NA;
+                            mbar_wait(&a_full[slot], (it / (uint32_t)p.NA) & 1u);
+                            a_addr[j] = smem_u32(smem_a + (size_t)slot * p.a_slot_bytes);
+                        }
+                        for (int ti = 0; ti < tpg; ++ti) {
+                            const int dyi = p.G == 3 ? ti : ti / 3;
+                            const int rowoff = dyi * p.PW + (p.G == 3 ? 0 : ti - dyi * 3);
+                            const uint32_t bs = b_it % (uint32_t)p.NB;
+                            mbar_wait(&b_full[bs], (b_it / (uint32_t)p.NB) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * B_STAGE);
+                            for (int j = 0; j < cnt; ++j) {
+                                const uint32_t d_tmem = tmem_base + ab * ACC_COLS + j * N_TILE;
+                                const uint32_t a0 = a_addr[j] + (uint32_t)rowoff * 128u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 16, 1024);
+                                    const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                                    umma_bf16(d_tmem, da, db, idesc, (!first || k > 0) ? 1u : 0u);
+                                }
+                            }
+                            first = false;
+                            umma_commit(&b_empty[bs]);
+                            ++b_it;
+                        }
+                        for (int j = 0; j < cnt; ++j) umma_commit(&a_empty[(a_it + j) % (uint32_t)p.NA]);
+                        a_it += cnt;
+                    }
+                }
+                umma_commit(&acc_full[ab]);
+                ++gi;
+            }
+        }
+    } else {
+        // ---- epilogue: TMEM -> registers -> global, overlapped with the next pair's main loop ---------
+        const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int r = q * 32 + lane;                 // position inside the subtile
+        const int img_rows = p.RH * p.PW;
+        const int n_rel = r / img_rows;
+        const int rem = r - n_rel * img_rows;
+        const int h_rel = rem / p.PW;
+        const int w_ = rem - h_rel * p.PW;
+        const int tid = threadIdx.x - 64;
+        UnitWalk wk{u_lo, u_hi, p.n_sub};
+        int nt, s0, cnt;
+        uint32_t gi = 0;
+        while (wk.next(nt, s0, cnt)) {
+            const uint32_t ab = gi & 1u;
+            float* sc_s = s_affine + ab * 2 * N_TILE;
+            float* sh_s = sc_s + N_TILE;
+            for (int c = tid; c < N_TILE; c += 128) {
+                sc_s[c] = p.scale ? __ldg(p.scale + nt * N_TILE + c) : 1.f;
+                sh_s[c] = p.shift ? __ldg(p.shift + nt * N_TILE + c) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&acc_full[ab], (gi >> 1) & 1u);
+            tc_fence_after();
+            for (int j = 0; j < cnt; ++j) {
+                const int sub = s0 + j;
+                const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
+                const int h_ = th * p.bh + h_rel, n_ = tn * p.BN + n_rel;
+                const bool valid = n_rel < p.BN && h_rel < p.bh && w_ < p.W && h_ < p.H && n_ < p.B;
+                const int64_t pix = ((int64_t)n_ * p.H + h_) * p.W + w_;
+#pragma unroll 1
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    uint32_t rr[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + j * N_TILE + (uint32_t)c0, rr);
+                    tmem_ld_wait();
+                    const int cbase = nt * N_TILE + c0;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + c0 + i);
+                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + c0 + i);
+                        v[i] = fmaf(__uint_as_float(rr[i]), sc.x, sh.x);
+                        v[i + 1] = fmaf(__uint_as_float(rr[i + 1]), sc.y, sh.y);
+                        v[i + 2] = fmaf(__uint_as_float(rr[i + 2]), sc.z, sh.z);
+                        v[i + 3] = fmaf(__uint_as_float(rr[i + 3]), sc.w, sh.w);
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (valid) {
+                        if (p.y_dtype == TD_BF16) {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) Vec<__nv_bfloat16>::pack(v + i).store(dst + i);
+                        } else {
+                            float* dst = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) Vec<float>::pack(v + i).store(dst + i);
+                        }
+                    }
+                    if (p.stats) {
+                        float sq[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = valid ? v[i] : 0.f;
+                            sq[i] = v[i] * v[i];
+                        }
+                        const float cs = warp_column_sums(v, lane);
+                        const float cq = warp_column_sums(sq, lane);
+                        s_stats[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
+                        s_stats[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
+                    }
+                }
+                if (p.stats) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    float* row = p.stats + (int64_t)sub * 2 * p.cout + nt * N_TILE;
+                    for (int c = tid; c < 2 * N_TILE; c += 128) {
+                        const int which = c / N_TILE, cc = c - which * N_TILE;
+                        const float t = (s_stats[(0 * 2 + which) * N_TILE + cc] + s_stats[(1 * 2 + which) * N_TILE + cc]) +
+                                        (s_stats[(2 * 2 + which) * N_TILE + cc] + s_stats[(3 * 2 + which) * N_TILE + cc]);
+                        row[which * p.cout + cc] = t;
+                    }
+                    if (sub == 0)       // td_bn_finalize reads a zero "shift" row after the partial rows
+                        for (int c = tid; c < N_TILE; c += 128) p.stats[(int64_t)p.n_sub * 2 * p.cout + nt * N_TILE + c] = 0.f;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[ab]);
+            ++gi;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * ACC_COLS>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: geometry, tensor maps, launch
+// ---------------------------------------------------------------------------------------------
+struct HaloGeom {
+    int G, PW, bh, BN;
+    double eff;        // useful positions / computed positions
+};
+
+// Best subtile (<= 128 positions) of an H x W feature map for each layout; eff = 0 when not applicable.
+static HaloGeom best_flat(int B, int H, int W) {
+    HaloGeom g{1, W + 1, 0, 1, 0.0};
+    const int PW = W + 1;
+    for (int bh = 1; bh <= H; ++bh) {               // bh rows of one image
+        if ((bh - 1) * PW + W - 1 >= 128) break;
+        const double eff = (double)H * W / ((double)ceil_div(H, bh) * 128.0);
+        if (eff > g.eff + 1e-9) { g.eff = eff; g.bh = bh; g.BN = 1; }
+    }
+    const int img = (H + 2) * PW;                   // BN whole images
+    for (int bn = 2; bn <= B; ++bn) {
+        if ((bn - 1) * img + (H - 1) * PW + W - 1 >= 128 || bn * (H + 2) > 256 || bn > 256) break;
+        const double eff = (double)B * H * W / ((double)ceil_div(B, bn) * 128.0);
+        if (eff > g.eff + 1e-9) { g.eff = eff; g.bh = H; g.BN = bn; }
+    }
+    return g;
+}
+static HaloGeom best_dx(int H, int W) {
+    HaloGeom g{3, W, 0, 1, 0.0};
+    if (W % 8 != 0 || W > 128) return g;
+    for (int bh = 1; bh <= H && bh * W <= 128; ++bh) {
+        const double eff = (double)H * W / ((double)ceil_div(H, bh) * 128.0);
+        if (eff > g.eff + 1e-9) { g.eff = eff; g.bh = bh; }
+    }
+    return g;
+}
+
+bool halo_plan_init(td_conv_plan* p, int* status) {
+    const td_conv3x3_desc& d = p->d;
+    *status = TD_OK;
+    if (const char* e = getenv("TD_TC_HALO")) if (atoi(e) == 0) return false;
+    if (d.width > 255 || d.height > 253) return false;
+    const int n_tile = d.cout % 128 == 0 ? 128 : 64;
+    // Relative cost per useful output: MMA cycles ~ 1/eff; L2 -> SM bytes ~ (A boxes + shared B) at ~45 B/clk.
+    HaloGeom cand[2] = {best_flat(d.batch, d.height, d.width), best_dx(d.height, d.width)};
+    int best = -1;
+    double best_cost = 0;
+    for (int i = 0; i < 2; ++i) {
+        const HaloGeom& g = cand[i];
+        if (g.eff < 0.6) continue;
+        const double mma_clk = 9.0 * 4.0 * n_tile / 2.0;                                   // per subtile and chunk
+        const double a_bytes = (double)g.G * g.PW * (g.bh + 2) * g.BN * 128.0;
+        const double b_bytes = 9.0 * n_tile * 128.0 / HALO_S;
+        const double cost = std::max(mma_clk, (a_bytes + b_bytes) / 45.0) / g.eff;
+        if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
+    }
+    if (const char* e = getenv("TD_TC_HALO_MODE")) {       // 1: flat, 3: dx (tests / sweeps)
+        const int want = atoi(e);
+        for (int i = 0; i < 2; ++i) if (cand[i].G == want && cand[i].eff > 0) best = i;
+    }
+    if (best < 0) return false;
+    const HaloGeom g = cand[best];
+    EncodeTiledFn encode = tc_get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled not available from the driver"); *status = TD_ERR_DRIVER; return true; }
+
+    p->halo = 1;
+    p->h_groups = g.G; p->h_pw = g.PW; p->h_bh = g.bh; p->h_bn = g.BN; p->h_rh = g.bh + 2;
+    p->tiles_w = 1;
+    p->tiles_h = (int)ceil_div(d.height, g.bh);
+    p->tiles_n = (int)ceil_div(d.batch, g.BN);
+    p->h_nsub = p->tiles_h * p->tiles_n;
+    p->block_n = n_tile;
+    p->n_tiles = d.cout / n_tile;
+    p->h_units = p->h_nsub * p->n_tiles;
+    p->split_k = 1;
+    const int box_bytes = g.PW * p->h_rh * g.BN * 128;
+    p->h_slot_bytes = (box_bytes + 1023) / 1024 * 1024 + 1024;
+    p->h_na = 4;
+    const int b_stage = n_tile * 128;
+    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 4) * 8 + 64 + (4 + 8) * n_tile * 4 + 1024;
+    int nb = (220 * 1024 - fixed) / b_stage;
+    if (nb > 8) nb = 8;
+    if (const char* e = getenv("TD_TC_HALO_NB")) { int v = atoi(e); if (v >= 2 && v <= nb) nb = v; }
+    if (nb < 3) { p->halo = 0; return false; }
+    p->h_nb = nb;
+    p->stages = nb;
+    p->smem_bytes = fixed + nb * (b_stage + 16);
+
+    {   // activations: (C, W, H, N), box (64, PW, bh + 2, BN); out-of-bounds elements are zero filled
+        cuuint64_t gdim[4] = {(cuuint64_t)d.ldx, (cuuint64_t)d.width, (cuuint64_t)d.height, (cuuint64_t)d.batch};
+        cuuint64_t gstr[3] = {(cuuint64_t)d.ldx * 2, (cuuint64_t)d.width * d.ldx * 2,
+                              (cuuint64_t)d.height * d.width * d.ldx * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)g.PW, (cuuint32_t)p->h_rh, (cuuint32_t)g.BN};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&p->tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d.x), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo activations) failed: %d", (int)r); *status = TD_ERR_DRIVER; return true; }
+    }
+    {   // weights: (K = 9*Cin, Cout)
+        cuuint64_t gdim[2] = {(cuuint64_t)9 * d.cin, (cuuint64_t)d.cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)9 * d.cin * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&p->tmap_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo weights) failed: %d", (int)r); *status = TD_ERR_DRIVER; return true; }
+    }
+    return true;
+}
+
+template <int N_TILE>
+static int launch_halo(const td_conv_plan* p, const HaloParams& prm, cudaStream_t s) {
+    static int configured_smem = 0;
+    if (p->smem_bytes > configured_smem) {
+        TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        configured_smem = p->smem_bytes;
+    }
+    const int grid = std::min(p->h_units, kNumSMs);
+    conv3x3_halo_kernel<N_TILE><<<grid, HALO_THREADS, p->smem_bytes, s>>>(p->tmap_x, p->tmap_w, prm);
+    return launch_status("conv3x3_halo");
+}
+
+int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
+    const td_conv3x3_desc& d = p->d;
+    HaloParams prm;
+    prm.B = d.batch; prm.H = d.height; prm.W = d.width; prm.cin = d.cin; prm.x_coff = d.x_coff;
+    prm.cout = d.cout; prm.ldy = d.ldy; prm.y_coff = d.y_coff; prm.y_dtype = d.y_dtype;
+    prm.y = d.y; prm.scale = d.scale; prm.shift = d.shift; prm.relu = d.relu; prm.stats = d.stats;
+    prm.G = p->h_groups; prm.PW = p->h_pw; prm.bh = p->h_bh; prm.BN = p->h_bn; prm.RH = p->h_rh;
+    prm.tiles_h = p->tiles_h; prm.n_sub = p->h_nsub; prm.units = p->h_units;
+    prm.NA = p->h_na; prm.NB = p->h_nb;
+    prm.a_box_bytes = (uint32_t)(p->h_pw * p->h_rh * p->h_bn * 128);
+    prm.a_slot_bytes = (uint32_t)p->h_slot_bytes;
+    return p->block_n == 128 ? launch_halo<128>(p, prm, s) : launch_halo<64>(p, prm, s);
+}
+
+}  // namespace td

@@ -17,6 +17,11 @@ struct td_conv_plan {
     int stages;
     int smem_bytes;
     int split_k;
+    // --- halo variant of the tcgen05 engine (conv_halo.cu): one shared-memory box serves several taps ---
+    int halo;               // 0: conv_tc.cu kernel, 1: conv_halo.cu kernel
+    int h_groups;           // 1: one box (w0 = -1) serves the 9 taps; 3: one box per dx
+    int h_pw, h_bh, h_bn, h_rh;   // box = (64 channels, pw, rh = bh + 2, bn images); pw = smem pixels per image row
+    int h_units, h_nsub, h_na, h_nb, h_slot_bytes;
 };
 
 struct td_wgrad_plan {
@@ -30,9 +35,15 @@ struct td_wgrad_plan {
 };
 
 namespace td {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tc_get_encode_fn();                                 // conv_tc.cu
 int wgrad_tc_splits(const td_wgrad_desc& d);                      // conv_wgrad_tc.cu
 int wgrad_tc_plan_init(td_wgrad_plan* p);                         // conv_wgrad_tc.cu
 int wgrad_tc_plan_run(const td_wgrad_plan* p, cudaStream_t s);    // conv_wgrad_tc.cu
 int tc_plan_init(td_conv_plan* p);                       // conv_tc.cu
 int tc_plan_run(const td_conv_plan* p, cudaStream_t s);   // conv_tc.cu
+bool halo_plan_init(td_conv_plan* p, int* status);       // conv_halo.cu; false: geometry not eligible
+int halo_plan_run(const td_conv_plan* p, cudaStream_t s); // conv_halo.cu
 }

@@ -39,21 +39,6 @@ struct TcParams {
 
 constexpr int TC_THREADS = 192;
 
-// v[j] of lane r = element (row r, column j) of a 32x32 tile; returns on lane L the sum over the 32 rows
-// of column L (31 shuffles: each step exchanges half of the live columns with the partner lane).
-__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int i = 0; i < s; ++i) {
-            const float send = up ? v[i] : v[i + s];
-            const float keep = up ? v[i + s] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    return v[0];
-}
 constexpr int TC_A_STAGE = 128 * 128;   // 128 rows x 128 bytes (64 bf16)
 
 template <int BLOCK_N>
@@ -275,10 +260,6 @@ conv_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t pixe
 // ---------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 EncodeTiledFn tc_get_encode_fn() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
@@ -317,6 +298,10 @@ int tc_plan_init(td_conv_plan* p) {
     if (((uintptr_t)d.x & 15) || ((uintptr_t)d.w & 15) || ((uintptr_t)d.y & 15)) {
         set_error("tc conv: tensors must be 16-byte aligned");
         return TD_ERR_ARG;
+    }
+    {   // layers whose feature map tiles well with a halo: one activation box per chunk instead of nine
+        int st = TD_OK;
+        if (halo_plan_init(p, &st)) return st;
     }
     EncodeTiledFn encode = tc_get_encode_fn();
     if (!encode) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TD_ERR_DRIVER; }
@@ -416,6 +401,7 @@ static int launch_tc(const td_conv_plan* p, const TcParams& prm, cudaStream_t s)
 }
 
 int tc_plan_run(const td_conv_plan* p, cudaStream_t s) {
+    if (p->halo) return halo_plan_run(p, s);
     const td_conv3x3_desc& d = p->d;
     TcParams prm;
     prm.B = d.batch; prm.H = d.height; prm.W = d.width; prm.cin = d.cin; prm.x_coff = d.x_coff;
