@@ -170,6 +170,8 @@ int td_conv3x3_stats_rows(const td_conv_plan* plan);
 void td_conv3x3_plan_destroy(td_conv_plan* plan);
 /* algorithmic FLOPs (2*MAC) of one run of the plan */
 double td_conv3x3_flops(const td_conv_plan* plan);
+/* tuning aid: per-CTA wait-cycle counters [148][8] of the last halo-kernel launch run with TD_TC_HALO_DBG=1 */
+int td_conv3x3_debug_counters(unsigned long long* host_out, int n);
 
 /* ------------------------------------------------------------------------------------------
  * NHWC glue kernels (HBM-bound)

@@ -81,6 +81,7 @@ _SIGS = {
     "td_conv3x3_stats_rows": (C.c_int, [_P]),
     "td_conv3x3_plan_destroy": (None, [_P]),
     "td_conv3x3_flops": (C.c_double, [_P]),
+    "td_conv3x3_debug_counters": (C.c_int, [_P, C.c_int]),
     "td_maxpool2_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_upcat_fwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, _P]),

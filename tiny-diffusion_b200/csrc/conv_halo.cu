@@ -17,7 +17,7 @@
 // Two subtiles (each with its own box) share every weight stage, accumulators are double buffered in
 // TMEM, and the kernel is persistent: each CTA walks a contiguous range of (n-tile, subtile) units so
 // that the epilogue of one pair overlaps the main loop of the next.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue.
+// Warp roles: 0 = TMA producer, 1-2 = MMA issuers (one per subtile), 3..6 = epilogue.
 #include <algorithm>
 
 #include "conv_plan.h"
@@ -40,12 +40,19 @@ struct HaloParams {
     int tiles_h, n_sub, units;
     int NA, NB;
     uint32_t a_box_bytes, a_slot_bytes;
+    int dbg;                 // TD_TC_HALO_DBG=1: per-CTA wait-cycle counters into g_halo_dbg
 };
 
-constexpr int HALO_THREADS = 192;
-constexpr int HALO_S = 2;     // subtiles sharing one weight stage
+// [CTA][8]: 0 total, 1 producer wait A slot, 2 producer wait B stage, 3 MMA wait A, 4 MMA wait B, 5 MMA wait
+// accumulator, 6 epilogue wait accumulator, 7 epilogue busy (clock64 cycles; tuning aid, read by td_conv3x3_debug_counters)
+__device__ unsigned long long g_halo_dbg[kNumSMs * 8];
+#define HALO_T0() const long long _t0 = p.dbg ? clock64() : 0
+#define HALO_ACC(var) do { if (p.dbg) var += clock64() - _t0; } while (0)
 
-struct UnitWalk {             // the same walk is replayed by the producer, the MMA issuer and the epilogue
+constexpr int HALO_THREADS = 224;   // warp 0 TMA producer, warps 1-2 MMA issuers (one per subtile), warps 3-6 epilogue
+constexpr int HALO_S = 2;           // subtiles sharing one weight stage
+
+struct UnitWalk {             // the same walk is replayed by the producer, the MMA issuers and the epilogue
     int u, u_hi, n_sub;
     __device__ bool next(int& nt, int& s0, int& cnt) {
         if (u >= u_hi) return false;
@@ -55,6 +62,12 @@ struct UnitWalk {             // the same walk is replayed by the producer, the 
         u += cnt;
         return true;
     }
+};
+
+struct Ring {                 // position in a ring of n mbarrier-guarded slots: index + phase parity, no divisions
+    uint32_t idx, phase, n;
+    __device__ void advance() { if (++idx == n) { idx = 0; phase ^= 1u; } }
+    __device__ void advance(uint32_t k) { idx += k; if (idx >= n) { idx -= n; phase ^= 1u; } }
 };
 
 template <int N_TILE>
@@ -72,8 +85,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint64_t* a_empty = a_full + p.NA;
     uint64_t* b_full = a_empty + p.NA;
     uint64_t* b_empty = b_full + p.NB;
-    uint64_t* acc_full = b_empty + p.NB;                   // [2]
-    uint64_t* acc_empty = acc_full + 2;                    // [2]
+    uint64_t* acc_full = b_empty + p.NB;                   // [2 buffers][2 subtiles]
+    uint64_t* acc_empty = acc_full + 4;                    // [2 buffers]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2][2][N_TILE]
     float* s_stats = s_affine + 4 * N_TILE;                // [4 warps][2][N_TILE]
@@ -90,16 +103,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < p.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < p.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], HALO_S); }
+        for (int s = 0; s < 4; ++s) mbar_init(&acc_full[s], 1);
+        for (int s = 0; s < 2; ++s) mbar_init(&acc_empty[s], 4);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<2 * ACC_COLS>(tmem_ptr);
-    // The 1 KB tail of every A slot is never written by TMA: zero it once.  In the flat layout the position one
+    if (warp == 3) tmem_alloc<2 * ACC_COLS>(tmem_ptr);
+    // The tail of every A slot (>= 1 KB past the box) is never written by TMA: zero it once.  In the flat layout the position one
     // past the box is the right-hand zero pad of the last row.
     for (int s = 0; s < p.NA; ++s) {
-        uint32_t* tail = reinterpret_cast<uint32_t*>(smem_a + (size_t)(s + 1) * p.a_slot_bytes - 1024);
-        for (int i = threadIdx.x; i < 256; i += HALO_THREADS) tail[i] = 0u;
+        uint32_t* tail = reinterpret_cast<uint32_t*>(smem_a + (size_t)s * p.a_slot_bytes + p.a_box_bytes);
+        for (int i = threadIdx.x; i < (int)((p.a_slot_bytes - p.a_box_bytes) >> 2); i += HALO_THREADS) tail[i] = 0u;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -111,78 +125,107 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (elect_one()) {
             UnitWalk wk{u_lo, u_hi, p.n_sub};
             int nt, s0, cnt;
-            uint32_t a_it = 0, b_it = 0;
+            Ring ra{0, 0, (uint32_t)p.NA}, rb{0, 0, (uint32_t)p.NB};
+            long long w0 = 0, w1 = 0;
+            const long long t_start = clock64();
             while (wk.next(nt, s0, cnt)) {
                 for (int cc = 0; cc < kchunks; ++cc) {
                     for (int g = 0; g < p.G; ++g) {
                         for (int j = 0; j < cnt; ++j) {
                             const int sub = s0 + j;
                             const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
-                            const uint32_t slot = a_it % (uint32_t)p.NA, ph = (a_it / (uint32_t)p.NA) & 1u;
-                            mbar_wait(&a_empty[slot], ph ^ 1u);
-                            mbar_arrive_expect_tx(&a_full[slot], p.a_box_bytes);
-                            tma_load_4d(smem_a + (size_t)slot * p.a_slot_bytes, &tmap_x, &a_full[slot], p.x_coff + cc * 64,
-                                        p.G == 3 ? g - 1 : -1, th * p.bh - 1, tn * p.BN);
-                            ++a_it;
+                            { HALO_T0(); mbar_wait(&a_empty[ra.idx], ra.phase ^ 1u); HALO_ACC(w0); }
+                            if (p.dbg & 2) {                  // timing experiment: no A traffic
+                                mbar_arrive(&a_full[ra.idx]);
+                            } else {
+                                mbar_arrive_expect_tx(&a_full[ra.idx], p.a_box_bytes);
+                                tma_load_4d(smem_a + (size_t)ra.idx * p.a_slot_bytes, &tmap_x, &a_full[ra.idx], p.x_coff + cc * 64,
+                                            p.G == 3 ? g - 1 : -1, th * p.bh - 1, tn * p.BN);
+                            }
+                            ra.advance();
                         }
                         for (int ti = 0; ti < tpg; ++ti) {
                             const int tap = p.G == 3 ? ti * 3 + g : ti;
-                            const uint32_t bs = b_it % (uint32_t)p.NB, ph = (b_it / (uint32_t)p.NB) & 1u;
-                            mbar_wait(&b_empty[bs], ph ^ 1u);
-                            mbar_arrive_expect_tx(&b_full[bs], (uint32_t)B_STAGE);
-                            tma_load_2d(smem_b + (size_t)bs * B_STAGE, &tmap_w, &b_full[bs], tap * p.cin + cc * 64, nt * N_TILE);
-                            ++b_it;
+                            { HALO_T0(); mbar_wait(&b_empty[rb.idx], rb.phase ^ 1u); HALO_ACC(w1); }
+                            if (p.dbg & 4) {                  // timing experiment: no B traffic
+                                mbar_arrive(&b_full[rb.idx]);
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[rb.idx], (uint32_t)B_STAGE);
+                                tma_load_2d(smem_b + (size_t)rb.idx * B_STAGE, &tmap_w, &b_full[rb.idx], tap * p.cin + cc * 64, nt * N_TILE);
+                            }
+                            rb.advance();
                         }
                     }
                 }
             }
+            if (p.dbg & 1) {
+                g_halo_dbg[blockIdx.x * 8 + 0] = clock64() - t_start;
+                g_halo_dbg[blockIdx.x * 8 + 1] = w0;
+                g_halo_dbg[blockIdx.x * 8 + 2] = w1;
+            }
         }
-    } else if (warp == 1) {
+    } else if (warp <= HALO_S) {
+        // ---- MMA issuers: warp 1 drives subtile 0, warp 2 subtile 1.  Two independent issue streams keep the tensor pipe
+        // busy while one of them sits in an mbarrier wait (a wait is ordered behind the thread's own queued MMAs and costs
+        // ~150 idle cycles per stage with a single issuer: tools/probe_umma_pipe.cu).
         if (elect_one()) {
+            const int j = warp - 1;
             constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 0, 0);
+            const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
+            const uint32_t a_base = smem_u32(smem_a) >> 4, b_base = smem_u32(smem_b) >> 4;
+            const uint32_t a_slot16 = p.a_slot_bytes >> 4;
             UnitWalk wk{u_lo, u_hi, p.n_sub};
             int nt, s0, cnt;
-            uint32_t a_it = 0, b_it = 0, gi = 0;
+            Ring ra{0, 0, (uint32_t)p.NA}, rb{0, 0, (uint32_t)p.NB};
+            uint32_t gi = 0;
+            long long w0 = 0, w1 = 0, w2 = 0;
             while (wk.next(nt, s0, cnt)) {
                 const uint32_t ab = gi & 1u;
-                mbar_wait(&acc_empty[ab], ((gi >> 1) & 1u) ^ 1u);
+                const bool active = j < cnt;
+                { HALO_T0(); mbar_wait(&acc_empty[ab], ((gi >> 1) & 1u) ^ 1u); HALO_ACC(w2); }
                 tc_fence_after();
-                bool first = true;
+                const uint32_t d_tmem = tmem_base + ab * ACC_COLS + j * N_TILE;
+                uint32_t accumulate = 0;
                 for (int cc = 0; cc < kchunks; ++cc) {
                     for (int g = 0; g < p.G; ++g) {
-                        uint32_t a_addr[HALO_S];
-                        for (int j = 0; j < cnt; ++j) {
-                            const uint32_t it = a_it + j, slot = it % (uint32_t)p.NA;
-                            mbar_wait(&a_full[slot], (it / (uint32_t)p.NA) & 1u);
-                            a_addr[j] = smem_u32(smem_a + (size_t)slot * p.a_slot_bytes);
+                        uint32_t a16 = 0, my_slot = 0;
+                        if (active) {
+                            Ring mine = ra;
+                            mine.advance((uint32_t)j);
+                            my_slot = mine.idx;
+                            { HALO_T0(); mbar_wait(&a_full[my_slot], mine.phase); HALO_ACC(w0); }
+                            a16 = a_base + my_slot * a_slot16;
                         }
+                        int dyi = 0, dxi = 0;
                         for (int ti = 0; ti < tpg; ++ti) {
-                            const int dyi = p.G == 3 ? ti : ti / 3;
-                            const int rowoff = dyi * p.PW + (p.G == 3 ? 0 : ti - dyi * 3);
-                            const uint32_t bs = b_it % (uint32_t)p.NB;
-                            mbar_wait(&b_full[bs], (b_it / (uint32_t)p.NB) & 1u);
-                            tc_fence_after();
-                            const uint32_t b_addr = smem_u32(smem_b + (size_t)bs * B_STAGE);
-                            for (int j = 0; j < cnt; ++j) {
-                                const uint32_t d_tmem = tmem_base + ab * ACC_COLS + j * N_TILE;
-                                const uint32_t a0 = a_addr[j] + (uint32_t)rowoff * 128u;
+                            const uint32_t rowoff = (uint32_t)(dyi * p.PW + (p.G == 3 ? 0 : dxi));      // 128-byte rows = 8 descriptor units
+                            if (p.G == 3 || ++dxi == 3) { dxi = 0; ++dyi; }
+                            const uint64_t da = desc0 + (uint64_t)(a16 + rowoff * 8u);
+                            const uint64_t db = desc0 + (uint64_t)(b_base + rb.idx * (uint32_t)(B_STAGE >> 4));
+                            { HALO_T0(); mbar_wait(&b_full[rb.idx], rb.phase); HALO_ACC(w1); }
+                            if (active) {
+                                tc_fence_after();
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 16, 1024);
-                                    const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                                    umma_bf16(d_tmem, da, db, idesc, (!first || k > 0) ? 1u : 0u);
-                                }
+                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate | (uint32_t)k);
+                                accumulate = 1;
+                                umma_commit(&b_empty[rb.idx]);
+                            } else {
+                                mbar_arrive(&b_empty[rb.idx]);      // keeps the stage's two-arrival count uniform
                             }
-                            first = false;
-                            umma_commit(&b_empty[bs]);
-                            ++b_it;
+                            rb.advance();
                         }
-                        for (int j = 0; j < cnt; ++j) umma_commit(&a_empty[(a_it + j) % (uint32_t)p.NA]);
-                        a_it += cnt;
+                        if (active) umma_commit(&a_empty[my_slot]);
+                        ra.advance((uint32_t)cnt);
                     }
                 }
-                umma_commit(&acc_full[ab]);
+                if (active) umma_commit(&acc_full[ab * 2 + j]);
+                else mbar_arrive(&acc_full[ab * 2 + j]);
                 ++gi;
+            }
+            if ((p.dbg & 1) && j == 0) {
+                g_halo_dbg[blockIdx.x * 8 + 3] = w0;
+                g_halo_dbg[blockIdx.x * 8 + 4] = w1;
+                g_halo_dbg[blockIdx.x * 8 + 5] = w2;
             }
         }
     } else {
@@ -194,10 +237,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int rem = r - n_rel * img_rows;
         const int h_rel = rem / p.PW;
         const int w_ = rem - h_rel * p.PW;
-        const int tid = threadIdx.x - 64;
+        const int tid = threadIdx.x - 96;
         UnitWalk wk{u_lo, u_hi, p.n_sub};
         int nt, s0, cnt;
         uint32_t gi = 0;
+        long long w0 = 0;
+        const long long t_start = clock64();
         while (wk.next(nt, s0, cnt)) {
             const uint32_t ab = gi & 1u;
             float* sc_s = s_affine + ab * 2 * N_TILE;
@@ -207,9 +252,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 sh_s[c] = p.shift ? __ldg(p.shift + nt * N_TILE + c) : 0.f;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&acc_full[ab], (gi >> 1) & 1u);
-            tc_fence_after();
-            for (int j = 0; j < cnt; ++j) {
+            for (int j = 0; j < HALO_S; ++j) {
+                { HALO_T0(); mbar_wait(&acc_full[ab * 2 + j], (gi >> 1) & 1u); HALO_ACC(w0); }
+                if (j >= cnt) continue;
+                tc_fence_after();
                 const int sub = s0 + j;
                 const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
                 const int h_ = th * p.bh + h_rel, n_ = tn * p.BN + n_rel;
@@ -278,10 +324,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
             ++gi;
         }
+        if ((p.dbg & 1) && tid == 0) {
+            g_halo_dbg[blockIdx.x * 8 + 6] = w0;
+            g_halo_dbg[blockIdx.x * 8 + 7] = clock64() - t_start - w0;
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 3) {
         tc_fence_after();
         tmem_dealloc<2 * ACC_COLS>(tmem_base);
     }
@@ -332,9 +382,9 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     HaloGeom cand[2] = {best_flat(d.batch, d.height, d.width), best_dx(d.height, d.width)};
     int best = -1;
     double best_cost = 0;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 1; ++i) {      // the dx layout moves 3x the activation bytes and measures slower than the per-tap kernel: opt-in only
         const HaloGeom& g = cand[i];
-        if (g.eff < 0.6) continue;
+        if (g.eff < 0.7) continue;
         const double mma_clk = 9.0 * 4.0 * n_tile / 2.0;                                   // per subtile and chunk
         const double a_bytes = (double)g.G * g.PW * (g.bh + 2) * g.BN * 128.0;
         const double b_bytes = 9.0 * n_tile * 128.0 / HALO_S;
@@ -362,9 +412,10 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->split_k = 1;
     const int box_bytes = g.PW * p->h_rh * g.BN * 128;
     p->h_slot_bytes = (box_bytes + 1023) / 1024 * 1024 + 1024;
-    p->h_na = 4;
+    p->h_na = g.G == 3 ? 6 : 4;        // dx layout: a box group lasts only three taps, keep three groups in flight
+    if (const char* e = getenv("TD_TC_HALO_NA")) { int v = atoi(e); if (v >= 2 && v <= 8) p->h_na = v; }
     const int b_stage = n_tile * 128;
-    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 4) * 8 + 64 + (4 + 8) * n_tile * 4 + 1024;
+    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (4 + 8) * n_tile * 4 + 1024;
     int nb = (220 * 1024 - fixed) / b_stage;
     if (nb > 8) nb = 8;
     if (const char* e = getenv("TD_TC_HALO_NB")) { int v = atoi(e); if (v >= 2 && v <= nb) nb = v; }
@@ -420,7 +471,19 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
     prm.NA = p->h_na; prm.NB = p->h_nb;
     prm.a_box_bytes = (uint32_t)(p->h_pw * p->h_rh * p->h_bn * 128);
     prm.a_slot_bytes = (uint32_t)p->h_slot_bytes;
+    {
+        const char* e = getenv("TD_TC_HALO_DBG");
+        prm.dbg = e ? atoi(e) : 0;
+    }
     return p->block_n == 128 ? launch_halo<128>(p, prm, s) : launch_halo<64>(p, prm, s);
 }
 
 }  // namespace td
+
+// Tuning aid: copies the wait-cycle counters of the last halo launch run with TD_TC_HALO_DBG=1 (synchronises).
+extern "C" int td_conv3x3_debug_counters(unsigned long long* host_out, int n) {
+    if (!host_out || n <= 0 || n > td::kNumSMs * 8) { td::set_error("td_conv3x3_debug_counters: bad arguments"); return TD_ERR_ARG; }
+    TD_CUDA(cudaDeviceSynchronize());
+    TD_CUDA(cudaMemcpyFromSymbol(host_out, td::g_halo_dbg, (size_t)n * sizeof(unsigned long long)));
+    return TD_OK;
+}
