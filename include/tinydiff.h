@@ -193,6 +193,12 @@ int td_upcat_fwd(const void* low, const void* skip, const float* temb, int ld_te
 int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int batch, int hi, int wi, int ho,
                            int wo, int c, void* stream);
 
+/* Network tail, eval path: F.interpolate(x, size=(ho,wo), bilinear, align_corners=True) followed by final_conv
+ * (3x3, c -> 1 channel, + bias), diffusion.py:157-160, in one pass over x (the resized c-channel tensor is never
+ * written).  x: NHWC [batch, hi, wi, ldx] channels [x_coff, x_coff + c); w_ohwi: fp32 [1][3][3][c]; y: fp32 NCHW. */
+int td_final_resize_conv(const void* x, int dtype, int ldx, int x_coff, int batch, int hi, int wi, int c,
+                         const float* w_ohwi, const float* bias, int ho, int wo, float* y_nchw, void* stream);
+
 /* Eval-mode BatchNorm folded into the conv epilogue (diffusion.py:34 in eval mode):
  *   scale = gamma / sqrt(running_var + eps) ; shift = beta + (conv_bias - running_mean) * scale */
 int td_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,

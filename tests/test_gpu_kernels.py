@@ -232,6 +232,20 @@ def test_conv_halo_channel_slices(dev):
     assert float((out[..., :128] - 7.0).abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.bfloat16, 3e-6)])
+@pytest.mark.parametrize("B,hi,ho,c", [(5, 32, 28, 64), (130, 32, 28, 64), (3, 28, 28, 64), (2, 16, 20, 32), (1, 9, 7, 8)])
+def test_final_resize_conv(dev, dtype, tol, B, hi, ho, c):
+    """interpolate(align_corners=True) + final_conv (C -> 1) fused; inputs rounded to the activation dtype on both sides."""
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(B + hi + c)
+    x = torch.randn(B, c, hi, hi, generator=g).to(dtype).float()
+    w = torch.randn(1, c, 3, 3, generator=g) / (9 * c) ** 0.5
+    b = torch.randn(1, generator=g)
+    want = F.conv2d(F.interpolate(x.double(), size=(ho, ho), mode="bilinear", align_corners=True), w.double(), b.double(), padding=1)
+    got = ops.final_resize_conv(nhwc(x).to(dtype).to(dev), ops.pack_conv_weight(w.to(dev)), b.to(dev), ho, ho)
+    assert rel(got, want) < tol
+
+
 def test_conv_direct_first_last(dev):
     from tinydiff import ops
     g = torch.Generator().manual_seed(9)

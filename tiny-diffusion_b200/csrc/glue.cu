@@ -1,6 +1,8 @@
 // NHWC glue kernels around the convolutions (all HBM/L2-bound, 16-byte vector accesses):
 // max-pool, decoder-input assembly (bilinear up-sample + skip/embedding add + resize + concat),
 // bilinear resize, the conditioning head and weight packing.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace td {
@@ -69,20 +71,6 @@ maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W,
 // ---------------------------------------------------------------------------------------------
 // out = [ up2x(low) | resize(skip + temb) ]
 // ---------------------------------------------------------------------------------------------
-// 4 taps with precombined weights: out = w00*f00 + w01*f01 + w10*f10 + w11*f11
-template <typename T>
-__device__ inline void bilerp4(const T* __restrict__ r0, const T* __restrict__ r1, int C, int i0, int i1, float w00,
-                               float w01, float w10, float w11, float* out) {
-    constexpr int V = Vec<T>::N;
-    float f00[V], f01[V], f10[V], f11[V];
-    Vec<T>::load(r0 + (int64_t)i0 * C).unpack(f00);
-    Vec<T>::load(r0 + (int64_t)i1 * C).unpack(f01);
-    Vec<T>::load(r1 + (int64_t)i0 * C).unpack(f10);
-    Vec<T>::load(r1 + (int64_t)i1 * C).unpack(f11);
-#pragma unroll
-    for (int k = 0; k < V; ++k) out[k] = fmaf(w00, f00[k], fmaf(w01, f01[k], fmaf(w10, f10[k], w11 * f11[k])));
-}
-
 constexpr int kMaxRowW = 64;      // widest output row the column tables are sized for
 
 // column interpolation table of one output row, built once per CTA
@@ -90,59 +78,99 @@ __device__ inline void build_col_table(Bil* tab, int in, int out) {
     for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < out; i += blockDim.x * blockDim.y) tab[i] = bil(i, in, out);
 }
 
+// One thread produces one 16-byte channel vector of EVERY pixel of an output row, walking the row left to right.
+// The two source columns it interpolates between stay in registers, already combined vertically, so a source
+// vector is loaded and converted once instead of once per output tap (the per-pixel 4-tap version of this
+// kernel was issue-bound: ~300 instructions per 16 bytes of output, ncu r01h).
+//   out[w] = l0(w) * v[i0(w)] + l1(w) * v[i1(w)] (+ add),     v[i] = lh0 * r0[i] + lh1 * r1[i]
+template <typename T>
+__device__ inline void resample_row(const T* __restrict__ r0, const T* __restrict__ r1, int cstride, float lh0, float lh1,
+                                    const Bil* __restrict__ col, int Wo, const float* add, T* __restrict__ dst, int dstride) {
+    constexpr int V = Vec<T>::N;
+    float va[V], vb[V];
+    int ia = -1, ib = -1;
+    auto fetch = [&](int i, float* v) {
+        float a[V], b[V];
+        Vec<T>::load(r0 + (int64_t)i * cstride).unpack(a);
+        Vec<T>::load(r1 + (int64_t)i * cstride).unpack(b);
+#pragma unroll
+        for (int k = 0; k < V; ++k) v[k] = lh0 * a[k] + lh1 * b[k];
+    };
+    for (int w = 0; w < Wo; ++w) {
+        const Bil bw = col[w];
+        if (bw.i0 != ia) {
+            if (bw.i0 == ib) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) va[k] = vb[k];
+            } else {
+                fetch(bw.i0, va);
+            }
+            ia = bw.i0;
+        }
+        if (bw.i1 != ib) {
+            if (bw.i1 == ia) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) vb[k] = va[k];
+            } else {
+                fetch(bw.i1, vb);
+            }
+            ib = bw.i1;
+        }
+        float r[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) r[k] = bw.l0 * va[k] + bw.l1 * vb[k];
+        if (add) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) r[k] += add[k];
+        }
+        Vec<T>::pack(r).store(dst + (int64_t)w * dstride);
+    }
+}
+
+// grid: (row groups, channel-vector groups, 2 halves); block: (vectors, rows).  blockIdx.z = 0 writes the
+// up-sampled `low` channels, 1 the resized skip (+ embedding) channels; the threads of a warp share the column
+// table of their half, so the register-cache branches above are warp-uniform.
 template <typename T>
 __global__ void __launch_bounds__(256)
 upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
              int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
     constexpr int V = Vec<T>::N;
-    __shared__ Bil col_low[kMaxRowW], col_skip[kMaxRowW];
+    __shared__ Bil col[kMaxRowW];
     const int Ct = Cu + Cs;
-    const int cv = Ct / V;
-    const int Hl = Ho / 2, Wl = Wo / 2;
-    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
-    T* orow = out + ((int64_t)b * Ho + ho) * Wo * Ct;
-    const bool same = (Hs == Ho && Ws == Wo);
-    build_col_table(col_low, Wl, Wo);
-    if (!same) build_col_table(col_skip, Ws, Wo);
+    const bool skip_half = blockIdx.z == 1;
+    const int Ch = skip_half ? Cs : Cu;                      // channels of this half
+    const int Hin = skip_half ? Hs : Ho / 2, Win = skip_half ? Ws : Wo / 2;
+    const T* src = skip_half ? skip : low;
+    const bool same = skip_half && Hs == Ho && Ws == Wo;
+    if (!same) build_col_table(col, Win, Wo);
     __syncthreads();
-    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
-        const int c = cvi * V;
-        if (c < Cu) {
-            const Bil bh = bil(ho, Hl, Ho);
-            const T* r0 = low + (((int64_t)b * Hl + bh.i0) * Wl) * Cu + c;
-            const T* r1 = low + (((int64_t)b * Hl + bh.i1) * Wl) * Cu + c;
-#pragma unroll 2
-            for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
-                const Bil bw = col_low[wo];
-                float r[V];
-                bilerp4<T>(r0, r1, Cu, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
-                Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
-            }
-        } else {
-            const int cs = c - Cu;
-            // the embedding is constant over space and the bilinear weights sum to one, so
-            // resize(skip + t) == resize(skip) + t
-            float te[V];
+    const int cvi = blockIdx.y * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;   // (b, ho) flattened
+    if (cvi * V >= Ch || row >= B * Ho) return;
+    const int c = cvi * V;
+    const int b = row / Ho, ho = row - b * Ho;
+    T* orow = out + (int64_t)row * Wo * Ct + (skip_half ? Cu : 0) + c;
+    float te[V];
+    if (skip_half) {
+        // the embedding is constant over space and the bilinear weights sum to one: resize(skip + t) == resize(skip) + t
 #pragma unroll
-            for (int k = 0; k < V; ++k) te[k] = temb[(int64_t)b * ld_temb + temb_off + cs + k];
-            const Bil bh = bil(ho, Hs, Ho);
-            const T* r0 = skip + (((int64_t)b * Hs + (same ? ho : bh.i0)) * Ws) * Cs + cs;
-            const T* r1 = skip + (((int64_t)b * Hs + (same ? ho : bh.i1)) * Ws) * Cs + cs;
-#pragma unroll 2
-            for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
-                float r[V];
-                if (same) {
-                    Vec<T>::load(r0 + (int64_t)wo * Cs).unpack(r);
-                } else {
-                    const Bil bw = col_skip[wo];
-                    bilerp4<T>(r0, r1, Cs, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
-                }
-#pragma unroll
-                for (int k = 0; k < V; ++k) r[k] += te[k];
-                Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + c);
-            }
-        }
+        for (int k = 0; k < V; ++k) te[k] = temb[(int64_t)b * ld_temb + temb_off + c + k];
     }
+    if (same) {
+        const T* r0 = src + ((int64_t)row * Ws) * Cs + c;
+        for (int w = 0; w < Wo; ++w) {
+            float r[V];
+            Vec<T>::load(r0 + (int64_t)w * Cs).unpack(r);
+#pragma unroll
+            for (int k = 0; k < V; ++k) r[k] += te[k];
+            Vec<T>::pack(r).store(orow + (int64_t)w * Ct);
+        }
+        return;
+    }
+    const Bil bh = bil(ho, Hin, Ho);
+    const T* r0 = src + (((int64_t)b * Hin + bh.i0) * Win) * Ch + c;
+    const T* r1 = src + (((int64_t)b * Hin + bh.i1) * Win) * Ch + c;
+    resample_row<T>(r0, r1, Ch, bh.l0, bh.l1, col, Wo, skip_half ? te : nullptr, orow, Ct);
 }
 
 template <typename T>
@@ -150,24 +178,24 @@ __global__ void __launch_bounds__(256)
 resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
-    const int cv = C / V;
-    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
-    const Bil bh = bil(ho, Hi, Ho);
-    T* yrow = y + ((int64_t)b * Ho + ho) * Wo * C;
     build_col_table(col, Wi, Wo);
     __syncthreads();
-    for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
-        const int c = cvi * V;
-        const T* r0 = x + (((int64_t)b * Hi + bh.i0) * Wi) * C + c;
-        const T* r1 = x + (((int64_t)b * Hi + bh.i1) * Wi) * C + c;
-#pragma unroll 2
-        for (int wo = threadIdx.y; wo < Wo; wo += blockDim.y) {
-            const Bil bw = col[wo];
-            float r[V];
-            bilerp4<T>(r0, r1, C, bw.i0, bw.i1, bh.l0 * bw.l0, bh.l0 * bw.l1, bh.l1 * bw.l0, bh.l1 * bw.l1, r);
-            Vec<T>::pack(r).store(yrow + (int64_t)wo * C + c);
-        }
-    }
+    const int cvi = blockIdx.y * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (cvi * V >= C || row >= B * Ho) return;
+    const int c = cvi * V;
+    const int b = row / Ho, ho = row - b * Ho;
+    const Bil bh = bil(ho, Hi, Ho);
+    const T* r0 = x + (((int64_t)b * Hi + bh.i0) * Wi) * C + c;
+    const T* r1 = x + (((int64_t)b * Hi + bh.i1) * Wi) * C + c;
+    resample_row<T>(r0, r1, C, bh.l0, bh.l1, col, Wo, nullptr, y + (int64_t)row * Wo * C + c, C);
+}
+
+// block (vectors of one half, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
+static inline dim3 walk_block(int cv) {
+    int bx = 1;
+    while (bx < cv && bx < 32) bx <<= 1;
+    return dim3((unsigned)bx, (unsigned)(256 / bx), 1);
 }
 
 // OIHW fp32 -> OHWI (fp32 or bf16)
@@ -234,12 +262,18 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
-        upcat_kernel<__nv_bfloat16><<<batch * ho, row_block((cu + cs) / 8), 0, s>>>(
+        const int cvh = std::max(cu, cs) / 8;
+        const dim3 blk = walk_block(cvh);
+        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(cvh, blk.x), 2);
+        upcat_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
             (const __nv_bfloat16*)low, (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out,
             batch, ho, wo, cu, hs, ws, cs);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(cu % 4 == 0 && cs % 4 == 0, "td_upcat_fwd: channel counts must be multiples of 4");
-        upcat_kernel<float><<<batch * ho, row_block((cu + cs) / 4), 0, s>>>(
+        const int cvh = std::max(cu, cs) / 4;
+        const dim3 blk = walk_block(cvh);
+        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(cvh, blk.x), 2);
+        upcat_kernel<float><<<grd, blk, 0, s>>>(
             (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs);
     } else {
         TD_CHECK_ARG(false, "td_upcat_fwd: unknown dtype %d", dtype);
@@ -254,11 +288,15 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");
-        resize_kernel<__nv_bfloat16><<<batch * ho, row_block(c / 8), 0, s>>>(
+        const dim3 blk = walk_block(c / 8);
+        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(c / 8, blk.x), 1);
+        resize_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 4 for fp32");
-        resize_kernel<float><<<batch * ho, row_block(c / 4), 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
+        const dim3 blk = walk_block(c / 4);
+        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(c / 4, blk.x), 1);
+        resize_kernel<float><<<grd, blk, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
     } else {
         TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
     }

@@ -196,6 +196,16 @@ def pack_conv_weight_dgrad(w_oihw, dtype=torch.float32):
     return out
 
 
+def final_resize_conv(x, w_ohwi, bias, ho, wo):
+    """x: NHWC (bf16/fp32); w_ohwi: fp32 [1,3,3,C]; returns fp32 NCHW [B,1,ho,wo] = final_conv(interpolate(x, (ho,wo)))."""
+    _dev(x)
+    B, hi, wi, c = x.shape
+    out = torch.empty(B, 1, ho, wo, device=x.device, dtype=torch.float32)
+    L.check(L.load().td_final_resize_conv(x.data_ptr(), L.dtype_code(x.dtype), c, 0, B, hi, wi, c, w_ohwi.data_ptr(),
+                                          L.ptr(bias), ho, wo, out.data_ptr(), L.stream_ptr()), "td_final_resize_conv")
+    return out
+
+
 def conv3x3_wgrad(x, dy, engine=L.CONV_SIMT, x_nchw=False, dy_nchw=False, x_coff=0, cin=None):
     """x: conv input NHWC (or NCHW fp32), dy: grad of the conv output NHWC (or NCHW).  Returns OIHW fp32."""
     _dev(x)

@@ -122,7 +122,7 @@ class UNetEngine:
             "cat2": buf(u2, d3 + c2), "dec2a": buf(u2, d2), "d2": buf(u2, d2),
             "cat1": buf(u1, d2 + c1), "dec1a": buf(u1, d1), "d1": buf(u1, d1),
         }
-        if cfg.final_resize:
+        if cfg.final_resize and cfg.in_ch != 1:
             self.bufs["d1r"] = buf(s0, d1)
         self.x_in = torch.zeros(B, cfg.in_ch, s0, s0, device=device, dtype=torch.float32)
         self.eps = torch.zeros(B, cfg.in_ch, s0, s0, device=device, dtype=torch.float32)
@@ -146,6 +146,7 @@ class UNetEngine:
             (c1, s0), (c2, s1), (c3, s2), (cfg.bott, s3), (d3, u3), (d2, u2), (d1, u1))], device)
         self._build_plans()
         self._weights_version = None
+        self._side = None
 
     # ------------------------------------------------------------------ parameters
     def _conv_modules(self):
@@ -279,14 +280,22 @@ class UNetEngine:
         add_upcat("d2", "e1", "cat1", S["u1"], d2, S["s0"], c1, 0)
         add_conv("dec1.0", bf["cat1"], d2 + c1, bf["dec1a"], d1, True)
         add_conv("dec1.3", bf["dec1a"], d1, bf["d1"], d1, True)
-        last = "d1"
-        if cfg.final_resize:
-            sp, dp = bf["d1"].data_ptr(), bf["d1r"].data_ptr()
+        if cfg.final_resize and cfg.in_ch == 1:
+            # resize + final_conv in one pass over d1 (both are linear: the 64-channel resized tensor never exists)
+            sp, ep = bf["d1"].data_ptr(), self.eps.data_ptr()
+            wp, bp = self.packed["final_conv"].data_ptr(), self.shift["final_conv"].data_ptr()
             u1, s0, adt = S["u1"], S["s0"], self.adt
-            ops.append(("resize:d1r", lambda st: L.check(
-                lib.td_resize_bilinear_fwd(sp, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_fwd")))
-            last = "d1r"
-        add_conv("final_conv", bf[last], d1, self.eps, cfg.in_ch, False, y_nchw=True)
+            ops.append(("final_resize_conv", lambda st: L.check(
+                lib.td_final_resize_conv(sp, adt, d1, 0, B, u1, u1, d1, wp, bp, s0, s0, ep, st), "td_final_resize_conv")))
+        else:
+            last = "d1"
+            if cfg.final_resize:
+                sp, dp = bf["d1"].data_ptr(), bf["d1r"].data_ptr()
+                u1, s0, adt = S["u1"], S["s0"], self.adt
+                ops.append(("resize:d1r", lambda st: L.check(
+                    lib.td_resize_bilinear_fwd(sp, dp, adt, B, u1, u1, s0, s0, d1, st), "td_resize_bilinear_fwd")))
+                last = "d1r"
+            add_conv("final_conv", bf[last], d1, self.eps, cfg.in_ch, False, y_nchw=True)
         self.ops = ops
         self.use_t_dev = False
 
@@ -359,10 +368,27 @@ class UNetEngine:
     # ------------------------------------------------------------------ execution
     def launch(self) -> None:
         """Enqueue one eval forward on the current stream (graph-capturable): reads x_in / t_in (or
-        t_dev) / y_in / text_in, writes eps."""
+        t_dev) / y_in / text_in, writes eps.  The conditioning head only feeds the decoder (first use:
+        the first upcat), so it runs on a forked stream beside the encoder convolutions and joins
+        there -- in a captured graph that is a parallel branch, off the critical path."""
+        main = torch.cuda.current_stream()
         st = L.stream_ptr()
-        for _, fn in self.ops:
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self._ev_fork.record(main)
+        self._side.wait_event(self._ev_fork)
+        with torch.cuda.stream(self._side):
+            self.ops[0][1](L.stream_ptr())
+            self._ev_join.record(self._side)
+        joined = False
+        for name, fn in self.ops[1:]:
+            if not joined and name.startswith("upcat"):
+                main.wait_event(self._ev_join)
+                joined = True
             fn(st)
+        if not joined:
+            main.wait_event(self._ev_join)
 
     def num_launches(self) -> int:
         return len(self.ops)
