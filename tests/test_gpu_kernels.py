@@ -202,10 +202,10 @@ def test_conv_tc_bf16(dev, B, H, cin, cout):
 # The halo kernel (conv_halo.cu): both shared-memory layouts forced on every map size they accept, the
 # per-tap kernel forced on the same shapes, and batches large enough that each persistent CTA walks
 # several (n-tile, subtile) units with paired and unpaired subtiles.
-@pytest.mark.parametrize("mode", ["1", "3", "off"])
+@pytest.mark.parametrize("mode", ["1", "2", "3", "off"])
 @pytest.mark.parametrize("B,H,cin,cout", [(5, 28, 64, 128), (3, 14, 128, 256), (7, 7, 256, 128), (2, 16, 128, 128),
                                           (3, 32, 64, 64), (2, 8, 64, 64), (9, 4, 64, 128), (66, 28, 64, 128),
-                                          (150, 16, 64, 64), (33, 20, 64, 64)])
+                                          (150, 16, 64, 64), (33, 20, 64, 64), (5, 24, 64, 64), (40, 32, 128, 64)])
 def test_conv_halo_layouts(dev, monkeypatch, mode, B, H, cin, cout):
     if mode == "off":
         monkeypatch.setenv("TD_TC_HALO", "0")

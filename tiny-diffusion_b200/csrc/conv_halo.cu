@@ -13,7 +13,11 @@
 //                   image doubles as the left halo of the next row; positions with w >= W are computed
 //                   and dropped.  One box per chunk serves all 9 taps.
 //   G = 3 ("dx")    W % 8 == 0, PW = W, no dead positions: one box per horizontal shift dx (columns
-//                   dx .. dx+W-1, zero filled by TMA), each serving the three dy taps.
+//                   dx .. dx+W-1, zero filled by TMA), each serving the three dy taps.  (opt-in: 3x the A bytes)
+//   strip           W % 8 == 0: a subtile is a strip of 8 columns x 16 rows read out of ONE box of 10 columns x 18
+//                   rows (PW = 10).  Each 8-row group of the A operand is one image row of the strip, so the groups
+//                   are PW*128 bytes apart: the descriptor's stride byte offset is 1280 instead of 1024
+//                   (tools/probe_umma_layouts.cu).  No dead positions and one box per chunk.
 // Two subtiles (each with its own box) share every weight stage, accumulators are double buffered in
 // TMEM, and the kernel is persistent: each CTA walks a contiguous range of (n-tile, subtile) units so
 // that the epilogue of one pair overlaps the main loop of the next.
@@ -37,7 +41,10 @@ struct HaloParams {
     float* stats;            // train-mode BatchNorm partials [n_sub][2][cout] (+ zero row), or NULL
     int G;                   // 1 or 3 (see above)
     int PW, bh, BN, RH;
-    int tiles_h, n_sub, units;
+    int bw;                  // image columns per subtile (W for flat / dx, 8 for strip)
+    int ew;                  // positions per subtile row in the M index (PW for flat, W for dx, 8 for strip)
+    int a_sbo;               // bytes between the 8-row groups of the A operand (1024, or PW*128 for strip)
+    int tiles_w, tiles_h, n_sub, units;
     int NA, NB;
     uint32_t a_box_bytes, a_slot_bytes;
     int dbg;                 // TD_TC_HALO_DBG=1: per-CTA wait-cycle counters into g_halo_dbg
@@ -133,14 +140,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     for (int g = 0; g < p.G; ++g) {
                         for (int j = 0; j < cnt; ++j) {
                             const int sub = s0 + j;
-                            const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
+                            const int tw = sub % p.tiles_w, th = (sub / p.tiles_w) % p.tiles_h, tn = sub / (p.tiles_w * p.tiles_h);
                             { HALO_T0(); mbar_wait(&a_empty[ra.idx], ra.phase ^ 1u); HALO_ACC(w0); }
                             if (p.dbg & 2) {                  // timing experiment: no A traffic
                                 mbar_arrive(&a_full[ra.idx]);
                             } else {
                                 mbar_arrive_expect_tx(&a_full[ra.idx], p.a_box_bytes);
                                 tma_load_4d(smem_a + (size_t)ra.idx * p.a_slot_bytes, &tmap_x, &a_full[ra.idx], p.x_coff + cc * 64,
-                                            p.G == 3 ? g - 1 : -1, th * p.bh - 1, tn * p.BN);
+                                            tw * p.bw + (p.G == 3 ? g - 1 : -1), th * p.bh - 1, tn * p.BN);
                             }
                             ra.advance();
                         }
@@ -172,6 +179,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const int j = warp - 1;
             constexpr uint32_t idesc = make_idesc_bf16(128, N_TILE, 0, 0);
             const uint64_t desc0 = make_smem_desc_sw128(0, 16, 1024);
+            const uint64_t desc0a = make_smem_desc_sw128(0, 16, (uint32_t)p.a_sbo);
             const uint32_t a_base = smem_u32(smem_a) >> 4, b_base = smem_u32(smem_b) >> 4;
             const uint32_t a_slot16 = p.a_slot_bytes >> 4;
             UnitWalk wk{u_lo, u_hi, p.n_sub};
@@ -200,7 +208,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         for (int ti = 0; ti < tpg; ++ti) {
                             const uint32_t rowoff = (uint32_t)(dyi * p.PW + (p.G == 3 ? 0 : dxi));      // 128-byte rows = 8 descriptor units
                             if (p.G == 3 || ++dxi == 3) { dxi = 0; ++dyi; }
-                            const uint64_t da = desc0 + (uint64_t)(a16 + rowoff * 8u);
+                            const uint64_t da = desc0a + (uint64_t)(a16 + rowoff * 8u);
                             const uint64_t db = desc0 + (uint64_t)(b_base + rb.idx * (uint32_t)(B_STAGE >> 4));
                             { HALO_T0(); mbar_wait(&b_full[rb.idx], rb.phase); HALO_ACC(w1); }
                             if (active) {
@@ -232,11 +240,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         // ---- epilogue: TMEM -> registers -> global, overlapped with the next pair's main loop ---------
         const int q = warp & 3;                      // TMEM lane quadrant this warp may access
         const int r = q * 32 + lane;                 // position inside the subtile
-        const int img_rows = p.RH * p.PW;
-        const int n_rel = r / img_rows;
+        const int img_rows = p.RH * p.PW;             // flat layout with whole images: positions per image (others: >= 128)
+        const int n_rel = p.BN > 1 ? r / img_rows : 0;
         const int rem = r - n_rel * img_rows;
-        const int h_rel = rem / p.PW;
-        const int w_ = rem - h_rel * p.PW;
+        const int h_rel = rem / p.ew;
+        const int w_rel = rem - h_rel * p.ew;
         const int tid = threadIdx.x - 96;
         UnitWalk wk{u_lo, u_hi, p.n_sub};
         int nt, s0, cnt;
@@ -257,9 +265,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 if (j >= cnt) continue;
                 tc_fence_after();
                 const int sub = s0 + j;
-                const int th = sub % p.tiles_h, tn = sub / p.tiles_h;
-                const int h_ = th * p.bh + h_rel, n_ = tn * p.BN + n_rel;
-                const bool valid = n_rel < p.BN && h_rel < p.bh && w_ < p.W && h_ < p.H && n_ < p.B;
+                const int tw = sub % p.tiles_w, th = (sub / p.tiles_w) % p.tiles_h, tn = sub / (p.tiles_w * p.tiles_h);
+                const int w_ = tw * p.bw + w_rel, h_ = th * p.bh + h_rel, n_ = tn * p.BN + n_rel;
+                const bool valid = n_rel < p.BN && h_rel < p.bh && w_rel < p.bw && w_ < p.W && h_ < p.H && n_ < p.B;
                 const int64_t pix = ((int64_t)n_ * p.H + h_) * p.W + w_;
 #pragma unroll 1
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
@@ -343,11 +351,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 struct HaloGeom {
     int G, PW, bh, BN;
     double eff;        // useful positions / computed positions
+    int strip;         // 1: 8-column strips (PW = 10, 16 rows per subtile)
 };
 
 // Best subtile (<= 128 positions) of an H x W feature map for each layout; eff = 0 when not applicable.
 static HaloGeom best_flat(int B, int H, int W) {
-    HaloGeom g{1, W + 1, 0, 1, 0.0};
+    HaloGeom g{1, W + 1, 0, 1, 0.0, 0};
     const int PW = W + 1;
     for (int bh = 1; bh <= H; ++bh) {               // bh rows of one image
         if ((bh - 1) * PW + W - 1 >= 128) break;
@@ -363,12 +372,19 @@ static HaloGeom best_flat(int B, int H, int W) {
     return g;
 }
 static HaloGeom best_dx(int H, int W) {
-    HaloGeom g{3, W, 0, 1, 0.0};
+    HaloGeom g{3, W, 0, 1, 0.0, 0};
     if (W % 8 != 0 || W > 128) return g;
     for (int bh = 1; bh <= H && bh * W <= 128; ++bh) {
         const double eff = (double)H * W / ((double)ceil_div(H, bh) * 128.0);
         if (eff > g.eff + 1e-9) { g.eff = eff; g.bh = bh; }
     }
+    return g;
+}
+
+static HaloGeom best_strip(int H, int W) {
+    HaloGeom g{1, 10, 16, 1, 0.0, 1};
+    if (W % 8 != 0) return g;
+    g.eff = (double)H / ((double)ceil_div(H, 16) * 16.0);
     return g;
 }
 
@@ -379,10 +395,10 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     if (d.width > 255 || d.height > 253) return false;
     const int n_tile = d.cout % 128 == 0 ? 128 : 64;
     // Relative cost per useful output: MMA cycles ~ 1/eff; L2 -> SM bytes ~ (A boxes + shared B) at ~45 B/clk.
-    HaloGeom cand[2] = {best_flat(d.batch, d.height, d.width), best_dx(d.height, d.width)};
+    HaloGeom cand[3] = {best_flat(d.batch, d.height, d.width), best_strip(d.height, d.width), best_dx(d.height, d.width)};
     int best = -1;
     double best_cost = 0;
-    for (int i = 0; i < 1; ++i) {      // the dx layout moves 3x the activation bytes and measures slower than the per-tap kernel: opt-in only
+    for (int i = 0; i < 2; ++i) {      // the dx layout moves 3x the activation bytes and measures slower than the per-tap kernel: opt-in only
         const HaloGeom& g = cand[i];
         if (g.eff < 0.7) continue;
         const double mma_clk = 9.0 * 4.0 * n_tile / 2.0;                                   // per subtile and chunk
@@ -391,9 +407,12 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
         const double cost = std::max(mma_clk, (a_bytes + b_bytes) / 45.0) / g.eff;
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
     }
-    if (const char* e = getenv("TD_TC_HALO_MODE")) {       // 1: flat, 3: dx (tests / sweeps)
+    if (const char* e = getenv("TD_TC_HALO_MODE")) {       // 1: flat, 2: strip, 3: dx (tests / sweeps)
         const int want = atoi(e);
-        for (int i = 0; i < 2; ++i) if (cand[i].G == want && cand[i].eff > 0) best = i;
+        for (int i = 0; i < 3; ++i) {
+            const int kind = cand[i].G == 3 ? 3 : (cand[i].strip ? 2 : 1);
+            if (kind == want && cand[i].eff > 0) best = i;
+        }
     }
     if (best < 0) return false;
     const HaloGeom g = cand[best];
@@ -402,10 +421,11 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
 
     p->halo = 1;
     p->h_groups = g.G; p->h_pw = g.PW; p->h_bh = g.bh; p->h_bn = g.BN; p->h_rh = g.bh + 2;
-    p->tiles_w = 1;
+    p->h_strip = g.strip;
+    p->tiles_w = g.strip ? d.width / 8 : 1;
     p->tiles_h = (int)ceil_div(d.height, g.bh);
     p->tiles_n = (int)ceil_div(d.batch, g.BN);
-    p->h_nsub = p->tiles_h * p->tiles_n;
+    p->h_nsub = p->tiles_w * p->tiles_h * p->tiles_n;
     p->block_n = n_tile;
     p->n_tiles = d.cout / n_tile;
     p->h_units = p->h_nsub * p->n_tiles;
@@ -467,7 +487,10 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
     prm.cout = d.cout; prm.ldy = d.ldy; prm.y_coff = d.y_coff; prm.y_dtype = d.y_dtype;
     prm.y = d.y; prm.scale = d.scale; prm.shift = d.shift; prm.relu = d.relu; prm.stats = d.stats;
     prm.G = p->h_groups; prm.PW = p->h_pw; prm.bh = p->h_bh; prm.BN = p->h_bn; prm.RH = p->h_rh;
-    prm.tiles_h = p->tiles_h; prm.n_sub = p->h_nsub; prm.units = p->h_units;
+    prm.tiles_w = p->tiles_w; prm.tiles_h = p->tiles_h; prm.n_sub = p->h_nsub; prm.units = p->h_units;
+    prm.bw = p->h_strip ? 8 : d.width;
+    prm.ew = p->h_strip ? 8 : p->h_pw;
+    prm.a_sbo = p->h_strip ? p->h_pw * 128 : 1024;
     prm.NA = p->h_na; prm.NB = p->h_nb;
     prm.a_box_bytes = (uint32_t)(p->h_pw * p->h_rh * p->h_bn * 128);
     prm.a_slot_bytes = (uint32_t)p->h_slot_bytes;

@@ -56,7 +56,7 @@ shapes = [(28, 64, 128), (28, 128, 128), (14, 128, 256), (14, 256, 256), (7, 256
           (16, 512, 128), (16, 128, 128), (32, 256, 64), (32, 64, 64)]
 B = int(os.environ.get("TD_PROFILE_BATCH", "128"))
 cfgs = [("per-tap", {"TD_TC_HALO": "0"}), ("halo", {}), ("noA,noB", {"TD_TC_HALO_DBG": "6"}), ("flat", {"TD_TC_HALO_MODE": "1"}),
-        ("dx", {"TD_TC_HALO_MODE": "3"}), ("NB=4", {"TD_TC_HALO_NB": "4"})]
+        ("strip", {"TD_TC_HALO_MODE": "2"}), ("dx", {"TD_TC_HALO_MODE": "3"})]
 print("shape".ljust(18) + "".join(n.rjust(20) for n, _ in cfgs))
 tot = [0.0] * len(cfgs)
 for H, ci, co in shapes:
