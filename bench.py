@@ -262,7 +262,7 @@ def run_gpu(args):
     tmodel = NoiseModel().to(dev).train()
     tmodel.precision = args.precision
     tfp = ForwardProcess(T_STEPS)
-    ts = TrainStep(tmodel, tfp, B, dev, lr=1e-3, use_graph=(world == 1))
+    ts = TrainStep(tmodel, tfp, B, dev, lr=1e-3, use_graph=(world == 1 or os.environ.get("TD_DP_GRAPH", "1") != "0"))
     x0_host = (torch.rand(B, 1, 28, 28, generator=gen) * 2 - 1).pin_memory()
     x0_dev = x0_host.to(dev)
     TS = args.train_steps
@@ -360,8 +360,18 @@ def run_gpu(args):
                                      "sample": f"{args.cpu_train_steps} train steps at batch {B} ({tdt:.1f} s of CPU work)"}
         emit_line(line)
     if world > 1:
+        # the captured data-parallel step holds NCCL kernels: release the graphs before the communicator goes away, and
+        # never let a slow communicator teardown keep the (already reported) run alive
+        ts.close()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        import threading
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return line
 
 

@@ -85,7 +85,8 @@ __device__ inline void build_col_table(Bil* tab, int in, int out) {
 //   out[w] = l0(w) * v[i0(w)] + l1(w) * v[i1(w)] (+ add),     v[i] = lh0 * r0[i] + lh1 * r1[i]
 template <typename T>
 __device__ inline void resample_row(const T* __restrict__ r0, const T* __restrict__ r1, int cstride, float lh0, float lh1,
-                                    const Bil* __restrict__ col, int Wo, const float* add, T* __restrict__ dst, int dstride) {
+                                    const Bil* __restrict__ col, int w_begin, int w_end, const float* add, T* __restrict__ dst,
+                                    int dstride) {
     constexpr int V = Vec<T>::N;
     float va[V], vb[V];
     int ia = -1, ib = -1;
@@ -96,7 +97,7 @@ __device__ inline void resample_row(const T* __restrict__ r0, const T* __restric
 #pragma unroll
         for (int k = 0; k < V; ++k) v[k] = lh0 * a[k] + lh1 * b[k];
     };
-    for (int w = 0; w < Wo; ++w) {
+    for (int w = w_begin; w < w_end; ++w) {
         const Bil bw = col[w];
         if (bw.i0 != ia) {
             if (bw.i0 == ib) {
@@ -133,7 +134,7 @@ __device__ inline void resample_row(const T* __restrict__ r0, const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256)
 upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
-             int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
+             int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs, int nseg) {
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
     const int Ct = Cu + Cs;
@@ -145,8 +146,11 @@ upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float*
     if (!same) build_col_table(col, Win, Wo);
     __syncthreads();
     const int cvi = blockIdx.y * blockDim.x + threadIdx.x;
-    const int row = blockIdx.x * blockDim.y + threadIdx.y;   // (b, ho) flattened
+    const int seg = blockIdx.x % nseg;                       // segment of the output row walked by this thread
+    const int row = (blockIdx.x / nseg) * blockDim.y + threadIdx.y;   // (b, ho) flattened
     if (cvi * V >= Ch || row >= B * Ho) return;
+    const int sw = (Wo + nseg - 1) / nseg;
+    const int w_begin = seg * sw, w_end = min(Wo, w_begin + sw);
     const int c = cvi * V;
     const int b = row / Ho, ho = row - b * Ho;
     T* orow = out + (int64_t)row * Wo * Ct + (skip_half ? Cu : 0) + c;
@@ -158,7 +162,7 @@ upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float*
     }
     if (same) {
         const T* r0 = src + ((int64_t)row * Ws) * Cs + c;
-        for (int w = 0; w < Wo; ++w) {
+        for (int w = w_begin; w < w_end; ++w) {
             float r[V];
             Vec<T>::load(r0 + (int64_t)w * Cs).unpack(r);
 #pragma unroll
@@ -170,25 +174,28 @@ upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float*
     const Bil bh = bil(ho, Hin, Ho);
     const T* r0 = src + (((int64_t)b * Hin + bh.i0) * Win) * Ch + c;
     const T* r1 = src + (((int64_t)b * Hin + bh.i1) * Win) * Ch + c;
-    resample_row<T>(r0, r1, Ch, bh.l0, bh.l1, col, Wo, skip_half ? te : nullptr, orow, Ct);
+    resample_row<T>(r0, r1, Ch, bh.l0, bh.l1, col, w_begin, w_end, skip_half ? te : nullptr, orow, Ct);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
+resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C, int nseg) {
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
     build_col_table(col, Wi, Wo);
     __syncthreads();
     const int cvi = blockIdx.y * blockDim.x + threadIdx.x;
-    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    const int seg = blockIdx.x % nseg;
+    const int row = (blockIdx.x / nseg) * blockDim.y + threadIdx.y;
     if (cvi * V >= C || row >= B * Ho) return;
+    const int sw = (Wo + nseg - 1) / nseg;
+    const int w_begin = seg * sw, w_end = min(Wo, w_begin + sw);
     const int c = cvi * V;
     const int b = row / Ho, ho = row - b * Ho;
     const Bil bh = bil(ho, Hi, Ho);
     const T* r0 = x + (((int64_t)b * Hi + bh.i0) * Wi) * C + c;
     const T* r1 = x + (((int64_t)b * Hi + bh.i1) * Wi) * C + c;
-    resample_row<T>(r0, r1, C, bh.l0, bh.l1, col, Wo, nullptr, y + (int64_t)row * Wo * C + c, C);
+    resample_row<T>(r0, r1, C, bh.l0, bh.l1, col, w_begin, w_end, nullptr, y + (int64_t)row * Wo * C + c, C);
 }
 
 // block (vectors of one half, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
@@ -196,6 +203,13 @@ static inline dim3 walk_block(int cv) {
     int bx = 1;
     while (bx < cv && bx < 32) bx <<= 1;
     return dim3((unsigned)bx, (unsigned)(256 / bx), 1);
+}
+// row segments per thread walk: enough threads in flight (~1500 per SM) to cover the load latency
+static inline int walk_segments(int64_t threads, int width) {
+    int64_t n = ceil_div((int64_t)kNumSMs * 1536, std::max<int64_t>(threads, 1));
+    n = std::max<int64_t>(1, std::min<int64_t>(n, std::max(1, width / 4)));
+    const int sw = (int)ceil_div(width, n);
+    return (int)ceil_div(width, sw);
 }
 
 // OIHW fp32 -> OHWI (fp32 or bf16)
@@ -264,17 +278,19 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
         TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
         const int cvh = std::max(cu, cs) / 8;
         const dim3 blk = walk_block(cvh);
-        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(cvh, blk.x), 2);
+        const int nseg = walk_segments((int64_t)batch * ho * cvh * 2, wo);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(cvh, blk.x), 2);
         upcat_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
             (const __nv_bfloat16*)low, (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out,
-            batch, ho, wo, cu, hs, ws, cs);
+            batch, ho, wo, cu, hs, ws, cs, nseg);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(cu % 4 == 0 && cs % 4 == 0, "td_upcat_fwd: channel counts must be multiples of 4");
         const int cvh = std::max(cu, cs) / 4;
         const dim3 blk = walk_block(cvh);
-        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(cvh, blk.x), 2);
+        const int nseg = walk_segments((int64_t)batch * ho * cvh * 2, wo);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(cvh, blk.x), 2);
         upcat_kernel<float><<<grd, blk, 0, s>>>(
-            (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs);
+            (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs, nseg);
     } else {
         TD_CHECK_ARG(false, "td_upcat_fwd: unknown dtype %d", dtype);
     }
@@ -289,14 +305,16 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");
         const dim3 blk = walk_block(c / 8);
-        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(c / 8, blk.x), 1);
+        const int nseg = walk_segments((int64_t)batch * ho * (c / 8), wo);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(c / 8, blk.x), 1);
         resize_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
-            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c);
+            (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c, nseg);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 4 for fp32");
         const dim3 blk = walk_block(c / 4);
-        const dim3 grd((unsigned)ceil_div((int64_t)batch * ho, blk.y), (unsigned)ceil_div(c / 4, blk.x), 1);
-        resize_kernel<float><<<grd, blk, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
+        const int nseg = walk_segments((int64_t)batch * ho * (c / 4), wo);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(c / 4, blk.x), 1);
+        resize_kernel<float><<<grd, blk, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c, nseg);
     } else {
         TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
     }

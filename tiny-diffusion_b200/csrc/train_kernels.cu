@@ -4,6 +4,8 @@
 //   resizes (decoder concat assembly, final 32->28 resize) and per-channel sums (bias gradients).
 // Reductions are deterministic: every CTA writes its partial to its own row, a finalize kernel
 // sums the rows in fixed order (in double).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace td {
@@ -315,78 +317,139 @@ __device__ inline BilT bil_transpose(int i, int in, int out) {
     return t;
 }
 
+constexpr int kMaxRowW = 64;      // widest output row the column table is sized for
+
+// Transposed resize, the mirror image of glue.cu's resample_row: one thread owns one 16-byte channel vector of one
+// INPUT row and walks the OUTPUT columns left to right.  Per column it gathers the (<= 8) output rows that read this
+// input row, then adds the result into two register accumulators -- the input columns i0 and i0+1 the output column
+// interpolated between -- and stores an accumulator when the walk has moved past its column.  Deterministic
+// (fixed summation order), no per-pixel table search (the previous per-input-pixel gather spent most of its
+// instructions in bil_transpose).
 template <typename T>
 __global__ void __launch_bounds__(kT)
 resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
-                  int Wo, int C) {
-    // one CTA per input row (b, hi); the row's transposed weights are computed once per thread
+                  int Wo, int C, int nseg) {
     constexpr int V = Vec<T>::N;
-    const int cv = C / V;
-    const int b = blockIdx.x / Hi, hi = blockIdx.x - b * Hi;
+    __shared__ Bil col[kMaxRowW];
     const bool same = (Hi == Ho && Wi == Wo);
-    BilT th;
-    th.n = 0; th.o_lo = 0;
-    if (!same) th = bil_transpose(hi, Hi, Ho);
-    T* xrow = dx + ((int64_t)b * Hi + hi) * Wi * C;
-    for (int wi = threadIdx.y; wi < Wi; wi += blockDim.y) {
-        BilT tw;
-        tw.n = 0; tw.o_lo = 0;
-        if (!same) tw = bil_transpose(wi, Wi, Wo);
-        for (int cvi = threadIdx.x; cvi < cv; cvi += blockDim.x) {
-            const int c = cvi * V;
-            float acc[V];
+    if (!same)
+        for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < Wo; i += blockDim.x * blockDim.y) col[i] = bil_t(i, Wi, Wo);
+    __syncthreads();
+    const int cvi = blockIdx.y * blockDim.x + threadIdx.x;
+    const int seg = blockIdx.x % nseg;                            // segment of INPUT columns owned by this thread
+    const int row = (blockIdx.x / nseg) * blockDim.y + threadIdx.y;        // (b, hi) flattened
+    if (cvi * V >= C || row >= B * Hi) return;
+    const int sw = (Wi + nseg - 1) / nseg;
+    const int ca = seg * sw, cb = min(Wi, ca + sw);               // input columns [ca, cb)
+    if (ca >= cb) return;
+    const int c = cvi * V;
+    const int b = row / Hi, hi = row - b * Hi;
+    T* xrow = dx + (int64_t)row * Wi * C + c;
+    if (same) {
+        const T* g = dy + ((int64_t)row * Wo) * ld + coff + c;
+        for (int w = ca; w < cb; ++w) Vec<T>::load(g + (int64_t)w * ld).store(xrow + (int64_t)w * C);
+        return;
+    }
+    const BilT th = bil_transpose(hi, Hi, Ho);
+    const T* g0 = dy + (((int64_t)b * Ho + th.o_lo) * Wo) * ld + coff + c;
+    // output columns that can touch [ca, cb): conservative bounds from the inverse scale, the walk filters exactly
+    const float inv = (Wi > 1) ? (float)(Wo - 1) / (float)(Wi - 1) : 0.f;
+    const int w_begin = Wi > 1 ? max(0, (int)floorf((float)(ca - 1) * inv) - 1) : 0;
+    const int w_end = Wi > 1 ? min(Wo, (int)ceilf((float)cb * inv) + 2) : Wo;
+    float acc0[V], acc1[V];
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = 0.f;
-            if (same) {
-                Vec<T>::load(dy + (((int64_t)b * Ho + hi) * Wo + wi) * ld + coff + c).unpack(acc);
-            } else {
-                for (int a = 0; a < th.n; ++a) {
-                    if (th.w[a] == 0.f) continue;
-                    const T* rowp = dy + (((int64_t)b * Ho + th.o_lo + a) * Wo + tw.o_lo) * ld + coff + c;
-                    for (int q = 0; q < tw.n; ++q) {
-                        const float wgt = th.w[a] * tw.w[q];
-                        if (wgt == 0.f) continue;
-                        float g[V];
-                        Vec<T>::load(rowp + (int64_t)q * ld).unpack(g);
+    for (int k = 0; k < V; ++k) acc0[k] = acc1[k] = 0.f;
+    int ia = ca;                                                  // input column held by acc0 (acc1: ia + 1)
+    for (int w = w_begin; w < w_end; ++w) {
+        const Bil bw = col[w];
+        if (bw.i1 < ca) continue;
+        if (bw.i0 >= cb) break;
+        float gv[V];
 #pragma unroll
-                        for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
-                    }
-                }
+        for (int k = 0; k < V; ++k) gv[k] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {                 // static indices keep th.w in registers
+            if (a < th.n) {
+                float f[V];
+                Vec<T>::load(g0 + ((int64_t)a * Wo + w) * ld).unpack(f);
+#pragma unroll
+                for (int k = 0; k < V; ++k) gv[k] = fmaf(th.w[a], f[k], gv[k]);
             }
-            Vec<T>::pack(acc).store(xrow + (int64_t)wi * C + c);
         }
+        while (ia < bw.i0) {                          // the walk has moved past column ia: it is final
+            Vec<T>::pack(acc0).store(xrow + (int64_t)ia * C);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { acc0[k] = acc1[k]; acc1[k] = 0.f; }
+            ++ia;
+        }
+        // contributions (i0, l0) and (i1, l1); columns outside [ca, cb) belong to the neighbouring segments
+        const float l0 = bw.i1 == bw.i0 ? bw.l0 + bw.l1 : bw.l0;
+        if (bw.i0 == ia) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc0[k] = fmaf(l0, gv[k], acc0[k]);
+            if (bw.i1 != bw.i0) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc1[k] = fmaf(bw.l1, gv[k], acc1[k]);
+            }
+        } else if (bw.i1 == ia && bw.i1 != bw.i0) {   // i0 == ia - 1 lies in the previous segment
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc0[k] = fmaf(bw.l1, gv[k], acc0[k]);
+        }
+    }
+    for (; ia < cb; ++ia) {
+        Vec<T>::pack(acc0).store(xrow + (int64_t)ia * C);
+#pragma unroll
+        for (int k = 0; k < V; ++k) { acc0[k] = acc1[k]; acc1[k] = 0.f; }
     }
 }
 
-// d_temb[b, off + c] = sum over the Ho*Wo output pixels of d_out[b, :, :, Cu + c]   (one CTA per sample)
+// block (channel vectors, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
+static inline dim3 walk_block(int cv) {
+    int bx = 1;
+    while (bx < cv && bx < 32) bx <<= 1;
+    return dim3((unsigned)bx, (unsigned)(kT / bx), 1);
+}
+// input-row segments per thread walk: enough threads in flight (~1500 per SM) to cover the load latency
+static inline int walk_segments(int64_t threads, int width) {
+    int64_t n = ceil_div((int64_t)kNumSMs * 1536, std::max<int64_t>(threads, 1));
+    n = std::max<int64_t>(1, std::min<int64_t>(n, std::max(1, width / 2)));
+    const int sw = (int)ceil_div(width, n);
+    return (int)ceil_div(width, sw);
+}
+
+// d_temb[b, off + c] = sum over the Ho*Wo output pixels of d_out[b, :, :, Cu + c].  grid (samples, channel slices of
+// 8 vectors); 8 lanes x 32 pixel rows per CTA, fixed-order tree over the rows.
 template <typename T>
 __global__ void __launch_bounds__(kT)
 temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restrict__ dtemb, int ld_temb, int temb_off,
                 int HW, int Cs) {
     constexpr int V = Vec<T>::N;
-    extern __shared__ float red[];               // [rows][Cs]
-    const int lanesC = Cs / V;
-    const int rows = kT / lanesC;
-    const int lane = threadIdx.x % lanesC, row = threadIdx.x / lanesC;
+    __shared__ float red[32][8 * V + 1];
+    const int lane = threadIdx.x & 7, prow = threadIdx.x >> 3;
     const int b = blockIdx.x;
+    const int c = (blockIdx.y * 8 + lane) * V;
     float s[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) s[k] = 0.f;
-    if (row < rows) {
-        for (int p = row; p < HW; p += rows) {
+    if (c < Cs) {
+        const T* src = dout + (int64_t)b * HW * ld + coff + c;
+        for (int p = prow; p < HW; p += 32) {
             float f[V];
-            Vec<T>::load(dout + ((int64_t)b * HW + p) * ld + coff + lane * V).unpack(f);
+            Vec<T>::load(src + (int64_t)p * ld).unpack(f);
 #pragma unroll
             for (int k = 0; k < V; ++k) s[k] += f[k];
         }
-#pragma unroll
-        for (int k = 0; k < V; ++k) red[(size_t)row * Cs + lane * V + k] = s[k];
     }
+#pragma unroll
+    for (int k = 0; k < V; ++k) red[prow][lane * V + k] = s[k];
     __syncthreads();
-    for (int j = threadIdx.x; j < Cs; j += kT) {
-        float t = 0.f;
-        for (int r = 0; r < rows; ++r) t += red[(size_t)r * Cs + j];
-        dtemb[(int64_t)b * ld_temb + temb_off + j] = t;
+    if (threadIdx.x < 8 * V) {
+        const int cc = blockIdx.y * 8 * V + threadIdx.x;
+        if (cc < Cs) {
+            float t = 0.f;
+            for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+            dtemb[(int64_t)b * ld_temb + temb_off + cc] = t;
+        }
     }
 }
 
@@ -564,8 +627,12 @@ extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff
     TD_CHECK_ARG(dy && dx && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "td_resize_bilinear_bwd: bad args");
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0 && ld_dy % V == 0 && dy_coff % V == 0, "td_resize_bilinear_bwd: channels must be a multiple of %d", V);
-    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * hi, row_block(c / V), 0, (cudaStream_t)stream>>>(
-                             (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c)));
+    TD_CHECK_ARG(wo <= kMaxRowW, "td_resize_bilinear_bwd: output rows wider than %d", kMaxRowW);
+    const dim3 blk = walk_block(c / V);
+    const int nseg = walk_segments((int64_t)batch * hi * (c / V), wi);
+    const dim3 grd((unsigned)(ceil_div((int64_t)batch * hi, blk.y) * nseg), (unsigned)ceil_div(c / V, blk.x), 1);
+    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, (cudaStream_t)stream>>>(
+                             (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c, nseg)));
     return launch_status("resize_bilinear_bwd");
 }
 
@@ -579,14 +646,22 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
     if (int st = check_lanes("td_upcat_bwd", dtype, cs)) return st;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ld = cu + cs;
-    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * (ho / 2), row_block(cu / V), 0, s>>>(
-                             (const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu)));
-    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<batch * hs, row_block(cs / V), 0, s>>>(
-                             (const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs)));
+    TD_CHECK_ARG(wo <= kMaxRowW, "td_upcat_bwd: output rows wider than %d", kMaxRowW);
     {
-        const size_t smem = (size_t)(kT / (cs / V)) * cs * sizeof(float);
-        TD_DISPATCH_T(dtype, (temb_bwd_kernel<T><<<batch, kT, smem, s>>>((const T*)dout, ld, cu, dtemb, ld_temb, temb_off,
-                                                                         ho * wo, cs)));
+        const dim3 blk = walk_block(cu / V);
+        const int nseg = walk_segments((int64_t)batch * (ho / 2) * (cu / V), wo / 2);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * (ho / 2), blk.y) * nseg), (unsigned)ceil_div(cu / V, blk.x), 1);
+        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, s>>>((const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu, nseg)));
+    }
+    {
+        const dim3 blk = walk_block(cs / V);
+        const int nseg = walk_segments((int64_t)batch * hs * (cs / V), ws);
+        const dim3 grd((unsigned)(ceil_div((int64_t)batch * hs, blk.y) * nseg), (unsigned)ceil_div(cs / V, blk.x), 1);
+        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, s>>>((const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs, nseg)));
+    }
+    {
+        const dim3 grd((unsigned)batch, (unsigned)ceil_div(cs / V, 8), 1);
+        TD_DISPATCH_T(dtype, (temb_bwd_kernel<T><<<grd, kT, 0, s>>>((const T*)dout, ld, cu, dtemb, ld_temb, temb_off, ho * wo, cs)));
     }
     return launch_status("upcat_bwd");
 }

@@ -234,6 +234,8 @@ class UNetTrainEngine:
         adt = self.adt
         self.conv_plans: Dict[str, _ConvPlan] = {}
         self._wg_specs: List = []
+        self._side = getattr(self, "_side", None)
+        self._side_f = getattr(self, "_side_f", None)
         fwd: List[Tuple[str, Callable[[int], None]]] = []
         bwd: List[Tuple[str, Callable[[int], None]]] = []
         m = self.module
@@ -385,6 +387,22 @@ class UNetTrainEngine:
         for nm in ("dec3.3", "dec3.0"):
             add_block_bwd(*Ls[nm])
         add_upcat_bwd("b", "e3", "cat3", S["u3"], cfg.bott, S["s2"], c3, c1 + c2)
+        # d_temb is complete here: the conditioning head's backward (a chain of small GEMMs) runs on a forked stream
+        # beside the encoder backward and joins at its old place at the end of the plan (a parallel graph branch)
+        cat3_name, cat3_fn = bwd[-1]
+
+        def cat3_bwd_then_fork(st):
+            cat3_fn(st)
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                self._run_embed_bwd(L.stream_ptr())
+                self._ev_join.record(self._side)
+        bwd[-1] = (cat3_name, cat3_bwd_then_fork)
         add_block_bwd(*Ls["bottleneck.0"])
         add_pool_bwd("e3", "p3", S["s2"], c3)
         for nm in ("enc3.3", "enc3.0"):
@@ -405,7 +423,7 @@ class UNetTrainEngine:
         bwd.append(("initial_conv:dbias", ic_bias))
         self._wgrad("initial_conv", self.x_in, cfg.in_ch, gr["x0"], c0, s0, L.CONV_SIMT, x_nchw=True)
         bwd.append(("initial_conv:wgrad", None))
-        bwd.append(("embed:bwd", self._run_embed_bwd))
+        bwd.append(("embed:bwd", lambda st: torch.cuda.current_stream().wait_event(self._ev_join)))
 
         # weight-gradient plans share one workspace
         ws_floats = max(need for _, _, _, need in self._wg_specs)
@@ -459,9 +477,27 @@ class UNetTrainEngine:
 
     # ------------------------------------------------------------------ execution
     def launch_forward(self) -> None:
+        """The conditioning head (first entry) only feeds the decoder: it runs on a forked stream beside the encoder and
+        joins before the first upcat (a parallel branch of the captured graph)."""
         st = L.stream_ptr()
-        for _, fn in self.fwd_ops:
+        main = torch.cuda.current_stream()
+        if self._side_f is None:
+            self._side_f = torch.cuda.Stream(device=self.device)
+            self._evf_fork, self._evf_join = torch.cuda.Event(), torch.cuda.Event()
+        assert self.fwd_ops[0][0] == "embed"
+        self._evf_fork.record(main)
+        self._side_f.wait_event(self._evf_fork)
+        with torch.cuda.stream(self._side_f):
+            self.fwd_ops[0][1](L.stream_ptr())
+            self._evf_join.record(self._side_f)
+        joined = False
+        for name, fn in self.fwd_ops[1:]:
+            if not joined and name.startswith("upcat"):
+                main.wait_event(self._evf_join)
+                joined = True
             fn(st)
+        if not joined:
+            main.wait_event(self._evf_join)
 
     def launch_backward(self) -> None:
         """Reads d_eps; fills ``pgrad`` (every parameter).  Conv biases that feed a BatchNorm have a
@@ -673,11 +709,13 @@ class TrainStep:
     def run(self) -> torch.Tensor:
         """One optimisation step on the staged batch; returns the (device) loss tensor."""
         self.model.train()
-        if not self.use_graph or self.world > 1:
+        if not self.use_graph:
             self.eng.refresh_weights()
             self._body()
             return self.loss
         if self.graph is None:
+            # world > 1: the bucketed NCCL all-reduces are captured too (every rank captures the same sequence; the
+            # async works become cross-stream edges of the graph), so the data-parallel step is ONE replay per rank
             self.eng.refresh_weights(force=True)
             # warm-up outside capture on a side stream (lazy module load / cudaFuncSetAttribute), restoring
             # every piece of state the step mutates
@@ -704,6 +742,10 @@ class TrainStep:
             self.graph = g
         self.graph.replay()
         return self.loss
+
+    def close(self) -> None:
+        """Drop the captured graph (with world_size > 1 it holds NCCL kernels: release it before the process group)."""
+        self.graph = None
 
     def __call__(self, x_0, y=None, t=None, noise=None) -> torch.Tensor:
         self.load(x_0, y, t, noise)
