@@ -14,7 +14,8 @@ for d in by.values():
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         if m in d:
             tot += d[m][0] * unit.get(d[m][1], 1.0)
-    key = "conv3x3_tc" if "conv3x3_tc_kernel" in d["name"] else ("wgrad_tc" if "wgrad_tc_kernel" in d["name"] else None)
+    key = "conv_tc" if ("conv3x3_tc_kernel" in d["name"] or "conv3x3_halo_kernel" in d["name"]) else (
+        "wgrad_tc" if "wgrad_tc_kernel" in d["name"] else None)
     if key:
         agg[key][0] += 1
         agg[key][1] += tot

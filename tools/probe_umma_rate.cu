@@ -16,7 +16,7 @@
 using namespace td::sm100;
 
 // PAIR = 0: cta_group::1, M = 128, B tile = N rows.   PAIR = 1: cta_group::2, M = 256, each CTA holds N/2 rows of B.
-template <int N, int PAIR, int STAGES>
+template <int N, int PAIR, int STAGES, int MN = 0, int ROWOFF = 0>
 __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -59,15 +59,17 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
     const uint32_t tmem_base = *tmem_ptr;
     long long t0 = 0, t1 = 0;
     if (threadIdx.x == 0 && rank == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N, 0, 0);
+        constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, N, MN, MN);
         t0 = clock64();
         for (int it = 0; it < iters; ++it) {
             const int s = it % STAGES;
             const uint32_t a_addr = smem_u32(smem_a + s * A_BYTES), b_addr = smem_u32(smem_b + s * B_BYTES);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                // MN-major (weight-gradient form): a stage is [64 K rows][128 B] per 64-channel box, boxes 8 KB apart
+                const uint64_t da = MN ? make_smem_desc_sw128(a_addr + ROWOFF * 128 + (k & 1) * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(a_addr + ROWOFF * 128 + k * 32, 16, 1024);
+                const uint64_t db = MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024) : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
                 if (PAIR) umma_bf16_pair(tmem_base, da, db, idesc, (it | k) ? 1u : 0u);
                 else umma_bf16(tmem_base, da, db, idesc, (it | k) ? 1u : 0u);
             }
@@ -90,13 +92,13 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
     }
 }
 
-template <int N, int PAIR, int STAGES>
+template <int N, int PAIR, int STAGES, int MN = 0, int ROWOFF = 0>
 static void run(const char* name, int ctas, int iters) {
     long long* d;
     cudaMalloc(&d, ctas * sizeof(long long));
     cudaMemset(d, 0, ctas * sizeof(long long));
     const int smem = STAGES * (128 * 128 + (PAIR ? N / 2 : N) * 128) + 64 + 1024;
-    auto kern = rate_kernel<N, PAIR, STAGES>;
+    auto kern = rate_kernel<N, PAIR, STAGES, MN, ROWOFF>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ctas);
@@ -146,6 +148,12 @@ int main() {
         run<128, 0, 4>("1-CTA M=128 N=128", ctas, iters);
         run<256, 0, 4>("1-CTA M=128 N=256", ctas, iters);
         run<128, 0, 1>("1-CTA M=128 N=128 (one stage)", ctas, iters);
+        run<128, 0, 4, 1>("1-CTA M=128 N=128 MN-major A and B", ctas, iters);
+        run<64, 0, 4, 1>("1-CTA M=128 N=64  MN-major A and B", ctas, iters);
+        run<128, 0, 4, 1, 1>("MN-major, A starts at row 1", ctas, iters);
+        run<128, 0, 4, 1, 3>("MN-major, A starts at row 3", ctas, iters);
+        run<128, 0, 4, 0, 1>("K-major, A starts at row 1", ctas, iters);
+        run<128, 0, 4, 0, 5>("K-major, A starts at row 5", ctas, iters);
         run<64, 1, 4>("CTA pair M=256 N=64", ctas, iters);
         run<128, 1, 4>("CTA pair M=256 N=128", ctas, iters);
         run<256, 1, 4>("CTA pair M=256 N=256", ctas, iters);

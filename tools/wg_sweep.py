@@ -6,7 +6,7 @@ from tinydiff import _lib as L
 dev = L.require_device("cuda:0")
 lib = L.load()
 def run(B, H, cin, cout, env, iters=10):
-    for k in ("TD_WG_STAGES", "TD_WG_BLOCK_N", "TD_WG_TARGET_CTAS"):
+    for k in ("TD_WG_STAGES", "TD_WG_BLOCK_N", "TD_WG_TARGET_CTAS", "TD_WG_HALO"):
         os.environ.pop(k, None)
     os.environ.update(env)
     x = torch.randn(B, H, H, cin, device=dev).to(torch.bfloat16)
@@ -35,8 +35,7 @@ def run(B, H, cin, cout, env, iters=10):
 shapes = [(28, 64, 128), (28, 128, 128), (14, 128, 256), (14, 256, 256), (7, 256, 512), (7, 512, 512), (4, 512, 512),
           (8, 1024, 256), (8, 256, 256), (16, 512, 128), (16, 128, 128), (32, 256, 64), (32, 64, 64)]
 B = int(os.environ.get("TD_PROFILE_BATCH", "128"))
-cfgs = [{}, {"TD_WG_STAGES": "2"}, {"TD_WG_STAGES": "3"}, {"TD_WG_TARGET_CTAS": "148"}, {"TD_WG_TARGET_CTAS": "592"},
-        {"TD_WG_BLOCK_N": "128"}, {"TD_WG_BLOCK_N": "128", "TD_WG_STAGES": "2"}, {"TD_WG_BLOCK_N": "64"}]
+cfgs = [{"TD_WG_HALO": "0"}, {}, {"TD_WG_STAGES": "2"}, {"TD_WG_TARGET_CTAS": "74"}, {"TD_WG_TARGET_CTAS": "296"}]
 print("shape".ljust(18) + "".join((",".join(f"{k[6:]}={v}" for k, v in c.items()) or "default").rjust(24) for c in cfgs))
 tot = [0.0] * len(cfgs)
 for H, ci, co in shapes:
