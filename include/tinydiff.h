@@ -204,6 +204,11 @@ int td_final_resize_conv(const void* x, int dtype, int ldx, int x_coff, int batc
 int td_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
                const float* conv_bias, float eps, float* scale, float* shift, int c, void* stream);
 
+/* Every bf16 conv layer of a model re-packed in one launch (after an optimizer step).  table: device array of
+ *   struct { const float* src_oihw; bf16* dst_ohwi; bf16* dst_dgrad_or_NULL; int cout, cin, tile_begin, pad; }
+ * (40 bytes per entry, cout and cin multiples of 32, tile_begin = running sum of (cout/32)*(cin/32)). */
+int td_pack_conv_weights_multi(const void* table, int n_entries, int total_tiles, void* stream);
+
 /* dtype conversion / weight packing helpers */
 int td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 /* OIHW fp32 (PyTorch conv weight) -> OHWI fp32 or bf16 */

@@ -89,6 +89,7 @@ _SIGS = {
     "td_final_resize_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int,
                                        C.c_int, _P, _P]),
     "td_cast_f32_to_bf16": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "td_pack_conv_weights_multi": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "td_pack_conv_weight": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_pack_conv_weight_dgrad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_conv3x3_wgrad_workspace": (C.c_int64, [C.POINTER(WgradDesc), C.c_int]),

@@ -100,35 +100,44 @@ chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const float
 // BatchNorm2d train-mode finalize (diffusion.py:34): batch mean / biased variance -> the affine
 // used by the apply pass; running statistics updated like torch (momentum, unbiased variance,
 // conv bias folded into the mean only).
-// one warp per channel: lanes stride the partial rows, shuffle-reduce in double (fixed order)
-__device__ inline void warp_sum_partials(const float* __restrict__ partials, int nrows, int C, int c, double& s1,
-                                         double& s2) {
-    const int lane = threadIdx.x & 31;
+// CTA = 32 channels (threadIdx.x, coalesced 128-byte reads of a partial row) x 32 row groups (threadIdx.y); the
+// row groups are combined through shared memory in fixed order, in double.  Result valid on the threadIdx.y == 0 row.
+// (One warp per channel with lanes striding the rows read one 4-byte element per 32-byte sector and took ~10 us.)
+__device__ inline void block_sum_partials(const float* __restrict__ partials, int nrows, int C, int c, double& s1,
+                                          double& s2) {
+    __shared__ double red[32][2][33];
     double a = 0.0, b = 0.0;
-    for (int r = lane; r < nrows; r += 32) {
-        a += (double)partials[(size_t)r * 2 * C + c];
-        b += (double)partials[(size_t)r * 2 * C + C + c];
+    if (c < C) {
+        const float* p = partials + c;
+#pragma unroll 4
+        for (int r = threadIdx.y; r < nrows; r += 32) {
+            a += (double)p[(size_t)r * 2 * C];
+            b += (double)p[(size_t)r * 2 * C + C];
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
+    red[threadIdx.y][0][threadIdx.x] = a;
+    red[threadIdx.y][1][threadIdx.x] = b;
+    __syncthreads();
+    s1 = 0.0; s2 = 0.0;
+    if (threadIdx.y == 0) {
+        for (int g = 0; g < 32; ++g) {
+            s1 += red[g][0][threadIdx.x];
+            s2 += red[g][1][threadIdx.x];
+        }
     }
-    s1 = a; s2 = b;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double count, const float* __restrict__ gamma,
                    const float* __restrict__ beta, const float* __restrict__ conv_bias, float eps, float momentum,
                    float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_invstd) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
-    if (c >= C) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt) nbt[0] += 1;
     double s1, s2;
-    warp_sum_partials(partials, nrows, C, c, s1, s2);
-    if ((threadIdx.x & 31) != 0) return;
+    block_sum_partials(partials, nrows, C, c, s1, s2);
+    if (threadIdx.y != 0 || c >= C) return;
     const double dm = s1 / count;                         // mean of (x - K)
     const double mean = (double)partials[(size_t)nrows * 2 * C + c] + dm;
     double var = s2 / count - dm * dm;
@@ -178,16 +187,15 @@ bn_relu_apply_kernel(const float* __restrict__ y, const float* __restrict__ scal
 }
 
 // BatchNorm backward coefficients: dy = cA*g + cB*y + cC (see bn_relu_bwd_apply_kernel)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double count,
                        const float* __restrict__ scale, const float* __restrict__ save_mean,
                        const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ coef) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double s1, s2;
-    warp_sum_partials(partials, nrows, C, c, s1, s2);
-    if ((threadIdx.x & 31) != 0) return;
+    block_sum_partials(partials, nrows, C, c, s1, s2);
+    if (threadIdx.y != 0 || c >= C) return;
     const double mean = save_mean[c], invstd = save_invstd[c], sc = scale[c];
     const double dg = s2 * invstd;                     // sum g * xhat   (s2 = sum g * (y - mean))
     dgamma[c] = (float)dg;
@@ -453,14 +461,13 @@ temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restr
     }
 }
 
-// out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials), one warp per channel
-__global__ void __launch_bounds__(128)
+// out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials)
+__global__ void __launch_bounds__(1024)
 partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int which, float* __restrict__ out) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
+    const int c = blockIdx.x * 32 + threadIdx.x;
     double s1, s2;
-    warp_sum_partials(partials, nrows, C, c, s1, s2);
-    if ((threadIdx.x & 31) == 0) out[c] = (float)(which ? s2 : s1);
+    block_sum_partials(partials, nrows, C, c, s1, s2);
+    if (threadIdx.y == 0 && c < C) out[c] = (float)(which ? s2 : s1);
 }
 
 // per-channel sum of an NCHW fp32 tensor (final_conv bias gradient): grid (chunks, C) partial sums,
@@ -551,7 +558,7 @@ extern "C" int td_bn_finalize(const float* partials, int nrows, int channels, in
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && gamma && beta && scale && shift && save_mean &&
                      save_invstd, "td_bn_finalize: bad args");
-    bn_finalize_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+    bn_finalize_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
         partials, nrows, channels, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
         num_batches_tracked, scale, shift, save_mean, save_invstd);
     return launch_status("bn_finalize");
@@ -590,7 +597,7 @@ extern "C" int td_bn_bwd_finalize(const float* partials, int nrows, int channels
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && scale && save_mean && save_invstd && dgamma &&
                      dbeta && coef, "td_bn_bwd_finalize: bad args");
-    bn_bwd_finalize_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+    bn_bwd_finalize_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
         partials, nrows, channels, (double)count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
     return launch_status("bn_bwd_finalize");
 }
@@ -669,7 +676,7 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
 extern "C" int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && out && nrows > 0 && channels > 0 && (which == 0 || which == 1), "td_partial_sum: bad args");
-    partial_sum_kernel<<<(channels + 3) / 4, 128, 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
+    partial_sum_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
     return launch_status("partial_sum");
 }
 

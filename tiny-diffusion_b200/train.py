@@ -143,6 +143,7 @@ class UNetTrainEngine:
                                          [(cin, size) for _, _, cin, size, _, _ in self.layers], device)
         self._build()
         self._weights_version = None
+        self._pack_table = None
 
     # ------------------------------------------------------------------ parameters
     def _conv_modules(self):
@@ -180,7 +181,14 @@ class UNetTrainEngine:
             return
         st = L.stream_ptr()
         lib = self.lib
+        if self._pack_table is None:
+            self._build_pack_table()
+        if self._pack_tiles > 0:          # every bf16 layer (forward + dgrad operand) in one launch
+            L.check(lib.td_pack_conv_weights_multi(self._pack_table.data_ptr(), self._pack_entries, self._pack_tiles, st),
+                    "td_pack_conv_weights_multi")
         for name, (conv, bn) in self.conv_of.items():
+            if name in self._pack_fused:
+                continue
             w = conv.weight.detach()
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
             pk = self.w_fwd[name]
@@ -199,6 +207,27 @@ class UNetTrainEngine:
             self.proj_b[off:off + c].copy_(proj.bias.detach())
             off += c
         self._weights_version = ver
+
+    def _build_pack_table(self) -> None:
+        """Device table for td_pack_conv_weights_multi: every conv whose packed operands are bf16 with channel counts
+        that are multiples of 32 (the tensor-core layers); the parameter tensors are stable (updated in place)."""
+        import struct
+        rows, tiles, fused = [], 0, set()
+        for name, (conv, bn) in self.conv_of.items():
+            w = conv.weight
+            pk = self.w_fwd[name]
+            pb = self.w_bwd.get(name)
+            co, ci = w.shape[0], w.shape[1]
+            if pk.dtype != torch.bfloat16 or co % 32 or ci % 32 or (pb is not None and pb.dtype != torch.bfloat16):
+                continue
+            assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+            rows.append(struct.pack("<QQQiiii", w.data_ptr(), pk.data_ptr(), pb.data_ptr() if pb is not None else 0,
+                                    co, ci, tiles, 0))
+            tiles += (co // 32) * (ci // 32)
+            fused.add(name)
+        self._pack_fused, self._pack_tiles, self._pack_entries = fused, tiles, len(rows)
+        raw = b"".join(rows) if rows else b"\0" * 40
+        self._pack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
 
     # ------------------------------------------------------------------ plan construction
     def _conv_desc(self, x, cin, y, cout, w, x_coff=0, shift=None, x_nchw=False, y_nchw=False, size=None):
