@@ -187,8 +187,17 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
     const int t = threadIdx.x / WR_C, c = threadIdx.x % WR_C;
     if (c < nc) {
         const float* src = ws + ((int64_t)o * 9 + t) * cin + c0 + c;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        // eight independent partial sums: eight loads in flight per thread (the kernel is latency-bound otherwise);
+        // the summation order is fixed by the split index, so the result is deterministic
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
         int z = 0;
+        for (; z + 8 <= splits; z += 8) {
+            const float v0 = __ldg(src + (int64_t)z * per), v1 = __ldg(src + (int64_t)(z + 1) * per);
+            const float v2 = __ldg(src + (int64_t)(z + 2) * per), v3 = __ldg(src + (int64_t)(z + 3) * per);
+            const float v4 = __ldg(src + (int64_t)(z + 4) * per), v5 = __ldg(src + (int64_t)(z + 5) * per);
+            const float v6 = __ldg(src + (int64_t)(z + 6) * per), v7 = __ldg(src + (int64_t)(z + 7) * per);
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3; a4 += v4; a5 += v5; a6 += v6; a7 += v7;
+        }
         for (; z + 4 <= splits; z += 4) {
             a0 += src[(int64_t)z * per];
             a1 += src[(int64_t)(z + 1) * per];
@@ -196,7 +205,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
             a3 += src[(int64_t)(z + 3) * per];
         }
         for (; z < splits; ++z) a0 += src[(int64_t)z * per];
-        tile[t][c] = (a0 + a1) + (a2 + a3);
+        tile[t][c] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     }
     __syncthreads();
     float* dst = dw + ((int64_t)o * cin + c0) * 9;

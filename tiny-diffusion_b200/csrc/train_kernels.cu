@@ -62,6 +62,7 @@ chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const float
         Vec<T>::load(a + a_coff + c0).unpack(mu);            // K = the first pixel of every channel
     }
     if (row < rows) {
+#pragma unroll 4
         for (int64_t p = (int64_t)blockIdx.x * rows + row; p < P; p += (int64_t)gridDim.x * rows) {
             float f[V];
             Vec<T>::load(a + p * lda + a_coff + c0).unpack(f);
@@ -173,6 +174,7 @@ bn_relu_apply_kernel(const float* __restrict__ y, const float* __restrict__ scal
 #pragma unroll
     for (int k = 0; k < V; ++k) { sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; }
     const int lsh = __ffs(lanesC) - 1;                    // lanesC is a power of two (checked on the host)
+#pragma unroll 4
     for (; i < (uint32_t)total; i += stride) {
         const int64_t p = i >> lsh;
         float f[V];
@@ -225,6 +227,7 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
         cA[k] = coef[c0 + k]; cB[k] = coef[C + c0 + k]; cC[k] = coef[2 * C + c0 + k];
     }
     const int lsh = __ffs(lanesC) - 1;                    // lanesC is a power of two (checked on the host)
+#pragma unroll 4
     for (; i < (uint32_t)total; i += stride) {
         const int64_t p = i >> lsh;
         float g[V], yy[V];
