@@ -213,7 +213,7 @@ def run_gpu(args):
     eng.refresh_weights()
     launches_per_reverse_step = eng.num_launches() + 2          # + p_sample + step counter
 
-    # ---- device-resident measurement: x_T, y already in HBM; 1000 graph replays per step --------
+    # ---- device-resident measurement: x_T, y already in HBM; the loop is replayed from captured graphs ----
     def device_step():
         eng.x_in.copy_(xT_dev)
         eng.y_in.copy_(y_dev)
@@ -338,7 +338,8 @@ def run_gpu(args):
                                    f"batch {B}/GPU (global {B * world}), random-init weights",
                        "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"sample-sharded x{world}",
                        "l2": f"no flush: activation working set {ws_bytes / 2**20:.0f} MiB per forward > 126 MB L2",
-                       "cuda_graph": "one reverse step captured, replayed 1000x per bench step"},
+                       "cuda_graph": f"{ReverseLoop.STEPS_PER_GRAPH} reverse steps captured per graph, "
+                                     f"{T_STEPS // ReverseLoop.STEPS_PER_GRAPH} replays per bench step; programmatic dependent launch between kernels"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xT_host.numel() * 4 + y_host.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(args.steps * T_STEPS * (launches_per_reverse_step + 4)),

@@ -38,6 +38,9 @@ int td_version(void);
 const char* td_last_error_string(void);
 /* 0 if `device` is an sm_100-class GPU this library can run on, TD_ERR_ARCH otherwise. */
 int td_device_check(int device);
+/* Programmatic dependent launch (every kernel's launch latency and on-chip prologue overlap the tail of the preceding kernel
+ * of the stream; on by default, TD_PDL=0 in the environment turns it off).  Returns the previous setting. */
+int td_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise DDPM kernels (HBM-bound)
@@ -72,6 +75,12 @@ int td_mse_grad(const float* pred, const float* target, float* grad, float* loss
 int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride,
                     const float* coef, const int32_t* t_dev, int64_t n, const uint64_t* seed_ptr,
                     void* stream);
+/* Classifier-free-guidance reverse step -- an EXTENSION: the reference has no guidance, BASELINE.json's
+ * config 2 names it.  x and eps hold a doubled batch, rows [0, n) conditional and rows [n, 2n) null-label:
+ *   e = eps_u + guidance*(eps_c - eps_u);  x <- c1[t]*(x - c2[t]*e) + c3[t]*z, stored to both halves.
+ * n = elements of ONE half (multiple of 4); z / Philox indexing as td_psample_step over n elements. */
+int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z, int64_t z_step_stride,
+                        const float* coef, const int32_t* t_dev, const uint64_t* seed_ptr, void* stream);
 /* t_dev[0] += delta ; used between captured steps. */
 int td_counter_add(int32_t* t_dev, int32_t delta, void* stream);
 

@@ -111,3 +111,75 @@ def test_conditional_sample_errors(dev):
         mod.sample(model, fp, dev, n_samples=4)                       # conditional_diffusion.py:358-361
     with pytest.raises(ValueError):
         mod.sample(model, fp, dev, n_samples=4, y=torch.zeros(3, dtype=torch.long))   # :362-363
+
+
+# ------------------------------------------------------------------------------------------
+# classifier-free guidance (extension): no reference behaviour exists; the target is the
+# composition eps_u + w*(eps_c - eps_u) of two reference (oracle) forwards inside the reference's reverse loop
+# ------------------------------------------------------------------------------------------
+def _cfg_model(dev, precision):
+    from tinydiff.conditional_diffusion import NoiseModel
+    sd10 = init_state_dict("conditional_diffusion")
+    g = torch.Generator().manual_seed(5)
+    sd = dict(sd10)
+    sd["class_embedding.weight"] = torch.cat([sd10["class_embedding.weight"], torch.randn(1, 256, generator=g)], 0)
+    model = NoiseModel(num_classes=11)                    # the 11th row is the null label
+    model.load_state_dict(sd, strict=True)
+    model.precision = precision
+    return model.to(dev).eval(), sd
+
+
+def test_cfg_step_kernel_bit_exact(dev):
+    """td_psample_step_cfg against the torch composition (separate fp32 roundings): bit-exact, both halves."""
+    from tinydiff import _lib as L
+    from tinydiff.conditional_diffusion import ForwardProcess
+    lib = L.load()
+    fp = ForwardProcess()
+    tab = fp._tables(dev)
+    g = torch.Generator().manual_seed(3)
+    n = 6 * 784
+    for t, w in ((999, 3.0), (500, 1.0), (1, 7.5), (0, 2.0)):
+        x = torch.randn(n, generator=g)
+        eps = torch.randn(2 * n, generator=g)
+        z = torch.randn(n, generator=g)
+        xd = torch.cat([x, x]).to(dev)
+        ed, zd = eps.to(dev), z.to(dev)
+        t_dev = torch.tensor([t], dtype=torch.int32, device=dev)
+        L.check(lib.td_psample_step_cfg(xd.data_ptr(), ed.data_ptr(), n, w, zd.data_ptr(), 0, tab["coef"].data_ptr(),
+                                        t_dev.data_ptr(), None, L.stream_ptr()), "td_psample_step_cfg")
+        e = eps[n:] + w * (eps[:n] - eps[n:])
+        want = O.p_sample_step(x, e, z, t, fp.betas, fp.alphas, fp.alphas_cumprod)
+        assert torch.equal(xd[:n].cpu(), want) and torch.equal(xd[n:].cpu(), want), (t, w)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+def test_cfg_sampler_vs_oracle_composition(dev, precision, tol):
+    from tinydiff.conditional_diffusion import ForwardProcess, sample, sample_cfg
+    model, sd = _cfg_model(dev, precision)
+    T, n, w = 40, 4, 2.5
+    fp = ForwardProcess(num_timesteps=T)
+    g = torch.Generator().manual_seed(21)
+    x_T = torch.randn(n, 1, 28, 28, generator=g)
+    z = torch.randn(T, n, 1, 28, 28, generator=g)
+    y = torch.tensor([3, 1, 4, 9])
+    null = torch.full_like(y, 10)
+
+    def eps_fn(x, t):
+        tt = torch.full((n,), t, dtype=torch.long)
+        ec = O.unet_forward(O.UNET_COND, sd, x, tt, y)
+        eu = O.unet_forward(O.UNET_COND, sd, x, tt, null)
+        return eu + w * (ec - eu)
+    want, _ = O.sample_loop(eps_fn, x_T, z, fp.betas, fp.alphas, fp.alphas_cumprod)
+    got = sample_cfg(model, fp, dev, n_samples=n, y=y, guidance_scale=w, x_T=x_T, z=z.to(dev))
+    assert got.shape == (n, 1, 28, 28) and not model.training
+    assert rel(got, want) < tol
+    eager = sample_cfg(model, fp, dev, n_samples=n, y=y, guidance_scale=w, x_T=x_T, z=z.to(dev), use_graph=False)
+    assert torch.equal(got, eager)
+    # w = 1 is plain conditional sampling (same kernels on the conditional half, so only the combine's rounding differs)
+    plain = sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, z=z.to(dev))
+    one = sample_cfg(model, fp, dev, n_samples=n, y=y, guidance_scale=1.0, x_T=x_T, z=z.to(dev))
+    assert rel(one, plain) < (1e-4 if precision == "fp32" else 2e-2)
+    with pytest.raises(ValueError):
+        sample_cfg(model, fp, dev, n_samples=n, y=None)
+    with pytest.raises(ValueError):
+        sample_cfg(model, fp, dev, n_samples=n, y=y, null_label=11)

@@ -368,3 +368,41 @@ def test_fused_train_step_vs_oracle_adam(dev, precision, use_graph):
             bad[k] = (err, tol)
     assert not bad, f"Adam update mismatch (err, tol): {bad}"
     assert int(got["enc1.1.num_batches_tracked"]) == int(init["enc1.1.num_batches_tracked"]) + 2
+
+
+# ------------------------------------------------------------------------------------------
+# validation pass
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("name", ["diffusion", "conditional_diffusion", "conditional_diffusion_laion"])
+def test_validation_step_vs_oracle(dev, name, precision, tol, use_graph):
+    """The validation loop body of the reference's train() (conditional_diffusion.py:275-289): q_sample ->
+    eval-mode forward -> F.mse_loss under no_grad, fused in ValStep.  Running statistics are perturbed first so the
+    eval-mode BatchNorm really reads them; two different batches go through the same (captured) step; buffers and
+    parameters must be left untouched and the model in eval mode."""
+    from tinydiff.train import ValStep
+    mod, model = build(name, dev, precision)
+    sd = init_state_dict(name)
+    g = torch.Generator().manual_seed(77)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = torch.randn(sd[k].shape, generator=g) * 0.2
+        elif k.endswith("running_var"):
+            sd[k] = torch.rand(sd[k].shape, generator=g) + 0.5
+    model.load_state_dict(sd, strict=True)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    fp = mod.ForwardProcess()
+    B = 6
+    vs = ValStep(model, fp, B, dev, use_graph=use_graph)
+    for seed in (901, 902):
+        inp = make_inputs(name, B, seed=seed)
+        loss = float(vs(inp["x0"], inp.get("cond"), t=inp["t"], noise=inp["noise"]))
+        x_t = O.q_sample(fp.alphas_cumprod, inp["x0"], inp["t"], inp["noise"])
+        eps = O.unet_forward(SPECS[name], sd, x_t, inp["t"], inp.get("cond"))
+        want, _ = O.mse_loss_and_grad(eps, inp["noise"])
+        assert abs(loss - float(want)) / float(want) < tol, (seed, loss, float(want))
+    assert not model.training
+    after = model.state_dict()
+    for k, v in before.items():
+        assert torch.equal(after[k], v), f"validation changed {k}"

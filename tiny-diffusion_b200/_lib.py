@@ -64,10 +64,12 @@ _SIGS = {
     "td_version": (C.c_int, []),
     "td_last_error_string": (C.c_char_p, []),
     "td_device_check": (C.c_int, [C.c_int]),
+    "td_set_pdl": (C.c_int, [C.c_int]),
     "td_qsample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "td_mse_num_partials": (C.c_int64, [C.c_int64]),
     "td_mse_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_float, _P]),
     "td_psample_step": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, _P, _P]),
+    "td_psample_step_cfg": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, C.c_int64, _P, _P, _P, _P]),
     "td_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, _P]),
     "td_counter_add": (C.c_int, [_P, C.c_int32, _P]),
     "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, C.c_float,

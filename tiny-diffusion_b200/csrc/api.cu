@@ -1,5 +1,6 @@
 // Library-level entry points: version, error reporting, architecture gate.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -37,7 +38,22 @@ int require_sm100() {
     return cached_status;
 }
 
+static int g_pdl = -1;      // -1: not read yet
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("TD_PDL");
+        g_pdl = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
+
 }  // namespace td
+
+extern "C" int td_set_pdl(int on) {
+    const int prev = td::pdl_enabled() ? 1 : 0;
+    td::g_pdl = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int td_version(void) { return 100; }
 extern "C" const char* td_last_error_string(void) { return td::g_err; }

@@ -49,6 +49,43 @@ inline int launch_status(const char* what) {
 
 constexpr int kNumSMs = 148;
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute (unless TD_PDL=0) and runs
+// pdl_sync() before it touches global memory: `griddepcontrol.wait` returns once the preceding kernel of the stream has
+// completed and flushed, so a kernel's launch latency, block scheduling and on-chip prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) overlap the tail of its predecessor; `griddepcontrol.launch_dependents` then lets the successor do the
+// same.  Because EVERY kernel waits, completion stays transitive along the stream (a kernel cannot finish before all earlier
+// ones have).  Kernels that allocate TMEM call pdl_sync() after the allocation: a successor made resident on the same SM can
+// then never take the columns first.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+bool pdl_enabled();      // api.cu: TD_PDL environment switch (default on), read once
+
+struct LaunchCfg {
+    dim3 grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    LaunchCfg(dim3 g, dim3 b, size_t s = 0, cudaStream_t st = nullptr) : grid(g), block(b), smem(s), stream(st) {}
+};
+
+template <typename... P, typename... A>
+inline void launch(void (*kernel)(P...), const LaunchCfg& c, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = c.grid;
+    cfg.blockDim = c.block;
+    cfg.dynamicSmemBytes = c.smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);       // errors surface through launch_status()
+}
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- dtype helpers -------------------------------------------------------------------------

@@ -21,7 +21,8 @@
 // Two subtiles (each with its own box) share every weight stage, accumulators are double buffered in
 // TMEM, and the kernel is persistent: each CTA walks a contiguous range of (n-tile, subtile) units so
 // that the epilogue of one pair overlaps the main loop of the next.
-// Warp roles: 0 = TMA producer, 1-2 = MMA issuers (one per subtile), 3..6 = epilogue.
+// Warp roles: 0 = TMA producer, 1-2 = MMA issuers (one per subtile), 3..6 = epilogue of subtile 0, 7..10 = epilogue of
+// subtile 1 (with one group of four warps the epilogue was as long as the main loop on the K = 576 layers).
 #include <algorithm>
 
 #include "conv_plan.h"
@@ -56,7 +57,7 @@ __device__ unsigned long long g_halo_dbg[kNumSMs * 8];
 #define HALO_T0() const long long _t0 = p.dbg ? clock64() : 0
 #define HALO_ACC(var) do { if (p.dbg) var += clock64() - _t0; } while (0)
 
-constexpr int HALO_THREADS = 224;   // warp 0 TMA producer, warps 1-2 MMA issuers (one per subtile), warps 3-6 epilogue
+constexpr int HALO_THREADS = 352;   // warp 0 TMA producer, warps 1-2 MMA issuers (one per subtile), warps 3-6 / 7-10 epilogue groups
 constexpr int HALO_S = 2;           // subtiles sharing one weight stage
 
 struct UnitWalk {             // the same walk is replayed by the producer, the MMA issuers and the epilogue
@@ -95,8 +96,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint64_t* acc_full = b_empty + p.NB;                   // [2 buffers][2 subtiles]
     uint64_t* acc_empty = acc_full + 4;                    // [2 buffers]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2][2][N_TILE]
-    float* s_stats = s_affine + 4 * N_TILE;                // [4 warps][2][N_TILE]
+    float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2 groups][2][2][N_TILE]
+    float* s_stats = s_affine + 8 * N_TILE;                // [2 groups][4 warps][2][N_TILE]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u_lo = (int)((int64_t)blockIdx.x * p.units / gridDim.x);
@@ -112,7 +113,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int s = 0; s < p.NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < p.NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], HALO_S); }
         for (int s = 0; s < 4; ++s) mbar_init(&acc_full[s], 1);
-        for (int s = 0; s < 2; ++s) mbar_init(&acc_empty[s], 4);
+        for (int s = 0; s < 2; ++s) mbar_init(&acc_empty[s], 8);
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc<2 * ACC_COLS>(tmem_ptr);
@@ -127,6 +128,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    td::pdl_sync();              // everything above is on-chip setup; global memory is touched only below
 
     if (warp == 0) {
         if (elect_one()) {
@@ -245,7 +247,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int rem = r - n_rel * img_rows;
         const int h_rel = rem / p.ew;
         const int w_rel = rem - h_rel * p.ew;
-        const int tid = threadIdx.x - 96;
+        const int grp = (warp - 3) >> 2;             // epilogue group = the subtile of the pair it drains
+        const int tid = threadIdx.x - 96 - grp * 128;
+        const int bar_id = 1 + grp;
+        float* const aff_g = s_affine + grp * 4 * N_TILE;
+        float* const stats_g = s_stats + grp * 8 * N_TILE;
         UnitWalk wk{u_lo, u_hi, p.n_sub};
         int nt, s0, cnt;
         uint32_t gi = 0;
@@ -253,16 +259,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const long long t_start = clock64();
         while (wk.next(nt, s0, cnt)) {
             const uint32_t ab = gi & 1u;
-            float* sc_s = s_affine + ab * 2 * N_TILE;
+            float* sc_s = aff_g + ab * 2 * N_TILE;
             float* sh_s = sc_s + N_TILE;
             for (int c = tid; c < N_TILE; c += 128) {
                 sc_s[c] = p.scale ? __ldg(p.scale + nt * N_TILE + c) : 1.f;
                 sh_s[c] = p.shift ? __ldg(p.shift + nt * N_TILE + c) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int j = 0; j < HALO_S; ++j) {
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            {
+                const int j = grp;
                 { HALO_T0(); mbar_wait(&acc_full[ab * 2 + j], (gi >> 1) & 1u); HALO_ACC(w0); }
-                if (j >= cnt) continue;
+                if (j < cnt) {
                 tc_fence_after();
                 const int sub = s0 + j;
                 const int tw = sub % p.tiles_w, th = (sub / p.tiles_w) % p.tiles_h, tn = sub / (p.tiles_w * p.tiles_h);
@@ -309,22 +316,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         }
                         const float cs = warp_column_sums(v, lane);
                         const float cq = warp_column_sums(sq, lane);
-                        s_stats[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
-                        s_stats[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
+                        stats_g[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
+                        stats_g[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
                     }
                 }
                 if (p.stats) {
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     float* row = p.stats + (int64_t)sub * 2 * p.cout + nt * N_TILE;
                     for (int c = tid; c < 2 * N_TILE; c += 128) {
                         const int which = c / N_TILE, cc = c - which * N_TILE;
-                        const float t = (s_stats[(0 * 2 + which) * N_TILE + cc] + s_stats[(1 * 2 + which) * N_TILE + cc]) +
-                                        (s_stats[(2 * 2 + which) * N_TILE + cc] + s_stats[(3 * 2 + which) * N_TILE + cc]);
+                        const float t = (stats_g[(0 * 2 + which) * N_TILE + cc] + stats_g[(1 * 2 + which) * N_TILE + cc]) +
+                                        (stats_g[(2 * 2 + which) * N_TILE + cc] + stats_g[(3 * 2 + which) * N_TILE + cc]);
                         row[which * p.cout + cc] = t;
                     }
                     if (sub == 0)       // td_bn_finalize reads a zero "shift" row after the partial rows
                         for (int c = tid; c < N_TILE; c += 128) p.stats[(int64_t)p.n_sub * 2 * p.cout + nt * N_TILE + c] = 0.f;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
                 }
             }
             tc_fence_before();
@@ -332,7 +340,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
             ++gi;
         }
-        if ((p.dbg & 1) && tid == 0) {
+        if ((p.dbg & 1) && tid == 0 && grp == 0) {
             g_halo_dbg[blockIdx.x * 8 + 6] = w0;
             g_halo_dbg[blockIdx.x * 8 + 7] = clock64() - t_start - w0;
         }
@@ -435,8 +443,8 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->h_na = g.G == 3 ? 6 : 4;        // dx layout: a box group lasts only three taps, keep three groups in flight
     if (const char* e = getenv("TD_TC_HALO_NA")) { int v = atoi(e); if (v >= 2 && v <= 8) p->h_na = v; }
     const int b_stage = n_tile * 128;
-    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (4 + 8) * n_tile * 4 + 1024;
-    int nb = (220 * 1024 - fixed) / b_stage;
+    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (8 + 16) * n_tile * 4 + 1024;
+    int nb = (226 * 1024 - fixed) / (b_stage + 16);
     if (nb > 8) nb = 8;
     if (const char* e = getenv("TD_TC_HALO_NB")) { int v = atoi(e); if (v >= 2 && v <= nb) nb = v; }
     if (nb < 3) { p->halo = 0; return false; }
@@ -476,7 +484,7 @@ static int launch_halo(const td_conv_plan* p, const HaloParams& prm, cudaStream_
         configured_smem = p->smem_bytes;
     }
     const int grid = std::min(p->h_units, kNumSMs);
-    conv3x3_halo_kernel<N_TILE><<<grid, HALO_THREADS, p->smem_bytes, s>>>(p->tmap_x, p->tmap_w, prm);
+    td::launch(conv3x3_halo_kernel<N_TILE>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
     return launch_status("conv3x3_halo");
 }
 

@@ -25,6 +25,7 @@ constexpr int SM_BM = 64, SM_BN = 64, SM_BK = 16, SM_THREADS = 256;
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(SM_THREADS)
 conv3x3_simt_kernel(const td_conv3x3_desc d) {
+    td::pdl_sync();
     __shared__ float As[SM_BK][SM_BM + 4];
     __shared__ float Bs[SM_BK][SM_BN + 4];
     const Tin* __restrict__ x = reinterpret_cast<const Tin*>(d.x);
@@ -115,6 +116,7 @@ conv3x3_simt_kernel(const td_conv3x3_desc d) {
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256)
 conv3x3_first_kernel(const td_conv3x3_desc d) {
+    td::pdl_sync();
     extern __shared__ float wsm[];          // [cout][9*cin]
     const int K = 9 * d.cin;
     for (int i = threadIdx.x; i < d.cout * K; i += blockDim.x) wsm[i] = reinterpret_cast<const float*>(d.w)[i];
@@ -168,6 +170,7 @@ conv3x3_first_kernel(const td_conv3x3_desc d) {
 template <typename Tin, int COUT>
 __global__ void __launch_bounds__(256)
 conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
+    td::pdl_sync();
     extern __shared__ float wsm[];          // [COUT][9*cin]
     constexpr int V = Vec<Tin>::N;
     const int K = 9 * d.cin;
@@ -242,6 +245,7 @@ constexpr int FP = 4;
 template <typename Tout>
 __global__ void __launch_bounds__(256, 2)
 conv3x3_first1_kernel(const td_conv3x3_desc d) {
+    td::pdl_sync();
     const int g = threadIdx.x;
     const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [cout][9]
     float w[8][9], sc[8], sh[8];
@@ -300,6 +304,7 @@ constexpr int LP = 2;
 template <typename Tin>
 __global__ void __launch_bounds__(256)
 conv3x3_last1_kernel(const td_conv3x3_desc d) {
+    td::pdl_sync();
     constexpr int V = Vec<Tin>::N;
     const int L = blockDim.x, lane = threadIdx.x;
     const float* __restrict__ wt = reinterpret_cast<const float*>(d.w);          // [1][9][cin]
@@ -353,10 +358,10 @@ static int run_simt(const td_conv_plan* p, cudaStream_t s) {
     const td_conv3x3_desc& d = p->d;
     const int64_t M = (int64_t)d.batch * d.height * d.width;
     dim3 grid((unsigned)ceil_div(M, SM_BM), (unsigned)ceil_div(d.cout, SM_BN));
-    if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) conv3x3_simt_kernel<float, float><<<grid, SM_THREADS, 0, s>>>(d);
-    else if (d.x_dtype == TD_BF16 && d.y_dtype == TD_BF16) conv3x3_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, SM_THREADS, 0, s>>>(d);
-    else if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) conv3x3_simt_kernel<float, __nv_bfloat16><<<grid, SM_THREADS, 0, s>>>(d);
-    else conv3x3_simt_kernel<__nv_bfloat16, float><<<grid, SM_THREADS, 0, s>>>(d);
+    if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) td::launch(conv3x3_simt_kernel<float, float>, td::LaunchCfg(grid, SM_THREADS, 0, s), d);
+    else if (d.x_dtype == TD_BF16 && d.y_dtype == TD_BF16) td::launch(conv3x3_simt_kernel<__nv_bfloat16, __nv_bfloat16>, td::LaunchCfg(grid, SM_THREADS, 0, s), d);
+    else if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) td::launch(conv3x3_simt_kernel<float, __nv_bfloat16>, td::LaunchCfg(grid, SM_THREADS, 0, s), d);
+    else td::launch(conv3x3_simt_kernel<__nv_bfloat16, float>, td::LaunchCfg(grid, SM_THREADS, 0, s), d);
     return launch_status("conv3x3_simt");
 }
 
@@ -368,16 +373,16 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
         dim3 block((unsigned)groups, (unsigned)std::max(1, 256 / groups));
         const int items = d.batch * d.height * ((d.width + FP - 1) / FP);
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, block.y), kNumSMs * 4));
-        if (d.y_dtype == TD_BF16) conv3x3_first1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
-        else conv3x3_first1_kernel<float><<<grid, block, 0, s>>>(d);
+        if (d.y_dtype == TD_BF16) td::launch(conv3x3_first1_kernel<__nv_bfloat16>, td::LaunchCfg(grid, block, 0, s), d);
+        else td::launch(conv3x3_first1_kernel<float>, td::LaunchCfg(grid, block, 0, s), d);
         return launch_status("conv3x3_first1");
     }
     if (d.cin <= 8) {
         const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
         const int64_t items = M * (d.cout / 8);
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(items, 256), kNumSMs * 8));
-        if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) conv3x3_first_kernel<float, __nv_bfloat16><<<grid, 256, smem, s>>>(d);
-        else if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) conv3x3_first_kernel<float, float><<<grid, 256, smem, s>>>(d);
+        if (d.x_dtype == TD_F32 && d.y_dtype == TD_BF16) td::launch(conv3x3_first_kernel<float, __nv_bfloat16>, td::LaunchCfg(grid, 256, smem, s), d);
+        else if (d.x_dtype == TD_F32 && d.y_dtype == TD_F32) td::launch(conv3x3_first_kernel<float, float>, td::LaunchCfg(grid, 256, smem, s), d);
         else { set_error("direct first conv: unsupported dtype combination"); return TD_ERR_UNSUPPORTED; }
         return launch_status("conv3x3_first");
     }
@@ -388,15 +393,15 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
         dim3 block((unsigned)Ln, (unsigned)(256 / Ln));
         const int64_t total = (int64_t)d.batch * d.height * d.width;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, (int64_t)block.y * LP), kNumSMs * 8));
-        if (d.x_dtype == TD_BF16) conv3x3_last1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
-        else conv3x3_last1_kernel<float><<<grid, block, 0, s>>>(d);
+        if (d.x_dtype == TD_BF16) td::launch(conv3x3_last1_kernel<__nv_bfloat16>, td::LaunchCfg(grid, block, 0, s), d);
+        else td::launch(conv3x3_last1_kernel<float>, td::LaunchCfg(grid, block, 0, s), d);
         return launch_status("conv3x3_last1");
     }
     int L = d.cin / V;
     if (L > 32) L = 32;
     const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(M * L, 256), kNumSMs * 8));
-#define TD_LAST(T, CO) conv3x3_last_kernel<T, CO><<<grid, 256, smem, s>>>(d, L)
+#define TD_LAST(T, CO) td::launch(conv3x3_last_kernel<T, CO>, td::LaunchCfg(grid, 256, smem, s), d, L)
     if (d.x_dtype == TD_BF16) {
         if (d.cout == 1) TD_LAST(__nv_bfloat16, 1);
         else if (d.cout == 4) TD_LAST(__nv_bfloat16, 4);

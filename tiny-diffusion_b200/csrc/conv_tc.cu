@@ -84,16 +84,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<BLOCK_N>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    td::pdl_sync();              // everything above is on-chip setup; global memory is touched only below
     if (warp >= 2) {
         for (int c = threadIdx.x - 64; c < BLOCK_N; c += TC_THREADS - 64) {
             s_scale[c] = p.scale ? __ldg(p.scale + nt * BLOCK_N + c) : 1.f;
             s_shift[c] = p.shift ? __ldg(p.shift + nt * BLOCK_N + c) : 0.f;
         }
     }
-    tc_fence_before();
     __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -227,6 +229,7 @@ template <typename Tout>
 __global__ void __launch_bounds__(256)
 conv_splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t pixels, int cout, const float* __restrict__ scale,
                           const float* __restrict__ shift, int relu, Tout* __restrict__ y, int ldy, int y_coff) {
+    td::pdl_sync();
     const int cq = cout >> 2;
     const int64_t total = pixels * cq;
     const int64_t slice = pixels * cout;
@@ -385,17 +388,17 @@ static int launch_tc(const td_conv_plan* p, const TcParams& prm, cudaStream_t s)
         configured_smem = p->smem_bytes;
     }
     dim3 grid((unsigned)(p->tiles_w * p->tiles_h * p->tiles_n), (unsigned)p->n_tiles, (unsigned)p->split_k);
-    conv3x3_tc_kernel<BLOCK_N><<<grid, TC_THREADS, p->smem_bytes, s>>>(p->tmap_x, p->tmap_w, prm);
+    td::launch(conv3x3_tc_kernel<BLOCK_N>, td::LaunchCfg(grid, TC_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
     int st = launch_status("conv3x3_tc");
     if (st != TD_OK || p->split_k == 1) return st;
     const td_conv3x3_desc& d = p->d;
     const int64_t pixels = (int64_t)d.batch * d.height * d.width;
     const int rgrid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(pixels * (d.cout / 4), 256), kNumSMs * 8));
     if (d.y_dtype == TD_BF16)
-        conv_splitk_reduce_kernel<__nv_bfloat16><<<rgrid, 256, 0, s>>>(d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
+        td::launch(conv_splitk_reduce_kernel<__nv_bfloat16>, td::LaunchCfg(rgrid, 256, 0, s), d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
                                                                        d.relu, (__nv_bfloat16*)d.y, d.ldy, d.y_coff);
     else
-        conv_splitk_reduce_kernel<float><<<rgrid, 256, 0, s>>>(d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
+        td::launch(conv_splitk_reduce_kernel<float>, td::LaunchCfg(rgrid, 256, 0, s), d.splitk_ws, p->split_k, pixels, d.cout, d.scale, d.shift,
                                                                d.relu, (float*)d.y, d.ldy, d.y_coff);
     return launch_status("conv_splitk_reduce");
 }

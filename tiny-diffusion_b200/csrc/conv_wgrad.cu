@@ -14,6 +14,7 @@ constexpr int WG_BM = 64, WG_BN = 64, WG_BK = 16, WG_THREADS = 256;
 template <typename Tx, typename Tdy>
 __global__ void __launch_bounds__(WG_THREADS)
 wgrad_simt_kernel(const td_wgrad_desc d, int pixels_per_split) {
+    td::pdl_sync();
     __shared__ float As[WG_BK][WG_BM + 4];   // dY  [k = pixel][i = cout]
     __shared__ float Bs[WG_BK][WG_BN + 4];   // X   [k = pixel][j = tap*cin + c]
     const Tx* __restrict__ x = reinterpret_cast<const Tx*>(d.x);
@@ -103,6 +104,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_narrow_kernel(const T* __restrict__ wide, int ldw, int w_coff, int cw, const float* __restrict__ narrow, int cn,
                     int B, int H, int W, int narrow_is_dy, int cin, int cout, float* __restrict__ ws) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     extern __shared__ float red[];                  // [rows][cw]
     const int lanesC = cw / V;
@@ -179,6 +181,7 @@ static bool narrow_ok(const td_wgrad_desc& d, int* grid_x) {
 constexpr int WR_C = 32;
 __global__ void __launch_bounds__(9 * WR_C)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
+    td::pdl_sync();
     __shared__ float tile[9][WR_C + 1];
     const int o = blockIdx.y;
     const int c0 = blockIdx.x * WR_C;
@@ -217,6 +220,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
 template <typename T>
 __global__ void __launch_bounds__(256)
 pack_weight_dgrad_kernel(const float* __restrict__ oihw, T* __restrict__ out, int cout, int cin) {
+    td::pdl_sync();
     const int64_t total = (int64_t)cout * 9 * cin;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int o = (int)(e % cout);
@@ -290,11 +294,11 @@ extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
         const int ldw = fin ? d.ldx : d.lddy, wcoff = fin ? d.x_coff : d.dy_coff;
         dim3 grid((unsigned)gx, (unsigned)cn);
         if (wdt == TD_BF16)
-            wgrad_narrow_kernel<__nv_bfloat16><<<grid, 256, smem, s>>>((const __nv_bfloat16*)wide, ldw, wcoff, cw, narrow, cn,
+            td::launch(wgrad_narrow_kernel<__nv_bfloat16>, td::LaunchCfg(grid, 256, smem, s), (const __nv_bfloat16*)wide, ldw, wcoff, cw, narrow, cn,
                                                                         d.batch, d.height, d.width, fin ? 1 : 0, d.cin, d.cout,
                                                                         d.workspace);
         else
-            wgrad_narrow_kernel<float><<<grid, 256, smem, s>>>((const float*)wide, ldw, wcoff, cw, narrow, cn, d.batch,
+            td::launch(wgrad_narrow_kernel<float>, td::LaunchCfg(grid, 256, smem, s), (const float*)wide, ldw, wcoff, cw, narrow, cn, d.batch,
                                                                d.height, d.width, fin ? 1 : 0, d.cin, d.cout, d.workspace);
         int st = launch_status("wgrad_narrow");
         if (st != TD_OK) return st;
@@ -302,15 +306,15 @@ extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
         const int64_t P = (int64_t)d.batch * d.height * d.width;
         const int per = (int)(ceil_div(ceil_div(P, p->splits), WG_BK) * WG_BK);
         dim3 grid((unsigned)ceil_div(9 * d.cin, WG_BN), (unsigned)ceil_div(d.cout, WG_BM), (unsigned)p->splits);
-        if (d.x_dtype == TD_F32 && d.dy_dtype == TD_F32) wgrad_simt_kernel<float, float><<<grid, WG_THREADS, 0, s>>>(d, per);
-        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_BF16) wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, WG_THREADS, 0, s>>>(d, per);
-        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_F32) wgrad_simt_kernel<__nv_bfloat16, float><<<grid, WG_THREADS, 0, s>>>(d, per);
-        else wgrad_simt_kernel<float, __nv_bfloat16><<<grid, WG_THREADS, 0, s>>>(d, per);
+        if (d.x_dtype == TD_F32 && d.dy_dtype == TD_F32) td::launch(wgrad_simt_kernel<float, float>, td::LaunchCfg(grid, WG_THREADS, 0, s), d, per);
+        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_BF16) td::launch(wgrad_simt_kernel<__nv_bfloat16, __nv_bfloat16>, td::LaunchCfg(grid, WG_THREADS, 0, s), d, per);
+        else if (d.x_dtype == TD_BF16 && d.dy_dtype == TD_F32) td::launch(wgrad_simt_kernel<__nv_bfloat16, float>, td::LaunchCfg(grid, WG_THREADS, 0, s), d, per);
+        else td::launch(wgrad_simt_kernel<float, __nv_bfloat16>, td::LaunchCfg(grid, WG_THREADS, 0, s), d, per);
         int st = launch_status("wgrad_simt");
         if (st != TD_OK) return st;
     }
     dim3 rgrid((unsigned)ceil_div(d.cin, WR_C), (unsigned)d.cout);
-    wgrad_reduce_kernel<<<rgrid, 9 * WR_C, 0, s>>>(d.workspace, p->splits, d.cout, d.cin, d.dw);
+    td::launch(wgrad_reduce_kernel, td::LaunchCfg(rgrid, 9 * WR_C, 0, s), d.workspace, p->splits, d.cout, d.cin, d.dw);
     return launch_status("wgrad_reduce");
 }
 
@@ -322,9 +326,9 @@ extern "C" int td_pack_conv_weight_dgrad(const float* oihw, void* out, int out_d
     const int64_t n = (int64_t)cout * cin * 9;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), kNumSMs * 16));
     if (out_dtype == TD_BF16)
-        pack_weight_dgrad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(oihw, (__nv_bfloat16*)out, cout, cin);
+        td::launch(pack_weight_dgrad_kernel<__nv_bfloat16>, td::LaunchCfg(grid, 256, 0, (cudaStream_t)stream), oihw, (__nv_bfloat16*)out, cout, cin);
     else if (out_dtype == TD_F32)
-        pack_weight_dgrad_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(oihw, (float*)out, cout, cin);
+        td::launch(pack_weight_dgrad_kernel<float>, td::LaunchCfg(grid, 256, 0, (cudaStream_t)stream), oihw, (float*)out, cout, cin);
     else
         TD_CHECK_ARG(false, "td_pack_conv_weight_dgrad: unknown dtype %d", out_dtype);
     return launch_status("pack_conv_weight_dgrad");

@@ -105,6 +105,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    td::pdl_sync();              // everything above is on-chip setup; global memory is touched only below
 
     if (warp == 0) {
         if (elect_one()) {
@@ -385,7 +386,7 @@ static int launch_wg(const td_wgrad_plan* p, const WgParams& prm, cudaStream_t s
         configured_smem = p->smem_bytes;
     }
     dim3 grid((unsigned)(p->m_tiles * p->n_tiles * (9 / TAPS)), (unsigned)p->splits);
-    wgrad_tc_kernel<BLOCK_N, TAPS><<<grid, WG_TC_THREADS, p->smem_bytes, s>>>(p->tmap_m, p->tmap_n, prm);
+    td::launch(wgrad_tc_kernel<BLOCK_N, TAPS>, td::LaunchCfg(grid, WG_TC_THREADS, p->smem_bytes, s), p->tmap_m, p->tmap_n, prm);
     return launch_status("wgrad_tc");
 }
 

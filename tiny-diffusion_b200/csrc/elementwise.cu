@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(kEwThreads)
 qsample_kernel(const float* __restrict__ x0, float* __restrict__ noise, const int64_t* __restrict__ t,
                const float* __restrict__ abar, float* __restrict__ x_t, int64_t per_sample4,
                int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
     const int64_t b = blockIdx.y;
     int tt = (int)t[b];
     tt = min(max(tt, 0), num_timesteps - 1);
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(kEwThreads)
 qsample_scalar_kernel(const float* __restrict__ x0, float* __restrict__ noise, const int64_t* __restrict__ t,
                       const float* __restrict__ abar, float* __restrict__ x_t, int64_t batch,
                       int64_t per_sample, int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
     const int64_t total = batch * per_sample;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(kEwThreads)
 mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ grad,
                 float* __restrict__ loss_out, float* __restrict__ partials, unsigned int* __restrict__ counter,
                 int64_t n, float inv_n) {
+    td::pdl_sync();
     float acc = 0.f;
     const float g2 = 2.0f * inv_n;
     const int64_t n4 = n >> 2;
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(kEwThreads)
 psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z_base,
                int64_t z_step_stride, const float* __restrict__ coef, const int32_t* __restrict__ t_dev, int64_t n,
                const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
     const int t = t_dev[0];
     const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
     const float4 c = reinterpret_cast<const float4*>(coef)[t];
@@ -171,7 +175,50 @@ psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float
     }
 }
 
-__global__ void counter_add_kernel(int32_t* c, int32_t delta) { c[0] += delta; }
+// Classifier-free-guidance reverse step (extension; the reference has no guidance).  The denoiser ran
+// on a doubled batch: rows [0, n) with the labels, rows [n, 2n) with the null label, both halves holding the same x.
+//   eps = eps_u + w*(eps_c - eps_u);   x <- c1*(x - c2*eps) + c3*z,   written to both halves (same noise for both).
+// Separate roundings, so the result equals the torch composition bit for bit.  20 algorithmic bytes per element of n.
+__global__ void __launch_bounds__(kEwThreads)
+psample_cfg_kernel(float* __restrict__ x, const float* __restrict__ eps, int64_t n, float w,
+                   const float* __restrict__ z_base, int64_t z_step_stride, const float* __restrict__ coef,
+                   const int32_t* __restrict__ t_dev, const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
+    const int t = t_dev[0];
+    const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
+    const float4 c = reinterpret_cast<const float4*>(coef)[t];
+    const float c1 = c.x, c2 = c.y, c3 = c.z;
+    const bool use_noise = (t > 0);
+    const int64_t n4 = n >> 2;                         // n is a multiple of 4 (checked on the host)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 xv = reinterpret_cast<const float4*>(x)[i];
+        const float4 ec = reinterpret_cast<const float4*>(eps)[i];
+        const float4 eu = reinterpret_cast<const float4*>(eps + n)[i];
+        float zz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (use_noise) {
+            if (z) {
+                const float4 zv = reinterpret_cast<const float4*>(z)[i];
+                zz[0] = zv.x; zz[1] = zv.y; zz[2] = zv.z; zz[3] = zv.w;
+            } else if (seed_ptr) {
+                Philox rng(seed_ptr[0]);
+                rng.normal4((uint64_t)i, seed_ptr[1] + (uint64_t)t, zz);
+            }
+        }
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, cs[4] = {ec.x, ec.y, ec.z, ec.w}, us[4] = {eu.x, eu.y, eu.z, eu.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e = __fadd_rn(us[k], __fmul_rn(w, __fsub_rn(cs[k], us[k])));
+            o[k] = __fadd_rn(__fmul_rn(c1, __fsub_rn(xs[k], __fmul_rn(c2, e))), __fmul_rn(c3, zz[k]));
+        }
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(x)[i] = ov;
+        reinterpret_cast<float4*>(x + n)[i] = ov;
+    }
+}
+
+__global__ void counter_add_kernel(int32_t* c, int32_t delta) {
+    td::pdl_sync(); c[0] += delta; }
 
 // Fused multi-tensor Adam (torch.optim.Adam defaults; diffusion.py:211,236).
 __global__ void __launch_bounds__(kEwThreads)
@@ -180,6 +227,7 @@ adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__
                   const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_offset,
                   int64_t chunk_elems, const int32_t* __restrict__ step_dev, float lr, float beta1, float beta2,
                   float eps, const float* __restrict__ grad_scale_dev, void* const* __restrict__ bf16_shadow) {
+    td::pdl_sync();
     const int tid = chunk_tensor[blockIdx.x];
     const int64_t off = chunk_offset[blockIdx.x];
     const int64_t n = min(chunk_elems, numel[tid] - off);
@@ -242,6 +290,7 @@ adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__
 
 __global__ void __launch_bounds__(kEwThreads)
 cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    td::pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = __float2bfloat16_rn(src[i]);
 }
@@ -270,9 +319,9 @@ extern "C" int td_qsample(const float* x0, float* noise, const int64_t* t, const
         int64_t ps4 = per_sample / 4;
         int gx = (int)std::min<int64_t>(ceil_div(ps4, kEwThreads), std::max<int64_t>(1, (kNumSMs * 16) / batch));
         dim3 grid(gx, (unsigned)batch);
-        qsample_kernel<<<grid, kEwThreads, 0, s>>>(x0, noise, t, alphas_cumprod, x_t, ps4, num_timesteps, seed_ptr);
+        td::launch(qsample_kernel, td::LaunchCfg(grid, kEwThreads, 0, s), x0, noise, t, alphas_cumprod, x_t, ps4, num_timesteps, seed_ptr);
     } else {
-        qsample_scalar_kernel<<<ew_grid(batch * per_sample), kEwThreads, 0, s>>>(
+        td::launch(qsample_scalar_kernel, td::LaunchCfg(ew_grid(batch * per_sample), kEwThreads, 0, s), 
             x0, noise, t, alphas_cumprod, x_t, batch, per_sample, num_timesteps, seed_ptr);
     }
     return launch_status("qsample");
@@ -285,7 +334,7 @@ extern "C" int td_mse_grad(const float* pred, const float* target, float* grad, 
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(pred && target && loss_out && partials && counter, "td_mse_grad: null pointer");
     TD_CHECK_ARG(n > 0, "td_mse_grad: n must be positive");
-    mse_grad_kernel<<<(int)td_mse_num_partials(n), kEwThreads, 0, (cudaStream_t)stream>>>(
+    td::launch(mse_grad_kernel, td::LaunchCfg((int)td_mse_num_partials(n), kEwThreads, 0, (cudaStream_t)stream), 
         pred, target, grad, loss_out, partials, counter, n, inv_n);
     return launch_status("mse_grad");
 }
@@ -295,15 +344,26 @@ extern "C" int td_psample_step(float* x, const float* eps, const float* z, int64
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step: null pointer");
     TD_CHECK_ARG(n > 0, "td_psample_step: n must be positive");
-    psample_kernel<<<ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream>>>(
+    td::launch(psample_kernel, td::LaunchCfg(ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream), 
         x, eps, z, z_step_stride, coef, t_dev, n, seed_ptr);
     return launch_status("psample_step");
+}
+
+extern "C" int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z,
+                                   int64_t z_step_stride, const float* coef, const int32_t* t_dev,
+                                   const uint64_t* seed_ptr, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step_cfg: null pointer");
+    TD_CHECK_ARG(n > 0 && n % 4 == 0, "td_psample_step_cfg: n (elements of one half) must be a positive multiple of 4");
+    td::launch(psample_cfg_kernel, td::LaunchCfg(ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)stream), x, eps, n, guidance, z,
+               z_step_stride, coef, t_dev, seed_ptr);
+    return launch_status("psample_step_cfg");
 }
 
 extern "C" int td_counter_add(int32_t* t_dev, int32_t delta, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(t_dev, "td_counter_add: null pointer");
-    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(t_dev, delta);
+    td::launch(counter_add_kernel, td::LaunchCfg(1, 1, 0, (cudaStream_t)stream), t_dev, delta);
     return launch_status("counter_add");
 }
 
@@ -316,7 +376,7 @@ extern "C" int td_adam_multi(float* const* p, const float* const* g, float* cons
     TD_CHECK_ARG(p && g && m && v && numel && chunk_tensor && chunk_offset && step_dev, "td_adam_multi: null pointer");
     TD_CHECK_ARG(chunk_elems > 0 && chunk_elems % 4 == 0, "td_adam_multi: chunk_elems must be a positive multiple of 4");
     if (num_chunks == 0) return TD_OK;
-    adam_multi_kernel<<<(unsigned)num_chunks, kEwThreads, 0, (cudaStream_t)stream>>>(
+    td::launch(adam_multi_kernel, td::LaunchCfg((unsigned)num_chunks, kEwThreads, 0, (cudaStream_t)stream), 
         p, g, m, v, numel, chunk_tensor, chunk_offset, chunk_elems, step_dev, lr, beta1, beta2, eps,
         grad_scale_dev, bf16_shadow);
     return launch_status("adam_multi");
@@ -326,6 +386,6 @@ extern "C" int td_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void*
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(src && dst && n >= 0, "td_cast_f32_to_bf16: bad args");
     if (n == 0) return TD_OK;
-    cast_bf16_kernel<<<ew_grid(n), kEwThreads, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+    td::launch(cast_bf16_kernel, td::LaunchCfg(ew_grid(n), kEwThreads, 0, (cudaStream_t)stream), src, (__nv_bfloat16*)dst, n);
     return launch_status("cast_bf16");
 }

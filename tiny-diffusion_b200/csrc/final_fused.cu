@@ -58,6 +58,7 @@ __device__ inline void reduce_taps(float (&acc)[9], int lane) {
 template <typename T, int L>
 __global__ void __launch_bounds__(256, 2)
 final_resize_conv_kernel(const FinalArgs a) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     extern __shared__ float sm[];
     const int bands = (a.Ho + a.BH - 1) / a.BH;
@@ -188,7 +189,7 @@ extern "C" int td_final_resize_conv(const void* x, int dtype, int ldx, int x_cof
             TD_CUDA(cudaFuncSetAttribute(final_resize_conv_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             cfg = smem;                                                                                                       \
         }                                                                                                                     \
-        final_resize_conv_kernel<T, LL><<<grid, 256, smem, s>>>(a);                                                           \
+        td::launch(final_resize_conv_kernel<T, LL>, td::LaunchCfg(grid, 256, smem, s), a);                                                           \
     } while (0)
 #define TD_FINAL_L(T)                                       \
     switch (L) {                                            \

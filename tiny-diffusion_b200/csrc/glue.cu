@@ -38,6 +38,7 @@ static inline dim3 row_block(int cv) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
     const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
@@ -135,6 +136,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
              int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs, int nseg) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
     const int Ct = Cu + Cs;
@@ -180,6 +182,7 @@ upcat_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float*
 template <typename T>
 __global__ void __launch_bounds__(256)
 resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C, int nseg) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
     build_col_table(col, Wi, Wo);
@@ -216,6 +219,7 @@ static inline int walk_segments(int64_t threads, int width) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 pack_weight_kernel(const float* __restrict__ oihw, T* __restrict__ ohwi, int cout, int cin) {
+    td::pdl_sync();
     const int64_t total = (int64_t)cout * 9 * cin;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)total; i += gridDim.x * blockDim.x) {
         int c = (int)(i % cin);
@@ -234,6 +238,7 @@ struct PackEntry { const float* src; __nv_bfloat16* fwd; __nv_bfloat16* dgrad; i
 constexpr int PK_T = 32;
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const PackEntry* __restrict__ tab, int n_entries) {
+    td::pdl_sync();
     __shared__ float tile[PK_T][PK_T * 9 + 1];
     int e = 0;
     while (e + 1 < n_entries && (int)blockIdx.x >= tab[e + 1].tile_begin) ++e;
@@ -263,6 +268,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
                                const float* __restrict__ mean, const float* __restrict__ var,
                                const float* __restrict__ conv_bias, float eps, float* __restrict__ scale,
                                float* __restrict__ shift, int c) {
+    td::pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     const float s = gamma[i] / sqrtf(var[i] + eps);
@@ -288,11 +294,11 @@ extern "C" int td_maxpool2_fwd(const void* x, void* y, int dtype, int batch, int
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_maxpool2_fwd: channels must be a multiple of 8 for bf16");
-        maxpool2_kernel<__nv_bfloat16><<<batch * ho, row_block(c / 8), 0, s>>>(
+        td::launch(maxpool2_kernel<__nv_bfloat16>, td::LaunchCfg(batch * ho, row_block(c / 8), 0, s), 
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, h, w, c, ho, wo);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_maxpool2_fwd: channels must be a multiple of 4 for fp32");
-        maxpool2_kernel<float><<<batch * ho, row_block(c / 4), 0, s>>>(
+        td::launch(maxpool2_kernel<float>, td::LaunchCfg(batch * ho, row_block(c / 4), 0, s), 
             (const float*)x, (float*)y, batch, h, w, c, ho, wo);
     } else {
         TD_CHECK_ARG(false, "td_maxpool2_fwd: unknown dtype %d", dtype);
@@ -313,7 +319,7 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
         const dim3 blk = walk_block(cvh);
         const int nseg = walk_segments((int64_t)batch * ho * cvh * 2, wo);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(cvh, blk.x), 2);
-        upcat_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
+        td::launch(upcat_kernel<__nv_bfloat16>, td::LaunchCfg(grd, blk, 0, s), 
             (const __nv_bfloat16*)low, (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out,
             batch, ho, wo, cu, hs, ws, cs, nseg);
     } else if (dtype == TD_F32) {
@@ -322,7 +328,7 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
         const dim3 blk = walk_block(cvh);
         const int nseg = walk_segments((int64_t)batch * ho * cvh * 2, wo);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(cvh, blk.x), 2);
-        upcat_kernel<float><<<grd, blk, 0, s>>>(
+        td::launch(upcat_kernel<float>, td::LaunchCfg(grd, blk, 0, s), 
             (const float*)low, (const float*)skip, temb, ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs, nseg);
     } else {
         TD_CHECK_ARG(false, "td_upcat_fwd: unknown dtype %d", dtype);
@@ -340,14 +346,14 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
         const dim3 blk = walk_block(c / 8);
         const int nseg = walk_segments((int64_t)batch * ho * (c / 8), wo);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(c / 8, blk.x), 1);
-        resize_kernel<__nv_bfloat16><<<grd, blk, 0, s>>>(
+        td::launch(resize_kernel<__nv_bfloat16>, td::LaunchCfg(grd, blk, 0, s), 
             (const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c, nseg);
     } else if (dtype == TD_F32) {
         TD_CHECK_ARG(c % 4 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 4 for fp32");
         const dim3 blk = walk_block(c / 4);
         const int nseg = walk_segments((int64_t)batch * ho * (c / 4), wo);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * ho, blk.y) * nseg), (unsigned)ceil_div(c / 4, blk.x), 1);
-        resize_kernel<float><<<grd, blk, 0, s>>>((const float*)x, (float*)y, batch, hi, wi, ho, wo, c, nseg);
+        td::launch(resize_kernel<float>, td::LaunchCfg(grd, blk, 0, s), (const float*)x, (float*)y, batch, hi, wi, ho, wo, c, nseg);
     } else {
         TD_CHECK_ARG(false, "td_resize_bilinear_fwd: unknown dtype %d", dtype);
     }
@@ -359,9 +365,9 @@ extern "C" int td_pack_conv_weight(const float* oihw, void* ohwi, int out_dtype,
     TD_CHECK_ARG(oihw && ohwi && cout > 0 && cin > 0, "td_pack_conv_weight: bad args");
     const int64_t n = (int64_t)cout * cin * 9;
     if (out_dtype == TD_BF16)
-        pack_weight_kernel<__nv_bfloat16><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(oihw, (__nv_bfloat16*)ohwi, cout, cin);
+        td::launch(pack_weight_kernel<__nv_bfloat16>, td::LaunchCfg(grid_for(n), kThreads, 0, (cudaStream_t)stream), oihw, (__nv_bfloat16*)ohwi, cout, cin);
     else if (out_dtype == TD_F32)
-        pack_weight_kernel<float><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(oihw, (float*)ohwi, cout, cin);
+        td::launch(pack_weight_kernel<float>, td::LaunchCfg(grid_for(n), kThreads, 0, (cudaStream_t)stream), oihw, (float*)ohwi, cout, cin);
     else
         TD_CHECK_ARG(false, "td_pack_conv_weight: unknown dtype %d", out_dtype);
     return launch_status("pack_conv_weight");
@@ -370,7 +376,7 @@ extern "C" int td_pack_conv_weight(const float* oihw, void* ohwi, int out_dtype,
 extern "C" int td_pack_conv_weights_multi(const void* table, int n_entries, int total_tiles, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(table && n_entries > 0 && total_tiles > 0, "td_pack_conv_weights_multi: bad args");
-    pack_weights_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackEntry*>(table), n_entries);
+    td::launch(pack_weights_multi_kernel, td::LaunchCfg(total_tiles, 256, 0, (cudaStream_t)stream), reinterpret_cast<const PackEntry*>(table), n_entries);
     return launch_status("pack_conv_weights_multi");
 }
 
@@ -378,6 +384,6 @@ extern "C" int td_bn_fold(const float* gamma, const float* beta, const float* me
                           const float* conv_bias, float eps, float* scale, float* shift, int c, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(gamma && beta && mean && var && scale && shift && c > 0, "td_bn_fold: bad args");
-    bn_fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, conv_bias, eps, scale, shift, c);
+    td::launch(bn_fold_kernel, td::LaunchCfg((c + 127) / 128, 128, 0, (cudaStream_t)stream), gamma, beta, mean, var, conv_bias, eps, scale, shift, c);
     return launch_status("bn_fold");
 }

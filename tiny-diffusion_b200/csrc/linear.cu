@@ -41,6 +41,7 @@ __device__ inline float act_grad(float v, int act) {
 
 __global__ void __launch_bounds__(G_THREADS)
 gemm_f32_kernel(const td_gemm_args g) {
+    td::pdl_sync();
     __shared__ float As[2][G_BK][G_BM + 4];
     __shared__ float Bs[2][G_BK][G_BN + 4];
     const int tid = threadIdx.x;
@@ -166,6 +167,7 @@ __device__ inline void gemm_store(const td_gemm_args& g, int gi, int gj, float a
 constexpr int S_BM = 32, S_BN = 32, S_BK = 32;
 __global__ void __launch_bounds__(256)
 gemm_f32_small_kernel(const td_gemm_args g) {
+    td::pdl_sync();
     __shared__ float As[S_BK][S_BM + 1];
     __shared__ float Bs[S_BK][S_BN + 1];
     const int tid = threadIdx.x;
@@ -210,6 +212,7 @@ gemm_f32_small_kernel(const td_gemm_args g) {
 // The sampler's per-step conditioning head is this shape (every sample shares t).
 __global__ void __launch_bounds__(256)
 gemv_f32_kernel(const td_gemm_args g) {
+    td::pdl_sync();
     const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (j >= g.N) return;
@@ -230,6 +233,7 @@ gemv_f32_kernel(const td_gemm_args g) {
 // second pass of the deterministic split-K: fixed-order sum over slices + the same epilogue
 __global__ void __launch_bounds__(256)
 gemm_splitk_reduce_kernel(const td_gemm_args g, int nz) {
+    td::pdl_sync();
     const int64_t total = (int64_t)g.M * g.N;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int gi = (int)(e / g.N), gj = (int)(e % g.N);
@@ -250,6 +254,7 @@ gemm_splitk_reduce_kernel(const td_gemm_args g, int nz) {
 // out[j] (+)= sum_i x[i, j]      (bias gradients); one warp-row per 32 columns, fixed order
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int M, int N, int accumulate) {
+    td::pdl_sync();
     __shared__ float part[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
@@ -269,6 +274,7 @@ colsum_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out,
 // dx = dy * act'(pre)
 __global__ void __launch_bounds__(256)
 act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, float* __restrict__ dx, int64_t n, int act) {
+    td::pdl_sync();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dx[i] = dy[i] * act_grad(pre[i], act);
 }
@@ -277,6 +283,7 @@ act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, floa
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ idx, float* __restrict__ out,
                      int M, int D, int accumulate) {
+    td::pdl_sync();
     const int c = blockIdx.x;
     for (int j = threadIdx.x; j < D; j += blockDim.x) {
         float s = 0.f;
@@ -292,6 +299,7 @@ embedding_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int64_t* __
 __global__ void __launch_bounds__(256)
 time_features_kernel(const int64_t* __restrict__ t, const int32_t* __restrict__ t_dev, float* __restrict__ out, int B,
                      int D, int mode) {
+    td::pdl_sync();
     const int width = (mode == 2) ? D : 1;
     const int64_t total = (int64_t)B * width;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int D,
                      float eps) {
+    td::pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -342,6 +351,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dx, int M, int D) {
+    td::pdl_sync();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_params_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                             const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
                             int D) {
+    td::pdl_sync();
     __shared__ float pg[8][33], pb[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;
@@ -396,6 +407,7 @@ bn1d_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restric
                 float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
                 float* __restrict__ save_rstd, float* __restrict__ y, int64_t ldy, int M, int N, float eps,
                 float momentum, int training, int relu) {
+    td::pdl_sync();
     __shared__ float part[8][33];
     __shared__ float s_mean[32], s_rstd[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -458,6 +470,7 @@ bn1d_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restr
                 const float* __restrict__ y_out, int64_t ldy, const float* __restrict__ gamma,
                 const float* __restrict__ save_mean, const float* __restrict__ save_rstd, float* __restrict__ dx,
                 int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int N, int relu) {
+    td::pdl_sync();
     __shared__ float p1[8][33], p2[8][33];
     __shared__ float s1[32], s2[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -496,6 +509,7 @@ bn1d_bwd_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restr
 __global__ void __launch_bounds__(256)
 add2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols,
              int accumulate) {
+    td::pdl_sync();
     const int64_t total = (int64_t)rows * cols;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int i = (int)(e / cols), j = (int)(e % cols);
@@ -513,6 +527,7 @@ add2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst
 __global__ void __launch_bounds__(256)
 dropout_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t ldo, int rows, int cols,
                int group, float p, const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
     const Philox rng(seed_ptr[0]);
     const uint64_t sub = seed_ptr[1];
     const int gcols = cols / group;
@@ -555,33 +570,33 @@ extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
     const int64_t ws = td_gemm_f32_workspace(a->M, a->N, a->K);
     if (ws > 0 && a->splitk_ws) nz = (int)(ws / ((int64_t)a->M * a->N));
     if (nz == 1 && a->M <= 4 && a->a_cs == 1 && a->b_rs == 1) {
-        gemv_f32_kernel<<<(unsigned)ceil_div(a->N, 8), 256, 0, s>>>(*a);
+        td::launch(gemv_f32_kernel, td::LaunchCfg((unsigned)ceil_div(a->N, 8), 256, 0, s), *a);
         return launch_status("gemv_f32");
     }
     if (nz == 1 && ceil_div(a->N, G_BN) * ceil_div(a->M, G_BM) < kNumSMs) {
         dim3 sgrid((unsigned)ceil_div(a->N, S_BN), (unsigned)ceil_div(a->M, S_BM));
-        gemm_f32_small_kernel<<<sgrid, 256, 0, s>>>(*a);
+        td::launch(gemm_f32_small_kernel, td::LaunchCfg(sgrid, 256, 0, s), *a);
         return launch_status("gemm_f32_small");
     }
     dim3 grid((unsigned)ceil_div(a->N, G_BN), (unsigned)ceil_div(a->M, G_BM), (unsigned)nz);
-    gemm_f32_kernel<<<grid, G_THREADS, 0, s>>>(*a);
+    td::launch(gemm_f32_kernel, td::LaunchCfg(grid, G_THREADS, 0, s), *a);
     int st = launch_status("gemm_f32");
     if (st != TD_OK || nz == 1) return st;
-    gemm_splitk_reduce_kernel<<<grid1d((int64_t)a->M * a->N), 256, 0, s>>>(*a, nz);
+    td::launch(gemm_splitk_reduce_kernel, td::LaunchCfg(grid1d((int64_t)a->M * a->N), 256, 0, s), *a, nz);
     return launch_status("gemm_splitk_reduce");
 }
 
 extern "C" int td_colsum_f32(const float* x, int64_t ldx, float* out, int M, int N, int accumulate, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && out && M > 0 && N > 0, "td_colsum_f32: bad args");
-    colsum_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, ldx, out, M, N, accumulate);
+    td::launch(colsum_kernel, td::LaunchCfg((N + 31) / 32, 256, 0, (cudaStream_t)stream), x, ldx, out, M, N, accumulate);
     return launch_status("colsum");
 }
 
 extern "C" int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(dy && pre && dx && n > 0, "td_act_bwd_f32: bad args");
-    act_bwd_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(dy, pre, dx, n, act);
+    td::launch(act_bwd_kernel, td::LaunchCfg(grid1d(n), 256, 0, (cudaStream_t)stream), dy, pre, dx, n, act);
     return launch_status("act_bwd");
 }
 
@@ -589,7 +604,7 @@ extern "C" int td_add2d_f32(const float* src, int64_t lds, float* dst, int64_t l
                             void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(src && dst && rows > 0 && cols > 0, "td_add2d_f32: bad args");
-    add2d_kernel<<<grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, lds, dst, ldd, rows, cols, accumulate);
+    td::launch(add2d_kernel, td::LaunchCfg(grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream), src, lds, dst, ldd, rows, cols, accumulate);
     return launch_status("add2d");
 }
 
@@ -598,7 +613,7 @@ extern "C" int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t l
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && out && seed_ptr && rows > 0 && cols > 0 && group > 0 && cols % group == 0, "td_dropout_f32: bad args");
     TD_CHECK_ARG(p >= 0.f && p < 1.f, "td_dropout_f32: p must be in [0, 1)");
-    dropout_kernel<<<grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(x, ldx, out, ldo, rows, cols, group, p,
+    td::launch(dropout_kernel, td::LaunchCfg(grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream), x, ldx, out, ldo, rows, cols, group, p,
                                                                                  seed_ptr);
     return launch_status("dropout");
 }
@@ -607,7 +622,7 @@ extern "C" int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx,
                                 int num_rows, int accumulate, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(g && idx && table_grad && M > 0 && D > 0 && num_rows > 0, "td_embedding_bwd: bad args");
-    embedding_bwd_kernel<<<num_rows, 256, 0, (cudaStream_t)stream>>>(g, ldg, idx, table_grad, M, D, accumulate);
+    td::launch(embedding_bwd_kernel, td::LaunchCfg(num_rows, 256, 0, (cudaStream_t)stream), g, ldg, idx, table_grad, M, D, accumulate);
     return launch_status("embedding_bwd");
 }
 
@@ -615,7 +630,7 @@ extern "C" int td_time_features(const int64_t* t, const int32_t* t_dev, float* o
                                 void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG((t || t_dev) && out && batch > 0 && dim > 0 && mode >= 0 && mode <= 2, "td_time_features: bad args");
-    time_features_kernel<<<grid1d((int64_t)batch * (mode == 2 ? dim : 1)), 256, 0, (cudaStream_t)stream>>>(
+    td::launch(time_features_kernel, td::LaunchCfg(grid1d((int64_t)batch * (mode == 2 ? dim : 1)), 256, 0, (cudaStream_t)stream), 
         t, t_dev, out, batch, dim, mode);
     return launch_status("time_features");
 }
@@ -624,7 +639,7 @@ extern "C" int td_layernorm_fwd(const float* x, const float* gamma, const float*
                                 float* rstd, int M, int D, float eps, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && gamma && beta && y && M > 0 && D > 0, "td_layernorm_fwd: bad args");
-    layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, rstd, M, D, eps);
+    td::launch(layernorm_fwd_kernel, td::LaunchCfg((M + 7) / 8, 256, 0, (cudaStream_t)stream), x, gamma, beta, y, mean, rstd, M, D, eps);
     return launch_status("layernorm_fwd");
 }
 
@@ -633,10 +648,10 @@ extern "C" int td_layernorm_bwd(const float* dy, const float* x, const float* ga
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(dy && x && gamma && mean && rstd && dx && M > 0 && D > 0, "td_layernorm_bwd: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    layernorm_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>(dy, x, gamma, mean, rstd, dx, M, D);
+    td::launch(layernorm_bwd_kernel, td::LaunchCfg((M + 7) / 8, 256, 0, s), dy, x, gamma, mean, rstd, dx, M, D);
     int st = launch_status("layernorm_bwd");
     if (st != TD_OK || !dgamma || !dbeta) return st;
-    layernorm_bwd_params_kernel<<<(D + 31) / 32, 256, 0, s>>>(dy, x, mean, rstd, dgamma, dbeta, M, D);
+    td::launch(layernorm_bwd_params_kernel, td::LaunchCfg((D + 31) / 32, 256, 0, s), dy, x, mean, rstd, dgamma, dbeta, M, D);
     return launch_status("layernorm_bwd_params");
 }
 
@@ -646,7 +661,7 @@ extern "C" int td_bn1d_fwd(const float* x, int64_t ldx, const float* gamma, cons
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && gamma && beta && y && M > 0 && N > 0, "td_bn1d_fwd: bad args");
     TD_CHECK_ARG(training || (running_mean && running_var), "td_bn1d_fwd: eval mode needs running statistics");
-    bn1d_fwd_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, ldx, gamma, beta, running_mean, running_var,
+    td::launch(bn1d_fwd_kernel, td::LaunchCfg((N + 31) / 32, 256, 0, (cudaStream_t)stream), x, ldx, gamma, beta, running_mean, running_var,
                                                                      save_mean, save_rstd, y, ldy, M, N, eps, momentum,
                                                                      training, relu);
     return launch_status("bn1d_fwd");
@@ -659,7 +674,7 @@ extern "C" int td_bn1d_bwd(const float* dy, int64_t lddy, const float* x, int64_
     TD_CHECK_ARG(dy && x && gamma && save_mean && save_rstd && dx && dgamma && dbeta && M > 0 && N > 0,
                  "td_bn1d_bwd: bad args");
     TD_CHECK_ARG(!relu || y_out, "td_bn1d_bwd: relu needs the saved forward output");
-    bn1d_bwd_kernel<<<(N + 31) / 32, 256, 0, (cudaStream_t)stream>>>(dy, lddy, x, ldx, y_out, ldy, gamma, save_mean,
+    td::launch(bn1d_bwd_kernel, td::LaunchCfg((N + 31) / 32, 256, 0, (cudaStream_t)stream), dy, lddy, x, ldx, y_out, ldy, gamma, save_mean,
                                                                      save_rstd, dx, lddx, dgamma, dbeta, M, N, relu);
     return launch_status("bn1d_bwd");
 }

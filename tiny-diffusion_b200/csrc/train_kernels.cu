@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kT)
 chan_reduce_kernel(const T* __restrict__ a, int64_t lda, int a_coff, const float* __restrict__ y, int64_t P, int C,
                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                    int shifted, float* __restrict__ partials) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     extern __shared__ float red[];               // [rows][2*C]
     const int lanesC = C / V;
@@ -134,6 +135,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double 
                    float* __restrict__ running_mean, float* __restrict__ running_var, int64_t* __restrict__ nbt,
                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ save_mean,
                    float* __restrict__ save_invstd) {
+    td::pdl_sync();
     const int c = blockIdx.x * 32 + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt) nbt[0] += 1;
     double s1, s2;
@@ -164,6 +166,7 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 bn_relu_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                      T* __restrict__ a, int64_t lda, int a_coff, int64_t P, int C, int relu) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     const int lanesC = C / V;
     const int64_t total = P * lanesC;
@@ -194,6 +197,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, dou
                        const float* __restrict__ scale, const float* __restrict__ save_mean,
                        const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ coef) {
+    td::pdl_sync();
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s1, s2;
     block_sum_partials(partials, nrows, C, c, s1, s2);
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(kT)
 bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y,
                          const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ coef, T* __restrict__ dy, int64_t P, int C) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     const int lanesC = C / V;
     const int64_t total = P * lanesC;
@@ -250,6 +255,7 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
                     int Ho, int Wo, int accumulate) {
+    td::pdl_sync();
     // one CTA per input row (b, h); threadIdx.x = channel vector, threadIdx.y = pixel of the row
     constexpr int V = Vec<T>::N;
     const int cv = C / V;
@@ -340,6 +346,7 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
                   int Wo, int C, int nseg) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     __shared__ Bil col[kMaxRowW];
     const bool same = (Hi == Ho && Wi == Wo);
@@ -434,6 +441,7 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restrict__ dtemb, int ld_temb, int temb_off,
                 int HW, int Cs) {
+    td::pdl_sync();
     constexpr int V = Vec<T>::N;
     __shared__ float red[32][8 * V + 1];
     const int lane = threadIdx.x & 7, prow = threadIdx.x >> 3;
@@ -467,6 +475,7 @@ temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restr
 // out[c] = sum_r partials[r][which][c]    (bias gradients from chan_reduce partials)
 __global__ void __launch_bounds__(1024)
 partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int which, float* __restrict__ out) {
+    td::pdl_sync();
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s1, s2;
     block_sum_partials(partials, nrows, C, c, s1, s2);
@@ -478,6 +487,7 @@ partial_sum_kernel(const float* __restrict__ partials, int nrows, int C, int whi
 constexpr int kChanSumChunks = 128;
 __global__ void __launch_bounds__(kT)
 nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __restrict__ ws) {
+    td::pdl_sync();
     __shared__ float red[kT];
     const int c = blockIdx.y;
     const int64_t total = (int64_t)B * HW;
@@ -495,6 +505,7 @@ nchw_chansum_kernel(const float* __restrict__ x, int B, int C, int HW, float* __
     if (threadIdx.x == 0) ws[(size_t)c * gridDim.x + blockIdx.x] = red[0];
 }
 __global__ void nchw_chansum_finalize_kernel(const float* __restrict__ ws, int chunks, int C, float* __restrict__ out) {
+    td::pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double s = 0.0;
@@ -548,7 +559,7 @@ extern "C" int td_bn_stats(const void* x, int dtype, int64_t ldx, int x_coff, in
     const int grid = td_chan_reduce_rows(dtype, pixels, channels);
     const int V = dtype == TD_BF16 ? 8 : 4;
     const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
-    TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 0><<<grid, kT, smem, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(chan_reduce_kernel<T, 0>, td::LaunchCfg(grid, kT, smem, (cudaStream_t)stream), 
                              (const T*)x, ldx, x_coff, nullptr, pixels, channels, nullptr, nullptr, nullptr, shifted,
                              partials)));
     return launch_status("bn_stats");
@@ -561,7 +572,7 @@ extern "C" int td_bn_finalize(const float* partials, int nrows, int channels, in
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && gamma && beta && scale && shift && save_mean &&
                      save_invstd, "td_bn_finalize: bad args");
-    bn_finalize_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
+    td::launch(bn_finalize_kernel, td::LaunchCfg((channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream), 
         partials, nrows, channels, (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
         num_batches_tracked, scale, shift, save_mean, save_invstd);
     return launch_status("bn_finalize");
@@ -575,7 +586,7 @@ extern "C" int td_bn_relu_apply(const float* y, const float* scale, const float*
     const int V = dtype == TD_BF16 ? 8 : 4;
     const int lanesC = channels / V;
     const int grid = stream_grid(pixels * lanesC, lanesC);
-    TD_DISPATCH_T(dtype, (bn_relu_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(bn_relu_apply_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), 
                              y, scale, shift, (T*)a, lda, a_coff, pixels, channels, relu)));
     return launch_status("bn_relu_apply");
 }
@@ -589,7 +600,7 @@ extern "C" int td_bn_relu_bwd_reduce(const void* da, int64_t ldda, int da_coff, 
     const int grid = td_chan_reduce_rows(dtype, pixels, channels);
     const int V = dtype == TD_BF16 ? 8 : 4;
     const size_t smem = (size_t)(kT / (channels / V)) * 2 * channels * sizeof(float);
-    TD_DISPATCH_T(dtype, (chan_reduce_kernel<T, 1><<<grid, kT, smem, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(chan_reduce_kernel<T, 1>, td::LaunchCfg(grid, kT, smem, (cudaStream_t)stream), 
                              (const T*)da, ldda, da_coff, y, pixels, channels, scale, shift, save_mean, 0, partials)));
     return launch_status("bn_relu_bwd_reduce");
 }
@@ -600,7 +611,7 @@ extern "C" int td_bn_bwd_finalize(const float* partials, int nrows, int channels
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && nrows > 0 && channels > 0 && count > 0 && scale && save_mean && save_invstd && dgamma &&
                      dbeta && coef, "td_bn_bwd_finalize: bad args");
-    bn_bwd_finalize_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
+    td::launch(bn_bwd_finalize_kernel, td::LaunchCfg((channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream), 
         partials, nrows, channels, (double)count, scale, save_mean, save_invstd, dgamma, dbeta, coef);
     return launch_status("bn_bwd_finalize");
 }
@@ -614,7 +625,7 @@ extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, c
     const int V = dtype == TD_BF16 ? 8 : 4;
     const int lanesC = channels / V;
     const int grid = stream_grid(pixels * lanesC, lanesC);
-    TD_DISPATCH_T(dtype, (bn_relu_bwd_apply_kernel<T><<<grid, kT, 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(bn_relu_bwd_apply_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), 
                              (const T*)da, ldda, da_coff, y, scale, shift, coef, (T*)dy, pixels, channels)));
     return launch_status("bn_relu_bwd_apply");
 }
@@ -626,7 +637,7 @@ extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtyp
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0, "td_maxpool2_bwd: channels must be a multiple of %d", V);
     const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
-    TD_DISPATCH_T(dtype, (maxpool2_bwd_kernel<T><<<batch * h, row_block(c / V), 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(maxpool2_bwd_kernel<T>, td::LaunchCfg(batch * h, row_block(c / V), 0, (cudaStream_t)stream), 
                              (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
     return launch_status("maxpool2_bwd");
 }
@@ -641,7 +652,7 @@ extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff
     const dim3 blk = walk_block(c / V);
     const int nseg = walk_segments((int64_t)batch * hi * (c / V), wi);
     const dim3 grd((unsigned)(ceil_div((int64_t)batch * hi, blk.y) * nseg), (unsigned)ceil_div(c / V, blk.x), 1);
-    TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, (cudaStream_t)stream>>>(
+    TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, (cudaStream_t)stream), 
                              (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c, nseg)));
     return launch_status("resize_bilinear_bwd");
 }
@@ -661,17 +672,17 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
         const dim3 blk = walk_block(cu / V);
         const int nseg = walk_segments((int64_t)batch * (ho / 2) * (cu / V), wo / 2);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * (ho / 2), blk.y) * nseg), (unsigned)ceil_div(cu / V, blk.x), 1);
-        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, s>>>((const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu, nseg)));
+        TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, s), (const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu, nseg)));
     }
     {
         const dim3 blk = walk_block(cs / V);
         const int nseg = walk_segments((int64_t)batch * hs * (cs / V), ws);
         const dim3 grd((unsigned)(ceil_div((int64_t)batch * hs, blk.y) * nseg), (unsigned)ceil_div(cs / V, blk.x), 1);
-        TD_DISPATCH_T(dtype, (resize_bwd_kernel<T><<<grd, blk, 0, s>>>((const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs, nseg)));
+        TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, s), (const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs, nseg)));
     }
     {
         const dim3 grd((unsigned)batch, (unsigned)ceil_div(cs / V, 8), 1);
-        TD_DISPATCH_T(dtype, (temb_bwd_kernel<T><<<grd, kT, 0, s>>>((const T*)dout, ld, cu, dtemb, ld_temb, temb_off, ho * wo, cs)));
+        TD_DISPATCH_T(dtype, (td::launch(temb_bwd_kernel<T>, td::LaunchCfg(grd, kT, 0, s), (const T*)dout, ld, cu, dtemb, ld_temb, temb_off, ho * wo, cs)));
     }
     return launch_status("upcat_bwd");
 }
@@ -679,7 +690,7 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
 extern "C" int td_partial_sum(const float* partials, int nrows, int channels, int which, float* out, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(partials && out && nrows > 0 && channels > 0 && (which == 0 || which == 1), "td_partial_sum: bad args");
-    partial_sum_kernel<<<(channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(partials, nrows, channels, which, out);
+    td::launch(partial_sum_kernel, td::LaunchCfg((channels + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream), partials, nrows, channels, which, out);
     return launch_status("partial_sum");
 }
 
@@ -688,7 +699,7 @@ extern "C" int td_nchw_chansum(const float* x, int batch, int channels, int hw, 
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && out && workspace && batch > 0 && channels > 0 && hw > 0, "td_nchw_chansum: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    nchw_chansum_kernel<<<dim3(kChanSumChunks, channels), kT, 0, s>>>(x, batch, channels, hw, workspace);
-    nchw_chansum_finalize_kernel<<<(channels + 63) / 64, 64, 0, s>>>(workspace, kChanSumChunks, channels, out);
+    td::launch(nchw_chansum_kernel, td::LaunchCfg(dim3(kChanSumChunks, channels), kT, 0, s), x, batch, channels, hw, workspace);
+    td::launch(nchw_chansum_finalize_kernel, td::LaunchCfg((channels + 63) / 64, 64, 0, s), workspace, kChanSumChunks, channels, out);
     return launch_status("nchw_chansum");
 }

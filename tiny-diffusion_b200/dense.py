@@ -19,6 +19,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
+from .checkpoint import CheckpointCompat
 
 Mat = Tuple[str, int, int]            # (buffer name, first column, end column)
 
@@ -345,7 +346,7 @@ class _DenseTrainFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(eng.pgrad[k].clone() for k, _ in eng.module.named_parameters())
 
 
-class DenseNoiseModel(torch.nn.Module):
+class DenseNoiseModel(CheckpointCompat, torch.nn.Module):
     """Shared dispatch of the two latent denoisers; subclasses declare parameters and ``_declare``."""
     in_dim = 20
     emb_mode = 0

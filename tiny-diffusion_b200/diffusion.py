@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from .checkpoint import CheckpointCompat
 from .process import ForwardProcess, ReverseLoop
 from .unet import MNIST_UNET, UNetConfig, UNetEngine
 
@@ -22,7 +23,7 @@ def _cbr(cin: int, cout: int):
     return [nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU()]
 
 
-class ConvUNetBase(nn.Module):
+class ConvUNetBase(CheckpointCompat, nn.Module):
     """Parameter container + dispatch shared by the three conv UNets.
 
     The ``torch.nn`` sub-modules exist only to own the parameters/buffers (so ``state_dict()``,

@@ -64,22 +64,34 @@ class ReverseLoop:
     """x_{t-1} = c1*(x_t - c2*eps) + c3*z for t = T-1 .. 0, one fused kernel per step, the step
     index held on the device.  ``eps_launch`` enqueues the denoiser for the current ``x``/``t``."""
 
+    STEPS_PER_GRAPH = 20      # reverse steps unrolled into one captured graph (fewer, longer replays)
+
     def __init__(self, process: ForwardProcess, x: torch.Tensor, eps: torch.Tensor, t_dev: torch.Tensor,
-                 eps_launch, use_graph: bool = True):
+                 eps_launch, use_graph: bool = True, guidance: Optional[float] = None):
+        """``guidance`` (extension, classifier-free guidance): x / eps hold a doubled batch, rows [0, n) conditional and
+        rows [n, 2n) null-label; every step combines eps_u + w*(eps_c - eps_u) (td_psample_step_cfg)."""
         self.p, self.x, self.eps, self.t_dev, self.eps_launch = process, x, eps, t_dev, eps_launch
         self.use_graph = use_graph
+        self.guidance = guidance
+        self.n = x.numel() if guidance is None else x.numel() // 2      # elements the noise stream covers
+        self.graphs = {}
         self.lib = L.load()
         self.tab = process._tables(x.device)
         self.seed = torch.zeros(2, device=x.device, dtype=torch.int64)
-        self.graph = None
+        self._key = None
         self._z_ref = None
 
     def _step(self, z_ptr, z_stride, seed_ptr):
         st = L.stream_ptr()
         self.eps_launch()
-        L.check(self.lib.td_psample_step(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
-                                         self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
-                                         seed_ptr, st), "td_psample_step")
+        if self.guidance is None:
+            L.check(self.lib.td_psample_step(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
+                                             self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
+                                             seed_ptr, st), "td_psample_step")
+        else:
+            L.check(self.lib.td_psample_step_cfg(self.x.data_ptr(), self.eps.data_ptr(), self.n, float(self.guidance),
+                                                 z_ptr, z_stride, self.tab["coef"].data_ptr(), self.t_dev.data_ptr(),
+                                                 seed_ptr, st), "td_psample_step_cfg")
         L.check(self.lib.td_counter_add(self.t_dev.data_ptr(), -1, st), "td_counter_add")
 
     def run(self, z: Optional[torch.Tensor] = None, seed: int = 0, steps: Optional[int] = None) -> None:
@@ -87,7 +99,7 @@ class ReverseLoop:
         z: optional injected noise table [T, *x.shape] (row t used at step t; row 0 unused)."""
         T = self.p.num_timesteps
         steps = T if steps is None else steps
-        n = self.x.numel()
+        n = self.n
         if z is not None:
             assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.shape[0] == T
             assert z.numel() == T * n
@@ -102,22 +114,37 @@ class ReverseLoop:
                 self._step(z_ptr, z_stride, seed_ptr)
             return
         key = (z_ptr, z_stride, seed_ptr)
-        if self.graph is None or self._key != key:
-            # one eager step first (lazy module loading and cudaFuncSetAttribute are not capturable),
-            # on a copy-restored x, then capture ONE step; the graph is replayed `steps` times.
-            x_saved = self.x.clone()
-            self.t_dev.fill_(T - 1)
+        if self._key != key:
+            self.graphs, self._key, self._z_ref = {}, key, z
+        self.t_dev.fill_(T - 1)
+        unroll = max(1, int(self.STEPS_PER_GRAPH))
+        done = 0
+        while done < steps:
+            k = unroll if steps - done >= unroll else 1
+            self._graph(k, z_ptr, z_stride, seed_ptr).replay()
+            done += k
+
+    def _graph(self, k: int, z_ptr, z_stride, seed_ptr) -> "torch.cuda.CUDAGraph":
+        """The captured graph of ``k`` consecutive reverse steps (the step index lives on the device, so the same graph
+        serves every position of the loop)."""
+        g = self.graphs.get(k)
+        if g is not None:
+            return g
+        # one eager step first (lazy module loading and cudaFuncSetAttribute are not capturable), then the capture;
+        # x and the step counter are restored afterwards
+        x_saved, t_saved = self.x.clone(), self.t_dev.clone()
+        if not self.graphs:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 self._step(z_ptr, z_stride, seed_ptr)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(k):
                 self._step(z_ptr, z_stride, seed_ptr)
-            self.x.copy_(x_saved)
-            self.graph, self._key, self._z_ref = g, key, z
-        self.t_dev.fill_(T - 1)
-        for _ in range(steps):
-            self.graph.replay()
+        self.x.copy_(x_saved)
+        self.t_dev.copy_(t_saved)
+        self.graphs[k] = g
+        return g

@@ -14,6 +14,7 @@ libtinydiff kernels over preallocated NHWC buffers, for one (batch, precision) p
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -99,8 +100,9 @@ class UNetTrainEngine:
         # pre-BN conv outputs stay fp32: under the large per-sample time-embedding offsets a bf16 y loses
         # the spatial signal before the normalisation (and flips ReLU masks in the backward)
         self.yraw = {name: buf(size, cout, torch.float32) for name, _, _, size, _, cout in self.layers}
-        max_y = max(B * size * size * cout for _, _, _, size, _, cout in self.layers)
-        self.dy = torch.zeros(max_y, device=dev, dtype=self.act)             # dL/d(conv output), one layer at a time
+        # dL/d(conv output), one buffer per layer: the weight gradients read them on a second stream while the main
+        # stream has moved on to the next layers (151 MB at B = 128)
+        self.dy = {name: buf(size, cout) for name, _, _, size, _, cout in self.layers}
         self.x_in = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
         self.eps = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
         self.d_eps = torch.zeros(B, cfg.in_ch, s0, s0, device=dev, dtype=torch.float32)
@@ -372,7 +374,7 @@ class UNetTrainEngine:
             st_ = self.bn[name]
             rows, P = st_["rows_bwd"], B * size * size
             y, da = self.yraw[name], gr[out]
-            dyv = self.dy[:P * cout].view(B, size, size, cout)
+            dyv = self.dy[name]
             yp, dap, dyp = y.data_ptr(), da.data_ptr(), dyv.data_ptr()
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
             coef = st_["coef"].data_ptr()
@@ -461,8 +463,41 @@ class UNetTrainEngine:
         for name, d, engine, _ in self._wg_specs:
             d.workspace = self.wg_ws.data_ptr()
             self.wg_plans[name] = _WgradPlan(d, engine)
-        bwd = [(n, (self.wg_plans[n.split(":")[0]].run if fn is None else fn)) for n, fn in bwd]
+        # Weight gradients run on a second stream (a parallel branch of the captured graph): nothing downstream in the
+        # backward needs them, so the latency-bound BatchNorm / resize / pool backward kernels of the following layers
+        # execute beside the tensor-core weight-gradient kernels instead of between them.  Each entry forks from the main
+        # stream (its inputs are complete there) and the plan joins at the end (`sync_wgrad_stream`).
+        self.wgrad_stream_on = os.environ.get("TD_WGRAD_STREAM", "1") != "0"
+        self._side_w = getattr(self, "_side_w", None)
+        self._wg_forked = False
+
+        def on_wgrad_stream(run):
+            if not self.wgrad_stream_on:
+                return run
+
+            def fn(st):
+                main = torch.cuda.current_stream()
+                if self._side_w is None:
+                    self._side_w = torch.cuda.Stream(device=self.device)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._side_w.wait_event(ev)
+                with torch.cuda.stream(self._side_w):
+                    run(L.stream_ptr())
+                self._wg_forked = True
+            return fn
+        bwd = [(n, (on_wgrad_stream(self.wg_plans[n.split(":")[0]].run) if fn is None else fn)) for n, fn in bwd]
+        bwd.append(("wgrad:join", lambda st: self.sync_wgrad_stream()))
         self.fwd_ops, self.bwd_ops = fwd, bwd
+
+    def sync_wgrad_stream(self) -> None:
+        """Make the current stream wait for every weight gradient enqueued so far (no-op when none is outstanding)."""
+        if not self._wg_forked:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self._side_w)
+        torch.cuda.current_stream().wait_event(ev)
+        self._wg_forked = False
 
     # ------------------------------------------------------------------ conditioning head
     def _embed_args(self) -> "L.EmbedArgs":
@@ -691,6 +726,8 @@ class TrainStep:
         self._works = []
         for i, (_, fn) in enumerate(e.bwd_ops):
             fn(st)
+            if self._ready_at.get(i):
+                e.sync_wgrad_stream()          # the bucket's weight gradients come from the second stream
             for lo, hi in self._ready_at.get(i, ()):
                 self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
 
@@ -775,6 +812,84 @@ class TrainStep:
     def close(self) -> None:
         """Drop the captured graph (with world_size > 1 it holds NCCL kernels: release it before the process group)."""
         self.graph = None
+
+    def __call__(self, x_0, y=None, t=None, noise=None) -> torch.Tensor:
+        self.load(x_0, y, t, noise)
+        return self.run()
+
+
+class ValStep:
+    """Fused validation step (conditional_diffusion.py:275-289; conditional_diffusion_laion.py:497-519):
+    ``t ~ randint; x_t, noise = q_sample(x_0, t); eps = model.eval()(x_t, t[, y]); loss = mse(eps, noise)`` with no
+    gradient, as one CUDA-graph replay of the eval-mode plan (running-statistics BatchNorm folded into the conv
+    epilogues, the kernels the sampler uses).  Like the reference's loop it leaves the model in eval mode; the
+    caller switches back with ``model.train()`` (conditional_diffusion.py:351)."""
+
+    def __init__(self, model, process, batch: int, device, use_graph: bool = True):
+        self.device = L.require_device(device)
+        self.model, self.process, self.B = model, process, batch
+        self.lib = L.load()
+        self.use_graph = use_graph
+        self.eng = model.engine(batch, self.device)
+        e = self.eng
+        self.x0 = torch.zeros_like(e.x_in)
+        self.noise = torch.zeros_like(e.x_in)
+        self.loss = torch.zeros(1, device=self.device)
+        n = e.eps.numel()
+        self.partials = torch.zeros(int(self.lib.td_mse_num_partials(n)), device=self.device)
+        self.counter = torch.zeros(1, device=self.device, dtype=torch.int32)
+        self.tab = process._tables(self.device)
+        self.graph = None
+        self._version = None
+
+    def _body(self):
+        e, lib, st = self.eng, self.lib, L.stream_ptr()
+        per = e.x_in.numel() // self.B
+        L.check(lib.td_qsample(self.x0.data_ptr(), self.noise.data_ptr(), e.t_in.data_ptr(), self.tab["abar"].data_ptr(),
+                               e.x_in.data_ptr(), self.B, per, self.process.num_timesteps, None, st), "td_qsample")
+        e.launch()
+        n = e.eps.numel()
+        L.check(lib.td_mse_grad(e.eps.data_ptr(), self.noise.data_ptr(), None, self.loss.data_ptr(),
+                                self.partials.data_ptr(), self.counter.data_ptr(), n, 1.0 / n, st), "td_mse_grad")
+
+    def load(self, x_0, y=None, t=None, noise=None):
+        e = self.eng
+        self.x0.copy_(x_0, non_blocking=True)
+        if e.cfg.cond == "class":
+            e.y_in.copy_(y, non_blocking=True)
+        elif e.cfg.cond == "text":
+            e.text_in.copy_(y, non_blocking=True)
+        if t is None:
+            e.t_in.copy_(torch.randint(0, self.process.num_timesteps, (self.B,), device=self.device))
+        else:
+            e.t_in.copy_(t, non_blocking=True)
+        if noise is None:
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise, non_blocking=True)
+
+    @torch.no_grad()
+    def run(self) -> torch.Tensor:
+        self.model.eval()
+        e = self.eng
+        e.use_t_dev = False
+        e.refresh_weights()          # re-folds BatchNorm / re-packs only when a parameter or buffer changed
+        if not self.use_graph:
+            self._body()
+            return self.loss
+        if self.graph is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph = g
+        self.graph.replay()
+        return self.loss
 
     def __call__(self, x_0, y=None, t=None, noise=None) -> torch.Tensor:
         self.load(x_0, y, t, noise)
