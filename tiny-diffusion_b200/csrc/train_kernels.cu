@@ -111,10 +111,19 @@ __device__ inline void block_sum_partials(const float* __restrict__ partials, in
     double a = 0.0, b = 0.0;
     if (c < C) {
         const float* p = partials + c;
-#pragma unroll 4
-        for (int r = threadIdx.y; r < nrows; r += 32) {
-            a += (double)p[(size_t)r * 2 * C];
-            b += (double)p[(size_t)r * 2 * C + C];
+        // batches of 16 rows per thread with every load of a batch issued before the first use: the kernel is a pure
+        // latency chain (4..16 CTAs), so the loads in flight decide its duration (896 rows: 2 round trips instead of 7)
+        for (int r0 = threadIdx.y; r0 < nrows; r0 += 32 * 16) {
+            float va[16], vb[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int r = r0 + 32 * k;
+                const bool ok = r < nrows;
+                va[k] = ok ? __ldg(p + (size_t)r * 2 * C) : 0.f;
+                vb[k] = ok ? __ldg(p + (size_t)r * 2 * C + C) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { a += (double)va[k]; b += (double)vb[k]; }
         }
     }
     red[threadIdx.y][0][threadIdx.x] = a;
@@ -138,26 +147,37 @@ bn_finalize_kernel(const float* __restrict__ partials, int nrows, int C, double 
     td::pdl_sync();
     const int c = blockIdx.x * 32 + threadIdx.x;
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && nbt) nbt[0] += 1;
+    // per-channel inputs of the tail are fetched before the reduction (one more round trip off the chain)
+    const bool tail = threadIdx.y == 0 && c < C;
+    float k_c = 0.f, g_c = 0.f, b_c = 0.f, cb_c = 0.f, rm_c = 0.f, rv_c = 0.f;
+    if (tail) {
+        k_c = partials[(size_t)nrows * 2 * C + c];
+        g_c = gamma[c];
+        b_c = beta[c];
+        if (conv_bias) cb_c = conv_bias[c];
+        if (running_mean) rm_c = running_mean[c];
+        if (running_var) rv_c = running_var[c];
+    }
     double s1, s2;
     block_sum_partials(partials, nrows, C, c, s1, s2);
-    if (threadIdx.y != 0 || c >= C) return;
+    if (!tail) return;
     const double dm = s1 / count;                         // mean of (x - K)
-    const double mean = (double)partials[(size_t)nrows * 2 * C + c] + dm;
+    const double mean = (double)k_c + dm;
     double var = s2 / count - dm * dm;
     if (var < 0.0) var = 0.0;
     const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * invstd;
+    const float sc = g_c * invstd;
     scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
+    shift[c] = b_c - (float)mean * sc;
     save_mean[c] = (float)mean;
     save_invstd[c] = invstd;
     if (running_mean) {
-        const float mb = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mb;
+        const float mb = (float)mean + cb_c;
+        running_mean[c] = (1.f - momentum) * rm_c + momentum * mb;
     }
     if (running_var) {
         const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        running_var[c] = (1.f - momentum) * rv_c + momentum * (float)unb;
     }
 }
 
@@ -199,10 +219,13 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nrows, int C, dou
                        float* __restrict__ coef) {
     td::pdl_sync();
     const int c = blockIdx.x * 32 + threadIdx.x;
+    const bool tail = threadIdx.y == 0 && c < C;
+    float mean_c = 0.f, invstd_c = 0.f, sc_c = 0.f;
+    if (tail) { mean_c = save_mean[c]; invstd_c = save_invstd[c]; sc_c = scale[c]; }
     double s1, s2;
     block_sum_partials(partials, nrows, C, c, s1, s2);
-    if (threadIdx.y != 0 || c >= C) return;
-    const double mean = save_mean[c], invstd = save_invstd[c], sc = scale[c];
+    if (!tail) return;
+    const double mean = mean_c, invstd = invstd_c, sc = sc_c;
     const double dg = s2 * invstd;                     // sum g * xhat   (s2 = sum g * (y - mean))
     dgamma[c] = (float)dg;
     dbeta[c] = (float)s1;
@@ -435,7 +458,18 @@ static inline int walk_segments(int64_t threads, int width) {
     return (int)ceil_div(width, sw);
 }
 
-// d_temb[b, off + c] = sum over the Ho*Wo output pixels of d_out[b, :, :, Cu + c].  grid (samples, channel slices of
+template <typename T>
+static int launch_resize_bwd(const void* dy, int64_t ld, int coff, void* dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
+                             cudaStream_t s) {
+    constexpr int V = Vec<T>::N;
+    const dim3 blk = walk_block(C / V);
+    const int nseg = walk_segments((int64_t)B * Hi * (C / V), Wi);
+    const dim3 grd((unsigned)(ceil_div((int64_t)B * Hi, blk.y) * nseg), (unsigned)ceil_div(C / V, blk.x), 1);
+    td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, s), (const T*)dy, ld, coff, (T*)dx, B, Hi, Wi, Ho, Wo, C, nseg);
+    return TD_OK;
+}
+
+// d_temb[b, off + c] = sum over the pixels of src[b, :, :, coff + c] (src: the skip gradient, see td_upcat_bwd).  grid (samples, channel slices of
 // 8 vectors); 8 lanes x 32 pixel rows per CTA, fixed-order tree over the rows.
 template <typename T>
 __global__ void __launch_bounds__(kT)
@@ -452,6 +486,7 @@ temb_bwd_kernel(const T* __restrict__ dout, int64_t ld, int coff, float* __restr
     for (int k = 0; k < V; ++k) s[k] = 0.f;
     if (c < Cs) {
         const T* src = dout + (int64_t)b * HW * ld + coff + c;
+#pragma unroll 8
         for (int p = prow; p < HW; p += 32) {
             float f[V];
             Vec<T>::load(src + (int64_t)p * ld).unpack(f);
@@ -514,7 +549,7 @@ __global__ void nchw_chansum_finalize_kernel(const float* __restrict__ ws, int c
 }
 
 static inline int reduce_grid(int64_t P, int rows) {
-    const int64_t want = ceil_div(P, (int64_t)rows * 8);     // >= 8 pixel rows per thread
+    const int64_t want = ceil_div(P, (int64_t)rows * 4);     // >= 4 pixel rows per thread: one batch of loads in flight
     return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * 4));
 }
 static inline int stream_grid(int64_t items, int lanesC) {
@@ -649,11 +684,7 @@ extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0 && ld_dy % V == 0 && dy_coff % V == 0, "td_resize_bilinear_bwd: channels must be a multiple of %d", V);
     TD_CHECK_ARG(wo <= kMaxRowW, "td_resize_bilinear_bwd: output rows wider than %d", kMaxRowW);
-    const dim3 blk = walk_block(c / V);
-    const int nseg = walk_segments((int64_t)batch * hi * (c / V), wi);
-    const dim3 grd((unsigned)(ceil_div((int64_t)batch * hi, blk.y) * nseg), (unsigned)ceil_div(c / V, blk.x), 1);
-    TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, (cudaStream_t)stream), 
-                             (const T*)dy, ld_dy, dy_coff, (T*)dx, batch, hi, wi, ho, wo, c, nseg)));
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dy, ld_dy, dy_coff, dx, batch, hi, wi, ho, wo, c, (cudaStream_t)stream)) return st; });
     return launch_status("resize_bilinear_bwd");
 }
 
@@ -668,21 +699,14 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ld = cu + cs;
     TD_CHECK_ARG(wo <= kMaxRowW, "td_upcat_bwd: output rows wider than %d", kMaxRowW);
-    {
-        const dim3 blk = walk_block(cu / V);
-        const int nseg = walk_segments((int64_t)batch * (ho / 2) * (cu / V), wo / 2);
-        const dim3 grd((unsigned)(ceil_div((int64_t)batch * (ho / 2), blk.y) * nseg), (unsigned)ceil_div(cu / V, blk.x), 1);
-        TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, s), (const T*)dout, ld, 0, (T*)dlow, batch, ho / 2, wo / 2, ho, wo, cu, nseg)));
-    }
-    {
-        const dim3 blk = walk_block(cs / V);
-        const int nseg = walk_segments((int64_t)batch * hs * (cs / V), ws);
-        const dim3 grd((unsigned)(ceil_div((int64_t)batch * hs, blk.y) * nseg), (unsigned)ceil_div(cs / V, blk.x), 1);
-        TD_DISPATCH_T(dtype, (td::launch(resize_bwd_kernel<T>, td::LaunchCfg(grd, blk, 0, s), (const T*)dout, ld, cu, (T*)dskip, batch, hs, ws, ho, wo, cs, nseg)));
-    }
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dout, ld, 0, dlow, batch, ho / 2, wo / 2, ho, wo, cu, s)) return st; });
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dout, ld, cu, dskip, batch, hs, ws, ho, wo, cs, s)) return st; });
     {
         const dim3 grd((unsigned)batch, (unsigned)ceil_div(cs / V, 8), 1);
-        TD_DISPATCH_T(dtype, (td::launch(temb_bwd_kernel<T>, td::LaunchCfg(grd, kT, 0, s), (const T*)dout, ld, cu, dtemb, ld_temb, temb_off, ho * wo, cs)));
+        // bilinear weights sum to one per output pixel, so the transposed resize preserves the per-channel total:
+        // sum over the output pixels of d_out == sum over the input pixels of d_skip -- read the smaller, dense tensor
+        // that the launch above has just written (L2-resident) instead of the strided skip half of d_out a second time
+        TD_DISPATCH_T(dtype, (td::launch(temb_bwd_kernel<T>, td::LaunchCfg(grd, kT, 0, s), (const T*)dskip, (int64_t)cs, 0, dtemb, ld_temb, temb_off, hs * ws, cs)));
     }
     return launch_status("upcat_bwd");
 }

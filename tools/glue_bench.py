@@ -82,3 +82,12 @@ w0 = ops.pack_conv_weight(torch.randn(64, 1, 3, 3, device=dev))
 b0 = torch.randn(64, device=dev)
 y0 = torch.empty(B, 28, 28, 64, device=dev, dtype=bf)
 report("initial_conv 1->64 @28", timeit(lambda: ops.conv3x3(xin, w0, None, b0, False, 2, bf, x_nchw=True, out=y0)), B * 784 * 4 + B * 784 * 64 * 2)
+# upcat backward (transposed resizes of both halves + the embedding-gradient reduction)
+for (hl, cu, hs, cs) in ((4, 512, 7, 512), (8, 256, 14, 256), (16, 128, 28, 128)):
+    dout = torch.randn(B, 2 * hl, 2 * hl, cu + cs, device=dev).to(bf)
+    dlow = torch.empty(B, hl, hl, cu, device=dev, dtype=bf)
+    dskip = torch.empty(B, hs, hs, cs, device=dev, dtype=bf)
+    dtemb = torch.zeros(B, cs, device=dev)
+    fn = lambda: L.check(lib.td_upcat_bwd(dout.data_ptr(), dlow.data_ptr(), dskip.data_ptr(), dtemb.data_ptr(), cs, 0, L.TD_BF16, B,
+                                          2 * hl, 2 * hl, cu, hs, hs, cs, L.stream_ptr()))
+    report(f"upcat_bwd {2*hl}->{hl} [{cu}|{cs}]", timeit(fn), (dout.numel() * 2 + dlow.numel() + dskip.numel()) * 2)
