@@ -317,7 +317,7 @@ def run_gpu(args):
         "e2e": {"value": world * B * n_train / (train_e2e_ms / 1e3), "unit": "img/s",
                 "h2d_bytes_per_step": int(x0_host.numel() * 4 + y_host.numel() * 8), "d2h_bytes_per_step": 4,
                 "ms_per_step": train_e2e_ms / n_train},
-        "gpu_launches_per_step": fwd_l + bwd_l + 5, "final_loss": final_loss,
+        "gpu_launches_per_step": int(getattr(ts, "launches_per_step", 0)) or (fwd_l + bwd_l + 5), "final_loss": final_loss,
         "model_flops_per_step": ts.eng.conv_flops(),
         "achieved_model_tflops": ts.eng.conv_flops() * n_train / (train_ms / 1e3) / 1e12,
     }
@@ -342,8 +342,8 @@ def run_gpu(args):
                                      f"{T_STEPS // ReverseLoop.STEPS_PER_GRAPH} replays per bench step; programmatic dependent launch between kernels"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(xT_host.numel() * 4 + y_host.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(args.steps * T_STEPS * (launches_per_reverse_step + 4)),
-            "launches_per_reverse_step": launches_per_reverse_step + 4,
+            "gpu_launches": int(args.steps * T_STEPS * (loop.launches_per_step or launches_per_reverse_step + 5)),
+            "launches_per_reverse_step": int(loop.launches_per_step or launches_per_reverse_step + 5),
             "clocks": clk,
             "roofline": roof,
             "model_flops_per_sample": eng.conv_flops() / B * T_STEPS,

@@ -41,6 +41,9 @@ int td_device_check(int device);
 /* Programmatic dependent launch (every kernel's launch latency and on-chip prologue overlap the tail of the preceding kernel
  * of the stream; on by default, TD_PDL=0 in the environment turns it off).  Returns the previous setting. */
 int td_set_pdl(int on);
+/* Number of kernels this library has launched (or captured into a graph) in this process so far; bench.py reads the
+ * difference over one eager step to report `gpu_launches`. */
+int64_t td_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Elementwise DDPM kernels (HBM-bound)

@@ -1,5 +1,6 @@
 // Library-level entry points: version, error reporting, architecture gate.
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -39,6 +40,8 @@ int require_sm100() {
 }
 
 static int g_pdl = -1;      // -1: not read yet
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
     if (g_pdl < 0) {
         const char* e = getenv("TD_PDL");
@@ -54,6 +57,8 @@ extern "C" int td_set_pdl(int on) {
     td::g_pdl = on ? 1 : 0;
     return prev;
 }
+
+extern "C" int64_t td_launch_count(void) { return (int64_t)td::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int td_version(void) { return 100; }
 extern "C" const char* td_last_error_string(void) { return td::g_err; }

@@ -63,6 +63,7 @@ __device__ __forceinline__ void pdl_sync() {
 }
 
 bool pdl_enabled();      // api.cu: TD_PDL environment switch (default on), read once
+void count_launch();     // api.cu: bumps the counter td_launch_count() reports
 
 struct LaunchCfg {
     dim3 grid, block;
@@ -83,6 +84,7 @@ inline void launch(void (*kernel)(P...), const LaunchCfg& c, A&&... args) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    count_launch();
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);       // errors surface through launch_status()
 }
 

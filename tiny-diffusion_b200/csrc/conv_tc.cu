@@ -327,7 +327,39 @@ int tc_plan_init(td_conv_plan* p) {
     p->tiles_w = tiles_w;
     p->tiles_h = (int)ceil_div(d.height, bbh);
     p->tiles_n = (int)ceil_div(d.batch, bbn);
-    p->block_n = pick_block_n(d.cout);
+    // N tile and split-K together.  The per-tap kernel is bound by L2 -> SM operand delivery (~45 B/clk/SM):
+    // one 64-channel stage moves 16 KB of activations + BLOCK_N x 128 B of weights, so a stage costs ~ (16 + BLOCK_N / 8) KB
+    // / 45 B/clk, and a layer costs waves x stages-per-CTA x that (+ a second pass when the K loop is split).  On the 8x8 and
+    // 4x4 maps the 256-wide tile leaves most SMs idle (256 -> 256 @ 8x8: 64 CTAs), a narrower tile fills them.
+    const int64_t m_tiles = (int64_t)p->tiles_w * p->tiles_h * p->tiles_n;
+    const int iters = 9 * (d.cin / 64);
+    const bool may_split = d.splitk_ws && !d.stats;
+    auto split_for = [&](int64_t ctas) {
+        // Too few tiles to fill the 148 SMs: split the K loop (taps x channel chunks) across CTAs.  Each split writes an fp32
+        // partial tile; a second kernel sums them in fixed order and applies the epilogue.  Short K loops lose more to the
+        // second pass than they gain.
+        if (!may_split || 2 * ctas > kNumSMs || iters < 64) return 1;
+        int sk = (int)(kNumSMs / ctas);
+        if (sk > 8) sk = 8;
+        while (sk > 1 && iters / sk < 8) --sk;
+        return sk;
+    };
+    int best_bn = pick_block_n(d.cout), best_sk = split_for(m_tiles * (d.cout / best_bn));
+    if (!getenv("TD_TC_BLOCK_N")) {
+        double best_cost = 0.0;
+        bool have = false;
+        for (int bn : {256, 128, 64}) {
+            if (d.cout % bn) continue;
+            const int64_t ctas = m_tiles * (d.cout / bn);
+            const int sk = split_for(ctas);
+            const double stage = (16.0 + bn / 8.0) * 1024.0 / 45.0;
+            const double waves = (double)ceil_div(ctas * sk, (int64_t)kNumSMs);
+            double cost = waves * (double)ceil_div(iters, sk) * std::max(stage, 4.0 * (bn == 256 ? 128.0 : 64.0));
+            if (sk > 1) cost += 12000.0;                     // the reduce pass (~6 us)
+            if (!have || cost < best_cost * 0.97) { have = true; best_cost = cost; best_bn = bn; best_sk = sk; }
+        }
+    }
+    p->block_n = best_bn;
     p->n_tiles = d.cout / p->block_n;
     const int stage_bytes = TC_A_STAGE + p->block_n * 128;
     int stages = (200 * 1024) / stage_bytes;
@@ -335,23 +367,13 @@ int tc_plan_init(td_conv_plan* p) {
     // Enough tiles for two waves of CTAs: keep two CTAs resident per SM (<= ~100 KB of stages each, TMEM
     // 2 x BLOCK_N <= 512 columns) so that one CTA's epilogue overlaps the other's main loop.  Measured on
     // B200 (tools/tc_sweep.py): 28x28 128->128 70 -> 45 us, 16x16 512->128 60 -> 37 us.
-    const int64_t ctas = (int64_t)p->tiles_w * p->tiles_h * p->tiles_n * p->n_tiles;
+    const int64_t ctas = m_tiles * p->n_tiles;
     if (ctas > kNumSMs) {
         int s2 = (100 * 1024) / stage_bytes;
         if (s2 >= 2) stages = s2 > 4 ? 4 : s2;
     }
-    // Too few tiles to fill the 148 SMs (4x4 / 7x7 / 8x8 feature maps at batch 128): split the K loop
-    // (taps x channel chunks) across CTAs.  Each split writes an fp32 partial tile; a second kernel sums
-    // them in fixed order and applies the epilogue.  Operand traffic per CTA is unchanged.
-    p->split_k = 1;
-    const int iters = 9 * (d.cin / 64);
-    if (d.splitk_ws && !d.stats && 2 * ctas <= kNumSMs && iters >= 64) {     // short K loops lose more to the second pass
-        int sk = (int)(kNumSMs / ctas);
-        if (sk > 8) sk = 8;
-        while (sk > 1 && iters / sk < 8) --sk;
-        if (const char* e = getenv("TD_TC_SPLIT_K")) { int v = atoi(e); if (v >= 1 && v <= sk) sk = v; }
-        p->split_k = sk;
-    }
+    p->split_k = best_sk;
+    if (const char* e = getenv("TD_TC_SPLIT_K")) { int v = atoi(e); if (v >= 1 && v <= split_for(ctas)) p->split_k = v; }
     if (const char* e = getenv("TD_TC_STAGES")) { int v = atoi(e); if (v >= 2 && v <= stages) stages = v; }
     p->stages = stages;
     p->smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 32 + 2 * p->block_n * 4 + 1024;

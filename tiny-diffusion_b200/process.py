@@ -80,6 +80,7 @@ class ReverseLoop:
         self.seed = torch.zeros(2, device=x.device, dtype=torch.int64)
         self._key = None
         self._z_ref = None
+        self.launches_per_step = 0
 
     def _step(self, z_ptr, z_stride, seed_ptr):
         st = L.stream_ptr()
@@ -141,9 +142,11 @@ class ReverseLoop:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.td_launch_count())
         with torch.cuda.graph(g):
             for _ in range(k):
                 self._step(z_ptr, z_stride, seed_ptr)
+        self.launches_per_step = (int(self.lib.td_launch_count()) - n0) // k      # library kernels per reverse step
         self.x.copy_(x_saved)
         self.t_dev.copy_(t_saved)
         self.graphs[k] = g

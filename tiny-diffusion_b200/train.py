@@ -694,6 +694,7 @@ class TrainStep:
         for lo, hi, r in self.buckets:
             self._ready_at.setdefault(max(r, 0), []).append((lo, hi))
         self.graph = None
+        self.launches_per_step = 0
 
     def _adam_tables(self):
         dev = self.device
@@ -803,8 +804,10 @@ class TrainStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = int(self.lib.td_launch_count())
             with torch.cuda.graph(g):
                 self._body()
+            self.launches_per_step = int(self.lib.td_launch_count()) - n0         # library kernels in one train step
             with torch.no_grad():
                 for p, s in zip(self.params, saved):
                     p.copy_(s)

@@ -60,7 +60,12 @@ def launches(path):
 
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """path: a .ncu-rep, or the CSV that `ncu -i rep --page raw --csv` printed (made on the GPU box when the report itself is
+    too large to bring back)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = _csv_rows(out)
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
