@@ -498,6 +498,12 @@ class UNetTrainEngine:
         bwd.append(("wgrad:join", lambda st: self.sync_wgrad_stream()))
         self.fwd_ops, self.bwd_ops = fwd, bwd
 
+    def wgrad_side_stream(self):
+        """The stream the weight gradients run on (None when they stay on the main stream or none was enqueued yet)."""
+        if self.wgrad_streams != 1 or not self._wg_forked[0]:
+            return None
+        return self._side_w[0]
+
     def sync_wgrad_stream(self) -> None:
         """Make the current stream wait for every weight gradient enqueued so far (no-op when none is outstanding)."""
         for lane in range(2):
@@ -695,6 +701,7 @@ class TrainStep:
             self._ready_at.setdefault(max(r, 0), []).append((lo, hi))
         self.graph = None
         self.launches_per_step = 0
+        self._ar_on_side = os.environ.get("TD_DP_AR_SIDE", "1") != "0"
 
     def _adam_tables(self):
         dev = self.device
@@ -736,10 +743,24 @@ class TrainStep:
         self._works = []
         for i, (_, fn) in enumerate(e.bwd_ops):
             fn(st)
-            if self._ready_at.get(i):
-                e.sync_wgrad_stream()          # the bucket's weight gradients come from the second stream
-            for lo, hi in self._ready_at.get(i, ()):
-                self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
+            ready = self._ready_at.get(i)
+            if not ready:
+                continue
+            # A bucket holds weight gradients (side stream) and BatchNorm / bias gradients (main stream).  Enqueue its
+            # all-reduce from the side stream once that stream has also seen the main stream's progress: the main chain
+            # never waits for a weight gradient here, only the final join before Adam does.
+            ar_stream = e.wgrad_side_stream() if self._ar_on_side else None
+            if ar_stream is None:
+                e.sync_wgrad_stream()
+                for lo, hi in ready:
+                    self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
+                continue
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ar_stream.wait_event(ev)
+            with torch.cuda.stream(ar_stream):
+                for lo, hi in ready:
+                    self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
 
     def _allreduce(self):
         if self.world == 1:
