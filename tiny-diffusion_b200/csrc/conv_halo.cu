@@ -98,6 +98,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2 groups][2][2][N_TILE]
     float* s_stats = s_affine + 8 * N_TILE;                // [2 groups][4 warps][2][N_TILE]
+    float* s_tile = s_stats + 16 * N_TILE;                 // [8 epilogue warps][32 rows][36]: output staging (see the epilogue)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u_lo = (int)((int64_t)blockIdx.x * p.units / gridDim.x);
@@ -276,6 +277,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 const int w_ = tw * p.bw + w_rel, h_ = th * p.bh + h_rel, n_ = tn * p.BN + n_rel;
                 const bool valid = n_rel < p.BN && h_rel < p.bh && w_rel < p.bw && w_ < p.W && h_ < p.H && n_ < p.B;
                 const int64_t pix = ((int64_t)n_ * p.H + h_) * p.W + w_;
+                // Output staging.  A thread owns one position (= one TMEM lane), so direct stores touch 32 different cache
+                // lines per warp instruction (16 bytes each) and the epilogue becomes LSU-bound: 4096 line accesses per fp32
+                // subtile against 4608 MMA cycles at K = 576.  Each 32 x 32 chunk is transposed through a padded shared-memory
+                // tile instead and leaves as whole 128-byte (fp32) / 64-byte (bf16) row segments, 4 / 8 rows per instruction.
+                float* tile = s_tile + (grp * 4 + (warp - 3 - grp * 4)) * (32 * 36);
+                const int64_t my_off = valid ? pix * p.ldy + p.y_coff + nt * N_TILE : (int64_t)-1;
+                const bool out_bf16 = p.y_dtype == TD_BF16;
+                const int rpi = out_bf16 ? 8 : 4;                      // rows per store instruction
+                const int lpr = 32 / rpi;                              // lanes per row
+                int64_t row_off[8];                                    // element offset of the row this lane stores in pass `it`
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = it * rpi + lane / lpr;
+                    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(my_off & 0xffffffffll), row & 31);
+                    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)my_off >> 32), row & 31);
+                    row_off[it] = (int64_t)(((uint64_t)hi << 32) | lo);
+                }
 #pragma unroll 1
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                     uint32_t rr[32];
@@ -296,17 +314,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (valid) {
-                        if (p.y_dtype == TD_BF16) {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+                    (void)cbase;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 8) Vec<__nv_bfloat16>::pack(v + i).store(dst + i);
-                        } else {
-                            float* dst = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + cbase;
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(tile + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    __syncwarp();
+                    if (out_bf16) {
+                        const int col = (lane & 3) * 8;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) Vec<float>::pack(v + i).store(dst + i);
+                        for (int it = 0; it < 4; ++it) {
+                            const int row = it * 8 + (lane >> 2);
+                            const float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
+                            const float4 b = *reinterpret_cast<const float4*>(tile + row * 36 + col + 4);
+                            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                            if (row_off[it] >= 0)
+                                Vec<__nv_bfloat16>::pack(f).store(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + col);
+                        }
+                    } else {
+                        const int col = (lane & 7) * 4;
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int row = it * 4 + (lane >> 3);
+                            const float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
+                            if (row_off[it] >= 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row_off[it] + c0 + col) = a;
                         }
                     }
+                    __syncwarp();
                     if (p.stats) {
                         float sq[32];
 #pragma unroll
@@ -443,7 +475,7 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->h_na = g.G == 3 ? 6 : 4;        // dx layout: a box group lasts only three taps, keep three groups in flight
     if (const char* e = getenv("TD_TC_HALO_NA")) { int v = atoi(e); if (v >= 2 && v <= 8) p->h_na = v; }
     const int b_stage = n_tile * 128;
-    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (8 + 16) * n_tile * 4 + 1024;
+    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (8 + 16) * n_tile * 4 + 8 * 32 * 36 * 4 + 1024;
     int nb = (226 * 1024 - fixed) / (b_stage + 16);
     if (nb > 8) nb = 8;
     if (const char* e = getenv("TD_TC_HALO_NB")) { int v = atoi(e); if (v >= 2 && v <= nb) nb = v; }
