@@ -144,20 +144,58 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int64_t pix = ((int64_t)n_ * p.H + h_) * p.W + w_;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
+        // Output staging (as in conv_halo.cu): a thread owns one position, so direct stores would touch 32 cache lines per
+        // warp instruction.  Every 32 x 32 chunk is transposed through a padded tile -- in the pipeline stages, idle by now --
+        // and leaves as whole 128-byte (fp32) / 64-byte (bf16) row segments.
+        float* tile = reinterpret_cast<float*>(smem_a) + 8 * BLOCK_N + q * (32 * 36);
+        const bool out_bf16 = !p.ws && p.y_dtype == TD_BF16;
+        float* const out_f32 = p.ws ? p.ws + (int64_t)blockIdx.z * ((int64_t)p.B * p.H * p.W) * p.cout : reinterpret_cast<float*>(p.y);
+        const int64_t ld_out = p.ws ? p.cout : p.ldy;
+        const int64_t my_off = valid ? pix * ld_out + (p.ws ? 0 : p.y_coff) + nt * BLOCK_N : (int64_t)-1;
+        const int rpi = out_bf16 ? 8 : 4, lpr = 32 / rpi;          // rows per store instruction, lanes per row
+        int64_t row_off[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rw_ = it * rpi + lane / lpr;
+            const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)(my_off & 0xffffffffll), rw_ & 31);
+            const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)my_off >> 32), rw_ & 31);
+            row_off[it] = (int64_t)(((uint64_t)hi << 32) | lo);
+        }
+        auto store_chunk = [&](const float* v, int c0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(tile + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            __syncwarp();
+            if (out_bf16) {
+                const int col = (lane & 3) * 8;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int rw_ = it * 8 + (lane >> 2);
+                    const float4 a = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col);
+                    const float4 b = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col + 4);
+                    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    if (row_off[it] >= 0) Vec<__nv_bfloat16>::pack(f).store(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + col);
+                }
+            } else {
+                const int col = (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rw_ = it * 4 + (lane >> 3);
+                    const float4 a = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col);
+                    if (row_off[it] >= 0) *reinterpret_cast<float4*>(out_f32 + row_off[it] + c0 + col) = a;
+                }
+            }
+            __syncwarp();
+        };
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
-            const int cbase = nt * BLOCK_N + c0;
             if (p.ws) {          // split-K: raw fp32 partial, the affine / activation run in the reduce kernel
-                if (valid) {
-                    float* dst = p.ws + ((int64_t)blockIdx.z * ((int64_t)p.B * p.H * p.W) + pix) * p.cout + cbase;
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                }
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                store_chunk(v, c0);
                 continue;
             }
             float v[32];
@@ -174,17 +212,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (valid) {
-                if (p.y_dtype == TD_BF16) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.ldy + p.y_coff + cbase;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) Vec<__nv_bfloat16>::pack(v + j).store(dst + j);
-                } else {
-                    float* dst = reinterpret_cast<float*>(p.y) + pix * p.ldy + p.y_coff + cbase;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) Vec<float>::pack(v + j).store(dst + j);
-                }
-            }
+            store_chunk(v, c0);
             if (p.stats) {
                 // per-channel sum / sum of squares over this warp's 32 rows, from the fp32 accumulators;
                 // the pipeline stages are idle by now, so their shared memory stages the 4 warps' partials

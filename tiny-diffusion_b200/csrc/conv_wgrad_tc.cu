@@ -187,21 +187,32 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
             const int nch0 = nt * BLOCK_N + c0;
-            if (mch < m_limit) {
-                if (!p.x_on_m) {
-                    // row = cout, columns = cin: 32 consecutive floats
-                    float* dst = ws + ((int64_t)mch * 9 + tap_) * p.cin + nch0;
+            if (p.x_on_m && mch < m_limit) {
+                // row = cin, columns = cout: lanes are consecutive cin -> coalesced per column
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (nch0 + j < p.cin)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                              __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                } else {
-                    // row = cin, columns = cout: lanes are consecutive cin -> coalesced per column
+                for (int j = 0; j < 32; ++j)
+                    if (nch0 + j < p.cout) ws[((int64_t)(nch0 + j) * 9 + tap_) * p.cin + mch] = __uint_as_float(r[j]);
+            }
+            if (!p.x_on_m) {
+                // row = cout, columns = cin.  A thread owns one row, so direct stores would touch 32 cache lines per warp
+                // instruction; the 32 x 32 chunk is transposed through a padded tile in the (idle) operand ring and leaves
+                // as 128-byte row segments, four rows per instruction.
+                float* tile = reinterpret_cast<float*>(smem) + q * (32 * 36);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nch0 + j < p.cout) ws[((int64_t)(nch0 + j) * 9 + tap_) * p.cin + mch] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int col = (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rw_ = it * 4 + (lane >> 3);
+                    const int mrow = mt * 128 + q * 32 + rw_;
+                    const float4 a = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col);
+                    if (mrow < m_limit && nch0 + col < p.cin)
+                        *reinterpret_cast<float4*>(ws + ((int64_t)mrow * 9 + tap_) * p.cin + nch0 + col) = a;
                 }
+                __syncwarp();
             }
         }
         tc_fence_before();
