@@ -246,9 +246,21 @@ pack_weights_multi_kernel(const PackEntry* __restrict__ tab, int n_entries) {
     const int t = blockIdx.x - L.tile_begin;
     const int cb = L.cin / PK_T;
     const int o0 = (t / cb) * PK_T, c0 = (t % cb) * PK_T;
-    for (int i = threadIdx.x; i < PK_T * PK_T * 9; i += 256) {
-        const int o = i / (PK_T * 9), r = i - o * (PK_T * 9);
-        tile[o][r] = L.src[((int64_t)(o0 + o) * L.cin + c0) * 9 + r];
+    // 32 rows of 288 contiguous floats (16-byte aligned: c0 is a multiple of 32): 9 float4 loads per thread, all in flight
+    // before the first shared-memory store (the loop was a chain of 36 dependent-latency scalar loads)
+    constexpr int ROW4 = PK_T * 9 / 4;                           // float4 per row
+    float4 v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int i = threadIdx.x + k * 256;                     // 9 * 256 == 32 * ROW4
+        const int o = i / ROW4, r4 = i - o * ROW4;
+        v[k] = __ldg(reinterpret_cast<const float4*>(L.src + ((int64_t)(o0 + o) * L.cin + c0) * 9) + r4);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int i = threadIdx.x + k * 256;
+        const int o = i / ROW4, r = (i - o * ROW4) * 4;
+        tile[o][r] = v[k].x; tile[o][r + 1] = v[k].y; tile[o][r + 2] = v[k].z; tile[o][r + 3] = v[k].w;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;

@@ -705,7 +705,7 @@ class TrainStep:
 
     def _adam_tables(self):
         dev = self.device
-        CH = 65536
+        CH = 16384          # one CTA per 16 K elements: ~800 CTAs for the UNet, all resident at once (65536 left the pass latency-bound at 4.1 TB/s)
         ptrs_p, ptrs_g, ptrs_m, ptrs_v, numel, ct, co = [], [], [], [], [], [], []
         for i, (p, off) in enumerate(zip(self.params, self.offsets)):
             n = p.numel()
