@@ -299,51 +299,58 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     uint32_t rr[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + j * N_TILE + (uint32_t)c0, rr);
                     tmem_ld_wait();
-                    const int cbase = nt * N_TILE + c0;
-                    float v[32];
+                    // raw accumulators go through the tile; the folded BatchNorm affine and the ReLU are applied after the
+                    // transpose, where a lane owns a fixed group of 8 (bf16) / 4 (fp32) channels for all rows: 4 loads of
+                    // scale / shift per chunk instead of 16 per thread (they were ~25 % of the epilogue's stall samples)
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + c0 + i);
-                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + c0 + i);
-                        v[i] = fmaf(__uint_as_float(rr[i]), sc.x, sh.x);
-                        v[i + 1] = fmaf(__uint_as_float(rr[i + 1]), sc.y, sh.y);
-                        v[i + 2] = fmaf(__uint_as_float(rr[i + 2]), sc.z, sh.z);
-                        v[i + 3] = fmaf(__uint_as_float(rr[i + 3]), sc.w, sh.w);
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    (void)cbase;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(tile + lane * 36 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<uint4*>(tile + lane * 36 + i) = make_uint4(rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
                     __syncwarp();
                     if (out_bf16) {
                         const int col = (lane & 3) * 8;
+                        float sc[8], sh[8];
+                        *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(sc_s + c0 + col);
+                        *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(sc_s + c0 + col + 4);
+                        *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(sh_s + c0 + col);
+                        *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(sh_s + c0 + col + 4);
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             const int row = it * 8 + (lane >> 2);
                             const float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
                             const float4 b = *reinterpret_cast<const float4*>(tile + row * 36 + col + 4);
-                            const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                            float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                f[k] = fmaf(f[k], sc[k], sh[k]);
+                                if (p.relu) f[k] = fmaxf(f[k], 0.f);
+                            }
                             if (row_off[it] >= 0)
                                 Vec<__nv_bfloat16>::pack(f).store(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + col);
                         }
                     } else {
                         const int col = (lane & 7) * 4;
+                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + c0 + col);
+                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + c0 + col);
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int row = it * 4 + (lane >> 3);
-                            const float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
+                            float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
+                            a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
+                            if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
                             if (row_off[it] >= 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row_off[it] + c0 + col) = a;
                         }
                     }
                     __syncwarp();
                     if (p.stats) {
-                        float sq[32];
+                        // statistics of the stored values (train mode stores the raw conv output: scale / shift NULL, no ReLU)
+                        float v[32], sq[32];
+                        const bool affine = p.scale || p.shift;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            v[i] = valid ? v[i] : 0.f;
+                            float t = __uint_as_float(rr[i]);
+                            if (affine) t = fmaf(t, sc_s[c0 + i], sh_s[c0 + i]);
+                            if (p.relu) t = fmaxf(t, 0.f);
+                            v[i] = valid ? t : 0.f;
                             sq[i] = v[i] * v[i];
                         }
                         const float cs = warp_column_sums(v, lane);
