@@ -281,7 +281,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 // lines per warp instruction (16 bytes each) and the epilogue becomes LSU-bound: 4096 line accesses per fp32
                 // subtile against 4608 MMA cycles at K = 576.  Each 32 x 32 chunk is transposed through a padded shared-memory
                 // tile instead and leaves as whole 128-byte (fp32) / 64-byte (bf16) row segments, 4 / 8 rows per instruction.
-                float* tile = s_tile + (grp * 4 + (warp - 3 - grp * 4)) * (32 * 36);
+                const uint32_t tile_s = smem_u32(s_tile + (warp - 3) * (32 * 36));
+                const uint32_t sc_u = smem_u32(sc_s), sh_u = smem_u32(sh_s);
                 const int64_t my_off = valid ? pix * p.ldy + p.y_coff + nt * N_TILE : (int64_t)-1;
                 const bool out_bf16 = p.y_dtype == TD_BF16;
                 const int rpi = out_bf16 ? 8 : 4;                      // rows per store instruction
@@ -303,21 +304,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     // transpose, where a lane owns a fixed group of 8 (bf16) / 4 (fp32) channels for all rows: 4 loads of
                     // scale / shift per chunk instead of 16 per thread (they were ~25 % of the epilogue's stall samples)
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<uint4*>(tile + lane * 36 + i) = make_uint4(rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
+                    for (int i = 0; i < 32; i += 4) sts128(tile_s + (uint32_t)(lane * 36 + i) * 4u, rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
                     __syncwarp();
                     if (out_bf16) {
                         const int col = (lane & 3) * 8;
                         float sc[8], sh[8];
-                        *reinterpret_cast<float4*>(sc) = *reinterpret_cast<const float4*>(sc_s + c0 + col);
-                        *reinterpret_cast<float4*>(sc + 4) = *reinterpret_cast<const float4*>(sc_s + c0 + col + 4);
-                        *reinterpret_cast<float4*>(sh) = *reinterpret_cast<const float4*>(sh_s + c0 + col);
-                        *reinterpret_cast<float4*>(sh + 4) = *reinterpret_cast<const float4*>(sh_s + c0 + col + 4);
+                        *reinterpret_cast<float4*>(sc) = lds128(sc_u + (uint32_t)(c0 + col) * 4u);
+                        *reinterpret_cast<float4*>(sc + 4) = lds128(sc_u + (uint32_t)(c0 + col + 4) * 4u);
+                        *reinterpret_cast<float4*>(sh) = lds128(sh_u + (uint32_t)(c0 + col) * 4u);
+                        *reinterpret_cast<float4*>(sh + 4) = lds128(sh_u + (uint32_t)(c0 + col + 4) * 4u);
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
                             const int row = it * 8 + (lane >> 2);
-                            const float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
-                            const float4 b = *reinterpret_cast<const float4*>(tile + row * 36 + col + 4);
+                            const float4 a = lds128(tile_s + (uint32_t)(row * 36 + col) * 4u);
+                            const float4 b = lds128(tile_s + (uint32_t)(row * 36 + col + 4) * 4u);
                             float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
@@ -329,12 +329,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         }
                     } else {
                         const int col = (lane & 7) * 4;
-                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + c0 + col);
-                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + c0 + col);
+                        const float4 sc = lds128(sc_u + (uint32_t)(c0 + col) * 4u);
+                        const float4 sh = lds128(sh_u + (uint32_t)(c0 + col) * 4u);
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int row = it * 4 + (lane >> 3);
-                            float4 a = *reinterpret_cast<const float4*>(tile + row * 36 + col);
+                            float4 a = lds128(tile_s + (uint32_t)(row * 36 + col) * 4u);
                             a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
                             if (p.relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
                             if (row_off[it] >= 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row_off[it] + c0 + col) = a;
