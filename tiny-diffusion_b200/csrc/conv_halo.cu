@@ -295,17 +295,43 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)my_off >> 32), row & 31);
                     row_off[it] = (int64_t)(((uint64_t)hi << 32) | lo);
                 }
-#pragma unroll 1
-                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-                    uint32_t rr[32];
-                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + j * N_TILE + (uint32_t)c0, rr);
-                    tmem_ld_wait();
+                // Software pipeline over the 32-column chunks: the TMEM load of chunk k+1 is in flight while chunk k is read
+                // back from the tile and stored (LDTM was the top stall of the epilogue); one register set suffices because
+                // the read-back works from shared memory.
+                uint32_t rr[32];
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + j * N_TILE;
+                auto stage = [&](int c0) {            // registers -> tile (+ train-mode statistics of this chunk)
                     // raw accumulators go through the tile; the folded BatchNorm affine and the ReLU are applied after the
                     // transpose, where a lane owns a fixed group of 8 (bf16) / 4 (fp32) channels for all rows: 4 loads of
                     // scale / shift per chunk instead of 16 per thread (they were ~25 % of the epilogue's stall samples)
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) sts128(tile_s + (uint32_t)(lane * 36 + i) * 4u, rr[i], rr[i + 1], rr[i + 2], rr[i + 3]);
+                    if (p.stats) {
+                        // statistics of the stored values (train mode stores the raw conv output: scale / shift NULL, no ReLU)
+                        float v[32], sq[32];
+                        const bool affine = p.scale || p.shift;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float t = __uint_as_float(rr[i]);
+                            if (affine) t = fmaf(t, sc_s[c0 + i], sh_s[c0 + i]);
+                            if (p.relu) t = fmaxf(t, 0.f);
+                            v[i] = valid ? t : 0.f;
+                            sq[i] = v[i] * v[i];
+                        }
+                        const float cs = warp_column_sums(v, lane);
+                        const float cq = warp_column_sums(sq, lane);
+                        stats_g[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
+                        stats_g[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
+                    }
                     __syncwarp();
+                };
+                tmem_ld_32x32(t_addr, rr);
+                tmem_ld_wait();
+                stage(0);
+#pragma unroll 1
+                for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+                    const bool more = c0 + 32 < N_TILE;
+                    if (more) tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32), rr);
                     if (out_bf16) {
                         const int col = (lane & 3) * 8;
                         float sc[8], sh[8];
@@ -341,22 +367,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         }
                     }
                     __syncwarp();
-                    if (p.stats) {
-                        // statistics of the stored values (train mode stores the raw conv output: scale / shift NULL, no ReLU)
-                        float v[32], sq[32];
-                        const bool affine = p.scale || p.shift;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float t = __uint_as_float(rr[i]);
-                            if (affine) t = fmaf(t, sc_s[c0 + i], sh_s[c0 + i]);
-                            if (p.relu) t = fmaxf(t, 0.f);
-                            v[i] = valid ? t : 0.f;
-                            sq[i] = v[i] * v[i];
-                        }
-                        const float cs = warp_column_sums(v, lane);
-                        const float cq = warp_column_sums(sq, lane);
-                        stats_g[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
-                        stats_g[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
+                    if (more) {
+                        tmem_ld_wait();
+                        stage(c0 + 32);
                     }
                 }
                 if (p.stats) {
