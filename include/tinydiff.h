@@ -330,6 +330,10 @@ typedef struct {
 } td_gemm_args;
 int64_t td_gemm_f32_workspace(int M, int N, int K);
 int td_gemm_f32(const td_gemm_args* a, void* stream);
+/* Which kernel family td_gemm_f32 would run for these arguments: 0 = fp32 FFMA (exact fp32 products), 1 = tcgen05 kind::tf32
+ * (M >= 2048, both operands K-major, 16-byte aligned rows; 10-bit operand mantissas, ~1e-3 relative; TD_GEMM_TF32=0 in the
+ * environment keeps everything on path 0). */
+int td_gemm_f32_path(const td_gemm_args* a);
 int td_colsum_f32(const float* x, int64_t ldx, float* out, int M, int N, int accumulate, void* stream);
 int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, int act, void* stream);
 /* dst[i,j] (+)= src[i,j] on strided fp32 matrices (residual-branch gradients) */

@@ -269,3 +269,100 @@ def test_bn1d_kernels(dev, M, N, relu):
                             ye.data_ptr(), N, M, N, 1e-5, 0.1, 0, int(relu), st))
     want = F.batch_norm(x, rm_r, rv_r, gamma, beta, False, 0.1, 1e-5)
     assert rel(ye, F.relu(want) if relu else want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# large-batch path: tcgen05 kind::tf32 GEMM (linear_tc.cu), M >= 2048
+# ------------------------------------------------------------------------------------------
+def _gemm_args(A, W, out, bias=None, act=0, pre=None, residual=None, gidx=None, gtab=None, accumulate=0):
+    from tinydiff import _lib as L
+    g = L.GemmArgs()
+    M, K = A.shape
+    N = W.shape[0]
+    g.M, g.N, g.K, g.alpha = M, N, K, 1.0
+    g.A, g.a_rs, g.a_cs = A.data_ptr(), A.stride(0), 1
+    g.B, g.b_rs, g.b_cs = W.data_ptr(), 1, W.stride(0)
+    g.C, g.ldc, g.bias, g.act = out.data_ptr(), out.stride(0), L.ptr(bias), act
+    g.pre_out, g.ld_pre = L.ptr(pre), (pre.stride(0) if pre is not None else 0)
+    g.residual, g.ldr = L.ptr(residual), (residual.stride(0) if residual is not None else 0)
+    g.gather_idx, g.gather_table, g.ld_table = L.ptr(gidx), L.ptr(gtab), (gtab.stride(0) if gtab is not None else 0)
+    g.accumulate, g.splitk_ws = accumulate, None
+    return g
+
+
+@pytest.mark.parametrize("M,N,K", [(2048, 64, 64), (4096, 256, 256), (4100, 520, 1000), (2500, 36, 40), (8192, 1024, 256)])
+def test_gemm_tf32_large_batch(dev, M, N, K):
+    """y = act(x W^T + b) + residual + table[idx] (+ C) on the tensor-core path against fp64; ragged M / N / K tails
+    (TMA zero fill), strided A (a view into a wider buffer), every epilogue option.  TF32 operands: rel-L2 <= 2e-3."""
+    import ctypes as C
+    from tinydiff import _lib as L
+    lib = L.load()
+    g_ = torch.Generator().manual_seed(M + N + K)
+    wide = torch.randn(M, K + 8, generator=g_).to(dev)
+    A = wide[:, 4:4 + K]                                    # row stride K + 8, 16-byte aligned start
+    W = (torch.randn(N, K, generator=g_) / K ** 0.5).to(dev)
+    bias = torch.randn(N, generator=g_).to(dev)
+    res = torch.randn(M, N, generator=g_).to(dev)
+    tab = torch.randn(10, N, generator=g_).to(dev)
+    idx = torch.randint(0, 10, (M,), generator=g_).to(dev)
+    ref_pre = A.double() @ W.double().t() + bias.double()
+    for act, name in ((L.ACT_NONE, "none"), (L.ACT_GELU, "gelu"), (L.ACT_SILU, "silu"), (L.ACT_RELU, "relu")):
+        out = torch.full((M, N), 0.5, device=dev)
+        pre = torch.empty(M, N, device=dev)
+        g = _gemm_args(A, W, out, bias=bias, act=act, pre=pre, residual=res, gidx=idx, gtab=tab, accumulate=1)
+        assert lib.td_gemm_f32_path(C.byref(g)) == 1, "not on the tensor-core path"
+        L.check(lib.td_gemm_f32(C.byref(g), L.stream_ptr()), "td_gemm_f32")
+        a = {"none": lambda v: v, "gelu": lambda v: F.gelu(v), "silu": F.silu, "relu": F.relu}[name](ref_pre)
+        want = a + res.double() + tab.double()[idx] + 0.5
+        assert rel(pre, ref_pre) < 2e-3, name
+        assert rel(out, want) < 2e-3, name
+    # plain product, no epilogue; and the small-batch call stays on the exact fp32 kernels
+    out = torch.empty(M, N, device=dev)
+    g = _gemm_args(A, W, out)
+    L.check(lib.td_gemm_f32(C.byref(g), L.stream_ptr()), "td_gemm_f32")
+    assert rel(out, A.double() @ W.double().t()) < 2e-3
+    small = _gemm_args(A[:128], W, out[:128])
+    assert lib.td_gemm_f32_path(C.byref(small)) == 0
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_eval_forward_large_batch_tf32(dev, name):
+    """Eval forward at 4096 samples (tensor-core GEMMs) against the CPU oracle: rel-L2 <= 1e-2, the tolerance of the other
+    reduced-precision engine; the same model at 128 samples stays within the fp32 tolerance."""
+    mod, model, sd = build(name, dev, **KW[name])
+    B = 4096
+    inp = make_inputs(name, B)
+    with torch.no_grad():
+        got = model(inp["noise"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+        want = FWD[name](sd, inp["noise"], inp["t"], inp["cond"], None)
+        small = model(inp["noise"][:128].to(dev), inp["t"][:128].to(dev), inp["cond"][:128].to(dev))
+    assert torch.isfinite(got).all()
+    assert rel(got, want) < 1e-2
+    assert rel(small, want[:128]) < 5e-4
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_train_step_large_batch_tf32(dev, name):
+    """Fused train step at 2048 samples: forward and data-gradient GEMMs on the tensor-core path (transposed weight copies),
+    weight gradients on the FFMA kernels.  Loss and updated parameters against the CPU oracle's Adam step: 1e-2 / update
+    direction agreement (Adam's first step is lr * sign(g))."""
+    from tinydiff.train import TrainStep
+    mod, model, sd = build(name, dev, train=True, **KW[name])
+    B = 2048
+    fp = mod.ForwardProcess()
+    inp = make_inputs(name, B)
+    ts = TrainStep(model, fp, B, dev, lr=1e-3, use_graph=True)
+    loss = float(ts(inp["x0"], inp["cond"], t=inp["t"], noise=inp["noise"]))
+    fwd = (lambda leaf, x, t, c, ns: FWD[name](leaf, x, t, c, ns, True))
+    want_loss, grads, _, _ = O.dense_loss_and_grads(fwd, sd, inp["x0"], inp["t"], inp["noise"], fp.alphas_cumprod, inp["cond"])
+    assert abs(loss - float(want_loss)) / float(want_loss) < 1e-2
+    after = model.state_dict()
+    agree, total = 0, 0
+    for k, g in grads.items():
+        if float(g.norm()) < 1e-7:                            # Linear biases in front of a BatchNorm1d: zero up to rounding noise
+            continue
+        big = g.abs() > 0.1 * g.abs().max()                  # entries whose sign is not at the mercy of rounding
+        step = (after[k].cpu() - sd[k])[big]
+        agree += int((torch.sign(step) == -torch.sign(g[big])).sum())
+        total += int(big.sum())
+    assert total > 1000 and agree / total > 0.99, (agree, total)

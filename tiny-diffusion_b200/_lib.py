@@ -116,6 +116,7 @@ _SIGS = {
     "td_nchw_chansum": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "td_gemm_f32_workspace": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "td_gemm_f32": (C.c_int, [C.POINTER(GemmArgs), _P]),
+    "td_gemm_f32_path": (C.c_int, [_P]),
     "td_colsum_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_act_bwd_f32": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
     "td_add2d_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),

@@ -1,11 +1,13 @@
 // fp32 dense layers of the conditioning head, the latent-MLP denoiser and the DiT parity path:
 // a strided SIMT GEMM with a fused epilogue (bias, activation, residual, embedding-row gather),
 // column sums (bias gradients), activation backward, LayerNorm and BatchNorm1d.
-// These are small (<= 0.1 GFLOP at the reference batch sizes) and latency-bound; the bf16
-// tensor-core path for large batches lives in linear_tc.cu.
+// These are small (<= 0.1 GFLOP at the reference batch sizes) and latency-bound; the tensor-core
+// (kind::tf32) path for batches of 2048 and more lives in linear_tc.cu.
 #include "common.cuh"
 
 namespace td {
+
+bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status);   // linear_tc.cu
 
 constexpr int G_BM = 64, G_BN = 64, G_BK = 16, G_THREADS = 256;
 
@@ -566,6 +568,10 @@ extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
     TD_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "td_gemm_f32: bad shape %d %d %d", a->M, a->N, a->K);
     TD_CHECK_ARG(a->act >= 0 && a->act <= TD_ACT_SIGMOID, "td_gemm_f32: bad activation %d", a->act);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        int st = TD_OK;
+        if (td::gemm_tf32_try(a, s, &st)) return st;       // large batches, K-major operands: tcgen05 kind::tf32 (linear_tc.cu)
+    }
     int nz = 1;
     const int64_t ws = td_gemm_f32_workspace(a->M, a->N, a->K);
     if (ws > 0 && a->splitk_ws) nz = (int)(ws / ((int64_t)a->M * a->N));

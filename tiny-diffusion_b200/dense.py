@@ -204,6 +204,7 @@ class DenseEngine:
 
         scratch_w = max(self.widths.values())
         self._scratch = torch.zeros(self.B, scratch_w, device=self.device)
+        self._wt: List[Tuple[torch.Tensor, torch.Tensor, int, int]] = []
         written["eps"] = [(0, self.widths["eps"])]               # seeded by the loss
         for op in reversed(self._ops):
             k = op["kind"]
@@ -247,9 +248,17 @@ class DenseEngine:
                 if op["xg"]:
                     gx = self.grad(op["x"])
                     af = acc_flag(op["x"])
-                    wp = w.data_ptr() + 4 * r0 * K
-                    steps.append(self._gemm(B, K, N, g_pre.data_ptr(), g_pre.stride(0), 1, wp, K, 1, gx.data_ptr(),
-                                            gx.stride(0), accumulate=af))             # dx (+)= g W
+                    if B >= 2048:
+                        # large batch: dx (+)= g W through the tensor-core GEMM, which wants both operands K-major
+                        # (kind::tf32, linear_tc.cu): a transposed copy of the weight rows, refreshed once per backward
+                        wt = torch.empty(K, N, device=self.device)
+                        self._wt.append((wt, w, r0, r1))
+                        steps.append(self._gemm(B, K, N, g_pre.data_ptr(), g_pre.stride(0), 1, wt.data_ptr(), 1, N,
+                                                gx.data_ptr(), gx.stride(0), accumulate=af))
+                    else:
+                        wp = w.data_ptr() + 4 * r0 * K
+                        steps.append(self._gemm(B, K, N, g_pre.data_ptr(), g_pre.stride(0), 1, wp, K, 1, gx.data_ptr(),
+                                                gx.stride(0), accumulate=af))         # dx (+)= g W
                 bwd.append((f"{name}:bwd", lambda st, steps=steps: [s(st) for s in steps] and None))
             elif k == "bn":
                 x, out, bn = self.val(op["x"]), self.val(op["out"]), op["bn"]
@@ -291,6 +300,12 @@ class DenseEngine:
                     bwd.append((f"{op['name']}:bwd", lambda st, s=g_out, d=gx, af=af: L.check(
                         lib.td_add2d_f32(s.data_ptr(), s.stride(0), d.data_ptr(), d.stride(0), B, s.shape[1], af, st),
                         "td_add2d_f32")))
+        if self._wt:
+            def refresh_wt(st):
+                with torch.no_grad():
+                    for wt, w, r0, r1 in self._wt:
+                        wt.copy_(w.detach()[r0:r1].t())
+            bwd.insert(0, ("weights^T", refresh_wt))
         return bwd
 
     # ------------------------------------------------------------------ UNetTrainEngine-compatible surface
