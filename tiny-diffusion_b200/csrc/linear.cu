@@ -3,6 +3,8 @@
 // column sums (bias gradients), activation backward, LayerNorm and BatchNorm1d.
 // These are small (<= 0.1 GFLOP at the reference batch sizes) and latency-bound; the tensor-core
 // (kind::tf32) path for batches of 2048 and more lives in linear_tc.cu.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace td {
@@ -458,7 +460,10 @@ bn1d_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restric
     }
     if (j < N) {
         const float mu = s_mean[lane], rs = s_rstd[lane], ga = gamma[j], be = beta[j];
-        for (int i = w; i < M; i += 8) {
+        // eval mode is purely elementwise: gridDim.y splits the rows (a 65536-row batch on N / 32 CTAs used 2-16 SMs)
+        const int rows_per = (M + (int)gridDim.y - 1) / (int)gridDim.y;
+        const int i_lo = blockIdx.y * rows_per, i_hi = min(M, i_lo + rows_per);
+        for (int i = i_lo + w; i < i_hi; i += 8) {
             float v = (x[(int64_t)i * ldx + j] - mu) * rs * ga + be;
             if (relu) v = fmaxf(v, 0.f);
             y[(int64_t)i * ldy + j] = v;
@@ -667,7 +672,10 @@ extern "C" int td_bn1d_fwd(const float* x, int64_t ldx, const float* gamma, cons
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && gamma && beta && y && M > 0 && N > 0, "td_bn1d_fwd: bad args");
     TD_CHECK_ARG(training || (running_mean && running_var), "td_bn1d_fwd: eval mode needs running statistics");
-    td::launch(bn1d_fwd_kernel, td::LaunchCfg((N + 31) / 32, 256, 0, (cudaStream_t)stream), x, ldx, gamma, beta, running_mean, running_var,
+    // train mode needs the whole column in one CTA (two-pass statistics in fixed order); eval mode splits the rows
+    const int gx = (N + 31) / 32;
+    const int gy = training ? 1 : std::max(1, std::min((M + 255) / 256, (4 * kNumSMs + gx - 1) / gx));
+    td::launch(bn1d_fwd_kernel, td::LaunchCfg(dim3((unsigned)gx, (unsigned)gy), 256, 0, (cudaStream_t)stream), x, ldx, gamma, beta, running_mean, running_var,
                                                                      save_mean, save_rstd, y, ldy, M, N, eps, momentum,
                                                                      training, relu);
     return launch_status("bn1d_fwd");
