@@ -99,6 +99,13 @@ class DenseEngine:
         self._ops.append({"kind": "copy", "name": name, "x": x, "out": out, "acc": int(accumulate)})
 
     # ------------------------------------------------------------------ plan construction
+    def _bn_streaming(self, op, x, N: int) -> bool:
+        """Train-mode BatchNorm1d + ReLU of a large batch on the many-CTA NHWC BatchNorm kernels: needs a contiguous
+        input and a channel count the 16-byte-vector kernels accept (4 * 2^k <= 1024)."""
+        lanes = N // 4
+        return (self.training and self.B >= 2048 and bool(op["relu"]) and x.stride(0) == N and N % 4 == 0
+                and lanes & (lanes - 1) == 0 and lanes <= 256)
+
     def _gemm(self, M, N, K, A, a_rs, a_cs, Bm, b_rs, b_cs, Cm, ldc, bias=None, act=0, pre=None, ld_pre=0, res=None,
               ldr=0, gidx=None, gtab=None, ldt=0, accumulate=0):
         g = L.GemmArgs()
@@ -153,6 +160,26 @@ class DenseEngine:
                 self._saved[op["name"]] = sv
                 tr = int(self.training)
                 mom = float(bn.momentum if bn.momentum is not None else 0.1)
+
+                if self._bn_streaming(op, x, N):
+                    # large batch, train mode: the conv engine's BatchNorm kernels on the [B][N] matrix (many-CTA partial
+                    # sums -> finalize -> apply) instead of td_bn1d_fwd, whose one CTA per 32 columns walks the whole batch
+                    rows = int(lib.td_chan_reduce_rows(L.TD_F32, B, N))
+                    sv.update({"scale": torch.zeros(N, device=self.device), "shift": torch.zeros(N, device=self.device),
+                               "coef": torch.zeros(3, N, device=self.device),
+                               "part": torch.zeros((rows * 2 + 1) * N, device=self.device), "rows": rows})
+
+                    def fs(st, x=x, out=out, bn=bn, sv=sv, N=N, mom=mom, rows=rows):
+                        L.check(lib.td_bn_stats(x.data_ptr(), L.TD_F32, N, 0, B, N, sv["part"].data_ptr(), 1, st), "td_bn_stats")
+                        L.check(lib.td_bn_finalize(sv["part"].data_ptr(), rows, N, B, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                                   None, float(bn.eps), mom, bn.running_mean.data_ptr(),
+                                                   bn.running_var.data_ptr(), bn.num_batches_tracked.data_ptr(),
+                                                   sv["scale"].data_ptr(), sv["shift"].data_ptr(), sv["mean"].data_ptr(),
+                                                   sv["rstd"].data_ptr(), st), "td_bn_finalize")
+                        L.check(lib.td_bn_relu_apply(x.data_ptr(), sv["scale"].data_ptr(), sv["shift"].data_ptr(),
+                                                     out.data_ptr(), L.TD_F32, out.stride(0), 0, B, N, 1, st), "td_bn_relu_apply")
+                    fwd.append((op["name"], fs))
+                    continue
 
                 def f(st, x=x, out=out, bn=bn, sv=sv, N=N, tr=tr, mom=mom, relu=int(op["relu"])):
                     L.check(lib.td_bn1d_fwd(x.data_ptr(), x.stride(0), bn.weight.data_ptr(), bn.bias.data_ptr(),
@@ -268,6 +295,21 @@ class DenseEngine:
                 dg = self.pgrad[self._pname[id(bn.weight)]]
                 db = self.pgrad[self._pname[id(bn.bias)]]
                 N = x.shape[1]
+                if "part" in sv:                    # large batch: the conv engine's BatchNorm backward kernels (see the forward)
+                    assert gx.stride(0) == N
+
+                    def bs(st, x=x, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db, N=N):
+                        L.check(lib.td_bn_relu_bwd_reduce(g_out.data_ptr(), g_out.stride(0), 0, x.data_ptr(), L.TD_F32,
+                                                          sv["scale"].data_ptr(), sv["shift"].data_ptr(), sv["mean"].data_ptr(),
+                                                          B, N, sv["part"].data_ptr(), st), "td_bn_relu_bwd_reduce")
+                        L.check(lib.td_bn_bwd_finalize(sv["part"].data_ptr(), sv["rows"], N, B, sv["scale"].data_ptr(),
+                                                       sv["mean"].data_ptr(), sv["rstd"].data_ptr(), dg.data_ptr(),
+                                                       db.data_ptr(), sv["coef"].data_ptr(), st), "td_bn_bwd_finalize")
+                        L.check(lib.td_bn_relu_bwd_apply(g_out.data_ptr(), g_out.stride(0), 0, x.data_ptr(), L.TD_F32,
+                                                         sv["scale"].data_ptr(), sv["shift"].data_ptr(), sv["coef"].data_ptr(),
+                                                         gx.data_ptr(), B, N, st), "td_bn_relu_bwd_apply")
+                    bwd.append((f"{op['name']}:bwd", bs))
+                    continue
                 bwd.append((f"{op['name']}:bwd", lambda st, x=x, out=out, bn=bn, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db,
                             N=N, relu=int(op["relu"]): L.check(
                     lib.td_bn1d_bwd(g_out.data_ptr(), g_out.stride(0), x.data_ptr(), x.stride(0), out.data_ptr(),
