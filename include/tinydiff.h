@@ -339,6 +339,8 @@ int td_act_bwd_f32(const float* dy, const float* pre, float* dx, int64_t n, int 
 /* dst[i,j] (+)= src[i,j] on strided fp32 matrices (residual-branch gradients) */
 int td_add2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int accumulate,
                  void* stream);
+/* dst[j, i] = src[i, j] on strided fp32 matrices (rows <= 2^21) */
+int td_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream);
 /* nn.Dropout / attention-weight dropout at L=1 (diffusion_transformer.py:19,27,29): out = x*keep/(1-p), one
  * Bernoulli draw per `group` consecutive columns; Philox keyed by seed_ptr[0], subsequence seed_ptr[1].
  * Applying the same call to a gradient is the backward. */

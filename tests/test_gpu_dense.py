@@ -366,3 +366,32 @@ def test_train_step_large_batch_tf32(dev, name):
         agree += int((torch.sign(step) == -torch.sign(g[big])).sum())
         total += int(big.sum())
     assert total > 1000 and agree / total > 0.99, (agree, total)
+
+
+@pytest.mark.parametrize("rows,cols", [(2048, 256), (4100, 20), (33, 1000)])
+def test_transpose_kernel(dev, rows, cols):
+    from tinydiff import _lib as L
+    lib = L.load()
+    src = torch.randn(rows, cols + 4, device=dev)[:, 2:2 + cols]            # strided source
+    dst = torch.zeros(cols, rows + 8, device=dev)
+    L.check(lib.td_transpose_f32(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, L.stream_ptr()),
+            "td_transpose_f32")
+    assert torch.equal(dst[:, :rows], src.t())
+    assert float(dst[:, rows:].abs().max()) == 0.0
+
+
+def test_weight_gradient_gemm_takes_tensor_core_path(dev):
+    """dW = g^T x with the batch as the reduction dimension: eligible once both operands are transposed (K-major)."""
+    import ctypes as C
+    from tinydiff import _lib as L
+    lib = L.load()
+    B, N, K = 4096, 256, 128
+    g_ = torch.Generator().manual_seed(3)
+    g = torch.randn(B, N, generator=g_).to(dev)
+    x = torch.randn(B, K, generator=g_).to(dev)
+    gt, xt = g.t().contiguous(), x.t().contiguous()
+    out = torch.empty(N, K, device=dev)
+    a = _gemm_args(gt, xt, out)                      # A = g^T [N][B], "W" = x^T [K][B]: out = g^T x
+    assert lib.td_gemm_f32_path(C.byref(a)) == 1
+    L.check(lib.td_gemm_f32(C.byref(a), L.stream_ptr()), "td_gemm_f32")
+    assert rel(out, g.double().t() @ x.double()) < 2e-3

@@ -526,6 +526,24 @@ add2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst
     }
 }
 
+// dst[j, i] = src[i, j]: 32 x 32 tiles through shared memory, coalesced on both sides.  Feeds the tensor-core weight
+// gradient of a Linear layer at large batch: dW = dY^T X reduces over the batch, and kind::tf32 wants that dimension
+// contiguous in both operands (linear_tc.cu).
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols) {
+    td::pdl_sync();
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < rows && j0 + tx < cols) tile[r][tx] = src[(int64_t)(i0 + r) * lds + j0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < cols && i0 + tx < rows) dst[(int64_t)(j0 + r) * ldd + i0 + tx] = tile[tx][r];
+}
+
 // nn.Dropout / the attention-weight dropout of nn.MultiheadAttention at sequence length 1
 // (diffusion_transformer.py:19,27,29): out = x * keep / (1 - p), one Bernoulli(1-p) draw per `group`
 // consecutive columns of a row (group 1: elementwise; group = head_dim: per (sample, head)).
@@ -617,6 +635,15 @@ extern "C" int td_add2d_f32(const float* src, int64_t lds, float* dst, int64_t l
     TD_CHECK_ARG(src && dst && rows > 0 && cols > 0, "td_add2d_f32: bad args");
     td::launch(add2d_kernel, td::LaunchCfg(grid1d((int64_t)rows * cols), 256, 0, (cudaStream_t)stream), src, lds, dst, ldd, rows, cols, accumulate);
     return launch_status("add2d");
+}
+
+extern "C" int td_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= rows, "td_transpose_f32: bad args");
+    const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    TD_CHECK_ARG(grid.y <= 65535, "td_transpose_f32: more than 2^21 rows");
+    td::launch(transpose_kernel, td::LaunchCfg(grid, 256, 0, (cudaStream_t)stream), src, lds, dst, ldd, rows, cols);
+    return launch_status("transpose");
 }
 
 extern "C" int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int cols, int group,

@@ -99,6 +99,10 @@ class DenseEngine:
         self._ops.append({"kind": "copy", "name": name, "x": x, "out": out, "acc": int(accumulate)})
 
     # ------------------------------------------------------------------ plan construction
+    def _tscratch(self, which: int, numel: int) -> torch.Tensor:
+        """One of the two scratch vectors that hold the transposed operands of a large-batch weight gradient."""
+        return self._ts[which][:numel]
+
     def _bn_streaming(self, op, x, N: int) -> bool:
         """Train-mode BatchNorm1d + ReLU of a large batch on the many-CTA NHWC BatchNorm kernels: needs a contiguous
         input and a channel count the 16-byte-vector kernels accept (4 * 2^k <= 1024)."""
@@ -232,6 +236,7 @@ class DenseEngine:
         scratch_w = max(self.widths.values())
         self._scratch = torch.zeros(self.B, scratch_w, device=self.device)
         self._wt: List[Tuple[torch.Tensor, torch.Tensor, int, int]] = []
+        self._ts = [torch.empty(self.B * scratch_w, device=self.device) for _ in range(2)] if self.B >= 2048 else None
         written["eps"] = [(0, self.widths["eps"])]               # seeded by the loss
         for op in reversed(self._ops):
             k = op["kind"]
@@ -265,8 +270,18 @@ class DenseEngine:
                         lib.td_act_bwd_f32(s.data_ptr(), pre.data_ptr(), d.data_ptr(), n, act, st), "td_act_bwd_f32"))
                 wg = self.pgrad[self._pname[id(w)]]
                 wgp = wg.data_ptr() + 4 * r0 * K
-                steps.append(self._gemm(N, K, B, g_pre.data_ptr(), 1, g_pre.stride(0), x.data_ptr(), x.stride(0), 1,
-                                        wgp, K))                                       # dW = g^T x
+                if B >= 2048 and B % 4 == 0 and K >= 32:
+                    # large batch: dW = g^T x on the tensor-core GEMM.  The reduction runs over the batch and kind::tf32
+                    # wants it contiguous in both operands: transpose g and x into two scratch matrices first
+                    gt = self._tscratch(0, N * B).view(N, B)
+                    xt = self._tscratch(1, K * B).view(K, B)
+                    steps.append(lambda st, g=g_pre, x=x, gt=gt, xt=xt, N=N, K=K: (
+                        L.check(lib.td_transpose_f32(g.data_ptr(), g.stride(0), gt.data_ptr(), B, B, N, st), "td_transpose_f32"),
+                        L.check(lib.td_transpose_f32(x.data_ptr(), x.stride(0), xt.data_ptr(), B, B, K, st), "td_transpose_f32")))
+                    steps.append(self._gemm(N, K, B, gt.data_ptr(), B, 1, xt.data_ptr(), 1, B, wgp, K))
+                else:
+                    steps.append(self._gemm(N, K, B, g_pre.data_ptr(), 1, g_pre.stride(0), x.data_ptr(), x.stride(0), 1,
+                                            wgp, K))                                   # dW = g^T x
                 if b is not None:
                     bg = self.pgrad[self._pname[id(b)]]
                     bgp = bg.data_ptr() + 4 * r0
