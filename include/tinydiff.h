@@ -327,11 +327,13 @@ typedef struct {
     const int64_t* gather_idx; const float* gather_table; int64_t ld_table;
     int accumulate;
     float* splitk_ws;        /* NULL, or td_gemm_f32_workspace(M,N,K) floats: deterministic split-K */
+    int allow_tf32;          /* 0: exact fp32 products (FFMA kernels); 1: the caller accepts 10-bit operand mantissas, the
+                              * tcgen05 kind::tf32 kernel runs when the operands qualify (see td_gemm_f32_path) */
 } td_gemm_args;
 int64_t td_gemm_f32_workspace(int M, int N, int K);
 int td_gemm_f32(const td_gemm_args* a, void* stream);
 /* Which kernel family td_gemm_f32 would run for these arguments: 0 = fp32 FFMA (exact fp32 products), 1 = tcgen05 kind::tf32
- * (M >= 2048, both operands K-major, 16-byte aligned rows; 10-bit operand mantissas, ~1e-3 relative; TD_GEMM_TF32=0 in the
+ * (allow_tf32 set, both operands K-major, 16-byte aligned rows, M, N, K >= 32; ~1e-3 relative; TD_GEMM_TF32=0 in the
  * environment keeps everything on path 0). */
 int td_gemm_f32_path(const td_gemm_args* a);
 int td_colsum_f32(const float* x, int64_t ldx, float* out, int M, int N, int accumulate, void* stream);

@@ -287,6 +287,7 @@ def _gemm_args(A, W, out, bias=None, act=0, pre=None, residual=None, gidx=None, 
     g.residual, g.ldr = L.ptr(residual), (residual.stride(0) if residual is not None else 0)
     g.gather_idx, g.gather_table, g.ld_table = L.ptr(gidx), L.ptr(gtab), (gtab.stride(0) if gtab is not None else 0)
     g.accumulate, g.splitk_ws = accumulate, None
+    g.allow_tf32 = 1
     return g
 
 
@@ -321,8 +322,11 @@ def test_gemm_tf32_large_batch(dev, M, N, K):
     g = _gemm_args(A, W, out)
     L.check(lib.td_gemm_f32(C.byref(g), L.stream_ptr()), "td_gemm_f32")
     assert rel(out, A.double() @ W.double().t()) < 2e-3
-    small = _gemm_args(A[:128], W, out[:128])
-    assert lib.td_gemm_f32_path(C.byref(small)) == 0
+    exact = _gemm_args(A, W, out)
+    exact.allow_tf32 = 0                                    # the default of every other caller: exact fp32 products
+    assert lib.td_gemm_f32_path(C.byref(exact)) == 0
+    L.check(lib.td_gemm_f32(C.byref(exact), L.stream_ptr()), "td_gemm_f32")
+    assert rel(out, A.double() @ W.double().t()) < 1e-5
 
 
 @pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])

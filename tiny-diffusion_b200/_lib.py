@@ -48,7 +48,7 @@ class GemmArgs(C.Structure):
                 ("C", _P), ("ldc", C.c_int64), ("alpha", C.c_float), ("bias", _P), ("act", C.c_int),
                 ("pre_out", _P), ("ld_pre", C.c_int64), ("residual", _P), ("ldr", C.c_int64),
                 ("gather_idx", _P), ("gather_table", _P), ("ld_table", C.c_int64),
-                ("accumulate", C.c_int), ("splitk_ws", _P)]
+                ("accumulate", C.c_int), ("splitk_ws", _P), ("allow_tf32", C.c_int)]
 
 
 class ConvDesc(C.Structure):

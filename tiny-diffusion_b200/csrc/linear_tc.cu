@@ -8,7 +8,7 @@
 // (a thread owns an accumulator row, so direct stores would touch 32 cache lines per warp instruction; see conv_halo.cu):
 // a lane then owns four consecutive columns of four rows per pass and every global access is a 16-byte vector.
 //
-// Used when the batch dimension (M, or K for the weight gradient) is >= 2048 only (TD_GEMM_TF32=0 disables it): at the reference batch sizes the FFMA kernels of linear.cu are
+// Opt-in per call (td_gemm_args.allow_tf32; the dense engines set it at batch >= 2048; TD_GEMM_TF32=0 disables it): at the reference batch sizes the FFMA kernels of linear.cu are
 // latency-bound anyway and keep the fp32 parity tolerances; at 4096-65536 samples per step they reach 5-7 TFLOP/s.
 // TF32 keeps 10 mantissa bits of each operand: results agree with fp32 to ~1e-3 (the tolerance of the bf16 conv engine is 1e-2).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (warp 2 owns the TMEM allocation).  Two CTAs per SM.
@@ -171,8 +171,8 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // true: the tensor-core path ran (or failed: *status != TD_OK); false: not eligible, the caller falls back to the FFMA kernels
 bool gemm_tf32_eligible(const td_gemm_args* a) {
     static const bool on = []() { const char* e = getenv("TD_GEMM_TF32"); return !(e && atoi(e) == 0); }();
-    if (!on || a->splitk_ws) return false;
-    if (a->M < 2048 && !(a->K >= 2048 && a->M >= 32)) return false;     // the batch is the M (forward, dX) or the K (dW) dimension
+    if (!on || !a->allow_tf32 || a->splitk_ws) return false;            // opt-in per call: the dense engines set it at batch >= 2048
+    if (a->M < 32) return false;
     if (a->a_cs != 1 || a->b_rs != 1) return false;                                  // both operands K-major
     if (a->a_rs % 4 || a->b_cs % 4 || a->N % 4 || a->ldc % 4) return false;          // 16-byte rows for TMA and the epilogue
     if (!aligned16(a->A) || !aligned16(a->B) || !aligned16(a->C)) return false;

@@ -120,6 +120,7 @@ class DenseEngine:
         g.pre_out, g.ld_pre, g.residual, g.ldr = pre, ld_pre, res, ldr
         g.gather_idx, g.gather_table, g.ld_table = gidx, gtab, ldt
         g.accumulate, g.splitk_ws = accumulate, None
+        g.allow_tf32 = int(self.B >= 2048)          # large batches: tcgen05 kind::tf32 GEMM (linear_tc.cu), tolerance 1e-2
         self.flops += 2.0 * M * N * K
         lib = self.lib
         return lambda st, g=g: L.check(lib.td_gemm_f32(C.byref(g), st), "td_gemm_f32")
