@@ -23,6 +23,9 @@
 // that the epilogue of one pair overlaps the main loop of the next.
 // Warp roles: 0 = TMA producer, 1-2 = MMA issuers (one per subtile), 3..6 = epilogue of subtile 0, 7..10 = epilogue of
 // subtile 1 (with one group of four warps the epilogue was as long as the main loop on the K = 576 layers).
+// Epilogue: TMEM -> registers -> one padded 32 x 32 shared-memory tile per warp -> folded BatchNorm affine / ReLU ->
+// whole row segments to global memory (a thread owns one position, so direct stores would hit 32 cache lines per warp
+// instruction); the TMEM load of the next chunk is in flight during the read-back of the current one.
 #include <algorithm>
 
 #include "conv_plan.h"
