@@ -103,6 +103,15 @@ class DenseEngine:
         """One of the two scratch vectors that hold the transposed operands of a large-batch weight gradient."""
         return self._ts[which][:numel]
 
+    def _colsum_part(self, numel: int) -> torch.Tensor:
+        """Partial-sum workspace of the large-batch bias gradients (one buffer, the bias gradients run one after another)."""
+        cur = getattr(self, "_cs_part", None)
+        if cur is None or cur.numel() < numel:
+            # earlier closures keep their (smaller) buffer alive; every step list captures the buffer it was built with
+            cur = torch.zeros(numel, device=self.device)
+            self._cs_part = cur
+        return cur
+
     def _bn_streaming(self, op, x, N: int) -> bool:
         """Train-mode BatchNorm1d + ReLU of a large batch on the many-CTA NHWC BatchNorm kernels: needs a contiguous
         input and a channel count the 16-byte-vector kernels accept (4 * 2^k <= 1024)."""
@@ -286,8 +295,19 @@ class DenseEngine:
                 if b is not None:
                     bg = self.pgrad[self._pname[id(b)]]
                     bgp = bg.data_ptr() + 4 * r0
-                    steps.append(lambda st, s=g_pre, bgp=bgp, n=N: L.check(
-                        lib.td_colsum_f32(s.data_ptr(), s.stride(0), bgp, B, n, 0, st), "td_colsum_f32"))
+                    lanes = N // 4
+                    if (B >= 2048 and N % 4 == 0 and lanes & (lanes - 1) == 0 and lanes <= 256 and g_pre.stride(0) % 4 == 0
+                            and g_pre.data_ptr() % 16 == 0):
+                        # large batch: many-CTA partial column sums + fixed-order finalize (the conv engine's kernels)
+                        # instead of td_colsum_f32, whose one CTA per 32 columns walks the whole batch
+                        rows = int(lib.td_chan_reduce_rows(L.TD_F32, B, N))
+                        part = self._colsum_part((rows * 2 + 1) * N)
+                        steps.append(lambda st, s=g_pre, bgp=bgp, n=N, rows=rows, part=part: (
+                            L.check(lib.td_bn_stats(s.data_ptr(), L.TD_F32, s.stride(0), 0, B, n, part.data_ptr(), 0, st), "td_bn_stats"),
+                            L.check(lib.td_partial_sum(part.data_ptr(), rows, n, 0, bgp, st), "td_partial_sum")))
+                    else:
+                        steps.append(lambda st, s=g_pre, bgp=bgp, n=N: L.check(
+                            lib.td_colsum_f32(s.data_ptr(), s.stride(0), bgp, B, n, 0, st), "td_colsum_f32"))
                 if op["xg"]:
                     gx = self.grad(op["x"])
                     af = acc_flag(op["x"])
