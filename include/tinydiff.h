@@ -74,16 +74,18 @@ int td_mse_grad(const float* pred, const float* target, float* grad, float* loss
  * whole loop is CUDA-graph capturable).  z: injected noise; step t reads z + t*z_step_stride
  * (stride 0: one buffer refilled by the caller each step; stride n: a [T, n] table);
  * if z == NULL and seed_ptr != NULL the noise is drawn in-kernel (Philox, subsequence = t).
+ * A step counter outside [0, num_timesteps) makes the launch a no-op (a graph replayed past t = 0).
+ * Noise rows that are not 16-byte aligned (z_step_stride % 4 != 0) take the scalar path.
  * 16 algorithmic bytes per element (12 at t == 0). */
 int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride,
-                    const float* coef, const int32_t* t_dev, int64_t n, const uint64_t* seed_ptr,
-                    void* stream);
+                    const float* coef, const int32_t* t_dev, int64_t n, int num_timesteps,
+                    const uint64_t* seed_ptr, void* stream);
 /* Classifier-free-guidance reverse step -- an EXTENSION: the reference has no guidance, BASELINE.json's
  * config 2 names it.  x and eps hold a doubled batch, rows [0, n) conditional and rows [n, 2n) null-label:
  *   e = eps_u + guidance*(eps_c - eps_u);  x <- c1[t]*(x - c2[t]*e) + c3[t]*z, stored to both halves.
  * n = elements of ONE half (multiple of 4); z / Philox indexing as td_psample_step over n elements. */
 int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z, int64_t z_step_stride,
-                        const float* coef, const int32_t* t_dev, const uint64_t* seed_ptr, void* stream);
+                        const float* coef, const int32_t* t_dev, int num_timesteps, const uint64_t* seed_ptr, void* stream);
 /* t_dev[0] += delta ; used between captured steps. */
 int td_counter_add(int32_t* t_dev, int32_t delta, void* stream);
 
@@ -91,15 +93,36 @@ int td_counter_add(int32_t* t_dev, int32_t delta, void* stream);
  * Tensors are described by a device-resident table: for chunk c (one CTA's worth of work)
  * chunk_tensor[c] / chunk_offset[c] give the tensor id and element offset; per tensor the four
  * pointer arrays give p, g, m, v.  `step_dev[0]` is the 1-based step (read on the device so the
- * launch can be graph-captured); grad_scale multiplies g first (1/world_size or clip factor,
- * read from grad_scale_dev[0] if non-NULL).  If `bf16_shadow` is non-NULL, each updated
+ * launch can be graph-captured); the learning rate is lr_dev[0] when lr_dev is non-NULL (a device
+ * scalar, so CosineAnnealingLR -- diffusion_transformer.py:176-177,288; conditional_diffusion_laion.py:
+ * 434-438,473 -- can drive a captured step), else `lr`; grad_scale multiplies g first (1/world_size
+ * and / or the clip factor of td_grad_clip_scale, read from grad_scale_dev[0] if non-NULL).  If `bf16_shadow` is non-NULL, each updated
  * parameter is also written as bf16 at bf16_shadow[tensor][i] (packed operand copy for the
  * tcgen05 convolutions).  28 algorithmic bytes per parameter. */
 int td_adam_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
                   const int64_t* numel, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                   int64_t num_chunks, int64_t chunk_elems, const int32_t* step_dev, float lr,
-                  float beta1, float beta2, float eps, const float* grad_scale_dev,
+                  const float* lr_dev, float beta1, float beta2, float eps, const float* grad_scale_dev,
                   void* const* bf16_shadow, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(parameters, max_norm), conditional_diffusion_laion.py:471, over one flat
+ * gradient buffer g[0, n) (padding must be zero):
+ *   norm_out[0] = pre_scale * ||g||_2 ;  scale_out[0] = pre_scale * min(1, max_norm / (norm + 1e-6))
+ * pre_scale = 1/world_size when g holds the all-reduced SUM of the ranks' gradients, else 1.  scale_out feeds
+ * td_adam_multi's grad_scale_dev, so the clipped gradient is never materialised.  max_norm <= 0: no clipping.
+ * Deterministic two-stage reduction like td_mse_grad (partials: td_grad_clip_num_partials(n) floats; counter: one
+ * zero-initialised uint32 the kernel resets).  4 algorithmic bytes per element. */
+int64_t td_grad_clip_num_partials(int64_t n);
+int td_grad_clip_scale(const float* g, int64_t n, float pre_scale, float max_norm, float* partials,
+                       unsigned int* counter, float* scale_out, float* norm_out, void* stream);
+
+/* t = torch.randint(low, high, (n,)) of the train step (diffusion.py:220) drawn on the device so that the whole
+ * step is graph-capturable: Philox4x32-10 keyed by seed_ptr[0], subsequence seed_ptr[1] | 2^63 (disjoint from the
+ * noise td_qsample draws with the same pair).  td_seed_advance bumps seed_ptr[1] between steps. */
+int td_randint(int64_t* out, int64_t n, int low, int high, const uint64_t* seed_ptr, void* stream);
+int td_seed_advance(uint64_t* seed_ptr, int64_t delta, void* stream);
+/* dst[0, n) = value (device scalars such as the learning rate td_adam_multi reads through lr_dev). */
+int td_fill_f32(float* dst, int64_t n, float value, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Conditioning head: time MLP (+class / text embedding) + the three 1x1 "time_proj" convs.

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from tinydiff.dp import allreduce_mean_, grad_ready_index, plan_buckets, shard_range
+from tinydiff.dp import BucketReducer, grad_ready_index, plan_buckets, shard_range
 
 
 def test_shard_range_partitions():
@@ -79,7 +79,14 @@ def _worker(rank, world, port, q):
         buckets = plan_buckets(offsets, sizes, grad_ready_index(names, ops), cap_elems=512)
         g = torch.Generator().manual_seed(100 + rank)
         flat = torch.randn(off, generator=g)
-        allreduce_mean_(flat, buckets, world)
+        # the exchange exactly as train.TrainStep drives it: buckets all-reduced as the backward plan reaches them
+        red = BucketReducer(flat, buckets)
+        started = 0
+        for i in range(len(ops)):
+            started += red.enqueue_ready(i)
+        assert started == len(buckets)
+        red.wait()
+        flat.mul_(red.grad_scale)
         want = sum(torch.randn(off, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
         q.put((rank, float((flat - want).abs().max())))
     finally:

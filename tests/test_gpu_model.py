@@ -146,7 +146,7 @@ def test_cfg_step_kernel_bit_exact(dev):
         ed, zd = eps.to(dev), z.to(dev)
         t_dev = torch.tensor([t], dtype=torch.int32, device=dev)
         L.check(lib.td_psample_step_cfg(xd.data_ptr(), ed.data_ptr(), n, w, zd.data_ptr(), 0, tab["coef"].data_ptr(),
-                                        t_dev.data_ptr(), None, L.stream_ptr()), "td_psample_step_cfg")
+                                        t_dev.data_ptr(), fp.num_timesteps, None, L.stream_ptr()), "td_psample_step_cfg")
         e = eps[n:] + w * (eps[:n] - eps[n:])
         want = O.p_sample_step(x, e, z, t, fp.betas, fp.alphas, fp.alphas_cumprod)
         assert torch.equal(xd[:n].cpu(), want) and torch.equal(xd[n:].cpu(), want), (t, w)
@@ -183,3 +183,28 @@ def test_cfg_sampler_vs_oracle_composition(dev, precision, tol):
         sample_cfg(model, fp, dev, n_samples=n, y=None)
     with pytest.raises(ValueError):
         sample_cfg(model, fp, dev, n_samples=n, y=y, null_label=11)
+
+
+@pytest.mark.parametrize("precision,final_tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_laion_sampler_vs_oracle(dev, precision, final_tol):
+    """The reverse loop of conditional_diffusion_laion.py:575-587 (text-conditioned, 4x32x32 latents, sinusoidal time
+    embedding, no skip resize) over all 1000 steps with x_T and the per-step noise injected, against the oracle's loop;
+    `vae=None` returns the latents (the AutoencoderKL edge is out of scope)."""
+    name = "conditional_diffusion_laion"
+    mod, model = build(name, dev, precision)
+    sd = init_state_dict(name)
+    n, T = 2, 1000
+    gen = torch.Generator().manual_seed(21)
+    text = torch.randn(n, 768, generator=gen)
+    x_T = torch.randn(n, 4, 32, 32, generator=gen)
+    z = torch.randn(T, n, 4, 32, 32, generator=gen)
+    fp = mod.ForwardProcess()
+    eps_fn = lambda x, t: O.unet_forward(O.UNET_LAION, sd, x, torch.full((n,), t, dtype=torch.long), text)
+    want, _ = O.sample_loop(eps_fn, x_T, z, fp.betas, fp.alphas, fp.alphas_cumprod)
+    got = mod.sample(model, fp, dev, text_embeds=text.to(dev), x_T=x_T, z=z.to(dev))
+    assert got.shape == (n, 4, 32, 32) and not model.training
+    assert rel(got, want) < final_tol
+    eager = mod.sample(model, fp, dev, text_embeds=text.to(dev), x_T=x_T, z=z.to(dev), use_graph=False)
+    assert torch.equal(got, eager)
+    with pytest.raises(ValueError):
+        mod.sample(model, fp, dev)                                    # conditional_diffusion_laion.py:565-566

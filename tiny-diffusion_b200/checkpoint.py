@@ -21,7 +21,12 @@ class CheckpointCompat:
     """Mixin for the drop-in ``nn.Module``s: ``load_state_dict`` accepts the compiled-module key prefix."""
 
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        return super().load_state_dict(strip_compile_prefix(state_dict), strict=strict, assign=assign)
+        out = super().load_state_dict(strip_compile_prefix(state_dict), strict=strict, assign=assign)
+        if assign and hasattr(self, "_engines"):
+            # assign=True swaps the parameter / buffer storages: the plans cache raw device pointers of the old ones
+            self._engines = {}
+        self._weights_gen = getattr(self, "_weights_gen", 0) + 1
+        return out
 
 
 def load_checkpoint(model: torch.nn.Module, path: str, map_location="cpu", strict: bool = True):

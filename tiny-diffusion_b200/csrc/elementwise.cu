@@ -129,14 +129,17 @@ mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target
 __global__ void __launch_bounds__(kEwThreads)
 psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z_base,
                int64_t z_step_stride, const float* __restrict__ coef, const int32_t* __restrict__ t_dev, int64_t n,
-               const uint64_t* __restrict__ seed_ptr) {
+               int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
     td::pdl_sync();
     const int t = t_dev[0];
+    if (t < 0 || t >= num_timesteps) return;          // a graph replayed past t = 0 (or started above T-1) is a no-op
     const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
     const float4 c = reinterpret_cast<const float4*>(coef)[t];
     const float c1 = c.x, c2 = c.y, c3 = c.z;
     const bool use_noise = (t > 0);
-    const int64_t n4 = n >> 2;
+    // 16-byte accesses need every row of the noise table aligned too (odd latent sizes: stride % 4 != 0)
+    const bool vec_ok = (((uintptr_t)x | (uintptr_t)eps | (uintptr_t)z) & 15) == 0;
+    const int64_t n4 = vec_ok ? (n >> 2) : 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
          i += (int64_t)gridDim.x * blockDim.x) {
         float4 xv = reinterpret_cast<const float4*>(x)[i];
@@ -158,8 +161,8 @@ psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float
         o.w = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.w, __fmul_rn(c2, ev.w))), __fmul_rn(c3, zz[3]));
         reinterpret_cast<float4*>(x)[i] = o;
     }
-    if (blockIdx.x == 0) {
-        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+    {   // scalar tail (< 4 elements), or the whole tensor when the noise rows are not 16-byte aligned: grid-strided
+        for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
             float zz = 0.f;
             if (use_noise) {
                 if (z) zz = z[i];
@@ -182,9 +185,10 @@ psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float
 __global__ void __launch_bounds__(kEwThreads)
 psample_cfg_kernel(float* __restrict__ x, const float* __restrict__ eps, int64_t n, float w,
                    const float* __restrict__ z_base, int64_t z_step_stride, const float* __restrict__ coef,
-                   const int32_t* __restrict__ t_dev, const uint64_t* __restrict__ seed_ptr) {
+                   const int32_t* __restrict__ t_dev, int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
     td::pdl_sync();
     const int t = t_dev[0];
+    if (t < 0 || t >= num_timesteps) return;
     const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
     const float4 c = reinterpret_cast<const float4*>(coef)[t];
     const float c1 = c.x, c2 = c.y, c3 = c.z;
@@ -217,6 +221,79 @@ psample_cfg_kernel(float* __restrict__ x, const float* __restrict__ eps, int64_t
     }
 }
 
+// Global gradient L2 norm + clip factor (torch.nn.utils.clip_grad_norm_, conditional_diffusion_laion.py:471) over the flat
+// gradient buffer: per-block partial sums of squares, the last block to finish reduces them in fixed order (deterministic
+// for a given grid) and writes
+//   norm = pre_scale * sqrt(sum g^2)          (pre_scale = 1/world_size: the buffer holds the all-reduced SUM)
+//   scale = pre_scale * min(1, max_norm / (norm + 1e-6))       -> td_adam_multi's grad_scale_dev
+// max_norm <= 0 disables clipping (scale = pre_scale).  4 algorithmic bytes per gradient element.
+__global__ void __launch_bounds__(kEwThreads)
+grad_clip_kernel(const float* __restrict__ g, int64_t n, float pre_scale, float max_norm, float* __restrict__ partials,
+                 unsigned int* __restrict__ counter, float* __restrict__ scale_out, float* __restrict__ norm_out) {
+    td::pdl_sync();
+    float acc = 0.f;
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(g)[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) acc += g[i] * g[i];
+    __shared__ float warp_part[kEwThreads / 32];
+    __shared__ bool is_last;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int i = 0; i < kEwThreads / 32; ++i) s += warp_part[i];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < 32) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) s += (double)__ldcg(&partials[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) {
+            const float norm = pre_scale * (float)sqrt(s);
+            float clip = 1.0f;
+            if (max_norm > 0.f) clip = fminf(max_norm / (norm + 1e-6f), 1.0f);
+            scale_out[0] = pre_scale * clip;
+            if (norm_out) norm_out[0] = norm;
+            *counter = 0u;
+        }
+    }
+}
+
+// t ~ randint(low, high) on the device (diffusion.py:220), Philox keyed by seed_ptr[0], subsequence seed_ptr[1] with the top
+// bit set (so the stream is disjoint from the noise q_sample draws with the same pair).  Our own RNG stream, not torch's.
+__global__ void __launch_bounds__(kEwThreads)
+randint_kernel(int64_t* __restrict__ out, int64_t n, int low, int high, const uint64_t* __restrict__ seed_ptr) {
+    td::pdl_sync();
+    const Philox rng(seed_ptr[0]);
+    const uint64_t sub = seed_ptr[1] | 0x8000000000000000ull;
+    const uint32_t span = (uint32_t)(high - low);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n + 3) / 4; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        rng.gen((uint64_t)i, sub, r);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (4 * i + k < n) out[4 * i + k] = (int64_t)low + (int64_t)__umulhi(r[k], span);      // floor(r * span / 2^32)
+    }
+}
+
+__global__ void __launch_bounds__(kEwThreads) fill_f32_kernel(float* __restrict__ dst, int64_t n, float v) {
+    td::pdl_sync();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+__global__ void seed_advance_kernel(uint64_t* seed, uint64_t delta) {
+    td::pdl_sync(); seed[1] += delta; }
+
 __global__ void counter_add_kernel(int32_t* c, int32_t delta) {
     td::pdl_sync(); c[0] += delta; }
 
@@ -225,7 +302,8 @@ __global__ void __launch_bounds__(kEwThreads)
 adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__ g, float* const* __restrict__ m,
                   float* const* __restrict__ v, const int64_t* __restrict__ numel,
                   const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_offset,
-                  int64_t chunk_elems, const int32_t* __restrict__ step_dev, float lr, float beta1, float beta2,
+                  int64_t chunk_elems, const int32_t* __restrict__ step_dev, float lr_host,
+                  const float* __restrict__ lr_dev, float beta1, float beta2,
                   float eps, const float* __restrict__ grad_scale_dev, void* const* __restrict__ bf16_shadow) {
     td::pdl_sync();
     const int tid = chunk_tensor[blockIdx.x];
@@ -238,6 +316,7 @@ adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__
     __nv_bfloat16* sh = bf16_shadow ? reinterpret_cast<__nv_bfloat16*>(bf16_shadow[tid]) : nullptr;
     if (sh) sh += off;
     const float step = (float)step_dev[0];
+    const float lr = lr_dev ? lr_dev[0] : lr_host;      // device scalar: schedulers change it under a captured graph
     const float bc1 = 1.0f - powf(beta1, step);
     const float bc2 = 1.0f - powf(beta2, step);
     const float step_size = lr / bc1;
@@ -340,24 +419,59 @@ extern "C" int td_mse_grad(const float* pred, const float* target, float* grad, 
 }
 
 extern "C" int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef,
-                               const int32_t* t_dev, int64_t n, const uint64_t* seed_ptr, void* stream) {
+                               const int32_t* t_dev, int64_t n, int num_timesteps, const uint64_t* seed_ptr, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step: null pointer");
-    TD_CHECK_ARG(n > 0, "td_psample_step: n must be positive");
+    TD_CHECK_ARG(n > 0 && num_timesteps > 0, "td_psample_step: n and num_timesteps must be positive");
     td::launch(psample_kernel, td::LaunchCfg(ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream), 
-        x, eps, z, z_step_stride, coef, t_dev, n, seed_ptr);
+        x, eps, z, z_step_stride, coef, t_dev, n, num_timesteps, seed_ptr);
     return launch_status("psample_step");
 }
 
 extern "C" int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z,
-                                   int64_t z_step_stride, const float* coef, const int32_t* t_dev,
+                                   int64_t z_step_stride, const float* coef, const int32_t* t_dev, int num_timesteps,
                                    const uint64_t* seed_ptr, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step_cfg: null pointer");
-    TD_CHECK_ARG(n > 0 && n % 4 == 0, "td_psample_step_cfg: n (elements of one half) must be a positive multiple of 4");
+    TD_CHECK_ARG(n > 0 && n % 4 == 0 && num_timesteps > 0, "td_psample_step_cfg: n (elements of one half) must be a positive multiple of 4");
+    TD_CHECK_ARG(!z || ((((uintptr_t)z) & 15) == 0 && z_step_stride % 4 == 0), "td_psample_step_cfg: noise table rows must be 16-byte aligned");
     td::launch(psample_cfg_kernel, td::LaunchCfg(ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)stream), x, eps, n, guidance, z,
-               z_step_stride, coef, t_dev, seed_ptr);
+               z_step_stride, coef, t_dev, num_timesteps, seed_ptr);
     return launch_status("psample_step_cfg");
+}
+
+extern "C" int64_t td_grad_clip_num_partials(int64_t n) { return ew_grid(std::max<int64_t>(n / 4, 1)); }
+
+extern "C" int td_grad_clip_scale(const float* g, int64_t n, float pre_scale, float max_norm, float* partials,
+                                  unsigned int* counter, float* scale_out, float* norm_out, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(g && partials && counter && scale_out, "td_grad_clip_scale: null pointer");
+    TD_CHECK_ARG(n > 0 && ((((uintptr_t)g) & 15) == 0), "td_grad_clip_scale: n must be positive and g 16-byte aligned");
+    td::launch(grad_clip_kernel, td::LaunchCfg((int)td_grad_clip_num_partials(n), kEwThreads, 0, (cudaStream_t)stream),
+               g, n, pre_scale, max_norm, partials, counter, scale_out, norm_out);
+    return launch_status("grad_clip_scale");
+}
+
+extern "C" int td_randint(int64_t* out, int64_t n, int low, int high, const uint64_t* seed_ptr, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(out && seed_ptr, "td_randint: null pointer");
+    TD_CHECK_ARG(n > 0 && high > low, "td_randint: need n > 0 and high > low");
+    td::launch(randint_kernel, td::LaunchCfg(ew_grid((n + 3) / 4), kEwThreads, 0, (cudaStream_t)stream), out, n, low, high, seed_ptr);
+    return launch_status("randint");
+}
+
+extern "C" int td_fill_f32(float* dst, int64_t n, float value, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(dst && n > 0, "td_fill_f32: bad arguments");
+    td::launch(fill_f32_kernel, td::LaunchCfg(ew_grid(n), kEwThreads, 0, (cudaStream_t)stream), dst, n, value);
+    return launch_status("fill_f32");
+}
+
+extern "C" int td_seed_advance(uint64_t* seed_ptr, int64_t delta, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(seed_ptr, "td_seed_advance: null pointer");
+    td::launch(seed_advance_kernel, td::LaunchCfg(1, 1, 0, (cudaStream_t)stream), seed_ptr, (uint64_t)delta);
+    return launch_status("seed_advance");
 }
 
 extern "C" int td_counter_add(int32_t* t_dev, int32_t delta, void* stream) {
@@ -370,14 +484,14 @@ extern "C" int td_counter_add(int32_t* t_dev, int32_t delta, void* stream) {
 extern "C" int td_adam_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
                              const int64_t* numel, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                              int64_t num_chunks, int64_t chunk_elems, const int32_t* step_dev, float lr,
-                             float beta1, float beta2, float eps, const float* grad_scale_dev,
+                             const float* lr_dev, float beta1, float beta2, float eps, const float* grad_scale_dev,
                              void* const* bf16_shadow, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(p && g && m && v && numel && chunk_tensor && chunk_offset && step_dev, "td_adam_multi: null pointer");
     TD_CHECK_ARG(chunk_elems > 0 && chunk_elems % 4 == 0, "td_adam_multi: chunk_elems must be a positive multiple of 4");
     if (num_chunks == 0) return TD_OK;
     td::launch(adam_multi_kernel, td::LaunchCfg((unsigned)num_chunks, kEwThreads, 0, (cudaStream_t)stream), 
-        p, g, m, v, numel, chunk_tensor, chunk_offset, chunk_elems, step_dev, lr, beta1, beta2, eps,
+        p, g, m, v, numel, chunk_tensor, chunk_offset, chunk_elems, step_dev, lr, lr_dev, beta1, beta2, eps,
         grad_scale_dev, bf16_shadow);
     return launch_status("adam_multi");
 }

@@ -429,11 +429,15 @@ class _DenseTrainFunction(torch.autograd.Function):
         engine.reseed(int(torch.randint(0, 2 ** 62, (1,)).item()) if engine._drop_slots else 0)
         engine.launch_forward()
         ctx.engine = engine
+        engine.generation = getattr(engine, "generation", 0) + 1      # saved tensors are shared per batch size (train.py)
+        ctx.generation = engine.generation
         return engine.eps.clone()
 
     @staticmethod
     def backward(ctx, d_eps):
         eng: DenseEngine = ctx.engine
+        from .train import _check_generation
+        _check_generation(eng, ctx)
         eng.d_eps.copy_(d_eps)
         eng.launch_backward()
         return (None, None, None, None) + tuple(eng.pgrad[k].clone() for k, _ in eng.module.named_parameters())

@@ -63,10 +63,43 @@ def plan_buckets(offsets: List[int], sizes: List[int], ready: List[int], cap_ele
     return buckets
 
 
-def allreduce_mean_(flat: torch.Tensor, buckets: List[Tuple[int, int, int]], world: int, group=None) -> None:
-    """Reference semantics of the data-parallel exchange: every bucket summed over ranks, then / world."""
-    for lo, hi, _ in buckets:
-        torch.distributed.all_reduce(flat[lo:hi], group=group)
-    flat.div_(world)
+class BucketReducer:
+    """The data-parallel gradient exchange of ``train.TrainStep``: the flat gradient buffer cut into
+    ``plan_buckets`` ranges; ``enqueue_ready(i)`` starts the asynchronous all-reduce (sum) of every
+    bucket whose last gradient is final once backward-plan entry ``i`` has been enqueued, ``wait()``
+    makes the current stream (CUDA) / the caller (CPU) wait for all of them.  The mean is taken by the
+    consumer (``grad_scale = 1 / world`` in the fused Adam / clip kernels), not here.
 
+    Backend-agnostic on purpose (NCCL on the GPUs, gloo in the CPU tests): no CUDA calls, the caller
+    picks the stream the collectives are enqueued from."""
 
+    def __init__(self, flat: torch.Tensor, buckets: List[Tuple[int, int, int]], group=None):
+        self.flat, self.buckets, self.group = flat, buckets, group
+        self.world = torch.distributed.get_world_size(group)
+        self.ready_at = {}
+        for lo, hi, r in buckets:
+            self.ready_at.setdefault(max(r, 0), []).append((lo, hi))
+        self.works = []
+
+    def has_ready(self, i: int) -> bool:
+        return i in self.ready_at
+
+    def enqueue_ready(self, i: int) -> int:
+        """Start the all-reduce of the buckets that become final at plan entry ``i``; returns how many."""
+        spans = self.ready_at.get(i, ())
+        for lo, hi in spans:
+            self.works.append(torch.distributed.all_reduce(self.flat[lo:hi], group=self.group, async_op=True))
+        return len(spans)
+
+    def enqueue_all(self) -> None:
+        for i in sorted(self.ready_at):
+            self.enqueue_ready(i)
+
+    def wait(self) -> None:
+        for w in self.works:
+            w.wait()
+        self.works = []
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / self.world

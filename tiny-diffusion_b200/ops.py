@@ -61,7 +61,7 @@ def psample_step(x, eps, z, coef, t: int, seed: Optional[int] = None):
     t_dev = torch.tensor([t], dtype=torch.int32, device=x.device)
     sd = None if seed is None else torch.tensor([seed, 0], dtype=torch.int64, device=x.device)
     L.check(L.load().td_psample_step(x.data_ptr(), eps.contiguous().data_ptr(), L.ptr(z), 0, coef.data_ptr(),
-                                     t_dev.data_ptr(), x.numel(), L.ptr(sd), L.stream_ptr()), "td_psample_step")
+                                     t_dev.data_ptr(), x.numel(), coef.shape[0], L.ptr(sd), L.stream_ptr()), "td_psample_step")
     return x
 
 

@@ -88,11 +88,11 @@ class ReverseLoop:
         if self.guidance is None:
             L.check(self.lib.td_psample_step(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
                                              self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
-                                             seed_ptr, st), "td_psample_step")
+                                             self.p.num_timesteps, seed_ptr, st), "td_psample_step")
         else:
             L.check(self.lib.td_psample_step_cfg(self.x.data_ptr(), self.eps.data_ptr(), self.n, float(self.guidance),
                                                  z_ptr, z_stride, self.tab["coef"].data_ptr(), self.t_dev.data_ptr(),
-                                                 seed_ptr, st), "td_psample_step_cfg")
+                                                 self.p.num_timesteps, seed_ptr, st), "td_psample_step_cfg")
         L.check(self.lib.td_counter_add(self.t_dev.data_ptr(), -1, st), "td_counter_add")
 
     def run(self, z: Optional[torch.Tensor] = None, seed: int = 0, steps: Optional[int] = None) -> None:
@@ -100,6 +100,8 @@ class ReverseLoop:
         z: optional injected noise table [T, *x.shape] (row t used at step t; row 0 unused)."""
         T = self.p.num_timesteps
         steps = T if steps is None else steps
+        if not 0 <= steps <= T:
+            raise ValueError(f"steps must be in [0, {T}] (the loop starts at t = T-1 and ends at t = 0)")
         n = self.n
         if z is not None:
             assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.shape[0] == T

@@ -20,7 +20,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .dp import allreduce_mean_, grad_ready_index, plan_buckets   # noqa: F401
+from .dp import BucketReducer, grad_ready_index, plan_buckets
 from .unet import UNetConfig, _CONVS, _ConvPlan, _pool, alloc_splitk_ws
 
 BN_EPS_DEFAULT = 1e-5
@@ -175,7 +175,8 @@ class UNetTrainEngine:
                 self.w_bwd[name] = torch.zeros(cin, 3, 3, cout, device=self.device, dtype=wdt_b)
 
     def weights_version(self):
-        return tuple(p._version for p in self.module.parameters())
+        # _weights_gen: bumped by TrainStep, whose kernels update the parameters through raw pointers (no _version bump)
+        return (getattr(self.module, "_weights_gen", 0),) + tuple(p._version for p in self.module.parameters())
 
     def refresh_weights(self, force: bool = False) -> None:
         ver = self.weights_version()
@@ -621,15 +622,28 @@ class _UNetTrainFunction(torch.autograd.Function):
         engine.launch_forward()
         ctx.engine = engine
         ctx.n_params = len(params)
+        # activations / BatchNorm statistics live in the engine's buffers, shared by every call at this batch size
+        engine.generation = getattr(engine, "generation", 0) + 1
+        ctx.generation = engine.generation
         return engine.eps.clone()
 
     @staticmethod
     def backward(ctx, d_eps):
         eng: UNetTrainEngine = ctx.engine
+        _check_generation(eng, ctx)
         eng.d_eps.copy_(d_eps)
         eng.launch_backward()
         grads = tuple(eng.pgrad[k].clone() for k, _ in eng.module.named_parameters())
         return (None, None, None, None) + grads
+
+
+def _check_generation(eng, ctx) -> None:
+    if eng.generation != ctx.generation:
+        raise RuntimeError(
+            "tinydiff: backward() of a train-mode forward whose saved activations were overwritten by a later train-mode "
+            f"forward at the same batch size (forward #{ctx.generation}, engine now at #{eng.generation}). The engine keeps "
+            "one set of saved tensors per batch size: call backward() before the next forward (gradient accumulation over "
+            "micro-batches: forward/backward one micro-batch at a time).")
 
 
 def train_engine(model, batch: int, device: torch.device):
@@ -654,26 +668,49 @@ def unet_train_forward(model, x, t, cond):
     return _UNetTrainFunction.apply(eng, x.to(torch.float32).contiguous(), t, cond, *params)
 
 
+class _LRHandle(torch.optim.Optimizer):
+    """A real ``torch.optim.Optimizer`` that owns nothing but the learning rate of a ``TrainStep``: the reference's
+    scheduler lines (``CosineAnnealingLR(optimizer, T_max=num_epochs)`` stepped per epoch, diffusion_transformer.py:
+    176-177,288; per batch with ``eta_min=1e-6``, conditional_diffusion_laion.py:434-438,473) work on it unchanged, and
+    ``TrainStep`` reads ``param_groups[0]["lr"]`` before every step.  ``step()`` is a no-op (the fused kernel updates)."""
+
+    def __init__(self, lr: float, device):
+        self._dummy = torch.nn.Parameter(torch.zeros(1, device=device), requires_grad=False)
+        super().__init__([self._dummy], {"lr": lr})
+
+    def step(self, closure=None):       # noqa: D401
+        return None
+
+
 class TrainStep:
     """Fused train step: ``t ~ randint; x_t, noise = q_sample(x_0, t); eps = model(x_t, t[, y]);
-    loss = mse(eps, noise); backward; Adam`` (diffusion.py:220-236) as one CUDA-graph replay.
+    loss = mse(eps, noise); backward; [clip_grad_norm_;] Adam`` (diffusion.py:220-236;
+    conditional_diffusion_laion.py:463-473) as one CUDA-graph replay.
 
-    ``world_size > 1``: data parallel -- gradients are all-reduced (sum) through ``torch.distributed``
-    (NCCL) in buckets, and the Adam pass scales them by 1/world_size.
+    * ``lr`` lives in a device scalar read by the Adam kernel: ``set_lr()`` / the ``optimizer`` handle (a
+      ``torch.optim.Optimizer`` for the reference's ``CosineAnnealingLR`` lines) change it under the captured graph.
+    * ``max_grad_norm``: ``clip_grad_norm_(parameters, max_grad_norm)`` as one deterministic norm kernel whose clip
+      factor feeds the Adam kernel's gradient scale (the clipped gradient is never materialised).
+    * When neither ``t`` nor ``noise`` is injected both are drawn inside the graph (td_randint + td_qsample's Philox
+      path): no library kernel runs in a step.
+    * ``world_size > 1``: data parallel -- gradients are all-reduced (sum) through ``torch.distributed``
+      (NCCL) in buckets (``dp.BucketReducer``), and the clip / Adam kernels scale them by 1/world_size.
     """
 
     def __init__(self, model, process, batch: int, device, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 use_graph: bool = True, process_group=None, bucket_mb: float = 8.0):
+                 use_graph: bool = True, process_group=None, bucket_mb: float = 8.0,
+                 max_grad_norm: Optional[float] = None, seed: Optional[int] = None):
         self.device = L.require_device(device)
         self.model, self.process, self.B = model, process, batch
         self.lib = L.load()
         self.eng = train_engine(model, batch, self.device)
-        self.lr, self.betas, self.adam_eps = lr, betas, eps
+        self.betas, self.adam_eps = betas, eps
         self.use_graph = use_graph
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
+        self.max_grad_norm = None if max_grad_norm is None else float(max_grad_norm)
         dev = self.device
         e = self.eng
         self.x0 = torch.zeros_like(e.x_in)
@@ -684,6 +721,14 @@ class TrainStep:
         self.counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.grad_scale = torch.full((1,), 1.0 / self.world, device=dev)
+        self.grad_norm = torch.zeros(1, device=dev)              # total norm before clipping (max_grad_norm set)
+        self.lr_dev = torch.full((1,), float(lr), device=dev)
+        self._lr_host = float(lr)
+        self.optimizer = _LRHandle(float(lr), dev)
+        # device RNG of the step (t and the q_sample noise when nothing is injected): Philox key + per-step offset
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # one draw from the CPU generator (torch.manual_seed applies)
+        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
         self.tab = process._tables(dev)
         # flat gradient buffer: pgrad tensors become views of it, so one all-reduce per bucket
         self.names = [k for k, _ in model.named_parameters()]
@@ -700,17 +745,38 @@ class TrainStep:
         e._build()          # rebuild the plans against the flat gradient views
         self.m = torch.zeros_like(self.flat_grad)
         self.v = torch.zeros_like(self.flat_grad)
+        self.clip_partials = torch.zeros(int(self.lib.td_grad_clip_num_partials(self.flat_grad.numel())), device=dev)
+        self.clip_counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self._adam_tables()
         # gradient buckets: contiguous ranges of the flat buffer, each all-reduced as soon as the backward
         # entry that finalises its last gradient has been enqueued (overlaps the rest of the backward)
         ready = grad_ready_index(self.names, [n for n, _ in e.bwd_ops])
         self.buckets = plan_buckets(self.offsets, sizes, ready, int(bucket_mb * 1024 * 1024 / 4))
-        self._ready_at: Dict[int, List[Tuple[int, int]]] = {}
-        for lo, hi, r in self.buckets:
-            self._ready_at.setdefault(max(r, 0), []).append((lo, hi))
-        self.graph = None
+        self.reducer = BucketReducer(self.flat_grad, self.buckets, self.pg) if self.world > 1 else None
+        self.graphs: Dict[bool, "torch.cuda.CUDAGraph"] = {}
         self.launches_per_step = 0
+        self._device_rng = False
         self._ar_on_side = os.environ.get("TD_DP_AR_SIDE", "1") != "0"
+
+    # -- learning rate -----------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return self._lr_host
+
+    @lr.setter
+    def lr(self, value: float) -> None:
+        self.set_lr(value)
+
+    def set_lr(self, lr: float) -> None:
+        """New learning rate from the next step on (device scalar: valid under the captured graph)."""
+        lr = float(lr)
+        self.optimizer.param_groups[0]["lr"] = lr
+        self._push_lr(lr)
+
+    def _push_lr(self, lr: float) -> None:
+        if lr != self._lr_host:
+            L.check(self.lib.td_fill_f32(self.lr_dev.data_ptr(), 1, lr, L.stream_ptr()), "td_fill_f32")
+            self._lr_host = lr
 
     def _adam_tables(self):
         dev = self.device
@@ -732,14 +798,28 @@ class TrainStep:
         self._ct = torch.tensor(ct, dtype=torch.int32, device=dev)
         self._co = t64(co)
         self._chunks, self._chunk_elems = len(ct), CH
+        self._ptrs = tuple(ptrs_p)
+
+    def _check_pointers(self) -> None:
+        """The plans and the Adam tables cache raw parameter pointers: refuse to run on storages that moved
+        (``load_state_dict(assign=True)``, ``.to()``, ``p.data = ...``)."""
+        if tuple(p.data_ptr() for p in self.params) != self._ptrs:
+            raise RuntimeError("tinydiff.TrainStep: a parameter's storage changed since this TrainStep was built "
+                               "(load_state_dict(assign=True) / .to() / .data assignment); build a new TrainStep")
 
     # -- pieces ------------------------------------------------------------------------------
     def _compute(self):
         """q_sample -> forward -> mse + dL/deps -> backward (everything up to the gradients)."""
         e, lib, st = self.eng, self.lib, L.stream_ptr()
         per = e.x_in.numel() // self.B
+        seed_ptr = None
+        if self._device_rng:                                       # diffusion.py:220 and :178 on the device, in the graph
+            seed_ptr = self.rng.data_ptr()
+            L.check(lib.td_randint(e.t_in.data_ptr(), self.B, 0, self.process.num_timesteps, seed_ptr, st), "td_randint")
         L.check(lib.td_qsample(self.x0.data_ptr(), self.noise.data_ptr(), e.t_in.data_ptr(), self.tab["abar"].data_ptr(),
-                               e.x_in.data_ptr(), self.B, per, self.process.num_timesteps, None, st), "td_qsample")
+                               e.x_in.data_ptr(), self.B, per, self.process.num_timesteps, seed_ptr, st), "td_qsample")
+        if self._device_rng:
+            L.check(lib.td_seed_advance(self.rng.data_ptr(), 1, st), "td_seed_advance")
         e.launch_forward()
         n = e.eps.numel()
         L.check(lib.td_mse_grad(e.eps.data_ptr(), self.noise.data_ptr(), e.d_eps.data_ptr(), self.loss.data_ptr(),
@@ -749,42 +829,42 @@ class TrainStep:
             return
         # data parallel: NCCL all-reduce of each bucket is enqueued (async, on NCCL's stream) right after the
         # backward entry that completes it, so the exchange overlaps the remaining backward kernels
-        self._works = []
+        red = self.reducer
         for i, (_, fn) in enumerate(e.bwd_ops):
             fn(st)
-            ready = self._ready_at.get(i)
-            if not ready:
+            if not red.has_ready(i):
                 continue
             # A bucket holds weight gradients (side stream) and BatchNorm / bias gradients (main stream).  Enqueue its
             # all-reduce from the side stream once that stream has also seen the main stream's progress: the main chain
             # never waits for a weight gradient here, only the final join before Adam does.
-            ar_stream = e.wgrad_side_stream() if self._ar_on_side else None
+            ar_stream = e.wgrad_side_stream() if (self._ar_on_side and hasattr(e, "wgrad_side_stream")) else None
             if ar_stream is None:
-                e.sync_wgrad_stream()
-                for lo, hi in ready:
-                    self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
+                if hasattr(e, "sync_wgrad_stream"):
+                    e.sync_wgrad_stream()
+                red.enqueue_ready(i)
                 continue
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             ar_stream.wait_event(ev)
             with torch.cuda.stream(ar_stream):
-                for lo, hi in ready:
-                    self._works.append(torch.distributed.all_reduce(self.flat_grad[lo:hi], group=self.pg, async_op=True))
+                red.enqueue_ready(i)
 
     def _allreduce(self):
-        if self.world == 1:
-            return
-        for w in self._works:
-            w.wait()
-        self._works = []
+        if self.reducer is not None:
+            self.reducer.wait()
 
     def _update(self):
         lib, st = self.lib, L.stream_ptr()
         L.check(lib.td_counter_add(self.step_dev.data_ptr(), 1, st), "td_counter_add")
+        if self.max_grad_norm is not None:                         # conditional_diffusion_laion.py:471
+            L.check(lib.td_grad_clip_scale(self.flat_grad.data_ptr(), self.flat_grad.numel(), 1.0 / self.world,
+                                           self.max_grad_norm, self.clip_partials.data_ptr(), self.clip_counter.data_ptr(),
+                                           self.grad_scale.data_ptr(), self.grad_norm.data_ptr(), st), "td_grad_clip_scale")
         L.check(lib.td_adam_multi(self._tp.data_ptr(), self._tg.data_ptr(), self._tm.data_ptr(), self._tv.data_ptr(),
                                   self._numel.data_ptr(), self._ct.data_ptr(), self._co.data_ptr(), self._chunks,
-                                  self._chunk_elems, self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1],
-                                  self.adam_eps, self.grad_scale.data_ptr(), None, st), "td_adam_multi")
+                                  self._chunk_elems, self.step_dev.data_ptr(), self._lr_host, self.lr_dev.data_ptr(),
+                                  self.betas[0], self.betas[1], self.adam_eps, self.grad_scale.data_ptr(), None, st),
+                "td_adam_multi")
         self.eng.refresh_weights(force=True)
 
     def _body(self):
@@ -794,66 +874,83 @@ class TrainStep:
 
     # -- public ------------------------------------------------------------------------------
     def load(self, x_0, y=None, t=None, noise=None):
-        """Stage one batch: x_0 (any device), optional labels / text, and optionally injected t / noise."""
+        """Stage one batch: x_0 (any device), optional labels / text, and optionally injected t / noise.  With neither
+        injected, t and the noise are drawn on the device inside the step (``seed`` of the constructor)."""
         e = self.eng
         self.x0.copy_(x_0, non_blocking=True)
         if e.cfg.cond == "class":
             e.y_in.copy_(y, non_blocking=True)
         elif e.cfg.cond == "text":
             e.text_in.copy_(y, non_blocking=True)
-        if t is None:
-            e.t_in.copy_(torch.randint(0, self.process.num_timesteps, (self.B,), device=self.device))   # diffusion.py:220
-        else:
-            e.t_in.copy_(t, non_blocking=True)
-        if noise is None:
-            self.noise.normal_()                                                                        # diffusion.py:178
-        else:
-            self.noise.copy_(noise, non_blocking=True)
+        self._device_rng = t is None and noise is None
+        if not self._device_rng:
+            if t is None:
+                e.t_in.copy_(torch.randint(0, self.process.num_timesteps, (self.B,), device=self.device))   # diffusion.py:220
+            else:
+                e.t_in.copy_(t, non_blocking=True)
+            if noise is None:
+                self.noise.normal_()                                                                    # diffusion.py:178
+            else:
+                self.noise.copy_(noise, non_blocking=True)
         if getattr(e, "_drop_slots", None):              # fresh dropout masks (outside the captured graph)
             e.reseed(int(torch.randint(0, 2 ** 62, (1,)).item()))
 
     def run(self) -> torch.Tensor:
         """One optimisation step on the staged batch; returns the (device) loss tensor."""
         self.model.train()
+        self._check_pointers()
+        self._push_lr(float(self.optimizer.param_groups[0]["lr"]))
+        # the step writes parameters and BatchNorm running statistics through raw pointers: invalidate the packed
+        # weights / folded BatchNorm of every eval-mode plan of this model (sample(), ValStep)
+        self.model._weights_gen = getattr(self.model, "_weights_gen", 0) + 1
         if not self.use_graph:
             self.eng.refresh_weights()
             self._body()
             return self.loss
-        if self.graph is None:
-            # world > 1: the bucketed NCCL all-reduces are captured too (every rank captures the same sequence; the
-            # async works become cross-stream edges of the graph), so the data-parallel step is ONE replay per rank
-            self.eng.refresh_weights(force=True)
-            # warm-up outside capture on a side stream (lazy module load / cudaFuncSetAttribute), restoring
-            # every piece of state the step mutates
-            saved = [p.detach().clone() for p in self.params]
-            bufs = [b.detach().clone() for b in self.model.buffers()]
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                self._body()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            n0 = int(self.lib.td_launch_count())
-            with torch.cuda.graph(g):
-                self._body()
-            self.launches_per_step = int(self.lib.td_launch_count()) - n0         # library kernels in one train step
-            with torch.no_grad():
-                for p, s in zip(self.params, saved):
-                    p.copy_(s)
-                for b, s in zip(self.model.buffers(), bufs):
-                    b.copy_(s)
-            self.m.zero_()
-            self.v.zero_()
-            self.step_dev.zero_()
-            self.eng.refresh_weights(force=True)
-            self.graph = g
-        self.graph.replay()
+        g = self.graphs.get(self._device_rng)
+        if g is None:
+            g = self._capture()
+            self.graphs[self._device_rng] = g
+        g.replay()
         return self.loss
 
+    def _capture(self) -> "torch.cuda.CUDAGraph":
+        # world > 1: the bucketed NCCL all-reduces are captured too (every rank captures the same sequence; the
+        # async works become cross-stream edges of the graph), so the data-parallel step is ONE replay per rank
+        self.eng.refresh_weights(force=True)
+        # warm-up outside capture on a side stream (lazy module load / cudaFuncSetAttribute), restoring
+        # every piece of state the step mutates
+        saved = [p.detach().clone() for p in self.params]
+        bufs = [b.detach().clone() for b in self.model.buffers()]
+        state = [t.clone() for t in (self.m, self.v, self.step_dev, self.rng, self.noise, self.eng.t_in)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.td_launch_count())
+        with torch.cuda.graph(g):
+            self._body()
+        self.launches_per_step = int(self.lib.td_launch_count()) - n0         # library kernels in one train step
+        with torch.no_grad():
+            for p, s in zip(self.params, saved):
+                p.copy_(s)
+            for b, s in zip(self.model.buffers(), bufs):
+                b.copy_(s)
+            for t, s in zip((self.m, self.v, self.step_dev, self.rng, self.noise, self.eng.t_in), state):
+                t.copy_(s)
+        self.eng.refresh_weights(force=True)
+        return g
+
+    @property
+    def graph(self):
+        return next(iter(self.graphs.values()), None)
+
     def close(self) -> None:
-        """Drop the captured graph (with world_size > 1 it holds NCCL kernels: release it before the process group)."""
-        self.graph = None
+        """Drop the captured graphs (with world_size > 1 they hold NCCL kernels: release them before the process group)."""
+        self.graphs = {}
 
     def __call__(self, x_0, y=None, t=None, noise=None) -> torch.Tensor:
         self.load(x_0, y, t, noise)

@@ -177,7 +177,9 @@ class UNetEngine:
             self.shift[name] = torch.zeros(cout, device=self.device, dtype=torch.float32)
 
     def weights_version(self):
-        return tuple(p._version for p in self.module.parameters()) + tuple(
+        # _weights_gen: bumped by train.TrainStep, whose kernels update parameters and BatchNorm running statistics through
+        # raw pointers (PyTorch's _version counters do not see those writes)
+        return (getattr(self.module, "_weights_gen", 0),) + tuple(p._version for p in self.module.parameters()) + tuple(
             b._version for b in self.module.buffers())
 
     def refresh_weights(self, force: bool = False) -> None:

@@ -61,10 +61,10 @@ for B, per, tag in ((16384, 4096, "64 M elements"), (128, 784, "bench size, 128 
         12 * n)
     t_dev = torch.tensor([500], dtype=torch.int32, device=dev)
     report(f"psample_step, injected z (16 B/elem) [{tag}]", timeit(lambda: L.check(lib.td_psample_step(
-        x_t.data_ptr(), grad.data_ptr(), noise.data_ptr(), 0, tab["coef"].data_ptr(), t_dev.data_ptr(), n, None, st))), 16 * n)
+        x_t.data_ptr(), grad.data_ptr(), noise.data_ptr(), 0, tab["coef"].data_ptr(), t_dev.data_ptr(), n, 1000, None, st))), 16 * n)
     seed = torch.tensor([7, 0], dtype=torch.int64, device=dev)
     report(f"psample_step, Philox z (12 B/elem)   [{tag}]", timeit(lambda: L.check(lib.td_psample_step(
-        x_t.data_ptr(), grad.data_ptr(), None, 0, tab["coef"].data_ptr(), t_dev.data_ptr(), n, seed.data_ptr(), st))), 12 * n)
+        x_t.data_ptr(), grad.data_ptr(), None, 0, tab["coef"].data_ptr(), t_dev.data_ptr(), n, 1000, seed.data_ptr(), st))), 12 * n)
 
 # fused Adam: one 64 M-element tensor (28 B/param) and the UNet's 11.18 M parameters as 90 tensors' worth of chunks
 for n, tag in ((64 << 20, "64 M parameters"), (11182273 // 4 * 4, "11.18 M parameters (UNet)")):
@@ -81,4 +81,4 @@ for n, tag in ((64 << 20, "64 M parameters"), (11182273 // 4 * 4, "11.18 M param
     gs = torch.ones(1, device=dev)
     report(f"adam_multi (28 B/param)        [{tag}]", timeit(lambda: L.check(lib.td_adam_multi(
         tp.data_ptr(), tg.data_ptr(), tm.data_ptr(), tv.data_ptr(), numel.data_ptr(), ct.data_ptr(), co.data_ptr(), chunks, CH,
-        step.data_ptr(), 1e-3, 0.9, 0.999, 1e-8, gs.data_ptr(), None, st))), 28 * n)
+        step.data_ptr(), 1e-3, None, 0.9, 0.999, 1e-8, gs.data_ptr(), None, st))), 28 * n)
