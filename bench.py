@@ -168,7 +168,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{MODEL} UNet 1x28x28, T={T_STEPS} ancestral sampling, batch {PER_GPU_BATCH} "
-                               "(CPU oracle port of the reference loop body, host cores)"},
+                               f"(CPU oracle PORT of the reference loop body on the host cores; {args.ref_reverse_steps} of the "
+                               f"{T_STEPS} reverse steps timed per bench step, extrapolated x{T_STEPS // args.ref_reverse_steps})",
+                   "per_gpu_batch": PER_GPU_BATCH, "reverse_steps_timed": args.ref_reverse_steps,
+                   "extrapolated": True, "kind": "port"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -327,7 +330,7 @@ def run_gpu(args):
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        roof = conv_roofline(eng, peaks, iters=max(3, args.steps))
+        roof = conv_roofline(eng, peaks, iters=max(3, args.steps), reverse_step_ms=dev_ms / args.steps / T_STEPS)
         ws_bytes = sum(b.numel() * b.element_size() for b in eng.bufs.values())
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -351,6 +354,13 @@ def run_gpu(args):
             "train": train,
         }
         train["roofline_frac_of_sustained_bf16"] = train["achieved_model_tflops"] / peaks["bf16_sustained"]
+        if world == 1:
+            train["roofline"] = train_roofline(ts, peaks, train_ms / n_train)
+            if not args.no_gpu_eager:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(dev, B)
+            if not args.no_configs:
+                ts.close()
+                line["configs"] = other_configs(dev, peaks)
         if world == 1 and not args.no_cpu_baseline:
             v, cores, dt = cpu_reference_samples_per_sec(args.cpu_reverse_steps)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -376,12 +386,15 @@ def run_gpu(args):
     return line
 
 
-def conv_roofline(eng, peaks, iters=3):
+def conv_roofline(eng, peaks, iters=3, reverse_step_ms=None):
     """Per-entry CUDA-event timing of one eval forward (same buffers as the timed loop) -> achieved TFLOP/s of the
     dominant kernels, the tcgen05 implicit-GEMM convolutions (conv3x3_halo_kernel, and conv3x3_tc_kernel on the
     4x4 / 8x8 maps) = algorithmic conv FLOPs / summed conv launch time.  Every plan entry is launched REPS times
     back to back between one event pair, so the host's launch latency is hidden behind the previous launch and
-    the figure is device time (a single launch between events also counts the idle gap before it starts)."""
+    the figure is device time (a single launch between events also counts the idle gap before it starts).
+    These are launches timed alone (clocks near max), so `peak` is the BURST bf16 figure of MEASURED_PEAKS.json;
+    `in_loop` is the same FLOP count over the driver-timed reverse step (graph replay, power-capped clocks, every
+    non-convolution kernel included) against the SUSTAINED figure -- a lower bound on the in-loop conv fraction."""
     from tinydiff import _lib as L
     st = L.stream_ptr()
     names = [n for n, _ in eng.ops]
@@ -404,21 +417,249 @@ def conv_roofline(eng, peaks, iters=3):
     tc_flops = sum(eng.plans[n].flops for n in tc)
     total_ms = sum(acc.values())
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     summ = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.isfile(summ):
         try:
             with open(summ) as f:
-                traffic = json.load(f).get("conv_tc_dram_bytes_per_launch")
+                d = json.load(f)
+            traffic, traffic_src = d.get("conv_tc_dram_bytes_per_launch"), d.get("source")
         except Exception:
             traffic = None
-    return {"bound": "tensor", "kernel": "conv3x3_halo_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, 13 launches per forward)",
-            "achieved": achieved, "peak": peaks["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16",
-            "traffic": traffic, "launches_per_forward": len(tc), "flops_per_forward": tc_flops,
-            "conv_ms_per_forward": tc_ms, "all_kernels_ms_per_forward": total_ms,
-            "conv_share_of_forward": tc_ms / total_ms if total_ms else None,
-            "per_kernel_us": {n: round(acc[n] * 1e3, 2) for n in names}}
+    per_layer = []
+    for n in tc:
+        dsc = eng.plans[n].desc
+        P = dsc.batch * dsc.height * dsc.width
+        byts = 2 * P * dsc.cin + 2 * P * dsc.cout + 2 * 9 * dsc.cin * dsc.cout       # bf16 in + out + weights, each once
+        us = acc[n] * 1e3
+        tf = eng.plans[n].flops / (acc[n] * 1e-3) / 1e12 if acc[n] > 0 else 0.0
+        per_layer.append({"layer": n, "shape": f"{dsc.cin}->{dsc.cout}@{dsc.height}x{dsc.width}", "gflop": round(eng.plans[n].flops / 1e9, 3),
+                          "algorithmic_mb": round(byts / 1e6, 2), "us": round(us, 2), "tflops": round(tf, 1),
+                          "frac_burst": round(tf / peaks["bf16_burst"], 3)})
+    out = {"bound": "tensor", "kernel": "conv3x3_halo_kernel + conv3x3_tc_kernel (tcgen05 implicit GEMM, 13 launches per forward)",
+           "achieved": achieved, "peak": peaks["bf16_burst"],
+           "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+           "peak_source": peaks["source"] + " burst bf16 (launches timed alone)",
+           "frac_of_sustained": achieved / peaks["bf16_sustained"],
+           "traffic": traffic, "traffic_source": traffic_src, "launches_per_forward": len(tc), "flops_per_forward": tc_flops,
+           "conv_ms_per_forward": tc_ms, "all_kernels_ms_per_forward": total_ms,
+           "conv_share_of_forward": tc_ms / total_ms if total_ms else None,
+           "per_layer": per_layer,
+           "per_kernel_us": {n: round(acc[n] * 1e3, 2) for n in names}}
+    if reverse_step_ms:
+        tfl = tc_flops / (reverse_step_ms * 1e-3) / 1e12
+        out["in_loop"] = {"achieved": tfl, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_sustained"],
+                          "note": "conv FLOPs / whole driver-timed reverse step (graph replay; glue kernels included in the time)"}
+    return out
+
+
+def train_roofline(ts, peaks, step_ms, iters=3):
+    """Per-entry timing of the train plan (eager launches, each entry followed by a join of the weight-gradient side stream
+    so the events on the main stream see it) -> which kernels the step spends its time in.  The headline fraction is model
+    FLOPs (forward conv + data gradient + weight gradient) over the driver-timed graph step against the sustained peak."""
+    from tinydiff import _lib as L
+    eng = ts.eng
+    st = L.stream_ptr()
+    eng.launch_forward()
+    eng.launch_backward()
+    torch.cuda.synchronize()
+    acc = {}
+    for tag, ops in (("fwd", eng.fwd_ops), ("bwd", eng.bwd_ops)):
+        for n, fn in ops:
+            if n in ("embed", "embed:bwd", "wgrad:join"):
+                continue
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fn(st)
+            eng.sync_wgrad_stream()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                fn(st)
+                eng.sync_wgrad_stream()
+            b.record()
+            torch.cuda.synchronize()
+            acc[f"{tag}:{n}"] = a.elapsed_time(b) / iters * 1e3
+    def group(k):
+        if ":wgrad" in k:
+            return "weight gradient (wgrad_tc + split-K reduce)"
+        if ":dgrad" in k:
+            return "data gradient conv (tcgen05)"
+        if k.startswith("fwd:bn:"):
+            return "BatchNorm forward (finalize + apply)"
+        if k.startswith("bwd:bn:"):
+            return "BatchNorm backward (reduce + finalize + apply)"
+        if "upcat" in k or "resize" in k or "pool" in k:
+            return "pool / upsample / concat glue"
+        if k.startswith("fwd:") and k.split(":")[1] in ("initial_conv", "final_conv") or k.startswith("bwd:final_conv") \
+                or k.startswith("bwd:initial_conv"):
+            return "1-channel boundary convs (direct kernels)"
+        if k.startswith("fwd:") and (k.split(":")[1] in eng.conv_plans):
+            return "forward conv (tcgen05)"
+        return "other"
+    groups = {}
+    for k, v in acc.items():
+        groups[group(k)] = groups.get(group(k), 0.0) + v
+    total = sum(acc.values())
+    top = sorted(acc.items(), key=lambda kv: -kv[1])[:8]
+    flops = eng.conv_flops()
+    tfl = flops / (step_ms * 1e-3) / 1e12
+    tensor_us = sum(v for g, v in groups.items() if "tcgen05" in g or "weight gradient" in g)
+    limiting = max(((g, v) for g, v in groups.items() if "tcgen05" not in g and "weight gradient" not in g),
+                   key=lambda gv: gv[1], default=("", 0.0))
+    return {"bound": "tensor", "achieved": tfl, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": tfl / peaks["bf16_sustained"], "peak_source": peaks["source"] + " sustained bf16 (kernels timed inside a long step)",
+            "model_flops_per_step": flops, "eager_entry_sum_us": round(total, 1),
+            "tensor_kernel_share_of_entry_time": round(tensor_us / total, 3) if total else None,
+            "limiting_non_tensor_group": {"name": limiting[0], "us_per_step": round(limiting[1], 1)},
+            "group_us": {g: round(v, 1) for g, v in sorted(groups.items(), key=lambda gv: -gv[1])},
+            "top_entries_us": {k: round(v, 1) for k, v in top}}
+
+
+def gpu_eager_baseline(dev, B, reverse_steps=10, train_steps=10):
+    """The on-box GPU bar (SURVEY.md 8d last sentence): the reference's own ops -- the functional
+    restatement in oracle/, i.e. F.conv2d / F.batch_norm / F.interpolate ... through cuDNN / cuBLAS / ATen -- run EAGERLY on
+    this B200, (i) fp32 with PyTorch's defaults (TF32 convolutions, as the reference runs on a GPU) and (ii) under
+    torch.autocast(bfloat16) with channels_last tensors.  A baseline, not part of the product path."""
+    from oracle import ddpm_oracle as O
+    from oracle.fixtures import init_state_dict, make_inputs
+    import torch.nn.functional as F
+    out = {"what": "oracle/ddpm_oracle.py (functional restatement of the reference's NoiseModel / train step) with CUDA tensors: "
+                   "library kernels (cuDNN / cuBLAS / ATen), eager, no CUDA graph",
+           "batch": B, "reverse_steps_timed": reverse_steps, "train_steps_timed": train_steps, "extrapolated": True}
+    sd0 = {k: v.to(dev) for k, v in init_state_dict(MODEL).items()}
+    inp = {k: v.to(dev) for k, v in make_inputs(MODEL, B).items()}
+    betas, alphas, ac = (v.to(dev) for v in O.make_schedule(T_STEPS))
+    for mode in ("fp32_tf32_default", "bf16_autocast_channels_last"):
+        bf = mode.startswith("bf16")
+        sd = dict(sd0)
+        if bf:
+            sd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd0.items()}
+        x = inp["noise"].clone()
+        if bf:
+            x = x.contiguous(memory_format=torch.channels_last)
+        ctx = lambda: torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf)
+
+        def rev_step(x, t):
+            with torch.no_grad(), ctx():
+                eps = O.unet_forward(O.UNET_COND, sd, x, torch.full((B,), t, device=dev, dtype=torch.long), inp["cond"]).float()
+            noise = torch.randn_like(x) if t > 0 else torch.zeros_like(x)
+            return (1 / torch.sqrt(alphas[t])) * (x - ((1 - alphas[t]) / torch.sqrt(1 - ac[t])) * eps) + torch.sqrt(betas[t]) * noise
+        for i in range(3):
+            x = rev_step(x, T_STEPS - 1 - i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reverse_steps):
+            x = rev_step(x, T_STEPS - 4 - i)
+        e1.record()
+        torch.cuda.synchronize()
+        rev_ms = e0.elapsed_time(e1) / reverse_steps
+        # train step: diffusion.py:220-236 with torch autograd + torch.optim.Adam
+        leaf = {k: (v.detach().clone().requires_grad_(True) if O.is_param(k) else v.clone()) for k, v in sd.items()}
+        opt = torch.optim.Adam([v for k, v in leaf.items() if O.is_param(k)], lr=1e-3)
+
+        def train_step():
+            t = torch.randint(0, T_STEPS, (B,), device=dev)
+            noise = torch.randn_like(inp["x0"])
+            x_t = torch.sqrt(ac[t]).view(-1, 1, 1, 1) * inp["x0"] + torch.sqrt(1 - ac[t]).view(-1, 1, 1, 1) * noise
+            if bf:
+                x_t = x_t.contiguous(memory_format=torch.channels_last)
+            stats = {}
+            with ctx():
+                pred = O.unet_forward(O.UNET_COND, leaf, x_t, t, inp["cond"], training=True, new_stats=stats)
+            loss = F.mse_loss(pred.float(), noise)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            for k, v in stats.items():
+                leaf[k] = v
+            return loss
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(train_steps):
+            train_step()
+        e1.record()
+        torch.cuda.synchronize()
+        tr_ms = e0.elapsed_time(e1) / train_steps
+        out[mode] = {"reverse_step_ms": rev_ms, "samples_per_sec_1000step": B / (rev_ms * T_STEPS * 1e-3),
+                     "train_step_ms": tr_ms, "train_imgs_per_sec": B / (tr_ms * 1e-3)}
+        del leaf, opt
+    torch.backends.cudnn.benchmark = False
+    return out
+
+
+def other_configs(dev, peaks):
+    """BASELINE.json configs 3-5 (DiT, latent MLP, LAION latent UNet) at the reference batch and at the largest point of the
+    SURVEY.md 8d sweep: fused train step (one CUDA graph, 10 timed replays) and graph-captured reverse step (T = 50 here;
+    the 1000-step figure is 20x).  Model FLOPs / time against the sustained bf16 peak (the dense denoisers compute in
+    fp32 / tf32; their fraction is quoted against the same bf16 denominator and is latency-bound at the reference batch)."""
+    import importlib
+    from tinydiff.train import TrainStep
+    T = 50
+    res = []
+    for cfg_id, name, batches in ((3, "diffusion_transformer", (128, 65536)), (4, "latent_diffusion", (128, 65536)),
+                                  (5, "conditional_diffusion_laion", (8, 256))):
+        for Bn in batches:
+            rec = {"config": cfg_id, "model": name, "batch": Bn}
+            try:
+                mod = importlib.import_module(f"tinydiff.{name}")
+                torch.manual_seed(0)
+                kw = {"dropout": 0.0} if name == "diffusion_transformer" else {}
+                model = mod.NoiseModel(**kw).to(dev)
+                fp = mod.ForwardProcess(num_timesteps=T)
+                g = torch.Generator().manual_seed(1)
+                if name == "conditional_diffusion_laion":
+                    x0 = (0.18215 * torch.randn(Bn, 4, 32, 32, generator=g)).to(dev)
+                    cond = torch.randn(Bn, 768, generator=g).to(dev)
+                else:
+                    x0 = torch.randn(Bn, 20, generator=g).to(dev)
+                    cond = torch.randint(0, 10, (Bn,), generator=g).to(dev)
+                model.train()
+                ts = TrainStep(model, fp, Bn, dev, use_graph=True,
+                               max_grad_norm=10.0 if name == "conditional_diffusion_laion" else None)
+                ts.load(x0, cond)
+                for _ in range(3):
+                    ts.run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    ts.run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                fl = ts.eng.conv_flops()
+                rec["train"] = {"ms_per_step": ms, "samples_per_sec": Bn / ms * 1e3, "model_tflops": fl / (ms * 1e-3) / 1e12,
+                                "frac_of_sustained_bf16": fl / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+                                "launches_per_step": ts.launches_per_step}
+                ts.close()
+                model.eval()
+                if name == "conditional_diffusion_laion":
+                    f = lambda: mod.sample(model, fp, dev, text_embeds=cond, seed=3)
+                    ffl = model.engine(Bn, dev).conv_flops()
+                else:
+                    f = lambda: mod.sample(None, model, fp, dev, n_samples=Bn, y=cond, seed=3)
+                    ffl = model.engine(Bn, dev, training=False).fwd_flops
+                f()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(2):
+                    f()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / 2 / T * 1e3
+                rec["sampler"] = {"reverse_step_us": us, "samples_per_sec_1000step": Bn / (us * 1e-6 * 1000),
+                                  "model_tflops": ffl / (us * 1e-6) / 1e12,
+                                  "frac_of_sustained_bf16": ffl / (us * 1e-6) / 1e12 / peaks["bf16_sustained"]}
+                del ts, model
+                torch.cuda.empty_cache()
+            except Exception as e:              # keep the sweep going; the failure is part of the record
+                rec["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+            res.append(rec)
+    return res
 
 
 class _StdoutGuard:
@@ -462,6 +703,8 @@ def main():
     ap.add_argument("--cpu-reverse-steps", type=int, default=12)
     ap.add_argument("--ref-reverse-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager cuDNN/ATen baseline on the GPU")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3-5 block")
     ap.add_argument("--train-steps", type=int, default=20, help="train steps per bench step")
     ap.add_argument("--cpu-train-steps", type=int, default=3)
     args = ap.parse_args()
