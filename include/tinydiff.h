@@ -98,11 +98,13 @@ int td_counter_add(int32_t* t_dev, int32_t delta, void* stream);
  * 434-438,473 -- can drive a captured step), else `lr`; grad_scale multiplies g first (1/world_size
  * and / or the clip factor of td_grad_clip_scale, read from grad_scale_dev[0] if non-NULL).  If `bf16_shadow` is non-NULL, each updated
  * parameter is also written as bf16 at bf16_shadow[tensor][i] (packed operand copy for the
- * tcgen05 convolutions).  28 algorithmic bytes per parameter. */
+ * tcgen05 convolutions).  The betas are doubles: bias corrections, step size and (1 - beta) are formed
+ * in double and rounded to fp32 once, as torch does with its Python-float betas.  28 algorithmic bytes
+ * per parameter. */
 int td_adam_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
                   const int64_t* numel, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                   int64_t num_chunks, int64_t chunk_elems, const int32_t* step_dev, float lr,
-                  const float* lr_dev, float beta1, float beta2, float eps, const float* grad_scale_dev,
+                  const float* lr_dev, double beta1, double beta2, float eps, const float* grad_scale_dev,
                   void* const* bf16_shadow, void* stream);
 
 /* torch.nn.utils.clip_grad_norm_(parameters, max_norm), conditional_diffusion_laion.py:471, over one flat

@@ -184,8 +184,10 @@ def test_dit_dropout_train_mode(dev):
     a = model(*args)
     b = model(*args)
     assert rel(a, b) > 1e-3                                   # different masks per call
-    loss = F.mse_loss(a, inp["noise"].to(dev))
+    loss = F.mse_loss(b, inp["noise"].to(dev))              # the latest forward owns the engine's saved tensors
     loss.backward()
+    with pytest.raises(RuntimeError, match="overwritten by a later train-mode forward"):
+        F.mse_loss(a, inp["noise"].to(dev)).backward()
     assert all(torch.isfinite(q.grad).all() for q in model.parameters())
     assert float(model.transformer_blocks[0].attention.in_proj_weight.grad[:512].abs().max()) == 0.0
     want = O.dit_forward(sd, inp["x0"], inp["t"], inp["cond"])

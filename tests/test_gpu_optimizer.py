@@ -95,8 +95,10 @@ def test_grad_clip_scale_vs_torch(dev, n, max_norm, world):
     for _ in range(2):                                               # the counter resets itself: a second launch works
         L.check(lib.td_grad_clip_scale(d.data_ptr(), n, 1.0 / world, max_norm, part.data_ptr(), cnt.data_ptr(),
                                        scale.data_ptr(), norm.data_ptr(), L.stream_ptr()), "td_grad_clip_scale")
-    assert abs(float(norm) - want_norm) / want_norm < 1e-6
-    assert rel(d * scale, mean[0].grad) < 1e-6
+    exact = float((flat_sum.double() / world).norm())              # torch's own fp32 norm of 11 M elements is ~1e-6 off
+    assert abs(float(norm) - exact) / exact < 1e-6
+    assert abs(float(norm) - want_norm) / want_norm < 1e-5
+    assert rel(d * scale, mean[0].grad) < 1e-5
     assert int(cnt) == 0
 
 

@@ -73,8 +73,8 @@ _SIGS = {
     "td_psample_step_cfg": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "td_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, _P]),
     "td_counter_add": (C.c_int, [_P, C.c_int32, _P]),
-    "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, _P, C.c_float,
-                                C.c_float, C.c_float, _P, _P, _P]),
+    "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, _P, C.c_double,
+                                C.c_double, C.c_float, _P, _P, _P]),
     "td_grad_clip_num_partials": (C.c_int64, [C.c_int64]),
     "td_grad_clip_scale": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, _P, _P, _P, _P, _P]),
     "td_randint": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, _P]),

@@ -303,7 +303,7 @@ adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__
                   float* const* __restrict__ v, const int64_t* __restrict__ numel,
                   const int32_t* __restrict__ chunk_tensor, const int64_t* __restrict__ chunk_offset,
                   int64_t chunk_elems, const int32_t* __restrict__ step_dev, float lr_host,
-                  const float* __restrict__ lr_dev, float beta1, float beta2,
+                  const float* __restrict__ lr_dev, double beta1_d, double beta2_d,
                   float eps, const float* __restrict__ grad_scale_dev, void* const* __restrict__ bf16_shadow) {
     td::pdl_sync();
     const int tid = chunk_tensor[blockIdx.x];
@@ -315,21 +315,25 @@ adam_multi_kernel(float* const* __restrict__ p, const float* const* __restrict__
     float* __restrict__ vp = v[tid] + off;
     __nv_bfloat16* sh = bf16_shadow ? reinterpret_cast<__nv_bfloat16*>(bf16_shadow[tid]) : nullptr;
     if (sh) sh += off;
-    const float step = (float)step_dev[0];
+    // Scalars as torch.optim.Adam forms them: bias corrections, step size and (1 - beta) in double from the double betas
+    // (Python floats there), rounded to fp32 once.  In fp32, 1 - 0.999f is off by 1.3e-5 relative, which goes straight into
+    // exp_avg_sq and the update.
+    const double step = (double)step_dev[0];
     const float lr = lr_dev ? lr_dev[0] : lr_host;      // device scalar: schedulers change it under a captured graph
-    const float bc1 = 1.0f - powf(beta1, step);
-    const float bc2 = 1.0f - powf(beta2, step);
-    const float step_size = lr / bc1;
-    const float inv_bc2_sqrt = 1.0f / sqrtf(bc2);
+    const double bc1 = 1.0 - pow(beta1_d, step);
+    const double bc2 = 1.0 - pow(beta2_d, step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
     const float gs = grad_scale_dev ? grad_scale_dev[0] : 1.0f;
-    const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
+    const float beta2 = (float)beta2_d;
+    const float omb1 = (float)(1.0 - beta1_d), omb2 = (float)(1.0 - beta2_d);
 
     auto upd = [&](float& pv, float gv, float& mv, float& vv) {
         gv *= gs;
         mv = mv + omb1 * (gv - mv);                  // exp_avg.lerp_(grad, 1-beta1)
         vv = vv * beta2 + omb2 * gv * gv;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2)
-        const float denom = sqrtf(vv) * inv_bc2_sqrt + eps;
-        pv = pv - step_size * (mv / denom);
+        const float denom = sqrtf(vv) / bc2_sqrt + eps;      // (exp_avg_sq.sqrt() / bias_correction2_sqrt).add_(eps)
+        pv = pv - step_size * (mv / denom);                  // param.addcdiv_(exp_avg, denom, value=-step_size)
     };
     // all four arrays share alignment only if the tensor base pointers are 16B aligned and
     // off % 4 == 0 (chunk_elems is a multiple of 4); torch allocations are 512B aligned.
@@ -484,7 +488,7 @@ extern "C" int td_counter_add(int32_t* t_dev, int32_t delta, void* stream) {
 extern "C" int td_adam_multi(float* const* p, const float* const* g, float* const* m, float* const* v,
                              const int64_t* numel, const int32_t* chunk_tensor, const int64_t* chunk_offset,
                              int64_t num_chunks, int64_t chunk_elems, const int32_t* step_dev, float lr,
-                             const float* lr_dev, float beta1, float beta2, float eps, const float* grad_scale_dev,
+                             const float* lr_dev, double beta1, double beta2, float eps, const float* grad_scale_dev,
                              void* const* bf16_shadow, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(p && g && m && v && numel && chunk_tensor && chunk_offset && step_dev, "td_adam_multi: null pointer");

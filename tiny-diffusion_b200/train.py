@@ -906,12 +906,14 @@ class TrainStep:
         if not self.use_graph:
             self.eng.refresh_weights()
             self._body()
+            self.optimizer.step()
             return self.loss
         g = self.graphs.get(self._device_rng)
         if g is None:
             g = self._capture()
             self.graphs[self._device_rng] = g
         g.replay()
+        self.optimizer.step()          # no-op: lets an attached lr_scheduler see "optimizer.step() before scheduler.step()"
         return self.loss
 
     def _capture(self) -> "torch.cuda.CUDAGraph":
