@@ -310,6 +310,28 @@ int td_bn_bwd_finalize(const float* partials, int nrows, int channels, int64_t c
 int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
                          const float* shift, const float* coef, void* dy, int64_t pixels, int channels, void* stream);
 
+/* Fused BatchNorm passes (train mode): the finalize runs in the prologue of the streaming kernel that consumes it, so a
+ * BatchNorm2d + ReLU is conv -> td_bn_apply_fused (forward) and td_bn_bwd_reduce -> td_bn_bwd_apply_fused (backward), with
+ * no finalize launch in between.  partials: [nrows][2][channels] + K[channels] as produced by a convolution's `stats`
+ * epilogue, td_bn_stats or td_bn_bwd_reduce.  channels % 32 == 0.
+ *   td_bn_apply_fused      = td_bn_finalize + td_bn_relu_apply   (also writes scale / shift / save_mean / save_invstd and
+ *                            updates the running statistics, diffusion.py:34-35)
+ *   td_bn_bwd_reduce       = td_bn_relu_bwd_reduce with one partial row per pixel chunk (td_bn_bwd_reduce_rows() <= 148)
+ *   td_bn_bwd_apply_fused  = td_bn_bwd_finalize + td_bn_relu_bwd_apply (writes dgamma / dbeta) */
+int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t count, const float* gamma,
+                      const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
+                      float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
+                      float* save_invstd, void* a, int dtype, int64_t lda, int a_coff, int64_t pixels, int channels,
+                      int relu, void* stream);
+int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels);
+int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
+                     const float* shift, const float* save_mean, int64_t pixels, int channels, float* partials,
+                     void* stream);
+int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* partials,
+                          int nrows, int64_t count, const float* scale, const float* shift, const float* save_mean,
+                          const float* save_invstd, float* dgamma, float* dbeta, void* dy, int64_t pixels, int channels,
+                          void* stream);
+
 /* backward of td_maxpool2_fwd (first maximum in scan order takes the gradient, like ATen) */
 int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int batch, int h, int w, int c, int ceil_mode,
                     int accumulate, void* stream);

@@ -39,11 +39,13 @@ def nchw(x):
 # ------------------------------------------------------------------------------------------
 # kernels
 # ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("offset", [0.3, 300.0])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
-@pytest.mark.parametrize("B,H,Cc", [(3, 7, 64), (2, 28, 128), (5, 4, 512), (2, 16, 32)])
-def test_bn_train_fwd_bwd(dev, dtype, tol, B, H, Cc, offset):
-    """offset = 300: per-channel mean >> std, the regime the raw-t time embedding creates."""
+@pytest.mark.parametrize("B,H,Cc", [(3, 7, 64), (2, 28, 128), (5, 4, 512), (2, 16, 32), (128, 28, 128), (128, 7, 512)])
+def test_bn_train_fwd_bwd(dev, dtype, tol, B, H, Cc, offset, fused):
+    """offset = 300: per-channel mean >> std, the regime the raw-t time embedding creates.  ``fused``: the finalize runs in
+    the prologue of the apply kernels (the train engine's path); the last two shapes are the benchmark batch."""
     from tinydiff import ops
     if dtype == torch.bfloat16 and Cc % 64:
         pytest.skip("bf16 path is used with multiples of 64 channels")
@@ -63,11 +65,11 @@ def test_bn_train_fwd_bwd(dev, dtype, tol, B, H, Cc, offset):
     nbt = torch.zeros(1, dtype=torch.int64, device=dev)
     yd = nhwc(y).to(dev)
     a, scale, shift, mean, invstd = ops.bn_train_fwd(yd, gamma.to(dev), beta.to(dev), bias.to(dev), rm_d, rv_d, nbt,
-                                                     out_dtype=dtype)
+                                                     out_dtype=dtype, fused=fused)
     big = offset > 1
     assert rel(nchw(a.float()), a_ref.detach()) < tol * (20 if big and dtype == torch.float32 else 1)
     assert rel(rm_d, rm_ref) < 1e-5 and rel(rv_d, rv_ref) < 1e-4 and int(nbt) == 1
-    dy, dgamma, dbeta = ops.bn_train_bwd(nhwc(da).to(dev).to(dtype), yd, scale, shift, mean, invstd)
+    dy, dgamma, dbeta = ops.bn_train_bwd(nhwc(da).to(dev).to(dtype), yd, scale, shift, mean, invstd, fused=fused)
     k = 20 if big else 3
     assert rel(nchw(dy.float()), yr.grad) < tol * k
     assert rel(dgamma, gr.grad) < tol * k and rel(dbeta, br.grad) < tol * 2

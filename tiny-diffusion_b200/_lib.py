@@ -112,6 +112,12 @@ _SIGS = {
     "td_bn_relu_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "td_bn_bwd_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "td_bn_relu_bwd_apply": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "td_bn_apply_fused": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P,
+                                    _P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
+    "td_bn_bwd_reduce_rows": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
+    "td_bn_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_bwd_apply_fused": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P,
+                                        _P, C.c_int64, C.c_int, _P]),
     "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_resize_bilinear_bwd": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, _P]),

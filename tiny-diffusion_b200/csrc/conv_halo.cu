@@ -102,6 +102,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     float* s_affine = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~(uintptr_t)15);  // [2 groups][2][2][N_TILE]
     float* s_stats = s_affine + 8 * N_TILE;                // [2 groups][4 warps][2][N_TILE]
     float* s_tile = s_stats + 16 * N_TILE;                 // [8 epilogue warps][32 rows][36]: output staging (see the epilogue)
+    double* s_acc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_tile + 8 * 32 * 36) + 7) & ~(uintptr_t)7);   // [2 groups][2][N_TILE]: per-CTA statistics
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int u_lo = (int)((int64_t)blockIdx.x * p.units / gridDim.x);
@@ -261,7 +262,36 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         uint32_t gi = 0;
         long long w0 = 0;
         const long long t_start = clock64();
+        // Train-mode statistics: ONE partial row per CTA (row = blockIdx.x), so the consumer's finalize prologue sums <= 148
+        // rows.  Both epilogue groups add their subtiles' column sums into per-group double accumulators (a (which, channel)
+        // entry is owned by one thread of the group); when the walk moves to the next n-tile, and at its end, the 256
+        // epilogue threads merge the two groups and write the row's slice of that n-tile.  N-tiles the CTA never visits are
+        // written as zeros at the end, so every row is fully defined.
+        int cur_nt = -1;
+        uint32_t visited = 0;
+        const int etid = threadIdx.x - 96;                     // 0..255 over both epilogue groups
+        double* const acc_g = s_acc + grp * 2 * N_TILE;
+        if (p.stats) {
+            for (int c = tid; c < 2 * N_TILE; c += 128) acc_g[c] = 0.0;
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+        }
+        auto flush_stats = [&](int nt_f) {
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            float* row = p.stats + (int64_t)blockIdx.x * 2 * p.cout + nt_f * N_TILE;
+            for (int c = etid; c < 2 * N_TILE; c += 256) {
+                const int which = c / N_TILE, cc = c - which * N_TILE;
+                row[which * p.cout + cc] = (float)(s_acc[c] + s_acc[2 * N_TILE + c]);
+                s_acc[c] = 0.0;
+                s_acc[2 * N_TILE + c] = 0.0;
+            }
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+        };
         while (wk.next(nt, s0, cnt)) {
+            if (p.stats && nt != cur_nt) {
+                if (cur_nt >= 0) flush_stats(cur_nt);
+                cur_nt = nt;
+                visited |= 1u << nt;
+            }
             const uint32_t ab = gi & 1u;
             float* sc_s = aff_g + ab * 2 * N_TILE;
             float* sh_s = sc_s + N_TILE;
@@ -377,15 +407,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 }
                 if (p.stats) {
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-                    float* row = p.stats + (int64_t)sub * 2 * p.cout + nt * N_TILE;
                     for (int c = tid; c < 2 * N_TILE; c += 128) {
                         const int which = c / N_TILE, cc = c - which * N_TILE;
                         const float t = (stats_g[(0 * 2 + which) * N_TILE + cc] + stats_g[(1 * 2 + which) * N_TILE + cc]) +
                                         (stats_g[(2 * 2 + which) * N_TILE + cc] + stats_g[(3 * 2 + which) * N_TILE + cc]);
-                        row[which * p.cout + cc] = t;
+                        acc_g[c] += (double)t;
                     }
-                    if (sub == 0)       // td_bn_finalize reads a zero "shift" row after the partial rows
-                        for (int c = tid; c < N_TILE; c += 128) p.stats[(int64_t)p.n_sub * 2 * p.cout + nt * N_TILE + c] = 0.f;
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 }
                 }
@@ -394,6 +421,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[ab]);
             ++gi;
+        }
+        if (p.stats) {
+            if (cur_nt >= 0) flush_stats(cur_nt);
+            const int n_tiles = p.cout / N_TILE;
+            for (int t2 = 0; t2 < n_tiles; ++t2) {
+                if (visited & (1u << t2)) continue;
+                float* row = p.stats + (int64_t)blockIdx.x * 2 * p.cout + t2 * N_TILE;
+                for (int c = etid; c < 2 * N_TILE; c += 256) {
+                    const int which = c / N_TILE, cc = c - which * N_TILE;
+                    row[which * p.cout + cc] = 0.f;
+                }
+            }
+            if (blockIdx.x == 0)        // the finalize reads a "shift" row K after the partial rows: zero for the conv epilogue
+                for (int c = etid; c < p.cout; c += 256) p.stats[(int64_t)gridDim.x * 2 * p.cout + c] = 0.f;
         }
         if ((p.dbg & 1) && tid == 0 && grp == 0) {
             g_halo_dbg[blockIdx.x * 8 + 6] = w0;
@@ -498,7 +539,8 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->h_na = g.G == 3 ? 6 : 4;        // dx layout: a box group lasts only three taps, keep three groups in flight
     if (const char* e = getenv("TD_TC_HALO_NA")) { int v = atoi(e); if (v >= 2 && v <= 8) p->h_na = v; }
     const int b_stage = n_tile * 128;
-    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (8 + 16) * n_tile * 4 + 8 * 32 * 36 * 4 + 1024;
+    const int fixed = p->h_na * p->h_slot_bytes + (2 * p->h_na + 6) * 8 + 64 + (8 + 16) * n_tile * 4 + 8 * 32 * 36 * 4 + 1024 +
+                      4 * n_tile * 8 + 16;
     int nb = (226 * 1024 - fixed) / (b_stage + 16);
     if (nb > 8) nb = 8;
     if (const char* e = getenv("TD_TC_HALO_NB")) { int v = atoi(e); if (v >= 2 && v <= nb) nb = v; }

@@ -175,12 +175,52 @@ static bool narrow_ok(const td_wgrad_desc& d, int* grid_x) {
 }
 
 // dw[o][c][tap] = sum_s ws[s][o][tap*cin + c]     (OHWI partials -> OIHW gradient)
-// grid (cin chunks of 32, cout), 288 threads = 9 taps x 32 channels: coalesced reads of the tap rows,
-// fixed-order sum over the splits, transposed through shared memory so that the [c][tap] run is
-// written contiguously.
+// grid (cin chunks of 32, cout), 288 threads = 4 split groups x 9 taps x 8 channel quads: every thread sums one float4
+// (4 input channels of one tap) over a contiguous quarter of the splits with all of its loads in flight at once (the
+// partials were just written and sit in the L2: the pass is a latency chain, not bandwidth), the four groups are combined in
+// fixed order through shared memory -- deterministic -- and the [c][tap] run is written contiguously (OHWI -> OIHW transpose).
 constexpr int WR_C = 32;
+constexpr int WR_G = 4;
 __global__ void __launch_bounds__(9 * WR_C)
 wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
+    td::pdl_sync();
+    __shared__ float4 part[WR_G][9][WR_C / 4];
+    __shared__ float tile[9][WR_C + 1];
+    const int o = blockIdx.y;
+    const int c0 = blockIdx.x * WR_C;
+    const int nc = min(WR_C, cin - c0);
+    const int64_t per = (int64_t)cout * 9 * cin;
+    const int q = threadIdx.x % (WR_C / 4), t = (threadIdx.x / (WR_C / 4)) % 9, g = threadIdx.x / (9 * WR_C / 4);
+    const int per_g = (splits + WR_G - 1) / WR_G;
+    const int z0 = g * per_g, z1 = min(splits, z0 + per_g);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q * 4 < nc) {
+        const float* src = ws + ((int64_t)o * 9 + t) * cin + c0 + q * 4;
+        for (int z = z0; z < z1; z += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = (z + k < z1) ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(z + k) * per)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }
+        }
+    }
+    part[g][t][q] = acc;
+    __syncthreads();
+    if (g == 0 && q * 4 < nc) {
+        float4 s4 = part[0][t][q];
+#pragma unroll
+        for (int k = 1; k < WR_G; ++k) { const float4 v = part[k][t][q]; s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w; }
+        tile[t][q * 4] = s4.x; tile[t][q * 4 + 1] = s4.y; tile[t][q * 4 + 2] = s4.z; tile[t][q * 4 + 3] = s4.w;
+    }
+    __syncthreads();
+    float* dst = dw + ((int64_t)o * cin + c0) * 9;
+    for (int e = threadIdx.x; e < nc * 9; e += 9 * WR_C) dst[e] = tile[e % 9][e / 9];
+}
+
+// scalar variant for channel counts that are not multiples of 4 (the 1- and 4-channel boundary convolutions)
+__global__ void __launch_bounds__(9 * WR_C)
+wgrad_reduce_scalar_kernel(const float* __restrict__ ws, int splits, int cout, int cin, float* __restrict__ dw) {
     td::pdl_sync();
     __shared__ float tile[9][WR_C + 1];
     const int o = blockIdx.y;
@@ -190,25 +230,15 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int cout, int cin,
     const int t = threadIdx.x / WR_C, c = threadIdx.x % WR_C;
     if (c < nc) {
         const float* src = ws + ((int64_t)o * 9 + t) * cin + c0 + c;
-        // eight independent partial sums: eight loads in flight per thread (the kernel is latency-bound otherwise);
-        // the summation order is fixed by the split index, so the result is deterministic
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int z = 0;
-        for (; z + 8 <= splits; z += 8) {
+        for (; z + 4 <= splits; z += 4) {
             const float v0 = __ldg(src + (int64_t)z * per), v1 = __ldg(src + (int64_t)(z + 1) * per);
             const float v2 = __ldg(src + (int64_t)(z + 2) * per), v3 = __ldg(src + (int64_t)(z + 3) * per);
-            const float v4 = __ldg(src + (int64_t)(z + 4) * per), v5 = __ldg(src + (int64_t)(z + 5) * per);
-            const float v6 = __ldg(src + (int64_t)(z + 6) * per), v7 = __ldg(src + (int64_t)(z + 7) * per);
-            a0 += v0; a1 += v1; a2 += v2; a3 += v3; a4 += v4; a5 += v5; a6 += v6; a7 += v7;
-        }
-        for (; z + 4 <= splits; z += 4) {
-            a0 += src[(int64_t)z * per];
-            a1 += src[(int64_t)(z + 1) * per];
-            a2 += src[(int64_t)(z + 2) * per];
-            a3 += src[(int64_t)(z + 3) * per];
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
         }
         for (; z < splits; ++z) a0 += src[(int64_t)z * per];
-        tile[t][c] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+        tile[t][c] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     float* dst = dw + ((int64_t)o * cin + c0) * 9;
@@ -314,7 +344,10 @@ extern "C" int td_conv3x3_wgrad_run(const td_wgrad_plan* p, void* stream) {
         if (st != TD_OK) return st;
     }
     dim3 rgrid((unsigned)ceil_div(d.cin, WR_C), (unsigned)d.cout);
-    td::launch(wgrad_reduce_kernel, td::LaunchCfg(rgrid, 9 * WR_C, 0, s), d.workspace, p->splits, d.cout, d.cin, d.dw);
+    if (d.cin % 4 == 0 && (((uintptr_t)d.workspace) & 15) == 0)
+        td::launch(wgrad_reduce_kernel, td::LaunchCfg(rgrid, 9 * WR_C, 0, s), d.workspace, p->splits, d.cout, d.cin, d.dw);
+    else
+        td::launch(wgrad_reduce_scalar_kernel, td::LaunchCfg(rgrid, 9 * WR_C, 0, s), d.workspace, p->splits, d.cout, d.cin, d.dw);
     return launch_status("wgrad_reduce");
 }
 

@@ -271,6 +271,235 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused BatchNorm passes: the finalize (sum of the partial rows -> per-channel coefficients) runs in the PROLOGUE of the
+// streaming kernel that consumes it, so a BatchNorm is conv -> apply (forward) and reduce -> apply (backward) with no
+// finalize launch in between (the finalize kernels were 4..16-CTA latency chains of ~8 us each, 26 per train step).
+// A CTA owns a slice of 32 channels and a contiguous pixel range: its prologue sums nrows x 2 x 32 partials (<= 148 rows:
+// the producers write one row per CTA) in fixed order, in double -- every CTA of a slice derives bit-identical coefficients --
+// and the CTAs of pixel chunk 0 publish the per-channel results (running statistics, saved mean / invstd, dgamma / dbeta).
+// Body: 32 / V threads per pixel (V = 8 bf16 / 4 fp32 channels per 16-byte vector), 128-byte fp32 and 64-byte bf16 segments.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSlice = 32;
+
+// sum of partials[r][which][c_base + ch] over r in fixed order; valid on threads 0..31 (ch = threadIdx.x) after the call
+__device__ inline void slice_sum_partials(const float* __restrict__ partials, int nrows, int C, int c_base, double& s1, double& s2) {
+    __shared__ double red[8][2][kSlice];
+    const int ch = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const float* p = partials + c_base + ch;
+    double a = 0.0, b = 0.0;
+    for (int r0 = rg; r0 < nrows; r0 += 8 * 8) {
+        float va[8], vb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = r0 + 8 * k;
+            const bool ok = r < nrows;
+            va[k] = ok ? __ldg(p + (size_t)r * 2 * C) : 0.f;
+            vb[k] = ok ? __ldg(p + (size_t)r * 2 * C + C) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += (double)va[k]; b += (double)vb[k]; }
+    }
+    red[rg][0][ch] = a;
+    red[rg][1][ch] = b;
+    __syncthreads();
+    s1 = 0.0; s2 = 0.0;
+    if (rg == 0) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { s1 += red[g][0][ch]; s2 += red[g][1][ch]; }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT)
+bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ partials, int nrows, double count,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                      float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                      int64_t* __restrict__ nbt, float* __restrict__ scale_out, float* __restrict__ shift_out,
+                      float* __restrict__ save_mean, float* __restrict__ save_invstd, T* __restrict__ a, int64_t lda,
+                      int a_coff, int64_t P, int C, int relu) {
+    td::pdl_sync();
+    constexpr int V = Vec<T>::N;
+    constexpr int TPP = kSlice / V;                 // threads per pixel
+    constexpr int PPP = kT / TPP;                   // pixels per pass
+    __shared__ float s_sc[kSlice], s_sh[kSlice];
+    const int c_base = blockIdx.y * kSlice;
+    {
+        const int c = c_base + (threadIdx.x & 31);
+        const bool tail = threadIdx.x < 32;
+        float k_c = 0.f, g_c = 0.f, b_c = 0.f, cb_c = 0.f, rm_c = 0.f, rv_c = 0.f;
+        if (tail) {                                 // per-channel inputs fetched before the reduction (off the latency chain)
+            k_c = partials[(size_t)nrows * 2 * C + c];
+            g_c = gamma[c];
+            b_c = beta[c];
+            if (blockIdx.x == 0) {
+                if (conv_bias) cb_c = conv_bias[c];
+                if (running_mean) rm_c = running_mean[c];
+                if (running_var) rv_c = running_var[c];
+            }
+        }
+        double s1, s2;
+        slice_sum_partials(partials, nrows, C, c_base, s1, s2);
+        if (tail) {
+            const double dm = s1 / count;                         // mean of (x - K)
+            const double mean = (double)k_c + dm;
+            double var = s2 / count - dm * dm;
+            if (var < 0.0) var = 0.0;
+            const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+            const float sc = g_c * invstd;
+            const float sh = b_c - (float)mean * sc;
+            s_sc[threadIdx.x] = sc;
+            s_sh[threadIdx.x] = sh;
+            if (blockIdx.x == 0) {
+                scale_out[c] = sc;
+                shift_out[c] = sh;
+                save_mean[c] = (float)mean;
+                save_invstd[c] = invstd;
+                if (running_mean) running_mean[c] = (1.f - momentum) * rm_c + momentum * ((float)mean + cb_c);
+                if (running_var) {
+                    const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+                    running_var[c] = (1.f - momentum) * rv_c + momentum * (float)unb;
+                }
+                if (blockIdx.y == 0 && threadIdx.x == 0 && nbt) nbt[0] += 1;
+            }
+        }
+        __syncthreads();
+    }
+    const int lane_c = (threadIdx.x % TPP) * V;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = s_sc[lane_c + k]; sh[k] = s_sh[lane_c + k]; }
+    const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
+    const int c0 = c_base + lane_c;
+#pragma unroll 4
+    for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
+        float f[V];
+        load_f32<V>(y + p * C + c0, f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            f[k] = fmaf(f[k], sc[k], sh[k]);
+            if (relu) f[k] = fmaxf(f[k], 0.f);
+        }
+        Vec<T>::pack(f).store(a + p * lda + a_coff + c0);
+    }
+}
+
+// BatchNorm backward partial sums, channel-sliced: s1 = sum g, s2 = sum g*(y-mean), g = da * [y*scale+shift > 0].
+// grid (chunks, C / 32); partials [chunks][2][C] (one row per pixel chunk).
+template <typename T>
+__global__ void __launch_bounds__(kT)
+bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y, int64_t P, int C,
+                            const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                            float* __restrict__ partials) {
+    td::pdl_sync();
+    constexpr int V = Vec<T>::N;
+    constexpr int TPP = kSlice / V;
+    constexpr int PPP = kT / TPP;
+    __shared__ float red[PPP][2 * kSlice + 1];
+    const int c_base = blockIdx.y * kSlice;
+    const int lane_c = (threadIdx.x % TPP) * V;
+    const int c0 = c_base + lane_c;
+    float s1[V], s2[V], sc[V], sh[V], mu[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k]; }
+    const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
+#pragma unroll 4
+    for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
+        float f[V], yy[V];
+        Vec<T>::load(da + p * ldda + da_coff + c0).unpack(f);
+        load_f32<V>(y + p * C + c0, yy);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float g = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? f[k] : 0.f;
+            s1[k] += g;
+            s2[k] = fmaf(g, yy[k] - mu[k], s2[k]);
+        }
+    }
+    const int prow = threadIdx.x / TPP;
+#pragma unroll
+    for (int k = 0; k < V; ++k) { red[prow][lane_c + k] = s1[k]; red[prow][kSlice + lane_c + k] = s2[k]; }
+    __syncthreads();
+    if (threadIdx.x < 2 * kSlice) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;                 // fixed order: four interleaved chains, then a tree
+#pragma unroll 4
+        for (int r = 0; r < PPP; r += 4) {
+            t0 += red[r][threadIdx.x]; t1 += red[r + 1][threadIdx.x]; t2 += red[r + 2][threadIdx.x]; t3 += red[r + 3][threadIdx.x];
+        }
+        const int which = threadIdx.x / kSlice, cc = threadIdx.x % kSlice;
+        partials[(size_t)blockIdx.x * 2 * C + (size_t)which * C + c_base + cc] = (t0 + t1) + (t2 + t3);
+    }
+}
+
+// dy = scale*(g - mean(g) - xhat*mean(g*xhat)) = cA*g + cB*y + cC with the coefficients derived in the prologue from the
+// partial rows of bn_bwd_reduce_sliced_kernel (or of a data-gradient convolution's epilogue); chunk 0 writes dgamma / dbeta.
+template <typename T>
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y,
+                          const float* __restrict__ partials, int nrows, double count, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ save_mean,
+                          const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                          T* __restrict__ dy, int64_t P, int C) {
+    td::pdl_sync();
+    constexpr int V = Vec<T>::N;
+    constexpr int TPP = kSlice / V;
+    constexpr int PPP = kT / TPP;
+    __shared__ float s_co[5][kSlice];               // scale, shift, cA, cB, cC
+    const int c_base = blockIdx.y * kSlice;
+    {
+        const int c = c_base + (threadIdx.x & 31);
+        const bool tail = threadIdx.x < 32;
+        float mean_c = 0.f, invstd_c = 0.f, sc_c = 0.f, sh_c = 0.f;
+        if (tail) { mean_c = save_mean[c]; invstd_c = save_invstd[c]; sc_c = scale[c]; sh_c = shift[c]; }
+        double s1, s2;
+        slice_sum_partials(partials, nrows, C, c_base, s1, s2);
+        if (tail) {
+            const double mean = mean_c, invstd = invstd_c, sc = sc_c;
+            const double dg = s2 * invstd;                     // sum g * xhat   (s2 = sum g * (y - mean))
+            const double cB = -sc * invstd * dg / count;
+            s_co[0][threadIdx.x] = sc_c;
+            s_co[1][threadIdx.x] = sh_c;
+            s_co[2][threadIdx.x] = (float)sc;
+            s_co[3][threadIdx.x] = (float)cB;
+            s_co[4][threadIdx.x] = (float)(-sc * s1 / count - cB * mean);
+            if (blockIdx.x == 0) {
+                dgamma[c] = (float)dg;
+                dbeta[c] = (float)s1;
+            }
+        }
+        __syncthreads();
+    }
+    const int lane_c = (threadIdx.x % TPP) * V;
+    float sc[V], sh[V], cA[V], cB[V], cC[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        sc[k] = s_co[0][lane_c + k]; sh[k] = s_co[1][lane_c + k];
+        cA[k] = s_co[2][lane_c + k]; cB[k] = s_co[3][lane_c + k]; cC[k] = s_co[4][lane_c + k];
+    }
+    const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
+    const int c0 = c_base + lane_c;
+#pragma unroll 4
+    for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
+        float g[V], yy[V];
+        Vec<T>::load(da + p * ldda + da_coff + c0).unpack(g);
+        load_f32<V>(y + p * C + c0, yy);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float gm = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            g[k] = fmaf(cA[k], gm, fmaf(cB[k], yy[k], cC[k]));
+        }
+        Vec<T>::pack(g).store(dy + p * C + c0);
+    }
+}
+
+// pixel chunks of the channel-sliced kernels: ~4 CTAs per SM in total, never more rows than SMs, >= 2 passes per CTA
+static inline int sliced_chunks(int64_t P, int C, int ppp) {
+    const int slices = C / kSlice;
+    int64_t n = std::max<int64_t>(1, (int64_t)kNumSMs * 4 / slices);
+    n = std::min<int64_t>(n, kNumSMs);
+    n = std::min<int64_t>(n, std::max<int64_t>(1, P / (2 * ppp)));
+    return (int)n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // MaxPool2d(2, ceil_mode) backward, gather form: an input pixel receives the window's gradient
 // iff it is the first maximum in (h, w) scan order (ATen's tie rule).
 // ---------------------------------------------------------------------------------------------
@@ -663,6 +892,56 @@ extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, c
     TD_DISPATCH_T(dtype, (td::launch(bn_relu_bwd_apply_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), 
                              (const T*)da, ldda, da_coff, y, scale, shift, coef, (T*)dy, pixels, channels)));
     return launch_status("bn_relu_bwd_apply");
+}
+
+extern "C" int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t count, const float* gamma,
+                                 const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
+                                 float* running_var, int64_t* num_batches_tracked, float* scale, float* shift,
+                                 float* save_mean, float* save_invstd, void* a, int dtype, int64_t lda, int a_coff,
+                                 int64_t pixels, int channels, int relu, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(y && partials && nrows > 0 && count > 0 && gamma && beta && scale && shift && save_mean && save_invstd && a &&
+                     pixels > 0, "td_bn_apply_fused: bad args");
+    TD_CHECK_ARG(channels % kSlice == 0 && lda % 8 == 0 && a_coff % 8 == 0, "td_bn_apply_fused: channels must be a multiple of 32");
+    const int ppp = dtype == TD_BF16 ? kT / 4 : kT / 8;
+    const dim3 grid((unsigned)sliced_chunks(pixels, channels, ppp), (unsigned)(channels / kSlice));
+    TD_DISPATCH_T(dtype, (td::launch(bn_apply_fused_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), y, partials, nrows,
+                             (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
+                             num_batches_tracked, scale, shift, save_mean, save_invstd, (T*)a, lda, a_coff, pixels, channels, relu)));
+    return launch_status("bn_apply_fused");
+}
+
+extern "C" int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels) {
+    if (channels % kSlice != 0) return 0;
+    return sliced_chunks(pixels, channels, dtype == TD_BF16 ? kT / 4 : kT / 8);
+}
+
+extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
+                                const float* shift, const float* save_mean, int64_t pixels, int channels, float* partials,
+                                void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(da && y && scale && shift && save_mean && partials && pixels > 0, "td_bn_bwd_reduce: bad args");
+    TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_reduce: channels must be a multiple of 32");
+    const dim3 grid((unsigned)td_bn_bwd_reduce_rows(dtype, pixels, channels), (unsigned)(channels / kSlice));
+    TD_DISPATCH_T(dtype, (td::launch(bn_bwd_reduce_sliced_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
+                             ldda, da_coff, y, pixels, channels, scale, shift, save_mean, partials)));
+    return launch_status("bn_bwd_reduce");
+}
+
+extern "C" int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype,
+                                     const float* partials, int nrows, int64_t count, const float* scale, const float* shift,
+                                     const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, void* dy,
+                                     int64_t pixels, int channels, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(da && y && partials && nrows > 0 && count > 0 && scale && shift && save_mean && save_invstd && dgamma && dbeta &&
+                     dy && pixels > 0, "td_bn_bwd_apply_fused: bad args");
+    TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_apply_fused: channels must be a multiple of 32");
+    const int ppp = dtype == TD_BF16 ? kT / 4 : kT / 8;
+    const dim3 grid((unsigned)sliced_chunks(pixels, channels, ppp), (unsigned)(channels / kSlice));
+    TD_DISPATCH_T(dtype, (td::launch(bn_bwd_apply_fused_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
+                             ldda, da_coff, y, partials, nrows, (double)count, scale, shift, save_mean, save_invstd, dgamma,
+                             dbeta, (T*)dy, pixels, channels)));
+    return launch_status("bn_bwd_apply_fused");
 }
 
 extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtype, int batch, int h, int w, int c,

@@ -235,8 +235,9 @@ def conv3x3_wgrad(x, dy, engine=L.CONV_SIMT, x_nchw=False, dy_nchw=False, x_coff
 
 
 def bn_train_fwd(y, gamma, beta, conv_bias, running_mean, running_var, nbt, eps=1e-5, momentum=0.1, relu=True,
-                 out_dtype=torch.float32):
-    """y: raw fp32 conv output NHWC (bias excluded).  Returns (a, scale, shift, save_mean, save_invstd)."""
+                 out_dtype=torch.float32, fused=False):
+    """y: raw fp32 conv output NHWC (bias excluded).  Returns (a, scale, shift, save_mean, save_invstd).
+    ``fused``: td_bn_apply_fused (finalize in the prologue of the apply pass) instead of finalize + apply."""
     _dev(y)
     assert y.dtype == torch.float32
     lib = L.load()
@@ -247,6 +248,13 @@ def bn_train_fwd(y, gamma, beta, conv_bias, running_mean, running_var, nbt, eps=
     st = L.stream_ptr()
     L.check(lib.td_bn_stats(y.data_ptr(), L.TD_F32, Cc, 0, P, Cc, part.data_ptr(), 1, st), "td_bn_stats")
     scale, shift, mean, invstd = (torch.empty(Cc, device=y.device) for _ in range(4))
+    if fused:
+        a = torch.empty(y.shape, device=y.device, dtype=out_dtype)
+        L.check(lib.td_bn_apply_fused(y.data_ptr(), part.data_ptr(), rows, P, gamma.data_ptr(), beta.data_ptr(),
+                                      L.ptr(conv_bias), eps, momentum, L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt),
+                                      scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), a.data_ptr(),
+                                      L.dtype_code(out_dtype), Cc, 0, P, Cc, int(relu), st), "td_bn_apply_fused")
+        return a, scale, shift, mean, invstd
     L.check(lib.td_bn_finalize(part.data_ptr(), rows, Cc, P, gamma.data_ptr(), beta.data_ptr(), L.ptr(conv_bias), eps,
                                momentum, L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt), scale.data_ptr(),
                                shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st), "td_bn_finalize")
@@ -256,13 +264,26 @@ def bn_train_fwd(y, gamma, beta, conv_bias, running_mean, running_var, nbt, eps=
     return a, scale, shift, mean, invstd
 
 
-def bn_train_bwd(da, y, scale, shift, mean, invstd):
-    """da: grad of the block output (fp32 / bf16), y: raw fp32 conv output.  Returns (dy, dgamma, dbeta)."""
+def bn_train_bwd(da, y, scale, shift, mean, invstd, fused=False):
+    """da: grad of the block output (fp32 / bf16), y: raw fp32 conv output.  Returns (dy, dgamma, dbeta).
+    ``fused``: td_bn_bwd_reduce + td_bn_bwd_apply_fused instead of reduce + finalize + apply."""
     _dev(y)
     lib = L.load()
     Cc = y.shape[-1]
     P = y.numel() // Cc
     dt = L.dtype_code(da.dtype)
+    if fused:
+        rows = int(lib.td_bn_bwd_reduce_rows(dt, P, Cc))
+        part = torch.empty(rows * 2 * Cc + Cc, device=y.device)
+        st = L.stream_ptr()
+        L.check(lib.td_bn_bwd_reduce(da.data_ptr(), Cc, 0, y.data_ptr(), dt, scale.data_ptr(), shift.data_ptr(),
+                                     mean.data_ptr(), P, Cc, part.data_ptr(), st), "td_bn_bwd_reduce")
+        dgamma, dbeta = torch.empty(Cc, device=y.device), torch.empty(Cc, device=y.device)
+        dy = torch.empty_like(da)
+        L.check(lib.td_bn_bwd_apply_fused(da.data_ptr(), Cc, 0, y.data_ptr(), dt, part.data_ptr(), rows, P, scale.data_ptr(),
+                                          shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
+                                          dbeta.data_ptr(), dy.data_ptr(), P, Cc, st), "td_bn_bwd_apply_fused")
+        return dy, dgamma, dbeta
     rows = int(lib.td_chan_reduce_rows(dt, P, Cc))
     part = torch.empty(rows * 2 * Cc + Cc, device=y.device)
     st = L.stream_ptr()

@@ -120,7 +120,7 @@ class UNetTrainEngine:
         max_part = 1
         for name, _, _, size, _, cout in self.layers:
             rows = int(self.lib.td_chan_reduce_rows(L.TD_F32, B * size * size, cout))
-            rows_b = int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout))
+            rows_b = int(self.lib.td_bn_bwd_reduce_rows(self.adt, B * size * size, cout))
             rows_fused = B * size * size // 32 + 2          # upper bound on the conv epilogue's partial rows (tiles)
             max_part = max(max_part, (max(rows, rows_b, rows_fused) * 2 + 1) * cout)
             self.bn[name] = {k: torch.zeros(cout, device=dev) for k in ("scale", "shift", "mean", "invstd")}
@@ -309,9 +309,9 @@ class UNetTrainEngine:
                 if fused_rows == 0:
                     nrows = rows
                     L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
-                L.check(lib.td_bn_finalize(part, nrows, cout, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, st),
-                        "td_bn_finalize")
-                L.check(lib.td_bn_relu_apply(yp, sc, sh, ap, adt, cout, 0, P, cout, 1, st), "td_bn_relu_apply")
+                # finalize (partial rows -> scale / shift, running statistics) in the prologue of the apply + ReLU pass
+                L.check(lib.td_bn_apply_fused(yp, part, nrows, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, ap, adt,
+                                              cout, 0, P, cout, 1, st), "td_bn_apply_fused")
             fwd.append((f"bn:{name}", bn_fwd))
 
         def add_pool(src, dst, h, c):
@@ -393,11 +393,10 @@ class UNetTrainEngine:
             db = self.pgrad[f"{blk}.{int(idx) + 1}.bias"].data_ptr()
 
             def bn_bwd(st):
-                L.check(lib.td_bn_relu_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, mu, P, cout, part, st),
-                        "td_bn_relu_bwd_reduce")
-                L.check(lib.td_bn_bwd_finalize(part, rows, cout, P, sc, mu, iv, dg, db, coef, st), "td_bn_bwd_finalize")
-                L.check(lib.td_bn_relu_bwd_apply(dap, cout, 0, yp, adt, sc, sh, coef, dyp, P, cout, st),
-                        "td_bn_relu_bwd_apply")
+                L.check(lib.td_bn_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, mu, P, cout, part, st), "td_bn_bwd_reduce")
+                # finalize (sum g, sum g*xhat -> dgamma / dbeta and the dy coefficients) in the prologue of the apply pass
+                L.check(lib.td_bn_bwd_apply_fused(dap, cout, 0, yp, adt, part, rows, P, sc, sh, mu, iv, dg, db, dyp, P, cout, st),
+                        "td_bn_bwd_apply_fused")
             bwd.append((f"bn:{name}:bwd", bn_bwd))
             eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
             self._wgrad(name, bf[xin], cin, dyv, cout, size, eng)
