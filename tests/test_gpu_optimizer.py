@@ -95,10 +95,13 @@ def test_grad_clip_scale_vs_torch(dev, n, max_norm, world):
     for _ in range(2):                                               # the counter resets itself: a second launch works
         L.check(lib.td_grad_clip_scale(d.data_ptr(), n, 1.0 / world, max_norm, part.data_ptr(), cnt.data_ptr(),
                                        scale.data_ptr(), norm.data_ptr(), L.stream_ptr()), "td_grad_clip_scale")
-    exact = float((flat_sum.double() / world).norm())              # torch's own fp32 norm of 11 M elements is ~1e-6 off
+    # against the norm in double: torch's own fp32 norm of 11 M elements is 4e-4 off (33.4256 vs 33.4391 measured), so
+    # clip_grad_norm_'s result is only a loose cross-check at that size
+    exact = float((flat_sum.double() / world).norm())
     assert abs(float(norm) - exact) / exact < 1e-6
-    assert abs(float(norm) - want_norm) / want_norm < 1e-5
-    assert rel(d * scale, mean[0].grad) < 1e-5
+    assert abs(float(norm) - want_norm) / want_norm < (1e-5 if n < 100000 else 1e-3)
+    clip = min(1.0, max_norm / (exact + 1e-6)) if max_norm > 0 else 1.0
+    assert rel(d * scale, flat_sum / world * clip) < 1e-6
     assert int(cnt) == 0
 
 

@@ -673,6 +673,122 @@ resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict_
     }
 }
 
+// Gather form of the transposed resize (default; TD_GLUE_WALK=1 selects the walker above): one CTA per INPUT row, one thread
+// per (input pixel, 16-byte channel vector), channel vectors on consecutive lanes.  The weights with which an input row /
+// column enters the output rows / columns (bil_transpose) are tabulated in shared memory once per CTA; a thread then sums
+//   dx[hi, wi] = sum_a wh[a] * ( sum_k ww[k] * dy[oh + a, ow + k] )
+// with all of its loads independent (<= 4 x 4 taps for a 2x up-sampling, ~3 x 3 for 28 <- 32), in a fixed order.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+resize_bwd_gather_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
+                         int Wo, int C) {
+    td::pdl_sync();
+    constexpr int V = Vec<T>::N;
+    __shared__ BilT colT[kMaxRowW];
+    __shared__ BilT rowT;
+    const int b = blockIdx.x / Hi, hi = blockIdx.x - b * Hi;
+    const int cvt = C / V;
+    T* xrow = dx + (int64_t)blockIdx.x * Wi * C;
+    if (Hi == Ho && Wi == Wo) {
+        const T* g = dy + (int64_t)blockIdx.x * Wo * ld + coff;
+        for (int idx = threadIdx.x; idx < Wi * cvt; idx += blockDim.x) {
+            const int w = idx / cvt, cv = idx - w * cvt;
+            Vec<T>::load(g + (int64_t)w * ld + cv * V).store(xrow + (int64_t)w * C + cv * V);
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i <= Wi; i += blockDim.x) {
+        if (i < Wi) colT[i] = bil_transpose(i, Wi, Wo);
+        else rowT = bil_transpose(hi, Hi, Ho);
+    }
+    __syncthreads();
+    const int hn = rowT.n;                        // weights are read from shared memory (dynamic indexing of a register copy would
+    const T* g0 = dy + ((int64_t)b * Ho + rowT.o_lo) * Wo * ld + coff;      // put the tables into local memory)
+    for (int idx = threadIdx.x; idx < Wi * cvt; idx += blockDim.x) {
+        const int wi = idx / cvt, cv = idx - wi * cvt;
+        const int wn = colT[wi].n;
+        const T* g = g0 + (int64_t)colT[wi].o_lo * ld + cv * V;
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        for (int a = 0; a < hn; ++a) {
+            float rowsum[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) rowsum[k] = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < wn; ++q) {
+                float f[V];
+                Vec<T>::load(g + ((int64_t)a * Wo + q) * ld).unpack(f);
+                const float wq = colT[wi].w[q];
+#pragma unroll
+                for (int k = 0; k < V; ++k) rowsum[k] = fmaf(wq, f[k], rowsum[k]);
+            }
+            const float wa = rowT.w[a];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(wa, rowsum[k], acc[k]);
+        }
+        Vec<T>::pack(acc).store(xrow + (int64_t)wi * C + cv * V);
+    }
+}
+
+// MaxPool2d(2, ceil_mode) backward, one thread per WINDOW (output pixel) and channel vector: the window's <= 4 inputs are read
+// once (the per-input-pixel form above reads every window four times), the first maximum in (h, w) scan order takes the
+// gradient (ATen's tie rule), the others get zero.
+template <typename T>
+__global__ void __launch_bounds__(512)
+maxpool2_bwd_window_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
+                           int Ho, int Wo, int accumulate) {
+    td::pdl_sync();
+    constexpr int V = Vec<T>::N;
+    const int cvt = C / V;
+    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
+    const int64_t img = (int64_t)b * H * W * C;
+    for (int idx = threadIdx.x; idx < Wo * cvt; idx += blockDim.x) {
+        const int wo = idx / cvt, c = (idx - wo * cvt) * V;
+        float f[4][V], g[V];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int hh = 2 * ho + (j >> 1), ww = 2 * wo + (j & 1);
+            ok[j] = hh < H && ww < W;
+            if (ok[j]) Vec<T>::load(x + img + ((int64_t)hh * W + ww) * C + c).unpack(f[j]);
+        }
+        Vec<T>::load(dy + (((int64_t)b * Ho + ho) * Wo + wo) * C + c).unpack(g);
+        int arg[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            float best = -INFINITY;
+            arg[k] = -1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (ok[j] && (f[j][k] > best || arg[k] < 0)) { best = f[j][k]; arg[k] = j; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!ok[j]) continue;
+            const int hh = 2 * ho + (j >> 1), ww = 2 * wo + (j & 1);
+            T* dst = dx + img + ((int64_t)hh * W + ww) * C + c;
+            float o[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = (arg[k] == j) ? g[k] : 0.f;
+            if (accumulate) {
+                float prev[V];
+                Vec<T>::load(dst).unpack(prev);
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] += prev[k];
+            }
+            Vec<T>::pack(o).store(dst);
+        }
+    }
+}
+
+static inline bool glue_walk() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("TD_GLUE_WALK"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v == 1;
+}
+static inline int row_threads(int64_t items) { return (int)std::min<int64_t>(1024, (items + 31) / 32 * 32); }
+
 // block (channel vectors, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
 static inline dim3 walk_block(int cv) {
     int bx = 1;
@@ -691,6 +807,11 @@ template <typename T>
 static int launch_resize_bwd(const void* dy, int64_t ld, int coff, void* dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
                              cudaStream_t s) {
     constexpr int V = Vec<T>::N;
+    if (!glue_walk()) {
+        td::launch(resize_bwd_gather_kernel<T>, td::LaunchCfg(B * Hi, row_threads((int64_t)Wi * C / V), 0, s), (const T*)dy, ld, coff,
+                   (T*)dx, B, Hi, Wi, Ho, Wo, C);
+        return TD_OK;
+    }
     const dim3 blk = walk_block(C / V);
     const int nseg = walk_segments((int64_t)B * Hi * (C / V), Wi);
     const dim3 grd((unsigned)(ceil_div((int64_t)B * Hi, blk.y) * nseg), (unsigned)ceil_div(C / V, blk.x), 1);
@@ -951,6 +1072,11 @@ extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtyp
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0, "td_maxpool2_bwd: channels must be a multiple of %d", V);
     const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
+    if (!glue_walk() && 2 * ho >= h && 2 * wo >= w) {            // every input pixel lies in a window (always true for ceil mode / even sizes)
+        TD_DISPATCH_T(dtype, (td::launch(maxpool2_bwd_window_kernel<T>, td::LaunchCfg(batch * ho, std::min(512, row_threads((int64_t)wo * c / V)), 0,
+                                 (cudaStream_t)stream), (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
+        return launch_status("maxpool2_bwd");
+    }
     TD_DISPATCH_T(dtype, (td::launch(maxpool2_bwd_kernel<T>, td::LaunchCfg(batch * h, row_block(c / V), 0, (cudaStream_t)stream), 
                              (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
     return launch_status("maxpool2_bwd");
