@@ -317,7 +317,9 @@ int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const float*
  *   td_bn_apply_fused      = td_bn_finalize + td_bn_relu_apply   (also writes scale / shift / save_mean / save_invstd and
  *                            updates the running statistics, diffusion.py:34-35)
  *   td_bn_bwd_reduce       = td_bn_relu_bwd_reduce with one partial row per pixel chunk (td_bn_bwd_reduce_rows() <= 148)
- *   td_bn_bwd_apply_fused  = td_bn_bwd_finalize + td_bn_relu_bwd_apply (writes dgamma / dbeta) */
+ *   td_bn_bwd_apply_fused  = td_bn_bwd_finalize + td_bn_relu_bwd_apply (writes dgamma / dbeta)
+ * The three evaluate the pre-activation as scale * (y - mean) + beta (beta = the BatchNorm bias parameter): under the raw-t
+ * time embedding y carries per-channel offsets of O(1e2..1e3), and y * scale + shift cancels in fp32. */
 int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t count, const float* gamma,
                       const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                       float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
@@ -325,10 +327,10 @@ int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t 
                       int relu, void* stream);
 int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels);
 int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
-                     const float* shift, const float* save_mean, int64_t pixels, int channels, float* partials,
+                     const float* beta, const float* save_mean, int64_t pixels, int channels, float* partials,
                      void* stream);
 int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* partials,
-                          int nrows, int64_t count, const float* scale, const float* shift, const float* save_mean,
+                          int nrows, int64_t count, const float* scale, const float* beta, const float* save_mean,
                           const float* save_invstd, float* dgamma, float* dbeta, void* dy, int64_t pixels, int channels,
                           void* stream);
 

@@ -201,95 +201,6 @@ resize_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi,
     resample_row<T>(r0, r1, C, bh.l0, bh.l1, col, w_begin, w_end, nullptr, y + (int64_t)row * Wo * C + c, C);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Gather form of the same two operators (default; TD_GLUE_WALK=1 selects the row walkers above): one CTA per output row,
-// one thread per (pixel, 16-byte channel vector) with the channel vectors of a pixel on consecutive lanes, so a warp reads and
-// writes whole pixels (256..512 contiguous bytes).  The four taps of a thread are independent loads -- the row walkers
-// serialise a thread's loads along the row and ran at 0.3-0.5 of the HBM peak -- and the column coefficients come from a
-// shared-memory table built once per CTA, so there is no per-element integer division or bilinear setup.
-//   out = h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)          (ATen's upsample_bilinear2d order)
-// ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ inline void gather4(const T* __restrict__ base, int64_t row0, int64_t row1, int ch_stride, const Bil& bw, float h0,
-                               float h1, float* r) {
-    constexpr int V = Vec<T>::N;
-    float a[V], b[V], c[V], d[V];
-    Vec<T>::load(base + row0 + (int64_t)bw.i0 * ch_stride).unpack(a);
-    Vec<T>::load(base + row0 + (int64_t)bw.i1 * ch_stride).unpack(b);
-    Vec<T>::load(base + row1 + (int64_t)bw.i0 * ch_stride).unpack(c);
-    Vec<T>::load(base + row1 + (int64_t)bw.i1 * ch_stride).unpack(d);
-#pragma unroll
-    for (int k = 0; k < V; ++k) r[k] = h0 * (bw.l0 * a[k] + bw.l1 * b[k]) + h1 * (bw.l0 * c[k] + bw.l1 * d[k]);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(1024)
-upcat_gather_kernel(const T* __restrict__ low, const T* __restrict__ skip, const float* __restrict__ temb, int ld_temb,
-                    int temb_off, T* __restrict__ out, int B, int Ho, int Wo, int Cu, int Hs, int Ws, int Cs) {
-    td::pdl_sync();
-    constexpr int V = Vec<T>::N;
-    __shared__ Bil colL[kMaxRowW], colS[kMaxRowW];
-    const int Ct = Cu + Cs, cvt = Ct / V, cvu = Cu / V;
-    const int Hl = Ho / 2, Wl = Wo / 2;
-    const bool same = Hs == Ho && Ws == Wo;
-    for (int i = threadIdx.x; i < Wo; i += blockDim.x) {
-        colL[i] = bil(i, Wl, Wo);
-        colS[i] = bil(i, Ws, Wo);
-    }
-    __syncthreads();
-    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
-    const Bil hL = bil(ho, Hl, Ho), hS = bil(ho, Hs, Ho);
-    const int64_t l0 = ((int64_t)b * Hl + hL.i0) * Wl * Cu, l1 = ((int64_t)b * Hl + hL.i1) * Wl * Cu;
-    const int64_t s0 = ((int64_t)b * Hs + hS.i0) * Ws * Cs, s1 = ((int64_t)b * Hs + hS.i1) * Ws * Cs;
-    T* orow = out + (int64_t)blockIdx.x * Wo * Ct;
-    const float* te = temb + (int64_t)b * ld_temb + temb_off;
-    for (int idx = threadIdx.x; idx < Wo * cvt; idx += blockDim.x) {
-        const int wo = idx / cvt, cv = idx - wo * cvt;
-        float r[V];
-        if (cv < cvu) {
-            gather4<T>(low + cv * V, l0, l1, Cu, colL[wo], hL.l0, hL.l1, r);
-        } else {
-            const int c = (cv - cvu) * V;
-            if (same) Vec<T>::load(skip + s0 + (int64_t)wo * Cs + c).unpack(r);
-            else gather4<T>(skip + c, s0, s1, Cs, colS[wo], hS.l0, hS.l1, r);
-            // the embedding is constant over space and the bilinear weights sum to one: resize(skip + t) == resize(skip) + t
-#pragma unroll
-            for (int k = 0; k < V; ++k) r[k] += te[c + k];
-        }
-        Vec<T>::pack(r).store(orow + (int64_t)wo * Ct + cv * V);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(1024)
-resize_gather_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int Hi, int Wi, int Ho, int Wo, int C) {
-    td::pdl_sync();
-    constexpr int V = Vec<T>::N;
-    __shared__ Bil col[kMaxRowW];
-    for (int i = threadIdx.x; i < Wo; i += blockDim.x) col[i] = bil(i, Wi, Wo);
-    __syncthreads();
-    const int cvt = C / V;
-    const int b = blockIdx.x / Ho, ho = blockIdx.x - b * Ho;
-    const Bil bh = bil(ho, Hi, Ho);
-    const int64_t r0 = ((int64_t)b * Hi + bh.i0) * Wi * C, r1 = ((int64_t)b * Hi + bh.i1) * Wi * C;
-    T* orow = y + (int64_t)blockIdx.x * Wo * C;
-    for (int idx = threadIdx.x; idx < Wo * cvt; idx += blockDim.x) {
-        const int wo = idx / cvt, cv = idx - wo * cvt;
-        float r[V];
-        gather4<T>(x + cv * V, r0, r1, C, col[wo], bh.l0, bh.l1, r);
-        Vec<T>::pack(r).store(orow + (int64_t)wo * C + cv * V);
-    }
-}
-
-static inline bool glue_walk() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("TD_GLUE_WALK"); v = (e && atoi(e) != 0) ? 1 : 0; }
-    return v == 1;
-}
-static inline int row_threads(int64_t items) {           // one CTA per row: a multiple of 32 threads, at most 1024
-    return (int)std::min<int64_t>(1024, (items + 31) / 32 * 32);
-}
-
 // block (vectors of one half, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
 static inline dim3 walk_block(int cv) {
     int bx = 1;
@@ -414,18 +325,6 @@ extern "C" int td_upcat_fwd(const void* low, const void* skip, const float* temb
     TD_CHECK_ARG(low && skip && temb && out, "td_upcat_fwd: null pointer");
     TD_CHECK_ARG(batch > 0 && ho > 0 && wo > 0 && ho % 2 == 0 && wo % 2 == 0 && wo <= kMaxRowW, "td_upcat_fwd: bad output size");
     cudaStream_t s = (cudaStream_t)stream;
-    if (!glue_walk() && (dtype == TD_BF16 || dtype == TD_F32)) {
-        const int V = dtype == TD_BF16 ? 8 : 4;
-        TD_CHECK_ARG(cu % V == 0 && cs % V == 0, "td_upcat_fwd: channel counts must be multiples of %d", V);
-        const int thr = row_threads((int64_t)wo * (cu + cs) / V);
-        if (dtype == TD_BF16)
-            td::launch(upcat_gather_kernel<__nv_bfloat16>, td::LaunchCfg(batch * ho, thr, 0, s), (const __nv_bfloat16*)low,
-                       (const __nv_bfloat16*)skip, temb, ld_temb, temb_off, (__nv_bfloat16*)out, batch, ho, wo, cu, hs, ws, cs);
-        else
-            td::launch(upcat_gather_kernel<float>, td::LaunchCfg(batch * ho, thr, 0, s), (const float*)low, (const float*)skip, temb,
-                       ld_temb, temb_off, (float*)out, batch, ho, wo, cu, hs, ws, cs);
-        return launch_status("upcat");
-    }
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(cu % 8 == 0 && cs % 8 == 0, "td_upcat_fwd: channel counts must be multiples of 8");
         const int cvh = std::max(cu, cs) / 8;
@@ -454,17 +353,6 @@ extern "C" int td_resize_bilinear_fwd(const void* x, void* y, int dtype, int bat
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && y && batch > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && wo <= kMaxRowW && c > 0, "td_resize_bilinear_fwd: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    if (!glue_walk() && (dtype == TD_BF16 || dtype == TD_F32)) {
-        const int V = dtype == TD_BF16 ? 8 : 4;
-        TD_CHECK_ARG(c % V == 0, "td_resize_bilinear_fwd: channels must be a multiple of %d", V);
-        const int thr = row_threads((int64_t)wo * c / V);
-        if (dtype == TD_BF16)
-            td::launch(resize_gather_kernel<__nv_bfloat16>, td::LaunchCfg(batch * ho, thr, 0, s), (const __nv_bfloat16*)x,
-                       (__nv_bfloat16*)y, batch, hi, wi, ho, wo, c);
-        else
-            td::launch(resize_gather_kernel<float>, td::LaunchCfg(batch * ho, thr, 0, s), (const float*)x, (float*)y, batch, hi, wi, ho, wo, c);
-        return launch_status("resize_bilinear");
-    }
     if (dtype == TD_BF16) {
         TD_CHECK_ARG(c % 8 == 0, "td_resize_bilinear_fwd: channels must be a multiple of 8 for bf16");
         const dim3 blk = walk_block(c / 8);

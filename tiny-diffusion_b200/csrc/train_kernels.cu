@@ -321,7 +321,7 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
     constexpr int V = Vec<T>::N;
     constexpr int TPP = kSlice / V;                 // threads per pixel
     constexpr int PPP = kT / TPP;                   // pixels per pass
-    __shared__ float s_sc[kSlice], s_sh[kSlice];
+    __shared__ float s_sc[kSlice], s_sh[kSlice], s_mu[kSlice];      // scale, beta, mean
     const int c_base = blockIdx.y * kSlice;
     {
         const int c = c_base + (threadIdx.x & 31);
@@ -348,7 +348,8 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
             const float sc = g_c * invstd;
             const float sh = b_c - (float)mean * sc;
             s_sc[threadIdx.x] = sc;
-            s_sh[threadIdx.x] = sh;
+            s_sh[threadIdx.x] = b_c;
+            s_mu[threadIdx.x] = (float)mean;
             if (blockIdx.x == 0) {
                 scale_out[c] = sc;
                 shift_out[c] = sh;
@@ -364,10 +365,12 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
         }
         __syncthreads();
     }
+    // a = relu(scale * (y - mean) + beta): y carries per-channel offsets of O(1e2..1e3) under the raw-t time embedding, and
+    // y * scale + (beta - mean * scale) would cancel in fp32 (ReLU masks flip at pre-activations of ~1e-5)
     const int lane_c = (threadIdx.x % TPP) * V;
-    float sc[V], sh[V];
+    float sc[V], sh[V], mu[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { sc[k] = s_sc[lane_c + k]; sh[k] = s_sh[lane_c + k]; }
+    for (int k = 0; k < V; ++k) { sc[k] = s_sc[lane_c + k]; sh[k] = s_sh[lane_c + k]; mu[k] = s_mu[lane_c + k]; }
     const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
     const int c0 = c_base + lane_c;
 #pragma unroll 4
@@ -376,7 +379,7 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
         load_f32<V>(y + p * C + c0, f);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            f[k] = fmaf(f[k], sc[k], sh[k]);
+            f[k] = fmaf(f[k] - mu[k], sc[k], sh[k]);
             if (relu) f[k] = fmaxf(f[k], 0.f);
         }
         Vec<T>::pack(f).store(a + p * lda + a_coff + c0);
@@ -388,7 +391,7 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
 template <typename T>
 __global__ void __launch_bounds__(kT)
 bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y, int64_t P, int C,
-                            const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                            const float* __restrict__ scale, const float* __restrict__ beta, const float* __restrict__ mean,
                             float* __restrict__ partials) {
     td::pdl_sync();
     constexpr int V = Vec<T>::N;
@@ -400,7 +403,7 @@ bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff,
     const int c0 = c_base + lane_c;
     float s1[V], s2[V], sc[V], sh[V], mu[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = scale[c0 + k]; sh[k] = shift[c0 + k]; mu[k] = mean[c0 + k]; }
+    for (int k = 0; k < V; ++k) { s1[k] = 0.f; s2[k] = 0.f; sc[k] = scale[c0 + k]; sh[k] = beta[c0 + k]; mu[k] = mean[c0 + k]; }
     const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
 #pragma unroll 4
     for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
@@ -409,9 +412,10 @@ bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff,
         load_f32<V>(y + p * C + c0, yy);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            const float g = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? f[k] : 0.f;
+            const float d = yy[k] - mu[k];
+            const float g = (fmaf(d, sc[k], sh[k]) > 0.f) ? f[k] : 0.f;      // the forward's pre-activation, same op order
             s1[k] += g;
-            s2[k] = fmaf(g, yy[k] - mu[k], s2[k]);
+            s2[k] = fmaf(g, d, s2[k]);
         }
     }
     const int prow = threadIdx.x / TPP;
@@ -435,20 +439,20 @@ template <typename T>
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y,
                           const float* __restrict__ partials, int nrows, double count, const float* __restrict__ scale,
-                          const float* __restrict__ shift, const float* __restrict__ save_mean,
+                          const float* __restrict__ beta, const float* __restrict__ save_mean,
                           const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                           T* __restrict__ dy, int64_t P, int C) {
     td::pdl_sync();
     constexpr int V = Vec<T>::N;
     constexpr int TPP = kSlice / V;
     constexpr int PPP = kT / TPP;
-    __shared__ float s_co[5][kSlice];               // scale, shift, cA, cB, cC
+    __shared__ float s_co[6][kSlice];               // scale, beta, cA, cB, cC, mean
     const int c_base = blockIdx.y * kSlice;
     {
         const int c = c_base + (threadIdx.x & 31);
         const bool tail = threadIdx.x < 32;
         float mean_c = 0.f, invstd_c = 0.f, sc_c = 0.f, sh_c = 0.f;
-        if (tail) { mean_c = save_mean[c]; invstd_c = save_invstd[c]; sc_c = scale[c]; sh_c = shift[c]; }
+        if (tail) { mean_c = save_mean[c]; invstd_c = save_invstd[c]; sc_c = scale[c]; sh_c = beta[c]; }
         double s1, s2;
         slice_sum_partials(partials, nrows, C, c_base, s1, s2);
         if (tail) {
@@ -459,7 +463,10 @@ bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, c
             s_co[1][threadIdx.x] = sh_c;
             s_co[2][threadIdx.x] = (float)sc;
             s_co[3][threadIdx.x] = (float)cB;
-            s_co[4][threadIdx.x] = (float)(-sc * s1 / count - cB * mean);
+            // dy = cA*g + cB*(y - mean) + cC with the mean subtracted per element: y carries per-channel offsets of O(1e2..1e3)
+            // (raw-t time embedding), and cB*y + (cC - cB*mean) would cancel in fp32
+            s_co[4][threadIdx.x] = (float)(-sc * s1 / count);
+            s_co[5][threadIdx.x] = mean_c;
             if (blockIdx.x == 0) {
                 dgamma[c] = (float)dg;
                 dbeta[c] = (float)s1;
@@ -468,11 +475,11 @@ bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, c
         __syncthreads();
     }
     const int lane_c = (threadIdx.x % TPP) * V;
-    float sc[V], sh[V], cA[V], cB[V], cC[V];
+    float sc[V], sh[V], cA[V], cB[V], cC[V], mu[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         sc[k] = s_co[0][lane_c + k]; sh[k] = s_co[1][lane_c + k];
-        cA[k] = s_co[2][lane_c + k]; cB[k] = s_co[3][lane_c + k]; cC[k] = s_co[4][lane_c + k];
+        cA[k] = s_co[2][lane_c + k]; cB[k] = s_co[3][lane_c + k]; cC[k] = s_co[4][lane_c + k]; mu[k] = s_co[5][lane_c + k];
     }
     const int64_t p_lo = P * blockIdx.x / gridDim.x, p_hi = P * (blockIdx.x + 1) / gridDim.x;
     const int c0 = c_base + lane_c;
@@ -483,8 +490,9 @@ bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, c
         load_f32<V>(y + p * C + c0, yy);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-            const float gm = (fmaf(yy[k], sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
-            g[k] = fmaf(cA[k], gm, fmaf(cB[k], yy[k], cC[k]));
+            const float d = yy[k] - mu[k];
+            const float gm = (fmaf(d, sc[k], sh[k]) > 0.f) ? g[k] : 0.f;
+            g[k] = fmaf(cA[k], gm, fmaf(cB[k], d, cC[k]));
         }
         Vec<T>::pack(g).store(dy + p * C + c0);
     }
@@ -673,69 +681,11 @@ resize_bwd_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict_
     }
 }
 
-// Gather form of the transposed resize (default; TD_GLUE_WALK=1 selects the walker above): one CTA per INPUT row, one thread
-// per (input pixel, 16-byte channel vector), channel vectors on consecutive lanes.  The weights with which an input row /
-// column enters the output rows / columns (bil_transpose) are tabulated in shared memory once per CTA; a thread then sums
-//   dx[hi, wi] = sum_a wh[a] * ( sum_k ww[k] * dy[oh + a, ow + k] )
-// with all of its loads independent (<= 4 x 4 taps for a 2x up-sampling, ~3 x 3 for 28 <- 32), in a fixed order.
-template <typename T>
-__global__ void __launch_bounds__(1024)
-resize_bwd_gather_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int B, int Hi, int Wi, int Ho,
-                         int Wo, int C) {
-    td::pdl_sync();
-    constexpr int V = Vec<T>::N;
-    __shared__ BilT colT[kMaxRowW];
-    __shared__ BilT rowT;
-    const int b = blockIdx.x / Hi, hi = blockIdx.x - b * Hi;
-    const int cvt = C / V;
-    T* xrow = dx + (int64_t)blockIdx.x * Wi * C;
-    if (Hi == Ho && Wi == Wo) {
-        const T* g = dy + (int64_t)blockIdx.x * Wo * ld + coff;
-        for (int idx = threadIdx.x; idx < Wi * cvt; idx += blockDim.x) {
-            const int w = idx / cvt, cv = idx - w * cvt;
-            Vec<T>::load(g + (int64_t)w * ld + cv * V).store(xrow + (int64_t)w * C + cv * V);
-        }
-        return;
-    }
-    for (int i = threadIdx.x; i <= Wi; i += blockDim.x) {
-        if (i < Wi) colT[i] = bil_transpose(i, Wi, Wo);
-        else rowT = bil_transpose(hi, Hi, Ho);
-    }
-    __syncthreads();
-    const int hn = rowT.n;                        // weights are read from shared memory (dynamic indexing of a register copy would
-    const T* g0 = dy + ((int64_t)b * Ho + rowT.o_lo) * Wo * ld + coff;      // put the tables into local memory)
-    for (int idx = threadIdx.x; idx < Wi * cvt; idx += blockDim.x) {
-        const int wi = idx / cvt, cv = idx - wi * cvt;
-        const int wn = colT[wi].n;
-        const T* g = g0 + (int64_t)colT[wi].o_lo * ld + cv * V;
-        float acc[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] = 0.f;
-        for (int a = 0; a < hn; ++a) {
-            float rowsum[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) rowsum[k] = 0.f;
-#pragma unroll 4
-            for (int q = 0; q < wn; ++q) {
-                float f[V];
-                Vec<T>::load(g + ((int64_t)a * Wo + q) * ld).unpack(f);
-                const float wq = colT[wi].w[q];
-#pragma unroll
-                for (int k = 0; k < V; ++k) rowsum[k] = fmaf(wq, f[k], rowsum[k]);
-            }
-            const float wa = rowT.w[a];
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(wa, rowsum[k], acc[k]);
-        }
-        Vec<T>::pack(acc).store(xrow + (int64_t)wi * C + cv * V);
-    }
-}
-
 // MaxPool2d(2, ceil_mode) backward, one thread per WINDOW (output pixel) and channel vector: the window's <= 4 inputs are read
 // once (the per-input-pixel form above reads every window four times), the first maximum in (h, w) scan order takes the
 // gradient (ATen's tie rule), the others get zero.
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(256)
 maxpool2_bwd_window_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C,
                            int Ho, int Wo, int accumulate) {
     td::pdl_sync();
@@ -782,12 +732,8 @@ maxpool2_bwd_window_kernel(const T* __restrict__ x, const T* __restrict__ dy, T*
     }
 }
 
-static inline bool glue_walk() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("TD_GLUE_WALK"); v = (e && atoi(e) != 0) ? 1 : 0; }
-    return v == 1;
-}
-static inline int row_threads(int64_t items) { return (int)std::min<int64_t>(1024, (items + 31) / 32 * 32); }
+// one CTA per row, at most 256 threads looping over the row (several CTAs resident per SM)
+static inline int row_threads(int64_t items) { return (int)std::min<int64_t>(256, (items + 31) / 32 * 32); }
 
 // block (channel vectors, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
 static inline dim3 walk_block(int cv) {
@@ -807,11 +753,6 @@ template <typename T>
 static int launch_resize_bwd(const void* dy, int64_t ld, int coff, void* dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
                              cudaStream_t s) {
     constexpr int V = Vec<T>::N;
-    if (!glue_walk()) {
-        td::launch(resize_bwd_gather_kernel<T>, td::LaunchCfg(B * Hi, row_threads((int64_t)Wi * C / V), 0, s), (const T*)dy, ld, coff,
-                   (T*)dx, B, Hi, Wi, Ho, Wo, C);
-        return TD_OK;
-    }
     const dim3 blk = walk_block(C / V);
     const int nseg = walk_segments((int64_t)B * Hi * (C / V), Wi);
     const dim3 grd((unsigned)(ceil_div((int64_t)B * Hi, blk.y) * nseg), (unsigned)ceil_div(C / V, blk.x), 1);
@@ -1038,9 +979,10 @@ extern "C" int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels) {
 }
 
 extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
-                                const float* shift, const float* save_mean, int64_t pixels, int channels, float* partials,
+                                const float* beta, const float* save_mean, int64_t pixels, int channels, float* partials,
                                 void* stream) {
     TD_REQUIRE_ARCH();
+    const float* shift = beta;
     TD_CHECK_ARG(da && y && scale && shift && save_mean && partials && pixels > 0, "td_bn_bwd_reduce: bad args");
     TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_reduce: channels must be a multiple of 32");
     const dim3 grid((unsigned)td_bn_bwd_reduce_rows(dtype, pixels, channels), (unsigned)(channels / kSlice));
@@ -1050,10 +992,11 @@ extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const
 }
 
 extern "C" int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype,
-                                     const float* partials, int nrows, int64_t count, const float* scale, const float* shift,
+                                     const float* partials, int nrows, int64_t count, const float* scale, const float* beta,
                                      const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, void* dy,
                                      int64_t pixels, int channels, void* stream) {
     TD_REQUIRE_ARCH();
+    const float* shift = beta;
     TD_CHECK_ARG(da && y && partials && nrows > 0 && count > 0 && scale && shift && save_mean && save_invstd && dgamma && dbeta &&
                      dy && pixels > 0, "td_bn_bwd_apply_fused: bad args");
     TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_apply_fused: channels must be a multiple of 32");
@@ -1072,8 +1015,8 @@ extern "C" int td_maxpool2_bwd(const void* x, const void* dy, void* dx, int dtyp
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0, "td_maxpool2_bwd: channels must be a multiple of %d", V);
     const int ho = ceil_mode ? (h + 1) / 2 : h / 2, wo = ceil_mode ? (w + 1) / 2 : w / 2;
-    if (!glue_walk() && 2 * ho >= h && 2 * wo >= w) {            // every input pixel lies in a window (always true for ceil mode / even sizes)
-        TD_DISPATCH_T(dtype, (td::launch(maxpool2_bwd_window_kernel<T>, td::LaunchCfg(batch * ho, std::min(512, row_threads((int64_t)wo * c / V)), 0,
+    if (2 * ho >= h && 2 * wo >= w) {            // every input pixel lies in a window (always true for ceil mode / even sizes)
+        TD_DISPATCH_T(dtype, (td::launch(maxpool2_bwd_window_kernel<T>, td::LaunchCfg(batch * ho, row_threads((int64_t)wo * c / V), 0,
                                  (cudaStream_t)stream), (const T*)x, (const T*)dy, (T*)dx, batch, h, w, c, ho, wo, accumulate)));
         return launch_status("maxpool2_bwd");
     }

@@ -264,7 +264,7 @@ def bn_train_fwd(y, gamma, beta, conv_bias, running_mean, running_var, nbt, eps=
     return a, scale, shift, mean, invstd
 
 
-def bn_train_bwd(da, y, scale, shift, mean, invstd, fused=False):
+def bn_train_bwd(da, y, scale, shift, mean, invstd, fused=False, beta=None):
     """da: grad of the block output (fp32 / bf16), y: raw fp32 conv output.  Returns (dy, dgamma, dbeta).
     ``fused``: td_bn_bwd_reduce + td_bn_bwd_apply_fused instead of reduce + finalize + apply."""
     _dev(y)
@@ -276,12 +276,12 @@ def bn_train_bwd(da, y, scale, shift, mean, invstd, fused=False):
         rows = int(lib.td_bn_bwd_reduce_rows(dt, P, Cc))
         part = torch.empty(rows * 2 * Cc + Cc, device=y.device)
         st = L.stream_ptr()
-        L.check(lib.td_bn_bwd_reduce(da.data_ptr(), Cc, 0, y.data_ptr(), dt, scale.data_ptr(), shift.data_ptr(),
+        L.check(lib.td_bn_bwd_reduce(da.data_ptr(), Cc, 0, y.data_ptr(), dt, scale.data_ptr(), beta.data_ptr(),
                                      mean.data_ptr(), P, Cc, part.data_ptr(), st), "td_bn_bwd_reduce")
         dgamma, dbeta = torch.empty(Cc, device=y.device), torch.empty(Cc, device=y.device)
         dy = torch.empty_like(da)
         L.check(lib.td_bn_bwd_apply_fused(da.data_ptr(), Cc, 0, y.data_ptr(), dt, part.data_ptr(), rows, P, scale.data_ptr(),
-                                          shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
+                                          beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
                                           dbeta.data_ptr(), dy.data_ptr(), P, Cc, st), "td_bn_bwd_apply_fused")
         return dy, dgamma, dbeta
     rows = int(lib.td_chan_reduce_rows(dt, P, Cc))

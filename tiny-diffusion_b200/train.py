@@ -388,14 +388,15 @@ class UNetTrainEngine:
             yp, dap, dyp = y.data_ptr(), da.data_ptr(), dyv.data_ptr()
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
             coef = st_["coef"].data_ptr()
+            bt = bn.bias.data_ptr()
             blk, idx = name.split(".")
             dg = self.pgrad[f"{blk}.{int(idx) + 1}.weight"].data_ptr()
             db = self.pgrad[f"{blk}.{int(idx) + 1}.bias"].data_ptr()
 
             def bn_bwd(st):
-                L.check(lib.td_bn_bwd_reduce(dap, cout, 0, yp, adt, sc, sh, mu, P, cout, part, st), "td_bn_bwd_reduce")
+                L.check(lib.td_bn_bwd_reduce(dap, cout, 0, yp, adt, sc, bt, mu, P, cout, part, st), "td_bn_bwd_reduce")
                 # finalize (sum g, sum g*xhat -> dgamma / dbeta and the dy coefficients) in the prologue of the apply pass
-                L.check(lib.td_bn_bwd_apply_fused(dap, cout, 0, yp, adt, part, rows, P, sc, sh, mu, iv, dg, db, dyp, P, cout, st),
+                L.check(lib.td_bn_bwd_apply_fused(dap, cout, 0, yp, adt, part, rows, P, sc, bt, mu, iv, dg, db, dyp, P, cout, st),
                         "td_bn_bwd_apply_fused")
             bwd.append((f"bn:{name}:bwd", bn_bwd))
             eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT

@@ -91,3 +91,18 @@ for (hl, cu, hs, cs) in ((4, 512, 7, 512), (8, 256, 14, 256), (16, 128, 28, 128)
     fn = lambda: L.check(lib.td_upcat_bwd(dout.data_ptr(), dlow.data_ptr(), dskip.data_ptr(), dtemb.data_ptr(), cs, 0, L.TD_BF16, B,
                                           2 * hl, 2 * hl, cu, hs, hs, cs, L.stream_ptr()))
     report(f"upcat_bwd {2*hl}->{hl} [{cu}|{cs}]", timeit(fn), (dout.numel() * 2 + dlow.numel() + dskip.numel()) * 2)
+# maxpool backward
+for (h, c) in ((28, 128), (14, 256), (7, 512)):
+    xi = torch.randn(B, h, h, c, device=dev).to(bf)
+    ho = (h + 1) // 2
+    gy = torch.randn(B, ho, ho, c, device=dev).to(bf)
+    gx = torch.empty_like(xi)
+    fn = lambda: L.check(lib.td_maxpool2_bwd(xi.data_ptr(), gy.data_ptr(), gx.data_ptr(), L.TD_BF16, B, h, h, c, 1, 0, L.stream_ptr()))
+    report(f"maxpool_bwd {ho}->{h} C={c}", timeit(fn), (2 * xi.numel() + gy.numel()) * 2)
+# final resize 32 -> 28 forward / backward (train mode)
+d1 = torch.randn(B, 32, 32, 64, device=dev).to(bf)
+d1r = torch.empty(B, 28, 28, 64, device=dev, dtype=bf)
+report("resize 32->28 C=64", timeit(lambda: L.check(lib.td_resize_bilinear_fwd(d1.data_ptr(), d1r.data_ptr(), L.TD_BF16, B, 32, 32, 28, 28, 64,
+       L.stream_ptr()))), (d1.numel() + d1r.numel()) * 2)
+report("resize_bwd 28->32 C=64", timeit(lambda: L.check(lib.td_resize_bilinear_bwd(d1r.data_ptr(), 64, 0, d1.data_ptr(), L.TD_BF16, B, 32, 32, 28, 28,
+       64, L.stream_ptr()))), (d1.numel() + d1r.numel()) * 2)
