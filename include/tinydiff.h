@@ -413,6 +413,37 @@ int td_bn1d_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, cons
                 const float* gamma, const float* save_mean, const float* save_rstd, float* dx, int64_t lddx,
                 float* dgamma, float* dbeta, int M, int N, int relu, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The conv / attention VAE of the reference's vae_laion.py, fp32, NHWC activations.
+ * ---------------------------------------------------------------------------------------- */
+
+/* torch.nn.utils.spectral_norm (vae_laion.py:72-78,98-131,138-165): W_mat = the weight with `dim` first, flattened to
+ * [rows][cols] (dim1 = 0: plain Conv2d weight; dim1 = 1: ConvTranspose2d weight (Cin, Cout, kh, kw), rows = Cout,
+ * cols = Cin*khw).  Runs `power_iterations` updates v = normalize(W^T u), u = normalize(W v) in place (1 in a training-mode
+ * forward, 0 in eval mode), then sigma_out[0] = u^T W v.  scratch_rows: `rows` floats. */
+int td_spectral_sigma(const float* w, int rows, int cols, int dim1, int khw, float* u, float* v, int power_iterations,
+                      float eps, float* sigma_out, float* scratch_rows, void* stream);
+/* x[0, n) /= sigma_dev[0]  (folds 1/sigma of a spectral-norm 3x3 convolution into its BatchNorm scale) */
+int td_scale_by_inv_sigma(float* x, const float* sigma_dev, int n, void* stream);
+/* Operand packing of the 4x4 stride-2 layers, multiplied by 1 / sigma_dev[0] (sigma_dev may be NULL):
+ * transposed = 0: Conv2d weight (Cout, Cin, 4, 4)          -> [Cout][(ky*4+kx)*Cin + ci]
+ * transposed = 1: ConvTranspose2d weight (Cin, Cout, 4, 4) -> [4 output-parity classes][Cout][(j*2+i)*Cin + ci]. */
+int td_pack_conv4x4_weight(const float* w, const float* sigma_dev, float* out, int cout, int cin, int transposed,
+                           void* stream);
+/* nn.Conv2d(cin, cout, 4, stride=2, padding=1) (+ bias, TD_ACT_*), vae_laion.py:98-131.  x: NHWC (or NCHW when x_nchw);
+ * y: NHWC [batch][hin/2][win/2][cout]. */
+int td_conv4x4s2_fwd(const float* x, const float* w_packed, const float* bias, float* y, int batch, int hin, int win, int cin,
+                     int cout, int x_nchw, int act, void* stream);
+/* nn.ConvTranspose2d(cin, cout, 4, stride=2, padding=1) (+ bias, TD_ACT_*), vae_laion.py:138-165.  x: NHWC; y: NHWC
+ * [batch][2*hin][2*win][cout] (or NCHW when y_nchw). */
+int td_convT4x4s2_fwd(const float* x, const float* w_packed, const float* bias, float* y, int batch, int hin, int win, int cin,
+                      int cout, int y_nchw, int act, void* stream);
+/* SelfAttention.forward (vae_laion.py:57-65), flash-style: y = gamma * softmax(Q K^T) V + x with the softmax over all n = H*W
+ * keys (no scaling), never materialising the n x n matrix.  qkv: [batch][n][2*dq + dv] rows (q | k | v) of the fused 1x1
+ * convolutions; x, y: NHWC [batch][n][dv].  (dq, dv) in {(4, 32), (8, 64), (16, 128)}; n % 128 == 0. */
+int td_self_attention_fwd(const float* qkv, const float* x, const float* gamma, float* y, int batch, int n, int dq, int dv,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,6 +177,33 @@ def mlp_case(B: int = 8):
     print(modname, "loss", float(loss))
 
 
+def vae_laion_case():
+    """vae_laion.VAE encode / decode (vae_laion.py:177-196) of the reference's own class (imported through
+    shim.load_vae_laion: HF dataset, VGG16 download and the hard-coded CUDA device stubbed), fixture weights."""
+    from oracle.fixtures import checksum
+    mod = shim.load_vae_laion()
+    sd = init_state_dict("vae_laion")
+    model = shim.build_vae_laion(mod, sd)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(77))
+    z = torch.randn(1, 128, generator=torch.Generator().manual_seed(78))
+    with torch.no_grad():
+        mu, logvar = model.encode(x)
+        rec = model.decode(z)
+    g = {"x_seed": 77, "z_seed": 78, "mu": mu.clone(), "logvar": logvar.clone(), "recon_checksum": checksum(rec),
+         "recon_sub": rec[:, :, ::8, ::8].clone()}
+    # spectral_norm in a TRAINING forward: one power iteration of (u, v), then sigma (vae_laion.py:98 through torch's hook)
+    conv = model.encoder[1][0]
+    conv.train()
+    u0, v0 = conv.weight_u.clone(), conv.weight_v.clone()
+    conv(torch.zeros(1, 32, 8, 8))
+    w = conv.weight_orig.detach()
+    sigma = torch.dot(conv.weight_u, torch.mv(w.reshape(w.shape[0], -1), conv.weight_v))
+    g["power_iter"] = {"layer": "encoder.1.0", "u0": u0, "v0": v0, "u1": conv.weight_u.clone(), "v1": conv.weight_v.clone(),
+                       "sigma": sigma.clone()}
+    torch.save(g, os.path.join(OUT, "vae_laion.pt"))
+    print("vae_laion", float(mu.abs().mean()), float(rec.mean()))
+
+
 if __name__ == "__main__":
     assert shim.available(), "reference not mounted"
     torch.set_num_threads(os.cpu_count() or 1)
@@ -185,3 +212,4 @@ if __name__ == "__main__":
     laion_case()
     dit_case()
     mlp_case()
+    vae_laion_case()

@@ -118,6 +118,12 @@ _SIGS = {
     "td_bn_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "td_bn_bwd_apply_fused": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P,
                                         _P, C.c_int64, C.c_int, _P]),
+    "td_spectral_sigma": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P, _P]),
+    "td_scale_by_inv_sigma": (C.c_int, [_P, _P, C.c_int, _P]),
+    "td_pack_conv4x4_weight": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "td_conv4x4s2_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_convT4x4s2_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_self_attention_fwd": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_resize_bilinear_bwd": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, _P]),
