@@ -222,17 +222,17 @@ def test_psample_out_of_range_step_is_noop_and_odd_noise_rows(dev):
     n = 3 * 7                                            # 21 floats per noise row: rows 1, 2, 3 ... are misaligned
     x, eps = torch.randn(n, generator=g), torch.randn(n, generator=g)
     z = torch.randn(10, n, generator=g)
-    zd = z.to(dev)
+    zd, ed = z.to(dev), eps.to(dev)
     for t in (-1, 10, 11):
         xd = x.to(dev)
         td = torch.tensor([t], dtype=torch.int32, device=dev)
-        L.check(lib.td_psample_step(xd.data_ptr(), eps.to(dev).data_ptr(), zd.data_ptr(), n, tab["coef"].data_ptr(),
+        L.check(lib.td_psample_step(xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), n, tab["coef"].data_ptr(),
                                     td.data_ptr(), n, 10, None, L.stream_ptr()), "td_psample_step")
         assert torch.equal(xd.cpu(), x), t
     for t in (9, 5, 1, 0):
         xd = x.to(dev)
         td = torch.tensor([t], dtype=torch.int32, device=dev)
-        L.check(lib.td_psample_step(xd.data_ptr(), eps.to(dev).data_ptr(), zd.data_ptr(), n, tab["coef"].data_ptr(),
+        L.check(lib.td_psample_step(xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), n, tab["coef"].data_ptr(),
                                     td.data_ptr(), n, 10, None, L.stream_ptr()), "td_psample_step")
         want = O.p_sample_step(x, eps, z[t], t, fp.betas, fp.alphas, fp.alphas_cumprod)
         assert torch.equal(xd.cpu(), want), t

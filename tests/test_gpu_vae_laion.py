@@ -44,10 +44,11 @@ def test_conv4x4s2(dev, B, H, cin, cout, x_nchw, act):
     want = F.conv2d(x, w / sig, b, stride=2, padding=1)
     want = F.relu(want) if act == 1 else want
     wp = torch.empty(cout * 16 * cin, device=dev)
-    L.check(lib.td_pack_conv4x4_weight(w.to(dev).data_ptr(), sig.to(dev).data_ptr(), wp.data_ptr(), cout, cin, 0, L.stream_ptr()))
+    wd, sd_, bd = w.to(dev), sig.to(dev), b.to(dev)              # named: a temporary's block may be re-used before the launch
+    L.check(lib.td_pack_conv4x4_weight(wd.data_ptr(), sd_.data_ptr(), wp.data_ptr(), cout, cin, 0, L.stream_ptr()))
     xd = (x if x_nchw else nhwc(x)).to(dev).contiguous()
     y = torch.empty(B, H // 2, H // 2, cout, device=dev)
-    L.check(lib.td_conv4x4s2_fwd(xd.data_ptr(), wp.data_ptr(), b.to(dev).data_ptr(), y.data_ptr(), B, H, H, cin, cout, int(x_nchw),
+    L.check(lib.td_conv4x4s2_fwd(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y.data_ptr(), B, H, H, cin, cout, int(x_nchw),
                                  act, L.stream_ptr()))
     assert rel(nchw(y), want) < 1e-5
 
@@ -65,9 +66,10 @@ def test_conv_transpose4x4s2(dev, B, H, cin, cout, y_nchw, act):
     want = F.conv_transpose2d(x, w / sig, b, stride=2, padding=1)
     want = F.relu(want) if act == 1 else (torch.sigmoid(want) if act == 4 else want)
     wp = torch.empty(4 * cout * 4 * cin, device=dev)
-    L.check(lib.td_pack_conv4x4_weight(w.to(dev).data_ptr(), sig.to(dev).data_ptr(), wp.data_ptr(), cout, cin, 1, L.stream_ptr()))
+    wd, sd_, bd, xd = w.to(dev), sig.to(dev), b.to(dev), nhwc(x).to(dev)
+    L.check(lib.td_pack_conv4x4_weight(wd.data_ptr(), sd_.data_ptr(), wp.data_ptr(), cout, cin, 1, L.stream_ptr()))
     y = torch.empty((B, cout, 2 * H, 2 * H) if y_nchw else (B, 2 * H, 2 * H, cout), device=dev)
-    L.check(lib.td_convT4x4s2_fwd(nhwc(x).to(dev).data_ptr(), wp.data_ptr(), b.to(dev).data_ptr(), y.data_ptr(), B, H, H, cin, cout,
+    L.check(lib.td_convT4x4s2_fwd(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y.data_ptr(), B, H, H, cin, cout,
                                   int(y_nchw), act, L.stream_ptr()))
     got = y if y_nchw else nchw(y)
     assert rel(got, want) < 1e-5
@@ -94,8 +96,8 @@ def test_self_attention_flash(dev, C, H):
     qkv = (xf @ wqkv.t() + bqkv).contiguous().to(dev)
     xd = xf.contiguous().to(dev)
     y = torch.empty_like(xd)
-    L.check(lib.td_self_attention_fwd(qkv.data_ptr(), xd.data_ptr(), sd[f"{p}.gamma"].to(dev).data_ptr(), y.data_ptr(), B, n, dq, C,
-                                      L.stream_ptr()))
+    gd = sd[f"{p}.gamma"].to(dev)
+    L.check(lib.td_self_attention_fwd(qkv.data_ptr(), xd.data_ptr(), gd.data_ptr(), y.data_ptr(), B, n, dq, C, L.stream_ptr()))
     assert rel(nchw(y.view(B, H, H, C)), want) < 1e-4
 
 
@@ -111,10 +113,10 @@ def test_spectral_sigma(dev, layer, dim1, iters):
     wn = V.spectral_weight(sd, layer, dim=1 if dim1 else 0, training=bool(iters), new_uv=new)
     sigma_ref = float((w / wn).flatten()[w.flatten().abs().argmax()])
     rows = w.shape[1] if dim1 else w.shape[0]
-    ud, vd = u.to(dev), v.to(dev)
+    ud, vd, wd = u.to(dev), v.to(dev), w.to(dev)
     sig = torch.empty(1, device=dev)
     scratch = torch.empty(rows, device=dev)
-    L.check(lib.td_spectral_sigma(w.to(dev).data_ptr(), rows, w.numel() // rows, int(dim1), w.shape[2] * w.shape[3], ud.data_ptr(),
+    L.check(lib.td_spectral_sigma(wd.data_ptr(), rows, w.numel() // rows, int(dim1), w.shape[2] * w.shape[3], ud.data_ptr(),
                                   vd.data_ptr(), iters, 1e-12, sig.data_ptr(), scratch.data_ptr(), L.stream_ptr()))
     assert abs(float(sig) - sigma_ref) / abs(sigma_ref) < 1e-4
     if iters:
