@@ -444,6 +444,16 @@ int td_convT4x4s2_fwd(const float* x, const float* w_packed, const float* bias, 
 int td_self_attention_fwd(const float* qkv, const float* x, const float* gamma, float* y, int batch, int n, int dq, int dv,
                           void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused eval-mode forward of the dense denoisers (latent_diffusion.py:107-128, diffusion_transformer.py:81-109) at the
+ * reference batch sizes: one persistent kernel walks a device-resident tape of ops (Linear with bias / eval BatchNorm1d +
+ * ReLU / activation / residual / embedding gather in the epilogue, LayerNorm, add, time features) with grid barriers
+ * between dependent ops.  ops: `n_ops` records of td_dense_tape_op_bytes() bytes (layout: csrc/dense_fused.cu TapeOp);
+ * barrier: two zero-initialised uint32 (reusable).  max_ctas: 0 = default (<= 128, all co-resident).
+ * ---------------------------------------------------------------------------------------- */
+int td_dense_tape_op_bytes(void);
+int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned int* barrier, int max_ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
