@@ -32,7 +32,8 @@ struct TapeOp {                  // mirrored by tinydiff/dense.py (ctypes)
     const long long* t; const int* t_dev;
 };
 
-constexpr int TP_THREADS = 256, TP_RT = 32, TP_NT = 16, TP_KC = 64;
+constexpr int TP_THREADS = 256, TP_RT = 32, TP_NT = 16, TP_KMAX = 1024;
+constexpr int TP_SMEM = (TP_RT + TP_NT) * (TP_KMAX + 4) * 4;
 
 __device__ inline float tape_act(float v, int act) {
     switch (act) {
@@ -66,49 +67,86 @@ __device__ inline void grid_barrier(unsigned int* bar) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TP_THREADS)
+__device__ inline void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// stage `rows` rows of `K` floats (row r at src + r*ld, rows >= valid are zero) into smem rows of stride K + 4
+__device__ inline void stage_rows(float* dst, const float* __restrict__ src, long long ld, int rows, int valid, int K, bool vec) {
+    const int stride = K + 4;
+    if (vec) {
+        const int k4 = K >> 2;
+        for (int e = threadIdx.x; e < rows * k4; e += TP_THREADS) {
+            const int r = e / k4, q = e - r * k4;
+            if (r < valid) cp_async16(dst + r * stride + q * 4, src + (long long)r * ld + q * 4);
+            else *reinterpret_cast<float4*>(dst + r * stride + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        for (int e = threadIdx.x; e < rows * K; e += TP_THREADS) {
+            const int r = e / K, k = e - r * K;
+            dst[r * stride + k] = r < valid ? __ldcg(src + (long long)r * ld + k) : 0.f;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
 dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned int* bar) {
+    extern __shared__ __align__(16) float tp_smem[];
+    float* const xs = tp_smem;                                   // [TP_RT][K + 4]
     td::pdl_sync();
-    __shared__ float xs[TP_RT][TP_KC + 1];
-    __shared__ float ws[TP_NT][TP_KC + 1];
     const int tid = threadIdx.x;
     for (int oi = 0; oi < n_ops; ++oi) {
         const TapeOp op = ops[oi];
-        if (op.barrier_before) grid_barrier(bar);
         if (op.kind == 0) {
-            // ---- Linear: tiles of 32 rows x 16 features; thread = (row, feature pair)
+            // ---- Linear: tiles of 32 rows x 16 features over the grid; the whole K extent of a tile's operands is staged in
+            // shared memory with asynchronous copies (one memory latency per op); the WEIGHT slice does not depend on earlier
+            // ops and is requested BEFORE the grid barrier.  thread = (row, features c and c + 8).
             const int row_tiles = (M + TP_RT - 1) / TP_RT, col_tiles = (op.N + TP_NT - 1) / TP_NT;
-            const int r = tid >> 3, cp = (tid & 7) * 2;
-            for (int tile = blockIdx.x; tile < row_tiles * col_tiles; tile += gridDim.x) {
+            const int n_tiles = row_tiles * col_tiles;
+            const int stride = op.K + 4;
+            float* const ws = xs + TP_RT * stride;               // [TP_NT][K + 4]
+            const bool vecw = (op.K & 3) == 0 && ((uintptr_t)op.w & 15) == 0;
+            const bool vecx = (op.K & 3) == 0 && ((uintptr_t)op.x & 15) == 0 && (op.ldx & 3) == 0;
+            const int r = tid >> 3, c = tid & 7;
+            __syncthreads();                                     // the previous op's tile is no longer read
+            bool w_staged = false;
+            if ((int)blockIdx.x < n_tiles && vecw) {
+                const int n0 = ((int)blockIdx.x / row_tiles) * TP_NT;
+                stage_rows(ws, op.w + (long long)n0 * op.K, op.K, TP_NT, min(TP_NT, op.N - n0), op.K, true);
+                w_staged = true;
+            }
+            if (op.barrier_before) grid_barrier(bar);
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int rt = tile % row_tiles, ct = tile / row_tiles;
                 const int m0 = rt * TP_RT, n0 = ct * TP_NT;
-                float a0 = 0.f, a1 = 0.f;
-                for (int k0 = 0; k0 < op.K; k0 += TP_KC) {
+                if (!w_staged) {
                     __syncthreads();
-                    for (int e = tid; e < TP_RT * TP_KC; e += TP_THREADS) {
-                        const int rr = e / TP_KC, kk = e - rr * TP_KC;
-                        const int m = m0 + rr, k = k0 + kk;
-                        xs[rr][kk] = (m < M && k < op.K) ? __ldcg(op.x + (long long)m * op.ldx + k) : 0.f;
-                    }
-                    for (int e = tid; e < TP_NT * TP_KC; e += TP_THREADS) {
-                        const int nn = e / TP_KC, kk = e - nn * TP_KC;
-                        const int n = n0 + nn, k = k0 + kk;
-                        ws[nn][kk] = (n < op.N && k < op.K) ? __ldg(op.w + (long long)n * op.K + k) : 0.f;
-                    }
-                    __syncthreads();
-#pragma unroll 16
-                    for (int kk = 0; kk < TP_KC; ++kk) {
-                        const float xv = xs[r][kk];
-                        a0 = fmaf(xv, ws[cp][kk], a0);
-                        a1 = fmaf(xv, ws[cp + 1][kk], a1);
-                    }
+                    stage_rows(ws, op.w + (long long)n0 * op.K, op.K, TP_NT, min(TP_NT, op.N - n0), op.K, vecw);
                 }
+                w_staged = false;
+                stage_rows(xs, op.x + (long long)m0 * op.ldx, op.ldx, TP_RT, min(TP_RT, M - m0), op.K, vecx);
+                cp_async_wait_all();
+                __syncthreads();
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;     // two partial sums per output: shorter dependent FMA chains
+                const float* xr = xs + r * stride;
+                const float* w0 = ws + c * stride;
+                const float* w1 = ws + (c + 8) * stride;
+                int k = 0;
+                for (; k + 4 <= op.K; k += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+                    const float4 u = *reinterpret_cast<const float4*>(w0 + k);
+                    const float4 v = *reinterpret_cast<const float4*>(w1 + k);
+                    a0 = fmaf(xv.x, u.x, a0); b0 = fmaf(xv.y, u.y, b0); a0 = fmaf(xv.z, u.z, a0); b0 = fmaf(xv.w, u.w, b0);
+                    a1 = fmaf(xv.x, v.x, a1); b1 = fmaf(xv.y, v.y, b1); a1 = fmaf(xv.z, v.z, a1); b1 = fmaf(xv.w, v.w, b1);
+                }
+                for (; k < op.K; ++k) { a0 = fmaf(xr[k], w0[k], a0); a1 = fmaf(xr[k], w1[k], a1); }
                 const int m = m0 + r;
                 if (m < M) {
-                    float acc[2] = {a0, a1};
+                    const float acc[2] = {a0 + b0, a1 + b1};
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const int n = n0 + cp + j;
+                        const int n = n0 + c + 8 * j;
                         if (n >= op.N) continue;
                         float v = acc[j] + (op.bias ? __ldg(op.bias + n) : 0.f);
                         if (op.bn_mean) {         // eval-mode BatchNorm1d (+ ReLU): (x - mean) * invstd * gamma + beta
@@ -123,7 +161,10 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned int
                     }
                 }
             }
-        } else if (op.kind == 1) {
+            continue;
+        }
+        if (op.barrier_before) grid_barrier(bar);
+        if (op.kind == 1) {
             // ---- LayerNorm over N features: one warp per row, two-pass (mean, then centred variance) like ATen
             const int warp = tid >> 5, lane = tid & 31;
             for (int m = blockIdx.x * (TP_THREADS / 32) + warp; m < M; m += gridDim.x * (TP_THREADS / 32)) {
@@ -177,10 +218,15 @@ extern "C" int td_dense_tape_op_bytes(void) { return (int)sizeof(TapeOp); }
 extern "C" int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned int* barrier, int max_ctas, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(ops && n_ops > 0 && batch > 0 && barrier, "td_dense_tape_run: bad args");
+    static bool configured = false;
+    if (!configured) {
+        TD_CUDA(cudaFuncSetAttribute(dense_tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+        configured = true;
+    }
     // the grid barrier needs every CTA resident at once: never more CTAs than SMs (one small CTA per SM)
     int grid = std::min(kNumSMs - 20, 128);
     if (max_ctas > 0) grid = std::min(grid, max_ctas);
-    td::launch(dense_tape_kernel, td::LaunchCfg(grid, TP_THREADS, 0, (cudaStream_t)stream), reinterpret_cast<const TapeOp*>(ops), n_ops,
+    td::launch(dense_tape_kernel, td::LaunchCfg(grid, TP_THREADS, TP_SMEM, (cudaStream_t)stream), reinterpret_cast<const TapeOp*>(ops), n_ops,
                batch, barrier);
     return launch_status("dense_tape");
 }

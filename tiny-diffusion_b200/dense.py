@@ -243,7 +243,8 @@ class DenseEngine:
         self.fwd_flops = self.flops
         self.bwd_ops = self._build_backward() if self.training else []
         self._tapes = None
-        if not self.training and self.B <= FUSED_MAX_BATCH and os.environ.get("TD_DENSE_FUSED", "1") != "0":
+        if (not self.training and self.B <= FUSED_MAX_BATCH and os.environ.get("TD_DENSE_FUSED", "1") != "0"
+                and all(op["w"].shape[1] <= 1024 for op in self._ops if op["kind"] == "linear")):      # K staged whole in smem
             self._build_tapes()
 
     # ------------------------------------------------------------------ fused eval-mode forward (one persistent kernel)
