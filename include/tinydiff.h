@@ -318,18 +318,20 @@ int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, const float*
  *                            updates the running statistics, diffusion.py:34-35)
  *   td_bn_bwd_reduce       = td_bn_relu_bwd_reduce with one partial row per pixel chunk (td_bn_bwd_reduce_rows() <= 148)
  *   td_bn_bwd_apply_fused  = td_bn_bwd_finalize + td_bn_relu_bwd_apply (writes dgamma / dbeta)
+ * y (the raw conv output) is fp32, or bf16 (y_dtype = TD_BF16, with bf16 activations) on layers whose outputs carry no large
+ * per-sample offsets -- every layer except the three that consume a decoder concat.
  * The three evaluate the pre-activation as scale * (y - mean) + beta (beta = the BatchNorm bias parameter): under the raw-t
  * time embedding y carries per-channel offsets of O(1e2..1e3), and y * scale + shift cancels in fp32. */
-int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t count, const float* gamma,
+int td_bn_apply_fused(const void* y, int y_dtype, const float* partials, int nrows, int64_t count, const float* gamma,
                       const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                       float* running_var, int64_t* num_batches_tracked, float* scale, float* shift, float* save_mean,
                       float* save_invstd, void* a, int dtype, int64_t lda, int a_coff, int64_t pixels, int channels,
                       int relu, void* stream);
 int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels);
-int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
+int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int y_dtype, int dtype, const float* scale,
                      const float* beta, const float* save_mean, int64_t pixels, int channels, float* partials,
                      void* stream);
-int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* partials,
+int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const void* y, int y_dtype, int dtype, const float* partials,
                           int nrows, int64_t count, const float* scale, const float* beta, const float* save_mean,
                           const float* save_invstd, float* dgamma, float* dbeta, void* dy, int64_t pixels, int channels,
                           void* stream);
@@ -449,10 +451,11 @@ int td_self_attention_fwd(const float* qkv, const float* x, const float* gamma, 
  * reference batch sizes: one persistent kernel walks a device-resident tape of ops (Linear with bias / eval BatchNorm1d +
  * ReLU / activation / residual / embedding gather in the epilogue, LayerNorm, add, time features) with grid barriers
  * between dependent ops.  ops: `n_ops` records of td_dense_tape_op_bytes() bytes (layout: csrc/dense_fused.cu TapeOp);
- * barrier: two zero-initialised uint32 (reusable).  max_ctas: 0 = default (<= 128, all co-resident).
+ * barrier: one zero-initialised uint64 arrival counter (never reset; launches that share it must use the same max_ctas).
+ * max_ctas: 0 = default (<= 128, all co-resident).
  * ---------------------------------------------------------------------------------------- */
 int td_dense_tape_op_bytes(void);
-int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned int* barrier, int max_ctas, void* stream);
+int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned long long* barrier, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,11 +112,11 @@ _SIGS = {
     "td_bn_relu_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "td_bn_bwd_finalize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "td_bn_relu_bwd_apply": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
-    "td_bn_apply_fused": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P,
+    "td_bn_apply_fused": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int64, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P,
                                     _P, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _P]),
     "td_bn_bwd_reduce_rows": (C.c_int, [C.c_int, C.c_int64, C.c_int]),
-    "td_bn_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
-    "td_bn_bwd_apply_fused": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P,
+    "td_bn_bwd_reduce": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P, _P]),
+    "td_bn_bwd_apply_fused": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int64, _P, _P, _P, _P, _P, _P,
                                         _P, C.c_int64, C.c_int, _P]),
     "td_spectral_sigma": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_int, C.c_float, _P, _P, _P]),
     "td_scale_by_inv_sigma": (C.c_int, [_P, _P, C.c_int, _P]),

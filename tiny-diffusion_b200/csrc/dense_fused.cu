@@ -45,24 +45,21 @@ __device__ inline float tape_act(float v, int act) {
     }
 }
 
-// sense-reversing grid barrier (reusable across launches: `arrive` returns to 0, `gen` only grows)
-__device__ inline void grid_barrier(unsigned int* bar) {
+// Grid barrier on one monotonically growing 64-bit arrival counter (never reset, reusable across launches).  The k-th barrier
+// of a launch is passed when the counter reaches base + k * gridDim.x, base = the counter at kernel start rounded DOWN to a
+// multiple of gridDim.x (a CTA that starts late may already see arrivals of the first barrier, but fewer than gridDim.x of
+// them).  Arrival is a fire-and-forget reduction after a fence; only the wait is a round trip.
+__device__ inline void grid_barrier(unsigned long long* counter, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile unsigned int* gen = bar + 1;
-        const unsigned int g = *gen;
         __threadfence();
-        if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            unsigned int spins = 0;
-            while (*gen == g) {
-                if (++spins > (1u << 28)) { printf("tinydiff: dense tape grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
-            }
-        }
-        __threadfence();
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned long long seen;
+        unsigned int spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+            if (++spins > (1u << 28)) { printf("tinydiff: dense tape grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+        } while (seen < target);
     }
     __syncthreads();
 }
@@ -91,11 +88,17 @@ __device__ inline void stage_rows(float* dst, const float* __restrict__ src, lon
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1)
-dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned int* bar) {
+dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned long long* bar) {
     extern __shared__ __align__(16) float tp_smem[];
     float* const xs = tp_smem;                                   // [TP_RT][K + 4]
     td::pdl_sync();
     const int tid = threadIdx.x;
+    unsigned long long bar_target;
+    {
+        unsigned long long c;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(bar) : "memory");
+        bar_target = c / gridDim.x * gridDim.x;
+    }
     for (int oi = 0; oi < n_ops; ++oi) {
         const TapeOp op = ops[oi];
         if (op.kind == 0) {
@@ -116,7 +119,7 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned int
                 stage_rows(ws, op.w + (long long)n0 * op.K, op.K, TP_NT, min(TP_NT, op.N - n0), op.K, true);
                 w_staged = true;
             }
-            if (op.barrier_before) grid_barrier(bar);
+            if (op.barrier_before) { bar_target += gridDim.x; grid_barrier(bar, bar_target); }
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int rt = tile % row_tiles, ct = tile / row_tiles;
                 const int m0 = rt * TP_RT, n0 = ct * TP_NT;
@@ -163,7 +166,7 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned int
             }
             continue;
         }
-        if (op.barrier_before) grid_barrier(bar);
+        if (op.barrier_before) { bar_target += gridDim.x; grid_barrier(bar, bar_target); }
         if (op.kind == 1) {
             // ---- LayerNorm over N features: one warp per row, two-pass (mean, then centred variance) like ATen
             const int warp = tid >> 5, lane = tid & 31;
@@ -215,7 +218,7 @@ using namespace td;
 
 extern "C" int td_dense_tape_op_bytes(void) { return (int)sizeof(TapeOp); }
 
-extern "C" int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned int* barrier, int max_ctas, void* stream) {
+extern "C" int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned long long* barrier, int max_ctas, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(ops && n_ops > 0 && batch > 0 && barrier, "td_dense_tape_run: bad args");
     static bool configured = false;
@@ -223,9 +226,11 @@ extern "C" int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned
         TD_CUDA(cudaFuncSetAttribute(dense_tape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
         configured = true;
     }
-    // the grid barrier needs every CTA resident at once: never more CTAs than SMs (one small CTA per SM)
+    // the grid barrier needs every CTA resident at once: never more CTAs than SMs (one CTA per SM).  The grid size is part of the
+    // barrier arithmetic: keep it the same for every launch that shares `barrier`.
     int grid = std::min(kNumSMs - 20, 128);
     if (max_ctas > 0) grid = std::min(grid, max_ctas);
+    TD_CHECK_ARG((((uintptr_t)barrier) & 7) == 0, "td_dense_tape_run: barrier must be 8-byte aligned");
     td::launch(dense_tape_kernel, td::LaunchCfg(grid, TP_THREADS, TP_SMEM, (cudaStream_t)stream), reinterpret_cast<const TapeOp*>(ops), n_ops,
                batch, barrier);
     return launch_status("dense_tape");

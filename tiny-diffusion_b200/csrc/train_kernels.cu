@@ -270,6 +270,13 @@ bn_relu_bwd_apply_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, co
     }
 }
 
+// V consecutive values of the raw conv output y (fp32, or bf16 on the layers without large per-sample offsets) as floats
+template <int V> __device__ inline void load_y(const float* p, float* f) { load_f32<V>(p, f); }
+template <int V> __device__ inline void load_y(const __nv_bfloat16* p, float* f) {
+    static_assert(V == 8, "bf16 y is paired with bf16 activations (8-element vectors)");
+    Vec<__nv_bfloat16>::load(p).unpack(f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused BatchNorm passes: the finalize (sum of the partial rows -> per-channel coefficients) runs in the PROLOGUE of the
 // streaming kernel that consumes it, so a BatchNorm is conv -> apply (forward) and reduce -> apply (backward) with no
@@ -309,9 +316,9 @@ __device__ inline void slice_sum_partials(const float* __restrict__ partials, in
     }
 }
 
-template <typename T>
+template <typename T, typename Ty>
 __global__ void __launch_bounds__(kT)
-bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ partials, int nrows, double count,
+bn_apply_fused_kernel(const Ty* __restrict__ y, const float* __restrict__ partials, int nrows, double count,
                       const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ conv_bias,
                       float eps, float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                       int64_t* __restrict__ nbt, float* __restrict__ scale_out, float* __restrict__ shift_out,
@@ -376,7 +383,7 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
 #pragma unroll 4
     for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
         float f[V];
-        load_f32<V>(y + p * C + c0, f);
+        load_y<V>(y + p * C + c0, f);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             f[k] = fmaf(f[k] - mu[k], sc[k], sh[k]);
@@ -388,9 +395,9 @@ bn_apply_fused_kernel(const float* __restrict__ y, const float* __restrict__ par
 
 // BatchNorm backward partial sums, channel-sliced: s1 = sum g, s2 = sum g*(y-mean), g = da * [y*scale+shift > 0].
 // grid (chunks, C / 32); partials [chunks][2][C] (one row per pixel chunk).
-template <typename T>
+template <typename T, typename Ty>
 __global__ void __launch_bounds__(kT)
-bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y, int64_t P, int C,
+bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const Ty* __restrict__ y, int64_t P, int C,
                             const float* __restrict__ scale, const float* __restrict__ beta, const float* __restrict__ mean,
                             float* __restrict__ partials) {
     td::pdl_sync();
@@ -409,7 +416,7 @@ bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff,
     for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
         float f[V], yy[V];
         Vec<T>::load(da + p * ldda + da_coff + c0).unpack(f);
-        load_f32<V>(y + p * C + c0, yy);
+        load_y<V>(y + p * C + c0, yy);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const float d = yy[k] - mu[k];
@@ -435,9 +442,9 @@ bn_bwd_reduce_sliced_kernel(const T* __restrict__ da, int64_t ldda, int da_coff,
 
 // dy = scale*(g - mean(g) - xhat*mean(g*xhat)) = cA*g + cB*y + cC with the coefficients derived in the prologue from the
 // partial rows of bn_bwd_reduce_sliced_kernel (or of a data-gradient convolution's epilogue); chunk 0 writes dgamma / dbeta.
-template <typename T>
+template <typename T, typename Ty>
 __global__ void __launch_bounds__(kT)
-bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const float* __restrict__ y,
+bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, const Ty* __restrict__ y,
                           const float* __restrict__ partials, int nrows, double count, const float* __restrict__ scale,
                           const float* __restrict__ beta, const float* __restrict__ save_mean,
                           const float* __restrict__ save_invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -487,7 +494,7 @@ bn_bwd_apply_fused_kernel(const T* __restrict__ da, int64_t ldda, int da_coff, c
     for (int64_t p = p_lo + threadIdx.x / TPP; p < p_hi; p += PPP) {
         float g[V], yy[V];
         Vec<T>::load(da + p * ldda + da_coff + c0).unpack(g);
-        load_f32<V>(y + p * C + c0, yy);
+        load_y<V>(y + p * C + c0, yy);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const float d = yy[k] - mu[k];
@@ -956,7 +963,12 @@ extern "C" int td_bn_relu_bwd_apply(const void* da, int64_t ldda, int da_coff, c
     return launch_status("bn_relu_bwd_apply");
 }
 
-extern "C" int td_bn_apply_fused(const float* y, const float* partials, int nrows, int64_t count, const float* gamma,
+#define TD_DISPATCH_TY(dtype, y_dtype, ...)                                                               \
+    if ((y_dtype) == TD_F32) { using Ty = float; TD_DISPATCH_T(dtype, __VA_ARGS__) }                      \
+    else if ((y_dtype) == TD_BF16 && (dtype) == TD_BF16) { using Ty = __nv_bfloat16; using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { TD_CHECK_ARG(false, "bf16 y needs bf16 activations (dtype %d, y_dtype %d)", (int)(dtype), (int)(y_dtype)); }
+
+extern "C" int td_bn_apply_fused(const void* y, int y_dtype, const float* partials, int nrows, int64_t count, const float* gamma,
                                  const float* beta, const float* conv_bias, float eps, float momentum, float* running_mean,
                                  float* running_var, int64_t* num_batches_tracked, float* scale, float* shift,
                                  float* save_mean, float* save_invstd, void* a, int dtype, int64_t lda, int a_coff,
@@ -967,7 +979,7 @@ extern "C" int td_bn_apply_fused(const float* y, const float* partials, int nrow
     TD_CHECK_ARG(channels % kSlice == 0 && lda % 8 == 0 && a_coff % 8 == 0, "td_bn_apply_fused: channels must be a multiple of 32");
     const int ppp = dtype == TD_BF16 ? kT / 4 : kT / 8;
     const dim3 grid((unsigned)sliced_chunks(pixels, channels, ppp), (unsigned)(channels / kSlice));
-    TD_DISPATCH_T(dtype, (td::launch(bn_apply_fused_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), y, partials, nrows,
+    TD_DISPATCH_TY(dtype, y_dtype, (td::launch(bn_apply_fused_kernel<T, Ty>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const Ty*)y, partials, nrows,
                              (double)count, gamma, beta, conv_bias, eps, momentum, running_mean, running_var,
                              num_batches_tracked, scale, shift, save_mean, save_invstd, (T*)a, lda, a_coff, pixels, channels, relu)));
     return launch_status("bn_apply_fused");
@@ -978,7 +990,7 @@ extern "C" int td_bn_bwd_reduce_rows(int dtype, int64_t pixels, int channels) {
     return sliced_chunks(pixels, channels, dtype == TD_BF16 ? kT / 4 : kT / 8);
 }
 
-extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const float* y, int dtype, const float* scale,
+extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const void* y, int y_dtype, int dtype, const float* scale,
                                 const float* beta, const float* save_mean, int64_t pixels, int channels, float* partials,
                                 void* stream) {
     TD_REQUIRE_ARCH();
@@ -986,12 +998,12 @@ extern "C" int td_bn_bwd_reduce(const void* da, int64_t ldda, int da_coff, const
     TD_CHECK_ARG(da && y && scale && shift && save_mean && partials && pixels > 0, "td_bn_bwd_reduce: bad args");
     TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_reduce: channels must be a multiple of 32");
     const dim3 grid((unsigned)td_bn_bwd_reduce_rows(dtype, pixels, channels), (unsigned)(channels / kSlice));
-    TD_DISPATCH_T(dtype, (td::launch(bn_bwd_reduce_sliced_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
-                             ldda, da_coff, y, pixels, channels, scale, shift, save_mean, partials)));
+    TD_DISPATCH_TY(dtype, y_dtype, (td::launch(bn_bwd_reduce_sliced_kernel<T, Ty>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
+                             ldda, da_coff, (const Ty*)y, pixels, channels, scale, shift, save_mean, partials)));
     return launch_status("bn_bwd_reduce");
 }
 
-extern "C" int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const float* y, int dtype,
+extern "C" int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, const void* y, int y_dtype, int dtype,
                                      const float* partials, int nrows, int64_t count, const float* scale, const float* beta,
                                      const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, void* dy,
                                      int64_t pixels, int channels, void* stream) {
@@ -1002,8 +1014,8 @@ extern "C" int td_bn_bwd_apply_fused(const void* da, int64_t ldda, int da_coff, 
     TD_CHECK_ARG(channels % kSlice == 0 && ldda % 8 == 0 && da_coff % 8 == 0, "td_bn_bwd_apply_fused: channels must be a multiple of 32");
     const int ppp = dtype == TD_BF16 ? kT / 4 : kT / 8;
     const dim3 grid((unsigned)sliced_chunks(pixels, channels, ppp), (unsigned)(channels / kSlice));
-    TD_DISPATCH_T(dtype, (td::launch(bn_bwd_apply_fused_kernel<T>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
-                             ldda, da_coff, y, partials, nrows, (double)count, scale, shift, save_mean, save_invstd, dgamma,
+    TD_DISPATCH_TY(dtype, y_dtype, (td::launch(bn_bwd_apply_fused_kernel<T, Ty>, td::LaunchCfg(grid, kT, 0, (cudaStream_t)stream), (const T*)da,
+                             ldda, da_coff, (const Ty*)y, partials, nrows, (double)count, scale, shift, save_mean, save_invstd, dgamma,
                              dbeta, (T*)dy, pixels, channels)));
     return launch_status("bn_bwd_apply_fused");
 }

@@ -332,7 +332,7 @@ class DenseEngine:
             raw = b"".join(bytes(t) for t in tape)
             return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device), len(tape), sum(t.barrier_before for t in tape)
 
-        self._tape_bar = torch.zeros(2, device=self.device, dtype=torch.int32)
+        self._tape_bar = torch.zeros(1, device=self.device, dtype=torch.int64)
         self._tapes = {False: make(False), True: make(True)}
 
     def _launch_tape(self, st: int) -> None:

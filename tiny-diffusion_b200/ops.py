@@ -250,7 +250,7 @@ def bn_train_fwd(y, gamma, beta, conv_bias, running_mean, running_var, nbt, eps=
     scale, shift, mean, invstd = (torch.empty(Cc, device=y.device) for _ in range(4))
     if fused:
         a = torch.empty(y.shape, device=y.device, dtype=out_dtype)
-        L.check(lib.td_bn_apply_fused(y.data_ptr(), part.data_ptr(), rows, P, gamma.data_ptr(), beta.data_ptr(),
+        L.check(lib.td_bn_apply_fused(y.data_ptr(), L.TD_F32, part.data_ptr(), rows, P, gamma.data_ptr(), beta.data_ptr(),
                                       L.ptr(conv_bias), eps, momentum, L.ptr(running_mean), L.ptr(running_var), L.ptr(nbt),
                                       scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), a.data_ptr(),
                                       L.dtype_code(out_dtype), Cc, 0, P, Cc, int(relu), st), "td_bn_apply_fused")
@@ -276,11 +276,11 @@ def bn_train_bwd(da, y, scale, shift, mean, invstd, fused=False, beta=None):
         rows = int(lib.td_bn_bwd_reduce_rows(dt, P, Cc))
         part = torch.empty(rows * 2 * Cc + Cc, device=y.device)
         st = L.stream_ptr()
-        L.check(lib.td_bn_bwd_reduce(da.data_ptr(), Cc, 0, y.data_ptr(), dt, scale.data_ptr(), beta.data_ptr(),
+        L.check(lib.td_bn_bwd_reduce(da.data_ptr(), Cc, 0, y.data_ptr(), L.dtype_code(y.dtype), dt, scale.data_ptr(), beta.data_ptr(),
                                      mean.data_ptr(), P, Cc, part.data_ptr(), st), "td_bn_bwd_reduce")
         dgamma, dbeta = torch.empty(Cc, device=y.device), torch.empty(Cc, device=y.device)
         dy = torch.empty_like(da)
-        L.check(lib.td_bn_bwd_apply_fused(da.data_ptr(), Cc, 0, y.data_ptr(), dt, part.data_ptr(), rows, P, scale.data_ptr(),
+        L.check(lib.td_bn_bwd_apply_fused(da.data_ptr(), Cc, 0, y.data_ptr(), L.dtype_code(y.dtype), dt, part.data_ptr(), rows, P, scale.data_ptr(),
                                           beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), dgamma.data_ptr(),
                                           dbeta.data_ptr(), dy.data_ptr(), P, Cc, st), "td_bn_bwd_apply_fused")
         return dy, dgamma, dbeta

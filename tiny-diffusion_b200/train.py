@@ -97,9 +97,14 @@ class UNetTrainEngine:
             self.last = "d1r"
         self.bufs = {k: buf(h, c) for k, (h, c) in shapes.items()}          # activations
         self.grads = {k: buf(h, c) for k, (h, c) in shapes.items()}         # dL/d(activation)
-        # pre-BN conv outputs stay fp32: under the large per-sample time-embedding offsets a bf16 y loses
-        # the spatial signal before the normalisation (and flips ReLU masks in the backward)
-        self.yraw = {name: buf(size, cout, torch.float32) for name, _, _, size, _, cout in self.layers}
+        # Pre-BN conv outputs y.  The three layers that consume a decoder concat [up | skip + time embedding] stay fp32: under the
+        # per-sample embedding offsets (raw t <= 999) a bf16 y loses the spatial signal before the normalisation and flips ReLU
+        # masks in the backward.  Everywhere else y is O(1..10) with no such offsets and is stored in the activation dtype
+        # (bf16 on the tensor-core engine: what the reference's own conv output is under autocast); the batch statistics
+        # still come from the fp32 accumulators in the conv epilogue.  TD_Y_FP32=1 keeps every y in fp32.
+        all_fp32 = precision == "fp32" or os.environ.get("TD_Y_FP32", "0") != "0"
+        self.yraw = {name: buf(size, cout, torch.float32 if (all_fp32 or xin.startswith("cat")) else self.act)
+                     for name, xin, _, size, _, cout in self.layers}
         # dL/d(conv output), one buffer per layer: the weight gradients read them on a second stream while the main
         # stream has moved on to the next layers (151 MB at B = 128)
         self.dy = {name: buf(size, cout) for name, _, _, size, _, cout in self.layers}
@@ -304,13 +309,15 @@ class UNetTrainEngine:
             eps_, mom = float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1)
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
 
+            ydt = L.dtype_code(y.dtype)
+
             def bn_fwd(st):
                 nrows = fused_rows
                 if fused_rows == 0:
                     nrows = rows
                     L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
                 # finalize (partial rows -> scale / shift, running statistics) in the prologue of the apply + ReLU pass
-                L.check(lib.td_bn_apply_fused(yp, part, nrows, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, ap, adt,
+                L.check(lib.td_bn_apply_fused(yp, ydt, part, nrows, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, ap, adt,
                                               cout, 0, P, cout, 1, st), "td_bn_apply_fused")
             fwd.append((f"bn:{name}", bn_fwd))
 
@@ -389,14 +396,15 @@ class UNetTrainEngine:
             sc, sh, mu, iv = (st_[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
             coef = st_["coef"].data_ptr()
             bt = bn.bias.data_ptr()
+            ydt = L.dtype_code(y.dtype)
             blk, idx = name.split(".")
             dg = self.pgrad[f"{blk}.{int(idx) + 1}.weight"].data_ptr()
             db = self.pgrad[f"{blk}.{int(idx) + 1}.bias"].data_ptr()
 
             def bn_bwd(st):
-                L.check(lib.td_bn_bwd_reduce(dap, cout, 0, yp, adt, sc, bt, mu, P, cout, part, st), "td_bn_bwd_reduce")
+                L.check(lib.td_bn_bwd_reduce(dap, cout, 0, yp, ydt, adt, sc, bt, mu, P, cout, part, st), "td_bn_bwd_reduce")
                 # finalize (sum g, sum g*xhat -> dgamma / dbeta and the dy coefficients) in the prologue of the apply pass
-                L.check(lib.td_bn_bwd_apply_fused(dap, cout, 0, yp, adt, part, rows, P, sc, bt, mu, iv, dg, db, dyp, P, cout, st),
+                L.check(lib.td_bn_bwd_apply_fused(dap, cout, 0, yp, ydt, adt, part, rows, P, sc, bt, mu, iv, dg, db, dyp, P, cout, st),
                         "td_bn_bwd_apply_fused")
             bwd.append((f"bn:{name}:bwd", bn_bwd))
             eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
