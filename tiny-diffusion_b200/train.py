@@ -124,7 +124,8 @@ class UNetTrainEngine:
         self.bn: Dict[str, Dict[str, torch.Tensor]] = {}
         max_part = 1
         for name, _, _, size, _, cout in self.layers:
-            rows = int(self.lib.td_chan_reduce_rows(L.TD_F32, B * size * size, cout))
+            rows = max(int(self.lib.td_chan_reduce_rows(L.TD_F32, B * size * size, cout)),
+                       int(self.lib.td_chan_reduce_rows(self.adt, B * size * size, cout)))
             rows_b = int(self.lib.td_bn_bwd_reduce_rows(self.adt, B * size * size, cout))
             rows_fused = B * size * size // 32 + 2          # upper bound on the conv epilogue's partial rows (tiles)
             max_part = max(max_part, (max(rows, rows_b, rows_fused) * 2 + 1) * cout)
@@ -300,7 +301,7 @@ class UNetTrainEngine:
             p = conv_plan(name, cd, eng)
             fwd.append((name, p.run))
             st_ = self.bn[name]
-            rows, P = st_["rows"], B * size * size
+            rows, P = int(lib.td_chan_reduce_rows(L.dtype_code(y.dtype), B * size * size, cout)), B * size * size
             fused_rows = int(lib.td_conv3x3_stats_rows(p.handle))
             assert (fused_rows * 2 + 1) * cout <= self.partials.numel()
             yp, ap = y.data_ptr(), a.data_ptr()
@@ -315,7 +316,7 @@ class UNetTrainEngine:
                 nrows = fused_rows
                 if fused_rows == 0:
                     nrows = rows
-                    L.check(lib.td_bn_stats(yp, L.TD_F32, cout, 0, P, cout, part, 1, st), "td_bn_stats")
+                    L.check(lib.td_bn_stats(yp, ydt, cout, 0, P, cout, part, 1, st), "td_bn_stats")
                 # finalize (partial rows -> scale / shift, running statistics) in the prologue of the apply + ReLU pass
                 L.check(lib.td_bn_apply_fused(yp, ydt, part, nrows, P, g_, b_, cb, eps_, mom, rm, rv, nbt, sc, sh, mu, iv, ap, adt,
                                               cout, 0, P, cout, 1, st), "td_bn_apply_fused")
