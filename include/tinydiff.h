@@ -41,6 +41,10 @@ int td_device_check(int device);
 /* Programmatic dependent launch (every kernel's launch latency and on-chip prologue overlap the tail of the preceding kernel
  * of the stream; on by default, TD_PDL=0 in the environment turns it off).  Returns the previous setting. */
 int td_set_pdl(int on);
+/* SMs the one-CTA-per-SM kernels (persistent halo convolution, tcgen05 weight gradient) size their grids for; plans read it
+ * when they are created.  Default 148.  The data-parallel train step sets 148 - (NCCL CTAs) so that a grid never runs as
+ * 140 CTAs + a second wave of 8 while an all-reduce holds SMs.  Returns the previous value. */
+int td_set_sm_budget(int sms);
 /* Number of kernels this library has launched (or captured into a graph) in this process so far; bench.py reads the
  * difference over one eager step to report `gpu_launches`. */
 int64_t td_launch_count(void);

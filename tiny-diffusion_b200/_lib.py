@@ -65,6 +65,7 @@ _SIGS = {
     "td_last_error_string": (C.c_char_p, []),
     "td_device_check": (C.c_int, [C.c_int]),
     "td_set_pdl": (C.c_int, [C.c_int]),
+    "td_set_sm_budget": (C.c_int, [C.c_int]),
     "td_launch_count": (C.c_int64, []),
     "td_qsample": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
     "td_mse_num_partials": (C.c_int64, [C.c_int64]),

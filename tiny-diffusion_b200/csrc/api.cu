@@ -50,7 +50,16 @@ bool pdl_enabled() {
     return g_pdl != 0;
 }
 
+static int g_sm_budget = kNumSMs;
+int sm_budget() { return g_sm_budget; }
+
 }  // namespace td
+
+extern "C" int td_set_sm_budget(int sms) {
+    const int prev = td::g_sm_budget;
+    if (sms >= 16 && sms <= td::kNumSMs) td::g_sm_budget = sms;
+    return prev;
+}
 
 extern "C" int td_set_pdl(int on) {
     const int prev = td::pdl_enabled() ? 1 : 0;

@@ -48,6 +48,10 @@ inline int launch_status(const char* what) {
 }
 
 constexpr int kNumSMs = 148;
+// SMs the persistent / one-CTA-per-SM kernels size their grids for (td_set_sm_budget): fewer than kNumSMs when other work
+// holds SMs for the duration of a step -- NCCL's all-reduce CTAs in the data-parallel train step -- so that a 148-CTA grid
+// does not run as 140 + a second wave of 8.  Read when a PLAN is created and stored in it.
+int sm_budget();
 
 // ---- programmatic dependent launch ------------------------------------------------------------------------------------
 // Every kernel of the library is launched with the programmatic-stream-serialization attribute (unless TD_PDL=0) and runs

@@ -533,6 +533,7 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->block_n = n_tile;
     p->n_tiles = d.cout / n_tile;
     p->h_units = p->h_nsub * p->n_tiles;
+    p->h_grid = std::min(p->h_units, sm_budget());
     p->split_k = 1;
     const int box_bytes = g.PW * p->h_rh * g.BN * 128;
     p->h_slot_bytes = (box_bytes + 1023) / 1024 * 1024 + 1024;
@@ -580,7 +581,7 @@ static int launch_halo(const td_conv_plan* p, const HaloParams& prm, cudaStream_
         TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         configured_smem = p->smem_bytes;
     }
-    const int grid = std::min(p->h_units, kNumSMs);
+    const int grid = p->h_grid;
     td::launch(conv3x3_halo_kernel<N_TILE>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
     return launch_status("conv3x3_halo");
 }

@@ -22,6 +22,7 @@ struct td_conv_plan {
     int h_groups;           // 1: one box (w0 = -1) serves the 9 taps; 3: one box per dx
     int h_pw, h_bh, h_bn, h_rh;   // box = (64 channels, pw, rh = bh + 2, bn images); pw = smem pixels per image row
     int h_units, h_nsub, h_na, h_nb, h_slot_bytes;
+    int h_grid;             // CTAs of the persistent halo kernel = min(h_units, sm_budget() at plan creation)
     int h_strip;            // 1: 8-column strip subtiles (A descriptor group stride = h_pw * 128 bytes)
 };
 

@@ -469,7 +469,7 @@ extern "C" int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc
 
 extern "C" int td_conv3x3_stats_rows(const td_conv_plan* plan) {
     if (!plan || !plan->d.stats || plan->engine != TD_CONV_TC) return 0;
-    if (plan->halo) return std::min(plan->h_units, kNumSMs);          // one row per (persistent) CTA
+    if (plan->halo) return plan->h_grid;                              // one row per (persistent) CTA
     return plan->tiles_w * plan->tiles_h * plan->tiles_n;              // per-tap kernel: one row per M tile
 }
 

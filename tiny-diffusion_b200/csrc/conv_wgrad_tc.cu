@@ -278,7 +278,7 @@ static bool wg_geometry_halo(const td_wgrad_desc& d, WgGeom& g) {
     // one CTA per SM (the operand ring fills the shared memory): a single wave of <= 148 CTAs
     const int total_boxes = g.tiles_h * g.tiles_n;
     const int base = g.m_tiles * g.n_tiles * 3;
-    int splits = std::max(1, kNumSMs / base);
+    int splits = std::max(1, sm_budget() / base);
     if (const char* e = getenv("TD_WG_TARGET_CTAS")) { int v = atoi(e); if (v > 0) splits = std::max(1, v / base); }
     splits = std::max(1, std::min(splits, std::max(1, total_boxes / 2)));
     g.boxes_per_split = (int)ceil_div(total_boxes, splits);

@@ -45,17 +45,27 @@ def grad_ready_index(param_names: List[str], bwd_op_names: List[str]) -> List[in
     return out
 
 
-def plan_buckets(offsets: List[int], sizes: List[int], ready: List[int], cap_elems: int) -> List[Tuple[int, int, int]]:
+def plan_buckets(offsets: List[int], sizes: List[int], ready: List[int], cap_elems: int,
+                 tail_fraction: float = 0.85, tail_div: int = 4) -> List[Tuple[int, int, int]]:
     """Greedy contiguous buckets over the flat gradient buffer: (lo, hi, ready_index).  A bucket may
-    be all-reduced once the backward-plan entry ``ready_index`` has been enqueued."""
+    be all-reduced once the backward-plan entry ``ready_index`` has been enqueued.
+
+    Gradients that only become final in the last ``1 - tail_fraction`` of the backward plan (the first layers and the
+    conditioning head) go into buckets of ``cap_elems / tail_div``: the all-reduce of the LAST bucket cannot overlap anything
+    and the optimizer waits for it, so it should be small."""
     buckets: List[Tuple[int, int, int]] = []
+    late = tail_fraction * max([r for r in ready if r >= 0] or [0])
     lo, hi, rdy = None, None, -1
     for off, n, r in zip(offsets, sizes, ready):
+        if lo is not None and ((r >= late) != (rdy >= late)) and rdy >= 0 and r >= 0:
+            buckets.append((lo, hi, rdy))             # never mix late and early gradients in one bucket
+            lo = None
         if lo is None:
             lo, hi, rdy = off, off, -1
         hi = off + (n + 3) // 4 * 4
         rdy = max(rdy, r)
-        if hi - lo >= cap_elems:
+        cap = cap_elems // tail_div if rdy >= late else cap_elems
+        if hi - lo >= cap:
             buckets.append((lo, hi, rdy))
             lo = None
     if lo is not None:

@@ -751,7 +751,12 @@ class TrainStep:
             e.pgrad[k] = view
             self.offsets.append(off)
             off += (s + 3) // 4 * 4
+        # data parallel: NCCL's all-reduce CTAs hold SMs while the backward runs; size the one-CTA-per-SM grids for the rest
+        reserve = int(os.environ.get("TD_DP_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "8"))) if self.world > 1 else 0
+        prev_budget = self.lib.td_set_sm_budget(148 - reserve) if 0 < reserve <= 64 else None
         e._build()          # rebuild the plans against the flat gradient views
+        if prev_budget is not None:
+            self.lib.td_set_sm_budget(prev_budget)
         self.m = torch.zeros_like(self.flat_grad)
         self.v = torch.zeros_like(self.flat_grad)
         self.clip_partials = torch.zeros(int(self.lib.td_grad_clip_num_partials(self.flat_grad.numel())), device=dev)
