@@ -33,7 +33,8 @@ struct TapeOp {                  // mirrored by tinydiff/dense.py (ctypes)
 };
 
 constexpr int TP_THREADS = 256, TP_RT = 32, TP_NT = 16, TP_KMAX = 1024;
-constexpr int TP_SMEM = (TP_RT + TP_NT) * (TP_KMAX + 4) * 4;
+constexpr int TP_PAD = 8;
+constexpr int TP_SMEM = (TP_RT + TP_NT) * (TP_KMAX + TP_PAD) * 4;
 
 __device__ inline float tape_act(float v, int act) {
     switch (act) {
@@ -69,9 +70,9 @@ __device__ inline void cp_async16(float* smem_dst, const float* gsrc) {
 }
 __device__ inline void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// stage `rows` rows of `K` floats (row r at src + r*ld, rows >= valid are zero) into smem rows of stride K + 4
+// stage `rows` rows of `K` floats (row r at src + r*ld, rows >= valid are zero) into smem rows of stride K + TP_PAD
 __device__ inline void stage_rows(float* dst, const float* __restrict__ src, long long ld, int rows, int valid, int K, bool vec) {
-    const int stride = K + 4;
+    const int stride = K + TP_PAD;
     if (vec) {
         const int k4 = K >> 2;
         for (int e = threadIdx.x; e < rows * k4; e += TP_THREADS) {
@@ -90,7 +91,7 @@ __device__ inline void stage_rows(float* dst, const float* __restrict__ src, lon
 __global__ void __launch_bounds__(TP_THREADS, 1)
 dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned long long* bar) {
     extern __shared__ __align__(16) float tp_smem[];
-    float* const xs = tp_smem;                                   // [TP_RT][K + 4]
+    float* const xs = tp_smem;                                   // [TP_RT][K + TP_PAD]
     td::pdl_sync();
     const int tid = threadIdx.x;
     unsigned long long bar_target;
@@ -107,8 +108,8 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned lon
             // ops and is requested BEFORE the grid barrier.  thread = (row, features c and c + 8).
             const int row_tiles = (M + TP_RT - 1) / TP_RT, col_tiles = (op.N + TP_NT - 1) / TP_NT;
             const int n_tiles = row_tiles * col_tiles;
-            const int stride = op.K + 4;
-            float* const ws = xs + TP_RT * stride;               // [TP_NT][K + 4]
+            const int stride = op.K + TP_PAD;
+            float* const ws = xs + TP_RT * stride;               // [TP_NT][K + TP_PAD]
             const bool vecw = (op.K & 3) == 0 && ((uintptr_t)op.w & 15) == 0;
             const bool vecx = (op.K & 3) == 0 && ((uintptr_t)op.x & 15) == 0 && (op.ldx & 3) == 0;
             const int r = tid >> 3, c = tid & 7;
@@ -131,27 +132,61 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned lon
                 stage_rows(xs, op.x + (long long)m0 * op.ldx, op.ldx, TP_RT, min(TP_RT, M - m0), op.K, vecx);
                 cp_async_wait_all();
                 __syncthreads();
-                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;     // two partial sums per output: shorter dependent FMA chains
-                const float* xr = xs + r * stride;
-                const float* w0 = ws + c * stride;
-                const float* w1 = ws + (c + 8) * stride;
-                int k = 0;
-                for (; k + 4 <= op.K; k += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(xr + k);
-                    const float4 u = *reinterpret_cast<const float4*>(w0 + k);
-                    const float4 v = *reinterpret_cast<const float4*>(w1 + k);
-                    a0 = fmaf(xv.x, u.x, a0); b0 = fmaf(xv.y, u.y, b0); a0 = fmaf(xv.z, u.z, a0); b0 = fmaf(xv.w, u.w, b0);
-                    a1 = fmaf(xv.x, v.x, a1); b1 = fmaf(xv.y, v.y, b1); a1 = fmaf(xv.z, v.z, a1); b1 = fmaf(xv.w, v.w, b1);
+                // 16 k-slices x (4 row groups x 4 column groups): a thread owns an 8 x 4 register tile over its slice of K (k = 4*ks +
+                // 64*j), so one 16-byte shared-memory read feeds 8-16 FMAs (a thread per output pair re-read both operands for
+                // every FMA pair and the loop was shared-memory-bandwidth bound: 12 k cycles per 512-deep tile).  Rows tr + 4i and
+                // columns tc + 4j are interleaved and the row stride is K + 8 floats: conflict-free for the two slices of a warp.
+                const int ks = tid >> 4, tr = (tid >> 2) & 3, tc = tid & 3;
+                float acc[8][4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+                if ((op.K & 3) == 0) {
+                    for (int k = ks * 4; k < op.K; k += 64) {
+                        float4 wv[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(ws + (tc + 4 * j) * stride + k);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 xv = *reinterpret_cast<const float4*>(xs + (tr + 4 * i) * stride + k);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[i][j] = fmaf(xv.x, wv[j].x, acc[i][j]);
+                                acc[i][j] = fmaf(xv.y, wv[j].y, acc[i][j]);
+                                acc[i][j] = fmaf(xv.z, wv[j].z, acc[i][j]);
+                                acc[i][j] = fmaf(xv.w, wv[j].w, acc[i][j]);
+                            }
+                        }
+                    }
+                } else {
+                    for (int k = ks; k < op.K; k += 16) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float xv = xs[(tr + 4 * i) * stride + k];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv, ws[(tc + 4 * j) * stride + k], acc[i][j]);
+                        }
+                    }
                 }
-                for (; k < op.K; ++k) { a0 = fmaf(xr[k], w0[k], a0); a1 = fmaf(xr[k], w1[k], a1); }
+                // fixed-order sum of the 16 k-slices through shared memory (the operand tiles are dead by now)
+                __syncthreads();
+                float* red = xs;                                   // [16 slices][512 outputs]
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) red[ks * 512 + (tr + 4 * i) * TP_NT + tc + 4 * j] = acc[i][j];
+                __syncthreads();
                 const int m = m0 + r;
                 if (m < M) {
-                    const float acc[2] = {a0 + b0, a1 + b1};
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
-                        const int n = n0 + c + 8 * j;
+                        const int cl = c + 8 * j, n = n0 + cl;
                         if (n >= op.N) continue;
-                        float v = acc[j] + (op.bias ? __ldg(op.bias + n) : 0.f);
+                        float v = 0.f;
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v += red[q * 512 + r * TP_NT + cl];
+                        v += op.bias ? __ldg(op.bias + n) : 0.f;
                         if (op.bn_mean) {         // eval-mode BatchNorm1d (+ ReLU): (x - mean) * invstd * gamma + beta
                             const float invstd = 1.f / sqrtf(__ldg(op.bn_var + n) + op.bn_eps);
                             v = (v - __ldg(op.bn_mean + n)) * invstd * __ldg(op.bn_gamma + n) + __ldg(op.bn_beta + n);
