@@ -742,116 +742,6 @@ maxpool2_bwd_window_kernel(const T* __restrict__ x, const T* __restrict__ dy, T*
 // one CTA per row, at most 256 threads looping over the row (several CTAs resident per SM)
 static inline int row_threads(int64_t items) { return (int)std::min<int64_t>(256, (items + 31) / 32 * 32); }
 
-// Transposed resize, whole-image form (default where the image slice fits in shared memory): one CTA per (image, slice of
-// 4 channel vectors).  The slice of dy -- every output pixel, 64 contiguous bytes each -- is staged in shared memory ONCE with
-// asynchronous copies (all loads of the CTA in flight together), then one thread per (input pixel, channel vector) sums
-//   dx[hi, wi] = sum_a wh[a] * ( sum_k ww[k] * dy[oh + a, ow + k] )
-// out of the staged slice in a fixed order, with the tap tables (bil_transpose) built once per CTA.  The row walker above
-// re-reads every output row for each of the ~2 input rows it feeds (an L2-bound 2x) and serialises a thread's loads along the
-// row.  With `dtemb` the per-channel sum over the image (the embedding gradient of the skip half, td_upcat_bwd) comes out of
-// the same pass in a fixed order.
-__device__ inline void cp_async16_g2s(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kT)
-resize_bwd_image_kernel(const T* __restrict__ dy, int64_t ld, int coff, T* __restrict__ dx, int Hi, int Wi, int Ho, int Wo, int C,
-                        float* __restrict__ dtemb, int ld_temb, int temb_off) {
-    td::pdl_sync();
-    constexpr int V = Vec<T>::N;
-    constexpr int CS = 4 * V;                                    // channels per CTA: 4 vectors = 64 B (bf16) / 64 B (fp32: V = 4)
-    extern __shared__ __align__(16) uint8_t img_raw[];
-    T* stage = reinterpret_cast<T*>(img_raw);                    // [Ho*Wo][CS]
-    __shared__ BilT rowT[kMaxRowW], colT[kMaxRowW];
-    __shared__ float tsum[kT / 4][CS + 1];
-    const int b = blockIdx.x, c0 = blockIdx.y * CS;
-    const int cvn = min(4, (C - c0) / V);                        // live channel vectors of this slice
-    const T* src = dy + (int64_t)b * Ho * Wo * ld + coff + c0;
-    for (int e = threadIdx.x; e < Ho * Wo * 4; e += kT) {
-        const int px = e >> 2, cv = e & 3;
-        if (cv < cvn) cp_async16_g2s(stage + (int64_t)px * CS + cv * V, src + (int64_t)px * ld + cv * V);
-    }
-    for (int i = threadIdx.x; i < Hi + Wi; i += kT) {
-        if (i < Hi) rowT[i] = bil_transpose(i, Hi, Ho);
-        else colT[i - Hi] = bil_transpose(i - Hi, Wi, Wo);
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    const int cv = threadIdx.x & 3;
-    float tot[V];
-#pragma unroll
-    for (int k = 0; k < V; ++k) tot[k] = 0.f;
-    T* xb = dx + (int64_t)b * Hi * Wi * C + c0 + cv * V;
-    for (int px = threadIdx.x >> 2; px < Hi * Wi; px += kT / 4) {
-        const int hi = px / Wi, wi = px - hi * Wi;
-        const int hn = rowT[hi].n, wn = colT[wi].n;
-        const T* sp = stage + ((int64_t)rowT[hi].o_lo * Wo + colT[wi].o_lo) * CS + cv * V;
-        float acc[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] = 0.f;
-        for (int a = 0; a < hn; ++a) {
-            float rowsum[V];
-#pragma unroll
-            for (int k = 0; k < V; ++k) rowsum[k] = 0.f;
-            for (int q = 0; q < wn; ++q) {
-                float f[V];
-                Vec<T>::load(sp + ((int64_t)a * Wo + q) * CS).unpack(f);
-                const float wq = colT[wi].w[q];
-#pragma unroll
-                for (int k = 0; k < V; ++k) rowsum[k] = fmaf(wq, f[k], rowsum[k]);
-            }
-            const float wa = rowT[hi].w[a];
-#pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] = fmaf(wa, rowsum[k], acc[k]);
-        }
-        if (cv < cvn) {
-            const Vec<T> packed = Vec<T>::pack(acc);
-            packed.store(xb + (int64_t)px * C);
-            if (dtemb) {                                         // the sum of the STORED (rounded) gradient, as the separate pass summed it
-                float rr[V];
-                packed.unpack(rr);
-#pragma unroll
-                for (int k = 0; k < V; ++k) tot[k] += rr[k];
-            }
-        }
-    }
-    if (dtemb) {
-#pragma unroll
-        for (int k = 0; k < V; ++k) tsum[threadIdx.x >> 2][cv * V + k] = tot[k];
-        __syncthreads();
-        if (threadIdx.x < cvn * V) {
-            float t = 0.f;
-            for (int r = 0; r < kT / 4; ++r) t += tsum[r][threadIdx.x];
-            dtemb[(int64_t)b * ld_temb + temb_off + c0 + threadIdx.x] = t;
-        }
-    }
-}
-
-// true when the whole-image kernel applies: the tables fit and the staged slice (Ho*Wo pixels x 64 bytes) fits in shared memory
-template <typename T>
-static bool image_form_ok(int Hi, int Wi, int Ho, int Wo, int C) {
-    constexpr int V = Vec<T>::N;
-    return !(Hi == Ho && Wi == Wo) && Hi <= kMaxRowW && Wi <= kMaxRowW && C % V == 0 &&
-           (size_t)Ho * Wo * 4 * V * sizeof(T) <= 96 * 1024 && getenv("TD_RESIZE_BWD_WALK") == nullptr;
-}
-
-template <typename T>
-static int launch_resize_bwd_image(const void* dy, int64_t ld, int coff, void* dx, int B, int Hi, int Wi, int Ho, int Wo, int C,
-                                   float* dtemb, int ld_temb, int temb_off, cudaStream_t s) {
-    constexpr int V = Vec<T>::N;
-    const size_t smem = (size_t)Ho * Wo * 4 * V * sizeof(T);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && configured < 96 * 1024) {
-        TD_CUDA(cudaFuncSetAttribute(resize_bwd_image_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = 96 * 1024;
-    }
-    const dim3 grd((unsigned)B, (unsigned)ceil_div(C, 4 * V));
-    td::launch(resize_bwd_image_kernel<T>, td::LaunchCfg(grd, kT, smem, s), (const T*)dy, ld, coff, (T*)dx, Hi, Wi, Ho, Wo, C, dtemb,
-               ld_temb, temb_off);
-    return TD_OK;
-}
-
 // block (channel vectors, rows) for the row-walking kernels: up to 32 channel vectors wide, 256 threads
 static inline dim3 walk_block(int cv) {
     int bx = 1;
@@ -1154,11 +1044,7 @@ extern "C" int td_resize_bilinear_bwd(const void* dy, int64_t ld_dy, int dy_coff
     const int V = dtype == TD_BF16 ? 8 : 4;
     TD_CHECK_ARG(c % V == 0 && ld_dy % V == 0 && dy_coff % V == 0, "td_resize_bilinear_bwd: channels must be a multiple of %d", V);
     TD_CHECK_ARG(wo <= kMaxRowW, "td_resize_bilinear_bwd: output rows wider than %d", kMaxRowW);
-    TD_DISPATCH_T(dtype, {
-        if (image_form_ok<T>(hi, wi, ho, wo, c)) {
-            if (int st = launch_resize_bwd_image<T>(dy, ld_dy, dy_coff, dx, batch, hi, wi, ho, wo, c, nullptr, 0, 0, (cudaStream_t)stream)) return st;
-        } else if (int st = launch_resize_bwd<T>(dy, ld_dy, dy_coff, dx, batch, hi, wi, ho, wo, c, (cudaStream_t)stream)) return st;
-    });
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dy, ld_dy, dy_coff, dx, batch, hi, wi, ho, wo, c, (cudaStream_t)stream)) return st; });
     return launch_status("resize_bilinear_bwd");
 }
 
@@ -1173,17 +1059,9 @@ extern "C" int td_upcat_bwd(const void* dout, void* dlow, void* dskip, float* dt
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ld = cu + cs;
     TD_CHECK_ARG(wo <= kMaxRowW, "td_upcat_bwd: output rows wider than %d", kMaxRowW);
-    bool temb_done = false;
-    TD_DISPATCH_T(dtype, {
-        if (image_form_ok<T>(ho / 2, wo / 2, ho, wo, cu)) {
-            if (int st = launch_resize_bwd_image<T>(dout, ld, 0, dlow, batch, ho / 2, wo / 2, ho, wo, cu, nullptr, 0, 0, s)) return st;
-        } else if (int st = launch_resize_bwd<T>(dout, ld, 0, dlow, batch, ho / 2, wo / 2, ho, wo, cu, s)) return st;
-        if (image_form_ok<T>(hs, ws, ho, wo, cs)) {
-            if (int st = launch_resize_bwd_image<T>(dout, ld, cu, dskip, batch, hs, ws, ho, wo, cs, dtemb, ld_temb, temb_off, s)) return st;
-            temb_done = true;
-        } else if (int st = launch_resize_bwd<T>(dout, ld, cu, dskip, batch, hs, ws, ho, wo, cs, s)) return st;
-    });
-    if (!temb_done) {
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dout, ld, 0, dlow, batch, ho / 2, wo / 2, ho, wo, cu, s)) return st; });
+    TD_DISPATCH_T(dtype, { if (int st = launch_resize_bwd<T>(dout, ld, cu, dskip, batch, hs, ws, ho, wo, cs, s)) return st; });
+    {
         const dim3 grd((unsigned)batch, (unsigned)ceil_div(cs / V, 8), 1);
         // bilinear weights sum to one per output pixel, so the transposed resize preserves the per-channel total:
         // sum over the output pixels of d_out == sum over the input pixels of d_skip -- read the smaller, dense tensor
