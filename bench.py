@@ -329,6 +329,10 @@ def run_gpu(args):
     }
     value = world * B * args.steps / (dev_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    dit_dp = None
+    if world > 1 and not args.no_configs:
+        # BASELINE config 3: the DiT train step, data parallel over the ranks (bucketed NCCL all-reduce inside the captured step)
+        dit_dp = dit_data_parallel(dev, world, dist, ts)
 
     line = None
     if rank == 0:
@@ -356,6 +360,8 @@ def run_gpu(args):
             "achieved_model_tflops": value * eng.conv_flops() / B * T_STEPS / 1e12 / world,
             "train": train,
         }
+        if dit_dp is not None:
+            line["configs"] = dit_dp
         train["roofline_frac_of_sustained_bf16"] = train["achieved_model_tflops"] / peaks["bf16_sustained"]
         if world == 1:
             train["roofline"] = train_roofline(ts, peaks, train_ms / n_train)
@@ -591,6 +597,43 @@ def gpu_eager_baseline(dev, B, reverse_steps=10, train_steps=10):
                      "train_step_ms": tr_ms, "train_imgs_per_sec": B / (tr_ms * 1e-3)}
         del leaf, opt
     torch.backends.cudnn.benchmark = False
+    return out
+
+
+def dit_data_parallel(dev, world, dist, prev_ts):
+    """BASELINE config 3 under data parallelism: fused DiT train step (one graph per rank, NCCL all-reduce of the 13 MB of
+    gradients inside it) at the reference batch and at 4096 per GPU; max over ranks, whole-job samples/s."""
+    from tinydiff.diffusion_transformer import ForwardProcess, NoiseModel
+    from tinydiff.train import TrainStep
+    prev_ts.close()
+    out = []
+    for Bn in (128, 4096):
+        torch.manual_seed(0)
+        model = NoiseModel(dropout=0.0).to(dev).train()
+        fp = ForwardProcess()
+        g = torch.Generator().manual_seed(1)
+        x0 = torch.randn(Bn, 20, generator=g).to(dev)
+        y = torch.randint(0, 10, (Bn,), generator=g).to(dev)
+        ts = TrainStep(model, fp, Bn, dev, lr=3e-4, use_graph=True)
+        ts.load(x0, y)
+        for _ in range(3):
+            ts.run()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ts.run()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        out.append({"config": 3, "model": "diffusion_transformer", "batch_per_gpu": Bn, "n_gpus": world,
+                    "train": {"ms_per_step": ms, "samples_per_sec": world * Bn / ms * 1e3, "buckets": len(ts.buckets)}})
+        ts.close()
+        del ts, model
     return out
 
 
