@@ -195,9 +195,8 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = L.require_device(f"cuda:{local_rank}")
     if world > 1:
-        # Every NCCL CTA takes a whole SM away from the persistent tcgen05 kernels (one CTA per SM, grids of 148) for as long as
-        # an all-reduce runs, so the data-parallel train step wants few channels: 44.7 MB per step is ~0.1 ms of NVLink time.
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # NCCL keeps its default channel count: capping it at 8 CTAs and sizing the persistent grids for the remaining 140 SMs
+        # measured SLOWER on 8 GPUs (2.30 vs 2.24 ms per data-parallel step; profiles/r02_dp_settings.txt)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():

@@ -751,8 +751,10 @@ class TrainStep:
             e.pgrad[k] = view
             self.offsets.append(off)
             off += (s + 3) // 4 * 4
-        # data parallel: NCCL's all-reduce CTAs hold SMs while the backward runs; size the one-CTA-per-SM grids for the rest
-        reserve = int(os.environ.get("TD_DP_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "8"))) if self.world > 1 else 0
+        # data parallel: NCCL's all-reduce CTAs hold SMs while the backward runs; TD_DP_SM_RESERVE=n sizes the one-CTA-per-SM
+        # grids for 148 - n SMs.  Off by default: with NCCL capped at 8 CTAs and n = 8 the 8-GPU step measured 2.30 ms against
+        # 2.24 ms with NCCL's defaults and full grids (profiles/r02_dp_settings.txt).
+        reserve = int(os.environ.get("TD_DP_SM_RESERVE", "0")) if self.world > 1 else 0
         prev_budget = self.lib.td_set_sm_budget(148 - reserve) if 0 < reserve <= 64 else None
         e._build()          # rebuild the plans against the flat gradient views
         if prev_budget is not None:
