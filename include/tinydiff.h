@@ -403,15 +403,19 @@ int td_transpose_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int
  * Applying the same call to a gradient is the backward. */
 int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t ldo, int rows, int cols, int group, float p,
                    const uint64_t* seed_ptr, void* stream);
-/* table_grad[c,:] = sum_{i: idx[i]==c} g[i,:]   (nn.Embedding backward, conditional_diffusion.py:31) */
+/* table_grad[c,:] = sum_{i: idx[i]==c} g[i,:]   (nn.Embedding backward, conditional_diffusion.py:31).  With a workspace
+ * (>= 2*num_rows*D floats; more = more row chunks, up to 296) and M >= 4096 the rows are split over many CTAs (table-shaped
+ * partial sums, fixed-order finalize); workspace NULL: one CTA per table row. */
 int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx, float* table_grad, int M, int D, int num_rows,
-                     int accumulate, void* stream);
+                     int accumulate, float* workspace, int64_t workspace_floats, void* stream);
 /* out[b, :] = t (mode 0), t/1000 (mode 1) [width 1] or the sinusoidal embedding [width dim] (mode 2) */
 int td_time_features(const int64_t* t, const int32_t* t_dev, float* out, int batch, int dim, int mode, void* stream);
 int td_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int M,
                      int D, float eps, void* stream);
+/* workspace (optional, >= 4*D floats; M >= 4096): dgamma / dbeta from many-CTA partial sums + fixed-order finalize */
 int td_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
-                     float* dx, float* dgamma, float* dbeta, int M, int D, void* stream);
+                     float* dx, float* dgamma, float* dbeta, int M, int D, float* workspace, int64_t workspace_floats,
+                     void* stream);
 int td_bn1d_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float* running_mean,
                 float* running_var, float* save_mean, float* save_rstd, float* y, int64_t ldy, int M, int N, float eps,
                 float momentum, int training, int relu, void* stream);

@@ -216,7 +216,7 @@ def test_vae_edges(dev, golden):
     assert x.shape == (3, 1, 28, 28) and float(x.min()) >= 0 and float(x.max()) <= 1
 
 
-@pytest.mark.parametrize("M,D", [(8, 256), (37, 20), (128, 1024)])
+@pytest.mark.parametrize("M,D", [(8, 256), (37, 20), (128, 1024), (8192, 256)])
 def test_layernorm_kernels(dev, M, D):
     import ctypes as C
     from tinydiff import _lib as L
@@ -235,9 +235,28 @@ def test_layernorm_kernels(dev, M, D):
                                  rstd.data_ptr(), M, D, 1e-5, st))
     assert rel(y, yr) < 1e-5
     dx, dg, db = torch.empty_like(xd), torch.empty(D, device=dev), torch.empty(D, device=dev)
+    ws = torch.empty(2 * D * 64, device=dev) if M >= 4096 else None         # many-CTA parameter gradients at large batch
     L.check(lib.td_layernorm_bwd(dyd.data_ptr(), xd.data_ptr(), gd.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                 dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, st))
+                                 dx.data_ptr(), dg.data_ptr(), db.data_ptr(), M, D, L.ptr(ws), ws.numel() if ws is not None else 0, st))
     assert rel(dx, xr.grad) < 1e-5 and rel(dg, gr.grad) < 1e-5 and rel(db, br.grad) < 1e-5
+
+
+@pytest.mark.parametrize("M,rows,use_ws", [(100, 10, False), (8192, 10, True), (5000, 1, True)])
+def test_embedding_bwd(dev, M, rows, use_ws):
+    """nn.Embedding backward: one CTA per table row, and the many-CTA chunked form (workspace) at large batch."""
+    from tinydiff import _lib as L
+    lib = L.load()
+    D = 256
+    g = torch.Generator().manual_seed(M + rows)
+    grad = torch.randn(M, D, generator=g)
+    idx = torch.randint(0, rows, (M,), generator=g)
+    want = torch.zeros(rows, D).index_add_(0, idx, grad)
+    gd, idd = grad.to(dev), idx.to(dev)
+    out = torch.full((rows, D), float("nan"), device=dev)
+    ws = torch.empty(64 * rows * D, device=dev) if use_ws else None
+    L.check(lib.td_embedding_bwd(gd.data_ptr(), D, idd.data_ptr(), out.data_ptr(), M, D, rows, 0, L.ptr(ws),
+                                 ws.numel() if ws is not None else 0, L.stream_ptr()))
+    assert rel(out, want) < 1e-5
 
 
 @pytest.mark.parametrize("M,N,relu", [(8, 64, True), (128, 512, True), (37, 100, False)])
@@ -401,3 +420,35 @@ def test_weight_gradient_gemm_takes_tensor_core_path(dev):
     assert lib.td_gemm_f32_path(C.byref(a)) == 1
     L.check(lib.td_gemm_f32(C.byref(a), L.stream_ptr()), "td_gemm_f32")
     assert rel(out, g.double().t() @ x.double()) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 16384), (1024, 256, 65536), (64, 512, 8192)])
+def test_gemm_tf32_splitk(dev, M, N, K):
+    """The tcgen05 kind::tf32 GEMM with K slices (the batch-reducing weight gradients of the dense denoisers at large batch):
+    C = A B^T with both operands K-major, raw partials + fixed-order second pass; tf32 tolerance, bit-reproducible."""
+    import ctypes as C
+    from tinydiff import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(K)
+    A = torch.randn(M, K, generator=g)
+    Bm = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    want = A.double() @ Bm.double().t() + bias.double()
+    Ad, Bd, bd = A.to(dev), Bm.to(dev), bias.to(dev)
+    need = int(lib.td_gemm_f32_workspace(M, N, K))
+    assert need >= 2 * M * N
+    ws = torch.empty(need, device=dev)
+    outs = []
+    for _ in range(2):
+        out = torch.empty(M, N, device=dev)
+        ga = L.GemmArgs()
+        ga.M, ga.N, ga.K, ga.alpha = M, N, K, 1.0
+        ga.A, ga.a_rs, ga.a_cs = Ad.data_ptr(), K, 1
+        ga.B, ga.b_rs, ga.b_cs = Bd.data_ptr(), 1, K
+        ga.C, ga.ldc, ga.bias = out.data_ptr(), N, bd.data_ptr()
+        ga.splitk_ws, ga.allow_tf32 = ws.data_ptr(), 1
+        assert int(lib.td_gemm_f32_path(C.byref(ga))) == 1
+        L.check(lib.td_gemm_f32(C.byref(ga), L.stream_ptr()), "td_gemm_f32")
+        outs.append(out)
+    assert rel(outs[0], want) < 2e-3
+    assert torch.equal(outs[0], outs[1])

@@ -142,10 +142,10 @@ _SIGS = {
     "td_add2d_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "td_transpose_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "td_dropout_f32": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
-    "td_embedding_bwd": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "td_embedding_bwd": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "td_time_features": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "td_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P]),
-    "td_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "td_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "td_bn1d_fwd": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_float,
                               C.c_float, C.c_int, C.c_int, _P]),
     "td_bn1d_bwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_int,

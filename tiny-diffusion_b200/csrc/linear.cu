@@ -9,7 +9,8 @@
 
 namespace td {
 
-bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status);   // linear_tc.cu
+bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status, int* nz_out);   // linear_tc.cu
+int gemm_tf32_splits(int M, int N, int K);                                             // linear_tc.cu
 
 constexpr int G_BM = 64, G_BN = 64, G_BK = 16, G_THREADS = 256;
 
@@ -298,6 +299,45 @@ embedding_bwd_kernel(const float* __restrict__ g, int64_t ldg, const int64_t* __
     }
 }
 
+// Large batches: the kernel above walks all M rows with one CTA per table row (10 CTAs, or ONE for the single-row positional
+// table).  Here grid.x row chunks accumulate table-shaped partial sums in shared memory -- thread j owns column j, so the order
+// inside a chunk is the row order and there are no conflicts --, written to partials[chunk][num_rows][D]; the second kernel sums
+// the chunks in fixed order.  Deterministic.
+__global__ void __launch_bounds__(256)
+embedding_bwd_partial_kernel(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ idx, float* __restrict__ partials,
+                             int M, int D, int num_rows) {
+    td::pdl_sync();
+    extern __shared__ float acc[];                   // [num_rows][D]
+    for (int e = threadIdx.x; e < num_rows * D; e += blockDim.x) acc[e] = 0.f;
+    __syncthreads();
+    const int i0 = (int)((int64_t)M * blockIdx.x / gridDim.x), i1 = (int)((int64_t)M * (blockIdx.x + 1) / gridDim.x);
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+#pragma unroll 4
+        for (int i = i0; i < i1; ++i) {
+            const int c = (int)idx[i];
+            if (c >= 0 && c < num_rows) acc[c * D + j] += g[(int64_t)i * ldg + j];
+        }
+    }
+    __syncthreads();
+    float* out = partials + (int64_t)blockIdx.x * num_rows * D;
+    for (int e = threadIdx.x; e < num_rows * D; e += blockDim.x) out[e] = acc[e];
+}
+__global__ void __launch_bounds__(256)
+embedding_bwd_finalize_kernel(const float* __restrict__ partials, int chunks, int n, float* __restrict__ out, int accumulate) {
+    td::pdl_sync();
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= chunks; k += 4) {
+        s0 += partials[(int64_t)k * n + e]; s1 += partials[(int64_t)(k + 1) * n + e];
+        s2 += partials[(int64_t)(k + 2) * n + e]; s3 += partials[(int64_t)(k + 3) * n + e];
+    }
+    for (; k < chunks; ++k) s0 += partials[(int64_t)k * n + e];
+    const float s = (s0 + s1) + (s2 + s3);
+    out[e] = accumulate ? out[e] + s : s;
+}
+
 // First layer input of the conditioning head: raw t, t/1000, or the sinusoidal embedding
 // (conditional_diffusion_laion.py:223-232: [sin | cos], divisor half-1).
 __global__ void __launch_bounds__(256)
@@ -398,6 +438,36 @@ layernorm_bwd_params_kernel(const float* __restrict__ dy, const float* __restric
 #pragma unroll
         for (int k = 0; k < 8; ++k) { a += pg[k][lane]; b += pb[k][lane]; }
         dgamma[j] = a; dbeta[j] = b;
+    }
+}
+
+// Large batches: grid (D / 32, row chunks) partial sums in the [chunk][2][D] layout of the BatchNorm partials (td_partial_sum
+// sums the chunks in fixed order): the kernel above is one CTA per 32 columns walking all M rows (8 CTAs for D = 256).
+__global__ void __launch_bounds__(256)
+layernorm_bwd_params_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, float* __restrict__ partials, int M, int D) {
+    td::pdl_sync();
+    __shared__ float pg[8][33], pb[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    const int i0 = (int)((int64_t)M * blockIdx.y / gridDim.y), i1 = (int)((int64_t)M * (blockIdx.y + 1) / gridDim.y);
+    float sg = 0.f, sb = 0.f;
+    if (j < D) {
+#pragma unroll 4
+        for (int i = i0 + w; i < i1; i += 8) {
+            const float g = dy[(int64_t)i * D + j];
+            sg += g * (x[(int64_t)i * D + j] - mean[i]) * rstd[i];
+            sb += g;
+        }
+    }
+    pg[w][lane] = sg; pb[w][lane] = sb;
+    __syncthreads();
+    if (w == 0 && j < D) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a += pg[k][lane]; b += pb[k][lane]; }
+        partials[((int64_t)blockIdx.y * 2 + 0) * D + j] = a;
+        partials[((int64_t)blockIdx.y * 2 + 1) * D + j] = b;
     }
 }
 
@@ -582,7 +652,8 @@ extern "C" int64_t td_gemm_f32_workspace(int M, int N, int K) {
     const int64_t tiles = ceil_div(M, G_BM) * ceil_div(N, G_BN);
     int nz = 1;
     if (tiles < kNumSMs && K >= 1024) nz = (int)std::min<int64_t>(std::min<int64_t>(kNumSMs / tiles, K / 256), 64);
-    return nz > 1 ? (int64_t)nz * M * N : 0;
+    const int nt = td::gemm_tf32_splits(M, N, K);            // the tcgen05 path's own split (linear_tc.cu)
+    return std::max<int64_t>(nz > 1 ? (int64_t)nz * M * N : 0, nt > 1 ? (int64_t)nt * M * N : 0);
 }
 
 extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
@@ -592,12 +663,19 @@ extern "C" int td_gemm_f32(const td_gemm_args* a, void* stream) {
     TD_CHECK_ARG(a->act >= 0 && a->act <= TD_ACT_SIGMOID, "td_gemm_f32: bad activation %d", a->act);
     cudaStream_t s = (cudaStream_t)stream;
     {
-        int st = TD_OK;
-        if (td::gemm_tf32_try(a, s, &st)) return st;       // large batches, K-major operands: tcgen05 kind::tf32 (linear_tc.cu)
+        int st = TD_OK, nzt = 1;
+        if (td::gemm_tf32_try(a, s, &st, &nzt)) {          // large batches, K-major operands: tcgen05 kind::tf32 (linear_tc.cu)
+            if (st != TD_OK || nzt == 1) return st;
+            td::launch(gemm_splitk_reduce_kernel, td::LaunchCfg(grid1d((int64_t)a->M * a->N), 256, 0, s), *a, nzt);
+            return launch_status("gemm_splitk_reduce");
+        }
     }
     int nz = 1;
-    const int64_t ws = td_gemm_f32_workspace(a->M, a->N, a->K);
-    if (ws > 0 && a->splitk_ws) nz = (int)(ws / ((int64_t)a->M * a->N));
+    {   // FFMA split-K slices (the workspace may be larger: it also covers the tcgen05 path's split)
+        const int64_t tiles = ceil_div(a->M, G_BM) * ceil_div(a->N, G_BN);
+        if (a->splitk_ws && tiles < kNumSMs && a->K >= 1024)
+            nz = (int)std::min<int64_t>(std::min<int64_t>(kNumSMs / tiles, a->K / 256), 64);
+    }
     if (nz == 1 && a->M <= 4 && a->a_cs == 1 && a->b_rs == 1) {
         td::launch(gemv_f32_kernel, td::LaunchCfg((unsigned)ceil_div(a->N, 8), 256, 0, s), *a);
         return launch_status("gemv_f32");
@@ -657,9 +735,23 @@ extern "C" int td_dropout_f32(const float* x, int64_t ldx, float* out, int64_t l
 }
 
 extern "C" int td_embedding_bwd(const float* g, int64_t ldg, const int64_t* idx, float* table_grad, int M, int D,
-                                int num_rows, int accumulate, void* stream) {
+                                int num_rows, int accumulate, float* workspace, int64_t workspace_floats, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(g && idx && table_grad && M > 0 && D > 0 && num_rows > 0, "td_embedding_bwd: bad args");
+    const int64_t n = (int64_t)num_rows * D;
+    if (workspace && M >= 4096 && n * 4 <= 96 * 1024 && workspace_floats >= 2 * n) {
+        const int chunks = (int)std::min<int64_t>(std::min<int64_t>(workspace_floats / n, 2 * kNumSMs), M / 256);
+        static size_t configured = 0;
+        if ((size_t)n * 4 > 48 * 1024 && configured < 96 * 1024) {
+            TD_CUDA(cudaFuncSetAttribute(embedding_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = 96 * 1024;
+        }
+        cudaStream_t s = (cudaStream_t)stream;
+        td::launch(embedding_bwd_partial_kernel, td::LaunchCfg(chunks, 256, (size_t)n * 4, s), g, ldg, idx, workspace, M, D, num_rows);
+        td::launch(embedding_bwd_finalize_kernel, td::LaunchCfg((unsigned)ceil_div(n, 256), 256, 0, s), (const float*)workspace, chunks, (int)n,
+                   table_grad, accumulate);
+        return launch_status("embedding_bwd");
+    }
     td::launch(embedding_bwd_kernel, td::LaunchCfg(num_rows, 256, 0, (cudaStream_t)stream), g, ldg, idx, table_grad, M, D, accumulate);
     return launch_status("embedding_bwd");
 }
@@ -682,13 +774,25 @@ extern "C" int td_layernorm_fwd(const float* x, const float* gamma, const float*
 }
 
 extern "C" int td_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
-                                const float* rstd, float* dx, float* dgamma, float* dbeta, int M, int D, void* stream) {
+                                const float* rstd, float* dx, float* dgamma, float* dbeta, int M, int D, float* workspace,
+                                int64_t workspace_floats, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(dy && x && gamma && mean && rstd && dx && M > 0 && D > 0, "td_layernorm_bwd: bad args");
     cudaStream_t s = (cudaStream_t)stream;
     td::launch(layernorm_bwd_kernel, td::LaunchCfg((M + 7) / 8, 256, 0, s), dy, x, gamma, mean, rstd, dx, M, D);
     int st = launch_status("layernorm_bwd");
     if (st != TD_OK || !dgamma || !dbeta) return st;
+    if (workspace && M >= 4096 && workspace_floats >= 4 * (int64_t)D) {
+        const int gx = (D + 31) / 32;
+        const int chunks = (int)std::min<int64_t>(std::min<int64_t>(workspace_floats / (2 * (int64_t)D), std::max(1, 4 * kNumSMs / gx)), M / 64);
+        td::launch(layernorm_bwd_params_partial_kernel, td::LaunchCfg(dim3((unsigned)gx, (unsigned)chunks), 256, 0, s), dy, x, mean, rstd,
+                   workspace, M, D);
+        st = launch_status("layernorm_bwd_params_partial");
+        if (st != TD_OK) return st;
+        st = td_partial_sum(workspace, chunks, D, 0, dgamma, stream);
+        if (st != TD_OK) return st;
+        return td_partial_sum(workspace, chunks, D, 1, dbeta, stream);
+    }
     td::launch(layernorm_bwd_params_kernel, td::LaunchCfg((D + 31) / 32, 256, 0, s), dy, x, mean, rstd, dgamma, dbeta, M, D);
     return launch_status("layernorm_bwd_params");
 }
@@ -811,7 +915,7 @@ extern "C" int td_embed_head_bwd(const td_embed_args* a, const td_embed_grads* g
         if ((st = td_gemm_f32(&g, stream)) != TD_OK) return st;
     }
     if (a->y && gr->d_class_table) {
-        if ((st = td_embedding_bwd(demb, D, a->y, gr->d_class_table, B, D, gr->num_classes, 0, stream)) != TD_OK) return st;
+        if ((st = td_embedding_bwd(demb, D, a->y, gr->d_class_table, B, D, gr->num_classes, 0, nullptr, 0, stream)) != TD_OK) return st;
     }
     {   // d_w2 [D, D] = demb^T h ; d_b2 = colsum(demb)
         td_gemm_args g = gemm_init(D, D, B);

@@ -50,7 +50,8 @@ constexpr int GT_A_STAGE = 128 * 128;        // 128 rows x 32 fp32
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(GT_THREADS, 2)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const td_gemm_args g) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const td_gemm_args g,
+                 const int splits, const int ipz) {
     extern __shared__ uint8_t smem_raw[];
     constexpr int B_STAGE = BLOCK_N * 128;
     const uint32_t raw = smem_u32(smem_raw);
@@ -63,7 +64,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * 128, n0 = blockIdx.x * BLOCK_N;
-    const int iters = (g.K + 31) / 32;                    // TMA zero-fills the K tail
+    const int iters_all = (g.K + 31) / 32;                // TMA zero-fills the K tail
+    // split-K (blockIdx.z): this CTA reduces K steps [it0, it1) and stores the RAW accumulators to splitk_ws[z][M][N]; the second
+    // pass (gemm_splitk_reduce_kernel) sums the slices in fixed order and applies the epilogue.  The batch-reducing weight
+    // gradients of the dense denoisers are 2..64 output tiles over 2048 K steps: without the split 16-64 CTAs do all the work.
+    const int it0 = splits > 1 ? (int)blockIdx.z * ipz : 0;
+    const int it1 = splits > 1 ? min(iters_all, it0 + ipz) : iters_all;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -85,7 +91,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (elect_one()) {
             int s = 0;
             uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(GT_A_STAGE + B_STAGE));
                 tma_load_2d(smem_a + (size_t)s * GT_A_STAGE, &tmap_a, &full_bar[s], it * 32, m0);
@@ -98,13 +104,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N);
             int s = 0;
             uint32_t ph = 0;
-            for (int it = 0; it < iters; ++it) {
+            for (int it = it0; it < it1; ++it) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint64_t da = make_smem_desc_sw128(smem_u32(smem_a + (size_t)s * GT_A_STAGE), 16, 1024);
                 const uint64_t db = make_smem_desc_sw128(smem_u32(smem_b + (size_t)s * B_STAGE), 16, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (it > it0 || k > 0) ? 1u : 0u);
                 umma_commit(&empty_bar[s]);
                 if (++s == GT_STAGES) { s = 0; ph ^= 1u; }
             }
@@ -127,6 +133,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < 32; i += 4) sts128(tile_s + (uint32_t)(lane * 36 + i) * 4u, r[i], r[i + 1], r[i + 2], r[i + 3]);
             __syncwarp();
             const int gj = n0 + c0 + col;
+            if (splits > 1) {
+                if (gj < g.N) {
+                    float* wsz = g.splitk_ws + (int64_t)blockIdx.z * g.M * g.N;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rw = it * 4 + (lane >> 3);
+                        const int gi = m0 + q * 32 + rw;
+                        if (gi < g.M) *reinterpret_cast<float4*>(wsz + (int64_t)gi * g.N + gj) = lds128(tile_s + (uint32_t)(rw * 36 + col) * 4u);
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             if (gj < g.N) {                                  // N is a multiple of 4 (checked on the host)
                 float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(g.bias + gj));
@@ -169,9 +188,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // true: the tensor-core path ran (or failed: *status != TD_OK); false: not eligible, the caller falls back to the FFMA kernels
+// K slices of the tcgen05 GEMM: only when the output grid leaves most SMs idle and K is long (the weight gradients at large batch)
+int gemm_tf32_splits(int M, int N, int K) {
+    const int bn = N > 64 ? 128 : 64;
+    const int64_t tiles = ceil_div(M, 128) * ceil_div(N, bn);
+    const int iters = (K + 31) / 32;
+    if (2 * tiles > kNumSMs || K < 8192) return 1;
+    int splits = (int)std::min<int64_t>(std::min<int64_t>(kNumSMs / tiles, iters / 32), 64);
+    if (splits < 2) return 1;
+    const int ipz = (iters + splits - 1) / splits;
+    return (iters + ipz - 1) / ipz;
+}
+
 bool gemm_tf32_eligible(const td_gemm_args* a) {
     static const bool on = []() { const char* e = getenv("TD_GEMM_TF32"); return !(e && atoi(e) == 0); }();
-    if (!on || !a->allow_tf32 || a->splitk_ws) return false;            // opt-in per call: the dense engines set it at batch >= 2048
+    if (!on || !a->allow_tf32) return false;            // opt-in per call: the dense engines set it at batch >= 2048
+    if (a->splitk_ws && !aligned16(a->splitk_ws)) return false;
     if (a->M < 32) return false;
     if (a->a_cs != 1 || a->b_rs != 1) return false;                                  // both operands K-major
     if (a->a_rs % 4 || a->b_cs % 4 || a->N % 4 || a->ldc % 4) return false;          // 16-byte rows for TMA and the epilogue
@@ -184,9 +216,13 @@ bool gemm_tf32_eligible(const td_gemm_args* a) {
     return tc_get_encode_fn() != nullptr;
 }
 
-bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status) {
+bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status, int* nz_out) {
     *status = TD_OK;
+    *nz_out = 1;
     if (!gemm_tf32_eligible(a)) return false;
+    const int splits = a->splitk_ws ? gemm_tf32_splits(a->M, a->N, a->K) : 1;
+    const int ipz = (((a->K + 31) / 32) + splits - 1) / splits;
+    *nz_out = splits;
     EncodeTiledFn encode = tc_get_encode_fn();
     const int bn = a->N > 64 ? 128 : 64;
     CUtensorMap ma, mb;
@@ -209,15 +245,15 @@ bool gemm_tf32_try(const td_gemm_args* a, cudaStream_t s, int* status) {
             return false;
     }
     const int smem = GT_STAGES * (GT_A_STAGE + bn * 128) + (2 * GT_STAGES + 1) * 8 + 16 + 1024;
-    const dim3 grid((unsigned)ceil_div(a->N, bn), (unsigned)ceil_div(a->M, 128), 1);
+    const dim3 grid((unsigned)ceil_div(a->N, bn), (unsigned)ceil_div(a->M, 128), (unsigned)splits);
     if (bn == 128) {
         static bool cfg = false;
         if (!cfg) { cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
-        td::launch(gemm_tf32_kernel<128>, td::LaunchCfg(grid, GT_THREADS, smem, s), ma, mb, *a);
+        td::launch(gemm_tf32_kernel<128>, td::LaunchCfg(grid, GT_THREADS, smem, s), ma, mb, *a, splits, ipz);
     } else {
         static bool cfg = false;
         if (!cfg) { cudaFuncSetAttribute(gemm_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); cfg = true; }
-        td::launch(gemm_tf32_kernel<64>, td::LaunchCfg(grid, GT_THREADS, smem, s), ma, mb, *a);
+        td::launch(gemm_tf32_kernel<64>, td::LaunchCfg(grid, GT_THREADS, smem, s), ma, mb, *a, splits, ipz);
     }
     *status = launch_status("gemm_tf32");
     return true;

@@ -134,8 +134,16 @@ class DenseEngine:
         return (self.training and self.B >= 2048 and bool(op["relu"]) and x.stride(0) == N and N % 4 == 0
                 and lanes & (lanes - 1) == 0 and lanes <= 256)
 
+    def _splitk_ws(self, numel: int) -> torch.Tensor:
+        """Split-K workspace of the batch-reducing weight-gradient GEMMs at large batch (one buffer: they run one after another)."""
+        cur = getattr(self, "_sk_ws", None)
+        if cur is None or cur.numel() < numel:
+            cur = torch.empty(numel, device=self.device)
+            self._sk_ws = cur
+        return cur
+
     def _gemm(self, M, N, K, A, a_rs, a_cs, Bm, b_rs, b_cs, Cm, ldc, bias=None, act=0, pre=None, ld_pre=0, res=None,
-              ldr=0, gidx=None, gtab=None, ldt=0, accumulate=0):
+              ldr=0, gidx=None, gtab=None, ldt=0, accumulate=0, splitk=False):
         g = L.GemmArgs()
         g.M, g.N, g.K, g.alpha = M, N, K, 1.0
         g.A, g.a_rs, g.a_cs = A, a_rs, a_cs
@@ -144,10 +152,16 @@ class DenseEngine:
         g.pre_out, g.ld_pre, g.residual, g.ldr = pre, ld_pre, res, ldr
         g.gather_idx, g.gather_table, g.ld_table = gidx, gtab, ldt
         g.accumulate, g.splitk_ws = accumulate, None
+        ws = None
+        if splitk:                                  # K = the batch: slices over K, fixed-order second pass (FFMA and tcgen05 paths)
+            need = int(self.lib.td_gemm_f32_workspace(M, N, K))
+            if need > 0:
+                ws = self._splitk_ws(need)
+                g.splitk_ws = ws.data_ptr()
         g.allow_tf32 = int(self.B >= 2048)          # large batches: tcgen05 kind::tf32 GEMM (linear_tc.cu), tolerance 1e-2
         self.flops += 2.0 * M * N * K
         lib = self.lib
-        return lambda st, g=g: L.check(lib.td_gemm_f32(C.byref(g), st), "td_gemm_f32")
+        return lambda st, g=g, ws=ws: L.check(lib.td_gemm_f32(C.byref(g), st), "td_gemm_f32")
 
     def build(self):
         """Materialise the forward launches and derive the backward plan (reverse order)."""
@@ -379,9 +393,11 @@ class DenseEngine:
                 if op["gather"] is not None:
                     idx, tab = op["gather"]
                     tg = self.pgrad[self._pname[id(tab)]]
-                    steps.append(lambda st, s=g_out, idx=idx, tg=tg: L.check(
+                    rows_t = tg.numel() // tg.shape[-1]
+                    ews = self._colsum_part(min(296, max(2, B // 256)) * rows_t * tg.shape[-1]) if B >= 4096 else None
+                    steps.append(lambda st, s=g_out, idx=idx, tg=tg, ews=ews, rows_t=rows_t: L.check(
                         lib.td_embedding_bwd(s.data_ptr(), s.stride(0), idx.data_ptr(), tg.data_ptr(), B, tg.shape[-1],
-                                             tg.numel() // tg.shape[-1], 0, st), "td_embedding_bwd"))
+                                             rows_t, 0, L.ptr(ews), ews.numel() if ews is not None else 0, st), "td_embedding_bwd"))
                 g_pre = g_out
                 if op["act"] != L.ACT_NONE:
                     pre = self.val(op["pre"])
@@ -399,10 +415,10 @@ class DenseEngine:
                     steps.append(lambda st, g=g_pre, x=x, gt=gt, xt=xt, N=N, K=K: (
                         L.check(lib.td_transpose_f32(g.data_ptr(), g.stride(0), gt.data_ptr(), B, B, N, st), "td_transpose_f32"),
                         L.check(lib.td_transpose_f32(x.data_ptr(), x.stride(0), xt.data_ptr(), B, B, K, st), "td_transpose_f32")))
-                    steps.append(self._gemm(N, K, B, gt.data_ptr(), B, 1, xt.data_ptr(), 1, B, wgp, K))
+                    steps.append(self._gemm(N, K, B, gt.data_ptr(), B, 1, xt.data_ptr(), 1, B, wgp, K, splitk=True))
                 else:
                     steps.append(self._gemm(N, K, B, g_pre.data_ptr(), 1, g_pre.stride(0), x.data_ptr(), x.stride(0), 1,
-                                            wgp, K))                                   # dW = g^T x
+                                            wgp, K, splitk=B >= 2048))                 # dW = g^T x
                 if b is not None:
                     bg = self.pgrad[self._pname[id(b)]]
                     bgp = bg.data_ptr() + 4 * r0
@@ -472,9 +488,11 @@ class DenseEngine:
                 db = self.pgrad[self._pname[id(ln.bias)]]
                 D = x.shape[1]
                 assert g_out.stride(0) == D and gx.stride(0) == D
-                bwd.append((f"{op['name']}:bwd", lambda st, x=x, ln=ln, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db, D=D: L.check(
+                lws = self._colsum_part(2 * D * min(296, max(2, B // 64))) if B >= 4096 else None
+                bwd.append((f"{op['name']}:bwd", lambda st, x=x, ln=ln, g_out=g_out, gx=gx, sv=sv, dg=dg, db=db, D=D, lws=lws: L.check(
                     lib.td_layernorm_bwd(g_out.data_ptr(), x.data_ptr(), ln.weight.data_ptr(), sv["mean"].data_ptr(),
-                                         sv["rstd"].data_ptr(), gx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, D, st),
+                                         sv["rstd"].data_ptr(), gx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, D, L.ptr(lws),
+                                         lws.numel() if lws is not None else 0, st),
                     "td_layernorm_bwd")))
             elif k == "drop":
                 g_out, gx, slot = self.grad(op["out"]), self.grad(op["x"]), op["slot"]
