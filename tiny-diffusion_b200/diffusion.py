@@ -13,7 +13,9 @@ import torch.nn as nn
 
 from . import _lib as L
 from .checkpoint import CheckpointCompat
-from .process import ForwardProcess, ReverseLoop
+import os
+
+from .process import ForwardProcess, ReverseLoop, SamplerChains
 from .unet import MNIST_UNET, UNetConfig, UNetEngine
 
 __all__ = ["NoiseModel", "ForwardProcess", "sample"]
@@ -67,14 +69,17 @@ class ConvUNetBase(CheckpointCompat, nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engines"] = {}
+        st.pop("_sampler_plans", None)
         return st
 
     def _apply(self, fn, *a, **k):
         self._engines = {}
         return super()._apply(fn, *a, **k)
 
-    def engine(self, batch: int, device: torch.device) -> UNetEngine:
-        key = (batch, str(device), self.precision)
+    def engine(self, batch: int, device: torch.device, replica: int = 0) -> UNetEngine:
+        """The eval plan for ``batch`` samples; ``replica`` > 0: another plan of the same shape with its own buffers (the
+        sampler runs sub-batches concurrently, process.SamplerChains)."""
+        key = (batch, str(device), self.precision) if replica == 0 else (batch, str(device), self.precision, replica)
         eng = self._engines.get(key)
         if eng is None:
             cfg = self.config
@@ -108,6 +113,65 @@ class NoiseModel(ConvUNetBase):
         return self._forward_impl(x, t, None)
 
 
+def sampler_chains(n: int) -> int:
+    """Sub-batches one sample() call is split into (TD_SAMPLE_CHAINS; default 2 for batches of >= 64 samples)."""
+    want = int(os.environ.get("TD_SAMPLE_CHAINS", "2"))
+    if want <= 1 or n < 64:
+        return 1
+    while want > 1 and n % want:
+        want -= 1
+    return want
+
+
+class SamplerPlan:
+    """Everything one ``sample()`` call of ``n`` samples needs on the device: the eval plans of its chains (sub-batches), their
+    conditioning, and the captured reverse loop.  Cached on the model per (n, process, use_graph)."""
+
+    def __init__(self, noise_model: "ConvUNetBase", diffusion: ForwardProcess, device, n: int, use_graph: bool = True):
+        self.model, self.p, self.n, self.device = noise_model, diffusion, n, device
+        k = sampler_chains(n)
+        self.bounds = [(n * c // k, n * (c + 1) // k) for c in range(k)]
+        self.engs = [noise_model.engine(hi - lo, device, replica=c) for c, (lo, hi) in enumerate(self.bounds)]
+        self.loop = SamplerChains(diffusion, [{"x": e.x_in, "eps": e.eps, "t_dev": e.t_dev, "launch": e.launch} for e in self.engs],
+                                  use_graph=use_graph)
+        self.use_graph = use_graph
+
+    def load(self, x_T: torch.Tensor, cond=None) -> None:
+        """x_T (any device, [n, C, H, W]) and the conditioning (labels / text embeddings) into the chains' plans."""
+        for e, (lo, hi) in zip(self.engs, self.bounds):
+            e.refresh_weights()
+            e.x_in.copy_(x_T[lo:hi].to(torch.float32), non_blocking=True)
+            if e.cfg.cond == "class":
+                e.y_in.copy_(cond[lo:hi], non_blocking=True)
+            elif e.cfg.cond == "text":
+                e.text_in.copy_(cond[lo:hi], non_blocking=True)
+            e.use_t_dev = True
+            e.prepare_sampler_embed()
+
+    def run(self, z=None, seed: int = 0, steps: Optional[int] = None) -> None:
+        self.loop.run(z=z, seed=seed, steps=steps)
+
+    def result(self) -> torch.Tensor:
+        out = torch.cat([e.x_in for e in self.engs], dim=0) if len(self.engs) > 1 else self.engs[0].x_in.clone()
+        for e in self.engs:
+            e.use_t_dev = False
+        return out
+
+    def conv_flops(self) -> float:
+        return sum(e.conv_flops() for e in self.engs)
+
+
+def sampler_plan(noise_model, diffusion, device, n: int, use_graph: bool = True) -> SamplerPlan:
+    cache = noise_model.__dict__.setdefault("_sampler_plans", {})
+    key = (n, str(device), noise_model.precision, id(diffusion), use_graph, sampler_chains(n), id(noise_model._engines))
+    plan = cache.get(key)
+    if plan is None:
+        plan = SamplerPlan(noise_model, diffusion, device, n, use_graph)
+        cache.clear()                 # one plan at a time (its graphs pin the chains' buffers)
+        cache[key] = plan
+    return plan
+
+
 def _sample_impl(noise_model: ConvUNetBase, diffusion: ForwardProcess, device, shape, cond=None,
                  x_T: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None, seed: Optional[int] = None,
                  use_graph: bool = True, steps: Optional[int] = None) -> torch.Tensor:
@@ -116,27 +180,14 @@ def _sample_impl(noise_model: ConvUNetBase, diffusion: ForwardProcess, device, s
     n = shape[0]
     if x_T is None:
         x_T = torch.randn(*shape)                         # CPU generator, then H2D  (diffusion.py:257)
-    eng = noise_model.engine(n, device)
-    eng.refresh_weights()
-    eng.x_in.copy_(x_T.to(torch.float32), non_blocking=True)
-    if eng.cfg.cond == "class":
-        eng.y_in.copy_(cond)
-    elif eng.cfg.cond == "text":
-        eng.text_in.copy_(cond)
-    eng.use_t_dev = True
-    eng.prepare_sampler_embed()
-    loop = getattr(eng, "_reverse_loop", None)
-    if loop is None or loop.p is not diffusion or loop.use_graph != use_graph:
-        loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch, use_graph=use_graph)
-        eng._reverse_loop = loop
+    plan = sampler_plan(noise_model, diffusion, device, n, use_graph)
+    plan.load(x_T, cond)
     if z is not None:
         z = z.to(device=device, dtype=torch.float32).contiguous()
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # one draw from the CPU generator
-    loop.run(z=z, seed=seed, steps=steps)
-    out = eng.x_in.clone()
-    eng.use_t_dev = False
-    return out
+    plan.run(z=z, seed=seed, steps=steps)
+    return plan.result()
 
 
 @torch.no_grad()

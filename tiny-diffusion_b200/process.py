@@ -153,3 +153,117 @@ class ReverseLoop:
         self.t_dev.copy_(t_saved)
         self.graphs[k] = g
         return g
+
+
+class SamplerChains:
+    """The reverse loop of ONE ``sample()`` call run as several independent sub-batches ("chains"), each on its own stream
+    inside the same captured graph.
+
+    Every sample is independent in eval mode (diffusion.py:256), so splitting the batch changes no result -- it is the
+    sample sharding of the multi-GPU path applied inside one GPU.  Why it pays: a reverse step is a dependent chain of ~30
+    kernels, 13 of them persistent one-CTA-per-SM convolutions; at batch 128 their (n-tile, subtile) units do not divide by
+    148 SMs (896 / 512 / 256 units: the last round runs a handful of CTAs), every launch pays ~6-8 us of pipeline fill and
+    drain, and the glue kernels between them leave most SMs idle.  With two chains the other chain's next kernel fills
+    those holes: its CTAs start as soon as an SM frees.
+
+    ``chains``: list of dicts with ``x`` / ``eps`` / ``t_dev`` tensors and a ``launch`` callable (one denoiser engine each).
+    Injected noise ``z`` is the full table [T, n_total, ...]; chain c reads its slice of every row.  In-kernel Philox noise is
+    keyed per chain (seed, c << 40)."""
+
+    STEPS_PER_GRAPH = ReverseLoop.STEPS_PER_GRAPH
+
+    def __init__(self, process: ForwardProcess, chains, use_graph: bool = True):
+        self.p, self.chains, self.use_graph = process, chains, use_graph
+        self.lib = L.load()
+        dev = chains[0]["x"].device
+        self.tab = process._tables(dev)
+        self.seeds = [torch.zeros(2, device=dev, dtype=torch.int64) for _ in chains]
+        self.sizes = [c["x"].numel() for c in chains]
+        self.n_total = sum(self.sizes)
+        self.side = [None] + [torch.cuda.Stream(device=dev) for _ in chains[1:]]
+        self.graphs = {}
+        self._key = None
+        self._z_ref = None
+        self.launches_per_step = 0
+
+    def _step(self, c: int, z_ptr, z_stride, use_seed: bool):
+        ch = self.chains[c]
+        st = L.stream_ptr()
+        ch["launch"]()
+        zp = None if z_ptr is None else z_ptr + 4 * sum(self.sizes[:c])
+        L.check(self.lib.td_psample_step(ch["x"].data_ptr(), ch["eps"].data_ptr(), zp, z_stride, self.tab["coef"].data_ptr(),
+                                         ch["t_dev"].data_ptr(), self.sizes[c], self.p.num_timesteps,
+                                         self.seeds[c].data_ptr() if use_seed else None, st), "td_psample_step")
+        L.check(self.lib.td_counter_add(ch["t_dev"].data_ptr(), -1, st), "td_counter_add")
+
+    def _steps_all(self, k: int, z_ptr, z_stride, use_seed: bool):
+        """k reverse steps of every chain: chain 0 on the current stream, the others on their side streams (forked here and
+        joined at the end; inside a capture these are parallel branches of the graph)."""
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for c in range(len(self.chains)):
+            if c == 0:
+                for _ in range(k):
+                    self._step(0, z_ptr, z_stride, use_seed)
+                continue
+            self.side[c].wait_event(fork)
+            with torch.cuda.stream(self.side[c]):
+                for _ in range(k):
+                    self._step(c, z_ptr, z_stride, use_seed)
+        for c in range(1, len(self.chains)):
+            ev = torch.cuda.Event()
+            ev.record(self.side[c])
+            main.wait_event(ev)
+
+    def run(self, z: Optional[torch.Tensor] = None, seed: int = 0, steps: Optional[int] = None) -> None:
+        T = self.p.num_timesteps
+        steps = T if steps is None else steps
+        if not 0 <= steps <= T:
+            raise ValueError(f"steps must be in [0, {T}] (the loop starts at t = T-1 and ends at t = 0)")
+        if z is not None:
+            assert z.is_cuda and z.dtype == torch.float32 and z.is_contiguous() and z.shape[0] == T
+            assert z.numel() == T * self.n_total
+            z_ptr, z_stride, use_seed = z.data_ptr(), self.n_total, False
+        else:
+            for c, s in enumerate(self.seeds):
+                s[0] = seed
+                s[1] = c << 40
+            z_ptr, z_stride, use_seed = None, 0, True
+        for ch in self.chains:
+            ch["t_dev"].fill_(T - 1)
+        if not self.use_graph:
+            self._steps_all(steps, z_ptr, z_stride, use_seed)
+            return
+        key = (z_ptr, z_stride, use_seed)
+        if self._key != key:
+            self.graphs, self._key, self._z_ref = {}, key, z
+        unroll = max(1, int(self.STEPS_PER_GRAPH))
+        done = 0
+        while done < steps:
+            k = unroll if steps - done >= unroll else 1
+            self._graph(k, z_ptr, z_stride, use_seed).replay()
+            done += k
+
+    def _graph(self, k: int, z_ptr, z_stride, use_seed):
+        g = self.graphs.get(k)
+        if g is not None:
+            return g
+        saved = [(ch["x"].clone(), ch["t_dev"].clone()) for ch in self.chains]
+        if not self.graphs:                       # one eager step first (lazy module loading, cudaFuncSetAttribute)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._steps_all(1, z_ptr, z_stride, use_seed)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.td_launch_count())
+        with torch.cuda.graph(g):
+            self._steps_all(k, z_ptr, z_stride, use_seed)
+        self.launches_per_step = (int(self.lib.td_launch_count()) - n0) // k
+        for ch, (xs, ts) in zip(self.chains, saved):
+            ch["x"].copy_(xs)
+            ch["t_dev"].copy_(ts)
+        self.graphs[k] = g
+        return g
