@@ -114,8 +114,10 @@ class NoiseModel(ConvUNetBase):
 
 
 def sampler_chains(n: int) -> int:
-    """Sub-batches one sample() call is split into (TD_SAMPLE_CHAINS; default 2 for batches of >= 64 samples)."""
-    want = int(os.environ.get("TD_SAMPLE_CHAINS", "2"))
+    """Sub-batches one sample() call is split into (TD_SAMPLE_CHAINS; default 1).  Two / four chains at batch 128 measured
+    SLOWER (514.7 / 610.0 us per reverse step against 429.3: the persistent convolutions hold every SM, so a second chain
+    cannot fill the first one's tails, and every launch's fixed cost doubles; profiles/r02_chains.txt)."""
+    want = int(os.environ.get("TD_SAMPLE_CHAINS", "1"))
     if want <= 1 or n < 64:
         return 1
     while want > 1 and n % want:
