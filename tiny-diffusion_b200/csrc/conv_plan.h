@@ -35,7 +35,6 @@ struct td_wgrad_plan {
     int bw, bh, bn, rows, tiles_w, tiles_h, tiles_n;
     int x_on_m, block_n, m_tiles, n_tiles, m_boxes, n_boxes, stages, boxes_per_split, smem_bytes;
     int taps, slot_bytes, ksteps;       // taps = 3: halo variant of the tcgen05 kernel (conv_wgrad_tc.cu)
-    int cta_splits, cluster;            // CTAs along the split dimension and the cluster size; `splits` = partial sets written
 };
 
 namespace td {

@@ -42,7 +42,6 @@ struct WgParams {
     int stages, splits, boxes_per_split;
     int slot_bytes;                               // TAPS = 3: bytes of one 64-channel box slot (1 KB front guard + box + zero tail)
     int ksteps;                                   // 16-pixel MMA steps per box
-    int cluster;                                  // CTAs (consecutive splits) whose partials are summed through DSMEM before the store
     float* ws;
 };
 
@@ -79,7 +78,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
     const int dyy = tap / 3 - 1, dxx = TAPS == 1 ? tap % 3 - 1 : 0;
     const int total_boxes = p.tiles_w * p.tiles_h * p.tiles_n;
     const int box_beg = split * p.boxes_per_split;
-    const int box_end = split < p.splits ? min(total_boxes, box_beg + p.boxes_per_split) : box_beg;    // padded CTAs of the last cluster: no work
+    const int box_end = min(total_boxes, box_beg + p.boxes_per_split);
     const int iters = max(box_end - box_beg, 0);
 
     if (warp == 0 && lane == 0) {
@@ -164,32 +163,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
             }
             umma_commit(tmem_full_bar);
         }
-    } else if (TAPS == 3 && p.cluster > 1) {
-        // ---- cluster split-K, phase 1: the accumulators (128 rows x 3*BLOCK_N fp32) go to this CTA's shared memory, row-major
-        // with a padded stride, over the operand ring (every MMA has completed, so every TMA load has been consumed).
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        if (iters > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            tc_fence_after();
-        }
-        float* stg = reinterpret_cast<float*>(smem);
-        constexpr int STG_LD = TAPS * BLOCK_N + 4;
-#pragma unroll 1
-        for (int cc = 0; cc < TAPS * BLOCK_N; cc += 32) {
-            uint32_t r[32];
-            if (iters > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, r);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            const uint32_t dst = smem_u32(stg + (size_t)m * STG_LD + cc);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) sts128(dst + (uint32_t)j * 4u, r[j], r[j + 1], r[j + 2], r[j + 3]);
-        }
-        tc_fence_before();
     } else {
         const int q = warp & 3;
         const int m = q * 32 + lane;                   // accumulator row = M-side channel within the tile
@@ -244,62 +217,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
         }
         tc_fence_before();
     }
-    if (TAPS == 3 && p.cluster > 1) {
-        // ---- cluster split-K, phase 2: CTA r of the cluster sums rows [r*128/CL, (r+1)*128/CL) of the CL staged tiles in rank
-        // order (deterministic) through distributed shared memory and writes ONE partial set per cluster: CL x fewer partial
-        // bytes leave the SM and the second pass (wgrad_reduce_kernel) reads CL x fewer.
-        cluster_sync_all();
-        if (warp >= 2) {
-            constexpr int STG_LD = TAPS * BLOCK_N + 4;
-            const int CL = p.cluster;
-            const uint32_t rank = cluster_ctarank();
-            const int rows = 128 / CL;
-            const int tid = threadIdx.x - 64;                        // 0..127 over the epilogue warps
-            float* wsz = p.ws + (int64_t)(blockIdx.y / CL) * ((int64_t)p.cout * 9 * p.cin);
-            const uint32_t stg0 = smem_u32(smem);
-            const int m_limit = p.x_on_m ? p.cin : p.cout;
-            if (!p.x_on_m) {
-                // row = cout, columns = (tap, cin): float4 along cin, consecutive lanes -> consecutive columns (128-byte runs)
-                constexpr int C4 = TAPS * BLOCK_N / 4;
-                for (int e = tid; e < rows * C4; e += 128) {
-                    const int rl = e / C4, c4 = e - rl * C4;
-                    const int row = (int)rank * rows + rl;
-                    const uint32_t off = stg0 + (uint32_t)(row * STG_LD + c4 * 4) * 4u;
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int sidx = 0; sidx < CL; ++sidx) {
-                        uint32_t ra;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(sidx));
-                        float4 v;
-                        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                    }
-                    const int col = c4 * 4, t_ = col / BLOCK_N, c0 = col - t_ * BLOCK_N;
-                    const int mrow = mt * 128 + row, nch = nt * BLOCK_N + c0;
-                    if (mrow < m_limit && nch < p.cin)
-                        *reinterpret_cast<float4*>(wsz + ((int64_t)mrow * 9 + (tap + t_)) * p.cin + nch) = acc;
-                }
-            } else {
-                // row = cin, columns = (tap, cout): consecutive lanes -> consecutive rows (coalesced along cin in the workspace)
-                for (int e = tid; e < rows * TAPS * BLOCK_N; e += 128) {
-                    const int col = e / rows, rl = e - col * rows;
-                    const int row = (int)rank * rows + rl;
-                    const uint32_t off = stg0 + (uint32_t)(row * STG_LD + col) * 4u;
-                    float acc = 0.f;
-                    for (int sidx = 0; sidx < CL; ++sidx) {
-                        uint32_t ra;
-                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(off), "r"(sidx));
-                        float v;
-                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-                        acc += v;
-                    }
-                    const int t_ = col / BLOCK_N, c0 = col - t_ * BLOCK_N;
-                    const int mch = mt * 128 + row, nch = nt * BLOCK_N + c0;
-                    if (mch < m_limit && nch < p.cout) wsz[((int64_t)nch * 9 + (tap + t_)) * p.cin + mch] = acc;
-                }
-            }
-        }
-        cluster_sync_all();              // nobody leaves while a peer may still read its tile
-    }
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -319,7 +236,6 @@ struct WgGeom {
     int bw, bh, bn, rows, tiles_w, tiles_h, tiles_n;
     int x_on_m, block_n, m_tiles, n_tiles, m_boxes, n_boxes, stages, splits, boxes_per_split, smem_bytes;
     int taps, slot_bytes, ksteps;       // taps = 3: halo variant (flat boxes with a pad column, one CTA per kernel row)
-    int cluster, psets;                 // CTAs per cluster along the split dimension; partial sets written = ceil(splits / cluster)
 };
 
 // Halo variant: box = (64 ch, PW = W + 1, bh, bn) positions, P = PW*bh*bn <= 128 K rows per box.
@@ -365,23 +281,14 @@ static bool wg_geometry_halo(const td_wgrad_desc& d, WgGeom& g) {
     int splits = std::max(1, sm_budget() / base);
     if (const char* e = getenv("TD_WG_TARGET_CTAS")) { int v = atoi(e); if (v > 0) splits = std::max(1, v / base); }
     splits = std::max(1, std::min(splits, std::max(1, total_boxes / 2)));
-    // Cluster split-K: CL consecutive splits sum their accumulators through distributed shared memory and store one partial
-    // set (TD_WG_CLUSTER, default 4; 1 = every CTA stores its own).  The staged tile (128 x (3*BLOCK_N + 4) fp32) must fit
-    // in the operand ring, and the split count is rounded DOWN to a multiple of CL so that the grid stays one wave.
-    int cl = 4;
-    if (const char* e = getenv("TD_WG_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cl = v; }
-    while (cl > 1 && (splits < 2 * cl || 128 * (3 * g.block_n + 4) * 4 > g.stages * stage)) cl >>= 1;
-    if (cl > 1) splits = splits / cl * cl;
     g.boxes_per_split = (int)ceil_div(total_boxes, splits);
     g.splits = (int)ceil_div(total_boxes, g.boxes_per_split);
-    g.cluster = cl;
-    g.psets = (int)ceil_div(g.splits, cl);
     return true;
 }
 
 static bool wg_geometry(const td_wgrad_desc& d, WgGeom& g) {
     if (wg_geometry_halo(d, g)) return true;
-    g.taps = 1; g.slot_bytes = 0; g.ksteps = 0; g.cluster = 1;
+    g.taps = 1; g.slot_bytes = 0; g.ksteps = 0;
     if (d.cin % 64 != 0 || d.cout % 64 != 0) return false;
     // pixel box: full-width rows, rows*... a multiple of 16 and <= 128; maximise useful pixels, then size
     const int bw = d.width <= 32 ? d.width : 32;
@@ -427,14 +334,12 @@ static bool wg_geometry(const td_wgrad_desc& d, WgGeom& g) {
     splits = std::max(1, std::min(splits, std::max(1, total_boxes / 4)));
     g.boxes_per_split = (int)ceil_div(total_boxes, splits);
     g.splits = (int)ceil_div(total_boxes, g.boxes_per_split);
-    g.psets = g.splits;
     return true;
 }
 
-// partial sets the kernel writes (= what the workspace holds and the second pass sums)
 int wgrad_tc_splits(const td_wgrad_desc& d) {
     WgGeom g;
-    return wg_geometry(d, g) ? g.psets : 1;
+    return wg_geometry(d, g) ? g.splits : 1;
 }
 
 static int encode_act(EncodeTiledFn encode, CUtensorMap* map, const void* ptr, int ld, int W, int H, int B, int bw, int bh,
@@ -471,8 +376,7 @@ int wgrad_tc_plan_init(td_wgrad_plan* p) {
     p->bw = g.bw; p->bh = g.bh; p->bn = g.bn; p->rows = g.rows;
     p->tiles_w = g.tiles_w; p->tiles_h = g.tiles_h; p->tiles_n = g.tiles_n;
     p->x_on_m = g.x_on_m; p->block_n = g.block_n; p->m_tiles = g.m_tiles; p->n_tiles = g.n_tiles;
-    p->m_boxes = g.m_boxes; p->n_boxes = g.n_boxes; p->stages = g.stages; p->splits = g.psets;
-    p->cta_splits = g.splits; p->cluster = g.cluster;
+    p->m_boxes = g.m_boxes; p->n_boxes = g.n_boxes; p->stages = g.stages; p->splits = g.splits;
     p->boxes_per_split = g.boxes_per_split; p->smem_bytes = g.smem_bytes;
     p->taps = g.taps; p->slot_bytes = g.slot_bytes; p->ksteps = g.ksteps;
     // the tensor map's channel extent is the live channel range, so the second 64-channel box of a
@@ -492,28 +396,9 @@ static int launch_wg(const td_wgrad_plan* p, const WgParams& prm, cudaStream_t s
         TD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BLOCK_N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         configured_smem = p->smem_bytes;
     }
-    const int cl = p->cluster > 1 ? p->cluster : 1;
-    dim3 grid((unsigned)(p->m_tiles * p->n_tiles * (9 / TAPS)), (unsigned)(ceil_div(p->cta_splits, cl) * cl));
-    if (cl == 1) {
-        td::launch(wgrad_tc_kernel<BLOCK_N, TAPS>, td::LaunchCfg(grid, WG_TC_THREADS, p->smem_bytes, s), p->tmap_m, p->tmap_n, prm);
-        return launch_status("wgrad_tc");
-    }
-    // thread-block cluster along the split dimension (+ programmatic dependent launch, as td::launch does)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(WG_TC_THREADS);
-    cfg.dynamicSmemBytes = (size_t)p->smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = (unsigned)cl; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = td::pdl_enabled() ? 2 : 1;
-    td::count_launch();
-    (void)cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<BLOCK_N, TAPS>, p->tmap_m, p->tmap_n, prm);
-    return launch_status("wgrad_tc (cluster)");
+    dim3 grid((unsigned)(p->m_tiles * p->n_tiles * (9 / TAPS)), (unsigned)p->splits);
+    td::launch(wgrad_tc_kernel<BLOCK_N, TAPS>, td::LaunchCfg(grid, WG_TC_THREADS, p->smem_bytes, s), p->tmap_m, p->tmap_n, prm);
+    return launch_status("wgrad_tc");
 }
 
 int wgrad_tc_plan_run(const td_wgrad_plan* p, cudaStream_t s) {
@@ -526,8 +411,7 @@ int wgrad_tc_plan_run(const td_wgrad_plan* p, cudaStream_t s) {
     prm.m_coff = p->x_on_m ? d.x_coff : d.dy_coff;
     prm.n_coff = p->x_on_m ? d.dy_coff : d.x_coff;
     prm.m_tiles = p->m_tiles; prm.n_tiles = p->n_tiles; prm.x_on_m = p->x_on_m;
-    prm.stages = p->stages; prm.splits = p->cta_splits; prm.boxes_per_split = p->boxes_per_split;
-    prm.cluster = p->cluster;
+    prm.stages = p->stages; prm.splits = p->splits; prm.boxes_per_split = p->boxes_per_split;
     prm.ws = d.workspace;
     prm.slot_bytes = p->slot_bytes; prm.ksteps = p->ksteps;
     if (p->taps == 3) return p->block_n == 128 ? launch_wg<128, 3>(p, prm, s) : launch_wg<64, 3>(p, prm, s);
