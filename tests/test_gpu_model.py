@@ -208,3 +208,26 @@ def test_laion_sampler_vs_oracle(dev, precision, final_tol):
     assert torch.equal(got, eager)
     with pytest.raises(ValueError):
         mod.sample(model, fp, dev)                                    # conditional_diffusion_laion.py:565-566
+
+
+def test_sampler_chains_match_single_chain(dev, monkeypatch):
+    """process.SamplerChains: one sample() call split into two independent sub-batches on parallel graph branches gives the
+    samples of the single-chain run when the noise is injected (every sample is independent in eval mode)."""
+    name = "conditional_diffusion"
+    mod, model = build(name, dev, "fp32")
+    fp = mod.ForwardProcess(num_timesteps=25)                 # one 20-step graph + 5 single steps per chain
+    n = 64
+    g = torch.Generator().manual_seed(4)
+    x_T = torch.randn(n, 1, 28, 28, generator=g)
+    y = torch.randint(0, 10, (n,), generator=g)
+    z = torch.randn(25, n, 1, 28, 28, generator=g).to(dev)
+    monkeypatch.setenv("TD_SAMPLE_CHAINS", "1")
+    one = mod.sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, z=z)
+    monkeypatch.setenv("TD_SAMPLE_CHAINS", "2")
+    two = mod.sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, z=z)
+    eager = mod.sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, z=z, use_graph=False)
+    assert rel(two, one) < 1e-5 and torch.equal(two, eager)
+    a = mod.sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, seed=3)       # in-kernel Philox noise, keyed per chain
+    b = mod.sample(model, fp, dev, n_samples=n, y=y, x_T=x_T, seed=3)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert not torch.equal(a[:32], a[32:])
