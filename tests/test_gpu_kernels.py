@@ -246,6 +246,40 @@ def test_final_resize_conv(dev, dtype, tol, B, hi, ho, c):
     assert rel(got, want) < tol
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 32, 32), (2, 7, 9), (5, 33, 17), (1, 1, 1), (2, 40, 40), (2, 3, 64)])
+def test_conv_direct_latent_boundary(dev, B, H, W):
+    """The 4-channel boundary layers of the latent UNet: initial_conv 4 -> 32 (two pixels per thread, written into the
+    lower half of a 64-channel buffer) and final_conv 64 / 128 -> 4 (contract-then-stencil, several row bands)."""
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(B * 100 + H + W)
+    x = torch.randn(B, 4, H, W, generator=g)
+    w = torch.randn(32, 4, 3, 3, generator=g) / 6
+    b = torch.randn(32, generator=g) * 0.1
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    for odt, tol in ((torch.float32, 2e-6), (torch.bfloat16, 4e-3)):
+        out = torch.full((B, H, W, 64), 3.0, device=dev, dtype=odt)
+        ops.conv3x3(x.to(dev), ops.pack_conv_weight(w.to(dev)), None, b.to(dev), False, 2, odt, x_nchw=True, out=out)
+        assert rel(nchw(out[..., :32]).double(), want) < tol
+        assert float((out[..., 32:].float() - 3.0).abs().max()) == 0.0
+    w64 = torch.randn(64, 4, 3, 3, generator=g) / 6            # final_conv's data gradient: 4 -> 64, two channel slices
+    got = ops.conv3x3(x.to(dev), ops.pack_conv_weight(w64.to(dev)), None, None, False, 2, torch.float32, x_nchw=True)
+    assert rel(nchw(got).double(), F.conv2d(x.double(), w64.double(), padding=1)) < 2e-6
+    for cin in (64, 128):
+        xa = torch.randn(B, cin, H, W, generator=g)
+        w2 = torch.randn(4, cin, 3, 3, generator=g) / (9 * cin) ** 0.5
+        b2 = torch.randn(4, generator=g)
+        for idt in (torch.float32, torch.bfloat16):
+            xr = xa.to(idt)
+            want2 = F.conv2d(xr.double(), w2.double(), b2.double(), padding=1)
+            wide = torch.zeros(B, H, W, cin + 8, dtype=idt)
+            wide[..., 8:] = nhwc(xr)
+            for y_nchw in (True, False):
+                got2 = ops.conv3x3(wide.to(dev), ops.pack_conv_weight(w2.to(dev)), None, b2.to(dev), False, 2,
+                                   torch.float32, y_nchw=y_nchw, x_coff=8, cin=cin)
+                got2 = got2 if y_nchw else nchw(got2)
+                assert rel(got2.double(), want2) < 2e-6
+
+
 def test_conv_direct_first_last(dev):
     from tinydiff import ops
     g = torch.Generator().manual_seed(9)

@@ -234,6 +234,173 @@ conv3x3_last_kernel(const td_conv3x3_desc d, int lanes_per_pixel) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Boundary layers of the latent UNet (4 latent channels, diffusion_laion.py): the two generic kernels above spend their
+// time on shared-memory weight loads (one per FMA) and on re-reading every pixel nine times.
+//
+// conv3x3_firstn_kernel: NCHW fp32 input with CIN channels -> NHWC channels, COUT of them per CTA (blockIdx.y selects the
+// slice; also the data gradient of final_conv, 4 -> 64).  One thread owns two horizontally adjacent pixels and COUT outputs: a broadcast 16-byte weight load feeds 8 FMAs, the 3x4 input window of one
+// channel lives in registers.
+// ---------------------------------------------------------------------------------------------
+template <int CIN, int COUT, typename Tout>
+__global__ void __launch_bounds__(256, 2)
+conv3x3_firstn_kernel(const td_conv3x3_desc d) {
+    td::pdl_sync();
+    __shared__ __align__(16) float wsm[9 * CIN][COUT];       // [tap * CIN + c][cout]
+    __shared__ float ssc[COUT], ssh[COUT];
+    const int n0 = blockIdx.y * COUT;                          // this CTA's slice of the output channels
+    for (int i = threadIdx.x; i < 9 * CIN * COUT; i += blockDim.x) {
+        const int k = i / COUT, n = i - k * COUT;              // source: [cout][9][cin] (4.6 KB, L1/L2 resident)
+        wsm[k][n] = __ldg(reinterpret_cast<const float*>(d.w) + (n0 + n) * (9 * CIN) + k);
+    }
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+        ssc[i] = d.scale ? d.scale[n0 + i] : 1.f;
+        ssh[i] = d.shift ? d.shift[n0 + i] : 0.f;
+    }
+    __syncthreads();
+    const float* __restrict__ x = reinterpret_cast<const float*>(d.x);
+    const int H = d.height, W = d.width, pairs = (W + 1) / 2;
+    const int items = d.batch * H * pairs;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+        const int row = it / pairs, x0 = (it - row * pairs) * 2;
+        const int b = row / H, h = row - b * H;
+        float acc[2][COUT];
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float* xc = x + ((int64_t)b * CIN + c) * H * W;
+            float xv[3][4];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int hh = h + r - 1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ww = x0 + q - 1;
+                    xv[r][q] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xc + hh * W + ww) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float a0 = xv[t / 3][t % 3], a1 = xv[t / 3][t % 3 + 1];
+#pragma unroll
+                for (int j = 0; j < COUT; j += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(&wsm[t * CIN + c][j]);
+                    acc[0][j] = fmaf(a0, wv.x, acc[0][j]);         acc[1][j] = fmaf(a1, wv.x, acc[1][j]);
+                    acc[0][j + 1] = fmaf(a0, wv.y, acc[0][j + 1]); acc[1][j + 1] = fmaf(a1, wv.y, acc[1][j + 1]);
+                    acc[0][j + 2] = fmaf(a0, wv.z, acc[0][j + 2]); acc[1][j + 2] = fmaf(a1, wv.z, acc[1][j + 2]);
+                    acc[0][j + 3] = fmaf(a0, wv.w, acc[0][j + 3]); acc[1][j + 3] = fmaf(a1, wv.w, acc[1][j + 3]);
+                }
+            }
+        }
+        Tout* yrow = reinterpret_cast<Tout*>(d.y) + ((int64_t)row * W + x0) * d.ldy + d.y_coff + n0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            if (x0 + p >= W) break;
+#pragma unroll
+            for (int j = 0; j < COUT; ++j) {
+                const float v = fmaf(acc[p][j], ssc[j], ssh[j]);
+                acc[p][j] = d.relu ? fmaxf(v, 0.f) : v;
+            }
+            Tout* dst = yrow + (int64_t)p * d.ldy;
+#pragma unroll
+            for (int j = 0; j < COUT; j += 8) {
+                if constexpr (sizeof(Tout) == 2) {
+                    Vec<__nv_bfloat16>::pack(acc[p] + j).store(reinterpret_cast<__nv_bfloat16*>(dst) + j);
+                } else {
+                    Vec<float>::pack(acc[p] + j).store(reinterpret_cast<float*>(dst) + j);
+                    Vec<float>::pack(acc[p] + j + 4).store(reinterpret_cast<float*>(dst) + j + 4);
+                }
+            }
+        }
+    }
+}
+
+// conv3x3_lastn_kernel: NHWC input with cin channels -> COUT fp32 channels, contract-then-stencil.  The channel
+// contraction commutes with the spatial shift: e[j][t][s] = sum_c x[s, c] w[j, t, c] is computed once per source pixel
+// (the cin-channel vector is read exactly once; one thread owns two pixels and all 9 * COUT partials, weights are
+// broadcast 16-byte shared-memory loads feeding 8 FMAs each), parked in shared memory for a band of rows plus its
+// one-row halo, and the 3x3 stencil then adds nine scalars per output.
+// ---------------------------------------------------------------------------------------------
+template <typename Tin, int COUT>
+__global__ void __launch_bounds__(512)
+conv3x3_lastn_kernel(const td_conv3x3_desc d, int BH, int bands) {
+    td::pdl_sync();
+    constexpr int V = Vec<Tin>::N, Q = 9 * COUT;
+    extern __shared__ __align__(16) float lsm[];
+    const int H = d.height, W = d.width, cin = d.cin;
+    float* wsm = lsm;                                    // [Q][cin]
+    float* e = lsm + Q * cin;                            // [Q][(BH + 2) * W]
+    const int plane = (BH + 2) * W;
+    for (int i = threadIdx.x; i < Q * cin; i += blockDim.x) wsm[i] = reinterpret_cast<const float*>(d.w)[i];
+    __syncthreads();
+    const int b = blockIdx.x / bands, band = blockIdx.x - b * bands;
+    const int r0 = band * BH, r1 = min(r0 + BH, H);
+    const int q0 = max(r0 - 1, 0), q1 = min(r1 + 1, H);
+    const int npix = (q1 - q0) * W;
+    const Tin* __restrict__ xb = reinterpret_cast<const Tin*>(d.x) + ((int64_t)b * H + q0) * W * d.ldx + d.x_coff;
+    for (int item = threadIdx.x; item * 2 < npix; item += blockDim.x) {
+        const int p0 = item * 2;
+        const bool has1 = p0 + 1 < npix;
+        const Tin* x0 = xb + (int64_t)p0 * d.ldx;
+        const Tin* x1 = has1 ? x0 + d.ldx : x0;
+        float a0[Q], a1[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) a0[q] = a1[q] = 0.f;
+        for (int c = 0; c < cin; c += V) {
+            float f0[V], f1[V];
+            Vec<Tin>::load(x0 + c).unpack(f0);
+            Vec<Tin>::load(x1 + c).unpack(f1);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                for (int k = 0; k < V; k += 4) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wsm + q * cin + c + k);
+                    a0[q] = fmaf(f0[k], wv.x, a0[q]);     a1[q] = fmaf(f1[k], wv.x, a1[q]);
+                    a0[q] = fmaf(f0[k + 1], wv.y, a0[q]); a1[q] = fmaf(f1[k + 1], wv.y, a1[q]);
+                    a0[q] = fmaf(f0[k + 2], wv.z, a0[q]); a1[q] = fmaf(f1[k + 2], wv.z, a1[q]);
+                    a0[q] = fmaf(f0[k + 3], wv.w, a0[q]); a1[q] = fmaf(f1[k + 3], wv.w, a1[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            e[q * plane + p0] = a0[q];
+            if (has1) e[q * plane + p0 + 1] = a1[q];
+        }
+    }
+    __syncthreads();
+    const int nr = r1 - r0;
+    float* __restrict__ y = reinterpret_cast<float*>(d.y);
+    for (int o = threadIdx.x; o < COUT * nr * W; o += blockDim.x) {
+        const int w_ = o % W, t2 = o / W;
+        const int rr = t2 % nr, j = t2 / nr, r = r0 + rr;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = r + t / 3 - 1, ww = w_ + t % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc += e[(j * 9 + t) * plane + (hh - q0) * W + ww];
+        }
+        if (d.scale) acc *= d.scale[j];
+        if (d.shift) acc += d.shift[j];
+        if (d.relu) acc = fmaxf(acc, 0.f);
+        if (d.y_nchw) y[(((int64_t)b * COUT + j) * H + r) * W + w_] = acc;
+        else y[(((int64_t)b * H + r) * W + w_) * d.ldy + d.y_coff + j] = acc;
+    }
+}
+
+// Rows per band of conv3x3_lastn_kernel (0: the geometry does not fit shared memory -> generic kernel).  A whole image
+// per CTA when it fits (no halo rows computed twice): 32 x 32 x 36 partials = 144 KB for the latent UNet.
+constexpr int LASTN_SMEM = 200 * 1024;
+static int lastn_band_rows(const td_conv3x3_desc& d) {
+    const int64_t wbytes = (int64_t)d.cout * 9 * d.cin * 4, row = (int64_t)d.width * 9 * d.cout * 4;
+    const int64_t max_rows = (LASTN_SMEM - wbytes) / row;
+    if (max_rows < 3) return 0;
+    const int bh = (int)std::min<int64_t>(d.height, max_rows - 2);
+    const int bands = (int)ceil_div(d.height, bh);
+    return (int)ceil_div(d.height, bands);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fast paths of the two network-boundary layers of the MNIST UNets (the generic kernels above were
 // instruction-bound: a shared-memory weight load per FMA and 64-bit index math per element).
 // One CTA per image row (b, h); weights live in registers; no integer division per element.
@@ -377,6 +544,14 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
         else td::launch(conv3x3_first1_kernel<float>, td::LaunchCfg(grid, block, 0, s), d);
         return launch_status("conv3x3_first1");
     }
+    if (d.cin == 4 && d.cout % 32 == 0 && d.cout <= 32 * 65535 && d.x_nchw && d.x_dtype == TD_F32 &&
+        (int64_t)d.batch * d.height * d.width < (1 << 30)) {
+        const int items = d.batch * d.height * ((d.width + 1) / 2);
+        const dim3 grid((unsigned)std::max<int64_t>(1, ceil_div(items, 256)), (unsigned)(d.cout / 32));
+        if (d.y_dtype == TD_BF16) td::launch(conv3x3_firstn_kernel<4, 32, __nv_bfloat16>, td::LaunchCfg(grid, 256, 0, s), d);
+        else td::launch(conv3x3_firstn_kernel<4, 32, float>, td::LaunchCfg(grid, 256, 0, s), d);
+        return launch_status("conv3x3_firstn");
+    }
     if (d.cin <= 8) {
         const size_t smem = (size_t)d.cout * 9 * d.cin * sizeof(float);
         const int64_t items = M * (d.cout / 8);
@@ -396,6 +571,26 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
         if (d.x_dtype == TD_BF16) td::launch(conv3x3_last1_kernel<__nv_bfloat16>, td::LaunchCfg(grid, block, 0, s), d);
         else td::launch(conv3x3_last1_kernel<float>, td::LaunchCfg(grid, block, 0, s), d);
         return launch_status("conv3x3_last1");
+    }
+    if (d.cout == 4 && d.cin % 8 == 0) {
+        const int bh = lastn_band_rows(d);
+        if (bh > 0) {
+            const int bands = (int)ceil_div(d.height, bh);
+            const size_t smem = ((size_t)36 * d.cin + (size_t)36 * (bh + 2) * d.width) * sizeof(float);
+            const int grid = d.batch * bands;
+            // one pass over the band when its pixel pairs fit one CTA (a second pass would run on a few warps only)
+            const int items = (int)ceil_div((int64_t)std::min(bh + 2, d.height) * d.width, 2);
+            const int threads = std::min(512, std::max(64, (items + 31) / 32 * 32));
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(conv3x3_lastn_kernel<__nv_bfloat16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, LASTN_SMEM);
+                cudaFuncSetAttribute(conv3x3_lastn_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, LASTN_SMEM);
+                attr_done = true;
+            }
+            if (d.x_dtype == TD_BF16) td::launch(conv3x3_lastn_kernel<__nv_bfloat16, 4>, td::LaunchCfg(grid, threads, smem, s), d, bh, bands);
+            else td::launch(conv3x3_lastn_kernel<float, 4>, td::LaunchCfg(grid, threads, smem, s), d, bh, bands);
+            return launch_status("conv3x3_lastn");
+        }
     }
     int L = d.cin / V;
     if (L > 32) L = 32;

@@ -68,6 +68,13 @@ class UNetTrainEngine:
         self.S = dict(s0=s0, s1=s1, s2=s2, s3=s3, u3=u3, u2=u2, u1=u1)
         B = batch
         dev = device
+        # initial_conv's output (and its gradient) is allocated 64 channels wide when the model has fewer (the LAION latent
+        # UNet: 32): the upper channels stay zero and enc1.0's packed operands are zero-padded to match, so its forward,
+        # data gradient and weight gradient run on the tcgen05 engine like every other layer (see unet.UNetEngine.c0p)
+        self.c0p = c0
+        if precision == "bf16" and c0 % 64 != 0 and c1 % 64 == 0 and c0 % 8 == 0:
+            self.c0p = (c0 + 63) // 64 * 64
+        c0p = self.c0p
 
         def buf(h, c, dtype=None):
             return torch.zeros(B, h, h, c, device=dev, dtype=dtype or self.act)
@@ -75,7 +82,7 @@ class UNetTrainEngine:
         # (block name) -> input buffer, cin, spatial size, output buffer name
         self.layers: List[Tuple[str, str, int, int, str, int]] = [
             # name, input buffer, cin, size, output buffer, cout
-            ("enc1.0", "x0", c0, s0, "enc1a", c1), ("enc1.3", "enc1a", c1, s0, "e1", c1),
+            ("enc1.0", "x0", c0p, s0, "enc1a", c1), ("enc1.3", "enc1a", c1, s0, "e1", c1),
             ("enc2.0", "p1", c1, s1, "enc2a", c2), ("enc2.3", "enc2a", c2, s1, "e2", c2),
             ("enc3.0", "p2", c2, s2, "enc3a", c3), ("enc3.3", "enc3a", c3, s2, "e3", c3),
             ("bottleneck.0", "p3", c3, s3, "b", cfg.bott),
@@ -84,7 +91,7 @@ class UNetTrainEngine:
             ("dec1.0", "cat1", d2 + c1, u1, "dec1a", d1), ("dec1.3", "dec1a", d1, u1, "d1", d1),
         ]
         shapes = {
-            "x0": (s0, c0), "enc1a": (s0, c1), "e1": (s0, c1), "p1": (s1, c1),
+            "x0": (s0, c0p), "enc1a": (s0, c1), "e1": (s0, c1), "p1": (s1, c1),
             "enc2a": (s1, c2), "e2": (s1, c2), "p2": (s2, c2),
             "enc3a": (s2, c3), "e3": (s2, c3), "p3": (s3, c3), "b": (s3, cfg.bott),
             "cat3": (u3, cfg.bott + c3), "dec3a": (u3, d3), "d3": (u3, d3),
@@ -172,11 +179,15 @@ class UNetTrainEngine:
         self.conv_of: Dict[str, Tuple[torch.nn.Module, Optional[torch.nn.Module]]] = {}
         for name, conv, bn in self._conv_modules():
             cout, cin = conv.weight.shape[0], conv.weight.shape[1]
+            if name == "enc1.0":
+                cin = self.c0p
             self.conv_of[name] = (conv, bn)
             direct = name in ("initial_conv", "final_conv")
             wdt_f = torch.bfloat16 if (not direct and self._tc(cin, cout)) else torch.float32
             wdt_b = torch.bfloat16 if (not direct and self._tc(cout, cin)) else torch.float32
             self.w_fwd[name] = torch.zeros(cout, 3, 3, cin, device=self.device, dtype=wdt_f)
+            if cin != conv.weight.shape[1]:
+                self._w_pad_tmp = torch.zeros(cout, 3, 3, conv.weight.shape[1], device=self.device, dtype=wdt_f)
             if name != "initial_conv":
                 self.w_bwd[name] = torch.zeros(cin, 3, 3, cout, device=self.device, dtype=wdt_b)
 
@@ -201,9 +212,15 @@ class UNetTrainEngine:
             w = conv.weight.detach()
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
             pk = self.w_fwd[name]
+            padded = pk.shape[3] != w.shape[1]           # enc1.0 with zero-padded input channels (c0p)
+            if padded:
+                pk = self._w_pad_tmp
             L.check(lib.td_pack_conv_weight(w.data_ptr(), pk.data_ptr(), L.dtype_code(pk.dtype), w.shape[0], w.shape[1],
                                             st), "td_pack_conv_weight")
+            if padded:
+                self.w_fwd[name][..., :w.shape[1]].copy_(pk)
             if name in self.w_bwd:
+                # [cin][3][3][cout]: the real input channels are the leading rows of the padded operand
                 pb = self.w_bwd[name]
                 L.check(lib.td_pack_conv_weight_dgrad(w.data_ptr(), pb.data_ptr(), L.dtype_code(pb.dtype), w.shape[0],
                                                       w.shape[1], st), "td_pack_conv_weight_dgrad")
@@ -229,6 +246,8 @@ class UNetTrainEngine:
             co, ci = w.shape[0], w.shape[1]
             if pk.dtype != torch.bfloat16 or co % 32 or ci % 32 or (pb is not None and pb.dtype != torch.bfloat16):
                 continue
+            if pk.shape[3] != ci:
+                continue
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
             rows.append(struct.pack("<QQQiiii", w.data_ptr(), pk.data_ptr(), pb.data_ptr() if pb is not None else 0,
                                     co, ci, tiles, 0))
@@ -251,13 +270,13 @@ class UNetTrainEngine:
         d.splitk_ws = L.ptr(self.splitk_ws)
         return d
 
-    def _wgrad(self, name, x, cin, dy, cout, size, engine, x_nchw=False, dy_nchw=False):
+    def _wgrad(self, name, x, cin, dy, cout, size, engine, x_nchw=False, dy_nchw=False, dw=None):
         d = L.WgradDesc()
         d.batch, d.height, d.width, d.cin, d.cout = self.B, size, size, cin, cout
         d.x_dtype, d.dy_dtype = L.dtype_code(x.dtype), L.dtype_code(dy.dtype)
         d.x, d.ldx, d.x_coff, d.x_nchw = x.data_ptr(), (cin if x_nchw else x.shape[3]), 0, int(x_nchw)
-        d.dy, d.lddy, d.dy_coff, d.dy_nchw = dy.data_ptr(), cout, 0, int(dy_nchw)
-        d.dw = self.pgrad[self._wkey(name)].data_ptr()
+        d.dy, d.lddy, d.dy_coff, d.dy_nchw = dy.data_ptr(), (cout if dy_nchw else dy.shape[3]), 0, int(dy_nchw)
+        d.dw = (self.pgrad[self._wkey(name)] if dw is None else dw).data_ptr()
         need = int(self.lib.td_conv3x3_wgrad_workspace(C.byref(d), engine))
         self._wg_specs.append((name, d, engine, need))
 
@@ -272,6 +291,7 @@ class UNetTrainEngine:
         adt = self.adt
         self.conv_plans: Dict[str, _ConvPlan] = {}
         self._wg_specs: List = []
+        self._wg_post: Dict[str, Callable[[], None]] = {}
         self._side = getattr(self, "_side", None)
         self._side_f = getattr(self, "_side_f", None)
         fwd: List[Tuple[str, Callable[[int], None]]] = []
@@ -409,7 +429,16 @@ class UNetTrainEngine:
                         "td_bn_bwd_apply_fused")
             bwd.append((f"bn:{name}:bwd", bn_bwd))
             eng = L.CONV_TC if self._tc(cin, cout) else L.CONV_SIMT
-            self._wgrad(name, bf[xin], cin, dyv, cout, size, eng)
+            wkey = self._wkey(name)
+            if tuple(self.pgrad[wkey].shape) != (cout, cin, 3, 3):
+                # zero-padded input channels (enc1.0 reading the widened x0): the kernel writes [cout][c0p][3][3] into a
+                # scratch tensor and the real channels are copied into the flat gradient buffer on the same stream
+                real = self.pgrad[wkey].shape[1]
+                pad = torch.zeros(cout, cin, 3, 3, device=self.device, dtype=torch.float32)
+                self._wg_post[name] = lambda pad=pad, real=real, wkey=wkey: self.pgrad[wkey].copy_(pad[:, :real])
+                self._wgrad(name, bf[xin], cin, dyv, cout, size, eng, dw=pad)
+            else:
+                self._wgrad(name, bf[xin], cin, dyv, cout, size, eng)
             bwd.append((f"{name}:wgrad", None))
             if need_dx:
                 engd = L.CONV_TC if self._tc(cout, cin) else L.CONV_SIMT
@@ -468,7 +497,7 @@ class UNetTrainEngine:
         P0 = B * s0 * s0
 
         def ic_bias(st):
-            L.check(lib.td_bn_stats(gx0, adt, c0, 0, P0, c0, part, 0, st), "td_bn_stats")
+            L.check(lib.td_bn_stats(gx0, adt, self.c0p, 0, P0, c0, part, 0, st), "td_bn_stats")
             L.check(lib.td_partial_sum(part, rows0, c0, 0, icb, st), "td_partial_sum")
         bwd.append(("initial_conv:dbias", ic_bias))
         self._wgrad("initial_conv", self.x_in, cfg.in_ch, gr["x0"], c0, s0, L.CONV_SIMT, x_nchw=True)
@@ -499,6 +528,13 @@ class UNetTrainEngine:
 
         def on_wgrad_stream(name):
             run, lane = self.wg_plans[name].run, self._wg_lane[name]
+            post = self._wg_post.get(name)
+            if post is not None:
+                plan_run = run
+
+                def run(st):
+                    plan_run(st)
+                    post()
             if self.wgrad_streams == 0:
                 return run
 

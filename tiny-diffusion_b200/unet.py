@@ -108,12 +108,18 @@ class UNetEngine:
             assert (u3, u2, u1) == (s2, s1, s0), "skip sizes must match without resize"
         self.sizes = dict(s0=s0, s1=s1, s2=s2, s3=s3, u3=u3, u2=u2, u1=u1)
         B = batch
+        # enc1.0 reads initial_conv's output.  When that has fewer than 64 channels (the LAION latent UNet: 32) the layer
+        # would miss the tcgen05 engine (K tiles of 64 channels), so the buffer is allocated 64 wide, the upper channels
+        # stay zero (initial_conv writes the first c0 with row stride c0p) and the packed weight is zero-padded to match.
+        self.c0p = c0
+        if precision == "bf16" and c0 % 64 != 0 and c1 % 64 == 0 and c0 % 8 == 0:
+            self.c0p = (c0 + 63) // 64 * 64
 
         def buf(h, c, dtype=None):
             return torch.zeros(B, h, h, c, device=device, dtype=dtype or self.act)
 
         self.bufs: Dict[str, torch.Tensor] = {
-            "x0": buf(s0, c0),
+            "x0": buf(s0, self.c0p),
             "enc1a": buf(s0, c1), "e1": buf(s0, c1), "p1": buf(s1, c1),
             "enc2a": buf(s1, c2), "e2": buf(s1, c2), "p2": buf(s2, c2),
             "enc3a": buf(s2, c3), "e3": buf(s2, c3), "p3": buf(s3, c3),
@@ -167,12 +173,16 @@ class UNetEngine:
 
     def _alloc_packed(self):
         self.engines: Dict[str, int] = {}
+        self._pack_tmp: Dict[str, torch.Tensor] = {}
         for name, conv, bn in self._conv_modules():
             cout, cin = conv.weight.shape[0], conv.weight.shape[1]
-            eng = self._engine_for(name, cin, cout)
+            cin_p = self.c0p if name == "enc1.0" else cin
+            eng = self._engine_for(name, cin_p, cout)
             self.engines[name] = eng
             wdt = torch.bfloat16 if eng == L.CONV_TC else torch.float32
-            self.packed[name] = torch.zeros(cout, 3, 3, cin, device=self.device, dtype=wdt)
+            self.packed[name] = torch.zeros(cout, 3, 3, cin_p, device=self.device, dtype=wdt)
+            if cin_p != cin:
+                self._pack_tmp[name] = torch.zeros(cout, 3, 3, cin, device=self.device, dtype=wdt)
             self.scale[name] = torch.ones(cout, device=self.device, dtype=torch.float32)
             self.shift[name] = torch.zeros(cout, device=self.device, dtype=torch.float32)
 
@@ -193,9 +203,11 @@ class UNetEngine:
         for name, conv, bn in self._conv_modules():
             w = conv.weight.detach()
             assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
-            pk = self.packed[name]
+            pk = self._pack_tmp.get(name, self.packed[name])
             L.check(lib.td_pack_conv_weight(w.data_ptr(), pk.data_ptr(), L.dtype_code(pk.dtype), w.shape[0],
                                             w.shape[1], st), "td_pack_conv_weight")
+            if pk is not self.packed[name]:
+                self.packed[name][..., :w.shape[1]].copy_(pk)      # zero-padded input channels (see c0p)
             if bn is None:
                 self.shift[name].copy_(conv.bias.detach())
             else:
@@ -263,7 +275,7 @@ class UNetEngine:
 
         ops.append(("embed", self._run_embed))
         add_conv("initial_conv", self.x_in, cfg.in_ch, bf["x0"], c0, False, x_nchw=True)
-        add_conv("enc1.0", bf["x0"], c0, bf["enc1a"], c1, True)
+        add_conv("enc1.0", bf["x0"], self.c0p, bf["enc1a"], c1, True)
         add_conv("enc1.3", bf["enc1a"], c1, bf["e1"], c1, True)
         add_pool("e1", "p1", S["s0"], c1)
         add_conv("enc2.0", bf["p1"], c1, bf["enc2a"], c2, True)
