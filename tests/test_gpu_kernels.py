@@ -277,7 +277,8 @@ def test_conv_direct_latent_boundary(dev, B, H, W):
                 got2 = ops.conv3x3(wide.to(dev), ops.pack_conv_weight(w2.to(dev)), None, b2.to(dev), False, 2,
                                    torch.float32, y_nchw=y_nchw, x_coff=8, cin=cin)
                 got2 = got2 if y_nchw else nchw(got2)
-                assert rel(got2.double(), want2) < 2e-6
+                # bf16 activations: mma.sync with the fp32 weights split into bf16 hi + lo (2^-17 relative per weight)
+                assert rel(got2.double(), want2) < (2e-6 if idt == torch.float32 else 8e-6)
 
 
 def test_conv_direct_first_last(dev):

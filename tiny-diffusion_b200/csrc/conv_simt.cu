@@ -315,6 +315,42 @@ conv3x3_firstn_kernel(const td_conv3x3_desc d) {
     }
 }
 
+// Second half of the contract-then-stencil kernels: out[j][r][w] = sum_t e[j * 9 + t][(r + dy_t, w + dx_t)] over the band's rows
+// [r0, r1); plane row 0 is image row q0.  One thread per pixel and pass: the index arithmetic and the border masks are shared
+// by the 9 * COUT shared-memory reads.
+template <int COUT>
+__device__ inline void lastn_stencil(const td_conv3x3_desc& d, const float* __restrict__ e, int plane, int b, int r0, int r1, int q0) {
+    const int H = d.height, W = d.width, nr = r1 - r0;
+    float* __restrict__ y = reinterpret_cast<float*>(d.y);
+    float sc[COUT], sh[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) {
+        sc[j] = d.scale ? __ldg(d.scale + j) : 1.f;
+        sh[j] = d.shift ? __ldg(d.shift + j) : 0.f;
+    }
+    for (int o = threadIdx.x; o < nr * W; o += blockDim.x) {
+        const int rr = o / W, w_ = o - rr * W, r = r0 + rr;
+        const float* ec = e + (r - q0) * W + w_;
+        bool ok[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int hh = r + t / 3 - 1, ww = w_ + t % 3 - 1;
+            ok[t] = hh >= 0 && hh < H && ww >= 0 && ww < W;
+        }
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (ok[t]) acc += ec[(j * 9 + t) * plane + (t / 3 - 1) * W + (t % 3 - 1)];
+            acc = fmaf(acc, sc[j], sh[j]);
+            if (d.relu) acc = fmaxf(acc, 0.f);
+            if (d.y_nchw) y[(((int64_t)b * COUT + j) * H + r) * W + w_] = acc;
+            else y[(((int64_t)b * H + r) * W + w_) * d.ldy + d.y_coff + j] = acc;
+        }
+    }
+}
+
 // conv3x3_lastn_kernel: NHWC input with cin channels -> COUT fp32 channels, contract-then-stencil.  The channel
 // contraction commutes with the spatial shift: e[j][t][s] = sum_c x[s, c] w[j, t, c] is computed once per source pixel
 // (the cin-channel vector is read exactly once; one thread owns two pixels and all 9 * COUT partials, weights are
@@ -369,23 +405,104 @@ conv3x3_lastn_kernel(const td_conv3x3_desc d, int BH, int bands) {
         }
     }
     __syncthreads();
-    const int nr = r1 - r0;
-    float* __restrict__ y = reinterpret_cast<float*>(d.y);
-    for (int o = threadIdx.x; o < COUT * nr * W; o += blockDim.x) {
-        const int w_ = o % W, t2 = o / W;
-        const int rr = t2 % nr, j = t2 / nr, r = r0 + rr;
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int hh = r + t / 3 - 1, ww = w_ + t % 3 - 1;
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) acc += e[(j * 9 + t) * plane + (hh - q0) * W + ww];
-        }
-        if (d.scale) acc *= d.scale[j];
-        if (d.shift) acc += d.shift[j];
-        if (d.relu) acc = fmaxf(acc, 0.f);
-        if (d.y_nchw) y[(((int64_t)b * COUT + j) * H + r) * W + w_] = acc;
-        else y[(((int64_t)b * H + r) * W + w_) * d.ldy + d.y_coff + j] = acc;
+    lastn_stencil<COUT>(d, e, plane, b, r0, r1, q0);
+}
+
+// bf16 activations: the same contract-then-stencil with the contraction on the tensor cores.  It is a [pixels x cin] x [cin x 36]
+// product -- far too narrow for a tcgen05 tile (N = 36) but a natural warp-level mma.sync.m16n8k16: one warp owns 16 pixels, A
+// fragments come straight from global memory (every 128-byte channel vector is read exactly once), the weights sit in shared
+// memory as a bf16 hi + lo pair (w = hi + lo to 2^-17, so the layer keeps its fp32 weights: two MMAs per fragment, still
+// 40x fewer issue slots than the FFMA loop), fp32 accumulators go to the shared-memory planes of the stencil.
+__device__ inline void mma_bf16_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int COUT, int KS>          // KS = cin / 16
+__global__ void __launch_bounds__(512)
+conv3x3_lastn_mma_kernel(const td_conv3x3_desc d, int BH, int bands, int plane) {
+    td::pdl_sync();
+    constexpr int Q = 9 * COUT, NT = (Q + 7) / 8, CIN = KS * 16, WS = CIN + 8;      // WS: padded row (conflict-free fragment loads)
+    extern __shared__ __align__(16) unsigned char lraw[];
+    __nv_bfloat16* whi = reinterpret_cast<__nv_bfloat16*>(lraw);      // [NT * 8][WS]
+    __nv_bfloat16* wlo = whi + NT * 8 * WS;
+    float* e = reinterpret_cast<float*>(wlo + NT * 8 * WS);           // [Q][plane]
+    const int H = d.height, W = d.width;
+    // The contraction does not care which physical channel sits at which logical k, so the channels are permuted to make the A
+    // fragments of TWO k-steps one 16-byte load per thread: thread t4 of a pixel row reads channels 32 kp + 8 t4 + [0, 8); they are
+    // the logical k = 2 t4 + {0, 1} and 8 + 2 t4 + {0, 1} of k-steps 2 kp and 2 kp + 1.  The weights are staged in that order.
+    for (int i = threadIdx.x; i < NT * 8 * CIN; i += blockDim.x) {
+        const int q = i / CIN, l = i - q * CIN;                 // l = logical position ks * 16 + k
+        const int ks = l >> 4, k = l & 15;
+        const int c = 32 * (ks >> 1) + ((k >> 1) & 3) * 8 + (ks & 1) * 4 + (k >> 3) * 2 + (k & 1);
+        const float w = q < Q ? __ldg(reinterpret_cast<const float*>(d.w) + q * CIN + c) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        whi[q * WS + l] = hi;
+        wlo[q * WS + l] = __float2bfloat16_rn(w - __bfloat162float(hi));
     }
+    __syncthreads();
+    const int b = blockIdx.x / bands, band = blockIdx.x - b * bands;
+    const int r0 = band * BH, r1 = min(r0 + BH, H);
+    const int q0 = max(r0 - 1, 0), q1 = min(r1 + 1, H);
+    const int npix = (q1 - q0) * W;
+    const __nv_bfloat16* __restrict__ xb =
+        reinterpret_cast<const __nv_bfloat16*>(d.x) + ((int64_t)b * H + q0) * W * d.ldx + d.x_coff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, t4 = lane & 3, nwarps = blockDim.x >> 5;
+    const int mtiles = (npix + 15) >> 4;
+    constexpr int MT = 8 / KS;                     // 16-pixel tiles per pass: all of their loads are in flight before the first MMA
+    // ldmatrix.x4 row address of this lane: matrices {hi k0.., hi k0+8.., lo k0.., lo k0+8..} of one (n-tile, k-step)
+    const uint32_t bfrag = (uint32_t)__cvta_generic_to_shared(((lane & 16) ? wlo : whi) + (lane & 7) * WS + ((lane >> 3) & 1) * 8);
+    for (int mt0 = warp * MT; mt0 < mtiles; mt0 += nwarps * MT) {
+        uint32_t a[MT][KS][4];
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+            const int p_lo = (mt0 + u) * 16 + gid, p_hi = p_lo + 8;
+            const __nv_bfloat16* xl = xb + (int64_t)min(p_lo, npix - 1) * d.ldx + t4 * 8;
+            const __nv_bfloat16* xh = xb + (int64_t)min(p_hi, npix - 1) * d.ldx + t4 * 8;
+#pragma unroll
+            for (int kp = 0; kp < KS / 2; ++kp) {
+                const uint4 vl = __ldg(reinterpret_cast<const uint4*>(xl + kp * 32));
+                const uint4 vh = __ldg(reinterpret_cast<const uint4*>(xh + kp * 32));
+                a[u][2 * kp][0] = vl.x; a[u][2 * kp][2] = vl.y; a[u][2 * kp + 1][0] = vl.z; a[u][2 * kp + 1][2] = vl.w;
+                a[u][2 * kp][1] = vh.x; a[u][2 * kp][3] = vh.y; a[u][2 * kp + 1][1] = vh.z; a[u][2 * kp + 1][3] = vh.w;
+            }
+        }
+        float acc[MT][NT][4];
+#pragma unroll
+        for (int u = 0; u < MT; ++u)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) acc[u][nt][0] = acc[u][nt][1] = acc[u][nt][2] = acc[u][nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t bh0, bh1, bl0, bl1;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(bh0), "=r"(bh1), "=r"(bl0), "=r"(bl1) : "r"(bfrag + (uint32_t)((nt * 8 * WS + ks * 16) * 2)));
+#pragma unroll
+                for (int u = 0; u < MT; ++u) {
+                    mma_bf16_m16n8k16(acc[u][nt], a[u][ks], bh0, bh1);
+                    mma_bf16_m16n8k16(acc[u][nt], a[u][ks], bl0, bl1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+            if (mt0 + u >= mtiles) break;
+            const int p_lo = (mt0 + u) * 16 + gid, p_hi = p_lo + 8;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int q = nt * 8 + t4 * 2;             // Q is even: q < Q implies q + 1 < Q
+                if (q < Q) {
+                    if (p_lo < npix) { e[q * plane + p_lo] = acc[u][nt][0]; e[(q + 1) * plane + p_lo] = acc[u][nt][1]; }
+                    if (p_hi < npix) { e[q * plane + p_hi] = acc[u][nt][2]; e[(q + 1) * plane + p_hi] = acc[u][nt][3]; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    lastn_stencil<COUT>(d, e, plane, b, r0, r1, q0);
 }
 
 // Rows per band of conv3x3_lastn_kernel (0: the geometry does not fit shared memory -> generic kernel).  A whole image
@@ -574,6 +691,24 @@ static int run_direct(const td_conv_plan* p, cudaStream_t s) {
     }
     if (d.cout == 4 && d.cin % 8 == 0) {
         const int bh = lastn_band_rows(d);
+        if (bh > 0 && d.x_dtype == TD_BF16 && (d.cin == 64 || d.cin == 128)) {
+            const int bands = (int)ceil_div(d.height, bh);
+            const int npix = std::min(bh + 2, d.height) * d.width;
+            const int plane = (npix + 15) / 16 * 16 + 4;                // == 4 mod 16: conflict-free accumulator stores
+            const size_t smem = (size_t)2 * 40 * (d.cin + 8) * 2 + (size_t)36 * plane * sizeof(float);
+            const int threads = std::min(512, std::max(64, (npix + 15) / 16 * 32));      // at most one warp per 16 pixels
+            static bool attr_mma = false;
+            if (!attr_mma) {
+                cudaFuncSetAttribute(conv3x3_lastn_mma_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                cudaFuncSetAttribute(conv3x3_lastn_mma_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                attr_mma = true;
+            }
+            if (smem <= (size_t)227 * 1024) {
+                if (d.cin == 64) td::launch(conv3x3_lastn_mma_kernel<4, 4>, td::LaunchCfg(d.batch * bands, threads, smem, s), d, bh, bands, plane);
+                else td::launch(conv3x3_lastn_mma_kernel<4, 8>, td::LaunchCfg(d.batch * bands, threads, smem, s), d, bh, bands, plane);
+                return launch_status("conv3x3_lastn_mma");
+            }
+        }
         if (bh > 0) {
             const int bands = (int)ceil_div(d.height, bh);
             const size_t smem = ((size_t)36 * d.cin + (size_t)36 * (bh + 2) * d.width) * sizeof(float);
