@@ -271,6 +271,11 @@ def _calibration(name, sd, inp, ac):
     return ref, cal
 
 
+# achieved on the B200 (fp32 engine, golden batch): 7.4e-4 / 2.9e-3 / 3.5e-3 (diffusion / conditional / laion); bf16 engine
+# 5.5e-2 / 5.9e-2 / 2.4e-1 against the reference's own bf16-autocast medians 1.1e-1 / 1.1e-1 / 2.6e-1
+MEDIAN_GRAD_TOL_FP32 = 1e-2
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["diffusion", "conditional_diffusion", "conditional_diffusion_laion"])
 def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
@@ -304,13 +309,15 @@ def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
     if "eps_train" in g:
         assert rel(pred.detach(), g["eps_train"]) < etol
     assert abs(float(loss) - float(loss_ref)) / float(loss_ref) < (1e-5 if precision == "fp32" else 1e-2)
-    bad = {}
+    bad, errs, cal_errs = {}, [], []
     for k, p in model.named_parameters():
         ref = grads_ref[k]
         if float(ref.norm()) < 1e-6:          # conv bias in front of a train-mode BN: mathematically zero
             assert float(p.grad.abs().max()) < 1e-5, k
             continue
         err = rel(p.grad, ref)
+        errs.append(err)
+        cal_errs.append(rel(grads_cal[k], ref))
         if precision == "fp32":
             tol = 1e-5 if k.startswith("final_conv") else 3e-2
         else:
@@ -318,6 +325,13 @@ def test_train_step_autograd_vs_oracle(dev, golden, name, precision):
         if err > tol:
             bad[k] = (err, tol)
     assert not bad, f"gradient mismatch (err, tol): {bad}"
+    # the per-tensor bound above is an upper bound sized for one ReLU-kink flip; the MEDIAN over the tensors is what a
+    # regression would move (fp32: fixed bound; bf16: 1.5x the reference's own bf16-autocast median)
+    med, med_cal = sorted(errs)[len(errs) // 2], sorted(cal_errs)[len(cal_errs) // 2]
+    print(f"[grad-parity] {name} {precision}: median rel-L2 {med:.3e}, max {max(errs):.3e} over {len(errs)} tensors "
+          f"(reference under bf16 autocast: median {med_cal:.3e})")
+    mtol = MEDIAN_GRAD_TOL_FP32 if precision == "fp32" else 1.5 * med_cal
+    assert med < mtol, f"median gradient rel-L2 {med:.3e} (bound {mtol:.3e})"
     # BatchNorm running statistics after one train-mode forward
     for k, v in stats_ref.items():
         got = dict(model.named_buffers())[k]
