@@ -745,7 +745,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tinydiff", choices=["tinydiff", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-reverse-steps", type=int, default=12)
+    ap.add_argument("--cpu-reverse-steps", type=int, default=48)
     ap.add_argument("--ref-reverse-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager cuDNN/ATen baseline on the GPU")
