@@ -34,6 +34,7 @@ struct TapeOp {                  // mirrored by tinydiff/dense.py (ctypes)
 
 constexpr int TP_THREADS = 256, TP_RT = 32, TP_NT = 16, TP_KMAX = 1024;
 constexpr int TP_PAD = 8;
+constexpr int TP_MAX_SMEM_OPS = 64;       // tapes up to this length are walked from shared memory
 constexpr int TP_SMEM = (TP_RT + TP_NT) * (TP_KMAX + TP_PAD) * 4;
 
 __device__ inline float tape_act(float v, int act) {
@@ -92,8 +93,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1)
 dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned long long* bar) {
     extern __shared__ __align__(16) float tp_smem[];
     float* const xs = tp_smem;                                   // [TP_RT][K + TP_PAD]
-    td::pdl_sync();
+    // The tape itself is host-written and constant: copy it to shared memory BEFORE the dependency wait (it overlaps the tail of the
+    // preceding kernel) so that fetching op i is not one more dependent global round trip in front of every op.
+    __shared__ __align__(16) unsigned char s_ops_raw[TP_MAX_SMEM_OPS * sizeof(TapeOp)];
     const int tid = threadIdx.x;
+    const bool ops_in_smem = n_ops <= TP_MAX_SMEM_OPS;
+    if (ops_in_smem) {
+        static_assert(sizeof(TapeOp) % 16 == 0, "TapeOp is copied as 16-byte vectors");
+        const int4* src = reinterpret_cast<const int4*>(ops);
+        int4* dst = reinterpret_cast<int4*>(s_ops_raw);
+        for (int i = tid; i < n_ops * (int)(sizeof(TapeOp) / 16); i += TP_THREADS) dst[i] = __ldg(src + i);
+    }
+    td::pdl_sync();
+    __syncthreads();
     unsigned long long bar_target;
     {
         unsigned long long c;
@@ -101,7 +113,7 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned lon
         bar_target = c / gridDim.x * gridDim.x;
     }
     for (int oi = 0; oi < n_ops; ++oi) {
-        const TapeOp op = ops[oi];
+        const TapeOp op = ops_in_smem ? reinterpret_cast<const TapeOp*>(s_ops_raw)[oi] : ops[oi];
         if (op.kind == 0) {
             // ---- Linear: tiles of 32 rows x 16 features over the grid; the whole K extent of a tile's operands is staged in
             // shared memory with asynchronous copies (one memory latency per op); the WEIGHT slice does not depend on earlier
@@ -130,6 +142,28 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned lon
                 }
                 w_staged = false;
                 stage_rows(xs, op.x + (long long)m0 * op.ldx, op.ldx, TP_RT, min(TP_RT, M - m0), op.K, vecx);
+                // the epilogue's operands (bias, folded BatchNorm, residual, gathered row) are requested now, beside the operand
+                // copies, instead of as a dependent round trip after the reduction
+                float e_bias[2] = {0.f, 0.f}, e_scale[2] = {1.f, 1.f}, e_shift[2] = {0.f, 0.f}, e_add[2] = {0.f, 0.f};
+                float e_gamma[2] = {1.f, 1.f}, e_beta[2] = {0.f, 0.f}, e_gat[2] = {0.f, 0.f};
+                {
+                    const int m = m0 + r;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int n = n0 + c + 8 * j;
+                        if (m >= M || n >= op.N) continue;
+                        if (op.bias) e_bias[j] = __ldg(op.bias + n);
+                        if (op.bn_mean) {         // eval-mode BatchNorm1d: (x - mean) * invstd * gamma + beta
+                            const float invstd = 1.f / sqrtf(__ldg(op.bn_var + n) + op.bn_eps);
+                            e_scale[j] = invstd;
+                            e_shift[j] = __ldg(op.bn_mean + n);
+                            e_gamma[j] = __ldg(op.bn_gamma + n);
+                            e_beta[j] = __ldg(op.bn_beta + n);
+                        }
+                        if (op.res) e_add[j] = __ldcg(op.res + (long long)m * op.ldr + n);
+                        if (op.gidx) e_gat[j] = __ldg(op.gtab + (long long)op.gidx[m] * op.ldt + n);
+                    }
+                }
                 cp_async_wait_all();
                 __syncthreads();
                 // 16 k-slices x (4 row groups x 4 column groups): a thread owns an 8 x 4 register tile over its slice of K (k = 4*ks +
@@ -186,15 +220,14 @@ dense_tape_kernel(const TapeOp* __restrict__ ops, int n_ops, int M, unsigned lon
                         float v = 0.f;
 #pragma unroll
                         for (int q = 0; q < 16; ++q) v += red[q * 512 + r * TP_NT + cl];
-                        v += op.bias ? __ldg(op.bias + n) : 0.f;
-                        if (op.bn_mean) {         // eval-mode BatchNorm1d (+ ReLU): (x - mean) * invstd * gamma + beta
-                            const float invstd = 1.f / sqrtf(__ldg(op.bn_var + n) + op.bn_eps);
-                            v = (v - __ldg(op.bn_mean + n)) * invstd * __ldg(op.bn_gamma + n) + __ldg(op.bn_beta + n);
+                        v += e_bias[j];
+                        if (op.bn_mean) {         // same operation order as before: (v - mean) * invstd * gamma + beta
+                            v = (v - e_shift[j]) * e_scale[j] * e_gamma[j] + e_beta[j];
                             if (op.bn_relu) v = fmaxf(v, 0.f);
                         }
                         v = tape_act(v, op.act);
-                        if (op.res) v += __ldcg(op.res + (long long)m * op.ldr + n);
-                        if (op.gidx) v += __ldg(op.gtab + (long long)op.gidx[m] * op.ldt + n);
+                        if (op.res) v += e_add[j];
+                        if (op.gidx) v += e_gat[j];
                         op.out[(long long)m * op.ldo + n] = v;
                     }
                 }
