@@ -465,6 +465,20 @@ int td_self_attention_fwd(const float* qkv, const float* x, const float* gamma, 
 int td_dense_tape_op_bytes(void);
 int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned long long* barrier, int max_ctas, void* stream);
 
+/* The same forward with thread-block clusters instead of a grid barrier (csrc/dense_cluster.cu): a cluster of 8 CTAs takes 8
+ * rows of the batch through the whole tape, activations replicated in the CTAs' shared memory (st.shared::cluster pushes +
+ * barrier.cluster), weight slices streamed from the L2 through a cp.async ring that runs ahead across ops.  ops: `n_ops`
+ * (<= max_ops) records of td_dense_cluster_op_bytes() bytes (layout: ClusterOp; activation operands are float offsets into
+ * the arena of `arena_floats` floats per CTA, assigned by the host for `rows` rows per cluster: td_dense_cluster_limits picks
+ * 8, or 9 when that saves a pass -- 128 rows on the 15 clusters a B200 keeps resident).  max_clusters: 0 = default. */
+int td_dense_cluster_op_bytes(void);
+int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops);
+int td_dense_cluster_run(const void* ops, int n_ops, int batch, int rows, int max_clusters, void* stream);
+/* tuning aid: 16 counters per CTA of the last launch made with TD_DENSE_CLUSTER_DBG=1 (globaltimer start / end, clock64 cycles
+ * in weight waits, FFMA chunks, output pushes, cluster barriers, row-wise ops, epilogue-operand requests, partial stores + CTA
+ * barrier, k-slice sum + epilogue math, 6 unused); synchronises the device */
+int td_dense_cluster_debug_counters(unsigned long long* host_out, int n);
+
 #ifdef __cplusplus
 }
 #endif

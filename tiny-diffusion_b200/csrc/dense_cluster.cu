@@ -1,0 +1,573 @@
+// Eval-mode forward of the dense denoisers (latent MLP latent_diffusion.py:107-128, length-1-sequence DiT
+// diffusion_transformer.py:81-109) at the reference batch: ONE kernel, thread-block clusters, no grid barrier.
+//
+// In eval mode every op of these models is independent per sample (Linear, LayerNorm, eval BatchNorm1d = per-feature affine,
+// residual adds, embedding gathers).  So the batch is cut into slices of 8 rows and a cluster of 8 CTAs takes one slice
+// through the WHOLE tape:
+//   * the slice's activations live in shared memory, replicated in every CTA of the cluster (an "arena" whose buffer offsets
+//     the host assigns by liveness); a Linear's output tile is pushed into all eight arenas with st.async (distributed shared
+//     memory), every 16-byte piece completing bytes on an mbarrier of the RECEIVING CTA: a CTA goes on as soon as the R x N x 4
+//     bytes of the op have landed in its own arena.  No cluster barrier between ops (barrier.cluster compiles to MEMBAR.ALL.GPU
+//     + UCGABAR + CCTL.IVALL and drains the weight copies in flight; the grid-barrier tape of dense_fused.cu paid four
+//     dependent L2 round trips per op: fence, arrival, observation, operand load);
+//   * CTA c of the cluster owns the features [c*fcp, (c+1)*fcp) of every Linear; its weight slice streams from the L2
+//     through a ring of stages in chunks of fcp rows x kc columns, one bulk copy (cp.async.bulk, mbarrier completion) per
+//     row.  The stream does not depend on activations, so it runs ahead ACROSS ops: the L2 -> shared-memory pipe never drains
+//     between layers;
+//   * row-wise ops (LayerNorm, add, time features, input load) are computed redundantly by every CTA on its own copy: no
+//     communication at all.
+// FFMA tile: a thread owns 4 features x 8 rows over a slice of the chunk's k range (one 16-byte weight read feeds 32 FMAs,
+// one broadcast activation read 16); the k-slices are summed in fixed order through shared memory, then bias / folded
+// BatchNorm1d / activation / residual / gathered embedding row in the epilogue, as in the tape kernel.
+#include <algorithm>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace td {
+
+struct ClusterOp {               // mirrored by tinydiff/dense.py (ctypes)
+    int kind;                    // 0 linear, 1 layernorm, 2 add, 3 time features, 4 load (global -> arena)
+    int N, K;
+    int act, accumulate, tmode, bn_relu;
+    int out_global;              // linear: the result goes to `gout` (global memory), not to the arena
+    int x_off, ldx;              // arena offsets / row strides in floats
+    int out_off, ldo;
+    int res_off, ldr;            // res_off < 0: no residual
+    int fcp;                     // linear: features per CTA (power of two, 4..128)
+    int kc;                      // linear: k extent of a weight chunk (multiple of 4); 0 = weights read straight from global memory
+    const float* w;              // linear: [N][K] row-major; layernorm: gamma
+    const float* bias;           // linear: [N] or NULL; layernorm: beta
+    const float* gx; long long gldx;      // load: global source
+    float* gout; long long gldo;
+    const long long* gidx; const float* gtab; long long ldt;
+    const float* bn_mean; const float* bn_var; const float* bn_gamma; const float* bn_beta;
+    float bn_eps, ln_eps;
+    const long long* t; const int* t_dev;
+};
+static_assert(sizeof(ClusterOp) % 16 == 0, "ClusterOp is copied as 16-byte vectors");
+
+constexpr int CK_THREADS = 256, CK_CL = 8;
+constexpr int CK_RMAX = 9;                                // rows per cluster: 8, or 9 when that saves a pass (128 rows on 15 clusters)
+constexpr int CK_STAGES = 3, CK_STAGE_FLOATS = 8704;      // 3 x 34 KB
+constexpr int CK_ARENA_FLOATS = 18432;                    // 72 KB
+constexpr int CK_RED_FLOATS = 256 * 4 * CK_RMAX + 256;    // [k-slices][rows][fcp] (+ one bank-shift pad per slice) whatever fcp is
+constexpr int CK_MAX_OPS = 64;
+constexpr int CK_SMEM = CK_MAX_OPS * (int)sizeof(ClusterOp) + (CK_ARENA_FLOATS + CK_STAGES * CK_STAGE_FLOATS + CK_RED_FLOATS) * 4;
+static_assert(CK_SMEM <= 227 * 1024, "dense_cluster_kernel: shared memory plan");
+
+__device__ inline float ck_act(float v, int act) {
+    switch (act) {
+        case TD_ACT_RELU: return fmaxf(v, 0.f);
+        case TD_ACT_SILU: return v / (1.f + expf(-v));
+        case TD_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        case TD_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+
+// one weight row (bytes % 16 == 0) global -> own shared memory, completing `bytes` on `bar`
+__device__ inline void ck_bulk_row(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ inline void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ inline uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ inline uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ inline uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ inline uint32_t map_to_rank(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+// asynchronous stores into a peer's (or the own) shared memory; the bytes complete on the RECEIVER's mbarrier `bar`
+__device__ inline void st_async_f32(uint32_t addr, float v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(__float_as_uint(v)), "r"(bar) : "memory");
+}
+__device__ inline void st_async_v4(uint32_t addr, float4 v, uint32_t bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)), "r"(bar)
+                 : "memory");
+}
+// wait for a phase of an mbarrier whose bytes are completed by peers of the cluster
+__device__ inline void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && ++spins > TD_SPIN_LIMIT) { printf("tinydiff: dense_cluster activation barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+    } while (!ok);
+}
+__device__ __noinline__ float4 ck_act4(float4 v, int act) {
+    v.x = ck_act(v.x, act); v.y = ck_act(v.y, act); v.z = ck_act(v.z, act); v.w = ck_act(v.w, act);
+    return v;
+}
+
+// Position in this CTA's weight stream: (pass over a row slice, op, chunk).  The producer side and the consumer side walk the
+// same sequence; ops that do not stream (non-linear, kc == 0, or no feature of the op belongs to this CTA) are skipped.
+struct ChunkCursor {
+    int pass, oi, ch;
+};
+__device__ inline bool ck_streams(const ClusterOp& op, int rank) { return op.kind == 0 && op.kc > 0 && rank * op.fcp < op.N; }
+__device__ inline bool ck_settle(ChunkCursor& c, const ClusterOp* ops, int n_ops, int n_pass, int rank) {
+    while (c.pass < n_pass) {
+        while (c.oi < n_ops) {
+            const ClusterOp& op = ops[c.oi];
+            if (ck_streams(op, rank) && c.ch * op.kc < op.K) return true;
+            ++c.oi;
+            c.ch = 0;
+        }
+        ++c.pass;
+        c.oi = 0;
+        c.ch = 0;
+    }
+    return false;
+}
+
+// request chunk `c` of this CTA's weight stream into `stage`: one bulk copy per weight row (thread = row), min(kc, K - k0)
+// columns, row stride kc + 4 floats (16-byte reads of 8 consecutive rows hit 32 distinct banks).  Rows of features past N are
+// not fetched: their accumulators are never stored.
+__device__ inline void ck_issue(const ChunkCursor& c, const ClusterOp* ops, int rank, float* stage, uint64_t* bar) {
+    const ClusterOp& op = ops[c.oi];
+    const int k0 = c.ch * op.kc;
+    const uint32_t row_bytes = (uint32_t)min(op.kc, op.K - k0) * 4u;
+    const int fbase = rank * op.fcp, nvalid = min(op.fcp, op.N - fbase);
+    if (threadIdx.x == 0) sm100::mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)nvalid);
+    // a warp issues its lanes' bulk copies one after another (uniform-register operands): the rows are dealt round-robin to the
+    // eight warps so that each issues fcp / 8 of them
+    const int row = (int)(threadIdx.x & 31) * (CK_THREADS / 32) + (int)(threadIdx.x >> 5);
+    if (row < nvalid) ck_bulk_row(stage + row * (op.kc + 4), op.w + (long long)(fbase + row) * op.K + k0, row_bytes, bar);
+}
+
+// tuning aid (TD_DENSE_CLUSTER_DBG=1): per CTA {globaltimer at start, at end, clock64 cycles in: weight-chunk waits, FFMA
+// chunks, k-slice reduction + epilogue + pushes, cluster barriers, row-wise ops}
+__device__ unsigned long long g_ck_dbg[kNumSMs * 16];
+__device__ inline unsigned long long ck_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define CK_T(var) do { if (dbg) { const long long _n = clock64(); var += _n - t_last; t_last = _n; } } while (0)
+
+template <int R>
+__global__ void __launch_bounds__(CK_THREADS, 1)
+dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int dbg) {
+    extern __shared__ __align__(16) unsigned char ck_smem[];
+    __shared__ __align__(8) uint64_t s_full[CK_STAGES];      // weight stage landed (bulk-copy bytes)
+    __shared__ __align__(8) uint64_t s_act[2];               // a Linear's output landed in THIS CTA's arena (peers' st.async bytes)
+    ClusterOp* const ops = reinterpret_cast<ClusterOp*>(ck_smem);
+    float* const arena = reinterpret_cast<float*>(ck_smem + CK_MAX_OPS * sizeof(ClusterOp));
+    float* const ring = arena + CK_ARENA_FLOATS;
+    float* const red = ring + CK_STAGES * CK_STAGE_FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_rank();
+    const int n_clusters = (int)cluster_count_x(), cid = (int)cluster_id_x();
+    const int n_slices = (M + R - 1) / R;
+    const int n_pass = cid < n_slices ? (n_slices - cid + n_clusters - 1) / n_clusters : 0;
+
+    {   // the tape is host-written and constant: copied before the dependency wait
+        const int4* src = reinterpret_cast<const int4*>(g_ops);
+        int4* dst = reinterpret_cast<int4*>(ops);
+        for (int i = tid; i < n_ops * (int)(sizeof(ClusterOp) / 16); i += CK_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < CK_STAGES; ++i) sm100::mbar_init(&s_full[i], 1);
+        sm100::mbar_init(&s_act[0], 1);
+        sm100::mbar_init(&s_act[1], 1);
+        sm100::fence_barrier_init();
+    }
+    td::pdl_sync();
+    __syncthreads();
+    const unsigned long long g_start = dbg ? ck_gtime() : 0ull;
+    long long t_last = dbg ? clock64() : 0, c_wait = 0, c_fma = 0, c_epi = 0, c_bar = 0, c_row = 0, c_e1 = 0, c_e2 = 0, c_pre = 0;
+
+    // weight stream prologue: CK_STAGES - 1 chunks in flight
+    ChunkCursor pc{0, 0, 0};
+    uint32_t p_stage = 0, c_stage = 0, c_phase = 0;
+#pragma unroll 1
+    for (int s = 0; s < CK_STAGES - 1; ++s) {
+        if (ck_settle(pc, ops, n_ops, n_pass, rank)) {
+            ck_issue(pc, ops, rank, ring + p_stage * CK_STAGE_FLOATS, &s_full[p_stage]);
+            ++pc.ch;
+        }
+        p_stage = p_stage + 1 == CK_STAGES ? 0 : p_stage + 1;
+    }
+    // the peers' mbarriers are initialised and their shared memory may be written
+    cluster_sync_all();
+    uint32_t act_n = 0;                                    // Linears pushed so far: barrier s_act[act_n & 1], parity (act_n >> 1) & 1
+    const uint32_t act0 = (uint32_t)__cvta_generic_to_shared(&s_act[0]);
+
+#pragma unroll 1
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int row0 = (cid + pass * n_clusters) * R;
+        if (pass > 0) cluster_sync_all();                  // every CTA of the cluster has left the previous slice
+        CK_T(c_bar);
+#pragma unroll 1
+        for (int oi = 0; oi < n_ops; ++oi) {
+            const ClusterOp& op = ops[oi];
+            if (op.kind == 0) {
+                const int fcp = op.fcp, nfg = fcp >> 2, nks = CK_THREADS / nfg;
+                const int kstride = R * fcp + (nfg >= 4 ? nfg : 0);    // floats between the k-slices of `red` (bank shift: conflict-free stores)
+                const int fbase = rank * fcp;
+                const bool mine = fbase < op.N;
+                // epilogue items of this thread: rows er0 and er0 + 256 / nfg, features fbase + 4*eg .. + 3 (256 % nfg == 0: the same
+                // features for both).  Their per-feature operands are REQUESTED now (raw values, no dependent use: the loads fly
+                // beside the weight chunks), combined after the reduction.
+                const int er0 = tid / nfg, eg = tid - er0 * nfg, er_step = CK_THREADS / nfg;
+                const int en = fbase + 4 * eg;
+                float e_bias[4] = {0.f, 0.f, 0.f, 0.f};
+                float e_var[4] = {1.f, 1.f, 1.f, 1.f}, e_mean[4] = {0.f, 0.f, 0.f, 0.f}, e_gamma[4] = {1.f, 1.f, 1.f, 1.f}, e_beta[4] = {0.f, 0.f, 0.f, 0.f};
+                long long e_gi0 = 0;
+                if (mine && er0 < R) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = min(en + j, op.N - 1);
+                        if (op.bias) e_bias[j] = __ldg(op.bias + n);
+                        if (op.bn_mean) {
+                            e_var[j] = __ldg(op.bn_var + n);
+                            e_mean[j] = __ldg(op.bn_mean + n);
+                            e_gamma[j] = __ldg(op.bn_gamma + n);
+                            e_beta[j] = __ldg(op.bn_beta + n);
+                        }
+                    }
+                    if (op.gidx) e_gi0 = __ldg(op.gidx + min(row0 + er0, M - 1));
+                }
+                CK_T(c_pre);
+                if (mine) {
+                    if (op.kc > 0) {
+                        const int fg = tid & (nfg - 1), ks = tid / nfg;
+                        const int stride = op.kc + 4;
+                        float acc[4][R];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
+                        const float* xbase = arena + op.x_off;
+                        const int ldx = op.ldx, K = op.K, kc = op.kc;
+                        const int wj = nfg * stride;
+#pragma unroll 1
+                        for (int k0 = 0; k0 < K; k0 += kc) {
+                            sm100::mbar_wait(&s_full[c_stage], c_phase);
+                            __syncthreads();                 // every thread is done with the stage refilled below
+                            CK_T(c_wait);
+                            if (ck_settle(pc, ops, n_ops, n_pass, rank)) {
+                                ck_issue(pc, ops, rank, ring + p_stage * CK_STAGE_FLOATS, &s_full[p_stage]);
+                                ++pc.ch;
+                            }
+                            p_stage = p_stage + 1 == CK_STAGES ? 0 : p_stage + 1;
+                            const float* wst = ring + c_stage * CK_STAGE_FLOATS + fg * stride;
+                            const int kq = min(kc, K - k0) >> 2;
+                            const float* xk = xbase + k0;
+#pragma unroll 1
+                            for (int q = ks; q < kq; q += nks) {
+                                float4 wv[4], xv[R];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(wst + j * wj + 4 * q);
+#pragma unroll
+                                for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(xk + r * ldx + 4 * q);
+#pragma unroll
+                                for (int r = 0; r < R; ++r)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].x, wv[j].x, acc[j][r]);
+#pragma unroll
+                                for (int r = 0; r < R; ++r)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].y, wv[j].y, acc[j][r]);
+#pragma unroll
+                                for (int r = 0; r < R; ++r)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].z, wv[j].z, acc[j][r]);
+#pragma unroll
+                                for (int r = 0; r < R; ++r)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].w, wv[j].w, acc[j][r]);
+                            }
+                            if (++c_stage == CK_STAGES) { c_stage = 0; c_phase ^= 1u; }
+                            CK_T(c_fma);
+                        }
+                        // partial sums of the k-slices: red[ks][row][feature]
+                        float* rk = red + ks * kstride + fg;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int r = 0; r < R; ++r) rk[r * fcp + nfg * j] = acc[j][r];
+                    } else {
+                        // weights straight from global memory (K not a multiple of 4, or an unaligned slice): thread = (row, feature)
+                        for (int e = tid; e < R * fcp; e += CK_THREADS) {
+                            const int r = e / fcp, fr = e - r * fcp;
+                            const int n = min(fbase + fr, op.N - 1);
+                            const float* wr = op.w + (long long)n * op.K;
+                            const float* xr = arena + op.x_off + r * op.ldx;
+                            float v = 0.f;
+                            for (int k = 0; k < op.K; ++k) v = fmaf(xr[k], __ldg(wr + k), v);
+                            red[r * fcp + fr] = v;
+                        }
+                    }
+                }
+                uint64_t* const my_act = &s_act[act_n & 1u];
+                const uint32_t act_parity = (act_n >> 1) & 1u;
+                if (!op.out_global && tid == 0) sm100::mbar_arrive_expect_tx(my_act, (uint32_t)(R * op.N) * 4u);
+                __syncthreads();
+                CK_T(c_e1);
+                if (mine) {
+                    const int nsl = op.kc > 0 ? nks : 1;
+                    const uint32_t bar_local = act0 + 8u * (act_n & 1u);
+#pragma unroll 1
+                    for (int er = er0; er < R; er += er_step) {
+                        const int em = row0 + er;
+                        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float* rp = red + er * fcp + 4 * eg;
+#pragma unroll 4
+                        for (int q = 0; q < nsl; ++q) {
+                            const float4 p = *reinterpret_cast<const float4*>(rp + q * kstride);
+                            s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+                        }
+                        float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float t = v[j] + e_bias[j];
+                            if (op.bn_mean) {
+                                t = (t - e_mean[j]) * (1.f / sqrtf(e_var[j] + op.bn_eps)) * e_gamma[j] + e_beta[j];
+                                if (op.bn_relu) t = fmaxf(t, 0.f);
+                            }
+                            v[j] = t;
+                        }
+                        if (op.act != TD_ACT_NONE) {
+                            const float4 a = ck_act4(make_float4(v[0], v[1], v[2], v[3]), op.act);
+                            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                        }
+                        if (op.res_off >= 0) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[j] += arena[op.res_off + er * op.ldr + min(en + j, op.N - 1)];
+                        }
+                        if (op.gidx) {
+                            const long long gi = er == er0 ? e_gi0 : __ldg(op.gidx + min(em, M - 1));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[j] += __ldg(op.gtab + gi * op.ldt + min(en + j, op.N - 1));
+                        }
+                        if (er == er0) CK_T(c_e2);
+                        if (op.out_global) {
+                            if (em < M)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (en + j < op.N) op.gout[(long long)em * op.gldo + en + j] = v[j];
+                        } else {
+                            const int o = op.out_off + er * op.ldo + en;
+                            const uint32_t local = (uint32_t)__cvta_generic_to_shared(arena + o);
+                            const bool vec = en + 3 < op.N && (o & 3) == 0;
+#pragma unroll
+                            for (int d = 0; d < CK_CL; ++d) {
+                                const uint32_t peer = (uint32_t)((rank + d) & (CK_CL - 1));
+                                const uint32_t dst = map_to_rank(local, peer), dbar = map_to_rank(bar_local, peer);
+                                if (vec) {
+                                    st_async_v4(dst, make_float4(v[0], v[1], v[2], v[3]), dbar);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (en + j < op.N) st_async_f32(dst + 4u * j, v[j], dbar);
+                                }
+                            }
+                        }
+                    }
+                }
+                CK_T(c_epi);
+                if (!op.out_global) {
+                    sm100::mbar_wait(my_act, act_parity);          // R x N x 4 bytes have landed in this CTA's arena (complete_tx by the peers' st.async)
+                    ++act_n;
+                    // a CTA that owns no feature of this op is not held back by its own pushes: realign the cluster (rare, tiny layers)
+                    if ((CK_CL - 1) * fcp >= op.N) cluster_sync_all();
+                }
+                __syncthreads();                                  // `red` and the row-wise scratch are free for the next op
+                CK_T(c_bar);
+                continue;
+            }
+            if (op.kind == 1) {
+                // LayerNorm on the CTA's own copy: a warp per row, the row in registers, two-pass (mean, then centred variance) like
+                // ATen with the lane-strided summation order of the other kernels
+                constexpr int LN_CACHE = 8;
+                if (op.N <= 32 * LN_CACHE) {
+                    float gv[LN_CACHE], bv[LN_CACHE];
+#pragma unroll
+                    for (int i = 0; i < LN_CACHE; ++i) {
+                        const int n = min(lane + 32 * i, op.N - 1);
+                        gv[i] = __ldg(op.w + n);
+                        bv[i] = __ldg(op.bias + n);
+                    }
+#pragma unroll 1
+                    for (int r = warp; r < R; r += CK_THREADS / 32) {
+                        const float* xr = arena + op.x_off + r * op.ldx;
+                        float* orow = arena + op.out_off + r * op.ldo;
+                        float xv[LN_CACHE];
+#pragma unroll
+                        for (int i = 0; i < LN_CACHE; ++i) xv[i] = lane + 32 * i < op.N ? xr[lane + 32 * i] : 0.f;
+                        float s = 0.f;
+#pragma unroll
+                        for (int i = 0; i < LN_CACHE; ++i) if (lane + 32 * i < op.N) s += xv[i];
+                        const float mean = warp_sum(s) / (float)op.N;
+                        float q = 0.f;
+#pragma unroll
+                        for (int i = 0; i < LN_CACHE; ++i)
+                            if (lane + 32 * i < op.N) { const float d = xv[i] - mean; q = fmaf(d, d, q); }
+                        const float rstd = 1.f / sqrtf(warp_sum(q) / (float)op.N + op.ln_eps);
+#pragma unroll
+                        for (int i = 0; i < LN_CACHE; ++i)
+                            if (lane + 32 * i < op.N) orow[lane + 32 * i] = (xv[i] - mean) * rstd * gv[i] + bv[i];
+                    }
+                } else {
+#pragma unroll 1
+                    for (int r = warp; r < R; r += CK_THREADS / 32) {
+                        const float* xr = arena + op.x_off + r * op.ldx;
+                        float* orow = arena + op.out_off + r * op.ldo;
+                        float s = 0.f;
+                        for (int n = lane; n < op.N; n += 32) s += xr[n];
+                        const float mean = warp_sum(s) / (float)op.N;
+                        float q = 0.f;
+                        for (int n = lane; n < op.N; n += 32) { const float d = xr[n] - mean; q = fmaf(d, d, q); }
+                        const float rstd = 1.f / sqrtf(warp_sum(q) / (float)op.N + op.ln_eps);
+                        for (int n = lane; n < op.N; n += 32) orow[n] = (xr[n] - mean) * rstd * __ldg(op.w + n) + __ldg(op.bias + n);
+                    }
+                }
+            } else if (op.kind == 2) {
+                for (int e = tid; e < R * op.N; e += CK_THREADS) {
+                    const int r = e / op.N, n = e - r * op.N;
+                    const float v = arena[op.x_off + r * op.ldx + n];
+                    float* o = arena + op.out_off + r * op.ldo + n;
+                    *o = op.accumulate ? *o + v : v;
+                }
+            } else if (op.kind == 3) {
+                const int width = op.tmode == 2 ? op.N : 1;
+                for (int e = tid; e < R * width; e += CK_THREADS) {
+                    const int r = e / width, j = e - r * width;
+                    const int m = min(row0 + r, M - 1);
+                    float tv = op.t ? (float)op.t[m] : (float)op.t_dev[0];
+                    if (op.tmode == 1) tv = tv / 1000.0f;
+                    float v = tv;
+                    if (op.tmode == 2) {
+                        const int half = op.N / 2;
+                        v = 0.f;
+                        if (j < 2 * half) {
+                            const int jj = (j < half) ? j : j - half;
+                            const float arg = tv * expf(-logf(10000.0f) * (float)jj / (float)(half - 1));
+                            v = (j < half) ? sinf(arg) : cosf(arg);
+                        }
+                    }
+                    arena[op.out_off + r * op.ldo + j] = v;
+                }
+            } else {
+                for (int e = tid; e < R * op.N; e += CK_THREADS) {
+                    const int r = e / op.N, n = e - r * op.N;
+                    const int m = row0 + r;
+                    arena[op.out_off + r * op.ldo + n] = m < M ? __ldcg(op.gx + (long long)m * op.gldx + n) : 0.f;
+                }
+            }
+            __syncthreads();
+            CK_T(c_row);
+        }
+    }
+    cluster_sync_all();          // no CTA leaves while a peer may still write into its shared memory
+    if (dbg && tid == 0 && blockIdx.x < kNumSMs) {
+        unsigned long long* d = g_ck_dbg + blockIdx.x * 16;
+        d[0] = g_start; d[1] = ck_gtime();
+        d[2] = c_wait; d[3] = c_fma; d[4] = c_epi; d[5] = c_bar; d[6] = c_row; d[7] = c_pre; d[8] = c_e1; d[9] = c_e2;
+    }
+}
+
+}  // namespace td
+
+using namespace td;
+
+extern "C" int td_dense_cluster_op_bytes(void) { return (int)sizeof(ClusterOp); }
+
+template <int R>
+static void ck_fill_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int clusters, cudaStream_t s) {
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(clusters * CK_CL);
+    cfg.blockDim = dim3(CK_THREADS);
+    cfg.dynamicSmemBytes = CK_SMEM;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CK_CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+}
+
+// Clusters of 8 CTAs (one CTA per SM, ~223 KB of shared memory each) the device keeps resident at once: 15 on a B200 (measured;
+// the GPCs do not all hold two such clusters).  Queried once; 15 when no device answers (tape construction on a CPU-only host).
+static int ck_max_active_clusters() {
+    static int cached = 0;
+    if (cached > 0) return cached;
+    int n = 0;
+    if (cudaFuncSetAttribute(dense_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM) == cudaSuccess &&
+        cudaFuncSetAttribute(dense_cluster_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0) == cudaSuccess) {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[2];
+        ck_fill_cfg<8>(cfg, attr, 16, nullptr);
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, dense_cluster_kernel<8>, &cfg) != cudaSuccess) n = 0;
+    }
+    (void)cudaGetLastError();
+    cached = n > 0 ? std::min(n, kNumSMs / CK_CL) : 15;
+    return cached;
+}
+
+// rows per cluster for a batch: 8, or 9 when that saves a pass over the weights (128 rows: 16 slices of 8 on 15 clusters = 2 passes)
+static int ck_rows(int batch) {
+    const int maxc = ck_max_active_clusters();
+    const int p8 = (int)ceil_div(ceil_div(batch, 8), maxc), p9 = (int)ceil_div(ceil_div(batch, 9), maxc);
+    return p9 < p8 ? 9 : 8;
+}
+
+extern "C" int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops) {
+    if (rows) *rows = ck_rows(batch > 0 ? batch : 1);
+    if (cluster) *cluster = CK_CL;
+    if (arena_floats) *arena_floats = CK_ARENA_FLOATS;
+    if (stage_floats) *stage_floats = CK_STAGE_FLOATS;
+    if (max_ops) *max_ops = CK_MAX_OPS;
+    return TD_OK;
+}
+
+template <int R>
+static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        TD_CUDA(cudaFuncSetAttribute(dense_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM));
+        configured = true;
+    }
+    int clusters = std::min((int)ceil_div(batch, R), ck_max_active_clusters());
+    if (max_clusters > 0) clusters = std::min(clusters, max_clusters);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    ck_fill_cfg<R>(cfg, attr, clusters, s);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("TD_DENSE_CLUSTER_DBG"); dbg = e ? atoi(e) : 0; }
+    if (dbg & 2) {
+        fprintf(stderr, "tinydiff: dense_cluster: batch %d, %d rows per cluster, %d clusters of %d (max active %d)\n", batch, R, clusters,
+                CK_CL, ck_max_active_clusters());
+        dbg &= ~2;
+    }
+    count_launch();
+    (void)cudaLaunchKernelEx(&cfg, dense_cluster_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+    return launch_status("dense_cluster");
+}
+
+extern "C" int td_dense_cluster_run(const void* ops, int n_ops, int batch, int rows, int max_clusters, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(ops && n_ops > 0 && n_ops <= CK_MAX_OPS && batch > 0, "td_dense_cluster_run: bad args");
+    TD_CHECK_ARG(rows == 8 || rows == 9, "td_dense_cluster_run: rows per cluster must be 8 or 9 (the tape's arena offsets were laid out for it)");
+    return rows == 9 ? ck_launch<9>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream)
+                     : ck_launch<8>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream);
+}
+
+// Tuning aid: the per-CTA counters of the last launch run with TD_DENSE_CLUSTER_DBG=1 (synchronises).
+extern "C" int td_dense_cluster_debug_counters(unsigned long long* host_out, int n) {
+    if (!host_out || n <= 0 || n > kNumSMs * 16) { td::set_error("td_dense_cluster_debug_counters: bad arguments"); return TD_ERR_ARG; }
+    TD_CUDA(cudaDeviceSynchronize());
+    TD_CUDA(cudaMemcpyFromSymbol(host_out, td::g_ck_dbg, (size_t)n * sizeof(unsigned long long)));
+    return TD_OK;
+}

@@ -36,7 +36,21 @@ class TapeOp(C.Structure):
                 ("t", _P), ("t_dev", _P)]
 
 
-FUSED_MAX_BATCH = 1024                # above this the per-layer GEMM kernels (tcgen05 tf32 at >= 2048) are the better shape
+class ClusterOp(C.Structure):
+    """One op of the cluster-resident eval forward (csrc/dense_cluster.cu ``ClusterOp``): activations are addressed by their
+    offset in the per-CTA shared-memory arena, not by pointer."""
+    _fields_ = [("kind", C.c_int), ("N", C.c_int), ("K", C.c_int), ("act", C.c_int), ("accumulate", C.c_int),
+                ("tmode", C.c_int), ("bn_relu", C.c_int), ("out_global", C.c_int),
+                ("x_off", C.c_int), ("ldx", C.c_int), ("out_off", C.c_int), ("ldo", C.c_int),
+                ("res_off", C.c_int), ("ldr", C.c_int), ("fcp", C.c_int), ("kc", C.c_int),
+                ("w", _P), ("bias", _P), ("gx", _P), ("gldx", C.c_longlong), ("gout", _P), ("gldo", C.c_longlong),
+                ("gidx", _P), ("gtab", _P), ("ldt", C.c_longlong),
+                ("bn_mean", _P), ("bn_var", _P), ("bn_gamma", _P), ("bn_beta", _P), ("bn_eps", C.c_float), ("ln_eps", C.c_float),
+                ("t", _P), ("t_dev", _P)]
+
+
+FUSED_MAX_BATCH = 1024
+CLUSTER_MAX_BATCH = 256               # up to here the cluster kernel (8 rows per cluster, <= 16 clusters) beats the grid-barrier tape                # above this the per-layer GEMM kernels (tcgen05 tf32 at >= 2048) are the better shape
 
 
 class DenseEngine:
@@ -257,9 +271,14 @@ class DenseEngine:
         self.fwd_flops = self.flops
         self.bwd_ops = self._build_backward() if self.training else []
         self._tapes = None
-        if (not self.training and self.B <= FUSED_MAX_BATCH and os.environ.get("TD_DENSE_FUSED", "1") != "0"
-                and all(op["w"].shape[1] <= 1024 for op in self._ops if op["kind"] == "linear")):      # K staged whole in smem
-            self._build_tapes()
+        self._ctapes = None
+        mode = os.environ.get("TD_DENSE_FUSED", "1")       # 0: one launch per op, 1: cluster kernel / tape kernel, 2: tape kernel only
+        if not self.training and mode != "0":
+            if self.B <= CLUSTER_MAX_BATCH and mode != "2":
+                self._build_cluster_tapes()
+            if (self._ctapes is None and self.B <= FUSED_MAX_BATCH
+                    and all(op["w"].shape[1] <= 1024 for op in self._ops if op["kind"] == "linear")):      # K staged whole in smem
+                self._build_tapes()
 
     # ------------------------------------------------------------------ fused eval-mode forward (one persistent kernel)
     def _build_tapes(self):
@@ -349,7 +368,165 @@ class DenseEngine:
         self._tape_bar = torch.zeros(1, device=self.device, dtype=torch.int64)
         self._tapes = {False: make(False), True: make(True)}
 
+    # ------------------------------------------------------------------ cluster-resident eval forward (csrc/dense_cluster.cu)
+    def _build_cluster_tapes(self):
+        """Compile the declared ops for ``dense_cluster_kernel``: every activation buffer gets an offset in the per-CTA
+        shared-memory arena (first-fit by liveness), buffers the tape reads but never writes are loaded from global memory
+        first, and the op that writes ``eps`` stores to global memory.  A Linear ends with a cluster barrier (its output
+        is pushed into the peers' arenas); an arena region is only reused for an op's output when its previous owner was
+        last touched BEFORE the preceding barrier -- a fast CTA may push a Linear's output while a slow peer still runs
+        the row-wise ops in front of that Linear.  Leaves ``_ctapes`` None when the model does not fit (the grid-barrier
+        tape then takes over)."""
+        lib = self.lib
+        assert int(lib.td_dense_cluster_op_bytes()) == C.sizeof(ClusterOp), "ClusterOp layout mismatch"
+        lim = [C.c_int() for _ in range(5)]
+        L.check(lib.td_dense_cluster_limits(self.B, *[C.byref(v) for v in lim]), "td_dense_cluster_limits")
+        R, CL, ARENA, STAGE, MAX_OPS = (int(v.value) for v in lim)
+        ops = list(self._ops)
+        fused_bn = {}
+        for i, op in enumerate(ops):
+            if op["kind"] == "bn" and i > 0 and ops[i - 1]["kind"] == "linear" and ops[i - 1]["out"] == op["x"] \
+                    and ops[i - 1]["act"] == L.ACT_NONE and ops[i - 1]["res"] is None and ops[i - 1]["gather"] is None:
+                fused_bn[i - 1] = op
+        skip = {id(v) for v in fused_bn.values()}
+        # abstract records: (kind, reads, write, payload)
+        recs = []
+        for i, op in enumerate(ops):
+            if id(op) in skip:
+                continue
+            k = op["kind"]
+            if k == "time":
+                recs.append({"kind": 3, "reads": [], "write": op["out"], "op": op})
+            elif k == "linear":
+                bn = fused_bn.get(i)
+                dst = bn["out"] if bn is not None else op["out"]
+                recs.append({"kind": 0, "reads": [m for m in (op["x"], op["res"]) if m is not None], "write": dst, "op": op, "bn": bn})
+            elif k == "ln":
+                recs.append({"kind": 1, "reads": [op["x"]], "write": op["out"], "op": op})
+            elif k in ("copy", "drop"):
+                if op["x"] == op["out"]:
+                    continue
+                reads = [op["x"]] + ([op["out"]] if op.get("acc", 0) else [])
+                recs.append({"kind": 2, "reads": reads, "write": op["out"], "op": op})
+            else:                                           # stand-alone BatchNorm1d: not declared by either model
+                return
+        # buffers read before any op wrote them come from global memory
+        written, loads = set(), []
+        for r in recs:
+            for m in r["reads"]:
+                if m[0] not in written and m[0] not in [l["write"][0] for l in loads]:
+                    loads.append({"kind": 4, "reads": [], "write": self.full(m[0]), "op": None})
+            written.add(r["write"][0])
+        recs = loads + recs
+        if len(recs) > MAX_OPS:
+            return
+        for j, r in enumerate(recs):
+            r["global"] = r["kind"] == 0 and r["write"][0] == "eps"
+            if r["write"][0] == "eps" and (not r["global"] or j != len(recs) - 1 or r["write"] != self.full("eps")):
+                return
+        if any(m[0] == "eps" for r in recs for m in r["reads"]) or not recs[-1]["global"]:
+            return
+        # epochs: ops between two cluster barriers
+        epoch, e = [], 0
+        for r in recs:
+            epoch.append(e)
+            if r["kind"] == 0 and not r["global"]:
+                e += 1
+        last_use, first_def = {}, {}
+        for j, r in enumerate(recs):
+            for m in r["reads"] + [r["write"]]:
+                last_use[m[0]] = j
+            first_def.setdefault(r["write"][0], j)
+        ld = {n: (w + 3) // 4 * 4 for n, w in self.widths.items()}
+        base, live = {}, []                                  # live: (offset, size, name)
+        for j, r in enumerate(recs):
+            name = r["write"][0]
+            if name == "eps" or name in base:
+                continue
+            live = [b for b in live if epoch[last_use[b[2]]] >= epoch[j]]
+            size, off = R * ld[name], 0
+            for b in sorted(live):
+                if off + size <= b[0]:
+                    break
+                off = max(off, b[0] + b[1])
+            if off + size > ARENA:
+                return
+            base[name] = off
+            live.append((off, size, name))
+
+        def make(use_t_dev: bool):
+            tape = []
+            for r in recs:
+                t = ClusterOp()
+                t.kind, t.res_off = r["kind"], -1
+                wname, c0, c1 = r["write"]
+                if r["global"]:
+                    out = self.val(r["write"])
+                    t.out_global, t.gout, t.gldo = 1, out.data_ptr(), out.stride(0)
+                else:
+                    t.out_off, t.ldo = base[wname] + c0, ld[wname]
+                op = r["op"]
+                if r["kind"] == 4:
+                    src = self.bufs[wname]
+                    t.N, t.gx, t.gldx = c1 - c0, src.data_ptr(), src.stride(0)
+                elif r["kind"] == 3:
+                    t.N, t.tmode = c1 - c0, self.emb_mode
+                    t.t = None if use_t_dev else self.t_in.data_ptr()
+                    t.t_dev = self.t_dev.data_ptr()
+                elif r["kind"] == 0:
+                    w, b = op["w"], op["b"]
+                    r0, r1 = op["rows"] if op["rows"] else (0, w.shape[0])
+                    N, K = r1 - r0, w.shape[1]
+                    xn, x0, x1 = op["x"]
+                    assert x1 - x0 == K and c1 - c0 == N
+                    t.N, t.K, t.act = N, K, op["act"]
+                    t.x_off, t.ldx = base[xn] + x0, ld[xn]
+                    t.w = w.data_ptr() + 4 * r0 * K
+                    t.bias = (b.data_ptr() + 4 * r0) if b is not None else None
+                    fcp = 4
+                    while fcp * CL < N:
+                        fcp *= 2
+                    if fcp > 128:
+                        return None
+                    t.fcp = fcp
+                    kc = min(K, (STAGE // fcp - 4) // 32 * 32)
+                    t.kc = kc if (K % 4 == 0 and t.w % 16 == 0 and t.x_off % 4 == 0 and kc >= 4) else 0
+                    if r["bn"] is not None:
+                        m = r["bn"]["bn"]
+                        t.bn_mean, t.bn_var = m.running_mean.data_ptr(), m.running_var.data_ptr()
+                        t.bn_gamma, t.bn_beta = m.weight.data_ptr(), m.bias.data_ptr()
+                        t.bn_eps, t.bn_relu = float(m.eps), int(r["bn"]["relu"])
+                    if op["res"] is not None:
+                        rn, q0, _ = op["res"]
+                        t.res_off, t.ldr = base[rn] + q0, ld[rn]
+                    if op["gather"] is not None:
+                        gi, gt = op["gather"]
+                        t.gidx, t.gtab, t.ldt = gi.data_ptr(), gt.data_ptr(), gt.shape[-1]
+                elif r["kind"] == 1:
+                    ln = op["ln"]
+                    xn, x0, x1 = op["x"]
+                    t.N, t.x_off, t.ldx = x1 - x0, base[xn] + x0, ld[xn]
+                    t.w, t.bias, t.ln_eps = ln.weight.data_ptr(), ln.bias.data_ptr(), float(ln.eps)
+                else:
+                    xn, x0, x1 = op["x"]
+                    t.N, t.accumulate = x1 - x0, int(op.get("acc", 0))
+                    t.x_off, t.ldx = base[xn] + x0, ld[xn]
+                tape.append(t)
+            raw = b"".join(bytes(t) for t in tape)
+            return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device), len(tape)
+
+        tapes = {False: make(False), True: make(True)}
+        if tapes[False] is None or tapes[True] is None:
+            return
+        self._ctapes = tapes
+        self._ctape_rows = R
+        self._ctape_arena = max(b + R * ld[n] for n, b in base.items())
+
     def _launch_tape(self, st: int) -> None:
+        if self._ctapes is not None:
+            buf, n = self._ctapes[bool(self.use_t_dev)]
+            L.check(self.lib.td_dense_cluster_run(buf.data_ptr(), n, self.B, self._ctape_rows, 0, st), "td_dense_cluster_run")
+            return
         buf, n, _ = self._tapes[bool(self.use_t_dev)]
         L.check(self.lib.td_dense_tape_run(buf.data_ptr(), n, self.B, self._tape_bar.data_ptr(), 0, st), "td_dense_tape_run")
 
@@ -534,7 +711,7 @@ class DenseEngine:
 
     def launch_forward(self) -> None:
         st = L.stream_ptr()
-        if self._tapes is not None:            # eval mode at the reference batch sizes: ONE persistent kernel (dense_fused.cu)
+        if self._tapes is not None or self._ctapes is not None:      # eval mode at the reference batch sizes: ONE kernel (dense_cluster.cu / dense_fused.cu)
             self._launch_tape(st)
             return
         for _, fn in self.fwd_ops:
