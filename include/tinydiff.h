@@ -472,8 +472,12 @@ int td_dense_tape_run(const void* ops, int n_ops, int batch, unsigned long long*
  * the arena of `arena_floats` floats per CTA, assigned by the host for `rows` rows per cluster: td_dense_cluster_limits picks
  * 8, or 9 when that saves a pass -- 128 rows on the 15 clusters a B200 keeps resident).  max_clusters: 0 = default. */
 int td_dense_cluster_op_bytes(void);
-int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops);
+int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops,
+                            int* max_clusters);
 int td_dense_cluster_run(const void* ops, int n_ops, int batch, int rows, int max_clusters, void* stream);
+/* 128-byte tensor map (written to HOST memory) of one Linear's fp32 weight [n][k] for the kernel's weight stream: TMA boxes of
+ * 32 floats x fcp rows, SWIZZLE_128B.  The caller keeps a 64-byte aligned device copy and points ClusterOp::tmap at it. */
+int td_dense_cluster_weight_map(const float* w, int n, int k, int fcp, void* map_out_host);
 /* tuning aid: 16 counters per CTA of the last launch made with TD_DENSE_CLUSTER_DBG=1 (globaltimer start / end, clock64 cycles
  * in weight waits, FFMA chunks, output pushes, cluster barriers, row-wise ops, epilogue-operand requests, partial stores + CTA
  * barrier, k-slice sum + epilogue math, 6 unused); synchronises the device */

@@ -100,6 +100,48 @@ def test_train_step_autograd_vs_oracle(dev, golden, name):
 
 
 @pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+@pytest.mark.parametrize("B,passes", [(128, "1"), (8, "1"), (135, "1"), (1, "1"), (200, "0"), (251, "0")])
+def test_cluster_kernel_vs_oracle(dev, name, B, passes, monkeypatch):
+    """The cluster-resident eval forward (csrc/dense_cluster.cu) against the CPU oracle at the benchmark batch (9 rows per cluster
+    on 15 clusters), at ragged / tiny batches, and -- forced, the engine would pick the tape there -- at batches that take a
+    second pass over the weights; the grid-barrier tape and the one-launch-per-op path must agree with it to rounding."""
+    from tinydiff.dense import DenseEngine
+    mod, model, sd = build(name, dev, **KW[name])
+    inp = make_inputs(name, B, seed=11)
+    want = FWD[name](sd, inp["x0"], inp["t"], inp["cond"], None)
+    outs = {}
+    for mode in ("1", "2", "0"):
+        monkeypatch.setenv("TD_DENSE_FUSED", mode)
+        monkeypatch.setenv("TD_DENSE_CLUSTER_PASSES", passes)
+        e = DenseEngine(model, B, dev, False, model.in_dim, model.emb_mode)
+        model._declare(e)
+        e.build()
+        assert (e._ctapes is not None) == (mode == "1"), "the cluster kernel must be the path that runs"
+        e.load_inputs(inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+        for _ in range(2):                       # twice: the mbarrier phases / weight ring must be reusable across launches
+            e.launch_forward()
+        outs[mode] = e.eps.clone()
+    assert rel(outs["1"], want) < 1e-5
+    assert rel(outs["1"], outs["2"]) < 2e-6 and rel(outs["1"], outs["0"]) < 2e-6
+
+
+def test_cluster_kernel_is_default_at_reference_batch(dev):
+    """At the reference batch the public forward runs the cluster kernel (one launch), above one pass the tape."""
+    from tinydiff import _lib as L
+    mod, model, sd = build("diffusion_transformer", dev, dropout=0.0)
+    lib = L.load()
+    for B, want_cluster in ((128, True), (200, False)):
+        inp = make_inputs("diffusion_transformer", B)
+        with torch.no_grad():
+            model(inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+            n0 = int(lib.td_launch_count())
+            model(inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+        assert int(lib.td_launch_count()) - n0 == 1
+        eng = model.engine(B, dev, training=False)
+        assert (eng._ctapes is not None) == want_cluster and (eng._tapes is not None) == (not want_cluster)
+
+
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
 def test_sampler_vs_oracle(dev, name):
     """Reverse loop with injected x_T / z (short schedule) against the oracle's sample_loop."""
     mod, model, sd = build(name, dev, **KW[name])

@@ -128,9 +128,10 @@ _SIGS = {
     "td_dense_tape_op_bytes": (C.c_int, []),
     "td_dense_tape_run": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "td_dense_cluster_op_bytes": (C.c_int, []),
-    "td_dense_cluster_limits": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
+    "td_dense_cluster_limits": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P]),
     "td_dense_cluster_run": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_dense_cluster_debug_counters": (C.c_int, [_P, C.c_int]),
+    "td_dense_cluster_weight_map": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_resize_bilinear_bwd": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, _P]),

@@ -11,9 +11,11 @@
 //     + UCGABAR + CCTL.IVALL and drains the weight copies in flight; the grid-barrier tape of dense_fused.cu paid four
 //     dependent L2 round trips per op: fence, arrival, observation, operand load);
 //   * CTA c of the cluster owns the features [c*fcp, (c+1)*fcp) of every Linear; its weight slice streams from the L2
-//     through a ring of stages in chunks of fcp rows x kc columns, one bulk copy (cp.async.bulk, mbarrier completion) per
-//     row.  The stream does not depend on activations, so it runs ahead ACROSS ops: the L2 -> shared-memory pipe never drains
-//     between layers;
+//     through a ring of stages in chunks of fcp rows x kc columns: TMA boxes of 32 floats x fcp rows (SWIZZLE_128B: eight
+//     consecutive rows read the same k without a bank conflict, no padding), mbarrier completion.  (One cp.async per 16 bytes
+//     and one bulk copy per row were both measured: 10-17 % of the kernel's issue slots went into requesting weights.)  The
+//     stream does not depend on activations, so it runs ahead ACROSS ops: the L2 -> shared-memory pipe never drains between
+//     layers;
 //   * row-wise ops (LayerNorm, add, time features, input load) are computed redundantly by every CTA on its own copy: no
 //     communication at all.
 // FFMA tile: a thread owns 4 features x 8 rows over a slice of the chunk's k range (one 16-byte weight read feeds 32 FMAs,
@@ -22,7 +24,7 @@
 #include <algorithm>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "conv_plan.h"
 #include "sm100.cuh"
 
 namespace td {
@@ -36,9 +38,11 @@ struct ClusterOp {               // mirrored by tinydiff/dense.py (ctypes)
     int out_off, ldo;
     int res_off, ldr;            // res_off < 0: no residual
     int fcp;                     // linear: features per CTA (power of two, 4..128)
-    int kc;                      // linear: k extent of a weight chunk (multiple of 4); 0 = weights read straight from global memory
+    int kc;                      // linear: k extent of a weight chunk (multiple of 32: TMA boxes of 32 floats x fcp rows); 0 = weights read straight from global memory
     const float* w;              // linear: [N][K] row-major; layernorm: gamma
     const float* bias;           // linear: [N] or NULL; layernorm: beta
+    const void* tmap;            // linear with kc > 0: device copy of the weight's tensor map (td_dense_cluster_weight_map), 64-byte aligned
+    long long pad_;
     const float* gx; long long gldx;      // load: global source
     float* gout; long long gldo;
     const long long* gidx; const float* gtab; long long ldt;
@@ -53,9 +57,9 @@ constexpr int CK_RMAX = 9;                                // rows per cluster: 8
 constexpr int CK_STAGES = 3, CK_STAGE_FLOATS = 8704;      // 3 x 34 KB
 constexpr int CK_ARENA_FLOATS = 18432;                    // 72 KB
 constexpr int CK_RED_FLOATS = 256 * 4 * CK_RMAX + 256;    // [k-slices][rows][fcp] (+ one bank-shift pad per slice) whatever fcp is
-constexpr int CK_MAX_OPS = 64;
-constexpr int CK_SMEM = CK_MAX_OPS * (int)sizeof(ClusterOp) + (CK_ARENA_FLOATS + CK_STAGES * CK_STAGE_FLOATS + CK_RED_FLOATS) * 4;
-static_assert(CK_SMEM <= 227 * 1024, "dense_cluster_kernel: shared memory plan");
+constexpr int CK_MAX_OPS = 56;
+constexpr int CK_SMEM = 1024 + CK_MAX_OPS * (int)sizeof(ClusterOp) + (CK_ARENA_FLOATS + CK_STAGES * CK_STAGE_FLOATS + CK_RED_FLOATS) * 4;   // 1 KB: alignment of the base
+static_assert(CK_SMEM + 64 <= 227 * 1024 && (CK_STAGE_FLOATS * 4) % 1024 == 0, "dense_cluster_kernel: shared memory plan");
 
 __device__ inline float ck_act(float v, int act) {
     switch (act) {
@@ -67,13 +71,6 @@ __device__ inline float ck_act(float v, int act) {
     }
 }
 
-// one weight row (bytes % 16 == 0) global -> own shared memory, completing `bytes` on `bar`
-__device__ inline void ck_bulk_row(float* smem_dst, const float* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
 __device__ inline void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -130,19 +127,16 @@ __device__ inline bool ck_settle(ChunkCursor& c, const ClusterOp* ops, int n_ops
     return false;
 }
 
-// request chunk `c` of this CTA's weight stream into `stage`: one bulk copy per weight row (thread = row), min(kc, K - k0)
-// columns, row stride kc + 4 floats (16-byte reads of 8 consecutive rows hit 32 distinct banks).  Rows of features past N are
-// not fetched: their accumulators are never stored.
+// request chunk `c` of this CTA's weight stream into `stage`: boxes of 32 floats x fcp rows (box b at stage + b * fcp * 32 floats),
+// warp b issues box b.  Rows past N and columns past K are zero-filled by TMA.
 __device__ inline void ck_issue(const ChunkCursor& c, const ClusterOp* ops, int rank, float* stage, uint64_t* bar) {
     const ClusterOp& op = ops[c.oi];
     const int k0 = c.ch * op.kc;
-    const uint32_t row_bytes = (uint32_t)min(op.kc, op.K - k0) * 4u;
-    const int fbase = rank * op.fcp, nvalid = min(op.fcp, op.N - fbase);
-    if (threadIdx.x == 0) sm100::mbar_arrive_expect_tx(bar, row_bytes * (uint32_t)nvalid);
-    // a warp issues its lanes' bulk copies one after another (uniform-register operands): the rows are dealt round-robin to the
-    // eight warps so that each issues fcp / 8 of them
-    const int row = (int)(threadIdx.x & 31) * (CK_THREADS / 32) + (int)(threadIdx.x >> 5);
-    if (row < nvalid) ck_bulk_row(stage + row * (op.kc + 4), op.w + (long long)(fbase + row) * op.K + k0, row_bytes, bar);
+    const int nb = (min(op.kc, op.K - k0) + 31) >> 5;
+    if (threadIdx.x == 0) sm100::mbar_arrive_expect_tx(bar, (uint32_t)(nb * op.fcp) * 128u);
+    if ((threadIdx.x & 31) == 0)
+        for (int b = (int)(threadIdx.x >> 5); b < nb; b += CK_THREADS / 32)
+            sm100::tma_load_2d(stage + b * op.fcp * 32, reinterpret_cast<const CUtensorMap*>(op.tmap), bar, k0 + 32 * b, rank * op.fcp);
 }
 
 // tuning aid (TD_DENSE_CLUSTER_DBG=1): per CTA {globaltimer at start, at end, clock64 cycles in: weight-chunk waits, FFMA
@@ -157,10 +151,11 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
     extern __shared__ __align__(16) unsigned char ck_smem[];
     __shared__ __align__(8) uint64_t s_full[CK_STAGES];      // weight stage landed (bulk-copy bytes)
     __shared__ __align__(8) uint64_t s_act[2];               // a Linear's output landed in THIS CTA's arena (peers' st.async bytes)
-    ClusterOp* const ops = reinterpret_cast<ClusterOp*>(ck_smem);
-    float* const arena = reinterpret_cast<float*>(ck_smem + CK_MAX_OPS * sizeof(ClusterOp));
-    float* const ring = arena + CK_ARENA_FLOATS;
-    float* const red = ring + CK_STAGES * CK_STAGE_FLOATS;
+    unsigned char* const base = ck_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(ck_smem) & 1023u)) & 1023u);   // swizzle = f(address)
+    float* const ring = reinterpret_cast<float*>(base);             // stages are 1024-byte aligned (34 KB each)
+    float* const arena = ring + CK_STAGES * CK_STAGE_FLOATS;
+    float* const red = arena + CK_ARENA_FLOATS;
+    ClusterOp* const ops = reinterpret_cast<ClusterOp*>(red + CK_RED_FLOATS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_rank();
     const int n_clusters = (int)cluster_count_x(), cid = (int)cluster_id_x();
@@ -196,6 +191,12 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
     }
     // the peers' mbarriers are initialised and their shared memory may be written
     cluster_sync_all();
+    // gamma / beta of the NEXT LayerNorm (<= 256 features) are requested while the Linear in front of it runs
+    constexpr int LN_CACHE = 8;
+    float ln_g[LN_CACHE], ln_b[LN_CACHE];
+    int ln_for = -1;                                       // op index ln_g / ln_b were requested for
+#pragma unroll
+    for (int i = 0; i < LN_CACHE; ++i) { ln_g[i] = 0.f; ln_b[i] = 0.f; }
     uint32_t act_n = 0;                                    // Linears pushed so far: barrier s_act[act_n & 1], parity (act_n >> 1) & 1
     const uint32_t act0 = (uint32_t)__cvta_generic_to_shared(&s_act[0]);
 
@@ -208,14 +209,14 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
         for (int oi = 0; oi < n_ops; ++oi) {
             const ClusterOp& op = ops[oi];
             if (op.kind == 0) {
-                const int fcp = op.fcp, nfg = fcp >> 2, nks = CK_THREADS / nfg;
+                const int fcp = op.fcp, nfg = fcp >> 2, lg_nfg = 31 - __clz(nfg), nks = CK_THREADS >> lg_nfg;      // fcp is a power of two
                 const int kstride = R * fcp + (nfg >= 4 ? nfg : 0);    // floats between the k-slices of `red` (bank shift: conflict-free stores)
                 const int fbase = rank * fcp;
                 const bool mine = fbase < op.N;
                 // epilogue items of this thread: rows er0 and er0 + 256 / nfg, features fbase + 4*eg .. + 3 (256 % nfg == 0: the same
                 // features for both).  Their per-feature operands are REQUESTED now (raw values, no dependent use: the loads fly
                 // beside the weight chunks), combined after the reduction.
-                const int er0 = tid / nfg, eg = tid - er0 * nfg, er_step = CK_THREADS / nfg;
+                const int er0 = tid >> lg_nfg, eg = tid & (nfg - 1), er_step = nks;
                 const int en = fbase + 4 * eg;
                 float e_bias[4] = {0.f, 0.f, 0.f, 0.f};
                 float e_var[4] = {1.f, 1.f, 1.f, 1.f}, e_mean[4] = {0.f, 0.f, 0.f, 0.f}, e_gamma[4] = {1.f, 1.f, 1.f, 1.f}, e_beta[4] = {0.f, 0.f, 0.f, 0.f};
@@ -234,11 +235,20 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                     }
                     if (op.gidx) e_gi0 = __ldg(op.gidx + min(row0 + er0, M - 1));
                 }
+                if (oi + 1 < n_ops && ops[oi + 1].kind == 1 && ops[oi + 1].N <= 32 * LN_CACHE) {
+                    const ClusterOp& ln = ops[oi + 1];
+#pragma unroll
+                    for (int i = 0; i < LN_CACHE; ++i) {
+                        const int n = min(lane + 32 * i, ln.N - 1);
+                        ln_g[i] = __ldg(ln.w + n);
+                        ln_b[i] = __ldg(ln.bias + n);
+                    }
+                    ln_for = oi + 1;
+                }
                 CK_T(c_pre);
                 if (mine) {
                     if (op.kc > 0) {
-                        const int fg = tid & (nfg - 1), ks = tid / nfg;
-                        const int stride = op.kc + 4;
+                        const int fg = eg, ks = er0;
                         float acc[4][R];
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -246,7 +256,6 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                             for (int r = 0; r < R; ++r) acc[j][r] = 0.f;
                         const float* xbase = arena + op.x_off;
                         const int ldx = op.ldx, K = op.K, kc = op.kc;
-                        const int wj = nfg * stride;
 #pragma unroll 1
                         for (int k0 = 0; k0 < K; k0 += kc) {
                             sm100::mbar_wait(&s_full[c_stage], c_phase);
@@ -257,32 +266,49 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                                 ++pc.ch;
                             }
                             p_stage = p_stage + 1 == CK_STAGES ? 0 : p_stage + 1;
-                            const float* wst = ring + c_stage * CK_STAGE_FLOATS + fg * stride;
+                            const float* wst = ring + c_stage * CK_STAGE_FLOATS;
                             const int kq = min(kc, K - k0) >> 2;
                             const float* xk = xbase + k0;
+                            // software pipeline: the weights of the NEXT k-piece and the next activation row are in flight during the
+                            // 16 FMAs of the current row (all warps run this loop in step: with load-then-compute phases the FMA pipe
+                            // idled while the shared-memory pipe served 13 loads per thread, and vice versa)
+                            auto w_at = [&](int q, int j) -> float4 {   // 16-byte piece c of row rr sits at piece c ^ (rr & 7) of its 128-byte line
+                                const int rr = (q >> 3) * fcp + fg + nfg * j;
+                                return *reinterpret_cast<const float4*>(wst + rr * 32 + (((q & 7) ^ (rr & 7)) << 2));
+                            };
+                            int q = ks;
+                            if (q < kq) {
+                                float4 wv[4], xc;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) wv[j] = w_at(q, j);
+                                xc = *reinterpret_cast<const float4*>(xk + 4 * q);
 #pragma unroll 1
-                            for (int q = ks; q < kq; q += nks) {
-                                float4 wv[4], xv[R];
+                                while (true) {
+                                    const int qn = q + nks;
+                                    const bool more = qn < kq;
+                                    const int ql = more ? qn : q;                 // (a finished thread re-reads its last piece: no branch)
+                                    float4 wn[4];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) wv[j] = *reinterpret_cast<const float4*>(wst + j * wj + 4 * q);
+                                    for (int j = 0; j < 4; ++j) wn[j] = w_at(ql, j);
 #pragma unroll
-                                for (int r = 0; r < R; ++r) xv[r] = *reinterpret_cast<const float4*>(xk + r * ldx + 4 * q);
+                                    for (int r = 0; r < R; ++r) {
+                                        const float4 xn = r + 1 < R ? *reinterpret_cast<const float4*>(xk + (r + 1) * ldx + 4 * q)
+                                                                    : *reinterpret_cast<const float4*>(xk + 4 * ql);
 #pragma unroll
-                                for (int r = 0; r < R; ++r)
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xc.x, wv[j].x, acc[j][r]);
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].x, wv[j].x, acc[j][r]);
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xc.y, wv[j].y, acc[j][r]);
 #pragma unroll
-                                for (int r = 0; r < R; ++r)
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xc.z, wv[j].z, acc[j][r]);
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].y, wv[j].y, acc[j][r]);
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xc.w, wv[j].w, acc[j][r]);
+                                        xc = xn;
+                                    }
+                                    if (!more) break;
 #pragma unroll
-                                for (int r = 0; r < R; ++r)
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].z, wv[j].z, acc[j][r]);
-#pragma unroll
-                                for (int r = 0; r < R; ++r)
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].w, wv[j].w, acc[j][r]);
+                                    for (int j = 0; j < 4; ++j) wv[j] = wn[j];
+                                    q = qn;
+                                }
                             }
                             if (++c_stage == CK_STAGES) { c_stage = 0; c_phase ^= 1u; }
                             CK_T(c_fma);
@@ -308,7 +334,9 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                 }
                 uint64_t* const my_act = &s_act[act_n & 1u];
                 const uint32_t act_parity = (act_n >> 1) & 1u;
-                if (!op.out_global && tid == 0) sm100::mbar_arrive_expect_tx(my_act, (uint32_t)(R * op.N) * 4u);
+                // bytes the PEERS will complete here; the CTA's own tile is a plain store ordered by the CTA barriers below
+                if (!op.out_global && tid == 0)
+                    sm100::mbar_arrive_expect_tx(my_act, (uint32_t)(R * (op.N - (mine ? min(fcp, op.N - fbase) : 0))) * 4u);
                 __syncthreads();
                 CK_T(c_e1);
                 if (mine) {
@@ -319,7 +347,7 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                         const int em = row0 + er;
                         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
                         const float* rp = red + er * fcp + 4 * eg;
-#pragma unroll 4
+#pragma unroll 8
                         for (int q = 0; q < nsl; ++q) {
                             const float4 p = *reinterpret_cast<const float4*>(rp + q * kstride);
                             s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
@@ -357,8 +385,15 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                             const int o = op.out_off + er * op.ldo + en;
                             const uint32_t local = (uint32_t)__cvta_generic_to_shared(arena + o);
                             const bool vec = en + 3 < op.N && (o & 3) == 0;
+                            if (vec) {
+                                *reinterpret_cast<float4*>(arena + o) = make_float4(v[0], v[1], v[2], v[3]);
+                            } else {
 #pragma unroll
-                            for (int d = 0; d < CK_CL; ++d) {
+                                for (int j = 0; j < 4; ++j)
+                                    if (en + j < op.N) arena[o + j] = v[j];
+                            }
+#pragma unroll
+                            for (int d = 1; d < CK_CL; ++d) {
                                 const uint32_t peer = (uint32_t)((rank + d) & (CK_CL - 1));
                                 const uint32_t dst = map_to_rank(local, peer), dbar = map_to_rank(bar_local, peer);
                                 if (vec) {
@@ -386,14 +421,14 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
             if (op.kind == 1) {
                 // LayerNorm on the CTA's own copy: a warp per row, the row in registers, two-pass (mean, then centred variance) like
                 // ATen with the lane-strided summation order of the other kernels
-                constexpr int LN_CACHE = 8;
                 if (op.N <= 32 * LN_CACHE) {
-                    float gv[LN_CACHE], bv[LN_CACHE];
+                    if (ln_for != oi) {
 #pragma unroll
-                    for (int i = 0; i < LN_CACHE; ++i) {
-                        const int n = min(lane + 32 * i, op.N - 1);
-                        gv[i] = __ldg(op.w + n);
-                        bv[i] = __ldg(op.bias + n);
+                        for (int i = 0; i < LN_CACHE; ++i) {
+                            const int n = min(lane + 32 * i, op.N - 1);
+                            ln_g[i] = __ldg(op.w + n);
+                            ln_b[i] = __ldg(op.bias + n);
+                        }
                     }
 #pragma unroll 1
                     for (int r = warp; r < R; r += CK_THREADS / 32) {
@@ -413,7 +448,7 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
                         const float rstd = 1.f / sqrtf(warp_sum(q) / (float)op.N + op.ln_eps);
 #pragma unroll
                         for (int i = 0; i < LN_CACHE; ++i)
-                            if (lane + 32 * i < op.N) orow[lane + 32 * i] = (xv[i] - mean) * rstd * gv[i] + bv[i];
+                            if (lane + 32 * i < op.N) orow[lane + 32 * i] = (xv[i] - mean) * rstd * ln_g[i] + ln_b[i];
                     }
                 } else {
 #pragma unroll 1
@@ -523,12 +558,34 @@ static int ck_rows(int batch) {
     return p9 < p8 ? 9 : 8;
 }
 
-extern "C" int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops) {
+extern "C" int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops,
+                                       int* max_clusters) {
     if (rows) *rows = ck_rows(batch > 0 ? batch : 1);
+    if (max_clusters) *max_clusters = ck_max_active_clusters();
     if (cluster) *cluster = CK_CL;
     if (arena_floats) *arena_floats = CK_ARENA_FLOATS;
     if (stage_floats) *stage_floats = CK_STAGE_FLOATS;
     if (max_ops) *max_ops = CK_MAX_OPS;
+    return TD_OK;
+}
+
+// Tensor map of one Linear's weight [n][k] (fp32, row-major) for the cluster kernel: boxes of 32 floats x fcp rows, SWIZZLE_128B.
+// Written to HOST memory (128 bytes); the caller copies it to a 64-byte aligned device buffer and points ClusterOp::tmap at it.
+extern "C" int td_dense_cluster_weight_map(const float* w, int n, int k, int fcp, void* map_out_host) {
+    TD_CHECK_ARG(w && map_out_host && n > 0 && k > 0 && k % 4 == 0 && fcp >= 4 && fcp <= 256 && (((uintptr_t)w) & 15) == 0,
+                 "td_dense_cluster_weight_map: bad arguments");
+    EncodeTiledFn encode = tc_get_encode_fn();
+    if (!encode) { set_error("cuTensorMapEncodeTiled not available from the driver"); return TD_ERR_DRIVER; }
+    CUtensorMap m;
+    cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)n};
+    cuuint64_t gstr[1] = {(cuuint64_t)k * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)fcp};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(dense weight %d x %d, box 32 x %d) failed: %d", n, k, fcp, (int)r); return TD_ERR_DRIVER; }
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    memcpy(map_out_host, &m, sizeof(m));
     return TD_OK;
 }
 

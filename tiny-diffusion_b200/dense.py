@@ -43,14 +43,15 @@ class ClusterOp(C.Structure):
                 ("tmode", C.c_int), ("bn_relu", C.c_int), ("out_global", C.c_int),
                 ("x_off", C.c_int), ("ldx", C.c_int), ("out_off", C.c_int), ("ldo", C.c_int),
                 ("res_off", C.c_int), ("ldr", C.c_int), ("fcp", C.c_int), ("kc", C.c_int),
-                ("w", _P), ("bias", _P), ("gx", _P), ("gldx", C.c_longlong), ("gout", _P), ("gldo", C.c_longlong),
+                ("w", _P), ("bias", _P), ("tmap", _P), ("pad_", C.c_longlong),
+                ("gx", _P), ("gldx", C.c_longlong), ("gout", _P), ("gldo", C.c_longlong),
                 ("gidx", _P), ("gtab", _P), ("ldt", C.c_longlong),
                 ("bn_mean", _P), ("bn_var", _P), ("bn_gamma", _P), ("bn_beta", _P), ("bn_eps", C.c_float), ("ln_eps", C.c_float),
                 ("t", _P), ("t_dev", _P)]
 
 
 FUSED_MAX_BATCH = 1024
-CLUSTER_MAX_BATCH = 256               # up to here the cluster kernel (8 rows per cluster, <= 16 clusters) beats the grid-barrier tape                # above this the per-layer GEMM kernels (tcgen05 tf32 at >= 2048) are the better shape
+CLUSTER_MAX_BATCH = 256               # the cluster kernel is tried up to here; it declines batches that need a second pass (> 135 rows)                # above this the per-layer GEMM kernels (tcgen05 tf32 at >= 2048) are the better shape
 
 
 class DenseEngine:
@@ -379,9 +380,11 @@ class DenseEngine:
         tape then takes over)."""
         lib = self.lib
         assert int(lib.td_dense_cluster_op_bytes()) == C.sizeof(ClusterOp), "ClusterOp layout mismatch"
-        lim = [C.c_int() for _ in range(5)]
+        lim = [C.c_int() for _ in range(6)]
         L.check(lib.td_dense_cluster_limits(self.B, *[C.byref(v) for v in lim]), "td_dense_cluster_limits")
-        R, CL, ARENA, STAGE, MAX_OPS = (int(v.value) for v in lim)
+        R, CL, ARENA, STAGE, MAX_OPS, MAX_CLUSTERS = (int(v.value) for v in lim)
+        if -(-self.B // R) > MAX_CLUSTERS and os.environ.get("TD_DENSE_CLUSTER_PASSES", "1") == "1":
+            return              # a second pass re-streams every weight: measured no faster than the grid-barrier tape (batch 200)
         ops = list(self._ops)
         fused_bn = {}
         for i, op in enumerate(ops):
@@ -454,6 +457,12 @@ class DenseEngine:
             base[name] = off
             live.append((off, size, name))
 
+        # one tensor map per streamed weight (TMA boxes of 32 floats x fcp rows), kept on the device beside the tape
+        n_lin = sum(1 for r in recs if r["kind"] == 0)
+        maps_host = torch.zeros(max(n_lin, 1) * 128, dtype=torch.uint8)
+        maps_dev = torch.zeros(max(n_lin, 1) * 128, dtype=torch.uint8, device=self.device)
+        map_slot: Dict[int, int] = {}
+
         def make(use_t_dev: bool):
             tape = []
             for r in recs:
@@ -489,8 +498,13 @@ class DenseEngine:
                     if fcp > 128:
                         return None
                     t.fcp = fcp
-                    kc = min(K, (STAGE // fcp - 4) // 32 * 32)
-                    t.kc = kc if (K % 4 == 0 and t.w % 16 == 0 and t.x_off % 4 == 0 and kc >= 4) else 0
+                    kc = 32 * (STAGE // (fcp * 32))                  # whole boxes per stage
+                    t.kc = kc if (K % 4 == 0 and t.w % 16 == 0 and t.x_off % 4 == 0 and kc >= 32) else 0
+                    if t.kc:
+                        slot = map_slot.setdefault(id(r), len(map_slot))
+                        if L.load().td_dense_cluster_weight_map(t.w, N, K, fcp, maps_host.data_ptr() + 128 * slot) != 0:
+                            return None                              # no driver entry point: the tape kernel takes over
+                        t.tmap = maps_dev.data_ptr() + 128 * slot
                     if r["bn"] is not None:
                         m = r["bn"]["bn"]
                         t.bn_mean, t.bn_var = m.running_mean.data_ptr(), m.running_var.data_ptr()
@@ -518,6 +532,8 @@ class DenseEngine:
         tapes = {False: make(False), True: make(True)}
         if tapes[False] is None or tapes[True] is None:
             return
+        maps_dev.copy_(maps_host)
+        self._ctape_maps = maps_dev
         self._ctapes = tapes
         self._ctape_rows = R
         self._ctape_arena = max(b + R * ld[n] for n, b in base.items())
