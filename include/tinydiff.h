@@ -191,6 +191,10 @@ typedef struct {
     int x_nchw, y_nchw;      /* direct kernels only: tensor is NCHW fp32 (network input/output) */
     float* splitk_ws;        /* NULL, or td_conv3x3_splitk_workspace() floats: lets the tcgen05 engine   */
                              /* split the K loop across CTAs when the layer has too few tiles            */
+    void* pool_y;            /* NULL, or MaxPool2d(2, ceil_mode = pool_ceil) of y (diffusion.py:101), same dtype, dense   */
+                             /* [batch, Hp, Wp, cout]: written by the epilogue of the tcgen05 halo kernel when the plan   */
+                             /* accepts it (td_conv3x3_pool_fused); otherwise the caller runs td_maxpool2_fwd on y        */
+    int pool_ceil;
 } td_conv3x3_desc;
 
 /* Engines.  Weight layout expected by each (w is [cout][3][3][cin] "OHWI" in every case):
@@ -206,6 +210,8 @@ typedef struct td_conv_plan td_conv_plan;
 int64_t td_conv3x3_splitk_workspace(const td_conv3x3_desc* desc);
 int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc* desc, int engine);
 int td_conv3x3_run(const td_conv_plan* plan, void* stream);
+/* 1: the plan writes desc.pool_y itself (eval mode, bf16 output, halo kernel with pooling windows inside a subtile) */
+int td_conv3x3_pool_fused(const td_conv_plan* plan);
 /* number of partial rows the plan writes to desc.stats per run (0: statistics are not fused, use td_bn_stats) */
 int td_conv3x3_stats_rows(const td_conv_plan* plan);
 void td_conv3x3_plan_destroy(td_conv_plan* plan);

@@ -216,6 +216,40 @@ def test_conv_halo_layouts(dev, monkeypatch, mode, B, H, cin, cout):
     assert float((got32 - want).abs().max()) < 1e-3           # no stray element (halo / dead-column handling)
 
 
+# MaxPool2d(2) fused into the halo epilogue (eval mode, bf16): every map the UNets pool (28 / 14 / 7 with ceil_mode, the latent
+# UNet's 32 / 16 in strips) plus floor mode, ragged batches and the benchmark batch.  The pooled map must be BIT-identical to
+# pooling the conv's own bf16 output (max commutes with the monotone bf16 rounding).
+@pytest.mark.parametrize("B,H,cin,cout,mode", [(5, 28, 128, 128, "ceil"), (3, 14, 256, 256, "ceil"), (8, 7, 512, 512, "ceil"),
+                                               (128, 28, 64, 128, "ceil"), (37, 14, 128, 256, "ceil"), (129, 7, 256, 512, "ceil"),
+                                               (3, 32, 64, 64, "floor"), (5, 16, 64, 128, "ceil"), (4, 7, 64, 64, "floor"),
+                                               (2, 20, 64, 64, "ceil"), (5, 24, 64, 128, "ceil")])
+def test_conv_halo_fused_maxpool(dev, B, H, cin, cout, mode):
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(B * 100 + H)
+    x = torch.randn(B, H, H, cin, generator=g).to(dev).to(torch.bfloat16)
+    w = ops.pack_conv_weight((torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).to(dev), torch.bfloat16)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(cout, generator=g) * 0.3).to(dev)
+    for relu in (True, False):
+        y_plain = ops.conv3x3(x, w, scale, shift, relu, 1, torch.bfloat16)
+        y, pooled = ops.conv3x3(x, w, scale, shift, relu, 1, torch.bfloat16, pool=mode)
+        assert torch.equal(y, y_plain), "the un-pooled output must not change"
+        assert pooled is not None, "the halo plan must accept the fused pool on these maps"
+        want = F.max_pool2d(y.float().permute(0, 3, 1, 2), 2, ceil_mode=(mode == "ceil")).permute(0, 2, 3, 1)
+        assert pooled.shape == want.shape
+        assert torch.equal(pooled.float(), want), f"relu={relu}: max abs diff {float((pooled.float() - want).abs().max())}"
+
+
+def test_conv_fused_maxpool_declined(dev):
+    """Plans that cannot pool in the epilogue (per-tap kernel on the 4x4 map, fp32 output) say so and leave pool_y untouched."""
+    from tinydiff import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 4, 4, 64, generator=g).to(dev).to(torch.bfloat16)
+    w = ops.pack_conv_weight((torch.randn(64, 64, 3, 3, generator=g) / 24.0).to(dev), torch.bfloat16)
+    _, pooled = ops.conv3x3(x, w, None, None, True, 1, torch.float32, pool="ceil")
+    assert pooled is None
+
+
 def test_conv_halo_channel_slices(dev):
     """Input read from / output written into a channel slice of a wider NHWC buffer (the decoder concat)."""
     from tinydiff import ops

@@ -57,7 +57,8 @@ class ConvDesc(C.Structure):
                 ("x", _P), ("ldx", C.c_int), ("x_coff", C.c_int),
                 ("y", _P), ("ldy", C.c_int), ("y_coff", C.c_int),
                 ("w", _P), ("scale", _P), ("shift", _P), ("relu", C.c_int),
-                ("stats", _P), ("x_nchw", C.c_int), ("y_nchw", C.c_int), ("splitk_ws", _P)]
+                ("stats", _P), ("x_nchw", C.c_int), ("y_nchw", C.c_int), ("splitk_ws", _P),
+                ("pool_y", _P), ("pool_ceil", C.c_int)]
 
 
 _SIGS = {
@@ -87,6 +88,7 @@ _SIGS = {
     "td_conv3x3_splitk_workspace": (C.c_int64, [C.POINTER(ConvDesc)]),
     "td_conv3x3_plan_create": (C.c_int, [C.POINTER(_P), C.POINTER(ConvDesc), C.c_int]),
     "td_conv3x3_run": (C.c_int, [_P, _P]),
+    "td_conv3x3_pool_fused": (C.c_int, [_P]),
     "td_conv3x3_stats_rows": (C.c_int, [_P]),
     "td_conv3x3_plan_destroy": (None, [_P]),
     "td_conv3x3_flops": (C.c_double, [_P]),

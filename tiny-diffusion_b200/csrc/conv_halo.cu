@@ -52,6 +52,8 @@ struct HaloParams {
     int NA, NB;
     uint32_t a_box_bytes, a_slot_bytes;
     int dbg;                 // TD_TC_HALO_DBG=1: per-CTA wait-cycle counters into g_halo_dbg
+    void* pool_y;            // eval mode: MaxPool2d(2) of the output written beside it (windows never straddle a subtile), or NULL
+    int pool_ceil, Hp, Wp;   // pooled map size
 };
 
 // [CTA][8]: 0 total, 1 producer wait A slot, 2 producer wait B stage, 3 MMA wait A, 4 MMA wait B, 5 MMA wait
@@ -255,6 +257,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int grp = (warp - 3) >> 2;             // epilogue group = the subtile of the pair it drains
         const int tid = threadIdx.x - 96 - grp * 128;
         const int bar_id = 1 + grp;
+        // Fused MaxPool2d(2): the group's four 32 x 32 staging tiles are one 128-position tile; thread `tid` owns pooled pixel
+        // tid >> 2 of the subtile and 8 of the chunk's 32 channels.  (pp_r[k] < 0: window element outside the image / subtile.)
+        int pp_r[4] = {-1, -1, -1, -1}, pp_n = 0, pp_h = 0, pp_w = 0;
+        bool pp_on = false;
+        if (p.pool_y) {
+            const int pw_cnt = (p.bw + 1) >> 1, ph_cnt = (p.bh + 1) >> 1;
+            const int pp = tid >> 2, per_img = pw_cnt * ph_cnt;
+            pp_n = pp / per_img;
+            const int rem_p = pp - pp_n * per_img;
+            pp_h = rem_p / pw_cnt;
+            pp_w = rem_p - pp_h * pw_cnt;
+            pp_on = pp_n < p.BN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int hh = 2 * pp_h + (k >> 1), ww = 2 * pp_w + (k & 1);
+                if (pp_on && hh < p.bh && ww < p.bw) {
+                    const int pos = pp_n * img_rows + hh * p.ew + ww;                // position inside the subtile = TMEM lane
+                    pp_r[k] = ((((pos >> 5) + 1) & 3) << 5) + (pos & 31);           // its row of the group tile (warp slot = (quadrant + 1) & 3)
+                }
+            }
+        }
         float* const aff_g = s_affine + grp * 4 * N_TILE;
         float* const stats_g = s_stats + grp * 8 * N_TILE;
         UnitWalk wk{u_lo, u_hi, p.n_sub};
@@ -358,6 +381,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                     __syncwarp();
                 };
+                // pooled pixel of this thread in this subtile (the window elements' validity against the image edge)
+                const int p_h0 = th * p.bh, p_w0 = tw * p.bw;
+                const int p_n = tn * p.BN + pp_n, p_ph = (p_h0 >> 1) + pp_h, p_pw = (p_w0 >> 1) + pp_w;
+                const bool p_store = pp_on && j < cnt && p_n < p.B && p_ph < p.Hp && p_pw < p.Wp;
+                const uint32_t gtile_s = smem_u32(s_tile + grp * (4 * 32 * 36));
                 tmem_ld_32x32(t_addr, rr);
                 tmem_ld_wait();
                 stage(0);
@@ -383,8 +411,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                                 f[k] = fmaf(f[k], sc[k], sh[k]);
                                 if (p.relu) f[k] = fmaxf(f[k], 0.f);
                             }
-                            if (row_off[it] >= 0)
-                                Vec<__nv_bfloat16>::pack(f).store(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + col);
+                            const Vec<__nv_bfloat16> packed = Vec<__nv_bfloat16>::pack(f);
+                            if (row_off[it] >= 0) packed.store(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + col);
+                            // fused max-pool: the finished bf16 values replace the row's first 64 bytes in place (the four lanes of a
+                            // row read its 128 fp32 bytes in the two loads above, before this store of the same warp instruction)
+                            if (p.pool_y) sts128(tile_s + (uint32_t)(row * 36) * 4u + (uint32_t)(lane & 3) * 16u, packed.v.x, packed.v.y, packed.v.z, packed.v.w);
                         }
                     } else {
                         const int col = (lane & 7) * 4;
@@ -399,7 +430,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             if (row_off[it] >= 0) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + row_off[it] + c0 + col) = a;
                         }
                     }
-                    __syncwarp();
+                    if (p.pool_y) {
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // the four warps' rows hold their bf16 results
+                        if (p_store) {
+                            const uint32_t NEG_INF2 = 0xFF80FF80u;                          // two bf16 -inf
+                            uint32_t m[4] = {NEG_INF2, NEG_INF2, NEG_INF2, NEG_INF2};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int hh = p_h0 + 2 * pp_h + (e >> 1), ww = p_w0 + 2 * pp_w + (e & 1);
+                                if (pp_r[e] < 0 || hh >= p.H || ww >= p.W) continue;
+                                const float4 a = lds128(gtile_s + (uint32_t)(pp_r[e] * 36) * 4u + (uint32_t)(tid & 3) * 16u);
+                                const uint32_t v[4] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&m[k]),
+                                                                     *reinterpret_cast<const __nv_bfloat162*>(&v[k]));
+                                    m[k] = *reinterpret_cast<const uint32_t*>(&r);
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pool_y) +
+                                                      (((int64_t)p_n * p.Hp + p_ph) * p.Wp + p_pw) * p.cout + nt * N_TILE + c0 + (tid & 3) * 8) =
+                                make_uint4(m[0], m[1], m[2], m[3]);
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");      // pooled reads done: the tile may be restaged
+                    } else {
+                        __syncwarp();
+                    }
                     if (more) {
                         tmem_ld_wait();
                         stage(c0 + 32);
@@ -459,11 +515,12 @@ struct HaloGeom {
 };
 
 // Best subtile (<= 128 positions) of an H x W feature map for each layout; eff = 0 when not applicable.
-static HaloGeom best_flat(int B, int H, int W) {
+static HaloGeom best_flat(int B, int H, int W, bool even_bh) {
     HaloGeom g{1, W + 1, 0, 1, 0.0, 0};
     const int PW = W + 1;
     for (int bh = 1; bh <= H; ++bh) {               // bh rows of one image
         if ((bh - 1) * PW + W - 1 >= 128) break;
+        if (even_bh && (bh & 1) && bh < H) continue;        // fused 2x2 max-pool: windows must not straddle two subtiles
         const double eff = (double)H * W / ((double)ceil_div(H, bh) * 128.0);
         if (eff > g.eff + 1e-9) { g.eff = eff; g.bh = bh; g.BN = 1; }
     }
@@ -499,7 +556,9 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     if (d.width > 255 || d.height > 253) return false;
     const int n_tile = d.cout % 128 == 0 ? 128 : 64;
     // Relative cost per useful output: MMA cycles ~ 1/eff; L2 -> SM bytes ~ (A boxes + shared B) at ~45 B/clk.
-    HaloGeom cand[3] = {best_flat(d.batch, d.height, d.width), best_strip(d.height, d.width), best_dx(d.height, d.width)};
+    // eval-mode layers followed by MaxPool2d(2): the epilogue writes the pooled map too when every window lies inside a subtile
+    const bool want_pool = d.pool_y && !d.stats && d.y_dtype == TD_BF16 && getenv("TD_TC_HALO_POOL") == nullptr;
+    HaloGeom cand[3] = {best_flat(d.batch, d.height, d.width, want_pool), best_strip(d.height, d.width), best_dx(d.height, d.width)};
     int best = -1;
     double best_cost = 0;
     for (int i = 0; i < 2; ++i) {      // the dx layout moves 3x the activation bytes and measures slower than the per-tap kernel: opt-in only
@@ -533,6 +592,11 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     p->block_n = n_tile;
     p->n_tiles = d.cout / n_tile;
     p->h_units = p->h_nsub * p->n_tiles;
+    {
+        const int bw = g.strip ? 8 : d.width;
+        p->h_pool = want_pool && g.G == 1 && (g.bh % 2 == 0 || p->tiles_h == 1) && (bw % 2 == 0 || p->tiles_w == 1) &&
+                    ((bw + 1) / 2) * ((g.bh + 1) / 2) * g.BN <= 32;
+    }
     p->h_grid = std::min(p->h_units, sm_budget());
     p->split_k = 1;
     const int box_bytes = g.PW * p->h_rh * g.BN * 128;
@@ -604,6 +668,10 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
         const char* e = getenv("TD_TC_HALO_DBG");
         prm.dbg = e ? atoi(e) : 0;
     }
+    prm.pool_y = p->h_pool ? d.pool_y : nullptr;
+    prm.pool_ceil = d.pool_ceil;
+    prm.Hp = d.pool_ceil ? (d.height + 1) / 2 : d.height / 2;
+    prm.Wp = d.pool_ceil ? (d.width + 1) / 2 : d.width / 2;
     return p->block_n == 128 ? launch_halo<128>(p, prm, s) : launch_halo<64>(p, prm, s);
 }
 

@@ -24,6 +24,7 @@ struct td_conv_plan {
     int h_units, h_nsub, h_na, h_nb, h_slot_bytes;
     int h_grid;             // CTAs of the persistent halo kernel = min(h_units, sm_budget() at plan creation)
     int h_strip;            // 1: 8-column strip subtiles (A descriptor group stride = h_pw * 128 bytes)
+    int h_pool;             // 1: the epilogue also writes d.pool_y (2x2 max-pool windows never straddle a subtile)
 };
 
 struct td_wgrad_plan {

@@ -797,6 +797,10 @@ extern "C" int td_conv3x3_plan_create(td_conv_plan** plan, const td_conv3x3_desc
     return TD_OK;
 }
 
+extern "C" int td_conv3x3_pool_fused(const td_conv_plan* plan) {
+    return plan && plan->engine == TD_CONV_TC && plan->halo && plan->h_pool ? 1 : 0;
+}
+
 extern "C" int td_conv3x3_stats_rows(const td_conv_plan* plan) {
     if (!plan || !plan->d.stats || plan->engine != TD_CONV_TC) return 0;
     if (plan->halo) return plan->h_grid;                              // one row per (persistent) CTA

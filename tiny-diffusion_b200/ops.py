@@ -107,8 +107,10 @@ def pack_conv_weight(w_oihw, dtype=torch.float32):
 
 
 def conv3x3(x, w_ohwi, scale=None, shift=None, relu=False, engine=L.CONV_SIMT, out_dtype=None, x_nchw=False,
-            y_nchw=False, out=None, y_coff=0, x_coff=0, cin=None, want_stats=False):
-    """x: NHWC (or NCHW fp32 when x_nchw).  Returns NHWC (or NCHW) output."""
+            y_nchw=False, out=None, y_coff=0, x_coff=0, cin=None, want_stats=False, pool=None):
+    """x: NHWC (or NCHW fp32 when x_nchw).  Returns NHWC (or NCHW) output.  ``pool`` = "ceil" / "floor": also returns
+    ``(MaxPool2d(2) of the output or None, fused)`` -- the pooled map comes from the conv epilogue when the plan accepts it
+    (``td_conv3x3_pool_fused``), else it is None and the caller pools the output itself."""
     _dev(x)
     lib = L.load()
     if x_nchw:
@@ -137,13 +139,22 @@ def conv3x3(x, w_ohwi, scale=None, shift=None, relu=False, engine=L.CONV_SIMT, o
     if want_stats:
         part = torch.full(((B * H * W // 32 + 2) * 2 * cout + cout,), float("nan"), device=x.device)
         d.stats = part.data_ptr()
+    pooled = None
+    if pool is not None:
+        ceil = pool == "ceil"
+        Hp, Wp = ((H + 1) // 2, (W + 1) // 2) if ceil else (H // 2, W // 2)
+        pooled = torch.full((B, Hp, Wp, cout), float("nan"), device=x.device, dtype=out.dtype)
+        d.pool_y, d.pool_ceil = pooled.data_ptr(), int(ceil)
     h = C.c_void_p()
     L.check(lib.td_conv3x3_plan_create(C.byref(h), C.byref(d), engine), "td_conv3x3_plan_create")
     try:
         L.check(lib.td_conv3x3_run(h, L.stream_ptr()), "td_conv3x3_run")
         rows = int(lib.td_conv3x3_stats_rows(h)) if want_stats else 0
+        fused = bool(lib.td_conv3x3_pool_fused(h)) if pool is not None else False
     finally:
         lib.td_conv3x3_plan_destroy(h)
+    if pool is not None:
+        return out, (pooled if fused else None)
     if want_stats:
         return out, part[:rows * 2 * cout].view(rows, 2, cout), part[rows * 2 * cout:rows * 2 * cout + cout]
     return out

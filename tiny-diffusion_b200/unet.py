@@ -227,7 +227,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ plan
     def _conv(self, name, x, cin, y, cout, relu, x_coff=0, y_coff=0, x_nchw=False, y_nchw=False, y_dtype=None,
-              x_dtype=None):
+              x_dtype=None, pool=None):
         B, H = self.B, (x.shape[2] if x_nchw else x.shape[1])
         d = L.ConvDesc()
         d.batch, d.height, d.width, d.cin, d.cout = B, H, H, cin, cout
@@ -243,6 +243,8 @@ class UNetEngine:
         d.stats = None
         d.x_nchw, d.y_nchw = int(x_nchw), int(y_nchw)
         d.splitk_ws = L.ptr(self.splitk_ws)
+        if pool is not None:                  # MaxPool2d(2) of y written by the conv epilogue when the plan accepts it
+            d.pool_y, d.pool_ceil = pool.data_ptr(), int(self.cfg.ceil_pool)
         plan = _ConvPlan(d, self.engines[name])
         self.plans[name] = plan
         return plan
@@ -258,6 +260,15 @@ class UNetEngine:
         def add_conv(name, *a, **k):
             plan = self._conv(name, *a, **k)
             ops.append((name, plan.run))
+            return plan
+
+        def add_conv_pool(name, x, cin, y_name, cout, p_name, h):
+            """conv + BatchNorm + ReLU followed by MaxPool2d(2): one launch when the tcgen05 halo epilogue can pool (windows
+            inside a subtile), else the separate pooling kernel."""
+            fuse = self.adt == L.TD_BF16 and self.engines[name] == L.CONV_TC
+            plan = add_conv(name, x, cin, bf[y_name], cout, True, pool=bf[p_name] if fuse else None)
+            if not (fuse and int(lib.td_conv3x3_pool_fused(plan.handle))):
+                add_pool(y_name, p_name, h, cout)
 
         def add_pool(src, dst, h, c):
             sp, dp = bf[src].data_ptr(), bf[dst].data_ptr()
@@ -276,14 +287,11 @@ class UNetEngine:
         ops.append(("embed", self._run_embed))
         add_conv("initial_conv", self.x_in, cfg.in_ch, bf["x0"], c0, False, x_nchw=True)
         add_conv("enc1.0", bf["x0"], self.c0p, bf["enc1a"], c1, True)
-        add_conv("enc1.3", bf["enc1a"], c1, bf["e1"], c1, True)
-        add_pool("e1", "p1", S["s0"], c1)
+        add_conv_pool("enc1.3", bf["enc1a"], c1, "e1", c1, "p1", S["s0"])
         add_conv("enc2.0", bf["p1"], c1, bf["enc2a"], c2, True)
-        add_conv("enc2.3", bf["enc2a"], c2, bf["e2"], c2, True)
-        add_pool("e2", "p2", S["s1"], c2)
+        add_conv_pool("enc2.3", bf["enc2a"], c2, "e2", c2, "p2", S["s1"])
         add_conv("enc3.0", bf["p2"], c2, bf["enc3a"], c3, True)
-        add_conv("enc3.3", bf["enc3a"], c3, bf["e3"], c3, True)
-        add_pool("e3", "p3", S["s2"], c3)
+        add_conv_pool("enc3.3", bf["enc3a"], c3, "e3", c3, "p3", S["s2"])
         add_conv("bottleneck.0", bf["p3"], c3, bf["b"], cfg.bott, True)
         add_upcat("b", "e3", "cat3", S["u3"], cfg.bott, S["s2"], c3, c1 + c2)
         add_conv("dec3.0", bf["cat3"], cfg.bott + c3, bf["dec3a"], d3, True)
