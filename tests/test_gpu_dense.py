@@ -125,6 +125,37 @@ def test_cluster_kernel_vs_oracle(dev, name, B, passes, monkeypatch):
     assert rel(outs["1"], outs["2"]) < 2e-6 and rel(outs["1"], outs["0"]) < 2e-6
 
 
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+def test_cluster_merged_weights_follow_parameter_updates(dev, name):
+    """Back-to-back Linears are merged into one in the cluster tape (W = W_b W_a, derived buffers): an in-place parameter update
+    must reach the next forward and the next sampler call."""
+    mod, model, sd = build(name, dev, **KW[name])
+    eng = model.engine(16, dev, training=False)
+    assert eng._ctapes is not None and len(eng._merged) >= 1
+    inp = make_inputs(name, 16, seed=3)
+    args = (inp["x0"].to(dev), inp["t"].to(dev), inp["cond"].to(dev))
+    with torch.no_grad():
+        eps0 = model(*args)
+        for mg in eng._merged:                       # touch both factors of every merged pair
+            mg["wb"].mul_(1.25)
+            if mg["ba"] is not None:
+                mg["ba"].add_(0.05)
+        eps1 = model(*args)
+    sd2 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    want = FWD[name](sd2, inp["x0"], inp["t"], inp["cond"], None)
+    assert rel(eps1, want) < 1e-5
+    assert rel(eps0, eps1) > 1e-4, "the update must change the output"
+    # TrainStep-style updates go through raw pointers: the model-level generation counter invalidates the merged weights too
+    with torch.no_grad():
+        for mg in eng._merged:
+            mg["wa"].data.mul_(0.9)                  # .data: no _version bump, like a kernel writing through the pointer
+    model._weights_gen = getattr(model, "_weights_gen", 0) + 1
+    with torch.no_grad():
+        eps2 = model(*args)
+    sd3 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    assert rel(eps2, FWD[name](sd3, inp["x0"], inp["t"], inp["cond"], None)) < 1e-5
+
+
 def test_cluster_kernel_is_default_at_reference_batch(dev):
     """At the reference batch the public forward runs the cluster kernel (one launch), above one pass the tape."""
     from tinydiff import _lib as L

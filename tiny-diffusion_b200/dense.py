@@ -413,6 +413,37 @@ class DenseEngine:
                 recs.append({"kind": 2, "reads": reads, "write": op["out"], "op": op})
             else:                                           # stand-alone BatchNorm1d: not declared by either model
                 return
+        # Two Linears back to back with nothing in between (the length-1 attention's out_proj(v_proj(x)), diffusion_transformer.py:99)
+        # are ONE Linear with W = W_b W_a, b = W_b b_a + b_b in eval mode: one op, one push and one barrier wait fewer.  The merged
+        # weights are derived buffers, recomputed by refresh_weights() when a parameter changes.
+        self._merged = []
+        if os.environ.get("TD_DENSE_MERGE", "1") != "0":
+            n_reads: Dict[str, int] = {}
+            for r in recs:
+                for m in r["reads"]:
+                    n_reads[m[0]] = n_reads.get(m[0], 0) + 1
+            out, i = [], 0
+            while i < len(recs):
+                a = recs[i]
+                b = recs[i + 1] if i + 1 < len(recs) else None
+                ok = (b is not None and a["kind"] == 0 and b["kind"] == 0 and a["bn"] is None and a["op"]["act"] == L.ACT_NONE
+                      and a["op"]["res"] is None and a["op"]["gather"] is None and a["write"] == self.full(a["write"][0])
+                      and b["op"]["x"] == a["write"] and n_reads.get(a["write"][0], 0) == 1 and a["write"][0] != "eps")
+                if not ok:
+                    out.append(a)
+                    i += 1
+                    continue
+                wa, ba, wb, bb = a["op"]["w"], a["op"]["b"], b["op"]["w"], b["op"]["b"]
+                ra = a["op"]["rows"] if a["op"]["rows"] else (0, wa.shape[0])
+                rb = b["op"]["rows"] if b["op"]["rows"] else (0, wb.shape[0])
+                mg = {"wa": wa, "ba": ba, "ra": ra, "wb": wb, "bb": bb, "rb": rb,
+                      "W": torch.zeros(rb[1] - rb[0], wa.shape[1], device=self.device),
+                      "b": torch.zeros(rb[1] - rb[0], device=self.device)}
+                self._merged.append(mg)
+                out.append({"kind": 0, "reads": [a["op"]["x"]] + ([b["op"]["res"]] if b["op"]["res"] is not None else []),
+                            "write": b["write"], "op": b["op"], "bn": b["bn"], "merged": mg, "x": a["op"]["x"]})
+                i += 2
+            recs = out
         # buffers read before any op wrote them come from global memory
         written, loads = set(), []
         for r in recs:
@@ -483,15 +514,21 @@ class DenseEngine:
                     t.t = None if use_t_dev else self.t_in.data_ptr()
                     t.t_dev = self.t_dev.data_ptr()
                 elif r["kind"] == 0:
-                    w, b = op["w"], op["b"]
-                    r0, r1 = op["rows"] if op["rows"] else (0, w.shape[0])
-                    N, K = r1 - r0, w.shape[1]
-                    xn, x0, x1 = op["x"]
+                    mg = r.get("merged")
+                    if mg is not None:
+                        N, K = mg["W"].shape
+                        xn, x0, x1 = r["x"]
+                        t.w, t.bias = mg["W"].data_ptr(), mg["b"].data_ptr()
+                    else:
+                        w, b = op["w"], op["b"]
+                        r0, r1 = op["rows"] if op["rows"] else (0, w.shape[0])
+                        N, K = r1 - r0, w.shape[1]
+                        xn, x0, x1 = op["x"]
+                        t.w = w.data_ptr() + 4 * r0 * K
+                        t.bias = (b.data_ptr() + 4 * r0) if b is not None else None
                     assert x1 - x0 == K and c1 - c0 == N
                     t.N, t.K, t.act = N, K, op["act"]
                     t.x_off, t.ldx = base[xn] + x0, ld[xn]
-                    t.w = w.data_ptr() + 4 * r0 * K
-                    t.bias = (b.data_ptr() + 4 * r0) if b is not None else None
                     fcp = 4
                     while fcp * CL < N:
                         fcp *= 2
@@ -535,6 +572,8 @@ class DenseEngine:
         maps_dev.copy_(maps_host)
         self._ctape_maps = maps_dev
         self._ctapes = tapes
+        self._merged_version = None
+        self.refresh_weights()
         self._ctape_rows = R
         self._ctape_arena = max(b + R * ld[n] for n, b in base.items())
 
@@ -712,8 +751,36 @@ class DenseEngine:
     def _build(self):
         self.build()
 
-    def refresh_weights(self, force: bool = False) -> None:      # parameters are read in place
-        return
+    def weights_version(self):
+        # _weights_gen: bumped by train.TrainStep, whose kernels update the parameters through raw pointers (no _version bump)
+        return (getattr(self.module, "_weights_gen", 0),) + tuple(p._version for p in self.module.parameters())
+
+    def refresh_weights(self, force: bool = False) -> None:
+        """Parameters are read in place; only the merged weights of fused Linear pairs (cluster tape) are derived buffers."""
+        merged = getattr(self, "_merged", None)
+        if not merged or getattr(self, "_ctapes", None) is None:
+            return
+        ver = self.weights_version()
+        if not force and ver == self._merged_version:
+            return
+        st, flops = L.stream_ptr(), self.flops
+        for mg in merged:
+            wa, wb = mg["wa"], mg["wb"]
+            (a0, a1), (b0, b1) = mg["ra"], mg["rb"]
+            Na, Ka, Nb = a1 - a0, wa.shape[1], b1 - b0
+            assert wb.shape[1] == Na
+            wa_p, wb_p = wa.data_ptr() + 4 * a0 * Ka, wb.data_ptr() + 4 * b0 * Na
+            # W = W_b W_a  ([Nb][Na] x [Na][Ka]) and b = W_b b_a + b_b with the library's own fp32 GEMM
+            self._gemm(Nb, Ka, Na, wb_p, Na, 1, wa_p, Ka, 1, mg["W"].data_ptr(), Ka)(st)
+            bb_p = (mg["bb"].data_ptr() + 4 * b0) if mg["bb"] is not None else None
+            if mg["ba"] is not None:
+                self._gemm(Nb, 1, Na, wb_p, Na, 1, mg["ba"].data_ptr() + 4 * a0, 1, 1, mg["b"].data_ptr(), 1, res=bb_p, ldr=1)(st)
+            elif mg["bb"] is not None:
+                mg["b"].copy_(mg["bb"].detach()[b0:b1])
+            else:
+                mg["b"].zero_()
+        self.flops = flops
+        self._merged_version = ver
 
     def reseed(self, seed: int) -> None:
         """New dropout masks: every dropout site gets (seed, site id) as its Philox key / subsequence."""
@@ -813,6 +880,7 @@ class DenseNoiseModel(CheckpointCompat, torch.nn.Module):
             return _DenseTrainFunction.apply(eng, x, t, y.to(device), *params)
         eng.load_inputs(x, t, y.to(device))
         eng.use_t_dev = False
+        eng.refresh_weights()
         eng.launch_forward()
         return eng.eps.clone()
 
@@ -836,6 +904,7 @@ def dense_sample(vae, noise_model: DenseNoiseModel, diffusion, device, n_samples
     eng.x_in.copy_(x_T.to(torch.float32))
     eng.y_in.copy_(y)
     eng.use_t_dev = True
+    eng.refresh_weights()
     loop = getattr(eng, "_reverse_loop", None)
     if loop is None or loop.p is not diffusion or loop.use_graph != use_graph:
         loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch_forward, use_graph=use_graph)
