@@ -509,6 +509,373 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Two-group variant (the default): the CTA's eight compute warps are TWO independent groups of four, each taking half of the
+// cluster's rows through the tape with its own named barrier, its own activation mbarriers and its own k-slice scratch; a ninth
+// warp is the weight producer (TMA boxes into the shared ring, full / empty mbarriers).  A Linear is a chain of dependent
+// latencies (weight wait -> FMA tile -> partial stores -> barrier -> k-slice sum -> pushes -> wait for the slowest peer); with one
+// chain per SM the FP32 pipe ran at 30 %.  Two chains interleave on the same SM -- and share every weight stage, so the L2 -> SM
+// traffic does not grow.
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int CK2_GT = 128;                                // threads per group
+constexpr int CK2_THREADS = 2 * CK2_GT + 32;               // + producer warp
+constexpr int CK2_RED_FLOATS = 2 * (128 * 4 * 5 + 128);    // per group: [k-slices][rows <= 5][fcp] + bank-shift pad
+constexpr int CK2_SMEM = 1024 + CK_MAX_OPS * (int)sizeof(ClusterOp) + (CK_ARENA_FLOATS + CK_STAGES * CK_STAGE_FLOATS + CK2_RED_FLOATS) * 4;
+
+__device__ inline void ck2_issue(const ChunkCursor& c, const ClusterOp* ops, int rank, float* stage, uint64_t* bar) {   // one thread
+    const ClusterOp& op = ops[c.oi];
+    const int k0 = c.ch * op.kc;
+    const int nb = (min(op.kc, op.K - k0) + 31) >> 5;
+    sm100::mbar_arrive_expect_tx(bar, (uint32_t)(nb * op.fcp) * 128u);
+    for (int b = 0; b < nb; ++b)
+        sm100::tma_load_2d(stage + b * op.fcp * 32, reinterpret_cast<const CUtensorMap*>(op.tmap), bar, k0 + 32 * b, rank * op.fcp);
+}
+
+template <int R>
+__global__ void __launch_bounds__(CK2_THREADS, 1)
+dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int dbg) {
+    constexpr int RG = (R + 1) / 2;                          // rows of a group's register tile (group 0: RG rows, group 1: R - RG)
+    extern __shared__ __align__(16) unsigned char ck_smem[];
+    __shared__ __align__(8) uint64_t s_full[CK_STAGES];      // weight stage landed (TMA bytes)
+    __shared__ __align__(8) uint64_t s_empty[CK_STAGES];     // both groups are done with the stage
+    __shared__ __align__(8) uint64_t s_act[2][2];            // [group][parity]: a Linear's output rows landed in THIS CTA's arena
+    unsigned char* const base = ck_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(ck_smem) & 1023u)) & 1023u);
+    float* const ring = reinterpret_cast<float*>(base);
+    float* const arena = ring + CK_STAGES * CK_STAGE_FLOATS;
+    float* const red_all = arena + CK_ARENA_FLOATS;
+    ClusterOp* const ops = reinterpret_cast<ClusterOp*>(red_all + CK2_RED_FLOATS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_rank();
+    const int n_clusters = (int)cluster_count_x(), cid = (int)cluster_id_x();
+    const int n_slices = (M + R - 1) / R;
+    const int n_pass = cid < n_slices ? (n_slices - cid + n_clusters - 1) / n_clusters : 0;
+
+    {
+        const int4* src = reinterpret_cast<const int4*>(g_ops);
+        int4* dst = reinterpret_cast<int4*>(ops);
+        for (int i = tid; i < n_ops * (int)(sizeof(ClusterOp) / 16); i += CK2_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int i = 0; i < CK_STAGES; ++i) { sm100::mbar_init(&s_full[i], 1); sm100::mbar_init(&s_empty[i], 2); }
+        for (int i = 0; i < 4; ++i) sm100::mbar_init(&s_act[i >> 1][i & 1], 1);
+        sm100::fence_barrier_init();
+    }
+    td::pdl_sync();
+    __syncthreads();
+    cluster_sync_all();          // the peers' mbarriers are initialised and their shared memory may be written
+
+    if (warp == 2 * CK2_GT / 32) {
+        // ---- weight producer: walks this CTA's chunk stream, at most CK_STAGES chunks ahead of the slower group
+        ChunkCursor pc{0, 0, 0};
+        uint32_t stage = 0, phase = 0;
+        int cur_pass = 0;
+        while (ck_settle(pc, ops, n_ops, n_pass, rank)) {
+            while (cur_pass < pc.pass) { cluster_sync_all(); ++cur_pass; }      // the groups meet the cluster at every slice boundary
+            if (lane == 0) {
+                sm100::mbar_wait(&s_empty[stage], phase ^ 1u);
+                ck2_issue(pc, ops, rank, ring + stage * CK_STAGE_FLOATS, &s_full[stage]);
+            }
+            __syncwarp();
+            ++pc.ch;
+            if (++stage == CK_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        while (cur_pass < n_pass - 1) { cluster_sync_all(); ++cur_pass; }
+    } else {
+        const int g = warp >> 2, gtid = tid & (CK2_GT - 1), gwarp = warp & 3;
+        const int rbase = g == 0 ? 0 : RG, rcnt = g == 0 ? RG : R - RG;       // this group's rows of the slice
+        float* const red = red_all + g * (CK2_RED_FLOATS / 2);
+        const uint32_t bar_id = 1u + (uint32_t)g;
+        auto gbar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
+        const unsigned long long g_start = dbg ? ck_gtime() : 0ull;
+        long long t_last = dbg ? clock64() : 0, c_wait = 0, c_fma = 0, c_epi = 0, c_bar = 0, c_row = 0, c_e1 = 0, c_e2 = 0, c_pre = 0;
+        constexpr int LN_CACHE = 8;
+        float ln_g[LN_CACHE], ln_b[LN_CACHE];
+        int ln_for = -1;
+#pragma unroll
+        for (int i = 0; i < LN_CACHE; ++i) { ln_g[i] = 0.f; ln_b[i] = 0.f; }
+        uint32_t act_n = 0, c_stage = 0, c_phase = 0;
+        const uint32_t act0 = (uint32_t)__cvta_generic_to_shared(&s_act[g][0]);
+
+#pragma unroll 1
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int row0 = (cid + pass * n_clusters) * R + rbase;          // first global row of this group
+            if (pass > 0) cluster_sync_all();
+            CK_T(c_bar);
+#pragma unroll 1
+            for (int oi = 0; oi < n_ops; ++oi) {
+                const ClusterOp& op = ops[oi];
+                if (op.kind == 0) {
+                    const int fcp = op.fcp, nfg = fcp >> 2, lg_nfg = 31 - __clz(nfg), nks = CK2_GT >> lg_nfg;
+                    const int kstride = RG * fcp + (nfg >= 4 ? nfg : 0);
+                    const int fbase = rank * fcp;
+                    const bool mine = fbase < op.N;
+                    const int er0 = gtid >> lg_nfg, eg = gtid & (nfg - 1), er_step = nks;
+                    const int en = fbase + 4 * eg;
+                    float e_bias[4] = {0.f, 0.f, 0.f, 0.f};
+                    float e_var[4] = {1.f, 1.f, 1.f, 1.f}, e_mean[4] = {0.f, 0.f, 0.f, 0.f}, e_gamma[4] = {1.f, 1.f, 1.f, 1.f}, e_beta[4] = {0.f, 0.f, 0.f, 0.f};
+                    long long e_gi0 = 0;
+                    if (mine && er0 < rcnt) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int n = min(en + j, op.N - 1);
+                            if (op.bias) e_bias[j] = __ldg(op.bias + n);
+                            if (op.bn_mean) {
+                                e_var[j] = __ldg(op.bn_var + n);
+                                e_mean[j] = __ldg(op.bn_mean + n);
+                                e_gamma[j] = __ldg(op.bn_gamma + n);
+                                e_beta[j] = __ldg(op.bn_beta + n);
+                            }
+                        }
+                        if (op.gidx) e_gi0 = __ldg(op.gidx + min(row0 + er0, M - 1));
+                    }
+                    if (oi + 1 < n_ops && ops[oi + 1].kind == 1 && ops[oi + 1].N <= 32 * LN_CACHE) {
+                        const ClusterOp& ln = ops[oi + 1];
+#pragma unroll
+                        for (int i = 0; i < LN_CACHE; ++i) {
+                            const int n = min(lane + 32 * i, ln.N - 1);
+                            ln_g[i] = __ldg(ln.w + n);
+                            ln_b[i] = __ldg(ln.bias + n);
+                        }
+                        ln_for = oi + 1;
+                    }
+                    CK_T(c_pre);
+                    if (mine) {
+                        if (op.kc > 0) {
+                            const int fg = eg, ks = er0;
+                            float acc[4][RG];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int r = 0; r < RG; ++r) acc[j][r] = 0.f;
+                            const int ldx = op.ldx, K = op.K, kc = op.kc;
+                            // the tile's rows (a short group repeats its last row: the copy is never stored)
+                            const float* xrow[RG];
+#pragma unroll
+                            for (int r = 0; r < RG; ++r) xrow[r] = arena + op.x_off + (rbase + min(r, rcnt - 1)) * ldx;
+#pragma unroll 1
+                            for (int k0 = 0; k0 < K; k0 += kc) {
+                                sm100::mbar_wait(&s_full[c_stage], c_phase);
+                                CK_T(c_wait);
+                                const float* wst = ring + c_stage * CK_STAGE_FLOATS;
+                                const int kq = min(kc, K - k0) >> 2;
+                                auto w_at = [&](int q, int j) -> float4 {   // 16-byte piece c of row rr sits at piece c ^ (rr & 7) of its 128-byte line
+                                    const int rr = (q >> 3) * fcp + fg + nfg * j;
+                                    return *reinterpret_cast<const float4*>(wst + rr * 32 + (((q & 7) ^ (rr & 7)) << 2));
+                                };
+#pragma unroll 2
+                                for (int q = ks; q < kq; q += nks) {
+                                    float4 wv[4], xv[RG];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) wv[j] = w_at(q, j);
+#pragma unroll
+                                    for (int r = 0; r < RG; ++r) xv[r] = *reinterpret_cast<const float4*>(xrow[r] + k0 + 4 * q);
+#pragma unroll
+                                    for (int r = 0; r < RG; ++r) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].x, wv[j].x, acc[j][r]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].y, wv[j].y, acc[j][r]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].z, wv[j].z, acc[j][r]);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) acc[j][r] = fmaf(xv[r].w, wv[j].w, acc[j][r]);
+                                    }
+                                }
+                                gbar();                                          // the whole group is done with the stage
+                                if (gtid == 0) sm100::mbar_arrive(&s_empty[c_stage]);
+                                if (++c_stage == CK_STAGES) { c_stage = 0; c_phase ^= 1u; }
+                                CK_T(c_fma);
+                            }
+                            float* rk = red + ks * kstride + fg;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int r = 0; r < RG; ++r) rk[r * fcp + nfg * j] = acc[j][r];
+                        } else {
+                            for (int e = gtid; e < rcnt * fcp; e += CK2_GT) {
+                                const int r = e / fcp, fr = e - r * fcp;
+                                const int n = min(fbase + fr, op.N - 1);
+                                const float* wr = op.w + (long long)n * op.K;
+                                const float* xr = arena + op.x_off + (rbase + r) * op.ldx;
+                                float v = 0.f;
+                                for (int k = 0; k < op.K; ++k) v = fmaf(xr[k], __ldg(wr + k), v);
+                                red[r * fcp + fr] = v;
+                            }
+                        }
+                    }
+                    uint64_t* const my_act = &s_act[g][act_n & 1u];
+                    const uint32_t act_parity = (act_n >> 1) & 1u;
+                    if (!op.out_global && gtid == 0)
+                        sm100::mbar_arrive_expect_tx(my_act, (uint32_t)(rcnt * (op.N - (mine ? min(fcp, op.N - fbase) : 0))) * 4u);
+                    gbar();
+                    CK_T(c_e1);
+                    if (mine) {
+                        const int nsl = op.kc > 0 ? nks : 1;
+                        const uint32_t bar_local = act0 + 8u * (act_n & 1u);
+#pragma unroll 1
+                        for (int er = er0; er < rcnt; er += er_step) {
+                            const int em = row0 + er;
+                            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float* rp = red + er * fcp + 4 * eg;
+#pragma unroll 8
+                            for (int q = 0; q < nsl; ++q) {
+                                const float4 p = *reinterpret_cast<const float4*>(rp + q * kstride);
+                                s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+                            }
+                            float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float t = v[j] + e_bias[j];
+                                if (op.bn_mean) {
+                                    t = (t - e_mean[j]) * (1.f / sqrtf(e_var[j] + op.bn_eps)) * e_gamma[j] + e_beta[j];
+                                    if (op.bn_relu) t = fmaxf(t, 0.f);
+                                }
+                                v[j] = t;
+                            }
+                            if (op.act != TD_ACT_NONE) {
+                                const float4 a = ck_act4(make_float4(v[0], v[1], v[2], v[3]), op.act);
+                                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                            }
+                            if (op.res_off >= 0) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] += arena[op.res_off + (rbase + er) * op.ldr + min(en + j, op.N - 1)];
+                            }
+                            if (op.gidx) {
+                                const long long gi = er == er0 ? e_gi0 : __ldg(op.gidx + min(em, M - 1));
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) v[j] += __ldg(op.gtab + gi * op.ldt + min(en + j, op.N - 1));
+                            }
+                            if (er == er0) CK_T(c_e2);
+                            if (op.out_global) {
+                                if (em < M)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (en + j < op.N) op.gout[(long long)em * op.gldo + en + j] = v[j];
+                            } else {
+                                const int o = op.out_off + (rbase + er) * op.ldo + en;
+                                const uint32_t local = (uint32_t)__cvta_generic_to_shared(arena + o);
+                                const bool vec = en + 3 < op.N && (o & 3) == 0;
+                                if (vec) {
+                                    *reinterpret_cast<float4*>(arena + o) = make_float4(v[0], v[1], v[2], v[3]);
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        if (en + j < op.N) arena[o + j] = v[j];
+                                }
+#pragma unroll
+                                for (int d = 1; d < CK_CL; ++d) {
+                                    const uint32_t peer = (uint32_t)((rank + d) & (CK_CL - 1));
+                                    const uint32_t dst = map_to_rank(local, peer), dbar = map_to_rank(bar_local, peer);
+                                    if (vec) {
+                                        st_async_v4(dst, make_float4(v[0], v[1], v[2], v[3]), dbar);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            if (en + j < op.N) st_async_f32(dst + 4u * j, v[j], dbar);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    CK_T(c_epi);
+                    if (!op.out_global) {
+                        sm100::mbar_wait(my_act, act_parity);          // this group's rows of the op have landed (complete_tx by the peers' st.async)
+                        ++act_n;
+                    }
+                    gbar();                                            // `red`, and the own tile stored above, are settled for the group
+                    CK_T(c_bar);
+                    continue;
+                }
+                if (op.kind == 1) {
+                    if (op.N <= 32 * LN_CACHE) {
+                        if (ln_for != oi) {
+#pragma unroll
+                            for (int i = 0; i < LN_CACHE; ++i) {
+                                const int n = min(lane + 32 * i, op.N - 1);
+                                ln_g[i] = __ldg(op.w + n);
+                                ln_b[i] = __ldg(op.bias + n);
+                            }
+                        }
+#pragma unroll 1
+                        for (int r = gwarp; r < rcnt; r += CK2_GT / 32) {
+                            const float* xr = arena + op.x_off + (rbase + r) * op.ldx;
+                            float* orow = arena + op.out_off + (rbase + r) * op.ldo;
+                            float xv[LN_CACHE];
+#pragma unroll
+                            for (int i = 0; i < LN_CACHE; ++i) xv[i] = lane + 32 * i < op.N ? xr[lane + 32 * i] : 0.f;
+                            float s = 0.f;
+#pragma unroll
+                            for (int i = 0; i < LN_CACHE; ++i) if (lane + 32 * i < op.N) s += xv[i];
+                            const float mean = warp_sum(s) / (float)op.N;
+                            float q = 0.f;
+#pragma unroll
+                            for (int i = 0; i < LN_CACHE; ++i)
+                                if (lane + 32 * i < op.N) { const float d = xv[i] - mean; q = fmaf(d, d, q); }
+                            const float rstd = 1.f / sqrtf(warp_sum(q) / (float)op.N + op.ln_eps);
+#pragma unroll
+                            for (int i = 0; i < LN_CACHE; ++i)
+                                if (lane + 32 * i < op.N) orow[lane + 32 * i] = (xv[i] - mean) * rstd * ln_g[i] + ln_b[i];
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int r = gwarp; r < rcnt; r += CK2_GT / 32) {
+                            const float* xr = arena + op.x_off + (rbase + r) * op.ldx;
+                            float* orow = arena + op.out_off + (rbase + r) * op.ldo;
+                            float s = 0.f;
+                            for (int n = lane; n < op.N; n += 32) s += xr[n];
+                            const float mean = warp_sum(s) / (float)op.N;
+                            float q = 0.f;
+                            for (int n = lane; n < op.N; n += 32) { const float d = xr[n] - mean; q = fmaf(d, d, q); }
+                            const float rstd = 1.f / sqrtf(warp_sum(q) / (float)op.N + op.ln_eps);
+                            for (int n = lane; n < op.N; n += 32) orow[n] = (xr[n] - mean) * rstd * __ldg(op.w + n) + __ldg(op.bias + n);
+                        }
+                    }
+                } else if (op.kind == 2) {
+                    for (int e = gtid; e < rcnt * op.N; e += CK2_GT) {
+                        const int r = e / op.N, n = e - r * op.N;
+                        const float v = arena[op.x_off + (rbase + r) * op.ldx + n];
+                        float* o = arena + op.out_off + (rbase + r) * op.ldo + n;
+                        *o = op.accumulate ? *o + v : v;
+                    }
+                } else if (op.kind == 3) {
+                    const int width = op.tmode == 2 ? op.N : 1;
+                    for (int e = gtid; e < rcnt * width; e += CK2_GT) {
+                        const int r = e / width, j = e - r * width;
+                        const int m = min(row0 + r, M - 1);
+                        float tv = op.t ? (float)op.t[m] : (float)op.t_dev[0];
+                        if (op.tmode == 1) tv = tv / 1000.0f;
+                        float v = tv;
+                        if (op.tmode == 2) {
+                            const int half = op.N / 2;
+                            v = 0.f;
+                            if (j < 2 * half) {
+                                const int jj = (j < half) ? j : j - half;
+                                const float arg = tv * expf(-logf(10000.0f) * (float)jj / (float)(half - 1));
+                                v = (j < half) ? sinf(arg) : cosf(arg);
+                            }
+                        }
+                        arena[op.out_off + (rbase + r) * op.ldo + j] = v;
+                    }
+                } else {
+                    for (int e = gtid; e < rcnt * op.N; e += CK2_GT) {
+                        const int r = e / op.N, n = e - r * op.N;
+                        const int m = row0 + r;
+                        arena[op.out_off + (rbase + r) * op.ldo + n] = m < M ? __ldcg(op.gx + (long long)m * op.gldx + n) : 0.f;
+                    }
+                }
+                gbar();
+                CK_T(c_row);
+            }
+        }
+        if (dbg && gtid == 0 && g == 0 && blockIdx.x < kNumSMs) {
+            unsigned long long* d = g_ck_dbg + blockIdx.x * 16;
+            d[0] = g_start; d[1] = ck_gtime();
+            d[2] = c_wait; d[3] = c_fma; d[4] = c_epi; d[5] = c_bar; d[6] = c_row; d[7] = c_pre; d[8] = c_e1; d[9] = c_e2;
+        }
+    }
+    cluster_sync_all();          // no CTA leaves while a peer may still write into its shared memory
+}
+
 }  // namespace td
 
 using namespace td;
@@ -589,11 +956,19 @@ extern "C" int td_dense_cluster_weight_map(const float* w, int n, int k, int fcp
     return TD_OK;
 }
 
+// 2 (default): two independent row groups + producer warp per CTA (dense_cluster2_kernel); 1: one group (dense_cluster_kernel)
+static int ck_groups() {
+    static int g = 0;
+    if (!g) { const char* e = getenv("TD_DENSE_CLUSTER_GROUPS"); g = (e && atoi(e) == 1) ? 1 : 2; }
+    return g;
+}
+
 template <int R>
 static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         TD_CUDA(cudaFuncSetAttribute(dense_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM));
+        TD_CUDA(cudaFuncSetAttribute(dense_cluster2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK2_SMEM));
         configured = true;
     }
     int clusters = std::min((int)ceil_div(batch, R), ck_max_active_clusters());
@@ -609,7 +984,13 @@ static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cu
         dbg &= ~2;
     }
     count_launch();
-    (void)cudaLaunchKernelEx(&cfg, dense_cluster_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+    if (ck_groups() == 2) {
+        cfg.blockDim = dim3(CK2_THREADS);
+        cfg.dynamicSmemBytes = CK2_SMEM;
+        (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+    } else {
+        (void)cudaLaunchKernelEx(&cfg, dense_cluster_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+    }
     return launch_status("dense_cluster");
 }
 
