@@ -90,6 +90,13 @@ int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_s
  * n = elements of ONE half (multiple of 4); z / Philox indexing as td_psample_step over n elements. */
 int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z, int64_t z_step_stride,
                         const float* coef, const int32_t* t_dev, int num_timesteps, const uint64_t* seed_ptr, void* stream);
+/* The same steps with the counter update folded in: the last block of the grid to finish writes t_dev[0] = t - 1 (every block has
+ * read t by then), so a reverse step needs no td_counter_add launch.  ticket: one zero-initialised uint32 (left at zero). */
+int td_psample_step_advance(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef, int32_t* t_dev,
+                            int64_t n, int num_timesteps, const uint64_t* seed_ptr, unsigned int* ticket, void* stream);
+int td_psample_step_cfg_advance(float* x, const float* eps, int64_t n, float guidance, const float* z, int64_t z_step_stride,
+                                const float* coef, int32_t* t_dev, int num_timesteps, const uint64_t* seed_ptr, unsigned int* ticket,
+                                void* stream);
 /* t_dev[0] += delta ; used between captured steps. */
 int td_counter_add(int32_t* t_dev, int32_t delta, void* stream);
 

@@ -240,3 +240,31 @@ def test_psample_out_of_range_step_is_noop_and_odd_noise_rows(dev):
     loop = ReverseLoop(fp, x.to(dev), eps.to(dev), torch.zeros(1, dtype=torch.int32, device=dev), lambda: None, use_graph=False)
     with pytest.raises(ValueError):
         loop.run(z=None, seed=1, steps=11)
+
+
+def test_psample_step_advance_counts_down(dev):
+    """td_psample_step_advance == td_psample_step followed by t_dev -= 1 (the last block of the grid writes the counter), for
+    tensors of one block and of many blocks, across the whole schedule and past its end (no-op steps still count down)."""
+    from tinydiff import _lib as L
+    from tinydiff.process import ForwardProcess
+    lib = L.load()
+    fp = ForwardProcess(num_timesteps=6)
+    tab = fp._tables(dev)
+    for n in (20, 2560, 128 * 784):
+        g = torch.Generator().manual_seed(n)
+        x0 = torch.randn(n, generator=g)
+        eps = torch.randn(8, n, generator=g).to(dev)
+        z = torch.randn(6, n, generator=g).to(dev)
+        xa, xb = x0.to(dev).clone(), x0.to(dev).clone()
+        ta = torch.tensor([5], device=dev, dtype=torch.int32)
+        tb = ta.clone()
+        ticket = torch.zeros(1, device=dev, dtype=torch.int32)
+        for i in range(8):                     # two steps past t = 0
+            L.check(lib.td_psample_step_advance(xa.data_ptr(), eps[i].data_ptr(), z.data_ptr(), n, tab["coef"].data_ptr(), ta.data_ptr(),
+                                                n, 6, None, ticket.data_ptr(), L.stream_ptr()), "td_psample_step_advance")
+            L.check(lib.td_psample_step(xb.data_ptr(), eps[i].data_ptr(), z.data_ptr(), n, tab["coef"].data_ptr(), tb.data_ptr(), n, 6,
+                                        None, L.stream_ptr()), "td_psample_step")
+            L.check(lib.td_counter_add(tb.data_ptr(), -1, L.stream_ptr()), "td_counter_add")
+            assert int(ta.item()) == int(tb.item()) == 4 - i
+            assert int(ticket.item()) == 0
+            assert torch.equal(xa, xb)

@@ -73,6 +73,8 @@ _SIGS = {
     "td_mse_grad": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_float, _P]),
     "td_psample_step": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int, _P, _P]),
     "td_psample_step_cfg": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, C.c_int64, _P, _P, C.c_int, _P, _P]),
+    "td_psample_step_advance": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int, _P, _P, _P]),
+    "td_psample_step_cfg_advance": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, C.c_int64, _P, _P, C.c_int, _P, _P, _P]),
     "td_bn_fold": (C.c_int, [_P, _P, _P, _P, _P, C.c_float, _P, _P, C.c_int, _P]),
     "td_counter_add": (C.c_int, [_P, C.c_int32, _P]),
     "td_adam_multi": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_float, _P, C.c_double,

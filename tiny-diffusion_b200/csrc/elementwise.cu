@@ -125,14 +125,31 @@ mse_grad_kernel(const float* __restrict__ pred, const float* __restrict__ target
     }
 }
 
+// t_dev[0] = t - 1 by the LAST block of the grid to get here (every block has read t by then); `ticket` is a zero-initialised
+// counter the last block resets.  Folds the per-step td_counter_add launch of the reverse loop into the step kernel.
+__device__ inline void step_counter_advance(int32_t* t_dev, int t, unsigned int* ticket) {
+    if (!ticket) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0u;
+            t_dev[0] = t - 1;
+        }
+    }
+}
+
 // x <- c1*(x - c2*eps) + c3*z        (diffusion.py:272-274), separate roundings as in PyTorch.
 __global__ void __launch_bounds__(kEwThreads)
 psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z_base,
-               int64_t z_step_stride, const float* __restrict__ coef, const int32_t* __restrict__ t_dev, int64_t n,
-               int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+               int64_t z_step_stride, const float* __restrict__ coef, int32_t* t_dev, int64_t n,
+               int num_timesteps, const uint64_t* __restrict__ seed_ptr, unsigned int* ticket) {
     td::pdl_sync();
     const int t = t_dev[0];
-    if (t < 0 || t >= num_timesteps) return;          // a graph replayed past t = 0 (or started above T-1) is a no-op
+    if (t < 0 || t >= num_timesteps) {                // a graph replayed past t = 0 (or started above T-1) is a no-op
+        step_counter_advance(t_dev, t, ticket);
+        return;
+    }
     const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
     const float4 c = reinterpret_cast<const float4*>(coef)[t];
     const float c1 = c.x, c2 = c.y, c3 = c.z;
@@ -176,6 +193,7 @@ psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float
             x[i] = __fadd_rn(__fmul_rn(c1, __fsub_rn(x[i], __fmul_rn(c2, eps[i]))), __fmul_rn(c3, zz));
         }
     }
+    step_counter_advance(t_dev, t, ticket);
 }
 
 // Classifier-free-guidance reverse step (extension; the reference has no guidance).  The denoiser ran
@@ -185,10 +203,13 @@ psample_kernel(float* __restrict__ x, const float* __restrict__ eps, const float
 __global__ void __launch_bounds__(kEwThreads)
 psample_cfg_kernel(float* __restrict__ x, const float* __restrict__ eps, int64_t n, float w,
                    const float* __restrict__ z_base, int64_t z_step_stride, const float* __restrict__ coef,
-                   const int32_t* __restrict__ t_dev, int num_timesteps, const uint64_t* __restrict__ seed_ptr) {
+                   int32_t* t_dev, int num_timesteps, const uint64_t* __restrict__ seed_ptr, unsigned int* ticket) {
     td::pdl_sync();
     const int t = t_dev[0];
-    if (t < 0 || t >= num_timesteps) return;
+    if (t < 0 || t >= num_timesteps) {
+        step_counter_advance(t_dev, t, ticket);
+        return;
+    }
     const float* __restrict__ z = z_base ? z_base + (int64_t)t * z_step_stride : nullptr;
     const float4 c = reinterpret_cast<const float4*>(coef)[t];
     const float c1 = c.x, c2 = c.y, c3 = c.z;
@@ -219,6 +240,7 @@ psample_cfg_kernel(float* __restrict__ x, const float* __restrict__ eps, int64_t
         reinterpret_cast<float4*>(x)[i] = ov;
         reinterpret_cast<float4*>(x + n)[i] = ov;
     }
+    step_counter_advance(t_dev, t, ticket);
 }
 
 // Global gradient L2 norm + clip factor (torch.nn.utils.clip_grad_norm_, conditional_diffusion_laion.py:471) over the flat
@@ -422,26 +444,52 @@ extern "C" int td_mse_grad(const float* pred, const float* target, float* grad, 
     return launch_status("mse_grad");
 }
 
-extern "C" int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef,
-                               const int32_t* t_dev, int64_t n, int num_timesteps, const uint64_t* seed_ptr, void* stream) {
+static int psample_step_launch(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef, int32_t* t_dev,
+                               int64_t n, int num_timesteps, const uint64_t* seed_ptr, unsigned int* ticket, void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step: null pointer");
     TD_CHECK_ARG(n > 0 && num_timesteps > 0, "td_psample_step: n and num_timesteps must be positive");
-    td::launch(psample_kernel, td::LaunchCfg(ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream), 
-        x, eps, z, z_step_stride, coef, t_dev, n, num_timesteps, seed_ptr);
+    td::launch(psample_kernel, td::LaunchCfg(ew_grid(std::max<int64_t>(n / 4, 1)), kEwThreads, 0, (cudaStream_t)stream),
+               x, eps, z, z_step_stride, coef, t_dev, n, num_timesteps, seed_ptr, ticket);
     return launch_status("psample_step");
 }
 
-extern "C" int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z,
-                                   int64_t z_step_stride, const float* coef, const int32_t* t_dev, int num_timesteps,
-                                   const uint64_t* seed_ptr, void* stream) {
+extern "C" int td_psample_step(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef,
+                               const int32_t* t_dev, int64_t n, int num_timesteps, const uint64_t* seed_ptr, void* stream) {
+    return psample_step_launch(x, eps, z, z_step_stride, coef, const_cast<int32_t*>(t_dev), n, num_timesteps, seed_ptr, nullptr, stream);
+}
+
+extern "C" int td_psample_step_advance(float* x, const float* eps, const float* z, int64_t z_step_stride, const float* coef,
+                                       int32_t* t_dev, int64_t n, int num_timesteps, const uint64_t* seed_ptr, unsigned int* ticket,
+                                       void* stream) {
+    TD_CHECK_ARG(ticket, "td_psample_step_advance: null ticket");
+    return psample_step_launch(x, eps, z, z_step_stride, coef, t_dev, n, num_timesteps, seed_ptr, ticket, stream);
+}
+
+static int psample_step_cfg_launch(float* x, const float* eps, int64_t n, float guidance, const float* z, int64_t z_step_stride,
+                                   const float* coef, int32_t* t_dev, int num_timesteps, const uint64_t* seed_ptr, unsigned int* ticket,
+                                   void* stream) {
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(x && eps && coef && t_dev, "td_psample_step_cfg: null pointer");
     TD_CHECK_ARG(n > 0 && n % 4 == 0 && num_timesteps > 0, "td_psample_step_cfg: n (elements of one half) must be a positive multiple of 4");
     TD_CHECK_ARG(!z || ((((uintptr_t)z) & 15) == 0 && z_step_stride % 4 == 0), "td_psample_step_cfg: noise table rows must be 16-byte aligned");
     td::launch(psample_cfg_kernel, td::LaunchCfg(ew_grid(n / 4), kEwThreads, 0, (cudaStream_t)stream), x, eps, n, guidance, z,
-               z_step_stride, coef, t_dev, num_timesteps, seed_ptr);
+               z_step_stride, coef, t_dev, num_timesteps, seed_ptr, ticket);
     return launch_status("psample_step_cfg");
+}
+
+extern "C" int td_psample_step_cfg(float* x, const float* eps, int64_t n, float guidance, const float* z,
+                                   int64_t z_step_stride, const float* coef, const int32_t* t_dev, int num_timesteps,
+                                   const uint64_t* seed_ptr, void* stream) {
+    return psample_step_cfg_launch(x, eps, n, guidance, z, z_step_stride, coef, const_cast<int32_t*>(t_dev), num_timesteps, seed_ptr,
+                                   nullptr, stream);
+}
+
+extern "C" int td_psample_step_cfg_advance(float* x, const float* eps, int64_t n, float guidance, const float* z,
+                                           int64_t z_step_stride, const float* coef, int32_t* t_dev, int num_timesteps,
+                                           const uint64_t* seed_ptr, unsigned int* ticket, void* stream) {
+    TD_CHECK_ARG(ticket, "td_psample_step_cfg_advance: null ticket");
+    return psample_step_cfg_launch(x, eps, n, guidance, z, z_step_stride, coef, t_dev, num_timesteps, seed_ptr, ticket, stream);
 }
 
 extern "C" int64_t td_grad_clip_num_partials(int64_t n) { return ew_grid(std::max<int64_t>(n / 4, 1)); }

@@ -78,22 +78,25 @@ class ReverseLoop:
         self.lib = L.load()
         self.tab = process._tables(x.device)
         self.seed = torch.zeros(2, device=x.device, dtype=torch.int64)
+        self.ticket = torch.zeros(1, device=x.device, dtype=torch.int32)      # last-block ticket of the step kernel (t_dev -= 1)
         self._key = None
         self._z_ref = None
         self.launches_per_step = 0
 
     def _step(self, z_ptr, z_stride, seed_ptr):
+        """One reverse step: the denoiser, then the update kernel, whose last block also decrements the step counter."""
         st = L.stream_ptr()
         self.eps_launch()
         if self.guidance is None:
-            L.check(self.lib.td_psample_step(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
-                                             self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
-                                             self.p.num_timesteps, seed_ptr, st), "td_psample_step")
+            L.check(self.lib.td_psample_step_advance(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
+                                                     self.tab["coef"].data_ptr(), self.t_dev.data_ptr(), self.x.numel(),
+                                                     self.p.num_timesteps, seed_ptr, self.ticket.data_ptr(), st),
+                    "td_psample_step_advance")
         else:
-            L.check(self.lib.td_psample_step_cfg(self.x.data_ptr(), self.eps.data_ptr(), self.n, float(self.guidance),
-                                                 z_ptr, z_stride, self.tab["coef"].data_ptr(), self.t_dev.data_ptr(),
-                                                 self.p.num_timesteps, seed_ptr, st), "td_psample_step_cfg")
-        L.check(self.lib.td_counter_add(self.t_dev.data_ptr(), -1, st), "td_counter_add")
+            L.check(self.lib.td_psample_step_cfg_advance(self.x.data_ptr(), self.eps.data_ptr(), self.n, float(self.guidance),
+                                                         z_ptr, z_stride, self.tab["coef"].data_ptr(), self.t_dev.data_ptr(),
+                                                         self.p.num_timesteps, seed_ptr, self.ticket.data_ptr(), st),
+                    "td_psample_step_cfg_advance")
 
     def run(self, z: Optional[torch.Tensor] = None, seed: int = 0, steps: Optional[int] = None) -> None:
         """Run ``steps`` (default all T) reverse steps in place on ``self.x``.
@@ -178,6 +181,7 @@ class SamplerChains:
         dev = chains[0]["x"].device
         self.tab = process._tables(dev)
         self.seeds = [torch.zeros(2, device=dev, dtype=torch.int64) for _ in chains]
+        self.tickets = [torch.zeros(1, device=dev, dtype=torch.int32) for _ in chains]
         self.sizes = [c["x"].numel() for c in chains]
         self.n_total = sum(self.sizes)
         self.side = [None] + [torch.cuda.Stream(device=dev) for _ in chains[1:]]
@@ -191,10 +195,10 @@ class SamplerChains:
         st = L.stream_ptr()
         ch["launch"]()
         zp = None if z_ptr is None else z_ptr + 4 * sum(self.sizes[:c])
-        L.check(self.lib.td_psample_step(ch["x"].data_ptr(), ch["eps"].data_ptr(), zp, z_stride, self.tab["coef"].data_ptr(),
-                                         ch["t_dev"].data_ptr(), self.sizes[c], self.p.num_timesteps,
-                                         self.seeds[c].data_ptr() if use_seed else None, st), "td_psample_step")
-        L.check(self.lib.td_counter_add(ch["t_dev"].data_ptr(), -1, st), "td_counter_add")
+        L.check(self.lib.td_psample_step_advance(ch["x"].data_ptr(), ch["eps"].data_ptr(), zp, z_stride, self.tab["coef"].data_ptr(),
+                                                 ch["t_dev"].data_ptr(), self.sizes[c], self.p.num_timesteps,
+                                                 self.seeds[c].data_ptr() if use_seed else None, self.tickets[c].data_ptr(), st),
+                "td_psample_step_advance")
 
     def _steps_all(self, k: int, z_ptr, z_stride, use_seed: bool):
         """k reverse steps of every chain: chain 0 on the current stream, the others on their side streams (forked here and
