@@ -454,6 +454,13 @@ def conv_roofline(eng, peaks, iters=3, reverse_step_ms=None):
            "conv_share_of_forward": tc_ms / total_ms if total_ms else None,
            "per_layer": per_layer,
            "per_kernel_us": {n: round(acc[n] * 1e3, 2) for n in names}}
+    fused_pool = [n for n in tc if getattr(eng.plans[n].desc, "pool_y", None)
+                  and int(L.load().td_conv3x3_pool_fused(eng.plans[n].handle))]
+    if fused_pool:
+        out["fused_into_conv_launches"] = {
+            "layers": fused_pool,
+            "note": "MaxPool2d(2) of these layers is written by their conv epilogue (no separate pooling launch): their launch time, "
+                    "and so `achieved` / `frac`, includes that work (+2..4 us each, profiles/r02_pool_fuse_sweep.txt)"}
     if reverse_step_ms:
         tfl = tc_flops / (reverse_step_ms * 1e-3) / 1e12
         out["in_loop"] = {"achieved": tfl, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tfl / peaks["bf16_sustained"],
