@@ -518,8 +518,8 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
 // traffic does not grow.
 // ------------------------------------------------------------------------------------------------------------------------------
 constexpr int CK2_GT = 128;                                // threads per group
-constexpr int CK2_THREADS = 2 * CK2_GT + 32;               // + producer warp
-constexpr int CK2_RED_FLOATS = 2 * (128 * 4 * 5 + 128);    // per group: [k-slices][rows <= 5][fcp] + bank-shift pad
+constexpr int CK2_GMAX = 3;                                // groups per CTA: 2 or 3
+constexpr int CK2_RED_FLOATS = 2 * (128 * 4 * 5 + 128);    // all groups: [k-slices][rows of the group][fcp] + bank-shift pad (2 x 5 rows >= 3 x 3 rows)
 constexpr int CK2_SMEM = 1024 + CK_MAX_OPS * (int)sizeof(ClusterOp) + (CK_ARENA_FLOATS + CK_STAGES * CK_STAGE_FLOATS + CK2_RED_FLOATS) * 4;
 
 __device__ inline void ck2_issue(const ChunkCursor& c, const ClusterOp* ops, int rank, float* stage, uint64_t* bar) {   // one thread
@@ -531,14 +531,17 @@ __device__ inline void ck2_issue(const ChunkCursor& c, const ClusterOp* ops, int
         sm100::tma_load_2d(stage + b * op.fcp * 32, reinterpret_cast<const CUtensorMap*>(op.tmap), bar, k0 + 32 * b, rank * op.fcp);
 }
 
-template <int R>
-__global__ void __launch_bounds__(CK2_THREADS, 1)
+template <int R, int G>
+__global__ void __launch_bounds__(G * CK2_GT + 32, 1)
 dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int dbg) {
-    constexpr int RG = (R + 1) / 2;                          // rows of a group's register tile (group 0: RG rows, group 1: R - RG)
+    constexpr int RG = (R + G - 1) / G;                      // rows of a group's register tile (the last group may own fewer)
+    constexpr int CK2_THREADS = G * CK2_GT + 32;             // + producer warp
+    constexpr int RED_G = 128 * (4 * RG + 1);                // floats of one group's k-slice scratch
+    static_assert(G * RED_G <= CK2_RED_FLOATS && G <= CK2_GMAX, "k-slice scratch");
     extern __shared__ __align__(16) unsigned char ck_smem[];
     __shared__ __align__(8) uint64_t s_full[CK_STAGES];      // weight stage landed (TMA bytes)
     __shared__ __align__(8) uint64_t s_empty[CK_STAGES];     // both groups are done with the stage
-    __shared__ __align__(8) uint64_t s_act[2][2];            // [group][parity]: a Linear's output rows landed in THIS CTA's arena
+    __shared__ __align__(8) uint64_t s_act[CK2_GMAX][2];     // [group][parity]: a Linear's output rows landed in THIS CTA's arena
     unsigned char* const base = ck_smem + ((1024u - ((uint32_t)__cvta_generic_to_shared(ck_smem) & 1023u)) & 1023u);
     float* const ring = reinterpret_cast<float*>(base);
     float* const arena = ring + CK_STAGES * CK_STAGE_FLOATS;
@@ -556,15 +559,15 @@ dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int
         for (int i = tid; i < n_ops * (int)(sizeof(ClusterOp) / 16); i += CK2_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        for (int i = 0; i < CK_STAGES; ++i) { sm100::mbar_init(&s_full[i], 1); sm100::mbar_init(&s_empty[i], 2); }
-        for (int i = 0; i < 4; ++i) sm100::mbar_init(&s_act[i >> 1][i & 1], 1);
+        for (int i = 0; i < CK_STAGES; ++i) { sm100::mbar_init(&s_full[i], 1); sm100::mbar_init(&s_empty[i], G); }
+        for (int i = 0; i < 2 * G; ++i) sm100::mbar_init(&s_act[i >> 1][i & 1], 1);
         sm100::fence_barrier_init();
     }
     td::pdl_sync();
     __syncthreads();
     cluster_sync_all();          // the peers' mbarriers are initialised and their shared memory may be written
 
-    if (warp == 2 * CK2_GT / 32) {
+    if (warp == G * CK2_GT / 32) {
         // ---- weight producer: walks this CTA's chunk stream, at most CK_STAGES chunks ahead of the slower group
         ChunkCursor pc{0, 0, 0};
         uint32_t stage = 0, phase = 0;
@@ -582,8 +585,8 @@ dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int
         while (cur_pass < n_pass - 1) { cluster_sync_all(); ++cur_pass; }
     } else {
         const int g = warp >> 2, gtid = tid & (CK2_GT - 1), gwarp = warp & 3;
-        const int rbase = g == 0 ? 0 : RG, rcnt = g == 0 ? RG : R - RG;       // this group's rows of the slice
-        float* const red = red_all + g * (CK2_RED_FLOATS / 2);
+        const int rbase = g * RG, rcnt = min(RG, R - g * RG);                 // this group's rows of the slice
+        float* const red = red_all + g * RED_G;
         const uint32_t bar_id = 1u + (uint32_t)g;
         auto gbar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
         const unsigned long long g_start = dbg ? ck_gtime() : 0ull;
@@ -956,10 +959,10 @@ extern "C" int td_dense_cluster_weight_map(const float* w, int n, int k, int fcp
     return TD_OK;
 }
 
-// 2 (default): two independent row groups + producer warp per CTA (dense_cluster2_kernel); 1: one group (dense_cluster_kernel)
+// 2 (default) / 3: independent row groups + producer warp per CTA (dense_cluster2_kernel); 1: one group (dense_cluster_kernel)
 static int ck_groups() {
     static int g = 0;
-    if (!g) { const char* e = getenv("TD_DENSE_CLUSTER_GROUPS"); g = (e && atoi(e) == 1) ? 1 : 2; }
+    if (!g) { const char* e = getenv("TD_DENSE_CLUSTER_GROUPS"); const int v = e ? atoi(e) : 2; g = (v == 1 || v == 3) ? v : 2; }
     return g;
 }
 
@@ -968,7 +971,8 @@ static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cu
     static bool configured = false;
     if (!configured) {
         TD_CUDA(cudaFuncSetAttribute(dense_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM));
-        TD_CUDA(cudaFuncSetAttribute(dense_cluster2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK2_SMEM));
+        TD_CUDA(cudaFuncSetAttribute(dense_cluster2_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK2_SMEM));
+        TD_CUDA(cudaFuncSetAttribute(dense_cluster2_kernel<R, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK2_SMEM));
         configured = true;
     }
     int clusters = std::min((int)ceil_div(batch, R), ck_max_active_clusters());
@@ -984,10 +988,13 @@ static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cu
         dbg &= ~2;
     }
     count_launch();
-    if (ck_groups() == 2) {
-        cfg.blockDim = dim3(CK2_THREADS);
+    if (ck_groups() >= 2) {
+        cfg.blockDim = dim3(ck_groups() * CK2_GT + 32);
         cfg.dynamicSmemBytes = CK2_SMEM;
-        (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+        if (ck_groups() == 3)
+            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 3>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+        else
+            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 2>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
     } else {
         (void)cudaLaunchKernelEx(&cfg, dense_cluster_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
     }
