@@ -488,6 +488,14 @@ int td_dense_cluster_op_bytes(void);
 int td_dense_cluster_limits(int batch, int* rows, int* cluster, int* arena_floats, int* stage_floats, int* max_ops,
                             int* max_clusters);
 int td_dense_cluster_run(const void* ops, int n_ops, int batch, int rows, int max_clusters, void* stream);
+/* One reverse step of the sampler in ONE launch (multi-group kernel only: td_dense_cluster_step_fused() == 1): the tape -- whose
+ * last op must be the Linear that writes eps [batch][n], n % 4 == 0 -- and, in that Linear's epilogue, the update of
+ * td_psample_step_advance on the sampler state x [batch][n] (the buffer the tape loads): same roundings, noise-table rows and
+ * Philox indexing; the last CTA of the grid to finish writes t_dev[0] = t - 1 (ticket: one zero-initialised uint32). */
+int td_dense_cluster_step_fused(void);
+int td_dense_cluster_step(const void* ops, int n_ops, int batch, int rows, int max_clusters, float* x, const float* coef,
+                          const float* z, int64_t z_step_stride, const uint64_t* seed_ptr, int32_t* t_dev, unsigned int* ticket,
+                          int num_timesteps, void* stream);
 /* 128-byte tensor map (written to HOST memory) of one Linear's fp32 weight [n][k] for the kernel's weight stream: TMA boxes of
  * 32 floats x fcp rows, SWIZZLE_128B.  The caller keeps a 64-byte aligned device copy and points ClusterOp::tmap at it. */
 int td_dense_cluster_weight_map(const float* w, int n, int k, int fcp, void* map_out_host);

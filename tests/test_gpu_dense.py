@@ -156,6 +156,38 @@ def test_cluster_merged_weights_follow_parameter_updates(dev, name):
     assert rel(eps2, FWD[name](sd3, inp["x0"], inp["t"], inp["cond"], None)) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["latent_diffusion", "diffusion_transformer"])
+@pytest.mark.parametrize("n", [37, 128])
+def test_fused_reverse_step_matches_unfused(dev, name, n, monkeypatch):
+    """The reverse-step update folded into the cluster kernel's last epilogue (td_dense_cluster_step: one launch per step) is
+    BIT-identical to the tape followed by td_psample_step_advance -- injected noise table and in-kernel Philox noise, eager and
+    captured -- and leaves the step counter at -1."""
+    from tinydiff import _lib as L
+    from tinydiff.dense import dense_sample
+    mod, model, sd = build(name, dev, **KW[name])
+    T = 12
+    fp = mod.ForwardProcess(num_timesteps=T)
+    g = torch.Generator().manual_seed(n)
+    x_T = torch.randn(n, 20, generator=g)
+    z = torch.randn(T, n, 20, generator=g).to(dev)
+    y = torch.randint(0, 10, (n,), generator=g).to(dev)
+    lib = L.load()
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("TD_DENSE_STEP_FUSED", fused)
+        model._init_engines()
+        for use_graph in (False, True):
+            outs[(fused, "z", use_graph)] = dense_sample(None, model, fp, dev, n, y, x_T=x_T, z=z, use_graph=use_graph)
+            outs[(fused, "seed", use_graph)] = dense_sample(None, model, fp, dev, n, y, x_T=x_T, seed=77, use_graph=use_graph)
+        eng = model.engine(n, dev, training=False)
+        assert int(eng.t_dev.item()) == -1
+        assert eng._reverse_loop.launches_per_step == (1 if fused == "1" else 2)
+    for kind in ("z", "seed"):
+        for use_graph in (False, True):
+            assert torch.equal(outs[("1", kind, use_graph)], outs[("0", kind, use_graph)]), (kind, use_graph)
+    assert not torch.equal(outs[("1", "z", True)], outs[("1", "seed", True)])
+
+
 def test_cluster_kernel_is_default_at_reference_batch(dev):
     """At the reference batch the public forward runs the cluster kernel (one launch), above one pass the tape."""
     from tinydiff import _lib as L

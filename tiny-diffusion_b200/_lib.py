@@ -135,6 +135,8 @@ _SIGS = {
     "td_dense_cluster_limits": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, _P]),
     "td_dense_cluster_run": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_dense_cluster_debug_counters": (C.c_int, [_P, C.c_int]),
+    "td_dense_cluster_step_fused": (C.c_int, []),
+    "td_dense_cluster_step": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, _P]),
     "td_dense_cluster_weight_map": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "td_maxpool2_bwd": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "td_resize_bilinear_bwd": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -517,6 +517,20 @@ dense_cluster_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int 
 // chain per SM the FP32 pipe ran at 30 %.  Two chains interleave on the same SM -- and share every weight stage, so the L2 -> SM
 // traffic does not grow.
 // ------------------------------------------------------------------------------------------------------------------------------
+// Reverse-step update folded into the tape's last Linear (the one that writes eps): x <- c1[t] (x - c2[t] eps) + c3[t] z with
+// the roundings, the noise-table rows and the Philox indexing of psample_kernel (elementwise.cu), and t_dev[0] = t - 1 by the last
+// CTA of the grid to finish.  x == NULL: plain forward.
+struct ClusterStep {
+    float* x;                    // [M][N] the sampler state (the tape's input buffer)
+    const float* coef;           // [T] float4 {c1, c2, c3, -}
+    const float* z;              // noise table [T][M * N] or NULL
+    long long z_step_stride;
+    const unsigned long long* seed;   // {seed, subsequence base} or NULL
+    int* t_dev;
+    unsigned int* ticket;
+    int num_timesteps;
+};
+
 constexpr int CK2_GT = 128;                                // threads per group
 constexpr int CK2_GMAX = 3;                                // groups per CTA: 2 or 3
 constexpr int CK2_RED_FLOATS = 2 * (128 * 4 * 5 + 128);    // all groups: [k-slices][rows of the group][fcp] + bank-shift pad (2 x 5 rows >= 3 x 3 rows)
@@ -533,7 +547,7 @@ __device__ inline void ck2_issue(const ChunkCursor& c, const ClusterOp* ops, int
 
 template <int R, int G>
 __global__ void __launch_bounds__(G * CK2_GT + 32, 1)
-dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int dbg) {
+dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int dbg, const ClusterStep step) {
     constexpr int RG = (R + G - 1) / G;                      // rows of a group's register tile (the last group may own fewer)
     constexpr int CK2_THREADS = G * CK2_GT + 32;             // + producer warp
     constexpr int RED_G = 128 * (4 * RG + 1);                // floats of one group's k-slice scratch
@@ -750,10 +764,38 @@ dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int
                             }
                             if (er == er0) CK_T(c_e2);
                             if (op.out_global) {
-                                if (em < M)
+                                if (em < M) {
 #pragma unroll
                                     for (int j = 0; j < 4; ++j)
                                         if (en + j < op.N) op.gout[(long long)em * op.gldo + en + j] = v[j];
+                                    if (step.x) {
+                                        // the reverse-step update of these (<= 4) elements; N % 4 == 0 (checked on the host), so
+                                        // they are one 16-byte piece of the flat state: piece index i of psample_kernel
+                                        const int t = step.t_dev[0];
+                                        if (t >= 0 && t < step.num_timesteps && en + 3 < op.N) {
+                                            const float4 c = reinterpret_cast<const float4*>(step.coef)[t];
+                                            const long long i4 = ((long long)em * op.N + en) >> 2;
+                                            float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                                            if (t > 0) {
+                                                if (step.z) {
+                                                    const float4 zv = reinterpret_cast<const float4*>(step.z + (long long)t * step.z_step_stride)[i4];
+                                                    zz[0] = zv.x; zz[1] = zv.y; zz[2] = zv.z; zz[3] = zv.w;
+                                                } else if (step.seed) {
+                                                    Philox rng(step.seed[0]);
+                                                    rng.normal4((uint64_t)i4, step.seed[1] + (uint64_t)t, zz);
+                                                }
+                                            }
+                                            float4* xp = reinterpret_cast<float4*>(step.x) + i4;
+                                            const float4 xv = *xp;
+                                            float4 o4;
+                                            o4.x = __fadd_rn(__fmul_rn(c.x, __fsub_rn(xv.x, __fmul_rn(c.y, v[0]))), __fmul_rn(c.z, zz[0]));
+                                            o4.y = __fadd_rn(__fmul_rn(c.x, __fsub_rn(xv.y, __fmul_rn(c.y, v[1]))), __fmul_rn(c.z, zz[1]));
+                                            o4.z = __fadd_rn(__fmul_rn(c.x, __fsub_rn(xv.z, __fmul_rn(c.y, v[2]))), __fmul_rn(c.z, zz[2]));
+                                            o4.w = __fadd_rn(__fmul_rn(c.x, __fsub_rn(xv.w, __fmul_rn(c.y, v[3]))), __fmul_rn(c.z, zz[3]));
+                                            *xp = o4;
+                                        }
+                                    }
+                                }
                             } else {
                                 const int o = op.out_off + (rbase + er) * op.ldo + en;
                                 const uint32_t local = (uint32_t)__cvta_generic_to_shared(arena + o);
@@ -877,6 +919,14 @@ dense_cluster2_kernel(const ClusterOp* __restrict__ g_ops, int n_ops, int M, int
         }
     }
     cluster_sync_all();          // no CTA leaves while a peer may still write into its shared memory
+    if (step.x && tid == 0) {    // every read of t_dev by this CTA is behind it: the last CTA of the grid counts the step down
+        const int t = step.t_dev[0];
+        __threadfence();
+        if (atomicAdd(step.ticket, 1u) == gridDim.x - 1) {
+            *step.ticket = 0u;
+            step.t_dev[0] = t - 1;
+        }
+    }
 }
 
 }  // namespace td
@@ -967,7 +1017,7 @@ static int ck_groups() {
 }
 
 template <int R>
-static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cudaStream_t s) {
+static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cudaStream_t s, const ClusterStep& step) {
     static bool configured = false;
     if (!configured) {
         TD_CUDA(cudaFuncSetAttribute(dense_cluster_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM));
@@ -992,10 +1042,11 @@ static int ck_launch(const void* ops, int n_ops, int batch, int max_clusters, cu
         cfg.blockDim = dim3(ck_groups() * CK2_GT + 32);
         cfg.dynamicSmemBytes = CK2_SMEM;
         if (ck_groups() == 3)
-            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 3>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 3>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg, step);
         else
-            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 2>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
+            (void)cudaLaunchKernelEx(&cfg, dense_cluster2_kernel<R, 2>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg, step);
     } else {
+        if (step.x) { set_error("td_dense_cluster_step: the one-group kernel (TD_DENSE_CLUSTER_GROUPS=1) has no fused reverse step"); return TD_ERR_UNSUPPORTED; }
         (void)cudaLaunchKernelEx(&cfg, dense_cluster_kernel<R>, reinterpret_cast<const ClusterOp*>(ops), n_ops, batch, dbg);
     }
     return launch_status("dense_cluster");
@@ -1005,8 +1056,31 @@ extern "C" int td_dense_cluster_run(const void* ops, int n_ops, int batch, int r
     TD_REQUIRE_ARCH();
     TD_CHECK_ARG(ops && n_ops > 0 && n_ops <= CK_MAX_OPS && batch > 0, "td_dense_cluster_run: bad args");
     TD_CHECK_ARG(rows == 8 || rows == 9, "td_dense_cluster_run: rows per cluster must be 8 or 9 (the tape's arena offsets were laid out for it)");
-    return rows == 9 ? ck_launch<9>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream)
-                     : ck_launch<8>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream);
+    const ClusterStep none{};
+    return rows == 9 ? ck_launch<9>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream, none)
+                     : ck_launch<8>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream, none);
+}
+
+// 1: td_dense_cluster_step is available (the multi-group kernel is the one that runs)
+extern "C" int td_dense_cluster_step_fused(void) { return ck_groups() >= 2 ? 1 : 0; }
+
+// One reverse step of the sampler in ONE launch: the tape (its last op must be the Linear that writes eps [batch][n] to global
+// memory, n % 4 == 0) followed, in that Linear's epilogue, by x <- c1[t] (x - c2[t] eps) + c3[t] z and t_dev[0] -= 1 -- the
+// arithmetic, noise-table layout and Philox indexing of td_psample_step_advance.  x: the sampler state the tape loads [batch][n].
+extern "C" int td_dense_cluster_step(const void* ops, int n_ops, int batch, int rows, int max_clusters, float* x, const float* coef,
+                                     const float* z, int64_t z_step_stride, const uint64_t* seed_ptr, int32_t* t_dev,
+                                     unsigned int* ticket, int num_timesteps, void* stream) {
+    TD_REQUIRE_ARCH();
+    TD_CHECK_ARG(ops && n_ops > 0 && n_ops <= CK_MAX_OPS && batch > 0, "td_dense_cluster_step: bad args");
+    TD_CHECK_ARG(rows == 8 || rows == 9, "td_dense_cluster_step: rows per cluster must be 8 or 9");
+    TD_CHECK_ARG(x && coef && t_dev && ticket && num_timesteps > 0, "td_dense_cluster_step: null pointer");
+    TD_CHECK_ARG((((uintptr_t)x | (uintptr_t)z) & 15) == 0 && z_step_stride % 4 == 0, "td_dense_cluster_step: x and the noise rows must be 16-byte aligned");
+    ClusterStep st{};
+    st.x = x; st.coef = coef; st.z = z; st.z_step_stride = z_step_stride;
+    st.seed = reinterpret_cast<const unsigned long long*>(seed_ptr);
+    st.t_dev = t_dev; st.ticket = ticket; st.num_timesteps = num_timesteps;
+    return rows == 9 ? ck_launch<9>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream, st)
+                     : ck_launch<8>(ops, n_ops, batch, max_clusters, (cudaStream_t)stream, st);
 }
 
 // Tuning aid: the per-CTA counters of the last launch run with TD_DENSE_CLUSTER_DBG=1 (synchronises).

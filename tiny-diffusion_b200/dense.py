@@ -577,6 +577,18 @@ class DenseEngine:
         self._ctape_rows = R
         self._ctape_arena = max(b + R * ld[n] for n, b in base.items())
 
+    def can_fuse_step(self) -> bool:
+        """The sampler's reverse-step update can ride in the cluster kernel's last epilogue (one launch per reverse step)."""
+        return (getattr(self, "_ctapes", None) is not None and os.environ.get("TD_DENSE_STEP_FUSED", "1") != "0"
+                and self.widths["x_in"] % 4 == 0 and bool(self.lib.td_dense_cluster_step_fused()))
+
+    def fused_step(self, z_ptr, z_stride, seed_ptr, coef_ptr, num_timesteps, ticket_ptr) -> None:
+        """eps = model(x_in, t_dev, y) and x_in <- c1 (x_in - c2 eps) + c3 z, t_dev -= 1, in one launch (``td_dense_cluster_step``)."""
+        buf, n = self._ctapes[True]
+        L.check(self.lib.td_dense_cluster_step(buf.data_ptr(), n, self.B, self._ctape_rows, 0, self.x_in.data_ptr(), coef_ptr, z_ptr,
+                                               z_stride, seed_ptr, self.t_dev.data_ptr(), ticket_ptr, num_timesteps, L.stream_ptr()),
+                "td_dense_cluster_step")
+
     def _launch_tape(self, st: int) -> None:
         if self._ctapes is not None:
             buf, n = self._ctapes[bool(self.use_t_dev)]
@@ -907,7 +919,8 @@ def dense_sample(vae, noise_model: DenseNoiseModel, diffusion, device, n_samples
     eng.refresh_weights()
     loop = getattr(eng, "_reverse_loop", None)
     if loop is None or loop.p is not diffusion or loop.use_graph != use_graph:
-        loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch_forward, use_graph=use_graph)
+        loop = ReverseLoop(diffusion, eng.x_in, eng.eps, eng.t_dev, eng.launch_forward, use_graph=use_graph,
+                           fused_step=eng.fused_step if eng.can_fuse_step() else None)
         eng._reverse_loop = loop
     if z is not None:
         z = z.to(device=device, dtype=torch.float32).contiguous()

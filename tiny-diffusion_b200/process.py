@@ -67,12 +67,15 @@ class ReverseLoop:
     STEPS_PER_GRAPH = 20      # reverse steps unrolled into one captured graph (fewer, longer replays)
 
     def __init__(self, process: ForwardProcess, x: torch.Tensor, eps: torch.Tensor, t_dev: torch.Tensor,
-                 eps_launch, use_graph: bool = True, guidance: Optional[float] = None):
+                 eps_launch, use_graph: bool = True, guidance: Optional[float] = None, fused_step=None):
         """``guidance`` (extension, classifier-free guidance): x / eps hold a doubled batch, rows [0, n) conditional and
         rows [n, 2n) null-label; every step combines eps_u + w*(eps_c - eps_u) (td_psample_step_cfg)."""
         self.p, self.x, self.eps, self.t_dev, self.eps_launch = process, x, eps, t_dev, eps_launch
         self.use_graph = use_graph
         self.guidance = guidance
+        # optional: ``fused_step(z_ptr, z_stride, seed_ptr, coef_ptr, T, ticket_ptr)`` runs denoiser + update + counter in ONE launch
+        # (the dense engines' cluster kernel, dense.DenseEngine.fused_step)
+        self.fused_step = fused_step if guidance is None else None
         self.n = x.numel() if guidance is None else x.numel() // 2      # elements the noise stream covers
         self.graphs = {}
         self.lib = L.load()
@@ -86,6 +89,9 @@ class ReverseLoop:
     def _step(self, z_ptr, z_stride, seed_ptr):
         """One reverse step: the denoiser, then the update kernel, whose last block also decrements the step counter."""
         st = L.stream_ptr()
+        if self.fused_step is not None:
+            self.fused_step(z_ptr, z_stride, seed_ptr, self.tab["coef"].data_ptr(), self.p.num_timesteps, self.ticket.data_ptr())
+            return
         self.eps_launch()
         if self.guidance is None:
             L.check(self.lib.td_psample_step_advance(self.x.data_ptr(), self.eps.data_ptr(), z_ptr, z_stride,
