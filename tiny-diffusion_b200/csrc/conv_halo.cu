@@ -598,6 +598,15 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
                     ((bw + 1) / 2) * ((g.bh + 1) / 2) * g.BN <= 32;
     }
     p->h_grid = std::min(p->h_units, sm_budget());
+    {   // The walk's duration is ceil(units / grid) units whatever the grid: take the SMALLEST grid with the same number of rounds
+        // (896 / 512 / 256 units at batch 128 -> 128 CTAs of exactly 7 / 4 / 2 units instead of 148 CTAs of which a handful run the
+        // extra one).  Every CTA then finishes together and the idle SMs' share of the power budget goes into the clock.
+        const char* e = getenv("TD_TC_HALO_BALANCE");
+        if (!e || atoi(e) != 0) {
+            const int rounds = (int)ceil_div(p->h_units, p->h_grid);
+            p->h_grid = (int)ceil_div(p->h_units, rounds);
+        }
+    }
     p->split_k = 1;
     const int box_bytes = g.PW * p->h_rh * g.BN * 128;
     p->h_slot_bytes = (box_bytes + 1023) / 1024 * 1024 + 1024;
