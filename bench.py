@@ -645,17 +645,17 @@ def dit_data_parallel(dev, world, dist, prev_ts):
 
 def other_configs(dev, peaks):
     """BASELINE.json configs 3-5 (DiT, latent MLP, LAION latent UNet) at the reference batch and at the largest point of the
-    SURVEY.md 8d sweep: fused train step (one CUDA graph, 10 timed replays) and graph-captured reverse step (T = 50 here;
-    the 1000-step figure is 20x).  Model FLOPs / time against the sustained bf16 peak (the dense denoisers compute in
+    SURVEY.md 8d sweep: fused train step (one CUDA graph, 10 timed replays) and graph-captured reverse steps through the public
+    `sample()` (the full T = 1000 schedule at batch <= 256, T = 60 at 65536 samples and scaled; whole 20-step graphs either way).  Model FLOPs / time against the sustained bf16 peak (the dense denoisers compute in
     fp32 / tf32; their fraction is quoted against the same bf16 denominator and is latency-bound at the reference batch)."""
     import importlib
     from tinydiff.train import TrainStep
-    T = 50
     res = []
     for cfg_id, name, batches in ((3, "diffusion_transformer", (128, 65536)), (4, "latent_diffusion", (128, 65536)),
                                   (5, "conditional_diffusion_laion", (8, 256))):
         for Bn in batches:
             rec = {"config": cfg_id, "model": name, "batch": Bn}
+            T = 1000 if Bn <= 256 else 60
             try:
                 mod = importlib.import_module(f"tinydiff.{name}")
                 torch.manual_seed(0)

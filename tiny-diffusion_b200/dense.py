@@ -534,6 +534,8 @@ class DenseEngine:
                         fcp *= 2
                     if fcp > 128:
                         return None
+                    if not r["global"] and (CL - 1) * fcp >= N:
+                        return None          # a CTA without features of a pushed op would not be paced by its peers (no cluster barrier)
                     t.fcp = fcp
                     kc = 32 * (STAGE // (fcp * 32))                  # whole boxes per stage
                     t.kc = kc if (K % 4 == 0 and t.w % 16 == 0 and t.x_off % 4 == 0 and kc >= 32) else 0
