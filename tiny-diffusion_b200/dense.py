@@ -54,6 +54,43 @@ FUSED_MAX_BATCH = 1024
 CLUSTER_MAX_BATCH = 256               # the cluster kernel is tried up to here; it declines batches that need a second pass (> 135 rows)                # above this the per-layer GEMM kernels (tcgen05 tf32 at >= 2048) are the better shape
 
 
+def cluster_arena_layout(recs: List[dict], ld: Dict[str, int], rows: int, arena_floats: int) -> Optional[Dict[str, int]]:
+    """Offsets (floats) of the activation buffers in the cluster kernel's per-CTA shared-memory arena, first-fit by liveness.
+
+    ``recs``: the tape in execution order, each ``{"kind", "reads": [Mat], "write": Mat, "global": bool}``; a kind-0 record
+    that is not ``global`` is a Linear whose output is PUSHED into the peers' arenas and ends an *epoch* (the peers only pace
+    each other through those pushes).  While a CTA pushes the output of the Linear that ends epoch e, a slower peer may still be
+    anywhere inside epoch e: in the row-wise ops in front of that Linear or in its own FMA loop.  So a region is reused for
+    an op's output only if its previous owner was last touched in an EARLIER epoch.  ``eps`` (written to global memory) gets no
+    region.  Returns None when the arena is too small."""
+    epoch, e = [], 0
+    for r in recs:
+        epoch.append(e)
+        if r["kind"] == 0 and not r["global"]:
+            e += 1
+    last_use: Dict[str, int] = {}
+    for j, r in enumerate(recs):
+        for m in r["reads"] + [r["write"]]:
+            last_use[m[0]] = j
+    base: Dict[str, int] = {}
+    live: List[Tuple[int, int, str]] = []                    # (offset, size, name)
+    for j, r in enumerate(recs):
+        name = r["write"][0]
+        if name == "eps" or name in base:
+            continue
+        live = [b for b in live if epoch[last_use[b[2]]] >= epoch[j]]
+        size, off = rows * ld[name], 0
+        for b in sorted(live):
+            if off + size <= b[0]:
+                break
+            off = max(off, b[0] + b[1])
+        if off + size > arena_floats:
+            return None
+        base[name] = off
+        live.append((off, size, name))
+    return base
+
+
 class DenseEngine:
     def __init__(self, module: torch.nn.Module, batch: int, device: torch.device, training: bool, in_dim: int,
                  emb_mode: int):
@@ -460,33 +497,10 @@ class DenseEngine:
                 return
         if any(m[0] == "eps" for r in recs for m in r["reads"]) or not recs[-1]["global"]:
             return
-        # epochs: ops between two cluster barriers
-        epoch, e = [], 0
-        for r in recs:
-            epoch.append(e)
-            if r["kind"] == 0 and not r["global"]:
-                e += 1
-        last_use, first_def = {}, {}
-        for j, r in enumerate(recs):
-            for m in r["reads"] + [r["write"]]:
-                last_use[m[0]] = j
-            first_def.setdefault(r["write"][0], j)
         ld = {n: (w + 3) // 4 * 4 for n, w in self.widths.items()}
-        base, live = {}, []                                  # live: (offset, size, name)
-        for j, r in enumerate(recs):
-            name = r["write"][0]
-            if name == "eps" or name in base:
-                continue
-            live = [b for b in live if epoch[last_use[b[2]]] >= epoch[j]]
-            size, off = R * ld[name], 0
-            for b in sorted(live):
-                if off + size <= b[0]:
-                    break
-                off = max(off, b[0] + b[1])
-            if off + size > ARENA:
-                return
-            base[name] = off
-            live.append((off, size, name))
+        base = cluster_arena_layout(recs, ld, R, ARENA)
+        if base is None:
+            return
 
         # one tensor map per streamed weight (TMA boxes of 32 floats x fcp rows), kept on the device beside the tape
         n_lin = sum(1 for r in recs if r["kind"] == 0)
