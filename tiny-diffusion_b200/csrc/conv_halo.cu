@@ -83,7 +83,7 @@ struct Ring {                 // position in a ring of n mbarrier-guarded slots:
     __device__ void advance(uint32_t k) { idx += k; if (idx >= n) { idx -= n; phase ^= 1u; } }
 };
 
-template <int N_TILE>
+template <int N_TILE, int RAW>          // RAW = 1: bf16 output without affine / ReLU / pooling (train mode), see the epilogue
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const HaloParams p) {
@@ -356,7 +356,41 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 // the read-back works from shared memory.
                 uint32_t rr[32];
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * ACC_COLS + j * N_TILE;
+                // bf16 outputs WITHOUT an affine (train mode: the raw conv output; BatchNorm follows as its own kernel): rounding
+                // happens in the thread-per-position layout and the tile holds finished bf16 rows -- 64 bytes per position, 16-byte
+                // piece g of row l at piece g ^ ((l >> 1) & 3): conflict-free for the stores (8 rows per quarter warp) and for the
+                // read-back (2 rows x 4 pieces) -- half the shared-memory traffic of the fp32 tile.  With the folded eval-mode affine
+                // the same layout needs 16 broadcast loads of scale / shift per chunk and thread and measured SLOWER (sampler 424.6
+                // -> 434.2 us per reverse step): eval keeps the fp32 tile and applies the affine after the transpose.
+                const bool raw_bf16 = RAW != 0;            // (the host instantiates RAW = 1 only for bf16 outputs without affine / ReLU / pooling)
                 auto stage = [&](int c0) {            // registers -> tile (+ train-mode statistics of this chunk)
+                    if (raw_bf16) {
+                        if (p.stats) {
+                            float v[32], sq[32];
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                v[i] = valid ? __uint_as_float(rr[i]) : 0.f;
+                                sq[i] = v[i] * v[i];
+                            }
+                            const float cs = warp_column_sums(v, lane);
+                            const float cq = warp_column_sums(sq, lane);
+                            stats_g[(q * 2 + 0) * N_TILE + c0 + lane] = cs;
+                            stats_g[(q * 2 + 1) * N_TILE + c0 + lane] = cq;
+                        }
+                        const uint32_t row_s = tile_s + (uint32_t)lane * 64u, sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(rr[8 * g + 2 * k]), __uint_as_float(rr[8 * g + 2 * k + 1]));
+                                w[k] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            sts128(row_s + (((uint32_t)g ^ sw) << 4), w[0], w[1], w[2], w[3]);
+                        }
+                        __syncwarp();
+                        return;
+                    }
                     // raw accumulators go through the tile; the folded BatchNorm affine and the ReLU are applied after the
                     // transpose, where a lane owns a fixed group of 8 (bf16) / 4 (fp32) channels for all rows: 4 loads of
                     // scale / shift per chunk instead of 16 per thread (they were ~25 % of the epilogue's stall samples)
@@ -393,7 +427,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                     const bool more = c0 + 32 < N_TILE;
                     if (more) tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32), rr);
-                    if (out_bf16) {
+                    if (raw_bf16) {
+                        // finished bf16 rows: lane = (row it * 8 + lane / 4, 16-byte piece lane % 4) -> 64-byte row segments
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int row = it * 8 + (lane >> 2);
+                            const float4 v = lds128(tile_s + (uint32_t)row * 64u + ((((uint32_t)lane & 3u) ^ ((uint32_t)(row >> 1) & 3u)) << 4));
+                            if (row_off[it] >= 0)
+                                *reinterpret_cast<float4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row_off[it] + c0 + (lane & 3) * 8) = v;
+                        }
+                    } else if (out_bf16) {
                         const int col = (lane & 3) * 8;
                         float sc[8], sh[8];
                         *reinterpret_cast<float4*>(sc) = lds128(sc_u + (uint32_t)(c0 + col) * 4u);
@@ -647,15 +690,15 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     return true;
 }
 
-template <int N_TILE>
+template <int N_TILE, int RAW>
 static int launch_halo(const td_conv_plan* p, const HaloParams& prm, cudaStream_t s) {
     static int configured_smem = 0;
     if (p->smem_bytes > configured_smem) {
-        TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         configured_smem = p->smem_bytes;
     }
     const int grid = p->h_grid;
-    td::launch(conv3x3_halo_kernel<N_TILE>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
+    td::launch(conv3x3_halo_kernel<N_TILE, RAW>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
     return launch_status("conv3x3_halo");
 }
 
@@ -681,7 +724,11 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
     prm.pool_ceil = d.pool_ceil;
     prm.Hp = d.pool_ceil ? (d.height + 1) / 2 : d.height / 2;
     prm.Wp = d.pool_ceil ? (d.width + 1) / 2 : d.width / 2;
-    return p->block_n == 128 ? launch_halo<128>(p, prm, s) : launch_halo<64>(p, prm, s);
+    static int raw_ok = -1;
+    if (raw_ok < 0) { const char* e = getenv("TD_TC_HALO_RAW"); raw_ok = (e && atoi(e) == 0) ? 0 : 1; }
+    const bool raw = raw_ok && d.y_dtype == TD_BF16 && !d.scale && !d.shift && !d.relu && !prm.pool_y;
+    if (raw) return p->block_n == 128 ? launch_halo<128, 1>(p, prm, s) : launch_halo<64, 1>(p, prm, s);
+    return p->block_n == 128 ? launch_halo<128, 0>(p, prm, s) : launch_halo<64, 0>(p, prm, s);
 }
 
 }  // namespace td
