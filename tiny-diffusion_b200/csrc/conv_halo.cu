@@ -83,7 +83,10 @@ struct Ring {                 // position in a ring of n mbarrier-guarded slots:
     __device__ void advance(uint32_t k) { idx += k; if (idx >= n) { idx -= n; phase ^= 1u; } }
 };
 
-template <int N_TILE, int RAW>          // RAW = 1: bf16 output without affine / ReLU / pooling (train mode), see the epilogue
+// EPI: epilogue variant.  0: fp32 transpose tile, affine after the transpose (fp32 outputs); 1: bf16 output without affine / ReLU /
+// pooling (train mode): rounded in the 32x32b layout, bf16 tile; 2: bf16 output with the folded affine (eval): 16x256b TMEM loads, a
+// thread owns 4 rows x 8 columns, affine + ReLU + rounding in registers, bf16 tile.
+template <int N_TILE, int EPI>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const HaloParams p) {
@@ -362,8 +365,35 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 // read-back (2 rows x 4 pieces) -- half the shared-memory traffic of the fp32 tile.  With the folded eval-mode affine
                 // the same layout needs 16 broadcast loads of scale / shift per chunk and thread and measured SLOWER (sampler 424.6
                 // -> 434.2 us per reverse step): eval keeps the fp32 tile and applies the affine after the transpose.
-                const bool raw_bf16 = RAW != 0;            // (the host instantiates RAW = 1 only for bf16 outputs without affine / ReLU / pooling)
+                constexpr bool raw_bf16 = EPI == 1, epi16 = EPI == 2;      // (chosen by the host: halo_plan_run)
                 auto stage = [&](int c0) {            // registers -> tile (+ train-mode statistics of this chunk)
+                    if (epi16) {
+                        // rr[16h + 4j + 2u + w] = (row 16h + 8u + lane/4, column 8j + 2(lane%4) + w): eight columns per thread, so scale /
+                        // shift are 16 registers (eight 8-byte shared-memory reads); the rounded pair (w = 0, 1) is one 4-byte store into
+                        // the bf16 tile of the raw path (piece j of row r at piece j ^ ((r >> 1) & 3): 8 rows x 4 words per store
+                        // instruction hit 32 distinct banks)
+                        float2 sc2[4], sh2[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            sc2[jj] = lds64(sc_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
+                            sh2[jj] = lds64(sh_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
+                        }
+#pragma unroll
+                        for (int hu = 0; hu < 4; ++hu) {
+                            const uint32_t row = (uint32_t)(8 * hu + (lane >> 2));        // 16h + 8u = 8 * (2h + u)
+                            const uint32_t row_s = tile_s + row * 64u + (uint32_t)(lane & 3) * 4u, sw = (row >> 1) & 3u;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float a = fmaf(__uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 0]), sc2[jj].x, sh2[jj].x);
+                                float b = fmaf(__uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 1]), sc2[jj].y, sh2[jj].y);
+                                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+                                sts32(row_s + (((uint32_t)jj ^ sw) << 4), *reinterpret_cast<const uint32_t*>(&h2));
+                            }
+                        }
+                        __syncwarp();
+                        return;
+                    }
                     if (raw_bf16) {
                         if (p.stats) {
                             float v[32], sq[32];
@@ -420,14 +450,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 const int p_n = tn * p.BN + pp_n, p_ph = (p_h0 >> 1) + pp_h, p_pw = (p_w0 >> 1) + pp_w;
                 const bool p_store = pp_on && j < cnt && p_n < p.B && p_ph < p.Hp && p_pw < p.Wp;
                 const uint32_t gtile_s = smem_u32(s_tile + grp * (4 * 32 * 36));
-                tmem_ld_32x32(t_addr, rr);
+                if (epi16) tmem_ld_16x256_pair(t_addr, rr);
+                else tmem_ld_32x32(t_addr, rr);
                 tmem_ld_wait();
                 stage(0);
 #pragma unroll 1
                 for (int c0 = 0; c0 < N_TILE; c0 += 32) {
                     const bool more = c0 + 32 < N_TILE;
-                    if (more) tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32), rr);
-                    if (raw_bf16) {
+                    if (more) {
+                        if (epi16) tmem_ld_16x256_pair(t_addr + (uint32_t)(c0 + 32), rr);
+                        else tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32), rr);
+                    }
+                    if (raw_bf16 || epi16) {
                         // finished bf16 rows: lane = (row it * 8 + lane / 4, 16-byte piece lane % 4) -> 64-byte row segments
 #pragma unroll
                         for (int it = 0; it < 4; ++it) {
@@ -482,7 +516,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             for (int e = 0; e < 4; ++e) {
                                 const int hh = p_h0 + 2 * pp_h + (e >> 1), ww = p_w0 + 2 * pp_w + (e & 1);
                                 if (pp_r[e] < 0 || hh >= p.H || ww >= p.W) continue;
-                                const float4 a = lds128(gtile_s + (uint32_t)(pp_r[e] * 36) * 4u + (uint32_t)(tid & 3) * 16u);
+                                const uint32_t pr = (uint32_t)pp_r[e];      // warp slot pr >> 5, row pr & 31 of that warp's tile
+                                const float4 a = epi16 ? lds128(gtile_s + (pr >> 5) * (32u * 36u * 4u) + (pr & 31u) * 64u +
+                                                                ((((uint32_t)tid & 3u) ^ ((pr >> 1) & 3u)) << 4))
+                                                       : lds128(gtile_s + (uint32_t)(pp_r[e] * 36) * 4u + (uint32_t)(tid & 3) * 16u);
                                 const uint32_t v[4] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
@@ -690,15 +727,15 @@ bool halo_plan_init(td_conv_plan* p, int* status) {
     return true;
 }
 
-template <int N_TILE, int RAW>
+template <int N_TILE, int EPI>
 static int launch_halo(const td_conv_plan* p, const HaloParams& prm, cudaStream_t s) {
     static int configured_smem = 0;
     if (p->smem_bytes > configured_smem) {
-        TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
+        TD_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<N_TILE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_bytes));
         configured_smem = p->smem_bytes;
     }
     const int grid = p->h_grid;
-    td::launch(conv3x3_halo_kernel<N_TILE, RAW>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
+    td::launch(conv3x3_halo_kernel<N_TILE, EPI>, td::LaunchCfg(grid, HALO_THREADS, p->smem_bytes, s), p->tmap_x, p->tmap_w, prm);
     return launch_status("conv3x3_halo");
 }
 
@@ -724,10 +761,13 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
     prm.pool_ceil = d.pool_ceil;
     prm.Hp = d.pool_ceil ? (d.height + 1) / 2 : d.height / 2;
     prm.Wp = d.pool_ceil ? (d.width + 1) / 2 : d.width / 2;
-    static int raw_ok = -1;
+    static int raw_ok = -1, epi16_ok = -1;
     if (raw_ok < 0) { const char* e = getenv("TD_TC_HALO_RAW"); raw_ok = (e && atoi(e) == 0) ? 0 : 1; }
-    const bool raw = raw_ok && d.y_dtype == TD_BF16 && !d.scale && !d.shift && !d.relu && !prm.pool_y;
-    if (raw) return p->block_n == 128 ? launch_halo<128, 1>(p, prm, s) : launch_halo<64, 1>(p, prm, s);
+    if (epi16_ok < 0) { const char* e = getenv("TD_TC_HALO_EPI16"); epi16_ok = (e && atoi(e) == 0) ? 0 : 1; }
+    const bool plain = !d.scale && !d.shift && !d.relu && !prm.pool_y;
+    if (raw_ok && d.y_dtype == TD_BF16 && plain) return p->block_n == 128 ? launch_halo<128, 1>(p, prm, s) : launch_halo<64, 1>(p, prm, s);
+    if (epi16_ok && d.y_dtype == TD_BF16 && !plain && !d.stats)
+        return p->block_n == 128 ? launch_halo<128, 2>(p, prm, s) : launch_halo<64, 2>(p, prm, s);
     return p->block_n == 128 ? launch_halo<128, 0>(p, prm, s) : launch_halo<64, 0>(p, prm, s);
 }
 

@@ -118,6 +118,28 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 32 fp32 columns as two 16x256b.x4 loads (lane offsets 0 and 16): register 16*h + 4*j + 2*u + w of thread l holds
+// (lane 16*h + 8*u + l/4, column 8*j + 2*(l%4) + w) -- tools/probe_tmem_ld_shapes.cu.  A thread owns 4 rows x 8 columns: per-column
+// epilogue operands cost 16 registers instead of 64.
+__device__ __forceinline__ void tmem_ld_16x256_pair(uint32_t taddr, uint32_t* r) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        asm volatile(
+            "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[16 * h + 0]), "=r"(r[16 * h + 1]), "=r"(r[16 * h + 2]), "=r"(r[16 * h + 3]), "=r"(r[16 * h + 4]),
+              "=r"(r[16 * h + 5]), "=r"(r[16 * h + 6]), "=r"(r[16 * h + 7]), "=r"(r[16 * h + 8]), "=r"(r[16 * h + 9]),
+              "=r"(r[16 * h + 10]), "=r"(r[16 * h + 11]), "=r"(r[16 * h + 12]), "=r"(r[16 * h + 13]), "=r"(r[16 * h + 14]),
+              "=r"(r[16 * h + 15])
+            : "r"(taddr + ((uint32_t)(16 * h) << 16))
+            : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory"); }
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+    return v;
+}
 // explicit shared-memory 16-byte accesses (pointers derived from a run-time carve-up of dynamic shared memory lose their
 // address space and compile to generic LD / ST otherwise)
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
