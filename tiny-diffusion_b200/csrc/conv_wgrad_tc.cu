@@ -43,6 +43,7 @@ struct WgParams {
     int slot_bytes;                               // TAPS = 3: bytes of one 64-channel box slot (1 KB front guard + box + zero tail)
     int ksteps;                                   // 16-pixel MMA steps per box
     float* ws;
+    int epi16;                                    // 1 (TD_WG_EPI16=1): direct 8-byte stores from the 16x256b register layout; default: transpose tile
 };
 
 constexpr int WG_TC_THREADS = 192;
@@ -174,45 +175,83 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_m, const __grid_constan
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
         }
+        if (!p.x_on_m && iters > 0 && p.epi16) {
+            // row = cout, columns = cin, straight from the accumulators: tcgen05.ld.16x256b hands thread l the registers
+            // [16h + 4j + 2u + w] = (row 16h + 8u + l/4, column 8j + 2(l%4) + w) (tools/probe_tmem_ld_shapes.cu), so one 8-byte store
+            // per (row, j) and thread makes every warp instruction 8 rows x 32 contiguous bytes = 8 whole sectors.  No transpose
+            // through shared memory, and the next chunk's load is in flight during the stores (the epilogue of this kernel is not
+            // overlapped with anything: it is the drain of every launch).
+            uint32_t r[2][32];
+            const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
+            tmem_ld_16x256_pair(t0, r[0]);
 #pragma unroll 1
-        for (int cc = 0; cc < TAPS * BLOCK_N; cc += 32) {
-            const int t_ = cc / BLOCK_N, c0 = cc - t_ * BLOCK_N;
-            const int tap_ = tap + t_;
-            uint32_t r[32];
-            if (iters > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, r);
+            for (int cc = 0; cc < TAPS * BLOCK_N; cc += 64) {
                 tmem_ld_wait();
-            } else {
+                tmem_ld_16x256_pair(t0 + (uint32_t)(cc + 32), r[1]);          // TAPS * BLOCK_N is a multiple of 64
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
-            }
-            const int nch0 = nt * BLOCK_N + c0;
-            if (p.x_on_m && mch < m_limit) {
-                // row = cin, columns = cout: lanes are consecutive cin -> coalesced per column
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1) {
+                        tmem_ld_wait();
+                        if (cc + 64 < TAPS * BLOCK_N) tmem_ld_16x256_pair(t0 + (uint32_t)(cc + 64), r[0]);
+                    }
+                    const int c = cc + 32 * half;
+                    const int t_ = c / BLOCK_N, c0 = c - t_ * BLOCK_N;
+                    const int nch0 = nt * BLOCK_N + c0;
+                    float* wt = ws + (int64_t)(tap + t_) * p.cin + nch0 + 2 * (lane & 3);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (nch0 + j < p.cout) ws[((int64_t)(nch0 + j) * 9 + tap_) * p.cin + mch] = __uint_as_float(r[j]);
-            }
-            if (!p.x_on_m) {
-                // row = cout, columns = cin.  A thread owns one row, so direct stores would touch 32 cache lines per warp
-                // instruction; the 32 x 32 chunk is transposed through a padded tile in the (idle) operand ring and leaves
-                // as 128-byte row segments, four rows per instruction.
-                float* tile = reinterpret_cast<float*>(smem) + q * (32 * 36);
+                    for (int hu = 0; hu < 4; ++hu) {
+                        const int mrow = mt * 128 + q * 32 + 8 * hu + (lane >> 2);
+                        if (mrow >= m_limit) continue;
+                        float* wr = wt + (int64_t)mrow * 9 * p.cin;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                __syncwarp();
-                const int col = (lane & 7) * 4;
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int rw_ = it * 4 + (lane >> 3);
-                    const int mrow = mt * 128 + q * 32 + rw_;
-                    const float4 a = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col);
-                    if (mrow < m_limit && nch0 + col < p.cin)
-                        *reinterpret_cast<float4*>(ws + ((int64_t)mrow * 9 + tap_) * p.cin + nch0 + col) = a;
+                        for (int j = 0; j < 4; ++j)
+                            if (nch0 + 8 * j + 2 * (lane & 3) < p.cin)
+                                *reinterpret_cast<float2*>(wr + 8 * j) = make_float2(__uint_as_float(r[half][16 * (hu >> 1) + 4 * j + 2 * (hu & 1)]),
+                                                                                    __uint_as_float(r[half][16 * (hu >> 1) + 4 * j + 2 * (hu & 1) + 1]));
+                    }
                 }
-                __syncwarp();
+            }
+        } else {
+#pragma unroll 1
+            for (int cc = 0; cc < TAPS * BLOCK_N; cc += 32) {
+                const int t_ = cc / BLOCK_N, c0 = cc - t_ * BLOCK_N;
+                const int tap_ = tap + t_;
+                uint32_t r[32];
+                if (iters > 0) {
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, r);
+                    tmem_ld_wait();
+                } else {
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                const int nch0 = nt * BLOCK_N + c0;
+                if (p.x_on_m && mch < m_limit) {
+                    // row = cin, columns = cout: lanes are consecutive cin -> coalesced per column
+    #pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nch0 + j < p.cout) ws[((int64_t)(nch0 + j) * 9 + tap_) * p.cin + mch] = __uint_as_float(r[j]);
+                }
+                if (!p.x_on_m) {
+                    // row = cout, columns = cin.  A thread owns one row, so direct stores would touch 32 cache lines per warp
+                    // instruction; the 32 x 32 chunk is transposed through a padded tile in the (idle) operand ring and leaves
+                    // as 128-byte row segments, four rows per instruction.
+                    float* tile = reinterpret_cast<float*>(smem) + q * (32 * 36);
+    #pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(tile + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                    __syncwarp();
+                    const int col = (lane & 7) * 4;
+    #pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rw_ = it * 4 + (lane >> 3);
+                        const int mrow = mt * 128 + q * 32 + rw_;
+                        const float4 a = *reinterpret_cast<const float4*>(tile + rw_ * 36 + col);
+                        if (mrow < m_limit && nch0 + col < p.cin)
+                            *reinterpret_cast<float4*>(ws + ((int64_t)mrow * 9 + tap_) * p.cin + nch0 + col) = a;
+                    }
+                    __syncwarp();
+                }
             }
         }
         tc_fence_before();
@@ -413,6 +452,11 @@ int wgrad_tc_plan_run(const td_wgrad_plan* p, cudaStream_t s) {
     prm.m_tiles = p->m_tiles; prm.n_tiles = p->n_tiles; prm.x_on_m = p->x_on_m;
     prm.stages = p->stages; prm.splits = p->splits; prm.boxes_per_split = p->boxes_per_split;
     prm.ws = d.workspace;
+    {
+        static int epi16 = -1;
+        if (epi16 < 0) { const char* e = getenv("TD_WG_EPI16"); epi16 = (e && atoi(e) == 1) ? 1 : 0; }     // opt-in: measured neutral
+        prm.epi16 = epi16;
+    }
     prm.slot_bytes = p->slot_bytes; prm.ksteps = p->ksteps;
     if (p->taps == 3) return p->block_n == 128 ? launch_wg<128, 3>(p, prm, s) : launch_wg<64, 3>(p, prm, s);
     switch (p->block_n) {
