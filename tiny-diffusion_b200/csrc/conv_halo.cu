@@ -85,7 +85,9 @@ struct Ring {                 // position in a ring of n mbarrier-guarded slots:
 
 // EPI: epilogue variant.  0: fp32 transpose tile, affine after the transpose (fp32 outputs); 1: bf16 output without affine / ReLU /
 // pooling (train mode): rounded in the 32x32b layout, bf16 tile; 2: bf16 output with the folded affine (eval): 16x256b TMEM loads, a
-// thread owns 4 rows x 8 columns, affine + ReLU + rounding in registers, bf16 tile.
+// thread owns 4 rows x 8 columns, affine + ReLU + rounding in registers, bf16 tile; 3: variant 1 WITH train-mode statistics in the
+// 16x256b layout: a thread pre-sums its 4 rows per column, a halving butterfly over the 8 row groups finishes the warp's column sums in
+// 14 shuffles (the 32x32b layout needs 62 per chunk, and shuffles share the pipe with shared memory).
 template <int N_TILE, int EPI>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -365,8 +367,41 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 // read-back (2 rows x 4 pieces) -- half the shared-memory traffic of the fp32 tile.  With the folded eval-mode affine
                 // the same layout needs 16 broadcast loads of scale / shift per chunk and thread and measured SLOWER (sampler 424.6
                 // -> 434.2 us per reverse step): eval keeps the fp32 tile and applies the affine after the transpose.
-                constexpr bool raw_bf16 = EPI == 1, epi16 = EPI == 2;      // (chosen by the host: halo_plan_run)
+                constexpr bool raw_bf16 = EPI == 1, epi16 = EPI == 2 || EPI == 3, stats16 = EPI == 3;      // (chosen by the host: halo_plan_run)
                 auto stage = [&](int c0) {            // registers -> tile (+ train-mode statistics of this chunk)
+                    if (stats16) {
+                        // column sums / sums of squares of this warp's 32 positions (invalid positions count as zero)
+                        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+                        float V[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) V[i] = 0.f;
+#pragma unroll
+                        for (int hu = 0; hu < 4; ++hu) {
+                            const bool rv = (vm >> (8 * hu + (lane >> 2))) & 1u;
+#pragma unroll
+                            for (int jw = 0; jw < 8; ++jw) {
+                                const float v = rv ? __uint_as_float(rr[16 * (hu >> 1) + 4 * (jw >> 1) + 2 * (hu & 1) + (jw & 1)]) : 0.f;
+                                V[jw] += v;
+                                V[8 + jw] = fmaf(v, v, V[8 + jw]);
+                            }
+                        }
+                        // halving butterfly over the row groups (lane bits 4, 3, 2): every step a lane keeps one half of its live values
+                        // and sends the other; lane l ends with kind = bit 4 (0 sum, 1 squares) of columns 8(2 b3 + b2) + 2(l%4) + {0, 1}
+#pragma unroll
+                        for (int st = 0; st < 3; ++st) {
+                            const int n = 8 >> st, xo = 16 >> st;
+                            const bool hi = (lane & xo) != 0;
+#pragma unroll
+                            for (int i = 0; i < n; ++i) {
+                                const float send = hi ? V[i] : V[n + i];
+                                const float keep = hi ? V[n + i] : V[i];
+                                V[i] = keep + __shfl_xor_sync(0xffffffffu, send, xo);
+                            }
+                        }
+                        const int kind = (lane >> 4) & 1, col = 8 * (2 * ((lane >> 3) & 1) + ((lane >> 2) & 1)) + 2 * (lane & 3);
+                        stats_g[(q * 2 + kind) * N_TILE + c0 + col] = V[0];
+                        stats_g[(q * 2 + kind) * N_TILE + c0 + col + 1] = V[1];
+                    }
                     if (epi16) {
                         // rr[16h + 4j + 2u + w] = (row 16h + 8u + lane/4, column 8j + 2(lane%4) + w): eight columns per thread, so scale /
                         // shift are 16 registers (eight 8-byte shared-memory reads); the rounded pair (w = 0, 1) is one 4-byte store into
@@ -375,8 +410,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         float2 sc2[4], sh2[4];
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            sc2[jj] = lds64(sc_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
-                            sh2[jj] = lds64(sh_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
+                            sc2[jj] = stats16 ? make_float2(1.f, 1.f) : lds64(sc_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
+                            sh2[jj] = stats16 ? make_float2(0.f, 0.f) : lds64(sh_u + (uint32_t)(c0 + 8 * jj + 2 * (lane & 3)) * 4u);
                         }
 #pragma unroll
                         for (int hu = 0; hu < 4; ++hu) {
@@ -384,9 +419,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             const uint32_t row_s = tile_s + row * 64u + (uint32_t)(lane & 3) * 4u, sw = (row >> 1) & 3u;
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
-                                float a = fmaf(__uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 0]), sc2[jj].x, sh2[jj].x);
-                                float b = fmaf(__uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 1]), sc2[jj].y, sh2[jj].y);
-                                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                float a = __uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 0]);
+                                float b = __uint_as_float(rr[16 * (hu >> 1) + 4 * jj + 2 * (hu & 1) + 1]);
+                                if (!stats16) {
+                                    a = fmaf(a, sc2[jj].x, sh2[jj].x);
+                                    b = fmaf(b, sc2[jj].y, sh2[jj].y);
+                                    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                                }
                                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
                                 sts32(row_s + (((uint32_t)jj ^ sw) << 4), *reinterpret_cast<const uint32_t*>(&h2));
                             }
@@ -765,6 +804,10 @@ int halo_plan_run(const td_conv_plan* p, cudaStream_t s) {
     if (raw_ok < 0) { const char* e = getenv("TD_TC_HALO_RAW"); raw_ok = (e && atoi(e) == 0) ? 0 : 1; }
     if (epi16_ok < 0) { const char* e = getenv("TD_TC_HALO_EPI16"); epi16_ok = (e && atoi(e) == 0) ? 0 : 1; }
     const bool plain = !d.scale && !d.shift && !d.relu && !prm.pool_y;
+    static int stats16_ok = -1;
+    if (stats16_ok < 0) { const char* e = getenv("TD_TC_HALO_STATS16"); stats16_ok = (e && atoi(e) == 0) ? 0 : 1; }
+    if (stats16_ok && raw_ok && d.y_dtype == TD_BF16 && plain && d.stats)
+        return p->block_n == 128 ? launch_halo<128, 3>(p, prm, s) : launch_halo<64, 3>(p, prm, s);
     if (raw_ok && d.y_dtype == TD_BF16 && plain) return p->block_n == 128 ? launch_halo<128, 1>(p, prm, s) : launch_halo<64, 1>(p, prm, s);
     if (epi16_ok && d.y_dtype == TD_BF16 && !plain && !d.stats)
         return p->block_n == 128 ? launch_halo<128, 2>(p, prm, s) : launch_halo<64, 2>(p, prm, s);
